@@ -1,0 +1,251 @@
+"""ctypes binding of the CPU oracle (oracle/liboip_oracle.so) and of the reference-backed
+checkers under oracle/_ref/.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF_CRC = None
+
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+class FrameGeom(C.Structure):
+    _fields_ = [("tile_cols", C.c_int), ("tile_lines", C.c_int)]
+
+
+def build(force: bool = False) -> None:
+    """compile the oracle (and oracle/_ref when /root/reference is present)."""
+    so = os.path.join(_HERE, "liboip_oracle.so")
+    src = os.path.join(_HERE, "oip_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboip_oracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/OpticalImageProcessor"):
+        subprocess.call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboip_oracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.oipo_crc16.restype = C.c_uint16
+        L.oipo_crc16.argtypes = [u8p, C.c_size_t]
+        L.oipo_aos_validate.restype = C.c_int
+        L.oipo_aos_validate.argtypes = [u8p] + [C.POINTER(C.c_uint32)] * 4
+        L.oipo_aos_scan.restype = C.c_int64
+        L.oipo_aos_scan.argtypes = [u8p, C.c_size_t, u64p, C.c_size_t, i64p]
+        L.oipo_imtr_deframe.restype = C.c_int64
+        L.oipo_imtr_deframe.argtypes = [u8p, u64p, C.c_int64, u8p, C.c_size_t, i64p]
+        L.oipo_image_frames.restype = C.c_int64
+        L.oipo_image_frames.argtypes = [u8p, C.c_size_t, C.POINTER(FrameGeom), C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int64, i64p]
+        L.oipo_rrc_u16.restype = None
+        L.oipo_rrc_u16.argtypes = [u16p, C.c_int, C.c_int64, f64p]
+        L.oipo_load_rrc_csv.restype = C.c_int
+        L.oipo_load_rrc_csv.argtypes = [C.c_char_p, C.c_int, f64p]
+        L.oipo_remap_cubic_u16.restype = None
+        L.oipo_remap_cubic_u16.argtypes = [u16p, C.c_int, C.c_int, C.c_int64, u16p, C.c_int, C.c_int, f32p, f32p]
+        L.oipo_cubic_tab.restype = None
+        L.oipo_cubic_tab.argtypes = [f32p]
+        L.oipo_prestitch_shift.restype = C.c_int64
+        L.oipo_prestitch_shift.argtypes = [u16p, C.c_int, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, u16p]
+        L.oipo_stitch_concat_u16.restype = None
+        L.oipo_stitch_concat_u16.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_int, u16p]
+        L.oipo_pan_pipeline.restype = C.c_int64
+        L.oipo_pan_pipeline.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p),
+                                        f64p, f64p, C.c_int, C.c_int, C.c_int, u16p]
+        L.oipo_set_min_process_lines.restype = None
+        L.oipo_set_min_process_lines.argtypes = [C.c_int]
+        L.oipo_band_align.restype = C.c_int64
+        L.oipo_band_align.argtypes = [C.POINTER(C.c_void_p), C.c_int64, C.c_int, f64p, f64p, C.c_int, C.c_int64,
+                                      C.c_int, C.c_int, u16p]
+        L.oipo_stitch_concat_c4.restype = None
+        L.oipo_stitch_concat_c4.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_int,
+                                            C.c_void_p, u16p]
+        L.oipo_unpack_bits.restype = None
+        L.oipo_unpack_bits.argtypes = [u8p, C.c_int, C.c_int, C.c_int64, C.c_int64, u16p]
+        L.oipo_swap16.restype = None
+        L.oipo_swap16.argtypes = [u16p, C.c_int64, u16p]
+        L.oipo_mss_split.restype = None
+        L.oipo_mss_split.argtypes = [u16p, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
+        _LIB = L
+    return _LIB
+
+
+def ref_crc_lib():
+    """the reference's own CRC.h behind a C shim (oracle/_ref/libref_crc.so), or None."""
+    global _REF_CRC
+    if _REF_CRC is None:
+        so = os.path.join(_HERE, "_ref", "libref_crc.so")
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        L.ref_crc16_ccitt_false.restype = C.c_uint16
+        L.ref_crc16_ccitt_false.argtypes = [u8p, C.c_size_t]
+        _REF_CRC = L
+    return _REF_CRC
+
+
+def _ptr_array(arrs):
+    a = (C.c_void_p * len(arrs))()
+    for i, x in enumerate(arrs):
+        a[i] = x.ctypes.data
+    return a
+
+
+# ---------------------------------------------------------------- convenience wrappers
+def crc16(data: np.ndarray) -> int:
+    d = np.ascontiguousarray(data, np.uint8)
+    return int(lib().oipo_crc16(d, d.size))
+
+
+def aos_scan(buf: np.ndarray):
+    buf = np.ascontiguousarray(buf, np.uint8)
+    cap = buf.size // 1024 + 1
+    off = np.zeros(cap, np.uint64)
+    cnt = np.zeros(3, np.int64)
+    n = lib().oipo_aos_scan(buf, buf.size, off, cap, cnt)
+    return off[:n].copy(), cnt
+
+
+def imtr_deframe(buf: np.ndarray, payload_off: np.ndarray):
+    buf = np.ascontiguousarray(buf, np.uint8)
+    payload_off = np.ascontiguousarray(payload_off, np.uint64)
+    cap = (payload_off.size * 880 // 882 + 1) * 866
+    out = np.zeros(cap, np.uint8)
+    st = np.zeros(9, np.int64)
+    n = lib().oipo_imtr_deframe(buf, payload_off, payload_off.size, out, cap, st)
+    if n < 0:
+        raise RuntimeError("oipo_imtr_deframe failed")
+    return out[:n].copy(), st
+
+
+def image_frames(imdt: np.ndarray, tile_cols: int, tile_lines: int):
+    imdt = np.ascontiguousarray(imdt, np.uint8)
+    g = FrameGeom(tile_cols, tile_lines)
+    st = np.zeros(4, np.int64)
+    n = lib().oipo_image_frames(imdt, imdt.size, C.byref(g), None, None, None, 0, st)
+    if n < 0:
+        return n, None, None, None, st
+    W = 8 * tile_cols
+    aux = np.zeros((n, 48 * 4 * tile_lines), np.uint8)
+    pan = np.zeros((n * 4 * tile_lines, W), np.uint16)
+    mss = np.zeros((n * tile_lines, W), np.uint16)
+    n2 = lib().oipo_image_frames(imdt, imdt.size, C.byref(g), aux.ctypes.data, pan.ctypes.data,
+                                 mss.ctypes.data, n, st)
+    assert n2 == n
+    return n, aux, pan, mss, st
+
+
+def rrc(img: np.ndarray, kb: np.ndarray) -> np.ndarray:
+    out = np.ascontiguousarray(img, np.uint16).copy()
+    h, w = out.shape
+    lib().oipo_rrc_u16(out, w, h, np.ascontiguousarray(kb, np.float64).reshape(-1))
+    return out
+
+
+def remap_cubic(src: np.ndarray, mapx: np.ndarray, mapy: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint16)
+    mapx = np.ascontiguousarray(mapx, np.float32)
+    mapy = np.ascontiguousarray(mapy, np.float32)
+    dh, dw = mapx.shape
+    dst = np.zeros((dh, dw), np.uint16)
+    lib().oipo_remap_cubic_u16(src, src.shape[1], src.shape[0], src.shape[1], dst, dw, dh, mapx, mapy)
+    return dst
+
+
+def cubic_tab() -> np.ndarray:
+    t = np.zeros(128, np.float32)
+    lib().oipo_cubic_tab(t)
+    return t.reshape(32, 4)
+
+
+def prestitch_shift(src: np.ndarray, dX: float, dY: float, section_rows=30000, row_guard=32767) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint16)
+    h, w = src.shape
+    dst = np.zeros_like(src)
+    n = lib().oipo_prestitch_shift(src, w, h, dX, dY, section_rows, row_guard, dst)
+    if n != h:
+        raise RuntimeError(f"oipo_prestitch_shift wrote {n} of {h} rows")
+    return dst
+
+
+def stitch_concat(ccds, fold_half: int) -> np.ndarray:
+    ccds = [np.ascontiguousarray(c, np.uint16) for c in ccds]
+    h, w = ccds[0].shape
+    n = len(ccds)
+    out = np.zeros((h, n * w - 2 * (n - 1) * fold_half), np.uint16)
+    lib().oipo_stitch_concat_u16(_ptr_array(ccds), n, w, h, fold_half, out)
+    return out
+
+
+def pan_pipeline(ccds, kbs, dX, dY, fold_half, section_rows=30000, row_guard=32767) -> np.ndarray:
+    ccds = [np.ascontiguousarray(c, np.uint16) for c in ccds]
+    kbs = [np.ascontiguousarray(k, np.float64) for k in kbs]
+    h, w = ccds[0].shape
+    n = len(ccds)
+    out = np.zeros((h, n * w - 2 * (n - 1) * fold_half), np.uint16)
+    rc = lib().oipo_pan_pipeline(_ptr_array(ccds), n, w, h, _ptr_array(kbs),
+                                 np.ascontiguousarray(dX, np.float64), np.ascontiguousarray(dY, np.float64),
+                                 fold_half, section_rows, row_guard, out)
+    if rc != h:
+        raise RuntimeError(f"oipo_pan_pipeline rc={rc}")
+    return out
+
+
+def band_align(planes, cX, cY, lines_per_section=20000, line_offset=0, overlap=520, keep_leading=False,
+               min_process_lines=1500):
+    planes = [np.ascontiguousarray(p, np.uint16) for p in planes]
+    lines, wb = planes[0].shape
+    rows = lines - line_offset - (0 if keep_leading else overlap)
+    out = np.zeros((max(rows, 0), wb, 4), np.uint16)
+    lib().oipo_set_min_process_lines(min_process_lines)
+    n = lib().oipo_band_align(_ptr_array(planes), lines, wb, np.ascontiguousarray(cX, np.float64).reshape(-1),
+                              np.ascontiguousarray(cY, np.float64).reshape(-1), lines_per_section, line_offset,
+                              overlap, int(keep_leading), out)
+    lib().oipo_set_min_process_lines(1500)
+    return n, out
+
+
+def stitch_concat_c4(imgs, fold_half: int, band_map=None) -> np.ndarray:
+    imgs = [np.ascontiguousarray(c, np.uint16) for c in imgs]
+    h, w, _ = imgs[0].shape
+    n = len(imgs)
+    out = np.zeros((h, n * w - 2 * (n - 1) * fold_half, 4), np.uint16)
+    bm = None
+    if band_map is not None:
+        bm = (C.c_int * 4)(*band_map)
+    lib().oipo_stitch_concat_c4(_ptr_array(imgs), n, w, h, fold_half, bm, out.reshape(-1))
+    return out
+
+
+def unpack_bits(raw: np.ndarray, bits: int, w: int, h: int, pitch: int) -> np.ndarray:
+    raw = np.ascontiguousarray(raw, np.uint8)
+    out = np.zeros((h, w), np.uint16)
+    lib().oipo_unpack_bits(raw, bits, w, h, pitch, out)
+    return out
+
+
+def mss_split(mixed: np.ndarray):
+    mixed = np.ascontiguousarray(mixed, np.uint16)
+    lines, w = mixed.shape
+    planes = [np.zeros((lines, w // 4), np.uint16) for _ in range(4)]
+    lib().oipo_mss_split(mixed, lines, w, _ptr_array(planes))
+    return planes
