@@ -1,0 +1,140 @@
+// oip_common.cuh -- shared plumbing of liboip_b200.so (sm_100a only; no CPU fallback).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/oip_b200.h"
+
+struct oip_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int64_t launches = 0;
+    // cached device-side plan buffers (re-uploaded only when the geometry changes)
+    void *d_plan = nullptr;
+    size_t d_plan_cap = 0;
+    std::vector<uint8_t> plan_key;
+    int64_t plan_tiles = 0;
+    void *d_mss_plan = nullptr;
+    size_t d_mss_plan_cap = 0;
+    std::vector<uint8_t> mss_plan_key;
+    int64_t mss_plan_tiles = 0;
+    // scratch for stage 1 (grown on demand)
+    void *d_scratch = nullptr;
+    size_t d_scratch_cap = 0;
+    void *h_pinned = nullptr; // small pinned staging for counters / plans
+    size_t h_pinned_cap = 0;
+    int *d_err = nullptr;     // device-side error flag
+};
+
+namespace oip {
+
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+
+#define OIP_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return oip::fail(OIP_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                           \
+    } while (0)
+
+#define OIP_CHECK_CTX(ctx)                                                     \
+    do {                                                                       \
+        if (!(ctx)) return oip::fail(OIP_E_INVALID, "null context");           \
+        OIP_CUDA(cudaSetDevice((ctx)->device));                                \
+    } while (0)
+
+int ensure_scratch(oip_ctx *ctx, size_t bytes);
+int ensure_pinned(oip_ctx *ctx, size_t bytes);
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk async copy global -> shared (TMA unit, SASS UBLKCP); 16-byte aligned src/dst/size
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ldg_nc_v4(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_na_v4(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t bswap16x2(uint32_t v) { return __byte_perm(v, 0, 0x2301); }
+
+// CRC-16/CCITT-FALSE one byte step (poly 0x1021, MSB first) -- same recurrence as ref CRC.h:806-834
+__device__ __forceinline__ uint32_t crc16_byte(uint32_t crc, uint32_t byte)
+{
+    uint32_t x = ((crc >> 8) ^ byte) & 0xFFu;
+    x ^= x >> 4;
+    return ((crc << 8) ^ (x << 12) ^ (x << 5) ^ x) & 0xFFFFu;
+}
+
+// (uint16_t)(k*s + b) exactly as the reference's x86 build evaluates it (ref imageop.h:134;
+// cvtsi2sd, mulsd, addsd, cvttsd2si(32-bit), low 16 bits).  No FMA contraction.
+__device__ __forceinline__ uint32_t rrc_px(uint32_t s, double k, double b)
+{
+    double v = __dadd_rn(__dmul_rn(k, (double)s), b);
+    int t = (v > -2147483649.0 && v < 2147483648.0) ? __double2int_rz(v) : (int)0x80000000;
+    return (uint32_t)t & 0xFFFFu;
+}
+#endif
+
+} // namespace oip

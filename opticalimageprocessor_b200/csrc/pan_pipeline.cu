@@ -1,0 +1,710 @@
+// pan_pipeline.cu -- fused unpack -> RRC -> sectioned cubic shift -> trimmed concat (PAN strips).
+//
+// One launch covers every CCD of a strip.  Work is cut into tiles of TW output columns x up to TH
+// output rows; a CTA marches down its tile in chunks of RC rows:
+//
+//   TMA-unit bulk copies (cp.async.bulk, SASS UBLKCP) stage the raw source rows of chunk k+1/k+2 in
+//   shared memory while chunk k is processed        -> every source byte is read from HBM once per
+//                                                      column strip (16-column halo = 6.7 %)
+//   "convert": byte swap + fp64 RRC (ref imageop.h:134) of the newly arrived rows into a float ring
+//   "resample": each thread owns one output column, slides a 4x4 register window down the ring and
+//   evaluates OpenCV's bicubic sum in OpenCV's own order  -> u16 store
+//
+// No intermediate (.RRC.RAW, .PRESTT.RAW) ever exists in HBM.  CCDs that are not shifted use
+// COPY tiles: same staging, RRC, straight to their trimmed position in the output raster.
+#include "oip_common.cuh"
+#include "pan_plan.hpp"
+
+namespace oip {
+namespace pan {
+
+constexpr int TW = 240;   // output columns per tile
+constexpr int SWC = 256;  // staged source columns per tile (TW + halo/alignment slack)
+constexpr int RC = 32;    // output rows per chunk
+constexpr int RING = 40;  // float ring rows (>= RC + 3 + 1)
+constexpr int STG = 40;   // raw staging rows per buffer (first chunk needs RC + 4)
+constexpr int NT = 256;   // threads per CTA
+constexpr int TH = 512;   // output rows per tile
+
+enum { KIND_COPY = 0, KIND_REMAP = 1 };
+
+struct Tile {
+    int32_t ccd, kind;
+    int32_t x_begin, x_end; // CCD columns [x_begin,x_end) produced by this tile
+    int32_t out_x;          // output raster column of x_begin
+    int32_t n_rows;
+    int64_t g0;             // first output row (global)
+    int64_t j0;             // section-local row of g0
+    int64_t sec_off;        // global source row of buffer row 0
+    int64_t stale_off;      // global source row of buffer row 0 for rows >= rows_s, -1 none
+    int32_t rows_s, hbuf;
+};
+
+struct SegDev {
+    const uint8_t *base;
+    int64_t row0, n_rows, pitch;
+};
+struct CcdDev {
+    SegDev seg[OIP_MAX_SEG];
+    const double *kb;
+    double dX, dY;
+    const int64_t *tile_off;
+    int32_t fmt, n_seg, tile_cols, tile_lines;
+};
+struct Params {
+    CcdDev ccd[8];
+    const Tile *tiles;
+    uint16_t *out;
+    int64_t out_pitch, out_row0;
+    const float *tab; // 32x4 cubic weights
+    int *err;
+    int32_t w, n_ccd, bulk_ok;
+};
+
+__device__ __forceinline__ int dev_sat_short(int v) { return max(-32768, min(32767, v)); }
+
+// cvRound(float(i + d) * 32): ref stitcher.h:96-97 + OpenCV remap fixed-point conversion
+__device__ __forceinline__ int dev_map_fixed(int64_t i, double d)
+{
+    float m = __double2float_rn(__dadd_rn((double)i, d));
+    return __float2int_rn(__fmul_rn(m, 32.0f));
+}
+__device__ __forceinline__ int dev_tap_base(int64_t i, double d) { return dev_sat_short(dev_map_fixed(i, d) >> 5) - 1; }
+
+__device__ __forceinline__ const uint8_t *row_ptr(const CcdDev &C, int64_t g)
+{
+#pragma unroll
+    for (int s = 0; s < OIP_MAX_SEG; ++s)
+        if (s < C.n_seg && g >= C.seg[s].row0 && g < C.seg[s].row0 + C.seg[s].n_rows)
+            return C.seg[s].base + (g - C.seg[s].row0) * C.seg[s].pitch;
+    return nullptr;
+}
+
+// buffer row t of the section -> global source row, -1 = zero border
+__device__ __forceinline__ int64_t local_to_global(const Tile &T, int64_t t)
+{
+    if (T.kind == KIND_COPY) return t;
+    if (t < 0 || t >= T.hbuf) return -1;
+    if (t < T.rows_s) return T.sec_off + t;
+    return T.stale_off >= 0 ? T.stale_off + t : -1;
+}
+
+// one raw sample for the generic (non-bulk) loader, returned in native byte order
+__device__ __forceinline__ uint32_t load_sample(const CcdDev &C, const uint8_t *row, int64_t g, int c)
+{
+    switch (C.fmt) {
+    case OIP_FMT_LE16: return *reinterpret_cast<const uint16_t *>(row + 2 * (int64_t)c);
+    case OIP_FMT_BE16: {
+        uint32_t v = *reinterpret_cast<const uint16_t *>(row + 2 * (int64_t)c);
+        return ((v & 0xFF) << 8) | (v >> 8);
+    }
+    case OIP_FMT_PACK12: {
+        const uint8_t *p = row + (int64_t)(c >> 1) * 3;
+        return (c & 1) ? (((uint32_t)(p[1] & 0x0F) << 8) | p[2]) : (((uint32_t)p[0] << 4) | (p[1] >> 4));
+    }
+    case OIP_FMT_PACK10: {
+        const uint8_t *p = row + (int64_t)(c >> 2) * 5;
+        int k = c & 3;
+        uint32_t hi = p[k], lo = p[k + 1];
+        return ((hi << (2 + 2 * k)) | (lo >> (6 - 2 * k))) & 0x3FF;
+    }
+    default: { // OIP_FMT_BE16_TILES: row == IMDT base, g = global PAN line (ref aux_separator.h:341-372)
+        int lpf = 4 * C.tile_lines;
+        int64_t f = g / lpf;
+        int rl = (int)(g - f * lpf);
+        int r = rl / C.tile_lines, y = rl - r * C.tile_lines;
+        int cc = c / C.tile_cols, x = c - cc * C.tile_cols;
+        int64_t off = C.tile_off[f * 40 + r * 8 + cc];
+        if (off < 0) return 0;
+        const uint8_t *p = row + off + ((int64_t)y * C.tile_cols + x) * 2;
+        return ((uint32_t)p[0] << 8) | p[1];
+    }
+    }
+}
+
+struct ChunkRows {
+    int64_t t_lo, t_hi;   // source (buffer-local) rows needed by the chunk, inclusive
+    int64_t new_lo;       // first row not yet in the ring
+    int n_new;
+};
+
+__device__ __forceinline__ ChunkRows chunk_rows(const Tile &T, double dY, int k)
+{
+    ChunkRows c;
+    int64_t ja = T.j0 + (int64_t)k * RC;
+    int64_t jb = min(ja + RC, T.j0 + (int64_t)T.n_rows) - 1;
+    if (T.kind == KIND_REMAP) {
+        c.t_lo = dev_tap_base(ja, dY);
+        c.t_hi = (int64_t)dev_tap_base(jb, dY) + 3;
+        if (k == 0) c.new_lo = c.t_lo;
+        else c.new_lo = max(c.t_lo, (int64_t)dev_tap_base(ja - 1, dY) + 4);
+    } else {
+        c.t_lo = ja;
+        c.t_hi = jb;
+        c.new_lo = ja;
+    }
+    c.n_new = (int)(c.t_hi - c.new_lo + 1);
+    if (c.n_new < 0) c.n_new = 0;
+    return c;
+}
+
+// bicubic sum, interior order: ((s0*w0+s1*w1)+s2*w2)+s3*w3 per row, rows added in turn
+__device__ __forceinline__ float row_dot(const float (&v)[4], const float (&w)[4])
+{
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[0], w[0]), __fmul_rn(v[1], w[1])), __fmul_rn(v[2], w[2])),
+                     __fmul_rn(v[3], w[3]));
+}
+__device__ __forceinline__ float cubic_interior(const float (&a)[4], const float (&b)[4], const float (&c)[4],
+                                                const float (&d)[4], const float (&w)[4][4])
+{
+    float s = row_dot(a, w[0]);
+    s = __fadd_rn(s, row_dot(b, w[1]));
+    s = __fadd_rn(s, row_dot(c, w[2]));
+    s = __fadd_rn(s, row_dot(d, w[3]));
+    return s;
+}
+// border order: flat left-to-right accumulation from 0 (out-of-image taps are 0 in the ring)
+__device__ __forceinline__ float row_acc(float s, const float (&v)[4], const float (&w)[4])
+{
+    s = __fadd_rn(s, __fmul_rn(v[0], w[0]));
+    s = __fadd_rn(s, __fmul_rn(v[1], w[1]));
+    s = __fadd_rn(s, __fmul_rn(v[2], w[2]));
+    s = __fadd_rn(s, __fmul_rn(v[3], w[3]));
+    return s;
+}
+__device__ __forceinline__ float cubic_border(const float (&a)[4], const float (&b)[4], const float (&c)[4],
+                                              const float (&d)[4], const float (&w)[4][4])
+{
+    float s = 0.f;
+    s = row_acc(s, a, w[0]);
+    s = row_acc(s, b, w[1]);
+    s = row_acc(s, c, w[2]);
+    s = row_acc(s, d, w[3]);
+    return s;
+}
+__device__ __forceinline__ uint16_t cast_u16(float s)
+{
+    int v = __float2int_rn(s); // cvRound
+    return (uint16_t)max(0, min(65535, v));
+}
+
+__global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Params P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    float *ring = reinterpret_cast<float *>(smem);                                 // RING x SWC f32
+    uint16_t *stg = reinterpret_cast<uint16_t *>(smem + RING * SWC * 4);           // 2 x STG x SWC u16
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ float s_tab[128];
+    __shared__ uint8_t s_rowzero[2][STG];
+    __shared__ int s_sy[RC];
+    __shared__ int s_regular;
+
+    const int tid = threadIdx.x;
+    const Tile T = P.tiles[blockIdx.x];
+    const CcdDev &C = P.ccd[T.ccd];
+    const int w = P.w;
+    const bool remap = T.kind == KIND_REMAP;
+    const bool bulk = P.bulk_ok != 0;
+    const bool swap = bulk && C.fmt == OIP_FMT_BE16;
+    const bool do_rrc = C.kb != nullptr;
+    const double dX = C.dX, dY = C.dY;
+
+    if (tid < 128) s_tab[tid] = P.tab[tid];
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+
+    // source column window of the tile
+    int c_first = remap ? dev_tap_base(T.x_begin, dX) : T.x_begin;
+    const int c_lo = (c_first >= 0 ? c_first : c_first - 7) / 8 * 8; // floor to a multiple of 8
+    const int n_cols = T.x_end - T.x_begin;
+    const int n_chunks = (T.n_rows + RC - 1) / RC;
+    const int64_t t_base = chunk_rows(T, dY, 0).t_lo;
+
+    // convert-phase mapping: thread = (column pair, row parity)
+    const int p = tid & 127, par = tid >> 7;
+    const int c0 = c_lo + 2 * p;
+    const bool v0ok = c0 >= 0 && c0 < w, v1ok = c0 + 1 >= 0 && c0 + 1 < w;
+    double k0 = 1.0, b0 = 0.0, k1 = 1.0, b1 = 0.0;
+    if (do_rrc) {
+        if (v0ok) { k0 = C.kb[2 * c0]; b0 = C.kb[2 * c0 + 1]; }
+        if (v1ok) { k1 = C.kb[2 * c0 + 2]; b1 = C.kb[2 * c0 + 3]; }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ loader
+    auto issue_chunk = [&](int k) {
+        const ChunkRows cr = chunk_rows(T, dY, k);
+        uint16_t *buf = stg + (size_t)(k & 1) * STG * SWC;
+        uint8_t *rz = s_rowzero[k & 1];
+        uint64_t *bar = &bars[k & 1];
+        if (bulk) {
+            if (tid < 32) {
+                const int ca = max(c_lo, 0), cb = min(c_lo + SWC, w);
+                const uint32_t nb = cb > ca ? (uint32_t)(cb - ca) * 2u : 0u;
+                const uint8_t *ptr[2] = {nullptr, nullptr};
+                uint32_t mine = 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    int r = tid + 32 * i;
+                    if (r < cr.n_new) {
+                        int64_t g = local_to_global(T, cr.new_lo + r);
+                        const uint8_t *q = (g >= 0 && nb) ? row_ptr(C, g) : nullptr;
+                        if (g >= 0 && nb && !q) atomicExch(P.err, 1); // host failed to supply a needed row
+                        ptr[i] = q;
+                        rz[r] = q == nullptr;
+                        if (q) mine += nb;
+                    }
+                }
+                uint32_t total = mine;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                if (tid == 0) mbar_arrive_expect_tx(bar, total);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    int r = tid + 32 * i;
+                    if (ptr[i]) bulk_g2s(buf + (size_t)r * SWC + (ca - c_lo), ptr[i] + 2 * (int64_t)ca, nb, bar);
+                }
+            }
+        } else {
+            // generic loader: any alignment / packed / tile layouts; native byte order in staging
+            for (int r = 0; r < cr.n_new; ++r) {
+                int64_t g = local_to_global(T, cr.new_lo + r);
+                const uint8_t *q = nullptr;
+                if (g >= 0) q = C.fmt == OIP_FMT_BE16_TILES ? C.seg[0].base : row_ptr(C, g);
+                if (g >= 0 && !q && tid == 0) atomicExch(P.err, 1);
+                if (tid == 0) rz[r] = q == nullptr;
+                if (q) {
+                    int c = c_lo + tid;
+                    buf[(size_t)r * SWC + tid] = (c >= 0 && c < w) ? (uint16_t)load_sample(C, q, g, c) : (uint16_t)0;
+                }
+            }
+        }
+    };
+
+    issue_chunk(0);
+    if (n_chunks > 1) issue_chunk(1);
+    __syncthreads();
+
+    // resample-phase per-thread column constants
+    int ix = 0, cx = 0;
+    bool col_int = false;
+    float wx[4] = {0.f, 0.f, 0.f, 0.f};
+    if (remap && tid < n_cols) {
+        int sx = dev_map_fixed(T.x_begin + tid, dX);
+        ix = dev_sat_short(sx >> 5) - 1;
+        cx = ix - c_lo;
+        col_int = (unsigned)ix < (unsigned)max(w - 3, 0);
+        const int fx = sx & 31;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wx[i] = s_tab[4 * fx + i];
+    }
+    uint16_t *out_col = P.out + (T.g0 - P.out_row0) * P.out_pitch + T.out_x + tid;
+
+    for (int k = 0; k < n_chunks; ++k) {
+        const ChunkRows cr = chunk_rows(T, dY, k);
+        const int64_t ja = T.j0 + (int64_t)k * RC;
+        const int nr = min(RC, T.n_rows - k * RC);
+        if (bulk) mbar_wait(&bars[k & 1], (uint32_t)((k >> 1) & 1));
+
+        // ---------------------------------------------------------- convert: swap + RRC
+        {
+            const uint32_t *buf32 = reinterpret_cast<const uint32_t *>(stg + (size_t)(k & 1) * STG * SWC);
+            const uint8_t *rz = s_rowzero[k & 1];
+            for (int r = par; r < cr.n_new; r += 2) {
+                const int64_t t = cr.new_lo + r;
+                uint32_t a = 0, b = 0;
+                const bool z = rz[r] != 0;
+                if (!z) {
+                    uint32_t raw = buf32[(size_t)r * (SWC / 2) + p];
+                    if (swap) raw = bswap16x2(raw);
+                    a = raw & 0xFFFFu;
+                    b = raw >> 16;
+                    if (do_rrc) {
+                        a = rrc_px(a, k0, b0);
+                        b = rrc_px(b, k1, b1);
+                    }
+                }
+                if (remap) {
+                    int slot = (int)(t - t_base) % RING;
+                    float2 o;
+                    o.x = (v0ok && !z) ? (float)a : 0.f;
+                    o.y = (v1ok && !z) ? (float)b : 0.f;
+                    reinterpret_cast<float2 *>(ring)[(size_t)slot * (SWC / 2) + p] = o;
+                } else if (!z) {
+                    uint16_t *orow = P.out + (t - P.out_row0) * P.out_pitch + T.out_x;
+                    if (c0 >= T.x_begin && c0 < T.x_end) orow[c0 - T.x_begin] = (uint16_t)a;
+                    if (c0 + 1 >= T.x_begin && c0 + 1 < T.x_end) orow[c0 + 1 - T.x_begin] = (uint16_t)b;
+                } else {
+                    uint16_t *orow = P.out + (t - P.out_row0) * P.out_pitch + T.out_x;
+                    if (c0 >= T.x_begin && c0 < T.x_end) orow[c0 - T.x_begin] = 0;
+                    if (c0 + 1 >= T.x_begin && c0 + 1 < T.x_end) orow[c0 + 1 - T.x_begin] = 0;
+                }
+            }
+            if (remap && tid < 32) {
+                // row map of the chunk + "regular" flag: unit row steps (hence one fy) and every
+                // row in the interior of the section buffer -> sliding-window fast path
+                const int sy = tid < nr ? dev_map_fixed(ja + tid, dY) : 0;
+                const int prev = __shfl_up_sync(0xffffffffu, sy, 1);
+                const bool ok = (tid == 0 || tid >= nr) ? true : (sy - prev == 32);
+                const bool all_ok = __all_sync(0xffffffffu, ok);
+                s_sy[tid] = sy;
+                if (tid == 0) {
+                    const int iy0 = dev_sat_short(sy >> 5) - 1;
+                    s_regular = all_ok && iy0 >= 0 && (iy0 + nr - 1) < T.hbuf - 3;
+                }
+            }
+        }
+        __syncthreads();
+        if (k + 2 < n_chunks) issue_chunk(k + 2);
+
+        // ---------------------------------------------------------- resample
+        if (remap && tid < n_cols) {
+            const int sy0 = s_sy[0];
+            const int iy0 = dev_sat_short(sy0 >> 5) - 1;
+            // regular chunk: unit row steps, one fy, every row interior -> sliding register window
+            if (s_regular) {
+                const int fy = sy0 & 31;
+                float wgt[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) wgt[r][c] = __fmul_rn(s_tab[4 * fy + r], wx[c]);
+                int slot = (int)(iy0 - t_base) % RING;
+                float ra[4], rb[4], rc[4], rd[4];
+                auto load_row = [&](float(&dst)[4]) {
+                    const float *q = ring + (size_t)slot * SWC + cx;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dst[c] = q[c];
+                    slot = slot + 1 == RING ? 0 : slot + 1;
+                };
+                load_row(ra);
+                load_row(rb);
+                load_row(rc);
+                uint16_t *o = out_col + (int64_t)k * RC * P.out_pitch;
+                if (col_int) {
+                    for (int i = 0; i < nr; i += 4) {
+                        load_row(rd);
+                        o[0] = cast_u16(cubic_interior(ra, rb, rc, rd, wgt));
+                        if (i + 1 < nr) { load_row(ra); o[P.out_pitch] = cast_u16(cubic_interior(rb, rc, rd, ra, wgt)); }
+                        if (i + 2 < nr) { load_row(rb); o[2 * P.out_pitch] = cast_u16(cubic_interior(rc, rd, ra, rb, wgt)); }
+                        if (i + 3 < nr) { load_row(rc); o[3 * P.out_pitch] = cast_u16(cubic_interior(rd, ra, rb, rc, wgt)); }
+                        o += 4 * P.out_pitch;
+                    }
+                } else {
+                    for (int i = 0; i < nr; i += 4) {
+                        load_row(rd);
+                        o[0] = cast_u16(cubic_border(ra, rb, rc, rd, wgt));
+                        if (i + 1 < nr) { load_row(ra); o[P.out_pitch] = cast_u16(cubic_border(rb, rc, rd, ra, wgt)); }
+                        if (i + 2 < nr) { load_row(rb); o[2 * P.out_pitch] = cast_u16(cubic_border(rc, rd, ra, rb, wgt)); }
+                        if (i + 3 < nr) { load_row(rc); o[3 * P.out_pitch] = cast_u16(cubic_border(rd, ra, rb, rc, wgt)); }
+                        o += 4 * P.out_pitch;
+                    }
+                }
+            } else {
+                // general path: section edges, map rounding anomalies
+                uint16_t *o = out_col + (int64_t)k * RC * P.out_pitch;
+                for (int i = 0; i < nr; ++i, o += P.out_pitch) {
+                    const int sy = s_sy[i];
+                    const int iy = dev_sat_short(sy >> 5) - 1, fy = sy & 31;
+                    float wgt[4][4], v[4][4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int64_t t = (int64_t)iy + r;
+                        const bool in = t >= cr.t_lo && t <= cr.t_hi; // always true by construction
+                        const int slot = in ? (int)(t - t_base) % RING : 0;
+                        const float *q = ring + (size_t)slot * SWC + cx;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            wgt[r][c] = __fmul_rn(s_tab[4 * fy + r], wx[c]);
+                            v[r][c] = in ? q[c] : 0.f;
+                        }
+                    }
+                    const bool row_int = (unsigned)iy < (unsigned)max(T.hbuf - 3, 0);
+                    float s = (row_int && col_int) ? cubic_interior(v[0], v[1], v[2], v[3], wgt)
+                                                   : cubic_border(v[0], v[1], v[2], v[3], wgt);
+                    *o = cast_u16(s);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+struct PlanKey {
+    int n_ccd, w, fold_half, section_rows, row_guard, shifted[8];
+    int64_t total_rows, row0, n_rows;
+    double dX[8], dY[8];
+};
+
+static int build_tiles(const oip_pan_desc *d, std::vector<Tile> &tiles)
+{
+    const int n = d->n_ccd, w = d->w, f = d->fold_half;
+    int out_x = 0;
+    for (int i = 0; i < n; ++i) {
+        const int lo = i == 0 ? 0 : f, hi = i == n - 1 ? w : w - f;
+        const bool shifted = d->ccd[i].shifted != 0;
+        std::vector<ShiftSegment> segs;
+        if (shifted) {
+            if (!plan_shift_segments(d->total_rows, d->section_rows, d->row_guard, d->ccd[i].dY, segs))
+                return fail(OIP_E_INVALID, "invalid section geometry (section_rows=%d row_guard=%d dY=%g)",
+                            d->section_rows, d->row_guard, d->ccd[i].dY);
+        } else {
+            segs.push_back({0, d->total_rows, 0, 0, 0, -1, 0});
+        }
+        for (const ShiftSegment &s : segs) {
+            int64_t g0 = std::max<int64_t>(s.g0, d->row0), g1 = std::min<int64_t>(s.g1, d->row0 + d->n_rows);
+            for (int64_t g = g0; g < g1; g += TH) {
+                int nr = (int)std::min<int64_t>(TH, g1 - g);
+                for (int x = lo; x < hi; x += TW) {
+                    Tile t{};
+                    t.ccd = i;
+                    t.kind = shifted ? KIND_REMAP : KIND_COPY;
+                    t.x_begin = x;
+                    t.x_end = std::min(hi, x + TW);
+                    t.out_x = out_x + (x - lo);
+                    t.n_rows = nr;
+                    t.g0 = g;
+                    t.j0 = shifted ? s.j0 + (g - s.g0) : g;
+                    t.sec_off = s.sec_off;
+                    t.stale_off = s.stale_off;
+                    t.rows_s = s.rows_s;
+                    t.hbuf = s.hbuf;
+                    tiles.push_back(t);
+                }
+            }
+        }
+        out_x += hi - lo;
+    }
+    return OIP_OK;
+}
+
+static float g_tab_host[128];
+static bool g_tab_ready = false;
+static void cubic_tab_host(float *tab)
+{
+    // OpenCV interpolateCubic, A = -0.75, evaluated in float without contraction (host code of
+    // this file is compiled by the host compiler for baseline x86-64: no FMA instructions)
+    const volatile float A = -0.75f;
+    for (int i = 0; i < 32; ++i) {
+        volatile float x = i * (1.f / 32);
+        volatile float x1 = x + 1;
+        volatile float t0 = A * x1;
+        volatile float t1 = t0 - 5 * A;
+        volatile float t2 = t1 * x1;
+        volatile float t3 = t2 + 8 * A;
+        volatile float t4 = t3 * x1;
+        tab[4 * i + 0] = t4 - 4 * A;
+        volatile float u0 = (A + 2) * x;
+        volatile float u1 = u0 - (A + 3);
+        volatile float u2 = u1 * x;
+        volatile float u3 = u2 * x;
+        tab[4 * i + 1] = u3 + 1;
+        volatile float y = 1 - x;
+        volatile float v0 = (A + 2) * y;
+        volatile float v1 = v0 - (A + 3);
+        volatile float v2 = v1 * y;
+        volatile float v3 = v2 * y;
+        tab[4 * i + 2] = v3 + 1;
+        volatile float s0 = 1.f - tab[4 * i + 0];
+        volatile float s1 = s0 - tab[4 * i + 1];
+        tab[4 * i + 3] = s1 - tab[4 * i + 2];
+    }
+}
+
+static int upload_tab()
+{
+    if (!g_tab_ready) {
+        cubic_tab_host(g_tab_host);
+        g_tab_ready = true;
+    }
+    return OIP_OK;
+}
+
+} // namespace pan
+} // namespace oip
+
+using namespace oip;
+
+extern "C" int oip_pan_out_width(int n_ccd, int w, int fold_half) { return n_ccd * w - 2 * (n_ccd - 1) * fold_half; }
+
+extern "C" void oip_cubic_tab(float *tab128)
+{
+    pan::upload_tab();
+    memcpy(tab128, pan::g_tab_host, sizeof pan::g_tab_host);
+}
+
+static int validate_desc(const oip_pan_desc *d)
+{
+    if (!d) return fail(OIP_E_INVALID, "null descriptor");
+    if (d->n_ccd < 1 || d->n_ccd > 8) return fail(OIP_E_INVALID, "n_ccd=%d out of range 1..8", d->n_ccd);
+    if (d->w < 8 || d->w > 32760) return fail(OIP_E_INVALID, "w=%d out of range", d->w);
+    if (d->fold_half < 0 || 2 * d->fold_half >= d->w) return fail(OIP_E_INVALID, "fold_half=%d invalid for w=%d", d->fold_half, d->w);
+    if (d->total_rows < 0 || d->row0 < 0 || d->n_rows < 0 || d->row0 + d->n_rows > d->total_rows)
+        return fail(OIP_E_INVALID, "row range [%lld,+%lld) outside strip of %lld rows", (long long)d->row0,
+                    (long long)d->n_rows, (long long)d->total_rows);
+    if (d->section_rows > d->row_guard) return fail(OIP_E_INVALID, "section_rows must be <= row_guard");
+    for (int i = 0; i < d->n_ccd; ++i) {
+        const oip_ccd_src &c = d->ccd[i];
+        if (c.fmt < OIP_FMT_LE16 || c.fmt > OIP_FMT_BE16_TILES) return fail(OIP_E_INVALID, "ccd %d: unknown sample format %d", i, c.fmt);
+        if (c.n_seg < 1 || c.n_seg > OIP_MAX_SEG) return fail(OIP_E_INVALID, "ccd %d: n_seg=%d", i, c.n_seg);
+        if (c.fmt == OIP_FMT_BE16_TILES && (!c.d_tile_off || c.tile_cols * 8 != d->w || c.tile_lines < 1))
+            return fail(OIP_E_INVALID, "ccd %d: tile layout needs d_tile_off and 8*tile_cols == w", i);
+        if (c.shifted && !(std::fabs(c.dX) < 16000.0 && std::fabs(c.dY) < 16000.0))
+            return fail(OIP_E_INVALID, "ccd %d: shift (%g,%g) out of range", i, c.dX, c.dY);
+    }
+    return OIP_OK;
+}
+
+extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
+{
+    OIP_CHECK_CTX(ctx);
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    if (!d->d_out && d->n_rows > 0) return fail(OIP_E_INVALID, "d_out is null");
+    if (d->n_rows == 0) return OIP_OK;
+    const int out_w = oip_pan_out_width(d->n_ccd, d->w, d->fold_half);
+    if (d->out_pitch_px < out_w) return fail(OIP_E_INVALID, "out_pitch_px=%lld < out_w=%d", (long long)d->out_pitch_px, out_w);
+
+    // ---- plan (cached on the geometry)
+    pan::PlanKey key{};
+    key.n_ccd = d->n_ccd; key.w = d->w; key.fold_half = d->fold_half; key.section_rows = d->section_rows;
+    key.row_guard = d->row_guard; key.total_rows = d->total_rows; key.row0 = d->row0;
+    key.n_rows = d->n_rows;
+    for (int i = 0; i < d->n_ccd; ++i) { key.dX[i] = d->ccd[i].dX; key.dY[i] = d->ccd[i].dY; key.shifted[i] = d->ccd[i].shifted != 0; }
+    const uint8_t *kb = reinterpret_cast<const uint8_t *>(&key);
+    if (ctx->plan_key.size() != sizeof key || memcmp(ctx->plan_key.data(), kb, sizeof key) != 0) {
+        std::vector<pan::Tile> tiles;
+        rc = pan::build_tiles(d, tiles);
+        if (rc) return rc;
+        pan::upload_tab();
+        size_t bytes = tiles.size() * sizeof(pan::Tile) + 512;
+        if (bytes > ctx->d_plan_cap) {
+            if (ctx->d_plan) { OIP_CUDA(cudaStreamSynchronize(ctx->stream)); OIP_CUDA(cudaFree(ctx->d_plan)); ctx->d_plan = nullptr; }
+            OIP_CUDA(cudaMalloc(&ctx->d_plan, bytes * 2));
+            ctx->d_plan_cap = bytes * 2;
+        }
+        rc = ensure_pinned(ctx, bytes);
+        if (rc) return rc;
+        OIP_CUDA(cudaStreamSynchronize(ctx->stream)); // pinned staging may still be in flight
+        memcpy(ctx->h_pinned, pan::g_tab_host, 512);
+        memcpy((uint8_t *)ctx->h_pinned + 512, tiles.data(), tiles.size() * sizeof(pan::Tile));
+        OIP_CUDA(cudaMemcpyAsync(ctx->d_plan, ctx->h_pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->plan_key.assign(kb, kb + sizeof key);
+        ctx->plan_tiles = (int64_t)tiles.size();
+    }
+    if (ctx->plan_tiles == 0) return OIP_OK;
+
+    pan::Params P{};
+    bool bulk_ok = d->w % 8 == 0;
+    for (int i = 0; i < d->n_ccd; ++i) {
+        const oip_ccd_src &c = d->ccd[i];
+        pan::CcdDev &o = P.ccd[i];
+        o.fmt = c.fmt; o.n_seg = c.n_seg; o.kb = c.d_kb; o.dX = c.dX; o.dY = c.dY;
+        o.tile_off = c.d_tile_off; o.tile_cols = c.tile_cols; o.tile_lines = c.tile_lines;
+        if (c.fmt != OIP_FMT_LE16 && c.fmt != OIP_FMT_BE16) bulk_ok = false;
+        for (int s = 0; s < c.n_seg; ++s) {
+            if (!c.seg[s].base) return fail(OIP_E_INVALID, "ccd %d segment %d: null base", i, s);
+            o.seg[s].base = (const uint8_t *)c.seg[s].base;
+            o.seg[s].row0 = c.seg[s].row0; o.seg[s].n_rows = c.seg[s].n_rows; o.seg[s].pitch = c.seg[s].pitch_bytes;
+            if (((uintptr_t)c.seg[s].base & 15) || (c.seg[s].pitch_bytes & 15)) bulk_ok = false;
+        }
+    }
+    P.tab = reinterpret_cast<const float *>(ctx->d_plan);
+    P.tiles = reinterpret_cast<const pan::Tile *>((const uint8_t *)ctx->d_plan + 512);
+    P.out = d->d_out; P.out_pitch = d->out_pitch_px; P.out_row0 = d->row0;
+    P.err = ctx->d_err; P.w = d->w; P.n_ccd = d->n_ccd; P.bulk_ok = bulk_ok ? 1 : 0;
+
+    const size_t smem = (size_t)pan::RING * pan::SWC * 4 + 2 * (size_t)pan::STG * pan::SWC * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        OIP_CUDA(cudaFuncSetAttribute(pan::pan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    pan::pan_kernel<<<(unsigned)ctx->plan_tiles, pan::NT, smem, ctx->stream>>>(P);
+    OIP_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return OIP_OK;
+}
+
+extern "C" int oip_pan_check_error(oip_ctx *ctx)
+{
+    OIP_CHECK_CTX(ctx);
+    int e = 0;
+    OIP_CUDA(cudaMemcpyAsync(&e, ctx->d_err, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
+    OIP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (e) {
+        OIP_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+        return fail(OIP_E_RANGE, "a kernel needed a source row that no segment supplies (halo planning error)");
+    }
+    return OIP_OK;
+}
+
+extern "C" int oip_pan_rows_needed(const oip_pan_desc *d, int ccd, int64_t *first, int64_t *last,
+                                   int64_t *stale_first, int64_t *stale_last)
+{
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    if (ccd < 0 || ccd >= d->n_ccd) return fail(OIP_E_INVALID, "ccd index");
+    int64_t f = INT64_MAX, l = INT64_MIN, sf = INT64_MAX, sl = INT64_MIN;
+    const bool shifted = d->ccd[ccd].shifted != 0;
+    if (!shifted) {
+        f = d->row0; l = d->row0 + d->n_rows;
+    } else {
+        std::vector<ShiftSegment> segs;
+        if (!plan_shift_segments(d->total_rows, d->section_rows, d->row_guard, d->ccd[ccd].dY, segs))
+            return fail(OIP_E_INVALID, "invalid section geometry");
+        for (const ShiftSegment &s : segs) {
+            int64_t g0 = std::max<int64_t>(s.g0, d->row0), g1 = std::min<int64_t>(s.g1, d->row0 + d->n_rows);
+            if (g1 <= g0) continue;
+            int64_t ta = tap_base(s.j0 + (g0 - s.g0), d->ccd[ccd].dY);
+            int64_t tb = (int64_t)tap_base(s.j0 + (g1 - 1 - s.g0), d->ccd[ccd].dY) + 3;
+            ta = std::max<int64_t>(ta, 0); tb = std::min<int64_t>(tb, s.hbuf - 1);
+            if (tb < ta) continue;
+            // fresh part
+            int64_t fa = ta, fb = std::min<int64_t>(tb, s.rows_s - 1);
+            if (fb >= fa) { f = std::min(f, s.sec_off + fa); l = std::max(l, s.sec_off + fb + 1); }
+            int64_t sa = std::max<int64_t>(ta, s.rows_s), sb = tb;
+            if (sb >= sa && s.stale_off >= 0) { sf = std::min(sf, s.stale_off + sa); sl = std::max(sl, s.stale_off + sb + 1); }
+        }
+    }
+    if (f == INT64_MAX) { f = 0; l = 0; }
+    if (sf == INT64_MAX) { sf = 0; sl = 0; }
+    if (first) *first = f;
+    if (last) *last = l;
+    if (stale_first) *stale_first = sf;
+    if (stale_last) *stale_last = sl;
+    return OIP_OK;
+}
+
+extern "C" int oip_shift_cubic_u16(oip_ctx *ctx, const uint16_t *d_src, uint16_t *d_dst, int w, int64_t rows,
+                                   double dX, double dY, int section_rows, int row_guard)
+{
+    oip_pan_desc d{};
+    d.n_ccd = 1; d.w = w; d.total_rows = rows; d.row0 = 0; d.n_rows = rows; d.fold_half = 0;
+    d.section_rows = section_rows; d.row_guard = row_guard;
+    d.ccd[0].fmt = OIP_FMT_LE16; d.ccd[0].n_seg = 1; d.ccd[0].shifted = 1;
+    d.ccd[0].seg[0] = {d_src, 0, rows, (int64_t)w * 2};
+    d.ccd[0].dX = dX; d.ccd[0].dY = dY;
+    d.d_out = d_dst; d.out_pitch_px = w;
+    return oip_pan_pipeline(ctx, &d);
+}
+
+extern "C" int oip_stitch_concat_u16(oip_ctx *ctx, const uint16_t *const *d_ccd, int n_ccd, int w, int64_t rows,
+                                     int fold_half, uint16_t *d_dst)
+{
+    if (n_ccd < 1 || n_ccd > 8 || !d_ccd) return fail(OIP_E_INVALID, "n_ccd=%d out of range 1..8", n_ccd);
+    oip_pan_desc d{};
+    d.n_ccd = n_ccd; d.w = w; d.total_rows = rows; d.row0 = 0; d.n_rows = rows; d.fold_half = fold_half;
+    d.section_rows = 30000; d.row_guard = 32767;
+    for (int i = 0; i < n_ccd; ++i) {
+        d.ccd[i].fmt = OIP_FMT_LE16; d.ccd[i].n_seg = 1; d.ccd[i].shifted = 0;
+        d.ccd[i].seg[0] = {d_ccd[i], 0, rows, (int64_t)w * 2};
+    }
+    d.d_out = d_dst; d.out_pitch_px = oip_pan_out_width(n_ccd, w, fold_half);
+    return oip_pan_pipeline(ctx, &d);
+}

@@ -1,0 +1,263 @@
+"""Host-side Python mirror of the reference's per-pixel functions over the C ABI.
+
+PyTorch is used for device memory and streams only; every operation below is one or more calls
+into liboip_b200.so (hand-written sm_100a kernels).  Names follow the reference:
+
+    inplace_rrc            IMO::InplaceRRC                      ref imageop.h:129-138
+    prestitch_shift        Stitcher::PreStitch/SectionaryRemap  ref stitcher.h:83-139, imageop.h:230-275
+    stitch_big_raw         IMO::StitchBigRaw                    ref imageop.h:277-363
+    pan_pipeline           the three above fused, N CCDs
+    band_align             PreProcessor::DoInterBandAlignment   ref preproc.h:351-468
+    stitch_tiff_geometry   IMO::StitchTiff* geometry            ref imageop.h:416-421, :501-538
+    aos_scan / imtr_deframe / image_frames_index / unpack_frames
+                           AuxSeparator                         ref aux_separator.h:256-690
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import (FMT_BE16, FMT_BE16_TILES, FMT_LE16, FMT_PACK10, FMT_PACK12, CcdSrc, FrameEntry, FrameGeom,
+                   MssDesc, PanDesc, RowSeg, check)
+
+SECTION_ROWS = 30000  # REMAP_SECTION_ROWS, ref imageop.h:20
+ROW_GUARD = 32767     # REMAP_ROW_GUARD,    ref imageop.h:19
+
+
+class Context:
+    """one per GPU; owns a CUDA stream unless bound to torch's current stream."""
+
+    def __init__(self, device: int = 0, use_torch_stream: bool = True):
+        self.lib = capi.load()
+        self.device = device
+        h = C.c_void_p()
+        stream = None
+        if use_torch_stream:
+            stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        check(self.lib.oip_ctx_create(device, stream, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.oip_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.oip_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.oip_ctx_launch_count(self.h))
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def u16(t: torch.Tensor) -> torch.Tensor:
+    return t.view(torch.uint16) if t.dtype != torch.uint16 else t
+
+
+# ------------------------------------------------------------------------------- stage 2 / 3 (PAN)
+def make_pan_desc(ccds: Sequence[torch.Tensor], fmt, kbs, dX, dY, shifted, fold_half: int, out: torch.Tensor,
+                  total_rows: Optional[int] = None, row0: int = 0, n_rows: Optional[int] = None,
+                  section_rows: int = SECTION_ROWS, row_guard: int = ROW_GUARD, segs=None, pitch_bytes=None,
+                  w: Optional[int] = None) -> PanDesc:
+    """ccds[i]: device tensor holding rows of CCD i (2-D u16 for 16-bit formats, 2-D u8 for packed).
+    segs[i] (optional): list of (tensor_or_ptr, row0, n_rows, pitch_bytes) overriding the single segment."""
+    d = PanDesc()
+    n = len(ccds)
+    d.n_ccd = n
+    if w is None:
+        w = ccds[0].shape[1]
+    d.w = w
+    h = ccds[0].shape[0]
+    d.total_rows = h if total_rows is None else total_rows
+    d.row0 = row0
+    d.n_rows = (d.total_rows - row0) if n_rows is None else n_rows
+    d.fold_half = fold_half
+    d.section_rows = section_rows
+    d.row_guard = row_guard
+    for i in range(n):
+        c = d.ccd[i]
+        c.fmt = fmt if isinstance(fmt, int) else fmt[i]
+        if segs is not None and segs[i] is not None:
+            c.n_seg = len(segs[i])
+            for s, (base, r0, nr, pb) in enumerate(segs[i]):
+                c.seg[s] = RowSeg(base if isinstance(base, int) else base.data_ptr(), r0, nr, pb)
+        else:
+            c.n_seg = 1
+            pb = ccds[i].stride(0) * ccds[i].element_size() if pitch_bytes is None else pitch_bytes
+            c.seg[0] = RowSeg(ccds[i].data_ptr(), 0, ccds[i].shape[0], pb)
+        c.d_kb = _ptr(kbs[i]) if kbs is not None and kbs[i] is not None else None
+        c.shifted = int(bool(shifted[i]))
+        c.dX = float(dX[i])
+        c.dY = float(dY[i])
+    d.d_out = out.data_ptr()
+    d.out_pitch_px = out.stride(0)
+    return d
+
+
+def pan_out_width(n_ccd: int, w: int, fold_half: int) -> int:
+    return capi.load().oip_pan_out_width(n_ccd, w, fold_half)
+
+
+def pan_pipeline(ctx: Context, ccds, kbs, dX, dY, fold_half: int, fmt=FMT_LE16, shifted=None,
+                 section_rows: int = SECTION_ROWS, row_guard: int = ROW_GUARD, out: Optional[torch.Tensor] = None,
+                 check_error: bool = True, w: Optional[int] = None) -> torch.Tensor:
+    """fused unpack -> RRC -> shift -> concat.  CCD 0 is copied, CCD i>=1 shifted by (dX[i], dY[i])."""
+    n = len(ccds)
+    if w is None:
+        w = ccds[0].shape[1]
+    h = ccds[0].shape[0]
+    if shifted is None:
+        shifted = [i > 0 for i in range(n)]
+    if out is None:
+        out = torch.empty((h, pan_out_width(n, w, fold_half)), dtype=torch.uint16, device=ccds[0].device)
+    d = make_pan_desc(ccds, fmt, kbs, dX, dY, shifted, fold_half, out, section_rows=section_rows,
+                      row_guard=row_guard, w=w)
+    check(ctx.lib.oip_pan_pipeline(ctx.h, C.byref(d)))
+    if check_error:
+        check(ctx.lib.oip_pan_check_error(ctx.h))
+    return out
+
+
+def inplace_rrc(ctx: Context, img: torch.Tensor, kb: torch.Tensor) -> torch.Tensor:
+    h, w = img.shape
+    check(ctx.lib.oip_rrc_u16(ctx.h, img.data_ptr(), w, h, img.stride(0), kb.data_ptr()))
+    return img
+
+
+def prestitch_shift(ctx: Context, src: torch.Tensor, dX: float, dY: float, section_rows: int = SECTION_ROWS,
+                    row_guard: int = ROW_GUARD) -> torch.Tensor:
+    h, w = src.shape
+    dst = torch.empty_like(src)
+    check(ctx.lib.oip_shift_cubic_u16(ctx.h, src.data_ptr(), dst.data_ptr(), w, h, dX, dY, section_rows, row_guard))
+    check(ctx.lib.oip_pan_check_error(ctx.h))
+    return dst
+
+
+def stitch_big_raw(ctx: Context, ccds: Sequence[torch.Tensor], fold_half: int) -> torch.Tensor:
+    n = len(ccds)
+    h, w = ccds[0].shape
+    out = torch.empty((h, pan_out_width(n, w, fold_half)), dtype=torch.uint16, device=ccds[0].device)
+    arr = (C.c_void_p * n)(*[c.data_ptr() for c in ccds])
+    check(ctx.lib.oip_stitch_concat_u16(ctx.h, arr, n, w, h, fold_half, out.data_ptr()))
+    check(ctx.lib.oip_pan_check_error(ctx.h))
+    return out
+
+
+def cubic_tab() -> np.ndarray:
+    t = np.zeros(128, np.float32)
+    capi.load().oip_cubic_tab(t.ctypes.data)
+    return t.reshape(32, 4)
+
+
+# ------------------------------------------------------------------------------- stage 3 (MSS)
+def band_align(ctx: Context, mss: torch.Tensor, wb: int, kbs, cX, cY, lines_per_section: int = 20000,
+               line_offset: int = 0, overlap: int = 520, keep_leading: bool = False, min_process_lines: int = 1500,
+               fmt: int = FMT_LE16, out: Optional[torch.Tensor] = None):
+    lines = mss.shape[0]
+    d = MssDesc()
+    d.fmt = fmt
+    d.wb = wb
+    d.lines = lines
+    d.pitch_px = mss.stride(0)
+    for b in range(4):
+        d.d_kb[b] = _ptr(kbs[b]) if kbs is not None and kbs[b] is not None else None
+    cX = np.asarray(cX, np.float64).reshape(-1)
+    cY = np.asarray(cY, np.float64).reshape(-1)
+    for i in range(8):
+        d.cX[i] = cX[i]
+    for i in range(12):
+        d.cY[i] = cY[i]
+    d.lines_per_section = lines_per_section
+    d.line_offset = line_offset
+    d.overlap = overlap
+    d.keep_leading = int(keep_leading)
+    d.min_process_lines = min_process_lines
+    rows = lines - line_offset - (0 if keep_leading else overlap)
+    if out is None:
+        out = torch.zeros((max(rows, 0), wb, 4), dtype=torch.uint16, device=mss.device)
+    n = C.c_int64(0)
+    check(ctx.lib.oip_band_align_merge(ctx.h, mss.data_ptr(), C.byref(d), out.data_ptr(), C.byref(n)))
+    return int(n.value), out
+
+
+def stitch_tiff_geometry(ctx: Context, imgs: Sequence[torch.Tensor], fold_half: int, band_map=None) -> torch.Tensor:
+    n = len(imgs)
+    h, w, _ = imgs[0].shape
+    out = torch.empty((h, pan_out_width(n, w, fold_half), 4), dtype=torch.uint16, device=imgs[0].device)
+    arr = (C.c_void_p * n)(*[c.data_ptr() for c in imgs])
+    bm = (C.c_int * 4)(*band_map) if band_map is not None else None
+    check(ctx.lib.oip_stitch_concat_c4(ctx.h, arr, n, w, h, fold_half, bm, out.data_ptr()))
+    return out
+
+
+def unpack_lines(ctx: Context, raw: torch.Tensor, fmt: int, w: int) -> torch.Tensor:
+    rows = raw.shape[0]
+    out = torch.empty((rows, w), dtype=torch.uint16, device=raw.device)
+    check(ctx.lib.oip_unpack_lines(ctx.h, raw.data_ptr(), fmt, w, rows, raw.stride(0) * raw.element_size(),
+                                   out.data_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------- stage 1
+def crc16_batch(ctx: Context, buf: torch.Tensor, off: torch.Tensor, length: int) -> torch.Tensor:
+    out = torch.empty(off.numel(), dtype=torch.uint16, device=buf.device)
+    check(ctx.lib.oip_crc16_batch(ctx.h, buf.data_ptr(), off.data_ptr(), off.numel(), length, out.data_ptr()))
+    return out
+
+
+def aos_scan(ctx: Context, buf: torch.Tensor):
+    """returns (payload_off device int64 tensor [n_valid], counters np.int64[3] = valid, invalid, empty)"""
+    n = buf.numel()
+    cap = n // 1024 + 1
+    off = torch.empty(cap, dtype=torch.int64, device=buf.device)
+    cnt = (C.c_int64 * 3)()
+    check(ctx.lib.oip_aos_scan(ctx.h, buf.data_ptr(), n, off.data_ptr(), cap, cnt))
+    return off[: cnt[0]], np.array(list(cnt), np.int64)
+
+
+def imtr_deframe(ctx: Context, buf: torch.Tensor, payload_off: torch.Tensor):
+    n = payload_off.numel()
+    cap = (n * 880 // 882 + 1) * 866
+    imdt = torch.empty(cap, dtype=torch.uint8, device=buf.device)
+    st = (C.c_int64 * 9)()
+    nb = C.c_int64(0)
+    check(ctx.lib.oip_imtr_deframe(ctx.h, buf.data_ptr(), payload_off.data_ptr(), n, imdt.data_ptr(), cap, st,
+                                   C.byref(nb)))
+    return imdt[: nb.value], np.array(list(st), np.int64)
+
+
+def image_frames_index(ctx: Context, imdt: torch.Tensor, tile_cols: int, tile_lines: int):
+    g = FrameGeom(tile_cols, tile_lines)
+    frame_bytes = 192 * tile_lines + 40 * tile_cols * tile_lines * 2 + 172
+    cap = max(16, 4 * (imdt.numel() // max(frame_bytes, 1) + 2) + 70000)
+    ents = (FrameEntry * cap)()
+    st = (C.c_int64 * 4)()
+    check(ctx.lib.oip_image_frames_index(ctx.h, imdt.data_ptr(), imdt.numel(), C.byref(g), ents, cap, st))
+    return ents, np.array(list(st), np.int64)
+
+
+def unpack_frames(ctx: Context, imdt: torch.Tensor, tile_cols: int, tile_lines: int, ents, n_frames: int,
+                  want_aux=True, want_pan=True, want_mss=True):
+    g = FrameGeom(tile_cols, tile_lines)
+    W = 8 * tile_cols
+    dev = imdt.device
+    aux = torch.empty((n_frames, 192 * tile_lines), dtype=torch.uint8, device=dev) if want_aux else None
+    pan = torch.empty((n_frames * 4 * tile_lines, W), dtype=torch.uint16, device=dev) if want_pan else None
+    mss = torch.empty((n_frames * tile_lines, W), dtype=torch.uint16, device=dev) if want_mss else None
+    check(ctx.lib.oip_unpack_frames(ctx.h, imdt.data_ptr(), imdt.numel(), C.byref(g), ents, n_frames, _ptr(aux),
+                                    _ptr(pan), _ptr(mss)))
+    return aux, pan, mss
