@@ -42,8 +42,10 @@ typedef enum {
 typedef struct oip_ctx oip_ctx;
 
 /* ---- context ----------------------------------------------------------------------------- */
-/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL = own stream */
-int oip_ctx_create(int device, void *stream, oip_ctx **out);
+/* own_stream != 0: the context creates its own non-blocking stream (`stream` ignored);
+ * own_stream == 0: enqueue on `stream`, a cudaStream_t (0 = the legacy default stream, which is
+ * what torch's current stream is unless the caller changed it) */
+int oip_ctx_create(int device, void *stream, int own_stream, oip_ctx **out);
 void oip_ctx_destroy(oip_ctx *ctx);
 int oip_ctx_sync(oip_ctx *ctx);
 void *oip_ctx_stream(oip_ctx *ctx);

@@ -54,7 +54,7 @@ class MssDesc(C.Structure):
 # every symbol include/oip_b200.h declares: name -> (restype, argtypes)
 _VP, _I, _I64, _SZ, _D = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 SYMBOLS = {
-    "oip_ctx_create": (_I, [_I, _VP, C.POINTER(_VP)]),
+    "oip_ctx_create": (_I, [_I, _VP, _I, C.POINTER(_VP)]),
     "oip_ctx_destroy": (None, [_VP]),
     "oip_ctx_sync": (_I, [_VP]),
     "oip_ctx_stream": (_VP, [_VP]),

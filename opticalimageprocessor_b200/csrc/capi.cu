@@ -59,7 +59,7 @@ extern "C" {
 const char *oip_last_error(void) { return oip::g_err; }
 int oip_abi_version(void) { return OIP_ABI_VERSION; }
 
-int oip_ctx_create(int device, void *stream, oip_ctx **out)
+int oip_ctx_create(int device, void *stream, int own_stream, oip_ctx **out)
 {
     if (!out) return oip::fail(OIP_E_INVALID, "oip_ctx_create: out is null");
     *out = nullptr;
@@ -79,7 +79,7 @@ int oip_ctx_create(int device, void *stream, oip_ctx **out)
     if (!c) return oip::fail(OIP_E_NOMEM, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (stream) {
+    if (!own_stream) {
         c->stream = (cudaStream_t)stream;
     } else {
         e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);

@@ -1,0 +1,913 @@
+// frames.cu -- stage 1: AOS sync search + CRC + chained scan, IMTR re-framing, image-frame index,
+// sub-image unpack.  All integer / byte work; results are bit-exact with the reference's
+// sequential loops (ref aux_separator.h:256-690), whose order-dependent rules are resolved with
+// parallel candidate evaluation + a short dependent walk over the (tiny) candidate table.
+#include <algorithm>
+
+#include "oip_common.cuh"
+
+namespace oip {
+namespace frames {
+
+// =============================================================================================
+// CRC-16/CCITT-FALSE split over the 32 lanes of a warp (ref CRC.h:806-834 is bit-serial).
+// lane l takes bytes [l*cs, (l+1)*cs) with a zero initial remainder; the pieces are joined with
+// rem = XOR_l (rem_l * x^(8*bytes_after_l) mod P)  ^  (0xFFFF * x^(8*len) mod P).
+// =============================================================================================
+struct CrcPlan {
+    int len, cs;           // message bytes, bytes per lane
+    uint16_t mul[32];      // x^(8*bytes_after_l) mod P
+    uint16_t init_term;    // 0xFFFF * x^(8*len) mod P
+};
+
+static uint16_t h_mulx8(uint16_t r)
+{
+    for (int i = 0; i < 8; ++i) r = (uint16_t)((r & 0x8000) ? ((r << 1) ^ 0x1021) : (r << 1));
+    return r;
+}
+static uint16_t h_gfmul(uint16_t a, uint16_t b)
+{
+    uint16_t r = 0;
+    for (int i = 15; i >= 0; --i) {
+        r = (uint16_t)((r & 0x8000) ? ((r << 1) ^ 0x1021) : (r << 1));
+        if ((b >> i) & 1) r ^= a;
+    }
+    return r;
+}
+static CrcPlan make_crc_plan(int len)
+{
+    CrcPlan p{};
+    p.len = len;
+    p.cs = ((len + 31) / 32 + 3) & ~3; // multiple of 4 bytes per lane
+    // xp[m] = x^(8m) mod P
+    std::vector<uint16_t> xp(len + 1);
+    xp[0] = 1;
+    for (int m = 1; m <= len; ++m) xp[m] = h_mulx8(xp[m - 1]);
+    for (int l = 0; l < 32; ++l) {
+        int end = std::min(len, (l + 1) * p.cs);
+        p.mul[l] = xp[len - end];
+    }
+    p.init_term = h_gfmul(0xFFFF, xp[len]);
+    return p;
+}
+
+__device__ __forceinline__ uint32_t gfmul16(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 15; i >= 0; --i) {
+        r = ((r << 1) ^ ((r & 0x8000u) ? 0x1021u : 0u)) & 0xFFFFu;
+        r ^= ((b >> i) & 1u) ? a : 0u;
+    }
+    return r;
+}
+
+// get(i) returns message byte i; every lane of the warp must call this
+template <typename GetByte>
+__device__ __forceinline__ uint32_t warp_crc16(const CrcPlan &P, GetByte get)
+{
+    const int lane = threadIdx.x & 31;
+    const int b0 = lane * P.cs, b1 = min(P.len, b0 + P.cs);
+    uint32_t r = 0;
+    for (int i = b0; i < b1; ++i) r = crc16_byte(r, get(i));
+    uint32_t c = gfmul16(r, P.mul[lane]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
+    return c ^ P.init_term;
+}
+
+// =============================================================================================
+// generic exclusive scan (u32), three small kernels; used on candidate tables only
+// =============================================================================================
+constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_B = SCAN_T * SCAN_I;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total)
+{
+    __shared__ uint32_t s_w[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < (blockDim.x >> 5) ? s_w[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        s_w[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t base = wid ? s_w[wid - 1] : 0;
+    if (total) *total = s_w[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+__global__ void scan_block_kernel(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *block_sums)
+{
+    const int64_t base = (int64_t)blockIdx.x * SCAN_B + (int64_t)threadIdx.x * SCAN_I;
+    uint32_t v[SCAN_I], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_I; ++i) {
+        v[i] = base + i < n ? in[base + i] : 0;
+        s += v[i];
+    }
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(s, &tot);
+#pragma unroll
+    for (int i = 0; i < SCAN_I; ++i) {
+        if (base + i < n) out[base + i] = ex;
+        ex += v[i];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+__global__ void scan_add_kernel(uint32_t *out, int64_t n, const uint32_t *block_prefix)
+{
+    const int64_t i = (int64_t)blockIdx.x * SCAN_B + threadIdx.x;
+    const uint32_t add = block_prefix[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_I; ++k) {
+        int64_t j = i + (int64_t)k * SCAN_T;
+        if (j < n) out[j] += add;
+    }
+}
+// scratch must hold ceil(n/SCAN_B) + recursive levels u32; returns via d_total (device u32)
+static int exclusive_scan_u32(oip_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t n, uint32_t *scratch,
+                              uint32_t *d_total)
+{
+    if (n <= 0) {
+        OIP_CUDA(cudaMemsetAsync(d_total, 0, 4, ctx->stream));
+        return OIP_OK;
+    }
+    const int64_t nb = (n + SCAN_B - 1) / SCAN_B;
+    scan_block_kernel<<<(unsigned)nb, SCAN_T, 0, ctx->stream>>>(in, out, n, scratch);
+    OIP_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (nb == 1) {
+        OIP_CUDA(cudaMemcpyAsync(d_total, scratch, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return OIP_OK;
+    }
+    uint32_t *prefix = scratch + nb;
+    int rc = exclusive_scan_u32(ctx, scratch, prefix, nb, prefix + nb, d_total);
+    if (rc) return rc;
+    scan_add_kernel<<<(unsigned)nb, SCAN_T, 0, ctx->stream>>>(out, n, prefix);
+    OIP_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return OIP_OK;
+}
+static size_t scan_scratch_elems(int64_t n)
+{
+    size_t t = 0;
+    while (n > 1) {
+        n = (n + SCAN_B - 1) / SCAN_B;
+        t += (size_t)n * 2 + 8;
+    }
+    return t + 16;
+}
+
+// =============================================================================================
+// AOS: sync search + frame validation, one CTA per 16 KiB chunk staged in shared memory
+// =============================================================================================
+constexpr int CH = 16384;           // file bytes owned by a CTA
+constexpr int CH_HALO = 1024;       // a frame starting at the last owned byte ends here
+constexpr int AOS_T = 256;
+
+struct ChunkInfo {
+    uint32_t slot0, count;
+};
+
+__global__ void __launch_bounds__(AOS_T) aos_scan_kernel(const uint8_t *__restrict__ buf, int64_t n,
+                                                         const __grid_constant__ CrcPlan crc, uint32_t *cursor,
+                                                         uint32_t cap, ChunkInfo *info, uint64_t *cand_off,
+                                                         int8_t *cand_st)
+{
+    __shared__ __align__(16) uint8_t s_buf[CH + CH_HALO + 16];
+    __shared__ uint32_t s_bits[CH / 32];
+    __shared__ uint16_t s_cand[CH / 4];
+    __shared__ uint32_t s_slot0, s_total;
+
+    const int tid = threadIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.x * CH;
+    const int avail = (int)min((int64_t)(CH + CH_HALO), n - c0); // bytes of the file in s_buf
+
+    // ---- stage the chunk (+halo).  16-byte vector loads when the buffer allows it.
+    if ((((uintptr_t)buf) & 15) == 0) {
+        const int nv = avail >> 4;
+        const uint4 *src = reinterpret_cast<const uint4 *>(buf + c0);
+        for (int i = tid; i < nv; i += AOS_T) reinterpret_cast<uint4 *>(s_buf)[i] = ldg_nc_v4(src + i);
+        for (int i = (nv << 4) + tid; i < avail; i += AOS_T) s_buf[i] = buf[c0 + i];
+    } else {
+        for (int i = tid; i < avail; i += AOS_T) s_buf[i] = buf[c0 + i];
+    }
+    for (int i = avail + tid; i < CH + CH_HALO + 16; i += AOS_T) s_buf[i] = 0;
+    for (int i = tid; i < CH / 32; i += AOS_T) s_bits[i] = 0;
+    __syncthreads();
+
+    // ---- sync search "1A CF FC 1D" (ref aux_separator.h:29, :622-625); a hit must leave room for a
+    //      whole frame (p + 1024 <= n), anything later can never be accepted or counted
+    const int own = (int)min((int64_t)CH, n - c0);
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(s_buf);
+    for (int wi = tid; wi < CH / 4; wi += AOS_T) {
+        const uint32_t w = w32[wi];
+        const uint32_t x = w ^ 0x1A1A1A1Au;
+        if ((x - 0x01010101u) & ~x & 0x80808080u) { // some byte equals 0x1A
+            const uint32_t nx = w32[wi + 1];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t v = __funnelshift_r(w, nx, 8 * b);
+                const int p = wi * 4 + b;
+                if (v == 0x1DFCCF1Au && p < own && c0 + p + 1024 <= n) atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- ordered list of hits (bitmap -> positions), two bitmap words per thread
+    {
+        const uint32_t m0 = s_bits[2 * tid], m1 = s_bits[2 * tid + 1];
+        const uint32_t cnt = __popc(m0) + __popc(m1);
+        uint32_t tot;
+        uint32_t at = block_exclusive_scan(cnt, &tot);
+        uint32_t m = m0;
+        while (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1;
+            s_cand[at++] = (uint16_t)(2 * tid * 32 + b);
+        }
+        m = m1;
+        while (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1;
+            s_cand[at++] = (uint16_t)((2 * tid + 1) * 32 + b);
+        }
+        if (tid == 0) {
+            s_total = tot;
+            s_slot0 = tot ? atomicAdd(cursor, tot) : 0;
+            info[blockIdx.x].slot0 = s_slot0;
+            info[blockIdx.x].count = tot;
+        }
+    }
+    __syncthreads();
+    const uint32_t total = s_total, slot0 = s_slot0;
+    if (slot0 + total > cap) return; // table too small: the host re-runs with the exact size
+
+    // ---- ValidateAosFrame (ref aux_separator.h:658-690), one warp per candidate
+    const int lane = tid & 31, wid = tid >> 5;
+    for (uint32_t j = wid; j < total; j += AOS_T / 32) {
+        const uint8_t *f = s_buf + s_cand[j];
+        const uint32_t vcid = f[5] & 0x3F;
+        const uint32_t inj = ((uint32_t)f[10] << 24) | ((uint32_t)f[11] << 16) | ((uint32_t)f[12] << 8) | f[13];
+        int st;
+        if (inj != 0xAAAAAAAAu && inj != 0u) st = -1;          // :675
+        else if (inj == 0xAAAAAAAAu && vcid == 0x3F) st = 0;   // :676
+        else {                                                 // :679-686, CRC over bytes 4..893
+            const uint32_t c = warp_crc16(crc, [&](int i) { return (uint32_t)f[4 + i]; });
+            const uint32_t want = ((uint32_t)f[894] << 8) | f[895];
+            st = c == want ? 1 : -1;
+        }
+        if (lane == 0) {
+            cand_off[slot0 + j] = (uint64_t)(c0 + s_cand[j]);
+            cand_st[slot0 + j] = (int8_t)st;
+        }
+    }
+}
+
+// candidates in file order: chunk c's run goes to [base[c], base[c]+count)
+__global__ void aos_order_kernel(const ChunkInfo *info, const uint32_t *base, int64_t n_chunks, const uint64_t *cand_off,
+                                 const int8_t *cand_st, uint64_t *ord_off, int8_t *ord_st)
+{
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= n_chunks) return;
+    const ChunkInfo ci = info[c];
+    const uint32_t b = base[c];
+    for (uint32_t j = lane; j < ci.count; j += 32) {
+        ord_off[b + j] = cand_off[ci.slot0 + j];
+        ord_st[b + j] = cand_st[ci.slot0 + j];
+    }
+}
+
+// A valid candidate with no valid candidate in the preceding 1023 bytes is always accepted by the
+// sequential scan (ref aux_separator.h:421-461): whatever was accepted before ends <= its offset.
+__global__ void aos_runstart_kernel(const uint64_t *off, const int8_t *st, int64_t m, uint8_t *rs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint8_t r = 0;
+    if (st[i] == 1) {
+        r = 1;
+        for (int64_t j = i - 1; j >= 0 && off[i] - off[j] < 1024; --j)
+            if (st[j] == 1) { r = 0; break; }
+    }
+    rs[i] = r;
+}
+
+// each run start replays the reference's skip rules up to the next run start:
+// accepted frame -> next search position = off+1024; rejected candidate -> off+4 (:440-441,:456-457)
+__global__ void aos_walk_kernel(const uint64_t *off, const int8_t *st, const uint8_t *rs, int64_t m, uint32_t *acc,
+                                unsigned long long *counters)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (!(rs[i] || i == 0)) { return; }
+    unsigned long long n_inv = 0, n_emp = 0, n_val = 0;
+    int64_t j = i;
+    uint64_t next_free = 0; // first byte the scan may look at
+    if (rs[i]) {
+        acc[i] = 1;
+        n_val = 1;
+        next_free = off[i] + 1024;
+        j = i + 1;
+    }
+    for (; j < m && !rs[j]; ++j) {
+        if (off[j] < next_free) { acc[j] = 0; continue; } // inside an accepted frame: never seen
+        if (st[j] == 1) {
+            acc[j] = 1;
+            n_val++;
+            next_free = off[j] + 1024;
+        } else {
+            acc[j] = 0;
+            if (st[j] < 0) n_inv++; else n_emp++;
+        }
+    }
+    if (n_val) atomicAdd(&counters[0], n_val);
+    if (n_inv) atomicAdd(&counters[1], n_inv);
+    if (n_emp) atomicAdd(&counters[2], n_emp);
+}
+
+__global__ void aos_emit_kernel(const uint64_t *off, const uint32_t *acc, const uint32_t *rank, int64_t m,
+                                uint64_t *payload_off, uint64_t cap)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m || !acc[i]) return;
+    if (rank[i] < cap) payload_off[rank[i]] = off[i] + 14; // AOS_DATA_OFF :44
+}
+
+// =============================================================================================
+// IMTR: fixed 882-byte cadence over the virtual concatenation of the 880-byte payloads
+// =============================================================================================
+__device__ __forceinline__ uint8_t stream_byte(const uint8_t *buf, const uint64_t *poff, int64_t s)
+{
+    const int64_t i = s / 880;
+    return buf[poff[i] + (uint64_t)(s - i * 880)];
+}
+
+constexpr int IMTR_WARPS = 8;
+__global__ void __launch_bounds__(IMTR_WARPS * 32) imtr_validate_kernel(const uint8_t *__restrict__ buf,
+                                                                         const uint64_t *__restrict__ poff,
+                                                                         int64_t n_frames,
+                                                                         const __grid_constant__ CrcPlan crc,
+                                                                         uint8_t *status, uint32_t *seq, uint8_t *chid,
+                                                                         uint32_t *valid)
+{
+    __shared__ uint8_t s_f[IMTR_WARPS][896];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t f = (int64_t)blockIdx.x * IMTR_WARPS + wid;
+    if (f >= n_frames) return;
+    uint8_t *fr = s_f[wid];
+    const int64_t s0 = f * 882;
+    // gather the frame (it spans 2 or 3 payloads)
+    {
+        int64_t i = s0 / 880;
+        int o = (int)(s0 - i * 880);
+        // lane-strided byte copy; (i,o) advanced per byte position
+        for (int b = lane; b < 882; b += 32) {
+            int oo = o + b;
+            int64_t ii = i;
+            while (oo >= 880) { oo -= 880; ++ii; }
+            fr[b] = buf[poff[ii] + (uint64_t)oo];
+        }
+    }
+    __syncwarp();
+    // ValidateImtrFrame, checks in the reference's order (ref aux_separator.h:558-590)
+    int st = 0;
+    if (!(fr[0] == 0x49 && fr[1] == 0x54 && fr[2] == 0xCE && fr[3] == 0x1F)) st = 1;                 // :559
+    else if (!(fr[878] == 0x2E && fr[879] == 0xE9 && fr[880] == 0xC8 && fr[881] == 0xFD)) st = 2;     // :563
+    else if (fr[9] != 0x22) st = 3;                                                                  // :572
+    else {
+        const uint32_t c = warp_crc16(crc, [&](int i) { return (uint32_t)fr[i]; });                  // :577-583
+        const uint32_t want = ((uint32_t)fr[876] << 8) | fr[877];
+        if (c != want) st = 4;
+    }
+    if (lane == 0) {
+        status[f] = (uint8_t)st;
+        seq[f] = ((uint32_t)fr[4] << 24) | ((uint32_t)fr[5] << 16) | ((uint32_t)fr[6] << 8) | fr[7];  // :568-569
+        chid[f] = fr[8];
+        valid[f] = st == 0;
+    }
+}
+
+// seq of the valid frames in order (to evaluate the "previous accepted seq" rules)
+__global__ void imtr_compact_seq_kernel(const uint32_t *valid, const uint32_t *rank, const uint32_t *seq, int64_t n,
+                                        uint32_t *seq_c)
+{
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n && valid[f]) seq_c[rank[f]] = seq[f];
+}
+// restart rule: the IMDT file is (re)created when the previously accepted frame had seq 0
+// (lastImtrSeq == 0, ref :513-528); gap rule :530-533
+__global__ void imtr_rules_kernel(const uint32_t *seq_c, int64_t n_valid, unsigned long long *restart_last,
+                                  unsigned long long *n_restarts, unsigned long long *n_gaps)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_valid) return;
+    const uint32_t prev = k ? seq_c[k - 1] : 0u;
+    if (prev == 0u) {
+        atomicMax(restart_last, (unsigned long long)k);
+        atomicAdd(n_restarts, 1ull);
+    }
+    if (prev + 1u != seq_c[k]) atomicAdd(n_gaps, 1ull);
+}
+__global__ void __launch_bounds__(256) imtr_copy_kernel(const uint8_t *__restrict__ buf, const uint64_t *__restrict__ poff,
+                                                        int64_t n_frames, const uint32_t *valid, const uint32_t *rank,
+                                                        const unsigned long long *restart_last, const uint8_t *chid,
+                                                        uint8_t *imdt, uint64_t cap, int *first_chid)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (f >= n_frames || !valid[f]) return;
+    const uint64_t r0 = *restart_last;
+    if (rank[f] < r0) return;
+    const uint64_t dst = (uint64_t)(rank[f] - r0) * 866;
+    if (dst + 866 > cap) return;
+    if (rank[f] == r0 && lane == 0) *first_chid = chid[f];
+    const int64_t s0 = f * 882 + 10; // IMTR_IMGDATA_OFF :72
+    int64_t i = s0 / 880;
+    const int o = (int)(s0 - i * 880);
+    for (int b = lane; b < 866; b += 32) {
+        int oo = o + b;
+        int64_t ii = i;
+        while (oo >= 880) { oo -= 880; ++ii; }
+        imdt[dst + b] = buf[poff[ii] + (uint64_t)oo];
+    }
+}
+
+// =============================================================================================
+// image frames: trailer-signature search, trailer gather, sub-image unpack
+// =============================================================================================
+__global__ void find_sig4_kernel(const uint8_t *__restrict__ buf, int64_t n, uint32_t sig_le, uint8_t first,
+                                 unsigned long long *hits, uint32_t cap, uint32_t *n_hits)
+{
+    // each thread scans 16 consecutive positions; word-wise reject on the first signature byte
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
+    const uint32_t pat = 0x01010101u * first;
+    for (int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; p0 < n; p0 += stride) {
+        uint32_t w[5];
+        if (p0 + 20 <= n && ((((uintptr_t)buf) + p0) & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) w[i] = reinterpret_cast<const uint32_t *>(buf + p0)[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                uint32_t v = 0;
+                for (int b = 0; b < 4; ++b) {
+                    int64_t q = p0 + 4 * i + b;
+                    v |= (uint32_t)(q < n ? buf[q] : 0) << (8 * b);
+                }
+                w[i] = v;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t x = w[i] ^ pat;
+            if ((x - 0x01010101u) & ~x & 0x80808080u) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int64_t p = p0 + 4 * i + b;
+                    if (__funnelshift_r(w[i], w[i + 1], 8 * b) == sig_le && p + 4 <= n) {
+                        uint32_t k = atomicAdd(n_hits, 1u);
+                        if (k < cap) hits[k] = (unsigned long long)p;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void gather_trailers_kernel(const uint8_t *buf, int64_t n, const unsigned long long *hits, uint32_t n_hits,
+                                       uint8_t *out)
+{
+    const uint32_t h = blockIdx.x;
+    if (h >= n_hits) return;
+    for (int b = threadIdx.x; b < 172; b += blockDim.x) {
+        int64_t q = (int64_t)hits[h] + b;
+        out[(size_t)h * 172 + b] = q < n ? buf[q] : 0;
+    }
+}
+
+struct UnpackParams {
+    const uint8_t *imdt;
+    const int64_t *tab; // per frame: frame_off, tile_off[40]
+    uint8_t *aux;
+    uint16_t *pan, *mss;
+    int tile_cols, tile_lines;
+    int64_t n_frames;
+};
+// grid: (frame, item) with item 0..39 = sub-image r*8+c, 40 = aux block (ref aux_separator.h:335-393)
+__global__ void __launch_bounds__(256) unpack_frames_kernel(const __grid_constant__ UnpackParams P)
+{
+    const int64_t fr = blockIdx.x;
+    const int item = blockIdx.y;
+    const int TC = P.tile_cols, TL = P.tile_lines;
+    const int64_t W = 8 * (int64_t)TC;
+    const int64_t *ent = P.tab + fr * 41;
+    const int64_t frame_off = ent[0];
+    if (item == 40) {
+        if (!P.aux) return;
+        const int64_t nb = 192 * (int64_t)TL;
+        uint8_t *dst = P.aux + fr * nb;
+        if (frame_off < 0) {
+            for (int64_t i = threadIdx.x; i < nb; i += blockDim.x) dst[i] = 0;
+        } else {
+            const uint8_t *src = P.imdt + frame_off;
+            if (((((uintptr_t)src) | ((uintptr_t)dst)) & 3) == 0) {
+                for (int64_t i = threadIdx.x; i < nb / 4; i += blockDim.x)
+                    reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+            } else {
+                for (int64_t i = threadIdx.x; i < nb; i += blockDim.x) dst[i] = src[i];
+            }
+        }
+        return;
+    }
+    const int r = item >> 3, c = item & 7;
+    uint16_t *dst;
+    if (r < 4) {
+        if (!P.pan) return;
+        dst = P.pan + (fr * 4 * TL + (int64_t)r * TL) * W + (int64_t)c * TC;
+    } else {
+        if (!P.mss) return;
+        dst = P.mss + fr * TL * W + (int64_t)c * TC;
+    }
+    const int64_t toff = ent[1 + item];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (frame_off < 0 || toff < 0) { // zero-filled gap frame (ref :302-311)
+        for (int y = wid; y < TL; y += nw)
+            for (int x = lane; x < TC; x += 32) dst[(int64_t)y * W + x] = 0;
+        return;
+    }
+    const uint8_t *src = P.imdt + toff;
+    const bool a4 = ((((uintptr_t)src) & 3) == 0) && (TC % 2 == 0) && ((((uintptr_t)dst) & 3) == 0);
+    for (int y = wid; y < TL; y += nw) {
+        const uint8_t *sl = src + (int64_t)y * TC * 2;
+        uint16_t *dl = dst + (int64_t)y * W;
+        if (a4) {
+            for (int x = lane; x < TC / 2; x += 32)
+                reinterpret_cast<uint32_t *>(dl)[x] = bswap16x2(reinterpret_cast<const uint32_t *>(sl)[x]); // :387-392
+        } else {
+            for (int x = lane; x < TC; x += 32) dl[x] = (uint16_t)(((uint32_t)sl[2 * x] << 8) | sl[2 * x + 1]);
+        }
+    }
+}
+
+__global__ void crc16_batch_kernel(const uint8_t *__restrict__ buf, const uint64_t *__restrict__ off, int64_t n,
+                                   const __grid_constant__ CrcPlan crc, uint16_t *out)
+{
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const uint8_t *p = buf + off[i];
+    const uint32_t c = warp_crc16(crc, [&](int k) { return (uint32_t)p[k]; });
+    if ((threadIdx.x & 31) == 0) out[i] = (uint16_t)c;
+}
+
+} // namespace frames
+} // namespace oip
+
+using namespace oip;
+using namespace oip::frames;
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int oip_crc16_batch(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_off, int64_t n_items, int len,
+                               uint16_t *d_crc)
+{
+    OIP_CHECK_CTX(ctx);
+    if (!d_buf || !d_off || !d_crc) return fail(OIP_E_INVALID, "oip_crc16_batch: null pointer");
+    if (len < 0 || len > (1 << 20)) return fail(OIP_E_INVALID, "oip_crc16_batch: len=%d", len);
+    if (n_items <= 0) return OIP_OK;
+    const CrcPlan plan = make_crc_plan(len);
+    const int64_t blocks = (n_items * 32 + 255) / 256;
+    crc16_batch_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_buf, d_off, n_items, plan, d_crc);
+    OIP_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return OIP_OK;
+}
+
+extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, uint64_t *d_payload_off, size_t cap,
+                            int64_t counters[3])
+{
+    OIP_CHECK_CTX(ctx);
+    if (counters) counters[0] = counters[1] = counters[2] = 0;
+    if (!d_buf && n_bytes) return fail(OIP_E_INVALID, "oip_aos_scan: null buffer");
+    if (n_bytes < 1024) return OIP_OK; // ref :623
+    if (n_bytes / 4 > 0x7fffffffull) return fail(OIP_E_INVALID, "oip_aos_scan: buffer too large for one call");
+    const int64_t n = (int64_t)n_bytes;
+    const int64_t n_chunks = (n + CH - 1) / CH;
+    static const CrcPlan plan = make_crc_plan(890);
+
+    uint32_t cand_cap = (uint32_t)std::min<int64_t>(n / 4 + 1, n / 512 + 4096);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // scratch layout
+        size_t o = 0;
+        auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+        const size_t o_hdr = take(64);                       // cursor(u32) | total(u32) | counters(3 x u64) | acc_total
+        const size_t o_info = take((size_t)n_chunks * sizeof(ChunkInfo));
+        const size_t o_cnt = take((size_t)n_chunks * 4);
+        const size_t o_base = take((size_t)n_chunks * 4);
+        const size_t o_coff = take((size_t)cand_cap * 8);
+        const size_t o_cst = take((size_t)cand_cap);
+        const size_t o_ooff = take((size_t)cand_cap * 8);
+        const size_t o_ost = take((size_t)cand_cap);
+        const size_t o_rs = take((size_t)cand_cap);
+        const size_t o_acc = take((size_t)cand_cap * 4);
+        const size_t o_rank = take((size_t)cand_cap * 4);
+        const size_t o_scan = take(scan_scratch_elems(std::max<int64_t>(n_chunks, cand_cap)) * 4);
+        int rc = ensure_scratch(ctx, o);
+        if (rc) return rc;
+        uint8_t *S = (uint8_t *)ctx->d_scratch;
+        uint32_t *d_cursor = (uint32_t *)(S + o_hdr);
+        uint32_t *d_total = d_cursor + 1;
+        unsigned long long *d_counters = (unsigned long long *)(S + o_hdr + 8);
+        uint32_t *d_acc_total = (uint32_t *)(S + o_hdr + 40);
+        ChunkInfo *d_info = (ChunkInfo *)(S + o_info);
+        OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 64, ctx->stream));
+
+        aos_scan_kernel<<<(unsigned)n_chunks, AOS_T, 0, ctx->stream>>>(d_buf, n, plan, d_cursor, cand_cap, d_info,
+                                                                      (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst));
+        OIP_CUDA(cudaGetLastError());
+        ctx->launches++;
+        rc = ensure_pinned(ctx, 64);
+        if (rc) return rc;
+        uint32_t *h = (uint32_t *)ctx->h_pinned;
+        OIP_CUDA(cudaMemcpyAsync(h, d_cursor, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        OIP_CUDA(cudaStreamSynchronize(ctx->stream));
+        const uint32_t m = h[0];
+        if (m > cand_cap) { // pathological input (sync pattern everywhere): retry with the exact size
+            cand_cap = m;
+            continue;
+        }
+        if (m == 0) return OIP_OK;
+        // file order: scan the per-chunk counts (ChunkInfo.count is strided -> copy out first)
+        OIP_CUDA(cudaMemcpy2DAsync(S + o_cnt, 4, (uint8_t *)d_info + 4, sizeof(ChunkInfo), 4, (size_t)n_chunks,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+        rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_cnt), (uint32_t *)(S + o_base), n_chunks, (uint32_t *)(S + o_scan),
+                                d_total);
+        if (rc) return rc;
+        aos_order_kernel<<<(unsigned)((n_chunks * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            d_info, (uint32_t *)(S + o_base), n_chunks, (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst),
+            (uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost));
+        OIP_CUDA(cudaGetLastError());
+        const unsigned gb = (unsigned)((m + 255) / 256);
+        aos_runstart_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), m, S + o_rs);
+        OIP_CUDA(cudaGetLastError());
+        aos_walk_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), S + o_rs, m,
+                                                     (uint32_t *)(S + o_acc), d_counters);
+        OIP_CUDA(cudaGetLastError());
+        ctx->launches += 3;
+        rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_acc), (uint32_t *)(S + o_rank), m, (uint32_t *)(S + o_scan),
+                                d_acc_total);
+        if (rc) return rc;
+        if (d_payload_off) {
+            aos_emit_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (uint32_t *)(S + o_acc),
+                                                         (uint32_t *)(S + o_rank), m, d_payload_off, (uint64_t)cap);
+            OIP_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
+        unsigned long long *hc = (unsigned long long *)ctx->h_pinned;
+        OIP_CUDA(cudaMemcpyAsync(hc, d_counters, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        OIP_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (counters) { counters[0] = (int64_t)hc[0]; counters[1] = (int64_t)hc[1]; counters[2] = (int64_t)hc[2]; }
+        if (d_payload_off && hc[0] > cap) return fail(OIP_E_INVALID, "oip_aos_scan: %llu valid frames exceed capacity %zu", hc[0], cap);
+        return OIP_OK;
+    }
+    return fail(OIP_E_NOMEM, "oip_aos_scan: candidate table overflow");
+}
+
+extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_payload_off, int64_t n_payload,
+                                uint8_t *d_imdt, size_t cap, int64_t stats[9], int64_t *imdt_bytes)
+{
+    OIP_CHECK_CTX(ctx);
+    if (stats) { for (int i = 0; i < 9; ++i) stats[i] = 0; stats[7] = -1; }
+    if (imdt_bytes) *imdt_bytes = 0;
+    if (n_payload < 0) return fail(OIP_E_INVALID, "oip_imtr_deframe: n_payload < 0");
+    const int64_t nf = n_payload * 880 / 882; // frames cut by the cadence (ref :487-510)
+    if (nf == 0) return OIP_OK;
+    if (!d_buf || !d_payload_off || !d_imdt) return fail(OIP_E_INVALID, "oip_imtr_deframe: null pointer");
+    if (nf > 0x7fffffff) return fail(OIP_E_INVALID, "oip_imtr_deframe: too many frames for one call");
+    static const CrcPlan plan = make_crc_plan(876);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    const size_t o_hdr = take(64); // restart_last | n_restarts | n_gaps (u64 each) | total(u32) | first_chid(i32)
+    const size_t o_status = take((size_t)nf);
+    const size_t o_chid = take((size_t)nf);
+    const size_t o_seq = take((size_t)nf * 4);
+    const size_t o_valid = take((size_t)nf * 4);
+    const size_t o_rank = take((size_t)nf * 4);
+    const size_t o_seqc = take((size_t)nf * 4);
+    const size_t o_scan = take(scan_scratch_elems(nf) * 4);
+    int rc = ensure_scratch(ctx, o);
+    if (rc) return rc;
+    uint8_t *S = (uint8_t *)ctx->d_scratch;
+    unsigned long long *d_hdr = (unsigned long long *)(S + o_hdr);
+    uint32_t *d_total = (uint32_t *)(S + o_hdr + 24);
+    int *d_first_chid = (int *)(S + o_hdr + 28);
+    OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 64, ctx->stream));
+    OIP_CUDA(cudaMemsetAsync(d_first_chid, 0xFF, 4, ctx->stream));
+    imtr_validate_kernel<<<(unsigned)((nf + IMTR_WARPS - 1) / IMTR_WARPS), IMTR_WARPS * 32, 0, ctx->stream>>>(
+        d_buf, d_payload_off, nf, plan, S + o_status, (uint32_t *)(S + o_seq), S + o_chid, (uint32_t *)(S + o_valid));
+    OIP_CUDA(cudaGetLastError());
+    ctx->launches++;
+    rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank), nf, (uint32_t *)(S + o_scan), d_total);
+    if (rc) return rc;
+    const unsigned gb = (unsigned)((nf + 255) / 256);
+    imtr_compact_seq_kernel<<<gb, 256, 0, ctx->stream>>>((uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank),
+                                                         (uint32_t *)(S + o_seq), nf, (uint32_t *)(S + o_seqc));
+    OIP_CUDA(cudaGetLastError());
+    ctx->launches++;
+    rc = ensure_pinned(ctx, 64 + (size_t)nf);
+    if (rc) return rc;
+    uint8_t *hp = (uint8_t *)ctx->h_pinned;
+    OIP_CUDA(cudaMemcpyAsync(hp, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    OIP_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t n_valid = *(uint32_t *)hp;
+    if (n_valid) {
+        imtr_rules_kernel<<<(n_valid + 255) / 256, 256, 0, ctx->stream>>>((uint32_t *)(S + o_seqc), n_valid, d_hdr, d_hdr + 1,
+                                                                         d_hdr + 2);
+        OIP_CUDA(cudaGetLastError());
+        imtr_copy_kernel<<<(unsigned)((nf * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            d_buf, d_payload_off, nf, (uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank), d_hdr, S + o_chid, d_imdt,
+            (uint64_t)cap, d_first_chid);
+        OIP_CUDA(cudaGetLastError());
+        ctx->launches += 2;
+    }
+    OIP_CUDA(cudaMemcpyAsync(hp, S + o_hdr, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    OIP_CUDA(cudaMemcpyAsync(hp + 64, S + o_status, (size_t)nf, cudaMemcpyDeviceToHost, ctx->stream));
+    OIP_CUDA(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long *hh = (const unsigned long long *)hp;
+    int64_t bad[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = 0; i < nf; ++i) bad[hp[64 + i] < 5 ? hp[64 + i] : 0]++;
+    const int64_t out_frames = n_valid ? (int64_t)n_valid - (int64_t)hh[0] : 0;
+    if ((uint64_t)out_frames * 866 > cap) return fail(OIP_E_INVALID, "oip_imtr_deframe: output capacity %zu too small", cap);
+    if (stats) {
+        stats[0] = nf; stats[1] = n_valid; stats[2] = bad[1]; stats[3] = bad[2]; stats[4] = bad[3]; stats[5] = bad[4];
+        stats[6] = (int64_t)hh[2]; stats[7] = n_valid ? *(int *)(hp + 28) : -1; stats[8] = (int64_t)hh[1];
+    }
+    if (imdt_bytes) *imdt_bytes = out_frames * 866;
+    return OIP_OK;
+}
+
+extern "C" int oip_image_frames_index(oip_ctx *ctx, const uint8_t *d_imdt, size_t n_bytes, const oip_frame_geom *geom,
+                                      oip_frame_entry *entries, int64_t cap, int64_t stats[4])
+{
+    OIP_CHECK_CTX(ctx);
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (!geom || geom->tile_cols < 1 || geom->tile_lines < 1) return fail(OIP_E_INVALID, "oip_image_frames_index: bad geometry");
+    if (!d_imdt && n_bytes) return fail(OIP_E_INVALID, "oip_image_frames_index: null buffer");
+    const int64_t n = (int64_t)n_bytes;
+    const int64_t aux_all = 192 * (int64_t)geom->tile_lines;            // IMGSIG_AUX_ALLBYTES
+    const int64_t tile_bytes = (int64_t)geom->tile_lines * geom->tile_cols * 2;
+    if (n <= aux_all + 172) return OIP_OK;                               // ref :630
+    // ---- device: all occurrences of EB 90 E1 4D
+    uint32_t hit_cap = (uint32_t)std::min<int64_t>(n / 4 + 1, std::max<int64_t>(4096, n / 65536));
+    std::vector<unsigned long long> hits;
+    std::vector<uint8_t> trailers;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t o = 0;
+        auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+        const size_t o_n = take(16), o_hits = take((size_t)hit_cap * 8), o_tr = take((size_t)hit_cap * 172);
+        int rc = ensure_scratch(ctx, o);
+        if (rc) return rc;
+        uint8_t *S = (uint8_t *)ctx->d_scratch;
+        OIP_CUDA(cudaMemsetAsync(S + o_n, 0, 16, ctx->stream));
+        const int blocks = (int)std::min<int64_t>((n / 16 + 255) / 256 + 1, (int64_t)ctx->sm_count * 16);
+        find_sig4_kernel<<<blocks, 256, 0, ctx->stream>>>(d_imdt, n, 0x4DE190EBu, 0xEB, (unsigned long long *)(S + o_hits),
+                                                         hit_cap, (uint32_t *)(S + o_n));
+        OIP_CUDA(cudaGetLastError());
+        ctx->launches++;
+        uint32_t nh = 0;
+        OIP_CUDA(cudaMemcpyAsync(&nh, S + o_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        OIP_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (nh > hit_cap) { hit_cap = nh; continue; }
+        hits.resize(nh);
+        trailers.resize((size_t)nh * 172);
+        if (nh) {
+            gather_trailers_kernel<<<nh, 64, 0, ctx->stream>>>(d_imdt, n, (unsigned long long *)(S + o_hits), nh, S + o_tr);
+            OIP_CUDA(cudaGetLastError());
+            ctx->launches++;
+            OIP_CUDA(cudaMemcpyAsync(hits.data(), S + o_hits, (size_t)nh * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            OIP_CUDA(cudaMemcpyAsync(trailers.data(), S + o_tr, (size_t)nh * 172, cudaMemcpyDeviceToHost, ctx->stream));
+            OIP_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        break;
+    }
+    // order by offset (atomics give arbitrary order)
+    std::vector<uint32_t> order(hits.size());
+    for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hits[a] < hits[b]; });
+
+    // ---- host: NextImageDataFrame chain + gap rules (ref :627-656, :287-320); only trailers are needed
+    auto be32 = [](const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; };
+    int64_t p = 0, remain = n, emitted = 0, found = 0, incomplete = 0;
+    int last_seq = 0;
+    size_t hi = 0;
+    for (;;) {
+        if (remain <= aux_all + 172) break;                              // :630
+        while (hi < order.size() && (int64_t)hits[order[hi]] < p) ++hi;   // memmem from p
+        if (hi >= order.size()) break;
+        const int64_t sp = (int64_t)hits[order[hi]];
+        if (sp + 172 > n) break; // the reference would parse past the mapping
+        const uint8_t *t = trailers.data() + (size_t)order[hi] * 172;
+        const int64_t frame_end = sp + 172;                              // :634
+        const int z_ratio = t[4] & 0x3F;                                 // :639
+        const int seq = (int)(((uint32_t)t[6] << 8) | t[7]);            // :642-643
+        const uint32_t image_dwords = be32(t + 8);                       // :645-646
+        const int data_bytes = (int)(uint32_t)((uint64_t)image_dwords * 4u + (uint64_t)aux_all); // :653
+        if (sp - p < (int64_t)data_bytes) {                              // :654, :289-299
+            incomplete++;
+            remain -= frame_end - p;
+            p = frame_end;
+            continue;
+        }
+        if (data_bytes < 0) return fail(OIP_E_RANGE, "image frame #%d: trailer length field out of range", seq);
+        const int64_t frame = sp - data_bytes;                           // :655
+        found++;
+        if (z_ratio != 0)
+            return fail(OIP_E_UNSUPPORTED, "image frame #%d is JPEG-2000 compressed (z_ratio 0x%02X): not supported", seq, z_ratio);
+        if (seq > last_seq + 1) {                                        // :302-311
+            for (int i = 0; i < seq - last_seq - 1; ++i) {
+                if (emitted < cap && entries) {
+                    oip_frame_entry &e = entries[emitted];
+                    e.frame_off = -1;
+                    for (int k = 0; k < 40; ++k) e.tile_off[k] = -1;
+                    e.seq = last_seq + 1 + i;
+                    e.z_ratio = 0;
+                }
+                emitted++;
+            }
+        }
+        if (emitted < cap && entries) {
+            oip_frame_entry &e = entries[emitted];
+            e.frame_off = frame;
+            e.seq = seq;
+            e.z_ratio = z_ratio;
+            int64_t q = frame + aux_all;
+            for (int k = 0; k < 40; ++k) {                               // :347-356
+                if (q + tile_bytes > n) return fail(OIP_E_RANGE, "image frame #%d: sub-image %d leaves the buffer", seq, k);
+                e.tile_off[k] = q;
+                q += (int64_t)be32(t + 12 + 4 * k) * 4;
+            }
+        }
+        emitted++;
+        remain -= frame_end - p;                                         // :315-317
+        p = frame_end;
+        last_seq = seq;
+    }
+    if (stats) { stats[0] = found; stats[1] = emitted; stats[2] = incomplete; stats[3] = last_seq; }
+    if (entries && emitted > cap) return fail(OIP_E_INVALID, "oip_image_frames_index: %lld frames exceed capacity %lld", (long long)emitted, (long long)cap);
+    return OIP_OK;
+}
+
+extern "C" int oip_unpack_frames(oip_ctx *ctx, const uint8_t *d_imdt, size_t n_bytes, const oip_frame_geom *geom,
+                                 const oip_frame_entry *entries, int64_t n_frames, uint8_t *d_aux, uint16_t *d_pan,
+                                 uint16_t *d_mss)
+{
+    OIP_CHECK_CTX(ctx);
+    if (!geom || geom->tile_cols < 1 || geom->tile_lines < 1) return fail(OIP_E_INVALID, "oip_unpack_frames: bad geometry");
+    if (n_frames < 0 || (n_frames && !entries)) return fail(OIP_E_INVALID, "oip_unpack_frames: bad entries");
+    if (n_frames == 0) return OIP_OK;
+    if (n_frames > 0x7fffffff) return fail(OIP_E_INVALID, "oip_unpack_frames: too many frames");
+    const int64_t tile_bytes = (int64_t)geom->tile_lines * geom->tile_cols * 2;
+    const int64_t aux_all = 192 * (int64_t)geom->tile_lines;
+    const size_t tab_bytes = (size_t)n_frames * 41 * 8;
+    int rc = ensure_pinned(ctx, tab_bytes);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx, tab_bytes);
+    if (rc) return rc;
+    OIP_CUDA(cudaStreamSynchronize(ctx->stream));
+    int64_t *tab = (int64_t *)ctx->h_pinned;
+    for (int64_t f = 0; f < n_frames; ++f) {
+        const oip_frame_entry &e = entries[f];
+        if (e.frame_off >= 0) {
+            if (e.z_ratio != 0) return fail(OIP_E_UNSUPPORTED, "frame %lld is compressed", (long long)f);
+            if (e.frame_off + aux_all > (int64_t)n_bytes) return fail(OIP_E_RANGE, "frame %lld aux block leaves the buffer", (long long)f);
+            for (int k = 0; k < 40; ++k)
+                if (e.tile_off[k] < 0 || e.tile_off[k] + tile_bytes > (int64_t)n_bytes)
+                    return fail(OIP_E_RANGE, "frame %lld sub-image %d leaves the buffer", (long long)f, k);
+        }
+        tab[f * 41] = e.frame_off;
+        for (int k = 0; k < 40; ++k) tab[f * 41 + 1 + k] = e.tile_off[k];
+    }
+    OIP_CUDA(cudaMemcpyAsync(ctx->d_scratch, tab, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    UnpackParams P{};
+    P.imdt = d_imdt; P.tab = (const int64_t *)ctx->d_scratch; P.aux = d_aux; P.pan = d_pan; P.mss = d_mss;
+    P.tile_cols = geom->tile_cols; P.tile_lines = geom->tile_lines; P.n_frames = n_frames;
+    unpack_frames_kernel<<<dim3((unsigned)n_frames, 41), 256, 0, ctx->stream>>>(P);
+    OIP_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return OIP_OK;
+}

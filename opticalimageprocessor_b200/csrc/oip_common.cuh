@@ -25,6 +25,7 @@ struct oip_ctx {
     size_t d_mss_plan_cap = 0;
     std::vector<uint8_t> mss_plan_key;
     int64_t mss_plan_tiles = 0;
+    int64_t mss_plan_rows = 0;
     // scratch for stage 1 (grown on demand)
     void *d_scratch = nullptr;
     size_t d_scratch_cap = 0;
@@ -129,11 +130,25 @@ __device__ __forceinline__ uint32_t crc16_byte(uint32_t crc, uint32_t byte)
 
 // (uint16_t)(k*s + b) exactly as the reference's x86 build evaluates it (ref imageop.h:134;
 // cvtsi2sd, mulsd, addsd, cvttsd2si(32-bit), low 16 bits).  No FMA contraction.
+// The conversion pipe (I2F/F2I .F64) issues at 16 lanes/clk/SM on B200 against 64 for DADD/DMUL
+// (tools/pipe_rates.cu), so both conversions are done with exact magic-number adds instead:
+//   u16 -> f64 : (2^52 | s) - 2^52                      (exact, one DADD)
+//   trunc      : low word of RZ(v + 2^52) for 0 <= v < 2^31 (exact, one DADD.RZ); anything else
+//                takes the generic path (negative, >= 2^31, NaN: rare, input-contract territory)
 __device__ __forceinline__ uint32_t rrc_px(uint32_t s, double k, double b)
 {
-    double v = __dadd_rn(__dmul_rn(k, (double)s), b);
+    const double sd = __dadd_rn(__hiloint2double(0x43300000, (int)s), -4503599627370496.0);
+    const double v = __dadd_rn(__dmul_rn(k, sd), b);
+    const uint32_t hi = (uint32_t)__double2hiint(v);
+    if (hi < 0x41E00000u) // sign clear and exponent < 1023+31  <=>  0 <= v < 2^31
+        return (uint32_t)__double2loint(__dadd_rz(v, 4503599627370496.0)) & 0xFFFFu;
     int t = (v > -2147483649.0 && v < 2147483648.0) ? __double2int_rz(v) : (int)0x80000000;
     return (uint32_t)t & 0xFFFFu;
+}
+// exact u16 -> f32 without the conversion pipe
+__device__ __forceinline__ float u16_to_f32(uint32_t v)
+{
+    return __fadd_rn(__uint_as_float(0x4B000000u | v), -8388608.0f);
 }
 #endif
 

@@ -331,8 +331,8 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
                 if (remap) {
                     int slot = (int)(t - t_base) % RING;
                     float2 o;
-                    o.x = (v0ok && !z) ? (float)a : 0.f;
-                    o.y = (v1ok && !z) ? (float)b : 0.f;
+                    o.x = (v0ok && !z) ? u16_to_f32(a) : 0.f;
+                    o.y = (v1ok && !z) ? u16_to_f32(b) : 0.f;
                     reinterpret_cast<float2 *>(ring)[(size_t)slot * (SWC / 2) + p] = o;
                 } else if (!z) {
                     uint16_t *orow = P.out + (t - P.out_row0) * P.out_pitch + T.out_x;

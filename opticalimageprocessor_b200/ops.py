@@ -38,7 +38,7 @@ class Context:
         stream = None
         if use_torch_stream:
             stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        check(self.lib.oip_ctx_create(device, stream, C.byref(h)))
+        check(self.lib.oip_ctx_create(device, stream, 0 if use_torch_stream else 1, C.byref(h)))
         self.h = h
 
     def close(self):
@@ -242,10 +242,11 @@ def imtr_deframe(ctx: Context, buf: torch.Tensor, payload_off: torch.Tensor):
 
 def image_frames_index(ctx: Context, imdt: torch.Tensor, tile_cols: int, tile_lines: int):
     g = FrameGeom(tile_cols, tile_lines)
-    frame_bytes = 192 * tile_lines + 40 * tile_cols * tile_lines * 2 + 172
-    cap = max(16, 4 * (imdt.numel() // max(frame_bytes, 1) + 2) + 70000)
-    ents = (FrameEntry * cap)()
     st = (C.c_int64 * 4)()
+    # first pass counts the emitted frames (gap frames included), second fills the table
+    check(ctx.lib.oip_image_frames_index(ctx.h, imdt.data_ptr(), imdt.numel(), C.byref(g), None, 0, st))
+    cap = max(1, int(st[1]))
+    ents = (FrameEntry * cap)()
     check(ctx.lib.oip_image_frames_index(ctx.h, imdt.data_ptr(), imdt.numel(), C.byref(g), ents, cap, st))
     return ents, np.array(list(st), np.int64)
 

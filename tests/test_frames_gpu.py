@@ -1,0 +1,228 @@
+"""GPU parity, stage 1 (frame handling): CUDA path vs the CPU oracle.  Bit-exact (integer work)."""
+import numpy as np
+import pytest
+import torch
+
+from opticalimageprocessor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _downlink(seed=3, n_frames=3, tc=16, tl=4, skip=()):
+    imdt, truth = synth.make_imdt(n_frames, tc, tl, seed=seed, skip_seqs=skip)
+    imtr = synth.imtr_frames(imdt, chid=0x22)
+    aos = synth.aos_frames(imtr.reshape(-1))
+    return imdt, truth, imtr, aos
+
+
+@pytest.mark.parametrize("length", [0, 1, 5, 31, 32, 33, 876, 890, 1000])
+def test_crc16_batch(ctx, oracle_mod, length):
+    from opticalimageprocessor_b200 import ops
+    rng = np.random.default_rng(length)
+    buf = rng.integers(0, 256, 8192, dtype=np.uint8)
+    off = rng.integers(0, 8192 - max(length, 1), 77).astype(np.int64)
+    got = ops.crc16_batch(ctx, _dev(buf), _dev(off), length).cpu().numpy()
+    want = np.array([oracle_mod.crc16(buf[o:o + length]) for o in off], np.uint16)
+    assert np.array_equal(got, want)
+
+
+def _check_aos(ctx, oracle_mod, buf):
+    from opticalimageprocessor_b200 import ops
+    off_w, cnt_w = oracle_mod.aos_scan(buf)
+    off_g, cnt_g = ops.aos_scan(ctx, _dev(buf))
+    assert cnt_g.tolist() == cnt_w.tolist()
+    assert np.array_equal(off_g.cpu().numpy().astype(np.uint64), off_w)
+    return off_w
+
+
+def test_aos_scan_with_anomalies(ctx, oracle_mod):
+    imdt, truth, imtr, aos = _downlink(n_frames=5)
+    buf = synth.build_aos_file(aos, empty_every=5, bad_crc_at={2, 7, 40}, bad_inject_at={4, 33},
+                               prefix=b"\x00\x11\x22" * 7, suffix=synth.AOS_SYNC + b"\x01" * 300)
+    _check_aos(ctx, oracle_mod, buf)
+
+
+def test_aos_scan_false_syncs(ctx, oracle_mod):
+    """false sync words inside payloads (shadowed), inside a rejected frame (visited), overlapping frames"""
+    imdt, truth, imtr, aos = _downlink(n_frames=4)
+    aos = aos.copy()
+    rng = np.random.default_rng(5)
+    for i in rng.choice(aos.shape[0], 12, replace=False):
+        p = int(rng.integers(20, 880))
+        aos[i, p:p + 4] = np.frombuffer(synth.AOS_SYNC, np.uint8)
+    crc = synth.crc16_rows(aos[:, 4:894])
+    aos[:, 894], aos[:, 895] = crc >> 8, crc & 0xFF
+    bad = aos.copy()
+    bad[5, 700] ^= 1   # CRC failure on frames that also contain a false sync
+    bad[9, 20] ^= 1
+    _check_aos(ctx, oracle_mod, aos.reshape(-1))
+    _check_aos(ctx, oracle_mod, bad.reshape(-1))
+    # two VALID frames overlapping by less than 1024 bytes: only the first is accepted
+    f = aos[3].copy()
+    emb = np.concatenate([aos[0][:300], f, aos[1]])
+    _check_aos(ctx, oracle_mod, emb)
+    # sync words every 4 bytes (candidate table overflow path)
+    storm = np.tile(np.frombuffer(synth.AOS_SYNC, np.uint8), 3000)
+    _check_aos(ctx, oracle_mod, np.concatenate([storm, aos[:8].reshape(-1), storm]))
+
+
+@pytest.mark.parametrize("n", [0, 1023, 1024, 1025, 16384, 16384 + 1024, 3 * 16384 - 5])
+def test_aos_scan_sizes_and_chunk_boundaries(ctx, oracle_mod, n):
+    imdt, truth, imtr, aos = _downlink(n_frames=2)
+    buf = np.concatenate([np.zeros(7, np.uint8), aos.reshape(-1)])[:n]  # frames straddle the 16 KiB chunks
+    _check_aos(ctx, oracle_mod, buf)
+
+
+def test_imtr_deframe(ctx, oracle_mod):
+    from opticalimageprocessor_b200 import ops
+    imdt, truth, imtr, aos = _downlink(n_frames=4)
+    imtr = imtr.copy()
+    imtr[1, 0] ^= 0xFF
+    imtr[2, 880] ^= 0xFF
+    imtr[3, 9] = 0x11
+    synth.refresh_imtr_crc(imtr[3:4])
+    imtr[4, 300] ^= 0x01
+    imtr[20, 4:8] = 0          # seq 0 -> restart rule
+    synth.refresh_imtr_crc(imtr[20:21])
+    buf = synth.build_aos_file(synth.aos_frames(imtr.reshape(-1)), empty_every=9)
+    off = _check_aos(ctx, oracle_mod, buf)
+    want, st_w = oracle_mod.imtr_deframe(buf, off)
+    got, st_g = ops.imtr_deframe(ctx, _dev(buf), _dev(off.astype(np.int64)))
+    assert st_g.tolist() == st_w.tolist()
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_imtr_deframe_clean_stream(ctx, oracle_mod):
+    from opticalimageprocessor_b200 import ops
+    imdt, truth, imtr, aos = _downlink(n_frames=6, seed=8)
+    buf = aos.reshape(-1)
+    off, _ = oracle_mod.aos_scan(buf)
+    want, st_w = oracle_mod.imtr_deframe(buf, off)
+    got, st_g = ops.imtr_deframe(ctx, _dev(buf), _dev(off.astype(np.int64)))
+    assert st_g.tolist() == st_w.tolist() and st_w[1] == st_w[0]
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(want[:imdt.size], imdt)
+
+
+@pytest.mark.parametrize("tc,tl,skip,junk", [(16, 4, (), 0), (16, 4, {3}, 0), (24, 2, {2, 3}, 333), (1536, 1, (), 0)])
+def test_image_frames_index_and_unpack(ctx, oracle_mod, tc, tl, skip, junk):
+    from opticalimageprocessor_b200 import ops
+    imdt, truth = synth.make_imdt(5, tc, tl, seed=10, skip_seqs=skip, junk_prefix=junk)
+    n_w, aux_w, pan_w, mss_w, st_w = oracle_mod.image_frames(imdt, tc, tl)
+    d = _dev(imdt)
+    ents, st_g = ops.image_frames_index(ctx, d, tc, tl)
+    assert st_g.tolist() == st_w.tolist()
+    aux, pan, mss = ops.unpack_frames(ctx, d, tc, tl, ents, int(st_g[1]))
+    ctx.sync()
+    assert np.array_equal(aux.cpu().numpy(), aux_w)
+    assert np.array_equal(pan.cpu().numpy(), pan_w)
+    assert np.array_equal(mss.cpu().numpy(), mss_w)
+
+
+def test_image_frames_incomplete_and_false_signature(ctx, oracle_mod):
+    from opticalimageprocessor_b200 import ops
+    tc, tl = 16, 4
+    imdt, truth = synth.make_imdt(4, tc, tl, seed=9)
+    frame_bytes = 192 * tl + 40 * tc * tl * 2 + 172
+    for variant in range(3):
+        buf = imdt.copy()
+        if variant == 0:
+            buf = buf[100:]
+        elif variant == 1:
+            pos = frame_bytes + 192 * tl + 64
+            buf[pos:pos + 4] = np.frombuffer(synth.IMG_SIG, np.uint8)
+        else:
+            buf = buf[:-50]  # last trailer cut
+        n_w, aux_w, pan_w, mss_w, st_w = oracle_mod.image_frames(buf, tc, tl)
+        d = _dev(buf)
+        ents, st_g = ops.image_frames_index(ctx, d, tc, tl)
+        assert st_g.tolist() == st_w.tolist(), variant
+        aux, pan, mss = ops.unpack_frames(ctx, d, tc, tl, ents, int(st_g[1]))
+        ctx.sync()
+        assert np.array_equal(pan.cpu().numpy(), pan_w) and np.array_equal(aux.cpu().numpy(), aux_w)
+        assert np.array_equal(mss.cpu().numpy(), mss_w)
+
+
+def test_full_downlink_to_raw(ctx, oracle_mod):
+    """AOS file -> payloads -> IMDT -> frames -> PAN/MSS/AUX, reference geometry tile width, vs ground truth"""
+    from opticalimageprocessor_b200 import ops
+    tc, tl = 1536, 2
+    imdt, truth = synth.make_imdt(3, tc, tl, seed=12, skip_seqs={2})
+    imtr = synth.imtr_frames(imdt, chid=0x11)
+    aos = synth.aos_frames(imtr.reshape(-1))
+    buf = synth.build_aos_file(aos, empty_every=64, bad_crc_at={10, 500})
+    d = _dev(buf)
+    off, cnt = ops.aos_scan(ctx, d)
+    assert cnt.tolist() == [aos.shape[0], 2, len(range(0, aos.shape[0], 64))]
+    got_imdt, st = ops.imtr_deframe(ctx, d, off)
+    assert st[7] == 0x11
+    ents, fst = ops.image_frames_index(ctx, got_imdt, tc, tl)
+    assert fst.tolist() == [2, 3, 0, 3]
+    aux, pan, mss = ops.unpack_frames(ctx, got_imdt, tc, tl, ents, 3)
+    ctx.sync()
+    pan, mss, aux = pan.cpu().numpy(), mss.cpu().numpy(), aux.cpu().numpy()
+    for s in (1, 3):
+        a, p, m = truth[s]
+        assert np.array_equal(pan[(s - 1) * 4 * tl:s * 4 * tl], p)
+        assert np.array_equal(mss[(s - 1) * tl:s * tl], m) and np.array_equal(aux[s - 1], a)
+    assert not pan[4 * tl:8 * tl].any()
+
+
+def test_fused_pipeline_from_frame_tiles(ctx, oracle_mod):
+    """raw image frames (BE16 sub-image layout inside the IMDT stream) straight into the fused PAN kernel"""
+    import ctypes as C
+    from opticalimageprocessor_b200 import capi, ops
+    tc, tl, n_fr, f = 64, 8, 6, 10
+    W = 8 * tc
+    streams, pans, tabs = [], [], []
+    for i in range(2):
+        imdt, truth = synth.make_imdt(n_fr, tc, tl, seed=30 + i, junk_prefix=3 * i)
+        d = _dev(imdt)
+        ents, st = ops.image_frames_index(ctx, d, tc, tl)
+        assert st[1] == n_fr
+        tab = np.array([[ents[k].tile_off[j] for j in range(40)] for k in range(n_fr)], np.int64)
+        streams.append(d)
+        tabs.append(_dev(tab))
+        pans.append(np.concatenate([truth[s][1] for s in range(1, n_fr + 1)]))
+    rows = n_fr * 4 * tl
+    rng = np.random.default_rng(1)
+    kbs = [synth.rrc_coeffs(W, 77 + i) for i in range(2)]
+    want = oracle_mod.pan_pipeline(pans, kbs, [0, 1.37], [0, -2.61], f)
+    out = torch.empty((rows, ops.pan_out_width(2, W, f)), dtype=torch.uint16, device="cuda")
+    d = capi.PanDesc()
+    d.n_ccd, d.w, d.total_rows, d.row0, d.n_rows = 2, W, rows, 0, rows
+    d.fold_half, d.section_rows, d.row_guard = f, 30000, 32767
+    keep = []
+    for i in range(2):
+        c = d.ccd[i]
+        c.fmt, c.n_seg = capi.FMT_BE16_TILES, 1
+        c.seg[0] = capi.RowSeg(streams[i].data_ptr(), 0, rows, 0)
+        kb = _dev(kbs[i])
+        keep.append(kb)
+        c.d_kb, c.shifted, c.dX, c.dY = kb.data_ptr(), int(i > 0), [0, 1.37][i], [0, -2.61][i]
+        c.d_tile_off, c.tile_cols, c.tile_lines = tabs[i].data_ptr(), tc, tl
+    d.d_out, d.out_pitch_px = out.data_ptr(), out.stride(0)
+    capi.check(ctx.lib.oip_pan_pipeline(ctx.h, C.byref(d)))
+    capi.check(ctx.lib.oip_pan_check_error(ctx.h))
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("bits", [10, 12])
+def test_packed_lines_extension(ctx, oracle_mod, bits):
+    from opticalimageprocessor_b200 import ops
+    rng = np.random.default_rng(bits)
+    w, rows, f = 512, 200, 10
+    imgs = [rng.integers(0, 1 << bits, (rows, w), dtype=np.uint16) for _ in range(2)]
+    raws = [synth.pack_bits(im, bits) for im in imgs]
+    fmt = ops.FMT_PACK12 if bits == 12 else ops.FMT_PACK10
+    for im, raw in zip(imgs, raws):
+        assert np.array_equal(oracle_mod.unpack_bits(raw, bits, w, rows, raw.shape[1]), im)
+        assert np.array_equal(ops.unpack_lines(ctx, _dev(raw), fmt, w).cpu().numpy(), im)
+    kbs = [synth.rrc_coeffs(w, 5 + i) for i in range(2)]
+    want = oracle_mod.pan_pipeline(imgs, kbs, [0, -0.83], [0, 3.19], f)
+    got = ops.pan_pipeline(ctx, [_dev(r) for r in raws], [_dev(k) for k in kbs], [0, -0.83], [0, 3.19], f, fmt=fmt, w=w)
+    assert np.array_equal(got.cpu().numpy(), want)
