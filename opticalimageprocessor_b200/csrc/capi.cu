@@ -105,6 +105,7 @@ void oip_ctx_destroy(oip_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    oip::host_pipe_destroy(ctx);
     if (ctx->d_plan) cudaFree(ctx->d_plan);
     if (ctx->d_mss_plan) cudaFree(ctx->d_mss_plan);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);

@@ -1,0 +1,185 @@
+// host_pipeline.cu -- oip_pan_pipeline_host: the fused PAN path for HOST buffers.
+// The strip is cut into row blocks; block b+1's source rows (plus the few halo / stale rows the
+// shift needs) travel host->device on a copy stream while block b runs on the compute stream and
+// block b-1's output travels device->host on a third stream (pinned buffers make all three
+// overlap).  This is what the CLI uses for files and what bench.py reports as "e2e".
+#include <algorithm>
+
+#include "oip_common.cuh"
+
+namespace oip {
+
+constexpr int HP_SLOTS = 3;
+constexpr int64_t HP_BLOCK_ROWS = 2048;
+
+struct HostPipe {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    struct Slot {
+        void *d_in[8] = {};
+        size_t in_cap[8] = {};
+        void *d_out = nullptr;
+        size_t out_cap = 0;
+        cudaEvent_t in_ready = nullptr, compute_done = nullptr, out_done = nullptr;
+    } slot[HP_SLOTS];
+    void *d_kb[8] = {};
+    size_t kb_cap[8] = {};
+};
+
+static int hp_get(oip_ctx *ctx, HostPipe **out)
+{
+    if (!ctx->host_pipe) {
+        HostPipe *hp = new (std::nothrow) HostPipe();
+        if (!hp) return fail(OIP_E_NOMEM, "out of host memory");
+        OIP_CUDA(cudaStreamCreateWithFlags(&hp->h2d, cudaStreamNonBlocking));
+        OIP_CUDA(cudaStreamCreateWithFlags(&hp->d2h, cudaStreamNonBlocking));
+        for (auto &s : hp->slot) {
+            OIP_CUDA(cudaEventCreateWithFlags(&s.in_ready, cudaEventDisableTiming));
+            OIP_CUDA(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
+            OIP_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+        }
+        ctx->host_pipe = hp;
+    }
+    *out = (HostPipe *)ctx->host_pipe;
+    return OIP_OK;
+}
+
+static int hp_reserve(void **p, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap) return OIP_OK;
+    if (*p) OIP_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    OIP_CUDA(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return OIP_OK;
+}
+
+void host_pipe_destroy(oip_ctx *ctx)
+{
+    HostPipe *hp = (HostPipe *)ctx->host_pipe;
+    if (!hp) return;
+    for (auto &s : hp->slot) {
+        for (int i = 0; i < 8; ++i)
+            if (s.d_in[i]) cudaFree(s.d_in[i]);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.in_ready) cudaEventDestroy(s.in_ready);
+        if (s.compute_done) cudaEventDestroy(s.compute_done);
+        if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    for (int i = 0; i < 8; ++i)
+        if (hp->d_kb[i]) cudaFree(hp->d_kb[i]);
+    if (hp->h2d) cudaStreamDestroy(hp->h2d);
+    if (hp->d2h) cudaStreamDestroy(hp->d2h);
+    delete hp;
+    ctx->host_pipe = nullptr;
+}
+
+static int64_t row_bytes(int fmt, int w)
+{
+    switch (fmt) {
+    case OIP_FMT_PACK12: return ((int64_t)w * 12 + 7) / 8;
+    case OIP_FMT_PACK10: return ((int64_t)w * 10 + 7) / 8;
+    default: return (int64_t)w * 2;
+    }
+}
+
+} // namespace oip
+
+using namespace oip;
+
+extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
+{
+    OIP_CHECK_CTX(ctx);
+    if (!h) return fail(OIP_E_INVALID, "null descriptor");
+    if (h->n_ccd < 1 || h->n_ccd > 8) return fail(OIP_E_INVALID, "n_ccd=%d out of range 1..8", h->n_ccd);
+    if (!h->d_out && h->n_rows > 0) return fail(OIP_E_INVALID, "output buffer is null");
+    for (int i = 0; i < h->n_ccd; ++i) {
+        if (h->ccd[i].fmt == OIP_FMT_BE16_TILES) return fail(OIP_E_UNSUPPORTED, "host pipeline takes line formats only");
+        if (h->ccd[i].n_seg != 1 || !h->ccd[i].seg[0].base) return fail(OIP_E_INVALID, "host pipeline needs exactly one host segment per CCD");
+    }
+    if (h->n_rows <= 0) return OIP_OK;
+    HostPipe *hp = nullptr;
+    int rc = hp_get(ctx, &hp);
+    if (rc) return rc;
+    const int out_w = oip_pan_out_width(h->n_ccd, h->w, h->fold_half);
+
+    // RRC coefficients: tiny, once per call, on the compute stream
+    const double *d_kb[8] = {};
+    for (int i = 0; i < h->n_ccd; ++i) {
+        if (!h->ccd[i].d_kb) continue;
+        const size_t bytes = (size_t)h->w * 16;
+        rc = hp_reserve(&hp->d_kb[i], &hp->kb_cap[i], bytes);
+        if (rc) return rc;
+        OIP_CUDA(cudaMemcpyAsync(hp->d_kb[i], h->ccd[i].d_kb, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_kb[i] = (const double *)hp->d_kb[i];
+    }
+
+    int blk = 0;
+    for (int64_t r0 = h->row0; r0 < h->row0 + h->n_rows; r0 += HP_BLOCK_ROWS, ++blk) {
+        const int64_t nr = std::min<int64_t>(HP_BLOCK_ROWS, h->row0 + h->n_rows - r0);
+        HostPipe::Slot &S = hp->slot[blk % HP_SLOTS];
+        oip_pan_desc d = *h;
+        d.row0 = r0;
+        d.n_rows = nr;
+        // ---- H2D of the rows this block reads (own rows + halo + stale-section rows)
+        OIP_CUDA(cudaStreamWaitEvent(hp->h2d, S.compute_done, 0)); // the slot's previous kernel is done with d_in
+        for (int i = 0; i < h->n_ccd; ++i) {
+            const oip_ccd_src &src = h->ccd[i];
+            int64_t first, last, sfirst, slast;
+            rc = oip_pan_rows_needed(&d, i, &first, &last, &sfirst, &slast);
+            if (rc) return rc;
+            const oip_row_seg &hs = src.seg[0];
+            first = std::max(first, hs.row0);
+            last = std::min(last, hs.row0 + hs.n_rows);
+            sfirst = std::max(sfirst, hs.row0);
+            slast = std::min(slast, hs.row0 + hs.n_rows);
+            const int64_t rb = row_bytes(src.fmt, h->w);
+            const int64_t pitch_d = (rb + 15) / 16 * 16;
+            const int64_t n_main = std::max<int64_t>(0, last - first), n_stale = std::max<int64_t>(0, slast - sfirst);
+            rc = hp_reserve(&S.d_in[i], &S.in_cap[i], (size_t)((HP_BLOCK_ROWS + 64 + n_stale) * pitch_d));
+            if (rc) return rc;
+            if ((size_t)((n_main + n_stale) * pitch_d) > S.in_cap[i]) {
+                rc = hp_reserve(&S.d_in[i], &S.in_cap[i], (size_t)((n_main + n_stale) * pitch_d));
+                if (rc) return rc;
+            }
+            uint8_t *dst = (uint8_t *)S.d_in[i];
+            oip_ccd_src &o = d.ccd[i];
+            o.d_kb = d_kb[i];
+            o.n_seg = 0;
+            if (n_main > 0) {
+                OIP_CUDA(cudaMemcpy2DAsync(dst, (size_t)pitch_d, (const uint8_t *)hs.base + (first - hs.row0) * hs.pitch_bytes,
+                                           (size_t)hs.pitch_bytes, (size_t)rb, (size_t)n_main, cudaMemcpyHostToDevice, hp->h2d));
+                o.seg[o.n_seg++] = {dst, first, n_main, pitch_d};
+            }
+            if (n_stale > 0) {
+                uint8_t *dst2 = dst + n_main * pitch_d;
+                OIP_CUDA(cudaMemcpy2DAsync(dst2, (size_t)pitch_d, (const uint8_t *)hs.base + (sfirst - hs.row0) * hs.pitch_bytes,
+                                           (size_t)hs.pitch_bytes, (size_t)rb, (size_t)n_stale, cudaMemcpyHostToDevice, hp->h2d));
+                o.seg[o.n_seg++] = {dst2, sfirst, n_stale, pitch_d};
+            }
+            if (o.n_seg == 0) { // nothing to read (can only happen for degenerate geometry): keep a valid segment
+                o.seg[0] = {dst, 0, 0, pitch_d};
+                o.n_seg = 1;
+            }
+        }
+        OIP_CUDA(cudaEventRecord(S.in_ready, hp->h2d));
+        // ---- compute
+        rc = hp_reserve(&S.d_out, &S.out_cap, (size_t)(HP_BLOCK_ROWS * out_w * 2));
+        if (rc) return rc;
+        OIP_CUDA(cudaStreamWaitEvent(ctx->stream, S.in_ready, 0));
+        OIP_CUDA(cudaStreamWaitEvent(ctx->stream, S.out_done, 0)); // previous D2H of this slot finished
+        d.d_out = (uint16_t *)S.d_out;
+        d.out_pitch_px = out_w;
+        rc = oip_pan_pipeline(ctx, &d);
+        if (rc) return rc;
+        OIP_CUDA(cudaEventRecord(S.compute_done, ctx->stream));
+        // ---- D2H
+        OIP_CUDA(cudaStreamWaitEvent(hp->d2h, S.compute_done, 0));
+        OIP_CUDA(cudaMemcpy2DAsync((uint8_t *)h->d_out + (r0 - h->row0) * h->out_pitch_px * 2, (size_t)h->out_pitch_px * 2,
+                                   S.d_out, (size_t)out_w * 2, (size_t)out_w * 2, (size_t)nr, cudaMemcpyDeviceToHost, hp->d2h));
+        OIP_CUDA(cudaEventRecord(S.out_done, hp->d2h));
+    }
+    OIP_CUDA(cudaStreamSynchronize(hp->d2h));
+    OIP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return oip_pan_check_error(ctx);
+}

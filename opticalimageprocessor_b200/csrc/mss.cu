@@ -307,10 +307,9 @@ extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_m
     P.out = d_out; P.err = ctx->d_err; P.fmt = d->fmt; P.wb = d->wb;
     P.vec_ok = (((uintptr_t)d_mss & 3) == 0 && (P.pitch_bytes & 3) == 0 && (d->wb % 2) == 0) ? 1 : 0;
     const size_t smem = (size_t)mss::RING * mss::SWC * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->mss_attr_set) {
         OIP_CUDA(cudaFuncSetAttribute(mss::band_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->mss_attr_set = true;
     }
     mss::band_align_kernel<<<(unsigned)ctx->mss_plan_tiles, mss::NT, smem, ctx->stream>>>(P);
     OIP_CUDA(cudaGetLastError());

@@ -32,6 +32,9 @@ struct oip_ctx {
     void *h_pinned = nullptr; // small pinned staging for counters / plans
     size_t h_pinned_cap = 0;
     int *d_err = nullptr;     // device-side error flag
+    bool pan_attr_set = false, mss_attr_set = false;
+    // host-buffer pipeline (oip_pan_pipeline_host): staging slots + side streams
+    void *host_pipe = nullptr;
 };
 
 namespace oip {
@@ -55,6 +58,7 @@ int fail(int code, const char *fmt, ...);
 
 int ensure_scratch(oip_ctx *ctx, size_t bytes);
 int ensure_pinned(oip_ctx *ctx, size_t bytes);
+void host_pipe_destroy(oip_ctx *ctx);
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

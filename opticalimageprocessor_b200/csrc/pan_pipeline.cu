@@ -588,12 +588,12 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
             OIP_CUDA(cudaMalloc(&ctx->d_plan, bytes * 2));
             ctx->d_plan_cap = bytes * 2;
         }
-        rc = ensure_pinned(ctx, bytes);
-        if (rc) return rc;
-        OIP_CUDA(cudaStreamSynchronize(ctx->stream)); // pinned staging may still be in flight
-        memcpy(ctx->h_pinned, pan::g_tab_host, 512);
-        memcpy((uint8_t *)ctx->h_pinned + 512, tiles.data(), tiles.size() * sizeof(pan::Tile));
-        OIP_CUDA(cudaMemcpyAsync(ctx->d_plan, ctx->h_pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        // pageable sources: cudaMemcpyAsync stages them before returning, and the copies are ordered
+        // on the compute stream behind any kernel still reading the previous plan
+        OIP_CUDA(cudaMemcpyAsync(ctx->d_plan, pan::g_tab_host, 512, cudaMemcpyHostToDevice, ctx->stream));
+        if (!tiles.empty())
+            OIP_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_plan + 512, tiles.data(), tiles.size() * sizeof(pan::Tile),
+                                     cudaMemcpyHostToDevice, ctx->stream));
         ctx->plan_key.assign(kb, kb + sizeof key);
         ctx->plan_tiles = (int64_t)tiles.size();
     }
@@ -620,10 +620,9 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
     P.err = ctx->d_err; P.w = d->w; P.n_ccd = d->n_ccd; P.bulk_ok = bulk_ok ? 1 : 0;
 
     const size_t smem = (size_t)pan::RING * pan::SWC * 4 + 2 * (size_t)pan::STG * pan::SWC * 2;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->pan_attr_set) {
         OIP_CUDA(cudaFuncSetAttribute(pan::pan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->pan_attr_set = true;
     }
     pan::pan_kernel<<<(unsigned)ctx->plan_tiles, pan::NT, smem, ctx->stream>>>(P);
     OIP_CUDA(cudaGetLastError());

@@ -132,6 +132,20 @@ def pan_pipeline(ctx: Context, ccds, kbs, dX, dY, fold_half: int, fmt=FMT_LE16, 
     return out
 
 
+def pan_pipeline_host(ctx: Context, ccds_host, kbs_host, dX, dY, fold_half: int, out_host: torch.Tensor,
+                      fmt=FMT_LE16, shifted=None, section_rows: int = SECTION_ROWS, row_guard: int = ROW_GUARD,
+                      w: Optional[int] = None) -> torch.Tensor:
+    """same operation for HOST buffers (ideally pinned): host->device, kernels and device->host are
+    overlapped in row blocks inside the library (oip_pan_pipeline_host).  Returns out_host."""
+    n = len(ccds_host)
+    if shifted is None:
+        shifted = [i > 0 for i in range(n)]
+    d = make_pan_desc(ccds_host, fmt, kbs_host, dX, dY, shifted, fold_half, out_host, section_rows=section_rows,
+                      row_guard=row_guard, w=w)
+    check(ctx.lib.oip_pan_pipeline_host(ctx.h, C.byref(d)))
+    return out_host
+
+
 def inplace_rrc(ctx: Context, img: torch.Tensor, kb: torch.Tensor) -> torch.Tensor:
     h, w = img.shape
     check(ctx.lib.oip_rrc_u16(ctx.h, img.data_ptr(), w, h, img.stride(0), kb.data_ptr()))

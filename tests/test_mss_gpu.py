@@ -61,10 +61,11 @@ def test_band_align_full_range_no_rrc(ctx, oracle_mod):
 def test_band_align_argument_errors(ctx):
     from opticalimageprocessor_b200 import ops
     from opticalimageprocessor_b200.capi import OipError
-    mixed = torch.zeros((2000, 32), dtype=torch.uint16, device="cuda")
+    mixed = torch.zeros((8000, 32), dtype=torch.uint16, device="cuda")
     z2, z3 = np.zeros((4, 2)), np.zeros((4, 3))
+    # same conditions and wording as ref preproc.h:355-367
     for kw, msg in [(dict(overlap=3001), "exceeds maximum"), (dict(lines_per_section=32768), "OpenCV allowed"),
-                    (dict(lines_per_section=1000), "too small"), (dict(line_offset=600), "Too few")]:
+                    (dict(lines_per_section=1000), "too small"), (dict(line_offset=6600), "Too few")]:
         with pytest.raises(OipError, match=msg):
             ops.band_align(ctx, mixed, 8, None, z2, z3, **kw)
 
