@@ -212,25 +212,8 @@ def run_gpu(args):
                 opened.append(p.value)
             return peer_ptr[(r, i)]
 
-        for i in range(N_CCD):
-            f, l, sf, sl = (C.c_int64() for _ in range(4))
-            capi.check(ctx.lib.oip_pan_rows_needed(C.byref(desc), i, f, l, sf, sl))
-            segs = [(d_in[i], row0, ROWS)]
-            need = [(f.value, l.value), (sf.value, sl.value)]
-            for a, b in need:
-                for r in range(world):
-                    if r == rank:
-                        continue
-                    lo, hi = max(a, r * ROWS), min(b, (r + 1) * ROWS)
-                    if hi > lo:
-                        segs.append((peer(r, i), r * ROWS, ROWS))
-            segs = list(dict.fromkeys(segs))
-            if len(segs) > capi.MAX_SEG:
-                raise SystemExit("shard needs rows from too many neighbours")
-            c = desc.ccd[i]
-            c.n_seg = len(segs)
-            for s, (base, r0, nr) in enumerate(segs):
-                c.seg[s] = capi.RowSeg(base, r0, nr, W * 2)
+        from opticalimageprocessor_b200 import sharding
+        sharding.attach_segments(desc, N_CCD, total_rows, world, rank, d_in, W * 2, peer)
         dist.barrier()
 
     def step():

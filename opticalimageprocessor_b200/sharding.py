@@ -1,0 +1,81 @@
+"""Scanline-block sharding of a strip across the GPUs of one box.
+
+No data-path collective: a rank owns `rows_per_rank` consecutive lines of every CCD; the few rows
+its shifted tiles read beyond that block (halo rows, and for the last rank the stale rows of the
+previous 30000-row section) are supplied as extra row segments that point into the owning
+neighbour's buffer.  On a GPU box those pointers are CUDA-IPC mappings (read over NVLink by the
+kernel's bulk copies); `torch.distributed` only carries the handle exchange.
+
+The planning here is pure host logic (it only calls the library's `oip_pan_rows_needed`, which needs
+no GPU), so it is covered by world_size-2 gloo tests on CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Sequence, Tuple
+
+from . import capi
+
+
+def shard_range(total_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """[first, last) lines owned by `rank`: equal blocks, the last rank takes the remainder"""
+    per = total_rows // world
+    first = rank * per
+    last = total_rows if rank == world - 1 else first + per
+    return first, last
+
+
+def rows_needed(desc: capi.PanDesc, ccd: int) -> Tuple[Tuple[int, int], Tuple[int, int]]:
+    L = capi.load()
+    f, l, sf, sl = (C.c_int64() for _ in range(4))
+    capi.check(L.oip_pan_rows_needed(C.byref(desc), ccd, f, l, sf, sl))
+    return (f.value, l.value), (sf.value, sl.value)
+
+
+def peer_requirements(desc: capi.PanDesc, n_ccd: int, total_rows: int, world: int, rank: int) -> List[List[int]]:
+    """for each CCD, the ranks (other than `rank`) that own rows this shard reads"""
+    out = []
+    for i in range(n_ccd):
+        need = rows_needed(desc, i)
+        owners = []
+        for a, b in need:
+            if b <= a:
+                continue
+            for r in range(world):
+                if r == rank:
+                    continue
+                lo, hi = shard_range(total_rows, world, r)
+                if min(b, hi) > max(a, lo) and r not in owners:
+                    owners.append(r)
+        out.append(owners)
+    return out
+
+
+def attach_segments(desc: capi.PanDesc, n_ccd: int, total_rows: int, world: int, rank: int, own_ptr: Sequence[int],
+                    pitch_bytes: int, peer_ptr: Callable[[int, int], int]) -> Dict[int, List[int]]:
+    """fill desc.ccd[i].seg[] with the own block plus one segment per neighbour that owns needed rows.
+    peer_ptr(rank, ccd) -> device-visible pointer to that rank's block of CCD `ccd`."""
+    req = peer_requirements(desc, n_ccd, total_rows, world, rank)
+    for i in range(n_ccd):
+        first, last = shard_range(total_rows, world, rank)
+        segs = [(own_ptr[i], first, last - first)]
+        for r in req[i]:
+            lo, hi = shard_range(total_rows, world, r)
+            segs.append((peer_ptr(r, i), lo, hi - lo))
+        if len(segs) > capi.MAX_SEG:
+            raise ValueError(f"CCD {i}: shard needs rows from {len(segs) - 1} neighbours (max {capi.MAX_SEG - 1})")
+        c = desc.ccd[i]
+        c.n_seg = len(segs)
+        for s, (base, r0, nr) in enumerate(segs):
+            c.seg[s] = capi.RowSeg(base, r0, nr, pitch_bytes)
+    return {i: req[i] for i in range(n_ccd)}
+
+
+def covers(desc: capi.PanDesc, ccd: int) -> bool:
+    """every row the shard reads is inside one of the attached segments"""
+    c = desc.ccd[ccd]
+    for a, b in rows_needed(desc, ccd):
+        for g in range(a, b):
+            if not any(c.seg[s].row0 <= g < c.seg[s].row0 + c.seg[s].n_rows for s in range(c.n_seg)):
+                return False
+    return True

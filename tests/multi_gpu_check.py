@@ -1,0 +1,87 @@
+"""torchrun worker: every rank computes its scanline-block shard of the fused PAN path, reading halo /
+stale rows from the neighbours' HBM through CUDA-IPC mappings; rank 0 gathers and compares with the
+CPU oracle of the WHOLE strip.  Launched by tests/test_multi_gpu.py (needs >= 2 GPUs)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from opticalimageprocessor_b200 import capi, ops, sharding, synth  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = ops.Context(local)
+    n, w, f, S, G = 3, 512, 20, 400, 450
+    total = 1500 * world + 37
+    dX, dY = [0.0, 1.37, -0.83], [0.0, -2.61, 3.19]
+    first, last = sharding.shard_range(total, world, rank)
+    rows = last - first
+    full = [synth.strip_dn(w, total, 900 + i) for i in range(n)]       # every rank can regenerate any row
+    kbs = [synth.rrc_coeffs(w, 950 + i) for i in range(n)]
+    d_in, handles = [], []
+    for i in range(n):
+        p = C.c_void_p()
+        nb = rows * w * 2
+        capi.check(ctx.lib.oip_dev_alloc(ctx.h, nb, C.byref(p)))
+        blk = np.ascontiguousarray(full[i][first:last].byteswap())
+        capi.check(ctx.lib.oip_copy_h2d(ctx.h, p, C.c_void_p(blk.ctypes.data), nb))
+        ctx.sync()
+        d_in.append(p.value)
+        hb = C.create_string_buffer(64)
+        capi.check(ctx.lib.oip_ipc_export(ctx.h, p, hb))
+        handles.append(hb.raw)
+    allh = [None] * world
+    dist.all_gather_object(allh, handles)
+    d_kb = [torch.from_numpy(k).cuda() for k in kbs]
+    out = torch.empty((rows, ops.pan_out_width(n, w, f)), dtype=torch.uint16, device="cuda")
+    shape_only = [torch.empty((rows, w), dtype=torch.uint16) for _ in range(n)]
+    desc = ops.make_pan_desc(shape_only, ops.FMT_BE16, d_kb, dX, dY, [i > 0 for i in range(n)], f, out,
+                             total_rows=total, row0=first, n_rows=rows, section_rows=S, row_guard=G,
+                             segs=[[(d_in[i], first, rows, w * 2)] for i in range(n)])
+    opened = {}
+
+    def peer(r, i):
+        if (r, i) not in opened:
+            p = C.c_void_p()
+            capi.check(ctx.lib.oip_ipc_open(ctx.h, allh[r][i], C.byref(p)))
+            opened[(r, i)] = p.value
+        return opened[(r, i)]
+
+    sharding.attach_segments(desc, n, total, world, rank, d_in, w * 2, peer)
+    dist.barrier()
+    capi.check(ctx.lib.oip_pan_pipeline(ctx.h, C.byref(desc)))
+    capi.check(ctx.lib.oip_pan_check_error(ctx.h))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    ok = True
+    if True:
+        import oracle
+        want = oracle.pan_pipeline(full, kbs, dX, dY, f, S, G)[first:last]
+        bad = np.argwhere(got != want)
+        ok = bad.size == 0
+        if not ok:
+            print(f"rank {rank}: {len(bad)} px differ, first {bad[:5].tolist()}", flush=True)
+    t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    for p in opened.values():
+        ctx.lib.oip_ipc_close(ctx.h, C.c_void_p(p))
+    dist.barrier()
+    for p in d_in:
+        ctx.lib.oip_dev_free(ctx.h, C.c_void_p(p))
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "OK" if t.item() == 1.0 else "FAIL", f"world={world} peers_opened_rank0={sorted(opened)}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
