@@ -3,28 +3,37 @@
 // One launch covers every CCD of a strip.  Work is cut into tiles of TW output columns x up to TH
 // output rows; a CTA marches down its tile in chunks of RC rows:
 //
-//   TMA-unit bulk copies (cp.async.bulk, SASS UBLKCP) stage the raw source rows of chunk k+1/k+2 in
-//   shared memory while chunk k is processed        -> every source byte is read from HBM once per
-//                                                      column strip (16-column halo = 6.7 %)
-//   "convert": byte swap + fp64 RRC (ref imageop.h:134) of the newly arrived rows into a float ring
-//   "resample": each thread owns one output column, slides a 4x4 register window down the ring and
-//   evaluates OpenCV's bicubic sum in OpenCV's own order  -> u16 store
+//   load     TMA-unit bulk copies (cp.async.bulk, SASS UBLKCP) stage the raw source rows of the next
+//            two chunks in shared memory behind an mbarrier while the current chunk is processed:
+//            every source byte is read from HBM once per column strip (halo columns hit L2)
+//   convert  a thread takes 8 adjacent detectors of one row: byte swap (PRMT), fp64 RRC with (k,b)
+//            held in registers (ref imageop.h:134), result as float into a 40-row ring
+//   resample a thread owns 4 output columns x 8 rows, slides a 4-row window down the ring with
+//            128-bit shared loads and evaluates OpenCV's bicubic sum in OpenCV's own order
+//             with packed FMUL2/FADD2 (two pixels per instruction, same IEEE roundings)
 //
-// No intermediate (.RRC.RAW, .PRESTT.RAW) ever exists in HBM.  CCDs that are not shifted use
-// COPY tiles: same staging, RRC, straight to their trimmed position in the output raster.
+// The kernel is instruction-issue bound, not HBM bound (profiles/): everything here is about
+// instructions per pixel.  No intermediate (.RRC.RAW, .PRESTT.RAW) ever exists in HBM.  CCDs that
+// are not shifted use COPY tiles: same staging, RRC, 128-bit stores to their trimmed position.
+//
+// Irregular situations (map rounding anomalies, section/image borders, partial tiles, unaligned or
+// packed inputs) take exact but slower generic paths inside the same kernel.
 #include "oip_common.cuh"
 #include "pan_plan.hpp"
 
 namespace oip {
 namespace pan {
 
-constexpr int TW = 240;   // output columns per tile
-constexpr int SWC = 256;  // staged source columns per tile (TW + halo/alignment slack)
+constexpr int TW = 256;   // output columns per tile
+constexpr int RW = 264;   // float ring width: TW + 3 taps + 1 (map anomaly) rounded to 8
+constexpr int SWC = 272;  // staged source columns: RW + up to 7 columns of 16-byte alignment slack
 constexpr int RC = 32;    // output rows per chunk
 constexpr int RING = 40;  // float ring rows (>= RC + 3 + 1)
 constexpr int STG = 40;   // raw staging rows per buffer (first chunk needs RC + 4)
 constexpr int NT = 256;   // threads per CTA
 constexpr int TH = 512;   // output rows per tile
+constexpr int CV_G = RW / 8;          // 33 column octets per ring row
+constexpr int CV_PH = NT / CV_G;      // 7 row phases in the convert step (231 threads busy)
 
 enum { KIND_COPY = 0, KIND_REMAP = 1 };
 
@@ -123,78 +132,190 @@ __device__ __forceinline__ uint32_t load_sample(const CcdDev &C, const uint8_t *
 }
 
 struct ChunkRows {
-    int64_t t_lo, t_hi;   // source (buffer-local) rows needed by the chunk, inclusive
-    int64_t new_lo;       // first row not yet in the ring
+    int t_lo, t_hi; // source (buffer-local) rows needed by the chunk, inclusive
+    int new_lo;     // first row not yet in the ring
     int n_new;
 };
 
 __device__ __forceinline__ ChunkRows chunk_rows(const Tile &T, double dY, int k)
 {
     ChunkRows c;
-    int64_t ja = T.j0 + (int64_t)k * RC;
-    int64_t jb = min(ja + RC, T.j0 + (int64_t)T.n_rows) - 1;
+    const int64_t ja = T.j0 + (int64_t)k * RC;
+    const int64_t jb = min(ja + RC, T.j0 + (int64_t)T.n_rows) - 1;
     if (T.kind == KIND_REMAP) {
         c.t_lo = dev_tap_base(ja, dY);
-        c.t_hi = (int64_t)dev_tap_base(jb, dY) + 3;
-        if (k == 0) c.new_lo = c.t_lo;
-        else c.new_lo = max(c.t_lo, (int64_t)dev_tap_base(ja - 1, dY) + 4);
-    } else {
-        c.t_lo = ja;
-        c.t_hi = jb;
-        c.new_lo = ja;
+        c.t_hi = dev_tap_base(jb, dY) + 3;
+        c.new_lo = k == 0 ? c.t_lo : max(c.t_lo, dev_tap_base(ja - 1, dY) + 4);
+    } else { // COPY tiles address rows relative to the tile's first row (keeps everything in int)
+        c.t_lo = k * RC;
+        c.t_hi = (int)(jb - T.j0);
+        c.new_lo = c.t_lo;
     }
-    c.n_new = (int)(c.t_hi - c.new_lo + 1);
-    if (c.n_new < 0) c.n_new = 0;
+    c.n_new = max(0, c.t_hi - c.new_lo + 1);
     return c;
 }
 
-// bicubic sum, interior order: ((s0*w0+s1*w1)+s2*w2)+s3*w3 per row, rows added in turn
-__device__ __forceinline__ float row_dot(const float (&v)[4], const float (&w)[4])
+// ---------------------------------------------------------------------------------------------
+// packed fp32 pairs: two pixels per FMUL2/FADD2, each lane rounds exactly like the scalar op
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi)
 {
-    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[0], w[0]), __fmul_rn(v[1], w[1])), __fmul_rn(v[2], w[2])),
-                     __fmul_rn(v[3], w[3]));
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
-__device__ __forceinline__ float cubic_interior(const float (&a)[4], const float (&b)[4], const float (&c)[4],
-                                                const float (&d)[4], const float (&w)[4][4])
+__device__ __forceinline__ float lo_of(f2 v)
 {
-    float s = row_dot(a, w[0]);
-    s = __fadd_rn(s, row_dot(b, w[1]));
-    s = __fadd_rn(s, row_dot(c, w[2]));
-    s = __fadd_rn(s, row_dot(d, w[3]));
-    return s;
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
 }
-// border order: flat left-to-right accumulation from 0 (out-of-image taps are 0 in the ring)
-__device__ __forceinline__ float row_acc(float s, const float (&v)[4], const float (&w)[4])
+__device__ __forceinline__ float hi_of(f2 v)
 {
-    s = __fadd_rn(s, __fmul_rn(v[0], w[0]));
-    s = __fadd_rn(s, __fmul_rn(v[1], w[1]));
-    s = __fadd_rn(s, __fmul_rn(v[2], w[2]));
-    s = __fadd_rn(s, __fmul_rn(v[3], w[3]));
-    return s;
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
 }
-__device__ __forceinline__ float cubic_border(const float (&a)[4], const float (&b)[4], const float (&c)[4],
-                                              const float (&d)[4], const float (&w)[4][4])
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false (it honours the
+// explicit .rn only for scalar ops), and it also folds fma(a,b,-0.0) back into a mul when the -0.0 is
+// a known constant.  The product is therefore an FMA whose addend is a (-0.0,-0.0) pair LOADED AT RUN
+// TIME (plan header): RN(a*b + -0.0) == RN(a*b) bit for bit, and an FMA cannot be fused with the add
+// that follows.  SASS check: FFMA2 count == FMUL2 would-be count, FADD2 count unchanged.
+__device__ __forceinline__ f2 mul2(f2 a, f2 b, f2 nz)
 {
-    float s = 0.f;
-    s = row_acc(s, a, w[0]);
-    s = row_acc(s, b, w[1]);
-    s = row_acc(s, c, w[2]);
-    s = row_acc(s, d, w[3]);
-    return s;
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+    return r;
 }
-__device__ __forceinline__ uint16_t cast_u16(float s)
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
 {
-    int v = __float2int_rn(s); // cvRound
-    return (uint16_t)max(0, min(65535, v));
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// one ring row as seen by a thread that owns output columns 4g..4g+3: source columns q0..q6
+struct RowRegs {
+    f2 A0, A1, A2; // (q0,q1) (q2,q3) (q4,q5)   straight from the two 128-bit loads
+    f2 B0, B1, B2; // (q1,q2) (q3,q4) (q5,q6)   re-paired copies
+};
+__device__ __forceinline__ void load_row_regs(RowRegs &R, const float *p)
+{
+    f2 a3;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(R.A0), "=l"(R.A1) : "r"(smem_u32(p)));
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(R.A2), "=l"(a3) : "r"(smem_u32(p + 4)));
+    R.B0 = pk(hi_of(R.A0), lo_of(R.A1));
+    R.B1 = pk(hi_of(R.A1), lo_of(R.A2));
+    R.B2 = pk(hi_of(R.A2), lo_of(a3));
+}
+// per-row dot products in OpenCV's interior order ((s0*w0 + s1*w1) + s2*w2) + s3*w3, pixels (0,1) and (2,3)
+__device__ __forceinline__ f2 dot01(const RowRegs &R, const f2 (&W)[4], f2 nz)
+{
+    return add2(add2(add2(mul2(R.A0, W[0], nz), mul2(R.B0, W[1], nz)), mul2(R.A1, W[2], nz)), mul2(R.B1, W[3], nz));
+}
+__device__ __forceinline__ f2 dot23(const RowRegs &R, const f2 (&W)[4], f2 nz)
+{
+    return add2(add2(add2(mul2(R.A1, W[0], nz), mul2(R.B1, W[1], nz)), mul2(R.A2, W[2], nz)), mul2(R.B2, W[3], nz));
+}
+
+__device__ __forceinline__ uint32_t cast_u16(float s)
+{
+    return (uint32_t)max(0, min(65535, __float2int_rn(s))); // cvRound + saturate_cast<ushort>
+}
+
+// generic single-pixel bicubic from the ring (any alignment, border or interior order)
+struct RingView {
+    const float *ring;
+    int t_base;  // buffer row held in ring slot 0 (mod RING)
+    int ix0;     // source column held in ring column 0
+    int t_lo, t_hi;
+};
+__device__ __forceinline__ uint32_t resample_px_general(const RingView &V, const float *s_tab, int sx, int sy, int w,
+                                                        int hbuf)
+{
+    const int ix = dev_sat_short(sx >> 5) - 1, fx = sx & 31;
+    const int iy = dev_sat_short(sy >> 5) - 1, fy = sy & 31;
+    float v[4][4], wg[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int t = iy + r;
+        const bool rin = t >= V.t_lo && t <= V.t_hi;
+        const int slot = rin ? (t - V.t_base) % RING : 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int rc = ix + c - V.ix0;
+            const bool in = rin && rc >= 0 && rc < RW;
+            v[r][c] = in ? V.ring[slot * RW + rc] : 0.f;
+            wg[r][c] = __fmul_rn(s_tab[4 * fy + r], s_tab[4 * fx + c]);
+        }
+    }
+    const bool interior = (unsigned)ix < (unsigned)max(w - 3, 0) && (unsigned)iy < (unsigned)max(hbuf - 3, 0);
+    float s;
+    if (interior) {
+        s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[r][0], wg[r][0]), __fmul_rn(v[r][1], wg[r][1])),
+                                          __fmul_rn(v[r][2], wg[r][2])),
+                                __fmul_rn(v[r][3], wg[r][3]));
+            s = r == 0 ? d : __fadd_rn(s, d);
+        }
+    } else { // border: flat accumulation from 0, out-of-image taps contribute 0 (they are 0 in the ring)
+        s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s = __fadd_rn(s, __fmul_rn(v[r][c], wg[r][c]));
+    }
+    return cast_u16(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// convert: 8 raw samples (5 staged words, first sample at halfword `odd`) -> RRC -> 8 values
+// ---------------------------------------------------------------------------------------------
+template <bool SWAP, bool ODD>
+__device__ __forceinline__ void extract8(const uint32_t (&wd)[5], uint32_t (&s)[8])
+{
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int h = (ODD ? 1 : 0) + j;
+        const uint32_t word = wd[h >> 1];
+        // one PRMT does halfword select + byte swap + zero extension
+        const uint32_t sel = (h & 1) ? (SWAP ? 0x4423u : 0x4432u) : (SWAP ? 0x4401u : 0x4410u);
+        s[j] = __byte_perm(word, 0u, sel);
+    }
+}
+
+__device__ __forceinline__ void rrc8(uint32_t (&s)[8], const double (&k)[8], const double (&b)[8])
+{
+    double v[8];
+    uint32_t hmax = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double sd = __dadd_rn(__hiloint2double(0x43300000, (int)s[j]), -4503599627370496.0);
+        v[j] = __dadd_rn(__dmul_rn(k[j], sd), b[j]);
+        hmax = max(hmax, (uint32_t)__double2hiint(v[j]));
+    }
+    if (hmax < 0x41E00000u) { // all eight in [0, 2^31): exact truncation with one DADD.RZ each
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = (uint32_t)__double2loint(__dadd_rz(v[j], 4503599627370496.0));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int t = (v[j] > -2147483649.0 && v[j] < 2147483648.0) ? __double2int_rz(v[j]) : (int)0x80000000;
+            s[j] = (uint32_t)t;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    float *ring = reinterpret_cast<float *>(smem);                                 // RING x SWC f32
-    uint16_t *stg = reinterpret_cast<uint16_t *>(smem + RING * SWC * 4);           // 2 x STG x SWC u16
+    float *ring = reinterpret_cast<float *>(smem);                          // RING x RW f32
+    uint16_t *stg = reinterpret_cast<uint16_t *>(smem + RING * RW * 4);     // 2 x STG x SWC u16
     __shared__ __align__(8) uint64_t bars[2];
-    __shared__ float s_tab[128];
+    __shared__ __align__(8) float s_tab[132]; // 32x4 weights + the (-0.0,-0.0) pair at [128..129]
     __shared__ uint8_t s_rowzero[2][STG];
     __shared__ int s_sy[RC];
     __shared__ int s_regular;
@@ -205,34 +326,53 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
     const int w = P.w;
     const bool remap = T.kind == KIND_REMAP;
     const bool bulk = P.bulk_ok != 0;
-    const bool swap = bulk && C.fmt == OIP_FMT_BE16;
+    const bool swap = bulk && C.fmt == OIP_FMT_BE16; // the generic loader already delivers native order
     const bool do_rrc = C.kb != nullptr;
     const double dX = C.dX, dY = C.dY;
 
-    if (tid < 128) s_tab[tid] = P.tab[tid];
+    if (tid < 130) s_tab[tid] = P.tab[tid];
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         fence_mbar_init();
     }
 
-    // source column window of the tile
-    int c_first = remap ? dev_tap_base(T.x_begin, dX) : T.x_begin;
-    const int c_lo = (c_first >= 0 ? c_first : c_first - 7) / 8 * 8; // floor to a multiple of 8
+    // ---- column geometry: ring column 0 <-> source column ix0; staging column 0 <-> c_lo
     const int n_cols = T.x_end - T.x_begin;
+    const int sx0 = remap ? dev_map_fixed(T.x_begin, dX) : 0;
+    const int ix0 = remap ? dev_sat_short(sx0 >> 5) - 1 : T.x_begin;
+    const int c_lo = (ix0 >= 0 ? ix0 : ix0 - 7) / 8 * 8; // floor to a multiple of 8 (16-byte aligned bulk copies)
+    const int delta = ix0 - c_lo;
     const int n_chunks = (T.n_rows + RC - 1) / RC;
-    const int64_t t_base = chunk_rows(T, dY, 0).t_lo;
+    const int t_base = chunk_rows(T, dY, 0).t_lo;
 
-    // convert-phase mapping: thread = (column pair, row parity)
-    const int p = tid & 127, par = tid >> 7;
-    const int c0 = c_lo + 2 * p;
-    const bool v0ok = c0 >= 0 && c0 < w, v1ok = c0 + 1 >= 0 && c0 + 1 < w;
-    double k0 = 1.0, b0 = 0.0, k1 = 1.0, b1 = 0.0;
-    if (do_rrc) {
-        if (v0ok) { k0 = C.kb[2 * c0]; b0 = C.kb[2 * c0 + 1]; }
-        if (v1ok) { k1 = C.kb[2 * c0 + 2]; b1 = C.kb[2 * c0 + 3]; }
+    // column-regular tile: the fixed-point column map advances by exactly one source pixel per
+    // output pixel (always true except where float(x + dX) rounds across a 1/32 boundary)
+    bool my_cols_regular = true;
+    if (remap) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int xi = tid + j * NT; // 0..n_cols
+            if (xi < n_cols && dev_map_fixed(T.x_begin + xi, dX) != sx0 + 32 * xi) my_cols_regular = false;
+        }
     }
-    __syncthreads();
+    const bool cols_regular = __syncthreads_and(my_cols_regular) != 0; // also publishes s_tab / barriers
+
+    // ---- convert-step mapping: (column octet g, row phase ph), RRC coefficients in registers
+    const int cvt_groups = remap ? CV_G : TW / 8;
+    const int cv_g = tid % cvt_groups, cv_ph = tid / cvt_groups;
+    const int cv_phases = NT / cvt_groups;
+    const bool cv_active = cv_ph < cv_phases;
+    double kk[8], bb[8];
+    uint32_t col_mask = 0; // bit j: column is inside the CCD
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = ix0 + 8 * cv_g + j;
+        const bool ok = c >= 0 && c < w;
+        col_mask |= ok ? (1u << j) : 0u;
+        kk[j] = (ok && do_rrc) ? C.kb[2 * c] : (ok ? 1.0 : 0.0); // k = b = 0 zeroes columns outside the CCD
+        bb[j] = (ok && do_rrc) ? C.kb[2 * c + 1] : 0.0;
+    }
 
     // ------------------------------------------------------------------ loader
     auto issue_chunk = [&](int k) {
@@ -240,6 +380,7 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
         uint16_t *buf = stg + (size_t)(k & 1) * STG * SWC;
         uint8_t *rz = s_rowzero[k & 1];
         uint64_t *bar = &bars[k & 1];
+        const int64_t row_bias = remap ? 0 : T.j0; // COPY rows are tile-relative
         if (bulk) {
             if (tid < 32) {
                 const int ca = max(c_lo, 0), cb = min(c_lo + SWC, w);
@@ -248,9 +389,9 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
                 uint32_t mine = 0;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    int r = tid + 32 * i;
+                    const int r = tid + 32 * i;
                     if (r < cr.n_new) {
-                        int64_t g = local_to_global(T, cr.new_lo + r);
+                        const int64_t g = local_to_global(T, row_bias + cr.new_lo + r);
                         const uint8_t *q = (g >= 0 && nb) ? row_ptr(C, g) : nullptr;
                         if (g >= 0 && nb && !q) atomicExch(P.err, 1); // host failed to supply a needed row
                         ptr[i] = q;
@@ -265,22 +406,23 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    int r = tid + 32 * i;
+                    const int r = tid + 32 * i;
                     if (ptr[i]) bulk_g2s(buf + (size_t)r * SWC + (ca - c_lo), ptr[i] + 2 * (int64_t)ca, nb, bar);
                 }
             }
         } else {
             // generic loader: any alignment / packed / tile layouts; native byte order in staging
             for (int r = 0; r < cr.n_new; ++r) {
-                int64_t g = local_to_global(T, cr.new_lo + r);
+                const int64_t g = local_to_global(T, row_bias + cr.new_lo + r);
                 const uint8_t *q = nullptr;
                 if (g >= 0) q = C.fmt == OIP_FMT_BE16_TILES ? C.seg[0].base : row_ptr(C, g);
                 if (g >= 0 && !q && tid == 0) atomicExch(P.err, 1);
                 if (tid == 0) rz[r] = q == nullptr;
-                if (q) {
-                    int c = c_lo + tid;
-                    buf[(size_t)r * SWC + tid] = (c >= 0 && c < w) ? (uint16_t)load_sample(C, q, g, c) : (uint16_t)0;
-                }
+                if (q)
+                    for (int i = tid; i < SWC; i += NT) {
+                        const int c = c_lo + i;
+                        buf[(size_t)r * SWC + i] = (c >= 0 && c < w) ? (uint16_t)load_sample(C, q, g, c) : (uint16_t)0;
+                    }
             }
         }
     };
@@ -289,20 +431,15 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
     if (n_chunks > 1) issue_chunk(1);
     __syncthreads();
 
-    // resample-phase per-thread column constants
-    int ix = 0, cx = 0;
-    bool col_int = false;
-    float wx[4] = {0.f, 0.f, 0.f, 0.f};
-    if (remap && tid < n_cols) {
-        int sx = dev_map_fixed(T.x_begin + tid, dX);
-        ix = dev_sat_short(sx >> 5) - 1;
-        cx = ix - c_lo;
-        col_int = (unsigned)ix < (unsigned)max(w - 3, 0);
-        const int fx = sx & 31;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) wx[i] = s_tab[4 * fx + i];
-    }
-    uint16_t *out_col = P.out + (T.g0 - P.out_row0) * P.out_pitch + T.out_x + tid;
+    // ---- resample-step mapping: thread = (column quad cg, row group rg) -> 4 columns x 8 rows
+    const int cg = tid & 63, rg = tid >> 6;
+    const int qx = 4 * cg; // first of my 4 tile columns
+    // my 4 pixels are on the packed fast path iff they exist and all their 4x4 footprints are inside the CCD
+    const bool quad_full = qx + 3 < n_cols;
+    const bool quad_interior = quad_full && (ix0 + qx) >= 0 && (ix0 + qx + 3) < w - 3;
+    const int fx = sx0 & 31;
+    uint16_t *const out_tile = P.out + (T.g0 - P.out_row0) * P.out_pitch + T.out_x;
+    const bool out_vec = ((((uintptr_t)P.out) & 7) == 0) && ((P.out_pitch & 3) == 0) && ((T.out_x & 3) == 0);
 
     for (int k = 0; k < n_chunks; ++k) {
         const ChunkRows cr = chunk_rows(T, dY, k);
@@ -311,122 +448,138 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
         if (bulk) mbar_wait(&bars[k & 1], (uint32_t)((k >> 1) & 1));
 
         // ---------------------------------------------------------- convert: swap + RRC
-        {
-            const uint32_t *buf32 = reinterpret_cast<const uint32_t *>(stg + (size_t)(k & 1) * STG * SWC);
+        if (cv_active) {
+            const uint16_t *buf = stg + (size_t)(k & 1) * STG * SWC;
             const uint8_t *rz = s_rowzero[k & 1];
-            for (int r = par; r < cr.n_new; r += 2) {
-                const int64_t t = cr.new_lo + r;
-                uint32_t a = 0, b = 0;
+            const int h0 = delta + 8 * cv_g; // staging halfword of my first column
+            for (int r = cv_ph; r < cr.n_new; r += cv_phases) {
+                uint32_t s[8];
                 const bool z = rz[r] != 0;
                 if (!z) {
-                    uint32_t raw = buf32[(size_t)r * (SWC / 2) + p];
-                    if (swap) raw = bswap16x2(raw);
-                    a = raw & 0xFFFFu;
-                    b = raw >> 16;
-                    if (do_rrc) {
-                        a = rrc_px(a, k0, b0);
-                        b = rrc_px(b, k1, b1);
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (size_t)r * SWC) + (h0 >> 1);
+                    uint32_t wd[5];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) wd[i] = wp[i];
+                    wd[4] = (h0 & 1) ? wp[4] : 0u;
+                    if (h0 & 1) {
+                        if (swap) extract8<true, true>(wd, s); else extract8<false, true>(wd, s);
+                    } else {
+                        if (swap) extract8<true, false>(wd, s); else extract8<false, false>(wd, s);
                     }
+                    if (do_rrc || col_mask != 0xFFu) rrc8(s, kk, bb);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s[j] = 0;
                 }
                 if (remap) {
-                    int slot = (int)(t - t_base) % RING;
-                    float2 o;
-                    o.x = (v0ok && !z) ? u16_to_f32(a) : 0.f;
-                    o.y = (v1ok && !z) ? u16_to_f32(b) : 0.f;
-                    reinterpret_cast<float2 *>(ring)[(size_t)slot * (SWC / 2) + p] = o;
-                } else if (!z) {
-                    uint16_t *orow = P.out + (t - P.out_row0) * P.out_pitch + T.out_x;
-                    if (c0 >= T.x_begin && c0 < T.x_end) orow[c0 - T.x_begin] = (uint16_t)a;
-                    if (c0 + 1 >= T.x_begin && c0 + 1 < T.x_end) orow[c0 + 1 - T.x_begin] = (uint16_t)b;
+                    const int slot = (cr.new_lo + r - t_base) % RING;
+                    float4 o0, o1;
+                    o0.x = u16_to_f32(s[0] & 0xFFFFu); o0.y = u16_to_f32(s[1] & 0xFFFFu);
+                    o0.z = u16_to_f32(s[2] & 0xFFFFu); o0.w = u16_to_f32(s[3] & 0xFFFFu);
+                    o1.x = u16_to_f32(s[4] & 0xFFFFu); o1.y = u16_to_f32(s[5] & 0xFFFFu);
+                    o1.z = u16_to_f32(s[6] & 0xFFFFu); o1.w = u16_to_f32(s[7] & 0xFFFFu);
+                    float4 *dst = reinterpret_cast<float4 *>(ring + (size_t)slot * RW + 8 * cv_g);
+                    dst[0] = o0;
+                    dst[1] = o1;
                 } else {
-                    uint16_t *orow = P.out + (t - P.out_row0) * P.out_pitch + T.out_x;
-                    if (c0 >= T.x_begin && c0 < T.x_end) orow[c0 - T.x_begin] = 0;
-                    if (c0 + 1 >= T.x_begin && c0 + 1 < T.x_end) orow[c0 + 1 - T.x_begin] = 0;
+                    // COPY tile: straight to the output raster
+                    uint16_t *orow = out_tile + (int64_t)(cr.new_lo + r) * P.out_pitch + 8 * cv_g;
+                    if (out_vec && ((T.out_x & 7) == 0) && ((P.out_pitch & 7) == 0) && ((((uintptr_t)P.out) & 15) == 0) &&
+                        8 * cv_g + 8 <= n_cols) {
+                        uint4 o;
+                        o.x = (s[0] & 0xFFFFu) | (s[1] << 16);
+                        o.y = (s[2] & 0xFFFFu) | (s[3] << 16);
+                        o.z = (s[4] & 0xFFFFu) | (s[5] << 16);
+                        o.w = (s[6] & 0xFFFFu) | (s[7] << 16);
+                        stg_na_v4(orow, o);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (8 * cv_g + j < n_cols) orow[j] = (uint16_t)s[j];
+                    }
                 }
             }
-            if (remap && tid < 32) {
-                // row map of the chunk + "regular" flag: unit row steps (hence one fy) and every
-                // row in the interior of the section buffer -> sliding-window fast path
-                const int sy = tid < nr ? dev_map_fixed(ja + tid, dY) : 0;
-                const int prev = __shfl_up_sync(0xffffffffu, sy, 1);
-                const bool ok = (tid == 0 || tid >= nr) ? true : (sy - prev == 32);
-                const bool all_ok = __all_sync(0xffffffffu, ok);
-                s_sy[tid] = sy;
-                if (tid == 0) {
-                    const int iy0 = dev_sat_short(sy >> 5) - 1;
-                    s_regular = all_ok && iy0 >= 0 && (iy0 + nr - 1) < T.hbuf - 3;
-                }
+        }
+        if (remap && tid < 32) {
+            // row map of the chunk + "regular" flag: unit row steps (hence one fy) and every row in
+            // the interior of the section buffer -> packed sliding-window path
+            const int sy = tid < nr ? dev_map_fixed(ja + tid, dY) : 0;
+            const int prev = __shfl_up_sync(0xffffffffu, sy, 1);
+            const bool ok = (tid == 0 || tid >= nr) ? true : (sy - prev == 32);
+            const bool all_ok = __all_sync(0xffffffffu, ok);
+            s_sy[tid] = sy;
+            if (tid == 0) {
+                const int iy0 = dev_sat_short(sy >> 5) - 1;
+                s_regular = all_ok && nr == RC && iy0 >= 0 && (iy0 + nr - 1) < T.hbuf - 3;
             }
         }
         __syncthreads();
         if (k + 2 < n_chunks) issue_chunk(k + 2);
 
         // ---------------------------------------------------------- resample
-        if (remap && tid < n_cols) {
+        if (remap) {
             const int sy0 = s_sy[0];
-            const int iy0 = dev_sat_short(sy0 >> 5) - 1;
-            // regular chunk: unit row steps, one fy, every row interior -> sliding register window
-            if (s_regular) {
+            uint16_t *o = out_tile + ((int64_t)k * RC + 8 * rg) * P.out_pitch + qx;
+            if (s_regular && cols_regular && quad_interior) {
+                const int iy0 = (sy0 >> 5) - 1; // regular chunk: no saturation, rows iy0 + i
                 const int fy = sy0 & 31;
-                float wgt[4][4];
+                const f2 nz = *reinterpret_cast<const f2 *>(&s_tab[128]);
+                f2 W[4][4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) wgt[r][c] = __fmul_rn(s_tab[4 * fy + r], wx[c]);
-                int slot = (int)(iy0 - t_base) % RING;
-                float ra[4], rb[4], rc[4], rd[4];
-                auto load_row = [&](float(&dst)[4]) {
-                    const float *q = ring + (size_t)slot * SWC + cx;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) dst[c] = q[c];
+                    for (int c = 0; c < 4; ++c) {
+                        const float wv = __fmul_rn(s_tab[4 * fy + r], s_tab[4 * fx + c]);
+                        W[r][c] = pk(wv, wv);
+                    }
+                int slot = (iy0 + 8 * rg - t_base) % RING;
+                const float *col = ring + qx;
+                RowRegs R0, R1, R2, R3;
+                auto next_row = [&](RowRegs &R) {
+                    load_row_regs(R, col + slot * RW);
                     slot = slot + 1 == RING ? 0 : slot + 1;
                 };
-                load_row(ra);
-                load_row(rb);
-                load_row(rc);
-                uint16_t *o = out_col + (int64_t)k * RC * P.out_pitch;
-                if (col_int) {
-                    for (int i = 0; i < nr; i += 4) {
-                        load_row(rd);
-                        o[0] = cast_u16(cubic_interior(ra, rb, rc, rd, wgt));
-                        if (i + 1 < nr) { load_row(ra); o[P.out_pitch] = cast_u16(cubic_interior(rb, rc, rd, ra, wgt)); }
-                        if (i + 2 < nr) { load_row(rb); o[2 * P.out_pitch] = cast_u16(cubic_interior(rc, rd, ra, rb, wgt)); }
-                        if (i + 3 < nr) { load_row(rc); o[3 * P.out_pitch] = cast_u16(cubic_interior(rd, ra, rb, rc, wgt)); }
-                        o += 4 * P.out_pitch;
+                auto emit = [&](const RowRegs &a, const RowRegs &b, const RowRegs &c, const RowRegs &d) {
+                    f2 s01 = dot01(a, W[0], nz), s23 = dot23(a, W[0], nz);
+                    s01 = add2(s01, dot01(b, W[1], nz)); s23 = add2(s23, dot23(b, W[1], nz));
+                    s01 = add2(s01, dot01(c, W[2], nz)); s23 = add2(s23, dot23(c, W[2], nz));
+                    s01 = add2(s01, dot01(d, W[3], nz)); s23 = add2(s23, dot23(d, W[3], nz));
+                    const uint32_t p0 = cast_u16(lo_of(s01)), p1 = cast_u16(hi_of(s01));
+                    const uint32_t p2 = cast_u16(lo_of(s23)), p3 = cast_u16(hi_of(s23));
+                    if (out_vec) {
+                        *reinterpret_cast<uint2 *>(o) = make_uint2(p0 | (p1 << 16), p2 | (p3 << 16));
+                    } else {
+                        o[0] = (uint16_t)p0; o[1] = (uint16_t)p1; o[2] = (uint16_t)p2; o[3] = (uint16_t)p3;
                     }
-                } else {
-                    for (int i = 0; i < nr; i += 4) {
-                        load_row(rd);
-                        o[0] = cast_u16(cubic_border(ra, rb, rc, rd, wgt));
-                        if (i + 1 < nr) { load_row(ra); o[P.out_pitch] = cast_u16(cubic_border(rb, rc, rd, ra, wgt)); }
-                        if (i + 2 < nr) { load_row(rb); o[2 * P.out_pitch] = cast_u16(cubic_border(rc, rd, ra, rb, wgt)); }
-                        if (i + 3 < nr) { load_row(rc); o[3 * P.out_pitch] = cast_u16(cubic_border(rd, ra, rb, rc, wgt)); }
-                        o += 4 * P.out_pitch;
-                    }
+                    o += P.out_pitch;
+                };
+                next_row(R0);
+                next_row(R1);
+                next_row(R2);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    next_row(R3); emit(R0, R1, R2, R3);
+                    next_row(R0); emit(R1, R2, R3, R0);
+                    next_row(R1); emit(R2, R3, R0, R1);
+                    next_row(R2); emit(R3, R0, R1, R2);
                 }
             } else {
-                // general path: section edges, map rounding anomalies
-                uint16_t *o = out_col + (int64_t)k * RC * P.out_pitch;
-                for (int i = 0; i < nr; ++i, o += P.out_pitch) {
-                    const int sy = s_sy[i];
-                    const int iy = dev_sat_short(sy >> 5) - 1, fy = sy & 31;
-                    float wgt[4][4], v[4][4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int64_t t = (int64_t)iy + r;
-                        const bool in = t >= cr.t_lo && t <= cr.t_hi; // always true by construction
-                        const int slot = in ? (int)(t - t_base) % RING : 0;
-                        const float *q = ring + (size_t)slot * SWC + cx;
+                // exact generic path: borders, section edges, partial tiles/chunks, map anomalies
+                RingView V{ring, t_base, ix0, cr.t_lo, cr.t_hi};
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 8 * rg + i;
+                    if (row < nr) {
+                        const int sy = s_sy[row];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            wgt[r][c] = __fmul_rn(s_tab[4 * fy + r], wx[c]);
-                            v[r][c] = in ? q[c] : 0.f;
+                            const int xi = qx + c;
+                            if (xi < n_cols) {
+                                const int sx = cols_regular ? sx0 + 32 * xi : dev_map_fixed(T.x_begin + xi, dX);
+                                o[c] = (uint16_t)resample_px_general(V, s_tab, sx, sy, w, T.hbuf);
+                            }
                         }
                     }
-                    const bool row_int = (unsigned)iy < (unsigned)max(T.hbuf - 3, 0);
-                    float s = (row_int && col_int) ? cubic_interior(v[0], v[1], v[2], v[3], wgt)
-                                                   : cubic_border(v[0], v[1], v[2], v[3], wgt);
-                    *o = cast_u16(s);
+                    o += P.out_pitch;
                 }
             }
         }
@@ -582,7 +735,7 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         rc = pan::build_tiles(d, tiles);
         if (rc) return rc;
         pan::upload_tab();
-        size_t bytes = tiles.size() * sizeof(pan::Tile) + 512;
+        size_t bytes = tiles.size() * sizeof(pan::Tile) + 1024;
         if (bytes > ctx->d_plan_cap) {
             if (ctx->d_plan) { OIP_CUDA(cudaStreamSynchronize(ctx->stream)); OIP_CUDA(cudaFree(ctx->d_plan)); ctx->d_plan = nullptr; }
             OIP_CUDA(cudaMalloc(&ctx->d_plan, bytes * 2));
@@ -590,9 +743,12 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         }
         // pageable sources: cudaMemcpyAsync stages them before returning, and the copies are ordered
         // on the compute stream behind any kernel still reading the previous plan
-        OIP_CUDA(cudaMemcpyAsync(ctx->d_plan, pan::g_tab_host, 512, cudaMemcpyHostToDevice, ctx->stream));
+        float hdr[256] = {};
+        memcpy(hdr, pan::g_tab_host, 512);
+        hdr[128] = hdr[129] = -0.0f; // run-time (-0.0,-0.0) addend of the packed products, see mul2()
+        OIP_CUDA(cudaMemcpyAsync(ctx->d_plan, hdr, 1024, cudaMemcpyHostToDevice, ctx->stream));
         if (!tiles.empty())
-            OIP_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_plan + 512, tiles.data(), tiles.size() * sizeof(pan::Tile),
+            OIP_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_plan + 1024, tiles.data(), tiles.size() * sizeof(pan::Tile),
                                      cudaMemcpyHostToDevice, ctx->stream));
         ctx->plan_key.assign(kb, kb + sizeof key);
         ctx->plan_tiles = (int64_t)tiles.size();
@@ -615,11 +771,11 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         }
     }
     P.tab = reinterpret_cast<const float *>(ctx->d_plan);
-    P.tiles = reinterpret_cast<const pan::Tile *>((const uint8_t *)ctx->d_plan + 512);
+    P.tiles = reinterpret_cast<const pan::Tile *>((const uint8_t *)ctx->d_plan + 1024);
     P.out = d->d_out; P.out_pitch = d->out_pitch_px; P.out_row0 = d->row0;
     P.err = ctx->d_err; P.w = d->w; P.n_ccd = d->n_ccd; P.bulk_ok = bulk_ok ? 1 : 0;
 
-    const size_t smem = (size_t)pan::RING * pan::SWC * 4 + 2 * (size_t)pan::STG * pan::SWC * 2;
+    const size_t smem = (size_t)pan::RING * pan::RW * 4 + 2 * (size_t)pan::STG * pan::SWC * 2;
     if (!ctx->pan_attr_set) {
         OIP_CUDA(cudaFuncSetAttribute(pan::pan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->pan_attr_set = true;
