@@ -6,17 +6,18 @@
 //   load     TMA-unit bulk copies (cp.async.bulk, SASS UBLKCP) stage the raw source rows of the next
 //            two chunks in shared memory behind an mbarrier while the current chunk is processed:
 //            every source byte is read from HBM once per column strip (halo columns hit L2)
-//   convert  a thread takes 8 adjacent detectors of one row: byte swap (PRMT), fp64 RRC with (k,b)
-//            held in registers (ref imageop.h:134), result as float into a 40-row ring
-//   resample a thread owns 4 output columns x 8 rows, slides a 4-row window down the ring with
-//            128-bit shared loads and evaluates OpenCV's bicubic sum in OpenCV's own order
-//             with packed FMUL2/FADD2 (two pixels per instruction, same IEEE roundings)
+//   convert  byte swap (one PRMT per sample) + fp64 RRC with (k,b) held in registers
+//            (ref imageop.h:134); results go as floats into a 40-row ring laid out as LANE PAIRS:
+//            ring slot s of a row holds (column s, column s+HALF) of the tile's source window
+//   resample a thread owns 2 slots x 8 rows = 32 pixels; 128-bit shared loads deliver ready-made
+//            packed operands, so OpenCV's bicubic sum (its own order, no FMA) runs as
+//            FMUL2/FADD2 on pixel pairs (left half, right half) with no register shuffling at all
 //
 // The kernel is instruction-issue bound, not HBM bound (profiles/): everything here is about
 // instructions per pixel.  No intermediate (.RRC.RAW, .PRESTT.RAW) ever exists in HBM.  CCDs that
 // are not shifted use COPY tiles: same staging, RRC, 128-bit stores to their trimmed position.
 //
-// Irregular situations (map rounding anomalies, section/image borders, partial tiles, unaligned or
+// Irregular situations (map rounding anomalies, section/image borders, partial chunks, unaligned or
 // packed inputs) take exact but slower generic paths inside the same kernel.
 #include "oip_common.cuh"
 #include "pan_plan.hpp"
@@ -24,16 +25,25 @@
 namespace oip {
 namespace pan {
 
-constexpr int TW = 256;   // output columns per tile
-constexpr int RW = 264;   // float ring width: TW + 3 taps + 1 (map anomaly) rounded to 8
-constexpr int SWC = 272;  // staged source columns: RW + up to 7 columns of 16-byte alignment slack
-constexpr int RC = 32;    // output rows per chunk
-constexpr int RING = 40;  // float ring rows (>= RC + 3 + 1)
-constexpr int STG = 40;   // raw staging rows per buffer (first chunk needs RC + 4)
-constexpr int NT = 256;   // threads per CTA
-constexpr int TH = 512;   // output rows per tile
-constexpr int CV_G = RW / 8;          // 33 column octets per ring row
-constexpr int CV_PH = NT / CV_G;      // 7 row phases in the convert step (231 threads busy)
+#ifndef OIP_PAN_NT
+#define OIP_PAN_NT 128
+#endif
+constexpr int NT = OIP_PAN_NT;         // threads per CTA; everything below derives from it
+constexpr int CTAS_PER_SM = NT == 128 ? 4 : 2;
+constexpr int SLOTS = NT / 2;          // ring slots per row; slot s = (window col s, window col s+HALF)
+constexpr int HALF = SLOTS - 4;        // lane 0 = tile columns [0,HALF), lane 1 = [HALF,TW); +3 taps +1 (map anomaly)
+constexpr int TW = 2 * HALF;           // output columns per tile
+constexpr int SRC_W = TW + 4;          // source columns of the window
+constexpr int SWC = (SRC_W + 7 + 7) / 8 * 8; // staged columns: + up to 7 columns of 16-byte alignment slack
+constexpr int RC = 32;                 // output rows per chunk
+constexpr int RING = 40;               // ring rows (>= RC + 3 + 1)
+constexpr int STG = 40;                // raw staging rows per buffer (first chunk needs RC + 4)
+constexpr int TH = 512;                // output rows per tile
+constexpr int CV_Q = SLOTS / 4;        // convert step: slot quads per row (power of two)
+constexpr int CV_PH = NT / CV_Q;       // convert step: row phases (8)
+constexpr int RS_CG = SLOTS / 2;       // resample step: threads per row group (HALF/2 of them active)
+constexpr int NWARPS = NT / 32;
+static_assert((CV_Q & (CV_Q - 1)) == 0 && NT / RS_CG == 4 && CV_PH == 8, "thread mapping");
 
 enum { KIND_COPY = 0, KIND_REMAP = 1 };
 
@@ -65,7 +75,7 @@ struct Params {
     const Tile *tiles;
     uint16_t *out;
     int64_t out_pitch, out_row0;
-    const float *tab; // 32x4 cubic weights
+    const float *tab; // 32x4 cubic weights, then the run-time (-0.0,-0.0) pair
     int *err;
     int32_t w, n_ccd, bulk_ok;
 };
@@ -181,7 +191,7 @@ __device__ __forceinline__ float hi_of(f2 v)
 // explicit .rn only for scalar ops), and it also folds fma(a,b,-0.0) back into a mul when the -0.0 is
 // a known constant.  The product is therefore an FMA whose addend is a (-0.0,-0.0) pair LOADED AT RUN
 // TIME (plan header): RN(a*b + -0.0) == RN(a*b) bit for bit, and an FMA cannot be fused with the add
-// that follows.  SASS check: FFMA2 count == FMUL2 would-be count, FADD2 count unchanged.
+// that follows.  SASS check: FFMA2 count == number of products, FADD2 count == number of sums.
 __device__ __forceinline__ f2 mul2(f2 a, f2 b, f2 nz)
 {
     f2 r;
@@ -195,28 +205,22 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b)
     return r;
 }
 
-// one ring row as seen by a thread that owns output columns 4g..4g+3: source columns q0..q6
+// ring slots s..s+4 of one row, each an (left-half pixel, right-half pixel) pair
 struct RowRegs {
-    f2 A0, A1, A2; // (q0,q1) (q2,q3) (q4,q5)   straight from the two 128-bit loads
-    f2 B0, B1, B2; // (q1,q2) (q3,q4) (q5,q6)   re-paired copies
+    f2 S[5];
 };
-__device__ __forceinline__ void load_row_regs(RowRegs &R, const float *p)
+__device__ __forceinline__ void load_row_regs(RowRegs &R, const f2 *p)
 {
-    f2 a3;
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(R.A0), "=l"(R.A1) : "r"(smem_u32(p)));
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(R.A2), "=l"(a3) : "r"(smem_u32(p + 4)));
-    R.B0 = pk(hi_of(R.A0), lo_of(R.A1));
-    R.B1 = pk(hi_of(R.A1), lo_of(R.A2));
-    R.B2 = pk(hi_of(R.A2), lo_of(a3));
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(R.S[0]), "=l"(R.S[1]) : "r"(smem_u32(p)));
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(R.S[2]), "=l"(R.S[3]) : "r"(smem_u32(p + 2)));
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(R.S[4]) : "r"(smem_u32(p + 4)));
 }
-// per-row dot products in OpenCV's interior order ((s0*w0 + s1*w1) + s2*w2) + s3*w3, pixels (0,1) and (2,3)
-__device__ __forceinline__ f2 dot01(const RowRegs &R, const f2 (&W)[4], f2 nz)
+// per-row dot product in OpenCV's interior order ((s0*w0 + s1*w1) + s2*w2) + s3*w3 for output slot o (0 or 1)
+template <int O>
+__device__ __forceinline__ f2 dot_row(const RowRegs &R, const f2 (&W)[4], f2 nz)
 {
-    return add2(add2(add2(mul2(R.A0, W[0], nz), mul2(R.B0, W[1], nz)), mul2(R.A1, W[2], nz)), mul2(R.B1, W[3], nz));
-}
-__device__ __forceinline__ f2 dot23(const RowRegs &R, const f2 (&W)[4], f2 nz)
-{
-    return add2(add2(add2(mul2(R.A1, W[0], nz), mul2(R.B1, W[1], nz)), mul2(R.A2, W[2], nz)), mul2(R.B2, W[3], nz));
+    return add2(add2(add2(mul2(R.S[O], W[0], nz), mul2(R.S[O + 1], W[1], nz)), mul2(R.S[O + 2], W[2], nz)),
+                mul2(R.S[O + 3], W[3], nz));
 }
 
 __device__ __forceinline__ uint32_t cast_u16(float s)
@@ -224,11 +228,14 @@ __device__ __forceinline__ uint32_t cast_u16(float s)
     return (uint32_t)max(0, min(65535, __float2int_rn(s))); // cvRound + saturate_cast<ushort>
 }
 
+// ring addressing: source-window column sc (0..SRC_W) -> float index inside a ring row
+__device__ __forceinline__ int ring_idx(int sc) { return sc < SLOTS ? 2 * sc : 2 * (sc - HALF) + 1; }
+
 // generic single-pixel bicubic from the ring (any alignment, border or interior order)
 struct RingView {
     const float *ring;
-    int t_base;  // buffer row held in ring slot 0 (mod RING)
-    int ix0;     // source column held in ring column 0
+    int t_base; // buffer row held in ring row 0 (mod RING)
+    int ix0;    // source column of window column 0
     int t_lo, t_hi;
 };
 __device__ __forceinline__ uint32_t resample_px_general(const RingView &V, const float *s_tab, int sx, int sy, int w,
@@ -244,9 +251,9 @@ __device__ __forceinline__ uint32_t resample_px_general(const RingView &V, const
         const int slot = rin ? (t - V.t_base) % RING : 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int rc = ix + c - V.ix0;
-            const bool in = rin && rc >= 0 && rc < RW;
-            v[r][c] = in ? V.ring[slot * RW + rc] : 0.f;
+            const int sc = ix + c - V.ix0;
+            const bool in = rin && sc >= 0 && sc < SRC_W;
+            v[r][c] = in ? V.ring[slot * (2 * SLOTS) + ring_idx(sc)] : 0.f;
             wg[r][c] = __fmul_rn(s_tab[4 * fy + r], s_tab[4 * fx + c]);
         }
     }
@@ -272,18 +279,17 @@ __device__ __forceinline__ uint32_t resample_px_general(const RingView &V, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// convert: 8 raw samples (5 staged words, first sample at halfword `odd`) -> RRC -> 8 values
+// convert helpers: staged halfwords -> zero-extended (byte-swapped) samples, 8-wide fp64 RRC
 // ---------------------------------------------------------------------------------------------
-template <bool SWAP, bool ODD>
-__device__ __forceinline__ void extract8(const uint32_t (&wd)[5], uint32_t (&s)[8])
+// N samples starting at halfword (ODD ? 1 : 0) of wd[]; one PRMT does select + swap + zero extension
+template <bool SWAP, bool ODD, int N, int NW>
+__device__ __forceinline__ void extract(const uint32_t (&wd)[NW], uint32_t *s)
 {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < N; ++j) {
         const int h = (ODD ? 1 : 0) + j;
-        const uint32_t word = wd[h >> 1];
-        // one PRMT does halfword select + byte swap + zero extension
         const uint32_t sel = (h & 1) ? (SWAP ? 0x4423u : 0x4432u) : (SWAP ? 0x4401u : 0x4410u);
-        s[j] = __byte_perm(word, 0u, sel);
+        s[j] = __byte_perm(wd[h >> 1], 0u, sel);
     }
 }
 
@@ -297,7 +303,8 @@ __device__ __forceinline__ void rrc8(uint32_t (&s)[8], const double (&k)[8], con
         v[j] = __dadd_rn(__dmul_rn(k[j], sd), b[j]);
         hmax = max(hmax, (uint32_t)__double2hiint(v[j]));
     }
-    if (hmax < 0x41E00000u) { // all eight in [0, 2^31): exact truncation with one DADD.RZ each
+    // every value of the warp in [0, 2^31): exact truncation with one DADD.RZ each (warp-uniform branch)
+    if (!__any_sync(__activemask(), hmax >= 0x41E00000u)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] = (uint32_t)__double2loint(__dadd_rz(v[j], 4503599627370496.0));
     } else {
@@ -309,11 +316,11 @@ __device__ __forceinline__ void rrc8(uint32_t (&s)[8], const double (&k)[8], con
     }
 }
 
-__global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Params P)
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) pan_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    float *ring = reinterpret_cast<float *>(smem);                          // RING x RW f32
-    uint16_t *stg = reinterpret_cast<uint16_t *>(smem + RING * RW * 4);     // 2 x STG x SWC u16
+    float *ring = reinterpret_cast<float *>(smem);                               // RING x SLOTS float2
+    uint16_t *stg = reinterpret_cast<uint16_t *>(smem + RING * SLOTS * 8);       // 2 x STG x SWC u16
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ __align__(8) float s_tab[132]; // 32x4 weights + the (-0.0,-0.0) pair at [128..129]
     __shared__ uint8_t s_rowzero[2][STG];
@@ -330,14 +337,14 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
     const bool do_rrc = C.kb != nullptr;
     const double dX = C.dX, dY = C.dY;
 
-    if (tid < 130) s_tab[tid] = P.tab[tid];
+    for (int i = tid; i < 130; i += NT) s_tab[i] = P.tab[i];
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        mbar_init(&bars[0], NWARPS); // one arrive.expect_tx per warp (each warp issues its share of the rows)
+        mbar_init(&bars[1], NWARPS);
         fence_mbar_init();
     }
 
-    // ---- column geometry: ring column 0 <-> source column ix0; staging column 0 <-> c_lo
+    // ---- column geometry: window column 0 <-> source column ix0; staging column 0 <-> c_lo
     const int n_cols = T.x_end - T.x_begin;
     const int sx0 = remap ? dev_map_fixed(T.x_begin, dX) : 0;
     const int ix0 = remap ? dev_sat_short(sx0 >> 5) - 1 : T.x_begin;
@@ -348,31 +355,29 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
 
     // column-regular tile: the fixed-point column map advances by exactly one source pixel per
     // output pixel (always true except where float(x + dX) rounds across a 1/32 boundary)
-    bool my_cols_regular = true;
-    if (remap) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int xi = tid + j * NT; // 0..n_cols
-            if (xi < n_cols && dev_map_fixed(T.x_begin + xi, dX) != sx0 + 32 * xi) my_cols_regular = false;
-        }
-    }
-    const bool cols_regular = __syncthreads_and(my_cols_regular) != 0; // also publishes s_tab / barriers
+    bool my_col_regular = true;
+    if (remap && tid < n_cols) my_col_regular = dev_map_fixed(T.x_begin + tid, dX) == sx0 + 32 * tid;
+    const bool cols_regular = __syncthreads_and(my_col_regular) != 0; // also publishes s_tab / barriers
 
-    // ---- convert-step mapping: (column octet g, row phase ph), RRC coefficients in registers
-    const int cvt_groups = remap ? CV_G : TW / 8;
-    const int cv_g = tid % cvt_groups, cv_ph = tid / cvt_groups;
-    const int cv_phases = NT / cvt_groups;
-    const bool cv_active = cv_ph < cv_phases;
+    // ---- convert-step mapping and RRC coefficients (registers)
+    //  REMAP: thread = (slot quad q, row phase): window columns 4q..4q+3 (lane 0) and 4q+HALF.. (lane 1)
+    //  COPY : thread = (column octet q, row phase): tile columns 8q..8q+7
+    const int cv_q = tid & (CV_Q - 1), cv_ph = tid / CV_Q;
+    int cv_col[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cv_col[j] = remap ? (4 * cv_q + (j & 3) + (j >> 2) * HALF) : (8 * cv_q + j);
     double kk[8], bb[8];
-    uint32_t col_mask = 0; // bit j: column is inside the CCD
+    bool cols_all_valid = true;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = ix0 + 8 * cv_g + j;
+        const int c = ix0 + cv_col[j];
         const bool ok = c >= 0 && c < w;
-        col_mask |= ok ? (1u << j) : 0u;
+        cols_all_valid = cols_all_valid && ok;
         kk[j] = (ok && do_rrc) ? C.kb[2 * c] : (ok ? 1.0 : 0.0); // k = b = 0 zeroes columns outside the CCD
         bb[j] = (ok && do_rrc) ? C.kb[2 * c + 1] : 0.0;
     }
+    const bool need_rrc = do_rrc || !cols_all_valid;
+    const bool cv_active = remap ? true : (8 * cv_q < n_cols);
 
     // ------------------------------------------------------------------ loader
     auto issue_chunk = [&](int k) {
@@ -382,34 +387,26 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
         uint64_t *bar = &bars[k & 1];
         const int64_t row_bias = remap ? 0 : T.j0; // COPY rows are tile-relative
         if (bulk) {
-            if (tid < 32) {
-                const int ca = max(c_lo, 0), cb = min(c_lo + SWC, w);
-                const uint32_t nb = cb > ca ? (uint32_t)(cb - ca) * 2u : 0u;
-                const uint8_t *ptr[2] = {nullptr, nullptr};
-                uint32_t mine = 0;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int r = tid + 32 * i;
-                    if (r < cr.n_new) {
-                        const int64_t g = local_to_global(T, row_bias + cr.new_lo + r);
-                        const uint8_t *q = (g >= 0 && nb) ? row_ptr(C, g) : nullptr;
-                        if (g >= 0 && nb && !q) atomicExch(P.err, 1); // host failed to supply a needed row
-                        ptr[i] = q;
-                        rz[r] = q == nullptr;
-                        if (q) mine += nb;
-                    }
-                }
-                uint32_t total = mine;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-                if (tid == 0) mbar_arrive_expect_tx(bar, total);
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int r = tid + 32 * i;
-                    if (ptr[i]) bulk_g2s(buf + (size_t)r * SWC + (ca - c_lo), ptr[i] + 2 * (int64_t)ca, nb, bar);
-                }
+            // every warp issues rows wid, wid+8, ... (lane i takes the i-th of them): the issue loop is
+            // serialised per lane by the uniform datapath, so spreading it keeps one warp from
+            // becoming the straggler at the next barrier
+            const int lane = tid & 31, wid = tid >> 5;
+            const int ca = max(c_lo, 0), cb = min(c_lo + SWC, w);
+            const uint32_t nb = cb > ca ? (uint32_t)(cb - ca) * 2u : 0u;
+            const int r = wid + NWARPS * lane;
+            const uint8_t *q = nullptr;
+            if (r < cr.n_new) {
+                const int64_t g = local_to_global(T, row_bias + cr.new_lo + r);
+                q = (g >= 0 && nb) ? row_ptr(C, g) : nullptr;
+                if (g >= 0 && nb && !q) atomicExch(P.err, 1); // host failed to supply a needed row
+                rz[r] = q == nullptr;
             }
+            uint32_t total = q ? nb : 0u;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            if (lane == 0) mbar_arrive_expect_tx(bar, total);
+            __syncwarp();
+            if (q) bulk_g2s(buf + (size_t)r * SWC + (ca - c_lo), q + 2 * (int64_t)ca, nb, bar);
         } else {
             // generic loader: any alignment / packed / tile layouts; native byte order in staging
             for (int r = 0; r < cr.n_new; ++r) {
@@ -431,15 +428,20 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
     if (n_chunks > 1) issue_chunk(1);
     __syncthreads();
 
-    // ---- resample-step mapping: thread = (column quad cg, row group rg) -> 4 columns x 8 rows
-    const int cg = tid & 63, rg = tid >> 6;
-    const int qx = 4 * cg; // first of my 4 tile columns
-    // my 4 pixels are on the packed fast path iff they exist and all their 4x4 footprints are inside the CCD
-    const bool quad_full = qx + 3 < n_cols;
-    const bool quad_interior = quad_full && (ix0 + qx) >= 0 && (ix0 + qx + 3) < w - 3;
+    // ---- resample-step mapping: thread = (slot pair cg, row group rg) -> slots 2cg,2cg+1 x 8 rows
+    //      = tile columns {2cg, 2cg+1} (lane 0) and {HALF+2cg, HALF+2cg+1} (lane 1)
+    const int cg = tid & (RS_CG - 1), rg = tid / RS_CG;
+    const bool rs_active = cg < HALF / 2;
+    const int xl = 2 * cg, xr = HALF + 2 * cg; // my left / right column pairs
+    // pixels that exist and whose 4x4 footprint is inside the CCD may use the packed interior path
+    auto col_interior = [&](int xi) { return (ix0 + xi) >= 0 && (ix0 + xi) < w - 3; };
+    const bool l_exists = xl < n_cols, r_exists = xr < n_cols; // pairs exist or not as a whole when n_cols is even
+    const bool pair_whole = ((n_cols & 1) == 0);
+    const bool fast_ok = rs_active && cols_regular && pair_whole && l_exists &&
+                         col_interior(xl) && col_interior(xl + 1) && (!r_exists || (col_interior(xr) && col_interior(xr + 1)));
     const int fx = sx0 & 31;
     uint16_t *const out_tile = P.out + (T.g0 - P.out_row0) * P.out_pitch + T.out_x;
-    const bool out_vec = ((((uintptr_t)P.out) & 7) == 0) && ((P.out_pitch & 3) == 0) && ((T.out_x & 3) == 0);
+    const bool out_vec2 = ((((uintptr_t)P.out) & 3) == 0) && ((P.out_pitch & 1) == 0) && ((T.out_x & 1) == 0);
 
     for (int k = 0; k < n_chunks; ++k) {
         const ChunkRows cr = chunk_rows(T, dY, k);
@@ -451,41 +453,52 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
         if (cv_active) {
             const uint16_t *buf = stg + (size_t)(k & 1) * STG * SWC;
             const uint8_t *rz = s_rowzero[k & 1];
-            const int h0 = delta + 8 * cv_g; // staging halfword of my first column
-            for (int r = cv_ph; r < cr.n_new; r += cv_phases) {
+            const bool odd = (delta & 1) != 0;
+            for (int r = cv_ph; r < cr.n_new; r += CV_PH) {
                 uint32_t s[8];
-                const bool z = rz[r] != 0;
-                if (!z) {
-                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (size_t)r * SWC) + (h0 >> 1);
-                    uint32_t wd[5];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) wd[i] = wp[i];
-                    wd[4] = (h0 & 1) ? wp[4] : 0u;
-                    if (h0 & 1) {
-                        if (swap) extract8<true, true>(wd, s); else extract8<false, true>(wd, s);
+                if (rz[r] == 0) {
+                    const uint32_t *row32 = reinterpret_cast<const uint32_t *>(buf + (size_t)r * SWC);
+                    if (remap) {
+                        const uint32_t *wa = row32 + ((delta + 4 * cv_q) >> 1);
+                        const uint32_t *wb = wa + HALF / 2;
+                        uint32_t a[3] = {wa[0], wa[1], odd ? wa[2] : 0u};
+                        uint32_t b[3] = {wb[0], wb[1], odd ? wb[2] : 0u};
+                        if (odd) {
+                            if (swap) { extract<true, true, 4, 3>(a, s); extract<true, true, 4, 3>(b, s + 4); }
+                            else { extract<false, true, 4, 3>(a, s); extract<false, true, 4, 3>(b, s + 4); }
+                        } else {
+                            if (swap) { extract<true, false, 4, 3>(a, s); extract<true, false, 4, 3>(b, s + 4); }
+                            else { extract<false, false, 4, 3>(a, s); extract<false, false, 4, 3>(b, s + 4); }
+                        }
                     } else {
-                        if (swap) extract8<true, false>(wd, s); else extract8<false, false>(wd, s);
+                        const uint32_t *wp = row32 + ((delta + 8 * cv_q) >> 1);
+                        uint32_t wd[5] = {wp[0], wp[1], wp[2], wp[3], odd ? wp[4] : 0u};
+                        if (odd) {
+                            if (swap) extract<true, true, 8, 5>(wd, s); else extract<false, true, 8, 5>(wd, s);
+                        } else {
+                            if (swap) extract<true, false, 8, 5>(wd, s); else extract<false, false, 8, 5>(wd, s);
+                        }
                     }
-                    if (do_rrc || col_mask != 0xFFu) rrc8(s, kk, bb);
+                    if (need_rrc) rrc8(s, kk, bb);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) s[j] = 0;
                 }
                 if (remap) {
                     const int slot = (cr.new_lo + r - t_base) % RING;
-                    float4 o0, o1;
-                    o0.x = u16_to_f32(s[0] & 0xFFFFu); o0.y = u16_to_f32(s[1] & 0xFFFFu);
-                    o0.z = u16_to_f32(s[2] & 0xFFFFu); o0.w = u16_to_f32(s[3] & 0xFFFFu);
-                    o1.x = u16_to_f32(s[4] & 0xFFFFu); o1.y = u16_to_f32(s[5] & 0xFFFFu);
-                    o1.z = u16_to_f32(s[6] & 0xFFFFu); o1.w = u16_to_f32(s[7] & 0xFFFFu);
-                    float4 *dst = reinterpret_cast<float4 *>(ring + (size_t)slot * RW + 8 * cv_g);
+                    float4 o0, o1; // (slot 4q: L,R) (slot 4q+1: L,R) | (slot 4q+2) (slot 4q+3)
+                    o0.x = u16_to_f32(s[0] & 0xFFFFu); o0.y = u16_to_f32(s[4] & 0xFFFFu);
+                    o0.z = u16_to_f32(s[1] & 0xFFFFu); o0.w = u16_to_f32(s[5] & 0xFFFFu);
+                    o1.x = u16_to_f32(s[2] & 0xFFFFu); o1.y = u16_to_f32(s[6] & 0xFFFFu);
+                    o1.z = u16_to_f32(s[3] & 0xFFFFu); o1.w = u16_to_f32(s[7] & 0xFFFFu);
+                    float4 *dst = reinterpret_cast<float4 *>(ring + (size_t)slot * (2 * SLOTS) + 8 * cv_q);
                     dst[0] = o0;
                     dst[1] = o1;
                 } else {
                     // COPY tile: straight to the output raster
-                    uint16_t *orow = out_tile + (int64_t)(cr.new_lo + r) * P.out_pitch + 8 * cv_g;
-                    if (out_vec && ((T.out_x & 7) == 0) && ((P.out_pitch & 7) == 0) && ((((uintptr_t)P.out) & 15) == 0) &&
-                        8 * cv_g + 8 <= n_cols) {
+                    uint16_t *orow = out_tile + (int64_t)(cr.new_lo + r) * P.out_pitch + 8 * cv_q;
+                    if (((T.out_x & 7) == 0) && ((P.out_pitch & 7) == 0) && ((((uintptr_t)P.out) & 15) == 0) &&
+                        8 * cv_q + 8 <= n_cols) {
                         uint4 o;
                         o.x = (s[0] & 0xFFFFu) | (s[1] << 16);
                         o.y = (s[2] & 0xFFFFu) | (s[3] << 16);
@@ -495,7 +508,7 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
                     } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            if (8 * cv_g + j < n_cols) orow[j] = (uint16_t)s[j];
+                            if (8 * cv_q + j < n_cols) orow[j] = (uint16_t)s[j];
                     }
                 }
             }
@@ -517,11 +530,11 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
         if (k + 2 < n_chunks) issue_chunk(k + 2);
 
         // ---------------------------------------------------------- resample
-        if (remap) {
+        if (remap && rs_active) {
             const int sy0 = s_sy[0];
-            uint16_t *o = out_tile + ((int64_t)k * RC + 8 * rg) * P.out_pitch + qx;
-            if (s_regular && cols_regular && quad_interior) {
-                const int iy0 = (sy0 >> 5) - 1; // regular chunk: no saturation, rows iy0 + i
+            uint16_t *o = out_tile + ((int64_t)k * RC + 8 * rg) * P.out_pitch;
+            if (s_regular && fast_ok) {
+                const int iy0 = (sy0 >> 5) - 1; // regular chunk: no saturation, tap rows iy0 + i
                 const int fy = sy0 & 31;
                 const f2 nz = *reinterpret_cast<const f2 *>(&s_tab[128]);
                 f2 W[4][4];
@@ -533,23 +546,25 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
                         W[r][c] = pk(wv, wv);
                     }
                 int slot = (iy0 + 8 * rg - t_base) % RING;
-                const float *col = ring + qx;
+                const f2 *col = reinterpret_cast<const f2 *>(ring) + 2 * cg;
                 RowRegs R0, R1, R2, R3;
                 auto next_row = [&](RowRegs &R) {
-                    load_row_regs(R, col + slot * RW);
+                    load_row_regs(R, col + slot * SLOTS);
                     slot = slot + 1 == RING ? 0 : slot + 1;
                 };
                 auto emit = [&](const RowRegs &a, const RowRegs &b, const RowRegs &c, const RowRegs &d) {
-                    f2 s01 = dot01(a, W[0], nz), s23 = dot23(a, W[0], nz);
-                    s01 = add2(s01, dot01(b, W[1], nz)); s23 = add2(s23, dot23(b, W[1], nz));
-                    s01 = add2(s01, dot01(c, W[2], nz)); s23 = add2(s23, dot23(c, W[2], nz));
-                    s01 = add2(s01, dot01(d, W[3], nz)); s23 = add2(s23, dot23(d, W[3], nz));
-                    const uint32_t p0 = cast_u16(lo_of(s01)), p1 = cast_u16(hi_of(s01));
-                    const uint32_t p2 = cast_u16(lo_of(s23)), p3 = cast_u16(hi_of(s23));
-                    if (out_vec) {
-                        *reinterpret_cast<uint2 *>(o) = make_uint2(p0 | (p1 << 16), p2 | (p3 << 16));
+                    f2 p0 = dot_row<0>(a, W[0], nz), p1 = dot_row<1>(a, W[0], nz);
+                    p0 = add2(p0, dot_row<0>(b, W[1], nz)); p1 = add2(p1, dot_row<1>(b, W[1], nz));
+                    p0 = add2(p0, dot_row<0>(c, W[2], nz)); p1 = add2(p1, dot_row<1>(c, W[2], nz));
+                    p0 = add2(p0, dot_row<0>(d, W[3], nz)); p1 = add2(p1, dot_row<1>(d, W[3], nz));
+                    const uint32_t l0 = cast_u16(lo_of(p0)), l1 = cast_u16(lo_of(p1));
+                    const uint32_t r0 = cast_u16(hi_of(p0)), r1 = cast_u16(hi_of(p1));
+                    if (out_vec2) {
+                        *reinterpret_cast<uint32_t *>(o + xl) = l0 | (l1 << 16);
+                        if (r_exists) *reinterpret_cast<uint32_t *>(o + xr) = r0 | (r1 << 16);
                     } else {
-                        o[0] = (uint16_t)p0; o[1] = (uint16_t)p1; o[2] = (uint16_t)p2; o[3] = (uint16_t)p3;
+                        o[xl] = (uint16_t)l0; o[xl + 1] = (uint16_t)l1;
+                        if (r_exists) { o[xr] = (uint16_t)r0; o[xr + 1] = (uint16_t)r1; }
                     }
                     o += P.out_pitch;
                 };
@@ -564,7 +579,7 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
                     next_row(R2); emit(R3, R0, R1, R2);
                 }
             } else {
-                // exact generic path: borders, section edges, partial tiles/chunks, map anomalies
+                // exact generic path: borders, section edges, partial chunks, odd widths, map anomalies
                 RingView V{ring, t_base, ix0, cr.t_lo, cr.t_hi};
                 for (int i = 0; i < 8; ++i) {
                     const int row = 8 * rg + i;
@@ -572,10 +587,10 @@ __global__ void __launch_bounds__(NT, 2) pan_kernel(const __grid_constant__ Para
                         const int sy = s_sy[row];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            const int xi = qx + c;
+                            const int xi = (c < 2 ? xl : xr) + (c & 1);
                             if (xi < n_cols) {
                                 const int sx = cols_regular ? sx0 + 32 * xi : dev_map_fixed(T.x_begin + xi, dX);
-                                o[c] = (uint16_t)resample_px_general(V, s_tab, sx, sy, w, T.hbuf);
+                                o[xi] = (uint16_t)resample_px_general(V, s_tab, sx, sy, w, T.hbuf);
                             }
                         }
                     }
@@ -613,12 +628,17 @@ static int build_tiles(const oip_pan_desc *d, std::vector<Tile> &tiles)
             int64_t g0 = std::max<int64_t>(s.g0, d->row0), g1 = std::min<int64_t>(s.g1, d->row0 + d->n_rows);
             for (int64_t g = g0; g < g1; g += TH) {
                 int nr = (int)std::min<int64_t>(TH, g1 - g);
-                for (int x = lo; x < hi; x += TW) {
+                // column strips of equal width (no skinny last strip); even for the 32-bit paired
+                // stores of REMAP tiles, multiple of 8 for the 128-bit stores of COPY tiles
+                const int n_strips = (hi - lo + TW - 1) / TW;
+                const int align = shifted ? 2 : 8;
+                const int sw = std::min(TW, ((hi - lo + n_strips - 1) / n_strips + align - 1) / align * align);
+                for (int x = lo; x < hi; x += sw) {
                     Tile t{};
                     t.ccd = i;
                     t.kind = shifted ? KIND_REMAP : KIND_COPY;
                     t.x_begin = x;
-                    t.x_end = std::min(hi, x + TW);
+                    t.x_end = std::min(hi, x + sw);
                     t.out_x = out_x + (x - lo);
                     t.n_rows = nr;
                     t.g0 = g;
@@ -775,7 +795,7 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
     P.out = d->d_out; P.out_pitch = d->out_pitch_px; P.out_row0 = d->row0;
     P.err = ctx->d_err; P.w = d->w; P.n_ccd = d->n_ccd; P.bulk_ok = bulk_ok ? 1 : 0;
 
-    const size_t smem = (size_t)pan::RING * pan::RW * 4 + 2 * (size_t)pan::STG * pan::SWC * 2;
+    const size_t smem = (size_t)pan::RING * pan::SLOTS * 8 + 2 * (size_t)pan::STG * pan::SWC * 2;
     if (!ctx->pan_attr_set) {
         OIP_CUDA(cudaFuncSetAttribute(pan::pan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->pan_attr_set = true;
