@@ -37,6 +37,8 @@ constexpr int SRC_W = TW + 4;          // source columns of the window
 constexpr int SWC = (SRC_W + 7 + 7) / 8 * 8; // staged columns: + up to 7 columns of 16-byte alignment slack
 constexpr int RC = 32;                 // output rows per chunk
 constexpr int RING = 40;               // ring rows (>= RC + 3 + 1)
+constexpr int RING_MIRROR = 10;        // ring rows 0..9 are mirrored behind row RING-1: a thread's 11-row run never wraps
+constexpr int RING_ROWS = RING + RING_MIRROR;
 constexpr int STG = 40;                // raw staging rows per buffer (first chunk needs RC + 4)
 constexpr int TH = 512;                // output rows per tile
 constexpr int CV_Q = SLOTS / 4;        // convert step: slot quads per row (power of two)
@@ -316,16 +318,101 @@ __device__ __forceinline__ void rrc8(uint32_t (&s)[8], const double (&k)[8], con
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// convert step: one thread-item = 8 samples of one staged row -> swap -> RRC -> ring / output.
+// REMAP: window columns 4q..4q+3 (lane 0) and 4q+HALF.. (lane 1) -> 4 ring slots (two 128-bit stores)
+// COPY : tile columns 8q..8q+7 -> 128-bit store straight into the output raster
+// SWAP / ODD (staging halfword parity) / REMAP are compile-time so the row loop has no dispatch.
+// ---------------------------------------------------------------------------------------------
+struct ConvertCtx {
+    const uint16_t *buf;   // staging buffer of this chunk
+    const uint8_t *rz;     // per staged row: 1 = zero border row
+    float *ring;
+    uint16_t *out_rows;    // COPY: output pointer of (tile row 0 of this chunk's new_lo, column 8q)
+    int64_t out_pitch;
+    int word0;             // first staging word of my samples
+    int slot0;             // REMAP: ring slot of staged row 0
+    int n_new, ph, q, n_cols;
+    bool need_rrc, copy_vec;
+};
+
+template <bool REMAP, bool SWAP, bool ODD>
+__device__ __forceinline__ void convert_rows(const ConvertCtx &X, const double (&kk)[8], const double (&bb)[8])
+{
+    int slot = X.slot0 + X.ph;
+    if (slot >= RING) slot -= RING;
+    for (int r = X.ph; r < X.n_new; r += CV_PH) {
+        uint32_t s[8];
+        if (X.rz[r] == 0) {
+            const uint32_t *row32 = reinterpret_cast<const uint32_t *>(X.buf + (size_t)r * SWC) + X.word0;
+            if (REMAP) {
+                const uint32_t *wb = row32 + HALF / 2;
+                uint32_t a[3] = {row32[0], row32[1], ODD ? row32[2] : 0u};
+                uint32_t b[3] = {wb[0], wb[1], ODD ? wb[2] : 0u};
+                extract<SWAP, ODD, 4, 3>(a, s);
+                extract<SWAP, ODD, 4, 3>(b, s + 4);
+            } else {
+                uint32_t wd[5] = {row32[0], row32[1], row32[2], row32[3], ODD ? row32[4] : 0u};
+                extract<SWAP, ODD, 8, 5>(wd, s);
+            }
+            if (X.need_rrc) rrc8(s, kk, bb);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = 0;
+        }
+        if (REMAP) {
+            float4 o0, o1; // (slot 4q: L,R) (slot 4q+1: L,R) | (slot 4q+2) (slot 4q+3)
+            o0.x = u16_to_f32(s[0] & 0xFFFFu); o0.y = u16_to_f32(s[4] & 0xFFFFu);
+            o0.z = u16_to_f32(s[1] & 0xFFFFu); o0.w = u16_to_f32(s[5] & 0xFFFFu);
+            o1.x = u16_to_f32(s[2] & 0xFFFFu); o1.y = u16_to_f32(s[6] & 0xFFFFu);
+            o1.z = u16_to_f32(s[3] & 0xFFFFu); o1.w = u16_to_f32(s[7] & 0xFFFFu);
+            float4 *dst = reinterpret_cast<float4 *>(X.ring + (size_t)slot * (2 * SLOTS) + 8 * X.q);
+            dst[0] = o0;
+            dst[1] = o1;
+            if (slot < RING_MIRROR) { // mirrored copy: any run of RING_MIRROR+1 ring rows is contiguous
+                float4 *dm = dst + (size_t)RING * (2 * SLOTS) / 4;
+                dm[0] = o0;
+                dm[1] = o1;
+            }
+            slot += CV_PH;
+            if (slot >= RING) slot -= RING;
+        } else {
+            uint16_t *orow = X.out_rows + (int64_t)r * X.out_pitch;
+            if (X.copy_vec && 8 * X.q + 8 <= X.n_cols) {
+                uint4 o;
+                o.x = __byte_perm(s[0], s[1], 0x5410);
+                o.y = __byte_perm(s[2], s[3], 0x5410);
+                o.z = __byte_perm(s[4], s[5], 0x5410);
+                o.w = __byte_perm(s[6], s[7], 0x5410);
+                stg_na_v4(orow, o);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (8 * X.q + j < X.n_cols) orow[j] = (uint16_t)s[j];
+            }
+        }
+    }
+}
+
+template <bool REMAP>
+__device__ __forceinline__ void convert_dispatch(const ConvertCtx &X, bool swap, bool odd, const double (&kk)[8],
+                                                 const double (&bb)[8])
+{
+    if (swap) {
+        if (odd) convert_rows<REMAP, true, true>(X, kk, bb); else convert_rows<REMAP, true, false>(X, kk, bb);
+    } else {
+        if (odd) convert_rows<REMAP, false, true>(X, kk, bb); else convert_rows<REMAP, false, false>(X, kk, bb);
+    }
+}
+
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) pan_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    float *ring = reinterpret_cast<float *>(smem);                               // RING x SLOTS float2
-    uint16_t *stg = reinterpret_cast<uint16_t *>(smem + RING * SLOTS * 8);       // 2 x STG x SWC u16
+    float *ring = reinterpret_cast<float *>(smem);                                            // RING_ROWS x SLOTS float2
+    uint16_t *stg = reinterpret_cast<uint16_t *>(smem + (size_t)RING_ROWS * SLOTS * 8);       // 2 x STG x SWC u16
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ __align__(8) float s_tab[132]; // 32x4 weights + the (-0.0,-0.0) pair at [128..129]
     __shared__ uint8_t s_rowzero[2][STG];
-    __shared__ int s_sy[RC];
-    __shared__ int s_regular;
 
     const int tid = threadIdx.x;
     const Tile T = P.tiles[blockIdx.x];
@@ -351,54 +438,85 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pan_kernel(const __grid_const
     const int c_lo = (ix0 >= 0 ? ix0 : ix0 - 7) / 8 * 8; // floor to a multiple of 8 (16-byte aligned bulk copies)
     const int delta = ix0 - c_lo;
     const int n_chunks = (T.n_rows + RC - 1) / RC;
-    const int t_base = chunk_rows(T, dY, 0).t_lo;
 
-    // column-regular tile: the fixed-point column map advances by exactly one source pixel per
-    // output pixel (always true except where float(x + dX) rounds across a 1/32 boundary)
-    bool my_col_regular = true;
-    if (remap && tid < n_cols) my_col_regular = dev_map_fixed(T.x_begin + tid, dX) == sx0 + 32 * tid;
-    const bool cols_regular = __syncthreads_and(my_col_regular) != 0; // also publishes s_tab / barriers
+    // ---- regular tile: the fixed-point maps advance by exactly one source pixel per output pixel /
+    //      row over the whole tile (always, except where float(i + d) rounds across a 1/32 boundary).
+    //      Then every per-chunk quantity is plain integer arithmetic.
+    const int sy_t0 = remap ? dev_map_fixed(T.j0, dY) : 0;
+    bool mine_regular = true;
+    if (remap) {
+        if (tid < n_cols) mine_regular = dev_map_fixed(T.x_begin + tid, dX) == sx0 + 32 * tid;
+        for (int i = tid; i < T.n_rows; i += NT) mine_regular = mine_regular && (dev_map_fixed(T.j0 + i, dY) == sy_t0 + 32 * i);
+    }
+    const bool regular = __syncthreads_and(mine_regular) != 0; // also publishes s_tab / barriers
+    const int iy_t0 = (sy_t0 >> 5) - 1;                         // first tap row of tile row 0 (regular tiles)
+
+    auto get_chunk = [&](int k) {
+        if (remap && regular) {
+            ChunkRows c;
+            const int nr = min(RC, T.n_rows - k * RC);
+            c.t_lo = iy_t0 + k * RC;
+            c.t_hi = c.t_lo + nr + 2;
+            c.new_lo = k == 0 ? c.t_lo : c.t_lo + 3;
+            c.n_new = c.t_hi - c.new_lo + 1;
+            return c;
+        }
+        return chunk_rows(T, dY, k);
+    };
+    const int t_base = get_chunk(0).t_lo;
 
     // ---- convert-step mapping and RRC coefficients (registers)
-    //  REMAP: thread = (slot quad q, row phase): window columns 4q..4q+3 (lane 0) and 4q+HALF.. (lane 1)
-    //  COPY : thread = (column octet q, row phase): tile columns 8q..8q+7
     const int cv_q = tid & (CV_Q - 1), cv_ph = tid / CV_Q;
-    int cv_col[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cv_col[j] = remap ? (4 * cv_q + (j & 3) + (j >> 2) * HALF) : (8 * cv_q + j);
     double kk[8], bb[8];
-    bool cols_all_valid = true;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = ix0 + cv_col[j];
+        const int c = ix0 + (remap ? (4 * cv_q + (j & 3) + (j >> 2) * HALF) : (8 * cv_q + j));
         const bool ok = c >= 0 && c < w;
-        cols_all_valid = cols_all_valid && ok;
         kk[j] = (ok && do_rrc) ? C.kb[2 * c] : (ok ? 1.0 : 0.0); // k = b = 0 zeroes columns outside the CCD
         bb[j] = (ok && do_rrc) ? C.kb[2 * c + 1] : 0.0;
     }
-    const bool need_rrc = do_rrc || !cols_all_valid;
+    const bool need_rrc = do_rrc || ix0 < 0 || ix0 + SRC_W > w; // uniform: RRC, or some window column is outside the CCD
     const bool cv_active = remap ? true : (8 * cv_q < n_cols);
+    uint16_t *const out_tile = P.out + (T.g0 - P.out_row0) * P.out_pitch + T.out_x;
+    const bool copy_vec = ((T.out_x & 7) == 0) && ((P.out_pitch & 7) == 0) && ((((uintptr_t)P.out) & 15) == 0);
 
     // ------------------------------------------------------------------ loader
     auto issue_chunk = [&](int k) {
-        const ChunkRows cr = chunk_rows(T, dY, k);
+        const ChunkRows cr = get_chunk(k);
         uint16_t *buf = stg + (size_t)(k & 1) * STG * SWC;
         uint8_t *rz = s_rowzero[k & 1];
         uint64_t *bar = &bars[k & 1];
         const int64_t row_bias = remap ? 0 : T.j0; // COPY rows are tile-relative
         if (bulk) {
-            // every warp issues rows wid, wid+8, ... (lane i takes the i-th of them): the issue loop is
-            // serialised per lane by the uniform datapath, so spreading it keeps one warp from
-            // becoming the straggler at the next barrier
+            // every warp issues rows wid, wid+NWARPS, ... (lane i takes the i-th of them): the issue
+            // loop is serialised per lane by the uniform datapath, so spreading it keeps one warp
+            // from becoming the straggler at the next barrier
             const int lane = tid & 31, wid = tid >> 5;
             const int ca = max(c_lo, 0), cb = min(c_lo + SWC, w);
             const uint32_t nb = cb > ca ? (uint32_t)(cb - ca) * 2u : 0u;
             const int r = wid + NWARPS * lane;
+            // common case: the chunk's rows are consecutive lines of one segment
+            const int64_t ga = local_to_global(T, row_bias + cr.new_lo);
+            const int64_t gb = local_to_global(T, row_bias + cr.new_lo + cr.n_new - 1);
+            const uint8_t *run = nullptr;
+            int64_t run_pitch = 0;
+            if (cr.n_new > 0 && ga >= 0 && gb - ga == cr.n_new - 1 && nb) {
+#pragma unroll
+                for (int s = 0; s < OIP_MAX_SEG; ++s)
+                    if (s < C.n_seg && ga >= C.seg[s].row0 && gb < C.seg[s].row0 + C.seg[s].n_rows) {
+                        run = C.seg[s].base + (ga - C.seg[s].row0) * C.seg[s].pitch;
+                        run_pitch = C.seg[s].pitch;
+                    }
+            }
             const uint8_t *q = nullptr;
             if (r < cr.n_new) {
-                const int64_t g = local_to_global(T, row_bias + cr.new_lo + r);
-                q = (g >= 0 && nb) ? row_ptr(C, g) : nullptr;
-                if (g >= 0 && nb && !q) atomicExch(P.err, 1); // host failed to supply a needed row
+                if (run) {
+                    q = run + r * run_pitch;
+                } else {
+                    const int64_t g = local_to_global(T, row_bias + cr.new_lo + r);
+                    q = (g >= 0 && nb) ? row_ptr(C, g) : nullptr;
+                    if (g >= 0 && nb && !q) atomicExch(P.err, 1); // host failed to supply a needed row
+                }
                 rz[r] = q == nullptr;
             }
             uint32_t total = q ? nb : 0u;
@@ -436,106 +554,39 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pan_kernel(const __grid_const
     // pixels that exist and whose 4x4 footprint is inside the CCD may use the packed interior path
     auto col_interior = [&](int xi) { return (ix0 + xi) >= 0 && (ix0 + xi) < w - 3; };
     const bool l_exists = xl < n_cols, r_exists = xr < n_cols; // pairs exist or not as a whole when n_cols is even
-    const bool pair_whole = ((n_cols & 1) == 0);
-    const bool fast_ok = rs_active && cols_regular && pair_whole && l_exists &&
-                         col_interior(xl) && col_interior(xl + 1) && (!r_exists || (col_interior(xr) && col_interior(xr + 1)));
-    const int fx = sx0 & 31;
-    uint16_t *const out_tile = P.out + (T.g0 - P.out_row0) * P.out_pitch + T.out_x;
+    const bool fast_ok = rs_active && regular && ((n_cols & 1) == 0) && l_exists && col_interior(xl) &&
+                         col_interior(xl + 1) && (!r_exists || (col_interior(xr) && col_interior(xr + 1)));
+    const int fx = sx0 & 31, fy = sy_t0 & 31;
     const bool out_vec2 = ((((uintptr_t)P.out) & 3) == 0) && ((P.out_pitch & 1) == 0) && ((T.out_x & 1) == 0);
 
     for (int k = 0; k < n_chunks; ++k) {
-        const ChunkRows cr = chunk_rows(T, dY, k);
-        const int64_t ja = T.j0 + (int64_t)k * RC;
+        const ChunkRows cr = get_chunk(k);
         const int nr = min(RC, T.n_rows - k * RC);
         if (bulk) mbar_wait(&bars[k & 1], (uint32_t)((k >> 1) & 1));
 
         // ---------------------------------------------------------- convert: swap + RRC
         if (cv_active) {
-            const uint16_t *buf = stg + (size_t)(k & 1) * STG * SWC;
-            const uint8_t *rz = s_rowzero[k & 1];
-            const bool odd = (delta & 1) != 0;
-            for (int r = cv_ph; r < cr.n_new; r += CV_PH) {
-                uint32_t s[8];
-                if (rz[r] == 0) {
-                    const uint32_t *row32 = reinterpret_cast<const uint32_t *>(buf + (size_t)r * SWC);
-                    if (remap) {
-                        const uint32_t *wa = row32 + ((delta + 4 * cv_q) >> 1);
-                        const uint32_t *wb = wa + HALF / 2;
-                        uint32_t a[3] = {wa[0], wa[1], odd ? wa[2] : 0u};
-                        uint32_t b[3] = {wb[0], wb[1], odd ? wb[2] : 0u};
-                        if (odd) {
-                            if (swap) { extract<true, true, 4, 3>(a, s); extract<true, true, 4, 3>(b, s + 4); }
-                            else { extract<false, true, 4, 3>(a, s); extract<false, true, 4, 3>(b, s + 4); }
-                        } else {
-                            if (swap) { extract<true, false, 4, 3>(a, s); extract<true, false, 4, 3>(b, s + 4); }
-                            else { extract<false, false, 4, 3>(a, s); extract<false, false, 4, 3>(b, s + 4); }
-                        }
-                    } else {
-                        const uint32_t *wp = row32 + ((delta + 8 * cv_q) >> 1);
-                        uint32_t wd[5] = {wp[0], wp[1], wp[2], wp[3], odd ? wp[4] : 0u};
-                        if (odd) {
-                            if (swap) extract<true, true, 8, 5>(wd, s); else extract<false, true, 8, 5>(wd, s);
-                        } else {
-                            if (swap) extract<true, false, 8, 5>(wd, s); else extract<false, false, 8, 5>(wd, s);
-                        }
-                    }
-                    if (need_rrc) rrc8(s, kk, bb);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) s[j] = 0;
-                }
-                if (remap) {
-                    const int slot = (cr.new_lo + r - t_base) % RING;
-                    float4 o0, o1; // (slot 4q: L,R) (slot 4q+1: L,R) | (slot 4q+2) (slot 4q+3)
-                    o0.x = u16_to_f32(s[0] & 0xFFFFu); o0.y = u16_to_f32(s[4] & 0xFFFFu);
-                    o0.z = u16_to_f32(s[1] & 0xFFFFu); o0.w = u16_to_f32(s[5] & 0xFFFFu);
-                    o1.x = u16_to_f32(s[2] & 0xFFFFu); o1.y = u16_to_f32(s[6] & 0xFFFFu);
-                    o1.z = u16_to_f32(s[3] & 0xFFFFu); o1.w = u16_to_f32(s[7] & 0xFFFFu);
-                    float4 *dst = reinterpret_cast<float4 *>(ring + (size_t)slot * (2 * SLOTS) + 8 * cv_q);
-                    dst[0] = o0;
-                    dst[1] = o1;
-                } else {
-                    // COPY tile: straight to the output raster
-                    uint16_t *orow = out_tile + (int64_t)(cr.new_lo + r) * P.out_pitch + 8 * cv_q;
-                    if (((T.out_x & 7) == 0) && ((P.out_pitch & 7) == 0) && ((((uintptr_t)P.out) & 15) == 0) &&
-                        8 * cv_q + 8 <= n_cols) {
-                        uint4 o;
-                        o.x = (s[0] & 0xFFFFu) | (s[1] << 16);
-                        o.y = (s[2] & 0xFFFFu) | (s[3] << 16);
-                        o.z = (s[4] & 0xFFFFu) | (s[5] << 16);
-                        o.w = (s[6] & 0xFFFFu) | (s[7] << 16);
-                        stg_na_v4(orow, o);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (8 * cv_q + j < n_cols) orow[j] = (uint16_t)s[j];
-                    }
-                }
-            }
-        }
-        if (remap && tid < 32) {
-            // row map of the chunk + "regular" flag: unit row steps (hence one fy) and every row in
-            // the interior of the section buffer -> packed sliding-window path
-            const int sy = tid < nr ? dev_map_fixed(ja + tid, dY) : 0;
-            const int prev = __shfl_up_sync(0xffffffffu, sy, 1);
-            const bool ok = (tid == 0 || tid >= nr) ? true : (sy - prev == 32);
-            const bool all_ok = __all_sync(0xffffffffu, ok);
-            s_sy[tid] = sy;
-            if (tid == 0) {
-                const int iy0 = dev_sat_short(sy >> 5) - 1;
-                s_regular = all_ok && nr == RC && iy0 >= 0 && (iy0 + nr - 1) < T.hbuf - 3;
-            }
+            ConvertCtx X;
+            X.buf = stg + (size_t)(k & 1) * STG * SWC;
+            X.rz = s_rowzero[k & 1];
+            X.ring = ring;
+            X.out_rows = out_tile + (int64_t)cr.new_lo * P.out_pitch + 8 * cv_q;
+            X.out_pitch = P.out_pitch;
+            X.word0 = (delta + (remap ? 4 : 8) * cv_q) >> 1;
+            X.slot0 = remap ? (cr.new_lo - t_base) % RING : 0;
+            X.n_new = cr.n_new; X.ph = cv_ph; X.q = cv_q; X.n_cols = n_cols;
+            X.need_rrc = need_rrc; X.copy_vec = copy_vec;
+            if (remap) convert_dispatch<true>(X, swap, (delta & 1) != 0, kk, bb);
+            else convert_dispatch<false>(X, swap, (delta & 1) != 0, kk, bb);
         }
         __syncthreads();
         if (k + 2 < n_chunks) issue_chunk(k + 2);
 
         // ---------------------------------------------------------- resample
         if (remap && rs_active) {
-            const int sy0 = s_sy[0];
             uint16_t *o = out_tile + ((int64_t)k * RC + 8 * rg) * P.out_pitch;
-            if (s_regular && fast_ok) {
-                const int iy0 = (sy0 >> 5) - 1; // regular chunk: no saturation, tap rows iy0 + i
-                const int fy = sy0 & 31;
+            const int iy0 = iy_t0 + k * RC; // regular tiles: first tap row of the chunk
+            if (fast_ok && nr == RC && iy0 >= 0 && iy0 + RC - 1 < T.hbuf - 3) {
                 const f2 nz = *reinterpret_cast<const f2 *>(&s_tab[128]);
                 f2 W[4][4];
 #pragma unroll
@@ -545,13 +596,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pan_kernel(const __grid_const
                         const float wv = __fmul_rn(s_tab[4 * fy + r], s_tab[4 * fx + c]);
                         W[r][c] = pk(wv, wv);
                     }
-                int slot = (iy0 + 8 * rg - t_base) % RING;
-                const f2 *col = reinterpret_cast<const f2 *>(ring) + 2 * cg;
+                // 11 consecutive ring rows from slot0: contiguous thanks to the mirrored rows
+                const int slot0 = (iy0 + 8 * rg - t_base) % RING;
+                const f2 *rowp = reinterpret_cast<const f2 *>(ring) + (size_t)slot0 * SLOTS + 2 * cg;
                 RowRegs R0, R1, R2, R3;
-                auto next_row = [&](RowRegs &R) {
-                    load_row_regs(R, col + slot * SLOTS);
-                    slot = slot + 1 == RING ? 0 : slot + 1;
-                };
                 auto emit = [&](const RowRegs &a, const RowRegs &b, const RowRegs &c, const RowRegs &d) {
                     f2 p0 = dot_row<0>(a, W[0], nz), p1 = dot_row<1>(a, W[0], nz);
                     p0 = add2(p0, dot_row<0>(b, W[1], nz)); p1 = add2(p1, dot_row<1>(b, W[1], nz));
@@ -568,15 +616,16 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pan_kernel(const __grid_const
                     }
                     o += P.out_pitch;
                 };
-                next_row(R0);
-                next_row(R1);
-                next_row(R2);
-#pragma unroll
+                load_row_regs(R0, rowp);
+                load_row_regs(R1, rowp + SLOTS);
+                load_row_regs(R2, rowp + 2 * SLOTS);
+#pragma unroll 1
                 for (int i = 0; i < 2; ++i) {
-                    next_row(R3); emit(R0, R1, R2, R3);
-                    next_row(R0); emit(R1, R2, R3, R0);
-                    next_row(R1); emit(R2, R3, R0, R1);
-                    next_row(R2); emit(R3, R0, R1, R2);
+                    load_row_regs(R3, rowp + 3 * SLOTS); emit(R0, R1, R2, R3);
+                    load_row_regs(R0, rowp + 4 * SLOTS); emit(R1, R2, R3, R0);
+                    load_row_regs(R1, rowp + 5 * SLOTS); emit(R2, R3, R0, R1);
+                    load_row_regs(R2, rowp + 6 * SLOTS); emit(R3, R0, R1, R2);
+                    rowp += 4 * SLOTS;
                 }
             } else {
                 // exact generic path: borders, section edges, partial chunks, odd widths, map anomalies
@@ -584,12 +633,13 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pan_kernel(const __grid_const
                 for (int i = 0; i < 8; ++i) {
                     const int row = 8 * rg + i;
                     if (row < nr) {
-                        const int sy = s_sy[row];
+                        const int64_t j = T.j0 + (int64_t)k * RC + row;
+                        const int sy = regular ? sy_t0 + 32 * (k * RC + row) : dev_map_fixed(j, dY);
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const int xi = (c < 2 ? xl : xr) + (c & 1);
                             if (xi < n_cols) {
-                                const int sx = cols_regular ? sx0 + 32 * xi : dev_map_fixed(T.x_begin + xi, dX);
+                                const int sx = regular ? sx0 + 32 * xi : dev_map_fixed(T.x_begin + xi, dX);
                                 o[xi] = (uint16_t)resample_px_general(V, s_tab, sx, sy, w, T.hbuf);
                             }
                         }
@@ -795,7 +845,7 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
     P.out = d->d_out; P.out_pitch = d->out_pitch_px; P.out_row0 = d->row0;
     P.err = ctx->d_err; P.w = d->w; P.n_ccd = d->n_ccd; P.bulk_ok = bulk_ok ? 1 : 0;
 
-    const size_t smem = (size_t)pan::RING * pan::SLOTS * 8 + 2 * (size_t)pan::STG * pan::SWC * 2;
+    const size_t smem = (size_t)pan::RING_ROWS * pan::SLOTS * 8 + 2 * (size_t)pan::STG * pan::SWC * 2;
     if (!ctx->pan_attr_set) {
         OIP_CUDA(cudaFuncSetAttribute(pan::pan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->pan_attr_set = true;
