@@ -301,7 +301,9 @@ __device__ __forceinline__ void rrc8(uint32_t (&s)[8], const double (&k)[8], con
     uint32_t hmax = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const double sd = __dadd_rn(__hiloint2double(0x43300000, (int)s[j]), -4503599627370496.0);
+        // u16 -> f64: one I2F.F64.U32 here (conversion pipe, 16 lanes/clk/SM) costs fewer issue slots than
+        // the magic-number form (MOV hi + DADD) and this kernel is issue-bound, not conversion-pipe-bound
+        const double sd = __uint2double_rn(s[j]);
         v[j] = __dadd_rn(__dmul_rn(k[j], sd), b[j]);
         hmax = max(hmax, (uint32_t)__double2hiint(v[j]));
     }
@@ -362,10 +364,10 @@ __device__ __forceinline__ void convert_rows(const ConvertCtx &X, const double (
         }
         if (REMAP) {
             float4 o0, o1; // (slot 4q: L,R) (slot 4q+1: L,R) | (slot 4q+2) (slot 4q+3)
-            o0.x = u16_to_f32(s[0] & 0xFFFFu); o0.y = u16_to_f32(s[4] & 0xFFFFu);
-            o0.z = u16_to_f32(s[1] & 0xFFFFu); o0.w = u16_to_f32(s[5] & 0xFFFFu);
-            o1.x = u16_to_f32(s[2] & 0xFFFFu); o1.y = u16_to_f32(s[6] & 0xFFFFu);
-            o1.z = u16_to_f32(s[3] & 0xFFFFu); o1.w = u16_to_f32(s[7] & 0xFFFFu);
+            // low 16 bits -> exact float: PRMT builds 0x4B00hhll (= 2^23 + v), one FADD removes the 2^23
+            auto f = [](uint32_t v) { return __fadd_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7610)), -8388608.0f); };
+            o0.x = f(s[0]); o0.y = f(s[4]); o0.z = f(s[1]); o0.w = f(s[5]);
+            o1.x = f(s[2]); o1.y = f(s[6]); o1.z = f(s[3]); o1.w = f(s[7]);
             float4 *dst = reinterpret_cast<float4 *>(X.ring + (size_t)slot * (2 * SLOTS) + 8 * X.q);
             dst[0] = o0;
             dst[1] = o1;

@@ -1,0 +1,128 @@
+"""Parity against outputs of THE REFERENCE ITSELF, run in the build container through
+oracle/_ref/libref_oip.so (reference headers compiled unmodified; tests/golden/make_golden_ref.py).
+
+CPU:  the oracle must reproduce the reference's files byte for byte (sha256 fixtures).
+GPU:  the CUDA path must reproduce the same fixtures (marked gpu)."""
+import hashlib
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from opticalimageprocessor_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _inputs():
+    """input generators shared with the fixture script (without loading the reference library)"""
+    src = open(os.path.join(GOLD, "make_golden_ref.py")).read()
+    ns = {}
+    # only the two pure generator functions are needed
+    import textwrap
+    code = "import numpy as np\nfrom opticalimageprocessor_b200 import synth\nW = 12288\n"
+    for fn in ("auxsep_input", "prestitch_input"):
+        a = src.index(f"def {fn}(")
+        b = src.index("\n\n\n", a)
+        code += src[a:b] + "\n\n"
+    exec(compile(code, "golden_inputs", "exec"), ns)
+    return ns
+
+
+@pytest.fixture(scope="module")
+def auxsep_case():
+    g = np.load(os.path.join(GOLD, "ref_auxsep.npz"))
+    buf = _inputs()["auxsep_input"]()
+    assert buf.size == int(g["input_bytes"]) and sha(buf) == str(g["input_sha256"]), "synthetic input drifted"
+    return g, buf
+
+
+def test_oracle_reproduces_reference_auxsep(auxsep_case):
+    """AuxSeparator::Separate() (ref aux_separator.h:224-245) ran on this exact downlink; the oracle's
+    three stages must give the same IMDT / AUX / PAN.RAW / MSS.RAW bytes"""
+    g, buf = auxsep_case
+    off, cnt = oracle.aos_scan(buf)
+    imdt, st = oracle.imtr_deframe(buf, off)
+    assert imdt.size == int(g["imdt_bytes"]) and sha(imdt) == str(g["imdt_sha256"])
+    assert ("CMOS-1" if st[7] == 0x11 else "CMOS-2") in str(g["imdt_name"])       # ref aux_separator.h:513-523
+    n, aux, pan, mss, fst = oracle.image_frames(imdt, 1536, 256)
+    assert aux.size == int(g["aux_bytes"]) and sha(aux) == str(g["aux_sha256"])
+    assert pan.size * 2 == int(g["pan_bytes"]) and sha(pan) == str(g["pan_sha256"])
+    assert mss.size * 2 == int(g["mss_bytes"]) and sha(mss) == str(g["mss_sha256"])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_reference_auxsep(ctx, auxsep_case):
+    import torch
+    from opticalimageprocessor_b200 import ops
+    g, buf = auxsep_case
+    d = torch.from_numpy(buf).cuda()
+    off, cnt = ops.aos_scan(ctx, d)
+    imdt, st = ops.imtr_deframe(ctx, d, off)
+    assert sha(imdt.cpu().numpy()) == str(g["imdt_sha256"])
+    ents, fst = ops.image_frames_index(ctx, imdt, 1536, 256)
+    aux, pan, mss = ops.unpack_frames(ctx, imdt, 1536, 256, ents, int(fst[1]))
+    ctx.sync()
+    assert sha(aux.cpu().numpy()) == str(g["aux_sha256"])
+    assert sha(pan.cpu().numpy()) == str(g["pan_sha256"])
+    assert sha(mss.cpu().numpy()) == str(g["mss_sha256"])
+
+
+def _check_prestitch(out, g, tag):
+    rows = int(g["rows"])
+    blocks = [sha(out[i:i + 1024]) for i in range(0, rows, 1024)]
+    bad = [i for i, (a, b) in enumerate(zip(blocks, g[tag + "_block_sha"])) if a != str(b)]
+    idx = g[tag + "_rows_idx"]
+    rows_bad = [int(r) for r, want in zip(idx, g[tag + "_rows"]) if not np.array_equal(out[r], want)]
+    assert not bad and not rows_bad, f"{tag}: blocks {bad} / rows {rows_bad} differ from the reference run"
+
+
+@pytest.mark.parametrize("tag", ["neg", "pos"])
+def test_oracle_reproduces_reference_prestitch(tag):
+    """Stitcher::PreStitch + SectionaryRemap (ref stitcher.h:83-139, imageop.h:230-275) at the reference's
+    real geometry: 12288 px, 30000-row sections, 32768 lines -> section edge + stale bottom rows"""
+    p = os.path.join(GOLD, "ref_prestitch.npz")
+    if not os.path.exists(p):
+        pytest.skip("ref_prestitch.npz not generated")
+    g = np.load(p)
+    src = _inputs()["prestitch_input"](int(g["rows"]), int(g["seed"]))
+    dx, dy = g[tag + "_shift"]
+    _check_prestitch(oracle.prestitch_shift(src, float(dx), float(dy)), g, tag)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["neg", "pos"])
+def test_gpu_reproduces_reference_prestitch(ctx, tag):
+    import torch
+    from opticalimageprocessor_b200 import ops
+    p = os.path.join(GOLD, "ref_prestitch.npz")
+    if not os.path.exists(p):
+        pytest.skip("ref_prestitch.npz not generated")
+    g = np.load(p)
+    src = _inputs()["prestitch_input"](int(g["rows"]), int(g["seed"]))
+    dx, dy = g[tag + "_shift"]
+    out = ops.prestitch_shift(ctx, torch.from_numpy(src).cuda(), float(dx), float(dy)).cpu().numpy()
+    _check_prestitch(out, g, tag)
+
+
+def test_reference_rrc_direct():
+    """IMO::InplaceRRC itself (ref imageop.h:129-138), when the checker library is present"""
+    so = os.path.join(os.path.dirname(oracle.__file__), "_ref", "libref_oip.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libref_oip.so not built (no /root/reference here)")
+    import ctypes as C
+    L = C.CDLL(so)
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 65536, (64, 12288), dtype=np.uint16)
+    kb = synth.rrc_coeffs(12288, 9)
+    kb[3] = (1.0, -0.5)
+    kb[4] = (2.0, 0.0)       # wraps past 65535 exactly like the reference's x86 build
+    want = img.copy()
+    L.ref_inplace_rrc(want.ctypes.data_as(C.c_void_p), 12288, 64, kb.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(oracle.rrc(img, kb), want)
