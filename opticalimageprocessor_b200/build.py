@@ -32,6 +32,7 @@ def needs_build() -> bool:
         return True
     t = os.path.getmtime(LIB)
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.hpp")) + [
+        os.path.join(HERE, "host", "oip_cli.cpp"),
         os.path.join(HERE, "..", "include", "oip_b200.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -60,7 +61,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print("\n".join(log))
     cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
+    build_cli()
     return LIB
+
+
+CLI_BIN = os.path.join(HERE, "OpticalImageProcessor")
+
+
+def build_cli() -> str:
+    """the reference-grammar command line (C++17 host code over the C ABI)"""
+    src = os.path.join(HERE, "host", "oip_cli.cpp")
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-o", CLI_BIN, src, "-L" + HERE, "-loip_b200",
+           "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + HERE]
+    subprocess.check_call(cmd)
+    return CLI_BIN
 
 
 if __name__ == "__main__":

@@ -1,0 +1,531 @@
+// oip_cli.cpp -- "OpticalImageProcessor" command line: the reference's process-level contract
+// (argv grammar, cwd-relative output names, exit codes, LOGFILE) re-implemented in C++17 on top of
+// the C ABI (include/oip_b200.h).  ref main.cpp:92-343 (grammar/exit codes), imageop.h:99-108 (names),
+// DOC/Usage.txt (task flow).  CLI11 is not available here: hand-written parser, same option names.
+//
+// Differences, all forced by what SURVEY 8f leaves for later rows:
+//   * prestitch: the inter-CMOS offset estimate (cv::phaseCorrelate, ref stitcher.h:148-201) is not
+//     implemented -> pass it with the extension options --dx/--dy.
+//   * default action: the inter-band correlation + polynomial fit (ref preproc.h:224-347,492-550) is
+//     not implemented -> pass the 4x5 coefficients with --poly FILE; the result is written as
+//     <stem>.ALIGNED.RAW (CV_16UC4 memory layout) because no TIFF writer exists yet.
+//   * stitch: RAW in / RAW out only (TIFF codec: SURVEY 8f N3).
+// There is no CPU fallback: without a B200 every command fails with exit code 2.
+#include <strings.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <filesystem>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/oip_b200.h"
+
+namespace fs = std::filesystem;
+
+// ---- reference constants (ref oipshared.h:27-64)
+static const int PIXELS_PER_LINE = 12288, BYTES_PER_PIXEL = 2, MSS_BANDS = 4;
+static const int REMAP_ROW_GUARD = 32767, REMAP_SECTION_ROWS = 30000; // ref imageop.h:19-20
+
+struct usage_error : std::invalid_argument { using std::invalid_argument::invalid_argument; };   // ref main.cpp:20-23
+struct parse_error : std::runtime_error { int code; parse_error(int c, const std::string &m) : std::runtime_error(m), code(c) {} };
+enum { CLI_VALIDATION = 105, CLI_REQUIRED = 106, CLI_REQUIRES = 107, CLI_EXTRAS = 109, CLI_CONVERSION = 104 }; // CLI11 ExitCodes
+
+// ---- logging: LOGFILE or oip.log, timestamped (ref main.cpp:319-329)
+static FILE *g_log = nullptr;
+static void logf(const char *lvl, const char *fmt, ...)
+{
+    char msg[2048];
+    va_list ap; va_start(ap, fmt); vsnprintf(msg, sizeof msg, fmt, ap); va_end(ap);
+    time_t t = time(nullptr); char ts[32]; strftime(ts, sizeof ts, "%Y-%m-%d %H:%M:%S", localtime(&t));
+    if (g_log) { fprintf(g_log, "%s [%s] %s\n", ts, lvl, msg); fflush(g_log); }
+    printf("%s\n", msg);
+}
+#define OLOG(...) logf("T", __VA_ARGS__)
+
+static void oip_check(int rc)
+{
+    if (rc == OIP_OK) return;
+    if (rc == OIP_E_INVALID) throw std::invalid_argument(oip_last_error());
+    throw std::runtime_error(oip_last_error());
+}
+static oip_ctx *ctx()
+{
+    static oip_ctx *c = nullptr;
+    if (!c) oip_check(oip_ctx_create(0, nullptr, 1, &c));
+    return c;
+}
+
+// ---- file helpers (ref imageop.h:43-108)
+static size_t file_size(const std::string &p)
+{
+    struct stat st {};
+    if (stat(p.c_str(), &st)) throw std::runtime_error("stat() call for file failed: " + p);
+    return (size_t)st.st_size;
+}
+static std::string build_output_path(const std::string &tmpl, const std::string &stem_ext, const char *replace_ext = nullptr)
+{
+    fs::path t = tmpl;                                       // ref imageop.h:99-108
+    fs::path o = fs::current_path() / t.stem();
+    o += stem_ext;
+    o += replace_ext ? replace_ext : t.extension().string();
+    return o.string();
+}
+static std::string lower(std::string s) { std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)tolower(c); }); return s; }
+
+struct Pinned {
+    void *p = nullptr; size_t n = 0;
+    explicit Pinned(size_t bytes) : n(bytes) { oip_check(oip_host_alloc_pinned(bytes ? bytes : 1, &p)); }
+    ~Pinned() { if (p) oip_host_free_pinned(p); }
+    Pinned(const Pinned &) = delete;
+};
+struct DevBuf {
+    void *p = nullptr;
+    explicit DevBuf(size_t bytes) { oip_check(oip_dev_alloc(ctx(), bytes ? bytes : 1, &p)); }
+    ~DevBuf() { if (p) oip_dev_free(ctx(), p); }
+    DevBuf(const DevBuf &) = delete;
+};
+static void read_file(const std::string &path, void *dst, size_t offset, size_t bytes)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) throw std::invalid_argument("cannot open file [" + path + "]");
+    if (fseeko(f, (off_t)offset, SEEK_SET)) { fclose(f); throw std::invalid_argument("ReadFileContent(): seek failed"); }
+    size_t got = 0;
+    while (got < bytes) {                                    // 8 MB units like ref imageop.h:69-79
+        size_t n = fread((char *)dst + got, 1, std::min<size_t>(8u << 20, bytes - got), f);
+        if (!n) break;
+        got += n;
+    }
+    fclose(f);
+    if (got != bytes) throw std::runtime_error("file size doesn't match with read byte count: " + path);
+}
+static void write_file(const std::string &path, const void *src, size_t bytes)
+{
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("open file [" + path + "] failed");
+    size_t done = 0;
+    while (done < bytes) {
+        size_t n = fwrite((const char *)src + done, 1, std::min<size_t>(8u << 20, bytes - done), f);
+        if (!n) { fclose(f); throw std::runtime_error("write file failed: " + path); }
+        done += n;
+    }
+    fclose(f);
+}
+static std::vector<double> load_rrc(const std::string &path, int cols)
+{
+    std::vector<double> kb((size_t)cols * 2);
+    oip_check(oip_load_rrc_csv(path.c_str(), cols, kb.data()));
+    return kb;
+}
+
+// ---- tiny option parser with CLI11's conventions (--opt=v, --opt v, -o v, flags, positionals)
+struct Args {
+    std::map<std::string, std::string> val;
+    std::vector<std::string> pos;
+    bool has(const std::string &k) const { return val.count(k) != 0; }
+    std::string get(const std::string &k, const std::string &d = "") const { auto i = val.find(k); return i == val.end() ? d : i->second; }
+    long long geti(const std::string &k, long long d) const {
+        if (!has(k)) return d;
+        char *e = nullptr; long long v = strtoll(get(k).c_str(), &e, 10);
+        if (!e || *e) throw parse_error(CLI_CONVERSION, "Could not convert: --" + k + " = " + get(k));
+        return v;
+    }
+    double getd(const std::string &k, double d) const {
+        if (!has(k)) return d;
+        char *e = nullptr; double v = strtod(get(k).c_str(), &e);
+        if (!e || *e) throw parse_error(CLI_CONVERSION, "Could not convert: --" + k + " = " + get(k));
+        return v;
+    }
+};
+struct OptSpec { const char *name; const char *alias; bool flag; };
+static Args parse(const std::vector<std::string> &argv, const std::vector<OptSpec> &specs, int max_pos)
+{
+    Args a;
+    auto find = [&](const std::string &n) -> const OptSpec * {
+        for (auto &s : specs) if (n == s.name || (s.alias && n == s.alias)) return &s;
+        return nullptr;
+    };
+    for (size_t i = 0; i < argv.size(); ++i) {
+        const std::string &t = argv[i];
+        if (t.size() > 1 && t[0] == '-') {
+            std::string key = t, v; bool hasv = false;
+            size_t eq = t.find('=');
+            if (eq != std::string::npos) { key = t.substr(0, eq); v = t.substr(eq + 1); hasv = true; }
+            const OptSpec *s = find(key);
+            if (!s) throw parse_error(CLI_EXTRAS, "The following argument was not expected: " + t);
+            std::string canon = std::string(s->name).substr(2);
+            if (s->flag) { a.val[canon] = "1"; continue; }
+            if (!hasv) {
+                if (i + 1 >= argv.size()) throw parse_error(114, key + ": 1 required");
+                v = argv[++i];
+            }
+            a.val[canon] = v;
+        } else {
+            if ((int)a.pos.size() >= max_pos) throw parse_error(CLI_EXTRAS, "The following argument was not expected: " + t);
+            a.pos.push_back(t);
+        }
+    }
+    return a;
+}
+static void require(const Args &a, const char *k) { if (!a.has(k)) throw parse_error(CLI_REQUIRED, std::string("--") + k + " is required"); }
+static void existing_file(const std::string &p, const char *what)
+{
+    struct stat st {};
+    if (stat(p.c_str(), &st) || !S_ISREG(st.st_mode)) throw parse_error(CLI_VALIDATION, std::string(what) + ": File does not exist: " + p);
+}
+
+// =============================================================================================
+// auxsep  (ref main.cpp:98-109, aux_separator.h:193-327)
+// =============================================================================================
+struct AosFileInfo { char station[16], satellite[16]; int year, month, day, hour, minute, second; };
+static bool parse_file_info(const char *name, AosFileInfo &afi)     // ref aux_separator.h:692-719 (same sscanf pattern)
+{
+    int cmos = 0; char y[5], mo[3], d[3], h[3], mi[3], s[3];
+    if (sscanf(name, "%15[A-Za-z0-9]%*[_-]%15[A-Za-z0-9-]_%4[0-9]%2[0-9]%2[0-9]_%2[0-9]%2[0-9]%2[0-9]_%d", afi.station, afi.satellite,
+               y, mo, d, h, mi, s, &cmos) != 9) return false;
+    afi.year = atoi(y); afi.month = atoi(mo); afi.day = atoi(d); afi.hour = atoi(h); afi.minute = atoi(mi); afi.second = atoi(s);
+    return true;
+}
+
+static int cmd_auxsep(const std::vector<std::string> &av)
+{
+    Args a = parse(av, {{"--offset", "-O", false}}, 1);
+    if (a.pos.empty()) throw parse_error(CLI_REQUIRED, "file is required");
+    const std::string file = a.pos[0];
+    existing_file(file, "file");
+    size_t offset = (size_t)a.geti("offset", 0);
+    const size_t ps = (size_t)getpagesize();
+    if (offset % ps) { offset = offset / ps * ps; OLOG("offset not aligned with system memory page size, adjusted to %zu (0x%zX).", offset, offset); }
+    const bool is_imdt = strcasecmp(fs::path(file).extension().string().c_str(), ".IMDT") == 0;   // ref :204-206
+
+    std::string imdt_name = file;
+    std::vector<uint8_t> keep_host;
+    DevBuf *d_imdt = nullptr;
+    int64_t imdt_bytes = 0;
+    std::unique_ptr<DevBuf> d_file, d_payload, d_imdt_own;
+    if (!is_imdt) {
+        AosFileInfo afi{};
+        if (!parse_file_info(fs::path(file).filename().string().c_str(), afi) &&
+            !parse_file_info(fs::path(file).parent_path().filename().string().c_str(), afi))
+            throw std::invalid_argument("unrecognized AOS file name pattern");                       // ref :208-213
+        OLOG("Launching AOS file separation ...");
+        const size_t total = file_size(file);
+        if (offset > total) throw std::invalid_argument("offset beyond end of file");
+        const size_t n = total - offset;
+        Pinned h(n);
+        read_file(file, h.p, offset, n);
+        d_file.reset(new DevBuf(n));
+        oip_check(oip_copy_h2d(ctx(), d_file->p, h.p, n));
+        const size_t cap = n / 1024 + 1;
+        d_payload.reset(new DevBuf(cap * 8));
+        int64_t cnt[3];
+        auto t0 = std::chrono::steady_clock::now();
+        oip_check(oip_aos_scan(ctx(), (const uint8_t *)d_file->p, n, (uint64_t *)d_payload->p, cap, cnt));
+        OLOG("%lld valid, %lld invalid, %lld empty AOS frames.", (long long)cnt[0], (long long)cnt[1], (long long)cnt[2]);
+        const size_t icap = (size_t)(cnt[0] * 880 / 882 + 1) * 866;
+        d_imdt_own.reset(new DevBuf(icap));
+        int64_t st[9];
+        oip_check(oip_imtr_deframe(ctx(), (const uint8_t *)d_file->p, (const uint64_t *)d_payload->p, cnt[0], (uint8_t *)d_imdt_own->p,
+                                   icap, st, &imdt_bytes));
+        double es = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        OLOG("%zu bytes processed for AOS filemap in %.3f seconds (%.1f MBps).", n, es, n / es / (1024.0 * 1024.0));
+        OLOG("%lld image transfer frames cut, %lld accepted (bad sig %lld, tail %lld, type %lld, CRC %lld).", (long long)st[0],
+             (long long)st[1], (long long)st[2], (long long)st[3], (long long)st[4], (long long)st[5]);
+        if (st[1] == 0) { OLOG("No more AOS frame data, end of job."); return 0; }
+        char nm[256];
+        snprintf(nm, sizeof nm, "%s_%s_%s_%04d%02d%02d_%02d%02d%02d.IMDT", afi.station, afi.satellite,
+                 st[7] == 0x11 ? "CMOS-1" : "CMOS-2", afi.year, afi.month, afi.day, afi.hour, afi.minute, afi.second); // ref :514-523
+        imdt_name = nm;
+        Pinned out((size_t)imdt_bytes);
+        oip_check(oip_copy_d2h(ctx(), out.p, d_imdt_own->p, (size_t)imdt_bytes));
+        oip_check(oip_ctx_sync(ctx()));
+        write_file(imdt_name, out.p, (size_t)imdt_bytes);                                             // cwd, ref :524
+        d_imdt = d_imdt_own.get();
+        OLOG("Parsing done.");
+    } else {
+        imdt_bytes = (int64_t)file_size(file);
+        Pinned h((size_t)imdt_bytes);
+        read_file(file, h.p, 0, (size_t)imdt_bytes);
+        d_imdt_own.reset(new DevBuf((size_t)imdt_bytes));
+        oip_check(oip_copy_h2d(ctx(), d_imdt_own->p, h.p, (size_t)imdt_bytes));
+        oip_check(oip_ctx_sync(ctx()));
+        d_imdt = d_imdt_own.get();
+    }
+    OLOG("Separating aux & image data ...");
+    const oip_frame_geom g{1536, 256};                                                                // ref :92-93
+    int64_t fst[4];
+    oip_check(oip_image_frames_index(ctx(), (const uint8_t *)d_imdt->p, (size_t)imdt_bytes, &g, nullptr, 0, fst));
+    const int64_t nf = fst[1];
+    std::vector<oip_frame_entry> ents((size_t)std::max<int64_t>(nf, 1));
+    oip_check(oip_image_frames_index(ctx(), (const uint8_t *)d_imdt->p, (size_t)imdt_bytes, &g, ents.data(), nf, fst));
+    const size_t aux_b = (size_t)nf * 49152, pan_b = (size_t)nf * 1024 * 12288 * 2, mss_b = (size_t)nf * 256 * 12288 * 2;
+    const std::string aux_name = build_output_path(imdt_name, "", ".AUX");                            // ref :260-262
+    const std::string pan_name = build_output_path(imdt_name, ".PAN", ".RAW");
+    const std::string mss_name = build_output_path(imdt_name, ".MSS", ".RAW");
+    if (nf > 0) {
+        DevBuf d_aux(aux_b), d_pan(pan_b), d_mss(mss_b);
+        oip_check(oip_unpack_frames(ctx(), (const uint8_t *)d_imdt->p, (size_t)imdt_bytes, &g, ents.data(), nf, (uint8_t *)d_aux.p,
+                                    (uint16_t *)d_pan.p, (uint16_t *)d_mss.p));
+        Pinned h(pan_b);
+        oip_check(oip_copy_d2h(ctx(), h.p, d_aux.p, aux_b)); oip_check(oip_ctx_sync(ctx())); write_file(aux_name, h.p, aux_b);
+        oip_check(oip_copy_d2h(ctx(), h.p, d_pan.p, pan_b)); oip_check(oip_ctx_sync(ctx())); write_file(pan_name, h.p, pan_b);
+        oip_check(oip_copy_d2h(ctx(), h.p, d_mss.p, mss_b)); oip_check(oip_ctx_sync(ctx())); write_file(mss_name, h.p, mss_b);
+    } else {
+        write_file(aux_name, "", 0); write_file(pan_name, "", 0); write_file(mss_name, "", 0);        // the reference creates them empty
+    }
+    OLOG("%4lld image frames processed.", (long long)fst[3]);
+    OLOG("Done.");
+    return 0;
+}
+
+// =============================================================================================
+// prestitch  (ref main.cpp:112-150, :270-286; stitcher.h)
+// =============================================================================================
+static int cmd_prestitch(const std::vector<std::string> &av)
+{
+    Args a = parse(av, {{"--pan1", nullptr, false}, {"--pan2", nullptr, false}, {"--rrc1", nullptr, false}, {"--rrc2", nullptr, false},
+                        {"--sections", "-s", false}, {"--section-lines", "-l", false}, {"--stitch-overlap", nullptr, false},
+                        {"--stt-threshold", nullptr, false}, {"--stt-maxdeltay", nullptr, false}, {"--edge-cols", "-e", false},
+                        {"--rrc", "-r", true}, {"--no-rrc", nullptr, true}, {"--only-calculate", "-c", true},
+                        {"--dx", nullptr, false}, {"--dy", nullptr, false}}, 0);
+    require(a, "pan1"); require(a, "pan2");
+    const std::string pan1 = a.get("pan1"), pan2 = a.get("pan2");
+    existing_file(pan1, "--pan1"); existing_file(pan2, "--pan2");
+    if (a.has("rrc1")) existing_file(a.get("rrc1"), "--rrc1");
+    if (a.has("rrc2")) existing_file(a.get("rrc2"), "--rrc2");
+    const long long overlap = a.geti("stitch-overlap", 200), edge = a.geti("edge-cols", 0);
+    if (edge < 0 || edge > overlap / 2) throw parse_error(CLI_VALIDATION, "--edge-cols: invalid edge cols");   // ref main.cpp:135-141
+    const int sections = (int)a.geti("sections", 10), sec_lines = (int)a.geti("section-lines", 16000);
+    const bool do_rrc = !a.has("no-rrc");
+    // Stitcher::Stitcher size checks, ref stitcher.h:60-77
+    const size_t s1 = file_size(pan1), s2 = file_size(pan2);
+    if ((size_t)sections * sec_lines * BYTES_PER_PIXEL > s1) throw std::invalid_argument("PAN1 size too small for SECTION & LINE_PER_SECTION argument");
+    if ((size_t)sections * sec_lines * BYTES_PER_PIXEL > s2) throw std::invalid_argument("PAN2 size too small for SECTION & LINE_PER_SECTION argument");
+    if (s1 != s2) throw std::invalid_argument("PAN1 size doesn't match PAN2 size");
+    const int64_t lines = (int64_t)(s1 / (PIXELS_PER_LINE * BYTES_PER_PIXEL));
+    OLOG("PAN: %lld lines total.", (long long)lines);
+    if (lines < (int64_t)sections * sec_lines)
+        throw std::invalid_argument("PAN line count less than sections times line-per-section, use smaller -s and/or -l value(s)");
+    if (!a.has("dx") || !a.has("dy"))
+        throw usage_error("inter-CMOS offset estimation (phase correlation, ref stitcher.h:148-201) is not part of this build: "
+                          "pass the offsets with --dx and --dy");
+    const double dx = a.getd("dx", 0), dy = a.getd("dy", 0);
+    OLOG("    dx: %.5f, dy: %.5f (given)", dx, dy);
+    if (a.has("only-calculate")) return 0;
+    if (do_rrc && (!a.has("rrc1") || !a.has("rrc2"))) throw std::runtime_error("open RRC Param file failed");
+
+    const size_t bytes = s1;
+    Pinned h(bytes);
+    DevBuf d_a(bytes), d_b(bytes);
+    std::string rrc2_path = pan2;
+    if (do_rrc) {                                                                                     // Stitcher::DoRRC, ref stitcher.h:141-146
+        const std::string p1 = build_output_path(pan1, ".RRC"), p2 = build_output_path(pan2, ".RRC");
+        for (int i = 0; i < 2; ++i) {
+            const std::string &src = i ? pan2 : pan1;
+            std::vector<double> kb = load_rrc(a.get(i ? "rrc2" : "rrc1"), PIXELS_PER_LINE);
+            DevBuf d_kb(kb.size() * 8);
+            read_file(src, h.p, 0, bytes);
+            oip_check(oip_copy_h2d(ctx(), d_a.p, h.p, bytes));
+            oip_check(oip_copy_h2d(ctx(), d_kb.p, kb.data(), kb.size() * 8));
+            OLOG("Do inplace RRC ...");
+            oip_check(oip_rrc_u16(ctx(), (uint16_t *)d_a.p, PIXELS_PER_LINE, lines, PIXELS_PER_LINE, (const double *)d_kb.p));
+            oip_check(oip_copy_d2h(ctx(), h.p, d_a.p, bytes));
+            oip_check(oip_ctx_sync(ctx()));
+            OLOG("Write RRC result as file \"%s\" ...", (i ? p2 : p1).c_str());
+            write_file(i ? p2 : p1, h.p, bytes);
+        }
+        rrc2_path = p2; // d_a now holds the corrected PAN2
+    } else {
+        read_file(pan2, h.p, 0, bytes);
+        oip_check(oip_copy_h2d(ctx(), d_a.p, h.p, bytes));
+    }
+    // Stitcher::PreStitch, ref stitcher.h:83-139
+    if (lines <= REMAP_ROW_GUARD) throw std::invalid_argument("too few data rows, please use cv::remap()");   // ref imageop.h:242-244
+    const std::string out = build_output_path(rrc2_path, ".PRESTT");
+    oip_check(oip_shift_cubic_u16(ctx(), (const uint16_t *)d_a.p, (uint16_t *)d_b.p, PIXELS_PER_LINE, lines, dx, dy, REMAP_SECTION_ROWS,
+                                  REMAP_ROW_GUARD));
+    oip_check(oip_pan_check_error(ctx()));
+    oip_check(oip_copy_d2h(ctx(), h.p, d_b.p, bytes));
+    oip_check(oip_ctx_sync(ctx()));
+    write_file(out, h.p, bytes);
+    OLOG("Pre-stitched PAN2 written to file '%s'.", out.c_str());
+    return 0;
+}
+
+// =============================================================================================
+// stitch  (ref main.cpp:153-190, stitcher.h:21-46, imageop.h:277-363)
+// =============================================================================================
+static int cmd_stitch(const std::vector<std::string> &av)
+{
+    Args a = parse(av, {{"--image1", nullptr, false}, {"--image2", nullptr, false}, {"--out", "-o", false}, {"--fold-cols", "-c", false},
+                        {"--GDAL", "-g", true}, {"--band-map", "-m", false}}, 0);
+    require(a, "image1"); require(a, "image2"); require(a, "fold-cols");
+    const int fold = (int)a.geti("fold-cols", 0);
+    if (fold < 2) throw parse_error(CLI_VALIDATION, "--fold-cols: fold column value too small");              // ref main.cpp:166-170
+    if (a.has("band-map") && !a.has("GDAL")) throw parse_error(CLI_REQUIRES, "--band-map requires --GDAL");     // ref :175-176
+    if (a.has("band-map")) {
+        int m[4];
+        if (sscanf(a.get("band-map").c_str(), "%d,%d,%d,%d", m, m + 1, m + 2, m + 3) != 4) throw parse_error(CLI_VALIDATION, "-m: need 4 band indices");
+        for (int i = 0; i < 4; ++i) if (m[i] <= 0 || m[i] > MSS_BANDS) throw parse_error(CLI_VALIDATION, "-m: invalid band index");
+    }
+    const std::string l = a.get("image1"), r = a.get("image2"), out = a.get("out");
+    const std::string le = lower(fs::path(l).extension().string()), re = lower(fs::path(r).extension().string());
+    if (le != re) throw std::invalid_argument("Stitch(): two images should be same type");                    // ref stitcher.h:31-33
+    if (le != ".tiff" && le != ".raw") throw std::invalid_argument("Stitch(): only RAW and TIFF image supported");
+    if (le == ".tiff") throw std::runtime_error("TIFF input is not supported by this build (no TIFF codec, SURVEY 8f N3); use RAW files");
+    if (out.empty() || lower(fs::path(out).extension().string()) == ".tiff")
+        throw std::runtime_error("TIFF output is not supported by this build (no TIFF codec, SURVEY 8f N3); pass -o <file>.RAW");
+    const size_t szl = file_size(l), szr = file_size(r);
+    if (szl != szr) throw std::invalid_argument("RAW image sizes not match");                                   // ref imageop.h:285-289
+    const int f = fold / 2;                                                                                     // ref main.cpp:189
+    const int64_t lines = (int64_t)(szl / (PIXELS_PER_LINE * BYTES_PER_PIXEL));
+    const int out_w = oip_pan_out_width(2, PIXELS_PER_LINE, f);
+    // host buffers straight through the fused kernel (no RRC, no shift): copies overlapped inside
+    Pinned hl(szl), hr(szr), ho((size_t)lines * out_w * 2);
+    read_file(l, hl.p, 0, szl);
+    read_file(r, hr.p, 0, szr);
+    oip_pan_desc d{};
+    d.n_ccd = 2; d.w = PIXELS_PER_LINE; d.total_rows = d.n_rows = lines; d.row0 = 0; d.fold_half = f;
+    d.section_rows = REMAP_SECTION_ROWS; d.row_guard = REMAP_ROW_GUARD;
+    for (int i = 0; i < 2; ++i) {
+        d.ccd[i].fmt = OIP_FMT_LE16; d.ccd[i].n_seg = 1;
+        d.ccd[i].seg[0] = {i ? hr.p : hl.p, 0, lines, (int64_t)PIXELS_PER_LINE * 2};
+    }
+    d.d_out = (uint16_t *)ho.p; d.out_pitch_px = out_w;
+    OLOG("Begin stitching two images ...");
+    oip_check(oip_pan_pipeline_host(ctx(), &d));
+    write_file(out, ho.p, (size_t)lines * out_w * 2);
+    OLOG("%zu bytes written.", (size_t)lines * out_w * 2);
+    return 0;
+}
+
+// =============================================================================================
+// default action  (ref main.cpp:193-258, :288-317; preproc.h)
+// =============================================================================================
+static int cmd_default(const std::vector<std::string> &av)
+{
+    Args a = parse(av, {{"--pan", nullptr, false}, {"--do-rrc4pan", nullptr, true}, {"--rrc-pan", nullptr, false},
+                        {"--write-rrcpan", nullptr, true}, {"--no-rrcpan", nullptr, true}, {"--mss", nullptr, false},
+                        {"--no-rrc4mss", nullptr, true}, {"--rrc-msb1", nullptr, false}, {"--rrc-msb2", nullptr, false},
+                        {"--rrc-msb3", nullptr, false}, {"--rrc-msb4", nullptr, false}, {"--slices", nullptr, false},
+                        {"--ibc-sections", nullptr, false}, {"--ibc-threshold", nullptr, false}, {"--line-offset", nullptr, false},
+                        {"--lines-section", nullptr, false}, {"--overlap-lines", nullptr, false}, {"--keep-leading", "-k", true},
+                        {"--poly", nullptr, false}}, 0);
+    if (a.has("pan")) existing_file(a.get("pan"), "--pan");
+    if (a.has("mss")) existing_file(a.get("mss"), "--mss");
+    if (a.has("rrc-pan") && !a.has("do-rrc4pan")) throw parse_error(CLI_REQUIRES, "--rrc-pan requires --do-rrc4pan");
+    const double thr = a.getd("ibc-threshold", 0.4);
+    if (thr < 0.0 || thr >= 1.0) throw parse_error(CLI_VALIDATION, "--ibc-threshold: invalid threshold value");   // ref main.cpp:233-239
+    const bool rrc_mss = !a.has("no-rrc4mss");
+    if (a.has("do-rrc4pan") && !a.has("rrc-pan")) throw usage_error("RRC parameter file of PAN needed");         // ref :290-292
+    if (rrc_mss && !(a.has("rrc-msb1") && a.has("rrc-msb2") && a.has("rrc-msb3") && a.has("rrc-msb4")))
+        throw usage_error("RRC parameter file of all MSS Bands needed");                                          // ref :293-299
+    // PreProcessor::CheckFilesAttributes, ref preproc.h:552-572
+    const size_t sp = file_size(a.get("pan")), sm = file_size(a.get("mss"));
+    if (sp != (size_t)MSS_BANDS * sm) throw std::runtime_error("PAN file size does not match MSS file size: PAN file should be 4x as large as MSS file");
+    if (sp % (PIXELS_PER_LINE * BYTES_PER_PIXEL)) throw std::runtime_error("PAN file size invalid: should be multiplies of 24576");
+    if (!a.has("poly"))
+        throw usage_error("inter-band correlation + polynomial fitting (ref preproc.h:224-347) is not part of this build: pass the "
+                          "coefficients with --poly FILE (4 lines: cx0 cx1 cy0 cy1 cy2)");
+    double cX[8], cY[12];
+    {
+        FILE *f = fopen(a.get("poly").c_str(), "r");
+        if (!f) throw std::invalid_argument("cannot open --poly file");
+        for (int b = 0; b < 4; ++b)
+            if (fscanf(f, "%lf %lf %lf %lf %lf", &cX[2 * b], &cX[2 * b + 1], &cY[3 * b], &cY[3 * b + 1], &cY[3 * b + 2]) != 5) {
+                fclose(f);
+                throw std::invalid_argument("--poly: need 4 lines of 5 numbers");
+            }
+        fclose(f);
+    }
+    const int wb = PIXELS_PER_LINE / MSS_BANDS;
+    const int64_t lines = (int64_t)(sm / (PIXELS_PER_LINE * BYTES_PER_PIXEL));
+    oip_mss_desc m{};
+    m.fmt = OIP_FMT_LE16; m.wb = wb; m.lines = lines; m.pitch_px = PIXELS_PER_LINE;
+    std::vector<std::unique_ptr<DevBuf>> kbs;
+    for (int b = 0; b < 4; ++b) {
+        m.d_kb[b] = nullptr;
+        if (rrc_mss) {
+            char key[16]; snprintf(key, sizeof key, "rrc-msb%d", b + 1);
+            existing_file(a.get(key), key);
+            std::vector<double> kb = load_rrc(a.get(key), wb);
+            kbs.emplace_back(new DevBuf(kb.size() * 8));
+            oip_check(oip_copy_h2d(ctx(), kbs.back()->p, kb.data(), kb.size() * 8));
+            oip_check(oip_ctx_sync(ctx()));
+            m.d_kb[b] = (const double *)kbs.back()->p;
+        }
+    }
+    memcpy(m.cX, cX, sizeof cX); memcpy(m.cY, cY, sizeof cY);
+    m.lines_per_section = (int)a.geti("lines-section", 20000); m.line_offset = a.geti("line-offset", 0);
+    m.overlap = (int)a.geti("overlap-lines", 520); m.keep_leading = a.has("keep-leading"); m.min_process_lines = 1500;
+    const int64_t out_rows = lines - m.line_offset - (m.keep_leading ? 0 : m.overlap);
+    if (out_rows <= 0) throw std::invalid_argument("Too few image lines left to process");
+    Pinned h(sm);
+    read_file(a.get("mss"), h.p, 0, sm);
+    DevBuf d_mss(sm), d_out((size_t)out_rows * wb * 8);
+    oip_check(oip_copy_h2d(ctx(), d_mss.p, h.p, sm));
+    oip_check(oip_memset_d(ctx(), d_out.p, 0, (size_t)out_rows * wb * 8));
+    OLOG("Doing inter-band alignment ...");
+    int64_t rows = 0;
+    oip_check(oip_band_align_merge(ctx(), d_mss.p, &m, (uint16_t *)d_out.p, &rows));
+    Pinned ho((size_t)out_rows * wb * 8);
+    oip_check(oip_copy_d2h(ctx(), ho.p, d_out.p, (size_t)out_rows * wb * 8));
+    oip_check(oip_ctx_sync(ctx()));
+    const std::string out = build_output_path(a.get("mss"), ".ALIGNED", ".RAW");
+    write_file(out, ho.p, (size_t)out_rows * wb * 8);
+    OLOG("%lld lines aligned; written to file [%s] (CV_16UC4 layout, %d px x 4 bands per line).", (long long)rows, out.c_str(), wb);
+    return 0;
+}
+
+static void usage()
+{
+    puts("Optical Satellite Image Pre-Processing/Processing Utility (B200-native hot path)\n"
+         "Usage: OpticalImageProcessor [OPTIONS] [SUBCOMMAND]\n\n"
+         "Options: -h,--help  -v,--version  --pan --mss --rrc-msb1..4 --do-rrc4pan --rrc-pan --no-rrc4mss --line-offset\n"
+         "         --lines-section --overlap-lines -k,--keep-leading --poly FILE\n"
+         "Subcommands:\n"
+         "  auxsep [-O,--offset N] file          Do aux & image data separation\n"
+         "  prestitch --pan1 F --pan2 F [--rrc1 F --rrc2 F] [-r|--no-rrc] [-c] --dx X --dy Y\n"
+         "  stitch --image1 F --image2 F -c,--fold-cols N -o OUT.RAW");
+}
+
+int main(int argc, const char *argv[])
+{
+    const char *lf = getenv("LOGFILE");
+    g_log = fopen(lf ? lf : "oip.log", "a");
+    try {
+        std::vector<std::string> av(argv + 1, argv + argc);
+        for (auto &t : av) {
+            if (t == "-v" || t == "--version") { puts("1.1"); return 0 + 255; }       // app.exit(e) + 255, ref main.cpp:263-264
+            if (t == "-h" || t == "--help") { usage(); return 0 + 255; }
+        }
+        try {
+            if (!av.empty() && av[0] == "auxsep") return cmd_auxsep({av.begin() + 1, av.end()});
+            if (!av.empty() && av[0] == "prestitch") return cmd_prestitch({av.begin() + 1, av.end()});
+            if (!av.empty() && av[0] == "stitch") return cmd_stitch({av.begin() + 1, av.end()});
+            return cmd_default(av);
+        } catch (const parse_error &e) {                                               // CLI::ParseError -> app.exit(e), ref :265-266
+            fprintf(stderr, "%s\nRun with --help for more information.\n", e.what());
+            return e.code;
+        }
+    } catch (usage_error &ex) {
+        printf("USAGE ERROR: %s.\n", ex.what());                                       // ref main.cpp:333-335
+        return 254;
+    } catch (std::exception &ex) {
+        logf("E", "%s.", ex.what());                                                   // ref :336-338
+        return 2;
+    } catch (...) {
+        logf("F", "UNKOWN FATAL ERROR OCCURED.");
+        return 1;
+    }
+}

@@ -1,0 +1,146 @@
+"""The drop-in boundary at process level: OpticalImageProcessor CLI (C++ host over the C ABI) keeps the
+reference's argv grammar, exit codes (ref main.cpp:260-267, :333-342) and cwd-relative output names
+(ref imageop.h:99-108).  Exit-code tests need no GPU; the file-flow tests compare the files the CLI
+writes with the files THE REFERENCE ITSELF wrote (tests/golden/ref_*.npz) and with the oracle."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from opticalimageprocessor_b200 import build, synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    build.build()
+    assert os.path.exists(build.CLI_BIN)
+    return build.CLI_BIN
+
+
+def run(cli, args, cwd):
+    env = dict(os.environ, LOGFILE=os.path.join(cwd, "test.log"))
+    return subprocess.run([cli] + args, cwd=cwd, env=env, capture_output=True, text=True, timeout=900)
+
+
+def sha_file(p):
+    h = hashlib.sha256()
+    with open(p, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 24), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+def test_exit_codes_and_grammar(cli, tmp_path):
+    d = str(tmp_path)
+    assert run(cli, ["-v"], d).returncode == 255 and run(cli, ["--version"], d).stdout.strip() == "1.1"  # app.exit(e)+255
+    assert run(cli, ["--help"], d).returncode == 255
+    assert run(cli, ["stitch", "--image1", "a.RAW"], d).returncode == 106           # CLI::RequiredError
+    assert run(cli, ["auxsep", "/nonexistent"], d).returncode == 105                # CLI::ExistingFile validator
+    assert run(cli, ["--bogus"], d).returncode == 109                               # CLI::ExtrasError
+    assert run(cli, ["stitch", "--image1", "a.RAW", "--image2", "b.RAW", "-c", "1"], d).returncode == 105  # fold < 2
+    r = run(cli, [], d)                                                              # usage_error -> 254, ref main.cpp:333-335
+    assert r.returncode == 254 and "USAGE ERROR: RRC parameter file of all MSS Bands needed." in r.stdout
+    open(os.path.join(d, "x.RAW"), "wb").write(b"\0" * 10)
+    open(os.path.join(d, "y.TIFF"), "wb").write(b"\0" * 10)
+    r = run(cli, ["stitch", "--image1", "x.RAW", "--image2", "y.TIFF", "-c", "200", "-o", "o.RAW"], d)
+    assert r.returncode == 2 and "two images should be same type" in r.stdout      # std::exception -> 2, ref :336-338
+    assert "two images should be same type" in open(os.path.join(d, "test.log")).read()  # LOGFILE, ref :324-328
+    r = run(cli, ["auxsep", "x.RAW"], d)
+    assert r.returncode == 2 and "unrecognized AOS file name pattern" in r.stdout   # ref aux_separator.h:208-213
+
+
+@pytest.mark.gpu
+def test_auxsep_files_equal_reference_run(cli, tmp_path):
+    """same downlink the reference's AuxSeparator parsed: identical file names and bytes"""
+    from test_reference_golden import _inputs
+    g = np.load(os.path.join(GOLD, "ref_auxsep.npz"))
+    d = str(tmp_path)
+    src = os.path.join(d, "in")
+    os.mkdir(src)
+    p = os.path.join(src, "KEL_MN200_20220316_120309_1.DAT")
+    _inputs()["auxsep_input"]().tofile(p)
+    r = run(cli, ["auxsep", p], d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    stem = str(g["imdt_name"])[:-5]
+    for ext, key in [(".IMDT", "imdt"), (".AUX", "aux"), (".PAN.RAW", "pan"), (".MSS.RAW", "mss")]:
+        f = os.path.join(d, stem + ext)
+        assert os.path.exists(f), f"{stem + ext} missing; cwd has {os.listdir(d)}"
+        assert os.path.getsize(f) == int(g[key + "_bytes"]) and sha_file(f) == str(g[key + "_sha256"]), ext
+    # .IMDT shortcut (ref aux_separator.h:204-206,230): same products again from the intermediate file
+    d2 = os.path.join(d, "again")
+    os.mkdir(d2)
+    r = run(cli, ["auxsep", os.path.join(d, stem + ".IMDT")], d2)
+    assert r.returncode == 0
+    assert sha_file(os.path.join(d2, stem + ".PAN.RAW")) == str(g["pan_sha256"])
+
+
+@pytest.mark.gpu
+def test_prestitch_and_stitch_task_flow(cli, tmp_path, oracle_mod):
+    """DOC/Usage.txt steps 1-2 on a 32768-line strip: file names, RRC files, PRESTT file, stitched RAW"""
+    from test_reference_golden import _inputs, _check_prestitch
+    g = np.load(os.path.join(GOLD, "ref_prestitch.npz"))
+    d = str(tmp_path)
+    W, rows = 12288, int(g["rows"])
+    src = _inputs()["prestitch_input"](rows, int(g["seed"]))
+    p2 = os.path.join(d, "SYN_PAN-2.RAW")
+    src.tofile(p2)
+    dx, dy = [float(v) for v in g["neg_shift"]]
+    # --no-rrc: PRESTT of the raw file must equal what the reference's PreStitch wrote for this input
+    r = run(cli, ["prestitch", "--pan1", p2, "--pan2", p2, "--no-rrc", f"--dx={dx}", f"--dy={dy}"], d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = np.fromfile(os.path.join(d, "SYN_PAN-2.PRESTT.RAW"), np.uint16).reshape(rows, W)
+    _check_prestitch(out, g, "neg")
+    # missing --dx/--dy: the estimate is not in this build -> usage error 254
+    assert run(cli, ["prestitch", "--pan1", p2, "--pan2", p2], d).returncode == 254
+    # with RRC (default): <stem>.RRC.RAW for both and <stem>.RRC.PRESTT.RAW, first/last rows vs oracle
+    kb1, kb2 = synth.rrc_coeffs(W, 1), synth.rrc_coeffs(W, 2)
+    synth.write_rrc_csv(os.path.join(d, "PAN-1.csv"), kb1)
+    synth.write_rrc_csv(os.path.join(d, "PAN-2.csv"), kb2)
+    p1 = os.path.join(d, "SYN_PAN-1.RAW")
+    src[::-1].tofile(p1)
+    r = run(cli, ["prestitch", f"--pan1={p1}", f"--pan2={p2}", "--rrc1", "PAN-1.csv", "--rrc2", "PAN-2.csv", "--dx", str(dx), "--dy", str(dy)], d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    sl = slice(0, 64)
+    rrc1 = np.fromfile(os.path.join(d, "SYN_PAN-1.RRC.RAW"), np.uint16).reshape(rows, W)
+    assert np.array_equal(rrc1[sl], oracle_mod.rrc(src[::-1][sl], kb1))
+    rrc2 = np.fromfile(os.path.join(d, "SYN_PAN-2.RRC.RAW"), np.uint16).reshape(rows, W)
+    assert np.array_equal(rrc2[-64:], oracle_mod.rrc(src[-64:], kb2))
+    pre = np.fromfile(os.path.join(d, "SYN_PAN-2.RRC.PRESTT.RAW"), np.uint16).reshape(rows, W)
+    want_top = oracle_mod.prestitch_shift(np.ascontiguousarray(rrc2[:600]), dx, dy)   # interior rows do not depend on the strip length
+    assert np.array_equal(pre[8:500], want_top[8:500])
+    # step 2: stitch the two RAW products (ref imageop.h:340-355)
+    r = run(cli, ["stitch", "--image1=SYN_PAN-1.RRC.RAW", "--image2=SYN_PAN-2.RRC.PRESTT.RAW", "--fold-cols=200", "-o", "stitched-PAN.RAW"], d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    st = np.fromfile(os.path.join(d, "stitched-PAN.RAW"), np.uint16).reshape(rows, 2 * (W - 100))
+    assert np.array_equal(st[:, :W - 100], rrc1[:, :W - 100]) and np.array_equal(st[:, W - 100:], pre[:, 100:])
+
+
+@pytest.mark.gpu
+def test_default_action_mss(cli, tmp_path, oracle_mod):
+    d = str(tmp_path)
+    W, wb, lines = 12288, 3072, 2100
+    rng = np.random.default_rng(3)
+    mss = rng.integers(0, 4096, (lines, W), dtype=np.uint16)
+    mss.tofile(os.path.join(d, "SYN_MSS-1.RAW"))
+    np.zeros((lines * 4, W), np.uint16).tofile(os.path.join(d, "SYN_PAN-1.RRC.RAW"))
+    kbs = [synth.rrc_coeffs(wb, 10 + b) for b in range(4)]
+    args = ["--pan=SYN_PAN-1.RRC.RAW", "--mss=SYN_MSS-1.RAW"]
+    for b in range(4):
+        synth.write_rrc_csv(os.path.join(d, f"MSS-1.B{b + 1}.csv"), kbs[b])
+        args += [f"--rrc-msb{b + 1}", f"MSS-1.B{b + 1}.csv"]
+    cX = [[0.8 + 0.1 * b, -1.5e-4 * (b + 1)] for b in range(4)]
+    cY = [[-3.2 + b, 2e-4 * (b + 1), -1e-8 * (b - 1.5)] for b in range(4)]
+    with open(os.path.join(d, "poly.txt"), "w") as f:
+        for b in range(4):
+            f.write("%r %r %r %r %r\n" % (cX[b][0], cX[b][1], cY[b][0], cY[b][1], cY[b][2]))
+    assert run(cli, args, d).returncode == 254          # coefficients not given: estimation is not in this build
+    r = run(cli, args + ["--poly", "poly.txt"], d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    planes = [oracle_mod.rrc(p, k) for p, k in zip(oracle_mod.mss_split(mss), kbs)]
+    n, want = oracle_mod.band_align(planes, cX, cY)
+    got = np.fromfile(os.path.join(d, "SYN_MSS-1.ALIGNED.RAW"), np.uint16).reshape(lines - 520, wb, 4)
+    assert n == lines - 520 and np.array_equal(got[:n], want[:n])
