@@ -54,6 +54,10 @@ int oip_abi_version(void);
 /* number of kernels this library launched on ctx since creation (bench.py "gpu_launches") */
 int64_t oip_ctx_launch_count(oip_ctx *ctx);
 
+/* tunables / test switches.  "pan_fast" (0|1, default 1): 0 sends every PAN tile through the generic kernel;
+ * "pan_fast_stages" (2..8): TMA stages per warp; "pan_fast_rows": output rows per warp-tile. */
+int oip_ctx_set_option(oip_ctx *ctx, const char *name, int64_t value);
+
 /* raw memory helpers for hosts without their own allocator (the CLI); torch callers pass data_ptr() */
 int oip_dev_alloc(oip_ctx *ctx, size_t bytes, void **d_ptr);
 int oip_dev_free(oip_ctx *ctx, void *d_ptr);
@@ -201,6 +205,12 @@ void oip_cubic_tab(float *tab128);
 /* source rows [*first,*last) of CCD `ccd` that producing [row0,row0+n_rows) reads (halo planning) */
 int oip_pan_rows_needed(const oip_pan_desc *desc, int ccd, int64_t *first, int64_t *last,
                         int64_t *stale_first, int64_t *stale_last);
+
+/* host-only planning diagnostic (no device work): how oip_pan_pipeline would split the output between its
+ * regular-interior fast kernel and the exact generic kernel.  cover (n_rows x out_pitch_px bytes, zeroed by the
+ * caller, may be NULL): += 1 per generic tile pixel, += 2 per fast tile pixel.
+ * stats = {generic px, fast px, generic tiles, fast warp-tiles}. */
+int oip_pan_plan_coverage(const oip_pan_desc *desc, int enable_fast, int fast_rows, uint8_t *cover, int64_t stats[4]);
 
 /* stand-alone forms of the same kernel (same code path, one CCD / no shift) */
 /* replaces Stitcher::PreStitch + IMO::SectionaryRemap -- ref stitcher.h:83-139, imageop.h:230-275 */

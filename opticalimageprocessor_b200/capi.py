@@ -61,6 +61,7 @@ SYMBOLS = {
     "oip_last_error": (C.c_char_p, []),
     "oip_abi_version": (_I, []),
     "oip_ctx_launch_count": (_I64, [_VP]),
+    "oip_ctx_set_option": (_I, [_VP, C.c_char_p, _I64]),
     "oip_dev_alloc": (_I, [_VP, _SZ, C.POINTER(_VP)]),
     "oip_dev_free": (_I, [_VP, _VP]),
     "oip_host_alloc_pinned": (_I, [_SZ, C.POINTER(_VP)]),
@@ -79,6 +80,7 @@ SYMBOLS = {
     "oip_rrc_u16": (_I, [_VP, _VP, _I, _I64, _I64, _VP]),
     "oip_load_rrc_csv": (_I, [C.c_char_p, _I, _VP]),
     "oip_pan_pipeline": (_I, [_VP, C.POINTER(PanDesc)]),
+    "oip_pan_plan_coverage": (_I, [C.POINTER(PanDesc), _I, _I, _VP, C.POINTER(_I64)]),
     "oip_pan_out_width": (_I, [_I, _I, _I]),
     "oip_pan_check_error": (_I, [_VP]),
     "oip_cubic_tab": (None, [_VP]),

@@ -115,6 +115,17 @@ void oip_ctx_destroy(oip_ctx *ctx)
     delete ctx;
 }
 
+int oip_ctx_set_option(oip_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name) return oip::fail(OIP_E_INVALID, "oip_ctx_set_option: null argument");
+    if (!strcmp(name, "pan_fast")) ctx->pan_fast = value != 0;
+    else if (!strcmp(name, "pan_fast_stages") && value >= 2 && value <= 8) ctx->pan_fast_stages = (int)value;
+    else if (!strcmp(name, "pan_fast_rows") && value >= 16 && value <= 32768) ctx->pan_fast_rows = (int)value;
+    else return oip::fail(OIP_E_INVALID, "unknown option or value out of range: %s=%lld", name, (long long)value);
+    ctx->plan_key.clear();
+    return OIP_OK;
+}
+
 int oip_ctx_sync(oip_ctx *ctx)
 {
     OIP_CHECK_CTX(ctx);

@@ -20,7 +20,13 @@ struct oip_ctx {
     void *d_plan = nullptr;
     size_t d_plan_cap = 0;
     std::vector<uint8_t> plan_key;
-    int64_t plan_tiles = 0;
+    int64_t plan_tiles = 0;      // generic tiles (pan_kernel CTAs)
+    int64_t plan_fast_ctas = 0;  // pan_fast_kernel CTAs (4 warp-tiles each)
+    size_t plan_fast_off = 0;    // byte offset of the FastTile array inside d_plan
+    // tunables (oip_ctx_set_option)
+    int pan_fast = 1;            // 0: everything on the generic kernel
+    int pan_fast_stages = 4;     // TMA stages per warp
+    int pan_fast_rows = 128;     // output rows per warp-tile
     void *d_mss_plan = nullptr;
     size_t d_mss_plan_cap = 0;
     std::vector<uint8_t> mss_plan_key;
@@ -32,7 +38,7 @@ struct oip_ctx {
     void *h_pinned = nullptr; // small pinned staging for counters / plans
     size_t h_pinned_cap = 0;
     int *d_err = nullptr;     // device-side error flag
-    bool pan_attr_set = false, mss_attr_set = false;
+    bool pan_attr_set = false, mss_attr_set = false, fast_attr_set = false;
     // host-buffer pipeline (oip_pan_pipeline_host): staging slots + side streams
     void *host_pipe = nullptr;
 };
@@ -121,6 +127,43 @@ __device__ __forceinline__ void stg_na_v4(void *p, uint4 v)
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                  "r"(v.w)
                  : "memory");
+}
+// packed fp32 pairs: two pixels per FFMA2/FADD2, each lane rounds exactly like the scalar op
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo_of(f2 v)
+{
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi_of(f2 v)
+{
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false (it honours the
+// explicit .rn only for scalar ops), and it also folds fma(a,b,-0.0) back into a mul when the -0.0 is
+// a known constant.  The product is therefore an FMA whose addend is a (-0.0,-0.0) pair LOADED AT RUN
+// TIME (plan header): RN(a*b + -0.0) == RN(a*b) bit for bit, and an FMA cannot be fused with the add
+// that follows.  SASS check: FFMA2 count == number of products, FADD2 count == number of sums.
+__device__ __forceinline__ f2 mul2(f2 a, f2 b, f2 nz)
+{
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+    return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
 }
 __device__ __forceinline__ uint32_t bswap16x2(uint32_t v) { return __byte_perm(v, 0, 0x2301); }
 

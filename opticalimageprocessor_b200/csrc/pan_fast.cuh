@@ -1,0 +1,57 @@
+// pan_fast.cuh -- warp-tile description shared by the planner (pan_pipeline.cu) and the fast kernel (pan_fast.cu)
+#pragma once
+#include <cuda.h> // CUtensorMap (type only; the encoder is fetched with cudaGetDriverEntryPoint)
+
+#include "oip_common.cuh"
+
+namespace oip {
+namespace panfast {
+
+constexpr int WARPS = 4;        // independent warp workers per CTA (one warp-tile each)
+constexpr int RC = 4;           // source rows per TMA stage
+constexpr int BOX_W = 136;      // u16 per box row (272 B = 17 x 16 B); two boxes per stage
+constexpr int HALF_MAX = 124;   // REMAP: output columns per half (31 lanes x 4); window = half + 3 (+1 slack) columns
+constexpr int COPY_MAX = 256;   // COPY: output columns per warp-tile (32 lanes x 8)
+constexpr int MAX_MAPS = 8 * OIP_MAX_SEG;
+
+enum { FT_NONE = -1, FT_COPY = 0, FT_REMAP = 1 };
+
+// one warp's work: a column strip of one CCD over n_rows output rows whose source rows sit in ONE row
+// segment, whose 4x4 footprints are all inside the section's fresh rows / the CCD's columns, and whose
+// fixed-point map advances by exactly 32 per output pixel and per output row ("regular")
+struct FastTile {
+    int32_t kind;     // FT_*
+    int32_t ccd;
+    int32_t tmap;     // tensor map index = ccd * OIP_MAX_SEG + segment
+    int32_t x_begin;  // first CCD column produced
+    int32_t half;     // REMAP: columns per half (multiple of 4, <= HALF_MAX), n_cols = 2*half; COPY: n_cols (multiple of 8)
+    int32_t src_x0;   // REMAP: source column of the first tap of x_begin;  COPY: x_begin
+    int32_t src_y0;   // row inside the segment of the first source row (first tap row of output row 0)
+    int32_t n_rows;   // output rows
+    int32_t fx, fy;   // sub-pixel phase (1/32) of the whole tile
+    int64_t out_off;  // element offset in the output raster of (output row 0, x_begin)
+};
+
+struct FastCcd {
+    const double *kb; // {k,b} per detector or null
+    int32_t swap;     // 1: samples are big-endian
+    int32_t pad;
+};
+
+struct FastParams {
+    CUtensorMap tmap[MAX_MAPS];
+    FastCcd ccd[8];
+    const FastTile *tiles;
+    uint16_t *out;
+    int64_t out_pitch;
+    const float *tab; // 32x4 cubic weights, then the run-time (-0.0,-0.0) pair
+    int32_t w;
+    int32_t n_stage; // TMA stages per warp (2..8)
+};
+
+// host side (pan_fast.cu)
+int fast_encode_tmap(CUtensorMap *tm, const void *base, int w, int64_t n_rows, int64_t pitch_bytes);
+int fast_launch(oip_ctx *ctx, const FastParams &P, int64_t n_ctas);
+
+} // namespace panfast
+} // namespace oip

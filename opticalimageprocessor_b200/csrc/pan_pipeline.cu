@@ -20,6 +20,7 @@
 // Irregular situations (map rounding anomalies, section/image borders, partial chunks, unaligned or
 // packed inputs) take exact but slower generic paths inside the same kernel.
 #include "oip_common.cuh"
+#include "pan_fast.cuh"
 #include "pan_plan.hpp"
 
 namespace oip {
@@ -165,46 +166,6 @@ __device__ __forceinline__ ChunkRows chunk_rows(const Tile &T, double dY, int k)
     }
     c.n_new = max(0, c.t_hi - c.new_lo + 1);
     return c;
-}
-
-// ---------------------------------------------------------------------------------------------
-// packed fp32 pairs: two pixels per FMUL2/FADD2, each lane rounds exactly like the scalar op
-// ---------------------------------------------------------------------------------------------
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pk(float lo, float hi)
-{
-    f2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float lo_of(f2 v)
-{
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return a;
-}
-__device__ __forceinline__ float hi_of(f2 v)
-{
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return b;
-}
-// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false (it honours the
-// explicit .rn only for scalar ops), and it also folds fma(a,b,-0.0) back into a mul when the -0.0 is
-// a known constant.  The product is therefore an FMA whose addend is a (-0.0,-0.0) pair LOADED AT RUN
-// TIME (plan header): RN(a*b + -0.0) == RN(a*b) bit for bit, and an FMA cannot be fused with the add
-// that follows.  SASS check: FFMA2 count == number of products, FADD2 count == number of sums.
-__device__ __forceinline__ f2 mul2(f2 a, f2 b, f2 nz)
-{
-    f2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
-    return r;
-}
-__device__ __forceinline__ f2 add2(f2 a, f2 b)
-{
-    f2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
 }
 
 // ring slots s..s+4 of one row, each an (left-half pixel, right-half pixel) pair
@@ -657,53 +618,221 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pan_kernel(const __grid_const
 // ------------------------------------------------------------------------------------ host side
 struct PlanKey {
     int n_ccd, w, fold_half, section_rows, row_guard, shifted[8];
-    int64_t total_rows, row0, n_rows;
+    int64_t total_rows, row0, n_rows, out_pitch;
     double dX[8], dY[8];
+    // what the fast-path split depends on: eligibility per CCD, row-segment layout, tunables
+    int fast[8], n_seg[8], fast_rows;
+    int64_t seg_row0[8][OIP_MAX_SEG], seg_rows[8][OIP_MAX_SEG];
 };
 
-static int build_tiles(const oip_pan_desc *d, std::vector<Tile> &tiles)
+// generic tiles (pan_kernel) over the rectangle [x_lo,x_hi) x [g_lo,g_hi) of CCD i inside shift segment s
+static void emit_generic(std::vector<Tile> &tiles, int i, bool shifted, const ShiftSegment &s, int x_lo, int x_hi,
+                         int out_x_lo, int64_t g_lo, int64_t g_hi)
+{
+    if (x_hi <= x_lo || g_hi <= g_lo) return;
+    for (int64_t g = g_lo; g < g_hi; g += TH) {
+        const int nr = (int)std::min<int64_t>(TH, g_hi - g);
+        // column strips of equal width (no skinny last strip); even for the 32-bit paired stores of REMAP
+        // tiles, multiple of 8 for the 128-bit stores of COPY tiles
+        const int n_strips = (x_hi - x_lo + TW - 1) / TW;
+        const int align = shifted ? 2 : 8;
+        const int sw = std::min(TW, ((x_hi - x_lo + n_strips - 1) / n_strips + align - 1) / align * align);
+        for (int x = x_lo; x < x_hi; x += sw) {
+            Tile t{};
+            t.ccd = i;
+            t.kind = shifted ? KIND_REMAP : KIND_COPY;
+            t.x_begin = x;
+            t.x_end = std::min(x_hi, x + sw);
+            t.out_x = out_x_lo + (x - x_lo);
+            t.n_rows = nr;
+            t.g0 = g;
+            t.j0 = shifted ? s.j0 + (g - s.g0) : g;
+            t.sec_off = s.sec_off;
+            t.stale_off = s.stale_off;
+            t.rows_s = s.rows_s;
+            t.hbuf = s.hbuf;
+            tiles.push_back(t);
+        }
+    }
+}
+
+// index of the row segment of CCD c that holds all of the global source rows [a, b], -1 if none does
+static int seg_holding(const oip_ccd_src &c, int64_t a, int64_t b)
+{
+    for (int k = 0; k < c.n_seg; ++k)
+        if (a >= c.seg[k].row0 && b < c.seg[k].row0 + c.seg[k].n_rows) return k;
+    return -1;
+}
+
+struct ColSpan { int xa, xb, sx_a; }; // columns [xa,xb) on the fast path; sx_a = fixed-point map of column xa
+
+// warp-tiles (pan_fast_kernel) for output rows [ga,gb) x the column span; the first source row of output row
+// ga is row `src_row_a` of row segment `seg`; fx/fy = sub-pixel phase
+static void emit_fast(std::vector<panfast::FastTile> &out, int kind, int i, int seg, const ColSpan &cs, int lo, int out_x_ccd,
+                      int64_t ga, int64_t gb, int64_t src_row_a, int fy, const oip_pan_desc *d, int th)
+{
+    const int max_w = kind == panfast::FT_REMAP ? 2 * panfast::HALF_MAX : panfast::COPY_MAX;
+    const int width = cs.xb - cs.xa; // multiple of 8
+    const int n_strips = (width + max_w - 1) / max_w;
+    const int base = width / n_strips / 8 * 8;
+    int extra = (width - base * n_strips) / 8; // this many strips are 8 columns wider
+    const int64_t len = gb - ga;
+    const int n_t = (int)((len + th - 1) / th);
+    const int64_t h = (len + n_t - 1) / n_t;
+    for (int64_t g = ga; g < gb; g += h) {
+        int x = cs.xa, ex = extra;
+        for (int sidx = 0; sidx < n_strips; ++sidx) {
+            const int sw = base + (ex > 0 ? 8 : 0);
+            if (ex > 0) --ex;
+            panfast::FastTile t{};
+            t.kind = kind;
+            t.ccd = i;
+            t.tmap = i * OIP_MAX_SEG + seg;
+            t.x_begin = x;
+            t.n_rows = (int)std::min<int64_t>(h, gb - g);
+            t.src_y0 = (int)(src_row_a + (g - ga));
+            t.out_off = (g - d->row0) * d->out_pitch_px + out_x_ccd + (x - lo);
+            if (kind == panfast::FT_REMAP) {
+                const int sx = cs.sx_a + 32 * (x - cs.xa);
+                t.half = sw / 2;
+                t.src_x0 = sat_short(sx >> 5) - 1;
+                t.fx = sx & 31;
+                t.fy = fy;
+            } else {
+                t.half = sw;
+                t.src_x0 = x;
+            }
+            out.push_back(t);
+            x += sw;
+        }
+    }
+}
+
+static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows, std::vector<Tile> &tiles,
+                      std::vector<panfast::FastTile> &ftiles)
 {
     const int n = d->n_ccd, w = d->w, f = d->fold_half;
+    const int64_t r_lo = d->row0, r_hi = d->row0 + d->n_rows;
+    std::vector<panfast::FastTile> fl;
+    // keep the plan small on very long strips: taller warp-tiles
+    int th = std::max(16, fast_rows);
+    while ((double)d->n_rows / th * ((double)n * w / 248.0) > 400000.0) th *= 2;
     int out_x = 0;
     for (int i = 0; i < n; ++i) {
+        const oip_ccd_src &C = d->ccd[i];
         const int lo = i == 0 ? 0 : f, hi = i == n - 1 ? w : w - f;
-        const bool shifted = d->ccd[i].shifted != 0;
-        std::vector<ShiftSegment> segs;
-        if (shifted) {
-            if (!plan_shift_segments(d->total_rows, d->section_rows, d->row_guard, d->ccd[i].dY, segs))
-                return fail(OIP_E_INVALID, "invalid section geometry (section_rows=%d row_guard=%d dY=%g)",
-                            d->section_rows, d->row_guard, d->ccd[i].dY);
-        } else {
-            segs.push_back({0, d->total_rows, 0, 0, 0, -1, 0});
-        }
-        for (const ShiftSegment &s : segs) {
-            int64_t g0 = std::max<int64_t>(s.g0, d->row0), g1 = std::min<int64_t>(s.g1, d->row0 + d->n_rows);
-            for (int64_t g = g0; g < g1; g += TH) {
-                int nr = (int)std::min<int64_t>(TH, g1 - g);
-                // column strips of equal width (no skinny last strip); even for the 32-bit paired
-                // stores of REMAP tiles, multiple of 8 for the 128-bit stores of COPY tiles
-                const int n_strips = (hi - lo + TW - 1) / TW;
-                const int align = shifted ? 2 : 8;
-                const int sw = std::min(TW, ((hi - lo + n_strips - 1) / n_strips + align - 1) / align * align);
-                for (int x = lo; x < hi; x += sw) {
-                    Tile t{};
-                    t.ccd = i;
-                    t.kind = shifted ? KIND_REMAP : KIND_COPY;
-                    t.x_begin = x;
-                    t.x_end = std::min(hi, x + sw);
-                    t.out_x = out_x + (x - lo);
-                    t.n_rows = nr;
-                    t.g0 = g;
-                    t.j0 = shifted ? s.j0 + (g - s.g0) : g;
-                    t.sec_off = s.sec_off;
-                    t.stale_off = s.stale_off;
-                    t.rows_s = s.rows_s;
-                    t.hbuf = s.hbuf;
-                    tiles.push_back(t);
+        const bool shifted = C.shifted != 0, fast = fast_ccd[i];
+        if (!shifted) {
+            const ShiftSegment s{0, d->total_rows, 0, 0, 0, -1, 0};
+            // COPY: 128-bit stores need the output column to be a multiple of 8
+            const int xs = lo + ((8 - (out_x % 8)) % 8);
+            const int usable = fast && xs < hi ? ((hi - xs) & ~7) : 0;
+            int64_t cur = r_lo;
+            if (usable >= 8) {
+                const ColSpan cs{xs, xs + usable, 0};
+                while (cur < r_hi) {
+                    const int k = seg_holding(C, cur, cur);
+                    if (k < 0) break;
+                    const int64_t end = std::min<int64_t>(r_hi, C.seg[k].row0 + C.seg[k].n_rows);
+                    emit_fast(fl, panfast::FT_COPY, i, k, cs, lo, out_x, cur, end, cur - C.seg[k].row0, 0, d, th);
+                    emit_generic(tiles, i, false, s, lo, xs, out_x, cur, end);
+                    emit_generic(tiles, i, false, s, xs + usable, hi, out_x + (xs + usable - lo), cur, end);
+                    cur = end;
                 }
             }
+            emit_generic(tiles, i, false, s, lo, hi, out_x, cur, r_hi); // rows no single segment holds (or no fast path)
+            out_x += hi - lo;
+            continue;
+        }
+        std::vector<ShiftSegment> segs;
+        if (!plan_shift_segments(d->total_rows, d->section_rows, d->row_guard, C.dY, segs))
+            return fail(OIP_E_INVALID, "invalid section geometry (section_rows=%d row_guard=%d dY=%g)", d->section_rows,
+                        d->row_guard, C.dY);
+        // fast column spans: interior footprints, regular map, output column a multiple of 4 (64-bit stores)
+        std::vector<ColSpan> spans;
+        if (fast) {
+            int x = lo;
+            while (x < hi) {
+                const int sx = map_fixed(x, C.dX), ix = sat_short(sx >> 5) - 1;
+                if (!(ix >= 0 && ix < w - 3)) { ++x; continue; }
+                int xe = x + 1, sxe = sx;
+                while (xe < hi) {
+                    const int s2 = map_fixed(xe, C.dX), i2 = sat_short(s2 >> 5) - 1;
+                    if (s2 != sxe + 32 || !(i2 >= 0 && i2 < w - 3)) break;
+                    sxe = s2;
+                    ++xe;
+                }
+                const int xs = x + ((4 - ((out_x + x - lo) % 4)) % 4);
+                const int usable = xs < xe ? ((xe - xs) & ~7) : 0;
+                if (usable >= 16) spans.push_back({xs, xs + usable, sx + 32 * (xs - x)});
+                x = xe;
+            }
+        }
+        for (const ShiftSegment &s : segs) {
+            const int64_t ga = std::max<int64_t>(s.g0, r_lo), gb = std::min<int64_t>(s.g1, r_hi);
+            if (gb <= ga) continue;
+            if (spans.empty()) {
+                emit_generic(tiles, i, true, s, lo, hi, out_x, ga, gb);
+                continue;
+            }
+            // fast row runs: 4 tap rows inside the section's fresh rows, regular map, one row segment
+            int64_t g = ga, gen_from = ga;
+            while (g < gb) {
+                auto probe = [&](int64_t gg, int &sy, int &k) {
+                    const int64_t j = s.j0 + (gg - s.g0);
+                    sy = map_fixed(j, C.dY);
+                    const int t = sat_short(sy >> 5) - 1;
+                    if (!(t >= 0 && t + 3 < s.rows_s && t + 3 < s.hbuf)) return false;
+                    k = seg_holding(C, s.sec_off + t, s.sec_off + t + 3);
+                    return k >= 0;
+                };
+                int sy0, k0;
+                if (!probe(g, sy0, k0)) { ++g; continue; }
+                int64_t ge = g + 1;
+                int syp = sy0;
+                while (ge < gb) {
+                    int sy, k;
+                    if (!probe(ge, sy, k) || sy != syp + 32 || k != k0) break;
+                    syp = sy;
+                    ++ge;
+                }
+                if (ge - g >= 8) {
+                    emit_generic(tiles, i, true, s, lo, hi, out_x, gen_from, g); // rows before the run: full width
+                    const int64_t src_row = s.sec_off + (sat_short(sy0 >> 5) - 1) - C.seg[k0].row0;
+                    int xg = lo; // columns between the fast spans stay generic
+                    for (const ColSpan &cs : spans) {
+                        emit_generic(tiles, i, true, s, xg, cs.xa, out_x + (xg - lo), g, ge);
+                        emit_fast(fl, panfast::FT_REMAP, i, k0, cs, lo, out_x, g, ge, src_row, sy0 & 31, d, th);
+                        xg = cs.xb;
+                    }
+                    emit_generic(tiles, i, true, s, xg, hi, out_x + (xg - lo), g, ge);
+                    gen_from = ge;
+                }
+                g = ge;
+            }
+            emit_generic(tiles, i, true, s, lo, hi, out_x, gen_from, gb);
         }
         out_x += hi - lo;
+    }
+    // CTA = WARPS warp-tiles of one kind / CCD / row band, bands in raster order (neighbouring strips share halo
+    // columns through L2, COPY and REMAP CTAs interleave on every SM)
+    std::stable_sort(fl.begin(), fl.end(), [&](const panfast::FastTile &a, const panfast::FastTile &b) {
+        const int64_t ra = a.out_off / d->out_pitch_px / th, rb = b.out_off / d->out_pitch_px / th;
+        if (ra != rb) return ra < rb;
+        if (a.ccd != b.ccd) return a.ccd < b.ccd;
+        return a.x_begin < b.x_begin;
+    });
+    ftiles.clear();
+    panfast::FastTile none{};
+    none.kind = panfast::FT_NONE;
+    for (size_t p = 0; p < fl.size();) {
+        size_t q = p;
+        const int64_t band = fl[p].out_off / d->out_pitch_px / th;
+        while (q < fl.size() && q - p < (size_t)panfast::WARPS && fl[q].ccd == fl[p].ccd && fl[q].kind == fl[p].kind &&
+               fl[q].out_off / d->out_pitch_px / th == band)
+            ftiles.push_back(fl[q++]);
+        for (size_t z = q - p; z < (size_t)panfast::WARPS; ++z) ftiles.push_back(none);
+        p = q;
     }
     return OIP_OK;
 }
@@ -785,6 +914,54 @@ static int validate_desc(const oip_pan_desc *d)
     return OIP_OK;
 }
 
+// which CCDs may use the fast kernel (TMA tensor copies, 64/128-bit stores): alignment and format
+static void fast_eligibility(const oip_pan_desc *d, bool enable, bool *fast_ccd)
+{
+    const bool out_ok = (((uintptr_t)d->d_out & 15) == 0) && (d->out_pitch_px % 8 == 0);
+    for (int i = 0; i < d->n_ccd; ++i) {
+        const oip_ccd_src &c = d->ccd[i];
+        bool ok = enable && out_ok && (c.fmt == OIP_FMT_LE16 || c.fmt == OIP_FMT_BE16) && (((uintptr_t)c.d_kb & 15) == 0) &&
+                  d->w >= 64;
+        for (int s = 0; s < c.n_seg && ok; ++s)
+            ok = c.seg[s].base && (((uintptr_t)c.seg[s].base & 15) == 0) && (c.seg[s].pitch_bytes % 16 == 0) &&
+                 c.seg[s].pitch_bytes >= 2 * (int64_t)d->w && c.seg[s].n_rows > 0;
+        fast_ccd[i] = ok;
+    }
+}
+
+/* host-only diagnostic: how the planner splits [row0,row0+n_rows) x out_w between the two kernels.  cover (may be
+ * null) receives, per output pixel, 1 = generic kernel, 2 = fast kernel, summed if a pixel were planned twice. */
+extern "C" int oip_pan_plan_coverage(const oip_pan_desc *d, int enable_fast, int fast_rows, uint8_t *cover, int64_t stats[4])
+{
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    bool fast_ccd[8] = {};
+    fast_eligibility(d, enable_fast != 0, fast_ccd);
+    std::vector<pan::Tile> tiles;
+    std::vector<panfast::FastTile> ftiles;
+    rc = pan::build_plan(d, fast_ccd, fast_rows, tiles, ftiles);
+    if (rc) return rc;
+    int64_t px_gen = 0, px_fast = 0, n_fast = 0;
+    const int64_t pitch = d->out_pitch_px;
+    for (const pan::Tile &t : tiles) {
+        px_gen += (int64_t)(t.x_end - t.x_begin) * t.n_rows;
+        if (cover)
+            for (int64_t r = 0; r < t.n_rows; ++r)
+                for (int x = 0; x < t.x_end - t.x_begin; ++x) cover[(t.g0 - d->row0 + r) * pitch + t.out_x + x] += 1;
+    }
+    for (const panfast::FastTile &t : ftiles) {
+        if (t.kind < 0) continue;
+        ++n_fast;
+        const int nc = t.kind == panfast::FT_REMAP ? 2 * t.half : t.half;
+        px_fast += (int64_t)nc * t.n_rows;
+        if (cover)
+            for (int64_t r = 0; r < t.n_rows; ++r)
+                for (int x = 0; x < nc; ++x) cover[t.out_off + r * pitch + x] += 2;
+    }
+    if (stats) { stats[0] = px_gen; stats[1] = px_fast; stats[2] = (int64_t)tiles.size(); stats[3] = n_fast; }
+    return OIP_OK;
+}
+
 extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
 {
     OIP_CHECK_CTX(ctx);
@@ -795,19 +972,28 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
     const int out_w = oip_pan_out_width(d->n_ccd, d->w, d->fold_half);
     if (d->out_pitch_px < out_w) return fail(OIP_E_INVALID, "out_pitch_px=%lld < out_w=%d", (long long)d->out_pitch_px, out_w);
 
+    bool fast_ccd[8] = {};
+    fast_eligibility(d, ctx->pan_fast != 0, fast_ccd);
+
     // ---- plan (cached on the geometry)
     pan::PlanKey key{};
     key.n_ccd = d->n_ccd; key.w = d->w; key.fold_half = d->fold_half; key.section_rows = d->section_rows;
     key.row_guard = d->row_guard; key.total_rows = d->total_rows; key.row0 = d->row0;
-    key.n_rows = d->n_rows;
-    for (int i = 0; i < d->n_ccd; ++i) { key.dX[i] = d->ccd[i].dX; key.dY[i] = d->ccd[i].dY; key.shifted[i] = d->ccd[i].shifted != 0; }
+    key.n_rows = d->n_rows; key.out_pitch = d->out_pitch_px; key.fast_rows = ctx->pan_fast_rows;
+    for (int i = 0; i < d->n_ccd; ++i) {
+        key.dX[i] = d->ccd[i].dX; key.dY[i] = d->ccd[i].dY; key.shifted[i] = d->ccd[i].shifted != 0;
+        key.fast[i] = fast_ccd[i]; key.n_seg[i] = d->ccd[i].n_seg;
+        for (int s = 0; s < d->ccd[i].n_seg; ++s) { key.seg_row0[i][s] = d->ccd[i].seg[s].row0; key.seg_rows[i][s] = d->ccd[i].seg[s].n_rows; }
+    }
     const uint8_t *kb = reinterpret_cast<const uint8_t *>(&key);
     if (ctx->plan_key.size() != sizeof key || memcmp(ctx->plan_key.data(), kb, sizeof key) != 0) {
         std::vector<pan::Tile> tiles;
-        rc = pan::build_tiles(d, tiles);
+        std::vector<panfast::FastTile> ftiles;
+        rc = pan::build_plan(d, fast_ccd, ctx->pan_fast_rows, tiles, ftiles);
         if (rc) return rc;
         pan::upload_tab();
-        size_t bytes = tiles.size() * sizeof(pan::Tile) + 1024;
+        const size_t fast_off = (1024 + tiles.size() * sizeof(pan::Tile) + 63) / 64 * 64;
+        const size_t bytes = fast_off + ftiles.size() * sizeof(panfast::FastTile) + 64;
         if (bytes > ctx->d_plan_cap) {
             if (ctx->d_plan) { OIP_CUDA(cudaStreamSynchronize(ctx->stream)); OIP_CUDA(cudaFree(ctx->d_plan)); ctx->d_plan = nullptr; }
             OIP_CUDA(cudaMalloc(&ctx->d_plan, bytes * 2));
@@ -822,11 +1008,40 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         if (!tiles.empty())
             OIP_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_plan + 1024, tiles.data(), tiles.size() * sizeof(pan::Tile),
                                      cudaMemcpyHostToDevice, ctx->stream));
+        if (!ftiles.empty())
+            OIP_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_plan + fast_off, ftiles.data(), ftiles.size() * sizeof(panfast::FastTile),
+                                     cudaMemcpyHostToDevice, ctx->stream));
         ctx->plan_key.assign(kb, kb + sizeof key);
         ctx->plan_tiles = (int64_t)tiles.size();
+        ctx->plan_fast_ctas = (int64_t)(ftiles.size() / panfast::WARPS);
+        ctx->plan_fast_off = fast_off;
+    }
+
+    // ---- fast kernel: regular interior warp-tiles
+    if (ctx->plan_fast_ctas > 0) {
+        panfast::FastParams F;
+        memset(&F, 0, sizeof F);
+        for (int i = 0; i < d->n_ccd; ++i) {
+            if (!fast_ccd[i]) continue;
+            const oip_ccd_src &c = d->ccd[i];
+            for (int s = 0; s < c.n_seg; ++s) {
+                rc = panfast::fast_encode_tmap(&F.tmap[i * OIP_MAX_SEG + s], c.seg[s].base, d->w, c.seg[s].n_rows, c.seg[s].pitch_bytes);
+                if (rc) return rc;
+            }
+            F.ccd[i].kb = c.d_kb;
+            F.ccd[i].swap = c.fmt == OIP_FMT_BE16;
+        }
+        F.tiles = reinterpret_cast<const panfast::FastTile *>((const uint8_t *)ctx->d_plan + ctx->plan_fast_off);
+        F.out = d->d_out; F.out_pitch = d->out_pitch_px;
+        F.tab = reinterpret_cast<const float *>(ctx->d_plan);
+        F.w = d->w;
+        F.n_stage = std::max(2, std::min(8, ctx->pan_fast_stages));
+        rc = panfast::fast_launch(ctx, F, ctx->plan_fast_ctas);
+        if (rc) return rc;
     }
     if (ctx->plan_tiles == 0) return OIP_OK;
 
+    // ---- generic kernel: borders, section edges, irregular map positions, packed / tiled / unaligned inputs
     pan::Params P{};
     bool bulk_ok = d->w % 8 == 0;
     for (int i = 0; i < d->n_ccd; ++i) {

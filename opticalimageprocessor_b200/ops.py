@@ -55,6 +55,9 @@ class Context:
     def sync(self):
         check(self.lib.oip_ctx_sync(self.h))
 
+    def set_option(self, name: str, value: int):
+        check(self.lib.oip_ctx_set_option(self.h, name.encode(), int(value)))
+
     @property
     def launches(self) -> int:
         return int(self.lib.oip_ctx_launch_count(self.h))

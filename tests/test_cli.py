@@ -90,19 +90,21 @@ def test_prestitch_and_stitch_task_flow(cli, tmp_path, oracle_mod):
     src.tofile(p2)
     dx, dy = [float(v) for v in g["neg_shift"]]
     # --no-rrc: PRESTT of the raw file must equal what the reference's PreStitch wrote for this input
-    r = run(cli, ["prestitch", "--pan1", p2, "--pan2", p2, "--no-rrc", f"--dx={dx}", f"--dy={dy}"], d)
+    sec = ["-s", "2", "-l", "16000"]           # defaults (10 x 16000 lines) need a 160000-line strip, ref stitcher.h:60-77
+    r = run(cli, ["prestitch", "--pan1", p2, "--pan2", p2, "--no-rrc", f"--dx={dx}", f"--dy={dy}"] + sec, d)
     assert r.returncode == 0, r.stdout + r.stderr
     out = np.fromfile(os.path.join(d, "SYN_PAN-2.PRESTT.RAW"), np.uint16).reshape(rows, W)
     _check_prestitch(out, g, "neg")
     # missing --dx/--dy: the estimate is not in this build -> usage error 254
-    assert run(cli, ["prestitch", "--pan1", p2, "--pan2", p2], d).returncode == 254
+    assert run(cli, ["prestitch", "--pan1", p2, "--pan2", p2] + sec, d).returncode == 254
+    assert run(cli, ["prestitch", "--pan1", p2, "--pan2", p2, "--dx=1", "--dy=1"], d).returncode == 2   # too few lines for 10 x 16000
     # with RRC (default): <stem>.RRC.RAW for both and <stem>.RRC.PRESTT.RAW, first/last rows vs oracle
     kb1, kb2 = synth.rrc_coeffs(W, 1), synth.rrc_coeffs(W, 2)
     synth.write_rrc_csv(os.path.join(d, "PAN-1.csv"), kb1)
     synth.write_rrc_csv(os.path.join(d, "PAN-2.csv"), kb2)
     p1 = os.path.join(d, "SYN_PAN-1.RAW")
     src[::-1].tofile(p1)
-    r = run(cli, ["prestitch", f"--pan1={p1}", f"--pan2={p2}", "--rrc1", "PAN-1.csv", "--rrc2", "PAN-2.csv", "--dx", str(dx), "--dy", str(dy)], d)
+    r = run(cli, ["prestitch", f"--pan1={p1}", f"--pan2={p2}", "--rrc1", "PAN-1.csv", "--rrc2", "PAN-2.csv", "--dx", str(dx), "--dy", str(dy)] + sec, d)
     assert r.returncode == 0, r.stdout + r.stderr
     sl = slice(0, 64)
     rrc1 = np.fromfile(os.path.join(d, "SYN_PAN-1.RRC.RAW"), np.uint16).reshape(rows, W)

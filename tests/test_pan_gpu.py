@@ -9,6 +9,14 @@ SHIFTS = [(0.0, 0.0), (3.0, -2.0), (0.5, 0.5), (1.37, -2.61), (-1.984375, 4.0156
           (-0.83, 3.19)]
 
 
+@pytest.fixture(params=["fast", "generic"], autouse=True)
+def pan_mode(request, ctx):
+    """every test runs twice: planner splits work between pan_fast_kernel and pan_kernel / generic kernel only"""
+    ctx.set_option("pan_fast", 1 if request.param == "fast" else 0)
+    yield request.param
+    ctx.set_option("pan_fast", 1)
+
+
 def _rand_img(rng, h, w, full=True):
     hi = 65536 if full else 4096
     return rng.integers(0, hi, (h, w), dtype=np.uint16)
@@ -102,3 +110,54 @@ def test_fused_pipeline_unaligned_generic_loader(ctx, oracle_mod):
     want = oracle_mod.pan_pipeline(ccds, kbs, [0, 1.37], [0, -2.61], f)
     got = ops.pan_pipeline(ctx, [_dev(c) for c in ccds], [_dev(k) for k in kbs], [0, 1.37], [0, -2.61], f).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("case", ["negative_b", "wrap", "out_of_int32", "no_rrc"])
+def test_fused_pipeline_rrc_modes(ctx, oracle_mod, case):
+    """RRC corner cases inside the fused kernels: the fast kernel picks an exact per-warp mode (none / non-negative
+    / general), ref imageop.h:134 semantics: truncation toward zero, wrap mod 2^16, x86 cvttsd2si out of range"""
+    from opticalimageprocessor_b200 import ops
+    rng = np.random.default_rng(23)
+    n, w, f, rows = 2, 2048, 100, 300
+    ccds = [_rand_img(rng, rows, w) for _ in range(n)]
+    kbs = [_kb(rng, w) for _ in range(n)]
+    for kb in kbs:
+        if case == "negative_b":
+            kb[::7, 1] = -300.5 * rng.random(len(kb[::7]))
+            kb[3::11, 0] *= -1.0
+        elif case == "wrap":
+            kb[::5, 0] = 2.0 + rng.random(len(kb[::5]))
+        elif case == "out_of_int32":
+            kb[100:140, 1] = 4294967296.0
+            kb[900:910, 1] = -4294967296.0
+            kb[1500, 1] = np.nan
+    dX, dY = [0.0, 1.37], [0.0, -2.61]
+    use_kb = case != "no_rrc"
+    ident = np.tile(np.array([1.0, 0.0]), (w, 1))            # k*s + b == s exactly
+    want = oracle_mod.pan_pipeline(ccds, kbs if use_kb else [ident] * n, dX, dY, f)
+    got = ops.pan_pipeline(ctx, [_dev(c) for c in ccds], [_dev(k) for k in kbs] if use_kb else None, dX, dY, f).cpu().numpy()
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"{len(bad)} px differ, first {bad[:5].tolist()}"
+
+
+def test_fused_pipeline_tall_tiles_and_stage_depths(ctx, oracle_mod, pan_mode):
+    """warp-tile heights that are not multiples of the 4-row stage, every TMA stage depth"""
+    from opticalimageprocessor_b200 import ops
+    if pan_mode != "fast":
+        pytest.skip("fast-kernel tunables")
+    rng = np.random.default_rng(29)
+    n, w, f, rows = 3, 1024, 26, 613
+    ccds = [_rand_img(rng, rows, w) for _ in range(n)]
+    kbs = [_kb(rng, w) for _ in range(n)]
+    dX, dY = [0.0, 1.37, -0.83], [0.0, -2.61, 3.19]
+    want = oracle_mod.pan_pipeline(ccds, kbs, dX, dY, f)
+    try:
+        for stages, th in [(2, 16), (3, 37), (5, 128), (8, 1000)]:
+            ctx.set_option("pan_fast_stages", stages)
+            ctx.set_option("pan_fast_rows", th)
+            got = ops.pan_pipeline(ctx, [_dev(c) for c in ccds], [_dev(k) for k in kbs], dX, dY, f).cpu().numpy()
+            bad = np.argwhere(got != want)
+            assert bad.size == 0, f"stages={stages} rows={th}: {len(bad)} px differ, first {bad[:5].tolist()}"
+    finally:
+        ctx.set_option("pan_fast_stages", 4)
+        ctx.set_option("pan_fast_rows", 128)

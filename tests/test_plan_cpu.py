@@ -1,0 +1,106 @@
+"""Host-side planner of the fused PAN pipeline (no GPU): every output pixel is planned exactly once, by the
+regular-interior fast kernel or by the exact generic kernel, for the reference geometry, BASELINE configs,
+multi-section strips, multi-GPU shards with halo segments and awkward alignments."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from opticalimageprocessor_b200 import build, capi
+from opticalimageprocessor_b200.capi import PanDesc, RowSeg
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return capi.load()
+
+
+def _desc(n, w, total, f, dX, dY, S=30000, G=32767, row0=0, n_rows=None, segs=None, base=0x7F0000000000, out_pitch=None,
+          out_base=0x7E0000000000, fmt=capi.FMT_BE16):
+    d = PanDesc()
+    d.n_ccd, d.w, d.total_rows, d.row0 = n, w, total, row0
+    d.n_rows = total - row0 if n_rows is None else n_rows
+    d.fold_half, d.section_rows, d.row_guard = f, S, G
+    for i in range(n):
+        c = d.ccd[i]
+        c.fmt = fmt
+        if segs is None:
+            c.n_seg = 1
+            c.seg[0] = RowSeg(base + i * (1 << 36), 0, total, 2 * w)
+        else:
+            c.n_seg = len(segs)
+            for k, (r0, nr) in enumerate(segs):
+                c.seg[k] = RowSeg(base + i * (1 << 36) + k * (1 << 32), r0, nr, 2 * w)
+        c.d_kb = 0x7D0000000000 + i * (1 << 24)
+        c.shifted = int(i > 0)
+        c.dX, c.dY = dX[i], dY[i]
+    d.d_out = out_base
+    out_w = n * w - 2 * (n - 1) * f
+    d.out_pitch_px = out_w if out_pitch is None else out_pitch
+    return d, out_w
+
+
+def _coverage(lib, d, out_w, enable=1, rows=128):
+    cover = np.zeros((d.n_rows, d.out_pitch_px), np.uint8)
+    st = (C.c_int64 * 4)()
+    capi.check(lib.oip_pan_plan_coverage(C.byref(d), enable, rows, cover.ctypes.data_as(C.c_void_p), st))
+    return cover, list(st)
+
+
+@pytest.mark.parametrize("n,w,total,f,S,G", [(2, 12288, 2048, 100, 30000, 32767),   # reference geometry (2 CMOS, 12288 px)
+                                             (3, 8192, 1500, 100, 400, 450),         # C2 geometry, many small sections
+                                             (3, 1024, 1100, 100, 400, 450), (2, 1536, 700, 100, 30000, 32767),
+                                             (4, 256, 333, 3, 100, 120), (1, 520, 70, 0, 30000, 32767)])
+def test_every_pixel_planned_once(lib, n, w, total, f, S, G):
+    dX, dY = [0.0, 1.37, -0.83, 2.2][:n], [0.0, -2.61, 3.19, 0.4][:n]
+    d, out_w = _desc(n, w, total, f, dX, dY, S, G)
+    cover, st = _coverage(lib, d, out_w)
+    assert set(np.unique(cover[:, :out_w])) <= {1, 2}, np.unique(cover[:, :out_w], return_counts=True)
+    assert st[0] + st[1] == total * out_w
+    if w >= 512 and total >= 300:
+        assert st[1] > 0.6 * total * out_w, st          # most pixels are regular interior
+    cover0, st0 = _coverage(lib, d, out_w, enable=0)      # fast path switched off: all generic
+    assert np.all(cover0[:, :out_w] == 1) and st0[1] == 0
+
+
+def test_bench_config_is_almost_entirely_fast(lib):
+    """C2: 3 x 8192 px, 32768 lines, fold 200 -- only section edges / map-rounding rows stay generic"""
+    d, out_w = _desc(3, 8192, 32768, 100, [0, 1.37, -0.83], [0, -2.61, 3.19])
+    _, st = _coverage_stats(lib, d)
+    assert st[0] + st[1] == 32768 * out_w
+    assert st[1] > 0.995 * 32768 * out_w, st
+
+
+def _coverage_stats(lib, d, enable=1, rows=128):
+    st = (C.c_int64 * 4)()
+    capi.check(lib.oip_pan_plan_coverage(C.byref(d), enable, rows, None, st))
+    return None, list(st)
+
+
+def test_shard_with_halo_segments(lib):
+    """a middle shard of a long strip: own rows in segment 0, halo rows above / below in segments 1 and 2"""
+    total, row0, n_rows = 4096, 1024, 1024
+    d, out_w = _desc(3, 2048, total, 50, [0, 1.37, -0.83], [0, -2.61, 3.19], S=30000, G=32767, row0=row0, n_rows=n_rows,
+                     segs=[(row0, n_rows), (row0 - 16, 16), (row0 + n_rows, 16)])
+    cover, st = _coverage(lib, d, out_w)
+    assert set(np.unique(cover[:, :out_w])) <= {1, 2}
+    assert st[0] + st[1] == n_rows * out_w and st[1] > 0.9 * n_rows * out_w
+
+
+@pytest.mark.parametrize("out_pitch,out_base,base", [(None, 0x7E0000000002, 0x7F0000000000), (3 * 1024 - 4 * 25 + 3, 0x7E0000000000, 0x7F0000000000),
+                                                     (None, 0x7E0000000000, 0x7F0000000008)])
+def test_unaligned_buffers_fall_back_to_generic(lib, out_pitch, out_base, base):
+    d, out_w = _desc(3, 1024, 500, 25, [0, 1.37, -0.83], [0, -2.61, 3.19], out_pitch=out_pitch, out_base=out_base, base=base)
+    cover, st = _coverage(lib, d, out_w)
+    assert np.all(cover[:, :out_w] == 1) and st[1] == 0
+
+
+def test_odd_fold_keeps_store_alignment(lib):
+    """fold_half = 7: CCD 1 starts at an odd output column -> fast spans start at the next multiple of 4 / 8"""
+    d, out_w = _desc(3, 1024, 400, 7, [0, 1.37, -0.83], [0, -2.61, 3.19], out_pitch=3048)   # out_w = 3044: pad the pitch to 8 px
+    cover, st = _coverage(lib, d, out_w)
+    assert set(np.unique(cover[:, :out_w])) <= {1, 2} and st[1] > 0.8 * 400 * out_w
+    fast_cols = np.where((cover == 2).any(axis=0))[0]
+    runs = np.split(fast_cols, np.where(np.diff(fast_cols) > 1)[0] + 1)
+    assert all(r[0] % 4 == 0 for r in runs)
