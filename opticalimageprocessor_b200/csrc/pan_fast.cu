@@ -56,6 +56,12 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
 __device__ __forceinline__ uint2 lds64(uint32_t a)
 {
     uint2 r;
@@ -117,13 +123,41 @@ __device__ __forceinline__ void issue_stage(const WarpCtx &C, int slot, int xa, 
 }
 
 // ------------------------------------------------------------------------------------------ REMAP warp-tile
-template <int MODE>
+// The TMA unit only accepts box origins on 16-byte boundaries of the tensor row (measured: tools/tma_probe.cu,
+// any other x coordinate raises "illegal instruction"), so a box starts at the source window's column rounded
+// down to a multiple of 8 and the lanes read their 4 samples DM = (window column mod 4) halfwords into an
+// aligned 8-byte word: DM is a template parameter, the loads and PRMT selections stay fixed.
+template <int DM>
+__device__ __forceinline__ void load4(uint32_t a, uint32_t sel_lo, uint32_t sel_hi, uint32_t *s)
+{
+    const uint2 A = lds64(a);
+    if (DM == 0) {
+        s[0] = __byte_perm(A.x, 0u, sel_lo); s[1] = __byte_perm(A.x, 0u, sel_hi);
+        s[2] = __byte_perm(A.y, 0u, sel_lo); s[3] = __byte_perm(A.y, 0u, sel_hi);
+    } else if (DM == 1) {
+        const uint32_t B = lds32(a + 8);
+        s[0] = __byte_perm(A.x, 0u, sel_hi); s[1] = __byte_perm(A.y, 0u, sel_lo);
+        s[2] = __byte_perm(A.y, 0u, sel_hi); s[3] = __byte_perm(B, 0u, sel_lo);
+    } else if (DM == 2) {
+        const uint32_t B = lds32(a + 8);
+        s[0] = __byte_perm(A.y, 0u, sel_lo); s[1] = __byte_perm(A.y, 0u, sel_hi);
+        s[2] = __byte_perm(B, 0u, sel_lo); s[3] = __byte_perm(B, 0u, sel_hi);
+    } else {
+        const uint2 B = lds64(a + 8);
+        s[0] = __byte_perm(A.y, 0u, sel_hi); s[1] = __byte_perm(B.x, 0u, sel_lo);
+        s[2] = __byte_perm(B.x, 0u, sel_hi); s[3] = __byte_perm(B.y, 0u, sel_lo);
+    }
+}
+
+template <int MODE, int DM>
 __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                            const double (&b)[8])
 {
     const int lane = C.lane, ns = C.ns;
     const int n_chunks = (T.n_rows + 3 + RC - 1) / RC;
-    const int xa = T.src_x0, xb = T.src_x0 + T.half;
+    const int xa = T.src_x0 & ~7, xb = (T.src_x0 + T.half) & ~7; // box origins; window column 0 sits (src_x0 & 7) samples in
+    const uint32_t offL = 8u * (uint32_t)(((T.src_x0 & 7) >> 2) + lane);
+    const uint32_t offR = BOX_STRIDE + 8u * (uint32_t)((((T.src_x0 + T.half) & 7) >> 2) + lane);
     if (lane == 0) {
         const int pre = min(ns, n_chunks);
         for (int c = 0; c < pre; ++c) issue_stage(C, c, xa, xb, T.src_y0 + c * RC);
@@ -150,15 +184,12 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
     uint32_t phase = 0;
     for (int c = 0; c < n_chunks; ++c) {
         mbar_wait_u32(C.bar0 + 8u * slot, phase);
-        const uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES + 8u * lane;
+        const uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES;
         // AN: new accumulator (weight row 0), A1..A3: rows that receive weight rows 1..3; A3 completes here
         auto row = [&](int rr, f2(&AN)[4], f2(&A1)[4], f2(&A2)[4], f2(&A3)[4]) {
-            const uint2 l = lds64(sa + rr * ROW_BYTES), r = lds64(sa + BOX_STRIDE + rr * ROW_BYTES);
             uint32_t s[8];
-            s[0] = __byte_perm(l.x, 0u, C.sel_lo); s[1] = __byte_perm(l.x, 0u, C.sel_hi);
-            s[2] = __byte_perm(l.y, 0u, C.sel_lo); s[3] = __byte_perm(l.y, 0u, C.sel_hi);
-            s[4] = __byte_perm(r.x, 0u, C.sel_lo); s[5] = __byte_perm(r.x, 0u, C.sel_hi);
-            s[6] = __byte_perm(r.y, 0u, C.sel_lo); s[7] = __byte_perm(r.y, 0u, C.sel_hi);
+            load4<DM>(sa + offL + rr * ROW_BYTES, C.sel_lo, C.sel_hi, s);
+            load4<DM>(sa + offR + rr * ROW_BYTES, C.sel_lo, C.sel_hi, s + 4);
             f2 win[7];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -288,9 +319,18 @@ __global__ void __launch_bounds__(WARPS * 32, 4) pan_fast_kernel(const __grid_co
     }
     const int mode = kbp ? (__any_sync(0xffffffffu, general) ? 2 : 1) : 0;
     if (T.kind == FT_REMAP) {
-        if (mode == 1) remap_tile<1>(P, T, C, k, b);
-        else if (mode == 0) remap_tile<0>(P, T, C, k, b);
-        else remap_tile<2>(P, T, C, k, b);
+        const int dm = T.src_x0 & 3;
+#define OIP_REMAP_DM(M)                                           \
+    do {                                                          \
+        if (dm == 0) remap_tile<M, 0>(P, T, C, k, b);             \
+        else if (dm == 1) remap_tile<M, 1>(P, T, C, k, b);        \
+        else if (dm == 2) remap_tile<M, 2>(P, T, C, k, b);        \
+        else remap_tile<M, 3>(P, T, C, k, b);                     \
+    } while (0)
+        if (mode == 1) OIP_REMAP_DM(1);
+        else if (mode == 0) OIP_REMAP_DM(0);
+        else OIP_REMAP_DM(2);
+#undef OIP_REMAP_DM
     } else {
         if (mode == 1) copy_tile<1>(P, T, C, k, b);
         else if (mode == 0) copy_tile<0>(P, T, C, k, b);

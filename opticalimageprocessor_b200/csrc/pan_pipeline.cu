@@ -724,9 +724,10 @@ static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows
         const bool shifted = C.shifted != 0, fast = fast_ccd[i];
         if (!shifted) {
             const ShiftSegment s{0, d->total_rows, 0, 0, 0, -1, 0};
-            // COPY: 128-bit stores need the output column to be a multiple of 8
-            const int xs = lo + ((8 - (out_x % 8)) % 8);
-            const int usable = fast && xs < hi ? ((hi - xs) & ~7) : 0;
+            // COPY: TMA box origins need source columns that are multiples of 8 (16 bytes), the 128-bit stores need
+            // the same of the output column
+            const int xs = (lo + 7) & ~7;
+            const int usable = fast && xs < hi && (out_x + xs - lo) % 8 == 0 ? ((hi - xs) & ~7) : 0;
             int64_t cur = r_lo;
             if (usable >= 8) {
                 const ColSpan cs{xs, xs + usable, 0};
