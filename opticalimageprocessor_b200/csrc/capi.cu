@@ -111,6 +111,9 @@ void oip_ctx_destroy(oip_ctx *ctx)
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_err) cudaFree(ctx->d_err);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -120,6 +123,7 @@ int oip_ctx_set_option(oip_ctx *ctx, const char *name, int64_t value)
     if (!ctx || !name) return oip::fail(OIP_E_INVALID, "oip_ctx_set_option: null argument");
     if (!strcmp(name, "pan_fast")) ctx->pan_fast = value != 0;
     else if (!strcmp(name, "pan_fast_stages") && value >= 2 && value <= 8) ctx->pan_fast_stages = (int)value;
+    else if (!strcmp(name, "pan_fast_minb") && value >= 3 && value <= 4) ctx->pan_fast_minb = (int)value;
     else if (!strcmp(name, "pan_fast_rows") && value >= 16 && value <= 32768) ctx->pan_fast_rows = (int)value;
     else return oip::fail(OIP_E_INVALID, "unknown option or value out of range: %s=%lld", name, (long long)value);
     ctx->plan_key.clear();

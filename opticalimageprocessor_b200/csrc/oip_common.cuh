@@ -27,6 +27,7 @@ struct oip_ctx {
     int pan_fast = 1;            // 0: everything on the generic kernel
     int pan_fast_stages = 4;     // TMA stages per warp
     int pan_fast_rows = 128;     // output rows per warp-tile
+    int pan_fast_minb = 4;       // register-allocation variant of pan_fast_kernel (CTAs per SM: 2, 3, 4)
     void *d_mss_plan = nullptr;
     size_t d_mss_plan_cap = 0;
     std::vector<uint8_t> mss_plan_key;
@@ -38,6 +39,8 @@ struct oip_ctx {
     void *h_pinned = nullptr; // small pinned staging for counters / plans
     size_t h_pinned_cap = 0;
     int *d_err = nullptr;     // device-side error flag
+    cudaStream_t aux_stream = nullptr; // side stream of oip_pan_pipeline (generic tiles next to the fast kernel)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool pan_attr_set = false, mss_attr_set = false, fast_attr_set = false;
     // host-buffer pipeline (oip_pan_pipeline_host): staging slots + side streams
     void *host_pipe = nullptr;

@@ -23,12 +23,11 @@
 namespace oip {
 namespace panfast {
 
-constexpr int ROW_BYTES = BOX_W * 2;                          // 272
-constexpr int BOX_BYTES = ROW_BYTES * RC;                     // 1088
-constexpr int BOX_STRIDE = (BOX_BYTES + 127) / 128 * 128;     // 1152: TMA destinations are 128-byte aligned
-constexpr int STAGE_BYTES = 2 * BOX_STRIDE;                   // two boxes per stage
+constexpr int ROW_BYTES = BOX_W * 4;                          // 544: a box row is BOX_W 32-bit elements = 272 samples
+constexpr int STAGE_BYTES = ROW_BYTES * RC;                   // 2176 = 17 x 128: TMA destinations are 128-byte aligned
 constexpr int MAX_STAGE = 8;
 static_assert(RC == 4, "the row loop is unrolled by the 4-deep accumulator rotation");
+static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int x, int y, uint32_t bar)
 {
@@ -85,6 +84,7 @@ __device__ __forceinline__ uint32_t cast_u16(float s)
     asm("cvt.rni.u16.f32 %0, %1;" : "=h"(r) : "f"(s));
     return r;
 }
+__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5410); }
 __device__ __forceinline__ f2 shfl_down1(f2 v)
 {
     uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
@@ -93,74 +93,95 @@ __device__ __forceinline__ f2 shfl_down1(f2 v)
     return ((f2)hi << 32) | lo;
 }
 
-// RRC modes: 0 = none (stitch only), 1 = every (k,b) of the warp is >= 0 and k*65535+b < 2^31 (exact with two
-// magic adds, no range test per pixel), 2 = general (sign / range handling exactly like x86 cvttsd2si)
-template <int MODE>
-__device__ __forceinline__ uint32_t rrc_mode(uint32_t s, double k, double b)
+// On B200 the integer/logic instructions (PRMT, LOP3, MOV, IADD3 ...) take their cycles from the same datapath
+// as the FP32 instructions (tools/mix_rates.cu: FFMA2 + LOP3 times add up, FFMA2 + DADD overlap), and the FP32
+// datapath is what bounds this kernel.  So a 32-bit word of two samples is turned into two exact doubles on the
+// conversion and FP64 pipes alone: I2F.F64.U32, then hi = RZ(x*2^-16 + 2^52) - 2^52, lo = x - 65536*hi.
+struct D2 { double lo, hi; };
+__device__ __forceinline__ D2 split_word(uint32_t w)
 {
-    if (MODE == 0) return s;
-    if (MODE == 1) {
-        const double sd = __dadd_rn(__hiloint2double(0x43300000, (int)s), -4503599627370496.0);
-        const double v = __dadd_rn(__dmul_rn(k, sd), b);
-        return (uint32_t)__double2loint(__dadd_rz(v, 4503599627370496.0)); // low 16 bits are taken by the caller
+    const double x = __uint2double_rn(w);
+    D2 r;
+    r.hi = __dadd_rn(__fma_rz(x, 1.52587890625e-05, 4503599627370496.0), -4503599627370496.0);
+    r.lo = __fma_rn(r.hi, -65536.0, x);
+    return r;
+}
+// RRC of an exact sample value.  MODE 1: every (k,b) of the warp is >= 0 and k*65535+b < 2^31: truncation is the
+// low word of RZ(v + 2^52).  MODE 2: general (sign / range handling exactly like x86 cvttsd2si).  The low 16
+// bits of the result are taken by the consumer (I2F.U16 / PRMT).
+template <int MODE>
+__device__ __forceinline__ uint32_t rrc_d(double sd, double k, double b)
+{
+    const double v = __dadd_rn(__dmul_rn(k, sd), b);
+    if (MODE == 1) return (uint32_t)__double2loint(__dadd_rz(v, 4503599627370496.0));
+    const uint32_t hi = (uint32_t)__double2hiint(v);
+    if (hi < 0x41E00000u) return (uint32_t)__double2loint(__dadd_rz(v, 4503599627370496.0));
+    return (uint32_t)((v > -2147483649.0 && v < 2147483648.0) ? __double2int_rz(v) : (int)0x80000000);
+}
+
+// 4 consecutive samples that start DM halfwords into the aligned 8-byte shared-memory word at `a`, as floats
+// (after byte swap and RRC).  The TMA unit only accepts box origins on 16-byte boundaries of a tensor row
+// (measured, tools/tma_probe.cu: any other coordinate raises "illegal instruction"), so the source window starts
+// (src_x0 & 7) samples into the box; DM = that offset mod 4 is a template parameter.
+template <int MODE, int DM, bool SWAP>
+__device__ __forceinline__ void convert4(uint32_t a, const double *k, const double *b, float *f)
+{
+    constexpr int NW = (DM & 1) ? 3 : 2;
+    uint32_t w[3] = {0u, 0u, 0u};
+    if (DM == 0) { const uint2 A = lds64(a); w[0] = A.x; w[1] = A.y; }
+    else if (DM == 1) { const uint2 A = lds64(a); w[0] = A.x; w[1] = A.y; w[2] = lds32(a + 8); }
+    else if (DM == 2) { w[0] = lds32(a + 4); w[1] = lds32(a + 8); }
+    else { w[0] = lds32(a + 4); const uint2 B = lds64(a + 8); w[1] = B.x; w[2] = B.y; }
+    if (SWAP) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = __byte_perm(w[i], 0u, 0x2301);
     }
-    return rrc_px(s, k, b);
+    if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int h = j + (DM & 1);
+            f[j] = (h & 1) ? (float)(uint16_t)(w[h >> 1] >> 16) : (float)(uint16_t)(w[h >> 1] & 0xFFFFu);
+        }
+    } else {
+        D2 d[3];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) d[i] = split_word(w[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int h = j + (DM & 1);
+            const double sd = (h & 1) ? d[h >> 1].hi : d[h >> 1].lo;
+            f[j] = (float)(uint16_t)rrc_d<MODE>(sd, k[j], b[j]);
+        }
+    }
 }
 
 struct WarpCtx {
     const CUtensorMap *tm;
     uint32_t stage0, bar0; // shared-memory addresses of this warp's stage ring and barriers
     int ns, lane;
-    uint32_t sel_lo, sel_hi; // PRMT selectors: halfword -> zero-extended (byte-swapped) sample
 };
 
-__device__ __forceinline__ void issue_stage(const WarpCtx &C, int slot, int xa, int xb, int y)
+// x: first sample of the box (multiple of 8); the tensor map counts 32-bit elements
+__device__ __forceinline__ void issue_stage(const WarpCtx &C, int slot, int x, int y)
 {
     const uint32_t bar = C.bar0 + 8u * slot, dst = C.stage0 + (uint32_t)slot * STAGE_BYTES;
-    mbar_expect_tx_u32(bar, 2 * BOX_BYTES);
-    tma_load_2d(dst, C.tm, xa, y, bar);
-    tma_load_2d(dst + BOX_STRIDE, C.tm, xb, y, bar);
+    mbar_expect_tx_u32(bar, STAGE_BYTES);
+    tma_load_2d(dst, C.tm, x >> 1, y, bar);
 }
 
 // ------------------------------------------------------------------------------------------ REMAP warp-tile
-// The TMA unit only accepts box origins on 16-byte boundaries of the tensor row (measured: tools/tma_probe.cu,
-// any other x coordinate raises "illegal instruction"), so a box starts at the source window's column rounded
-// down to a multiple of 8 and the lanes read their 4 samples DM = (window column mod 4) halfwords into an
-// aligned 8-byte word: DM is a template parameter, the loads and PRMT selections stay fixed.
-template <int DM>
-__device__ __forceinline__ void load4(uint32_t a, uint32_t sel_lo, uint32_t sel_hi, uint32_t *s)
-{
-    const uint2 A = lds64(a);
-    if (DM == 0) {
-        s[0] = __byte_perm(A.x, 0u, sel_lo); s[1] = __byte_perm(A.x, 0u, sel_hi);
-        s[2] = __byte_perm(A.y, 0u, sel_lo); s[3] = __byte_perm(A.y, 0u, sel_hi);
-    } else if (DM == 1) {
-        const uint32_t B = lds32(a + 8);
-        s[0] = __byte_perm(A.x, 0u, sel_hi); s[1] = __byte_perm(A.y, 0u, sel_lo);
-        s[2] = __byte_perm(A.y, 0u, sel_hi); s[3] = __byte_perm(B, 0u, sel_lo);
-    } else if (DM == 2) {
-        const uint32_t B = lds32(a + 8);
-        s[0] = __byte_perm(A.y, 0u, sel_lo); s[1] = __byte_perm(A.y, 0u, sel_hi);
-        s[2] = __byte_perm(B, 0u, sel_lo); s[3] = __byte_perm(B, 0u, sel_hi);
-    } else {
-        const uint2 B = lds64(a + 8);
-        s[0] = __byte_perm(A.y, 0u, sel_hi); s[1] = __byte_perm(B.x, 0u, sel_lo);
-        s[2] = __byte_perm(B.x, 0u, sel_hi); s[3] = __byte_perm(B.y, 0u, sel_lo);
-    }
-}
-
-template <int MODE, int DM>
+template <int MODE, int DM, bool SWAP>
 __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                            const double (&b)[8])
 {
     const int lane = C.lane, ns = C.ns;
     const int n_chunks = (T.n_rows + 3 + RC - 1) / RC;
-    const int xa = T.src_x0 & ~7, xb = (T.src_x0 + T.half) & ~7; // box origins; window column 0 sits (src_x0 & 7) samples in
-    const uint32_t offL = 8u * (uint32_t)(((T.src_x0 & 7) >> 2) + lane);
-    const uint32_t offR = BOX_STRIDE + 8u * (uint32_t)((((T.src_x0 + T.half) & 7) >> 2) + lane);
+    const int x0 = T.src_x0 & ~7; // box origin; window column 0 sits (src_x0 & 7) samples in
+    const uint32_t offL = 2u * (uint32_t)((T.src_x0 - x0) & ~3) + 8u * (uint32_t)lane;
+    const uint32_t offR = 2u * (uint32_t)((T.src_x0 - x0 + T.half) & ~3) + 8u * (uint32_t)lane;
     if (lane == 0) {
         const int pre = min(ns, n_chunks);
-        for (int c = 0; c < pre; ++c) issue_stage(C, c, xa, xb, T.src_y0 + c * RC);
+        for (int c = 0; c < pre; ++c) issue_stage(C, c, x0, T.src_y0 + c * RC);
     }
     // 2-D weights w[r][c] = fl32(wy[r] * wx[c]), identical for the whole tile
     const f2 nz = *reinterpret_cast<const f2 *>(P.tab + 128);
@@ -187,16 +208,12 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
         const uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES;
         // AN: new accumulator (weight row 0), A1..A3: rows that receive weight rows 1..3; A3 completes here
         auto row = [&](int rr, f2(&AN)[4], f2(&A1)[4], f2(&A2)[4], f2(&A3)[4]) {
-            uint32_t s[8];
-            load4<DM>(sa + offL + rr * ROW_BYTES, C.sel_lo, C.sel_hi, s);
-            load4<DM>(sa + offR + rr * ROW_BYTES, C.sel_lo, C.sel_hi, s + 4);
+            float fl[4], fr[4];
+            convert4<MODE, DM, SWAP>(sa + offL + rr * ROW_BYTES, k, b, fl);
+            convert4<MODE, DM, SWAP>(sa + offR + rr * ROW_BYTES, k + 4, b + 4, fr);
             f2 win[7];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float fl = (float)(uint16_t)rrc_mode<MODE>(s[j], k[j], b[j]);
-                const float fr = (float)(uint16_t)rrc_mode<MODE>(s[4 + j], k[4 + j], b[4 + j]);
-                win[j] = pk(fl, fr);
-            }
+            for (int j = 0; j < 4; ++j) win[j] = pk(fl[j], fr[j]);
 #pragma unroll
             for (int j = 0; j < 3; ++j) win[4 + j] = shfl_down1(win[j]);
             f2 out[4];
@@ -214,10 +231,10 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
             }
             const int m = c * RC + rr;
             if (active && (unsigned)(m - 3) < (unsigned)n_rows) {
-                stg_v2(oL, cast_u16(lo_of(out[0])) | (cast_u16(lo_of(out[1])) << 16),
-                       cast_u16(lo_of(out[2])) | (cast_u16(lo_of(out[3])) << 16));
-                stg_v2(oL + half, cast_u16(hi_of(out[0])) | (cast_u16(hi_of(out[1])) << 16),
-                       cast_u16(hi_of(out[2])) | (cast_u16(hi_of(out[3])) << 16));
+                stg_v2(oL, pack16(cast_u16(lo_of(out[0])), cast_u16(lo_of(out[1]))),
+                       pack16(cast_u16(lo_of(out[2])), cast_u16(lo_of(out[3]))));
+                stg_v2(oL + half, pack16(cast_u16(hi_of(out[0])), cast_u16(hi_of(out[1]))),
+                       pack16(cast_u16(hi_of(out[2])), cast_u16(hi_of(out[3]))));
             }
             oL += pitch;
         };
@@ -226,58 +243,82 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
         row(2, B2, B3, B0, B1);
         row(3, B1, B2, B3, B0);
         __syncwarp();
-        if (lane == 0 && c + ns < n_chunks) issue_stage(C, slot, xa, xb, T.src_y0 + (c + ns) * RC);
+        if (lane == 0 && c + ns < n_chunks) issue_stage(C, slot, x0, T.src_y0 + (c + ns) * RC);
         if (++slot == ns) { slot = 0; phase ^= 1u; }
     }
 }
 
 // ------------------------------------------------------------------------------------------- COPY warp-tile
-template <int MODE>
+template <int MODE, bool SWAP>
 __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                           const double (&b)[8])
 {
     const int lane = C.lane, ns = C.ns;
     const int n_rows = T.n_rows;
     const int n_chunks = (n_rows + RC - 1) / RC;
-    const int xa = T.x_begin, xb = T.x_begin + 128;
     if (lane == 0) {
         const int pre = min(ns, n_chunks);
-        for (int c = 0; c < pre; ++c) issue_stage(C, c, xa, xb, T.src_y0 + c * RC);
+        for (int c = 0; c < pre; ++c) issue_stage(C, c, T.x_begin, T.src_y0 + c * RC);
     }
     const bool active = 8 * lane < T.half;
     const int64_t pitch = P.out_pitch;
     uint16_t *o = P.out + T.out_off + 8 * lane;
-    const uint32_t my = (uint32_t)(lane >> 4) * BOX_STRIDE + (uint32_t)(lane & 15) * 16u;
     int slot = 0;
     uint32_t phase = 0;
     for (int c = 0; c < n_chunks; ++c) {
         mbar_wait_u32(C.bar0 + 8u * slot, phase);
-        const uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES + my;
+        const uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES + 16u * (uint32_t)lane;
 #pragma unroll
         for (int rr = 0; rr < RC; ++rr) {
             const uint4 v = lds128(sa + rr * ROW_BYTES);
-            const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-            uint32_t t[8];
+            uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+            if (SWAP) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                t[j] = rrc_mode<MODE>(__byte_perm(wd[j >> 1], 0u, (j & 1) ? C.sel_hi : C.sel_lo), k[j], b[j]);
-            if (active && c * RC + rr < n_rows) {
-                uint4 w;
-                w.x = __byte_perm(t[0], t[1], 0x5410);
-                w.y = __byte_perm(t[2], t[3], 0x5410);
-                w.z = __byte_perm(t[4], t[5], 0x5410);
-                w.w = __byte_perm(t[6], t[7], 0x5410);
-                stg_na_v4(o, w);
+                for (int i = 0; i < 4; ++i) wd[i] = __byte_perm(wd[i], 0u, 0x2301);
             }
+            if (MODE != 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const D2 d = split_word(wd[i]);
+                    wd[i] = pack16(rrc_d<MODE>(d.lo, k[2 * i], b[2 * i]), rrc_d<MODE>(d.hi, k[2 * i + 1], b[2 * i + 1]));
+                }
+            }
+            if (active && c * RC + rr < n_rows) stg_na_v4(o, make_uint4(wd[0], wd[1], wd[2], wd[3]));
             o += pitch;
         }
         __syncwarp();
-        if (lane == 0 && c + ns < n_chunks) issue_stage(C, slot, xa, xb, T.src_y0 + (c + ns) * RC);
+        if (lane == 0 && c + ns < n_chunks) issue_stage(C, slot, T.x_begin, T.src_y0 + (c + ns) * RC);
         if (++slot == ns) { slot = 0; phase ^= 1u; }
     }
 }
 
-__global__ void __launch_bounds__(WARPS * 32, 4) pan_fast_kernel(const __grid_constant__ FastParams P)
+template <int MODE, bool SWAP>
+__device__ __forceinline__ void remap_dispatch(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
+                                               const double (&b)[8])
+{
+    const int dm = T.src_x0 & 3;
+    if (dm == 0) remap_tile<MODE, 0, SWAP>(P, T, C, k, b);
+    else if (dm == 1) remap_tile<MODE, 1, SWAP>(P, T, C, k, b);
+    else if (dm == 2) remap_tile<MODE, 2, SWAP>(P, T, C, k, b);
+    else remap_tile<MODE, 3, SWAP>(P, T, C, k, b);
+}
+
+template <int MODE>
+__device__ __forceinline__ void tile_dispatch(const FastParams &P, const FastTile &T, const WarpCtx &C, bool swap, const double (&k)[8],
+                                              const double (&b)[8])
+{
+    if (T.kind == FT_REMAP) {
+        if (swap) remap_dispatch<MODE, true>(P, T, C, k, b);
+        else remap_dispatch<MODE, false>(P, T, C, k, b);
+    } else {
+        if (swap) copy_tile<MODE, true>(P, T, C, k, b);
+        else copy_tile<MODE, false>(P, T, C, k, b);
+    }
+}
+
+// MINB = CTAs per SM the register allocation must allow (4: 128 registers, 3: 168)
+template <int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) pan_fast_kernel(const __grid_constant__ FastParams P)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[WARPS][MAX_STAGE];
@@ -291,9 +332,6 @@ __global__ void __launch_bounds__(WARPS * 32, 4) pan_fast_kernel(const __grid_co
     C.tm = &P.tmap[T.tmap];
     C.stage0 = ((smem_u32(smem_raw) + 127u) & ~127u) + (uint32_t)(warp * C.ns) * STAGE_BYTES;
     C.bar0 = smem_u32(&bars[warp][0]);
-    const bool swap = P.ccd[T.ccd].swap != 0;
-    C.sel_lo = swap ? 0x4401u : 0x4410u;
-    C.sel_hi = swap ? 0x4423u : 0x4432u;
     if (lane == 0) {
         for (int s = 0; s < C.ns; ++s) mbar_init_u32(C.bar0 + 8u * s, 1);
         fence_mbar_init();
@@ -317,25 +355,11 @@ __global__ void __launch_bounds__(WARPS * 32, 4) pan_fast_kernel(const __grid_co
             general = general || !(v.x >= 0.0 && v.y >= 0.0 && __dadd_rn(__dmul_rn(v.x, 65535.0), v.y) < 2147483648.0);
         }
     }
+    const bool swap = P.ccd[T.ccd].swap != 0;
     const int mode = kbp ? (__any_sync(0xffffffffu, general) ? 2 : 1) : 0;
-    if (T.kind == FT_REMAP) {
-        const int dm = T.src_x0 & 3;
-#define OIP_REMAP_DM(M)                                           \
-    do {                                                          \
-        if (dm == 0) remap_tile<M, 0>(P, T, C, k, b);             \
-        else if (dm == 1) remap_tile<M, 1>(P, T, C, k, b);        \
-        else if (dm == 2) remap_tile<M, 2>(P, T, C, k, b);        \
-        else remap_tile<M, 3>(P, T, C, k, b);                     \
-    } while (0)
-        if (mode == 1) OIP_REMAP_DM(1);
-        else if (mode == 0) OIP_REMAP_DM(0);
-        else OIP_REMAP_DM(2);
-#undef OIP_REMAP_DM
-    } else {
-        if (mode == 1) copy_tile<1>(P, T, C, k, b);
-        else if (mode == 0) copy_tile<0>(P, T, C, k, b);
-        else copy_tile<2>(P, T, C, k, b);
-    }
+    if (mode == 1) tile_dispatch<1>(P, T, C, swap, k, b);
+    else if (mode == 0) tile_dispatch<0>(P, T, C, swap, k, b);
+    else tile_dispatch<2>(P, T, C, swap, k, b);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -360,11 +384,11 @@ int fast_encode_tmap(CUtensorMap *tm, const void *base, int w, int64_t n_rows, i
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(OIP_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)n_rows};
+    const cuuint64_t dims[2] = {(cuuint64_t)(w / 2), (cuuint64_t)n_rows}; // 32-bit elements = sample pairs
     const cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
     const cuuint32_t box[2] = {BOX_W, RC};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(OIP_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -375,11 +399,12 @@ int fast_launch(oip_ctx *ctx, const FastParams &P, int64_t n_ctas)
 {
     const size_t smem = (size_t)WARPS * P.n_stage * STAGE_BYTES + 128;
     if (!ctx->fast_attr_set) {
-        OIP_CUDA(cudaFuncSetAttribute(pan_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      WARPS * MAX_STAGE * STAGE_BYTES + 128));
+        OIP_CUDA(cudaFuncSetAttribute(pan_fast_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPS * MAX_STAGE * STAGE_BYTES + 128));
+        OIP_CUDA(cudaFuncSetAttribute(pan_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPS * MAX_STAGE * STAGE_BYTES + 128));
         ctx->fast_attr_set = true;
     }
-    pan_fast_kernel<<<(unsigned)n_ctas, WARPS * 32, smem, ctx->stream>>>(P);
+    if (ctx->pan_fast_minb == 3) pan_fast_kernel<3><<<(unsigned)n_ctas, WARPS * 32, smem, ctx->stream>>>(P);
+    else pan_fast_kernel<4><<<(unsigned)n_ctas, WARPS * 32, smem, ctx->stream>>>(P);
     OIP_CUDA(cudaGetLastError());
     ctx->launches++;
     return OIP_OK;

@@ -9,7 +9,7 @@ namespace panfast {
 
 constexpr int WARPS = 4;        // independent warp workers per CTA (one warp-tile each)
 constexpr int RC = 4;           // source rows per TMA stage
-constexpr int BOX_W = 136;      // u16 per box row (272 B = 17 x 16 B); two boxes per stage
+constexpr int BOX_W = 136;      // 32-bit elements (sample pairs) per box row: one box of 272 samples x RC rows per stage
 constexpr int HALF_MAX = 124;   // REMAP: output columns per half (31 lanes x 4); window = half + 3 (+1 slack) columns
 constexpr int COPY_MAX = 256;   // COPY: output columns per warp-tile (32 lanes x 8)
 constexpr int MAX_MAPS = 8 * OIP_MAX_SEG;

@@ -630,8 +630,11 @@ static void emit_generic(std::vector<Tile> &tiles, int i, bool shifted, const Sh
                          int out_x_lo, int64_t g_lo, int64_t g_hi)
 {
     if (x_hi <= x_lo || g_hi <= g_lo) return;
-    for (int64_t g = g_lo; g < g_hi; g += TH) {
-        const int nr = (int)std::min<int64_t>(TH, g_hi - g);
+    // a CTA marches down its tile 32 rows at a time: slivers (leftover columns next to the fast spans) get short
+    // tiles so that the launch is many short CTAs instead of a few that run as long as a full-width tile
+    const int th = x_hi - x_lo < 16 ? 32 : (x_hi - x_lo < 64 ? 128 : TH);
+    for (int64_t g = g_lo; g < g_hi; g += th) {
+        const int nr = (int)std::min<int64_t>(th, g_hi - g);
         // column strips of equal width (no skinny last strip); even for the 32-bit paired stores of REMAP
         // tiles, multiple of 8 for the 128-bit stores of COPY tiles
         const int n_strips = (x_hi - x_lo + TW - 1) / TW;
@@ -1018,6 +1021,51 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         ctx->plan_fast_off = fast_off;
     }
 
+    // the two kernels write disjoint pixels: the (small) generic launch runs on a side stream next to the fast one
+    const bool fork = ctx->plan_fast_ctas > 0 && ctx->plan_tiles > 0;
+    if (fork) {
+        if (!ctx->aux_stream) {
+            OIP_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+            OIP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            OIP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        OIP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        OIP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    }
+    cudaStream_t gstream = fork ? ctx->aux_stream : ctx->stream;
+
+    if (ctx->plan_tiles > 0) {
+        // ---- generic kernel: borders, section edges, irregular map positions, packed / tiled / unaligned inputs
+        pan::Params P{};
+        bool bulk_ok = d->w % 8 == 0;
+        for (int i = 0; i < d->n_ccd; ++i) {
+            const oip_ccd_src &c = d->ccd[i];
+            pan::CcdDev &o = P.ccd[i];
+            o.fmt = c.fmt; o.n_seg = c.n_seg; o.kb = c.d_kb; o.dX = c.dX; o.dY = c.dY;
+            o.tile_off = c.d_tile_off; o.tile_cols = c.tile_cols; o.tile_lines = c.tile_lines;
+            if (c.fmt != OIP_FMT_LE16 && c.fmt != OIP_FMT_BE16) bulk_ok = false;
+            for (int s = 0; s < c.n_seg; ++s) {
+                if (!c.seg[s].base) return fail(OIP_E_INVALID, "ccd %d segment %d: null base", i, s);
+                o.seg[s].base = (const uint8_t *)c.seg[s].base;
+                o.seg[s].row0 = c.seg[s].row0; o.seg[s].n_rows = c.seg[s].n_rows; o.seg[s].pitch = c.seg[s].pitch_bytes;
+                if (((uintptr_t)c.seg[s].base & 15) || (c.seg[s].pitch_bytes & 15)) bulk_ok = false;
+            }
+        }
+        P.tab = reinterpret_cast<const float *>(ctx->d_plan);
+        P.tiles = reinterpret_cast<const pan::Tile *>((const uint8_t *)ctx->d_plan + 1024);
+        P.out = d->d_out; P.out_pitch = d->out_pitch_px; P.out_row0 = d->row0;
+        P.err = ctx->d_err; P.w = d->w; P.n_ccd = d->n_ccd; P.bulk_ok = bulk_ok ? 1 : 0;
+
+        const size_t smem = (size_t)pan::RING_ROWS * pan::SLOTS * 8 + 2 * (size_t)pan::STG * pan::SWC * 2;
+        if (!ctx->pan_attr_set) {
+            OIP_CUDA(cudaFuncSetAttribute(pan::pan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->pan_attr_set = true;
+        }
+        pan::pan_kernel<<<(unsigned)ctx->plan_tiles, pan::NT, smem, gstream>>>(P);
+        OIP_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+
     // ---- fast kernel: regular interior warp-tiles
     if (ctx->plan_fast_ctas > 0) {
         panfast::FastParams F;
@@ -1040,37 +1088,10 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         rc = panfast::fast_launch(ctx, F, ctx->plan_fast_ctas);
         if (rc) return rc;
     }
-    if (ctx->plan_tiles == 0) return OIP_OK;
-
-    // ---- generic kernel: borders, section edges, irregular map positions, packed / tiled / unaligned inputs
-    pan::Params P{};
-    bool bulk_ok = d->w % 8 == 0;
-    for (int i = 0; i < d->n_ccd; ++i) {
-        const oip_ccd_src &c = d->ccd[i];
-        pan::CcdDev &o = P.ccd[i];
-        o.fmt = c.fmt; o.n_seg = c.n_seg; o.kb = c.d_kb; o.dX = c.dX; o.dY = c.dY;
-        o.tile_off = c.d_tile_off; o.tile_cols = c.tile_cols; o.tile_lines = c.tile_lines;
-        if (c.fmt != OIP_FMT_LE16 && c.fmt != OIP_FMT_BE16) bulk_ok = false;
-        for (int s = 0; s < c.n_seg; ++s) {
-            if (!c.seg[s].base) return fail(OIP_E_INVALID, "ccd %d segment %d: null base", i, s);
-            o.seg[s].base = (const uint8_t *)c.seg[s].base;
-            o.seg[s].row0 = c.seg[s].row0; o.seg[s].n_rows = c.seg[s].n_rows; o.seg[s].pitch = c.seg[s].pitch_bytes;
-            if (((uintptr_t)c.seg[s].base & 15) || (c.seg[s].pitch_bytes & 15)) bulk_ok = false;
-        }
+    if (fork) {
+        OIP_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+        OIP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
-    P.tab = reinterpret_cast<const float *>(ctx->d_plan);
-    P.tiles = reinterpret_cast<const pan::Tile *>((const uint8_t *)ctx->d_plan + 1024);
-    P.out = d->d_out; P.out_pitch = d->out_pitch_px; P.out_row0 = d->row0;
-    P.err = ctx->d_err; P.w = d->w; P.n_ccd = d->n_ccd; P.bulk_ok = bulk_ok ? 1 : 0;
-
-    const size_t smem = (size_t)pan::RING_ROWS * pan::SLOTS * 8 + 2 * (size_t)pan::STG * pan::SWC * 2;
-    if (!ctx->pan_attr_set) {
-        OIP_CUDA(cudaFuncSetAttribute(pan::pan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->pan_attr_set = true;
-    }
-    pan::pan_kernel<<<(unsigned)ctx->plan_tiles, pan::NT, smem, ctx->stream>>>(P);
-    OIP_CUDA(cudaGetLastError());
-    ctx->launches++;
     return OIP_OK;
 }
 
