@@ -104,7 +104,7 @@ def load() -> C.CDLL:
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -m opticalimageprocessor_b200.build` "
                 "(there is no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(os.environ.get("OIP_B200_LIB", LIB_PATH))  # override: kernel experiments (tools/build_variant.py)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError if the symbol is not exported
             fn.restype = res

@@ -20,6 +20,10 @@
 // COPY warp-tiles (unshifted CCDs) use the same staging: swap + RRC + 128-bit stores.
 #include "pan_fast.cuh"
 
+#ifndef OIP_DBG_VARIANT
+#define OIP_DBG_VARIANT 0 // 1..3: timing experiments that drop parts of the row loop (wrong output; tools/build_variant.py)
+#endif
+
 namespace oip {
 namespace panfast {
 
@@ -100,7 +104,7 @@ __device__ __forceinline__ f2 shfl_down1(f2 v)
 struct D2 { double lo, hi; };
 __device__ __forceinline__ D2 split_word(uint32_t w)
 {
-    const double x = __uint2double_rn(w);
+    const double x = __uint2double_rn(w); // I2F.F64.U32: one issue slot (the magic-number form costs MOV + DADD)
     D2 r;
     r.hi = __dadd_rn(__fma_rz(x, 1.52587890625e-05, 4503599627370496.0), -4503599627370496.0);
     r.lo = __fma_rn(r.hi, -65536.0, x);
@@ -123,6 +127,10 @@ __device__ __forceinline__ uint32_t rrc_d(double sd, double k, double b)
 // (after byte swap and RRC).  The TMA unit only accepts box origins on 16-byte boundaries of a tensor row
 // (measured, tools/tma_probe.cu: any other coordinate raises "illegal instruction"), so the source window starts
 // (src_x0 & 7) samples into the box; DM = that offset mod 4 is a template parameter.
+// The kernel is bound by instruction issue (a packed FFMA2/FADD2 holds the issue port of its SM sub-partition for two
+// cycles, every other instruction for one; tools/mix_rates.cu), so every step here is the form with the fewest
+// instructions: I2F.U16 takes the low 16 bits of the RRC result (the reference's mod-2^16 wrap) or a halfword of
+// the raw word directly; the conversion pipe (one warp instruction per 8 cycles) has the headroom.
 template <int MODE, int DM, bool SWAP>
 __device__ __forceinline__ void convert4(uint32_t a, const double *k, const double *b, float *f)
 {
@@ -138,7 +146,7 @@ __device__ __forceinline__ void convert4(uint32_t a, const double *k, const doub
     }
     if (MODE == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4; ++j) { // I2F.U16 with a halfword selector
             const int h = j + (DM & 1);
             f[j] = (h & 1) ? (float)(uint16_t)(w[h >> 1] >> 16) : (float)(uint16_t)(w[h >> 1] & 0xFFFFu);
         }
@@ -170,6 +178,14 @@ __device__ __forceinline__ void issue_stage(const WarpCtx &C, int slot, int x, i
 }
 
 // ------------------------------------------------------------------------------------------ REMAP warp-tile
+// predicated 64-bit store: keeps the unrolled row loop one basic block (no BSSY/BRA around the stores)
+__device__ __forceinline__ void stg_v2_if(void *p, uint32_t a, uint32_t b, bool on)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};\n\t}" ::"l"(p), "r"(a),
+                 "r"(b), "r"((uint32_t)on)
+                 : "memory");
+}
+
 template <int MODE, int DM, bool SWAP>
 __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                            const double (&b)[8])
@@ -196,60 +212,105 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
     const bool active = 4 * lane < T.half;
     const int64_t pitch = P.out_pitch;
     uint16_t *oL = P.out + T.out_off + 4 * lane - 3 * pitch; // output row (m - 3) while source row m is consumed
-    const int half = T.half, n_rows = T.n_rows;
+    uint16_t *oR = oL + T.half;
+    const int n_rows = T.n_rows;
     f2 B0[4], B1[4], B2[4], B3[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) B0[o] = B1[o] = B2[o] = B3[o] = 0ull;
 
+    // swap + RRC + float of this lane's 4 + 4 samples of one staged row, then the 3 + 3 window columns of lane+1
+    auto convert = [&](uint32_t sa, int rr, f2(&win)[7]) {
+        float fl[4], fr[4];
+#if OIP_DBG_VARIANT == 1 || OIP_DBG_VARIANT == 2 // timing experiment: no conversion at all
+        {
+            const uint2 A = lds64(sa + offL + rr * ROW_BYTES), B = lds64(sa + offR + rr * ROW_BYTES);
+            fl[0] = __uint_as_float(A.x); fl[1] = __uint_as_float(A.y); fl[2] = fl[0]; fl[3] = fl[1];
+            fr[0] = __uint_as_float(B.x); fr[1] = __uint_as_float(B.y); fr[2] = fr[0]; fr[3] = fr[1];
+        }
+#else
+        convert4<MODE, DM, SWAP>(sa + offL + rr * ROW_BYTES, k, b, fl);
+        convert4<MODE, DM, SWAP>(sa + offR + rr * ROW_BYTES, k + 4, b + 4, fr);
+#endif
+#pragma unroll
+        for (int j = 0; j < 4; ++j) win[j] = pk(fl[j], fr[j]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) win[4 + j] = shfl_down1(win[j]);
+    };
+    // one source row into the 4 output rows it feeds.  AN: new accumulator (weight row 0), A1..A3 receive weight
+    // rows 1..3; A3 completes here: per row ((s0*w0 + s1*w1) + s2*w2) + s3*w3, rows accumulated in order
+    // 0,1,2,3 (OpenCV's interior order), no FMA contraction
+    auto resample = [&](const f2(&win)[7], int m, f2(&AN)[4], f2(&A1)[4], f2(&A2)[4], f2(&A3)[4]) {
+        f2 out[4];
+#if OIP_DBG_VARIANT == 3 // timing experiment: no FP32 work
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { out[o] = win[o] ^ win[o + 3] ^ AN[o]; AN[o] = A1[o]; }
+#else
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            auto dot = [&](const f2(&Wr)[4]) {
+                return add2(add2(add2(mul2(win[o], Wr[0], nz), mul2(win[o + 1], Wr[1], nz)), mul2(win[o + 2], Wr[2], nz)),
+                            mul2(win[o + 3], Wr[3], nz));
+            };
+            AN[o] = dot(W[0]);
+            A1[o] = add2(A1[o], dot(W[1]));
+            A2[o] = add2(A2[o], dot(W[2]));
+            out[o] = add2(A3[o], dot(W[3]));
+        }
+#endif
+        const bool on = active && (unsigned)(m - 3) < (unsigned)n_rows;
+#if OIP_DBG_VARIANT == 2 // timing experiment: no F2I / pack, one store
+        stg_v2_if(oL, (uint32_t)(out[0] ^ out[1]), (uint32_t)((out[2] ^ out[3]) >> 32), on);
+#else
+        const uint2 vl = make_uint2(pack16(cast_u16(lo_of(out[0])), cast_u16(lo_of(out[1]))), pack16(cast_u16(lo_of(out[2])), cast_u16(lo_of(out[3]))));
+        const uint2 vr = make_uint2(pack16(cast_u16(hi_of(out[0])), cast_u16(hi_of(out[1]))), pack16(cast_u16(hi_of(out[2])), cast_u16(hi_of(out[3]))));
+        if (on) { // two predicated stores (streaming: written once, never re-read)
+            __stcs(reinterpret_cast<uint2 *>(oL), vl);
+            __stcs(reinterpret_cast<uint2 *>(oR), vr);
+        }
+#endif
+        oL += pitch;
+        oR += pitch;
+    };
+
+    // software pipeline: the conversion of source row m+1 (long XU / FP64 / SHFL latency chain) is issued ahead
+    // of the FP32 work of row m, so the two overlap inside one warp
     int slot = 0;
     uint32_t phase = 0;
-    for (int c = 0; c < n_chunks; ++c) {
-        mbar_wait_u32(C.bar0 + 8u * slot, phase);
-        const uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES;
-        // AN: new accumulator (weight row 0), A1..A3: rows that receive weight rows 1..3; A3 completes here
-        auto row = [&](int rr, f2(&AN)[4], f2(&A1)[4], f2(&A2)[4], f2(&A3)[4]) {
-            float fl[4], fr[4];
-            convert4<MODE, DM, SWAP>(sa + offL + rr * ROW_BYTES, k, b, fl);
-            convert4<MODE, DM, SWAP>(sa + offR + rr * ROW_BYTES, k + 4, b + 4, fr);
-            f2 win[7];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) win[j] = pk(fl[j], fr[j]);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) win[4 + j] = shfl_down1(win[j]);
-            f2 out[4];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                // per row ((s0*w0 + s1*w1) + s2*w2) + s3*w3, rows accumulated in order 0,1,2,3 (OpenCV interior order)
-                auto dot = [&](const f2(&Wr)[4]) {
-                    return add2(add2(add2(mul2(win[o], Wr[0], nz), mul2(win[o + 1], Wr[1], nz)), mul2(win[o + 2], Wr[2], nz)),
-                                mul2(win[o + 3], Wr[3], nz));
-                };
-                AN[o] = dot(W[0]);
-                A1[o] = add2(A1[o], dot(W[1]));
-                A2[o] = add2(A2[o], dot(W[2]));
-                out[o] = add2(A3[o], dot(W[3]));
-            }
-            const int m = c * RC + rr;
-            if (active && (unsigned)(m - 3) < (unsigned)n_rows) {
-                stg_v2(oL, pack16(cast_u16(lo_of(out[0])), cast_u16(lo_of(out[1]))),
-                       pack16(cast_u16(lo_of(out[2])), cast_u16(lo_of(out[3]))));
-                stg_v2(oL + half, pack16(cast_u16(hi_of(out[0])), cast_u16(hi_of(out[1]))),
-                       pack16(cast_u16(hi_of(out[2])), cast_u16(hi_of(out[3]))));
-            }
-            oL += pitch;
-        };
-        row(0, B0, B1, B2, B3);
-        row(1, B3, B0, B1, B2);
-        row(2, B2, B3, B0, B1);
-        row(3, B1, B2, B3, B0);
+    mbar_wait_u32(C.bar0, 0);
+    uint32_t sa = C.stage0;
+    f2 wa[7], wb[7];
+    convert(sa, 0, wa);
+    for (int c = 0; c + 1 < n_chunks; ++c) {
+        const int m = c * RC;
+        convert(sa, 1, wb);
+        resample(wa, m, B0, B1, B2, B3);
+        convert(sa, 2, wa);
+        resample(wb, m + 1, B3, B0, B1, B2);
+        convert(sa, 3, wb);
+        resample(wa, m + 2, B2, B3, B0, B1);
+        // stage `slot` is consumed: refill it, move on to the next stage and convert its first row
         __syncwarp();
         if (lane == 0 && c + ns < n_chunks) issue_stage(C, slot, x0, T.src_y0 + (c + ns) * RC);
         if (++slot == ns) { slot = 0; phase ^= 1u; }
+        mbar_wait_u32(C.bar0 + 8u * slot, phase);
+        sa = C.stage0 + (uint32_t)slot * STAGE_BYTES;
+        convert(sa, 0, wa);
+        resample(wb, m + 3, B1, B2, B3, B0);
+    }
+    { // last stage (peeled: the loop body above has no conditional conversion, so its registers line up)
+        const int m = (n_chunks - 1) * RC;
+        convert(sa, 1, wb);
+        resample(wa, m, B0, B1, B2, B3);
+        convert(sa, 2, wa);
+        resample(wb, m + 1, B3, B0, B1, B2);
+        convert(sa, 3, wb);
+        resample(wa, m + 2, B2, B3, B0, B1);
+        resample(wb, m + 3, B1, B2, B3, B0);
     }
 }
 
 // ------------------------------------------------------------------------------------------- COPY warp-tile
-template <int MODE, bool SWAP>
+template <int MODE, bool SWAP, bool TAIL>
 __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                           const double (&b)[8])
 {
@@ -260,7 +321,8 @@ __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T
         const int pre = min(ns, n_chunks);
         for (int c = 0; c < pre; ++c) issue_stage(C, c, T.x_begin, T.src_y0 + c * RC);
     }
-    const bool active = 8 * lane < T.half;
+    const bool full = 8 * lane + 8 <= T.half;       // T.half = columns of this strip: any number <= 256
+    const int tail = full ? 0 : max(0, T.half - 8 * lane); // the lane that holds the strip's last odd columns
     const int64_t pitch = P.out_pitch;
     uint16_t *o = P.out + T.out_off + 8 * lane;
     int slot = 0;
@@ -283,7 +345,15 @@ __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T
                     wd[i] = pack16(rrc_d<MODE>(d.lo, k[2 * i], b[2 * i]), rrc_d<MODE>(d.hi, k[2 * i + 1], b[2 * i + 1]));
                 }
             }
-            if (active && c * RC + rr < n_rows) stg_na_v4(o, make_uint4(wd[0], wd[1], wd[2], wd[3]));
+            if (c * RC + rr < n_rows) {
+                if (full) {
+                    stg_na_v4(o, make_uint4(wd[0], wd[1], wd[2], wd[3]));
+                } else if (TAIL) { // the strip's last odd columns (planner: only the last strip of a CCD can have them)
+#pragma unroll
+                    for (int j = 0; j < 7; ++j)
+                        if (j < tail) o[j] = (uint16_t)(wd[j >> 1] >> (16 * (j & 1)));
+                }
+            }
             o += pitch;
         }
         __syncwarp();
@@ -311,8 +381,13 @@ __device__ __forceinline__ void tile_dispatch(const FastParams &P, const FastTil
         if (swap) remap_dispatch<MODE, true>(P, T, C, k, b);
         else remap_dispatch<MODE, false>(P, T, C, k, b);
     } else {
-        if (swap) copy_tile<MODE, true>(P, T, C, k, b);
-        else copy_tile<MODE, false>(P, T, C, k, b);
+        if (T.half & 7) { // rare: keep the tail stores out of the common loop
+            if (swap) copy_tile<MODE, true, true>(P, T, C, k, b);
+            else copy_tile<MODE, false, true>(P, T, C, k, b);
+        } else {
+            if (swap) copy_tile<MODE, true, false>(P, T, C, k, b);
+            else copy_tile<MODE, false, false>(P, T, C, k, b);
+        }
     }
 }
 

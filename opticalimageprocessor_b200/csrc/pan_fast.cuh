@@ -24,7 +24,7 @@ struct FastTile {
     int32_t ccd;
     int32_t tmap;     // tensor map index = ccd * OIP_MAX_SEG + segment
     int32_t x_begin;  // first CCD column produced
-    int32_t half;     // REMAP: columns per half (multiple of 4, <= HALF_MAX), n_cols = 2*half; COPY: n_cols (multiple of 8)
+    int32_t half;     // REMAP: columns per half (multiple of 4, <= HALF_MAX), n_cols = 2*half; COPY: n_cols (any, <= COPY_MAX)
     int32_t src_x0;   // REMAP: source column of the first tap of x_begin;  COPY: x_begin
     int32_t src_y0;   // row inside the segment of the first source row (first tap row of output row 0)
     int32_t n_rows;   // output rows

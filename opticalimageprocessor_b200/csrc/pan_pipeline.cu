@@ -630,9 +630,9 @@ static void emit_generic(std::vector<Tile> &tiles, int i, bool shifted, const Sh
                          int out_x_lo, int64_t g_lo, int64_t g_hi)
 {
     if (x_hi <= x_lo || g_hi <= g_lo) return;
-    // a CTA marches down its tile 32 rows at a time: slivers (leftover columns next to the fast spans) get short
-    // tiles so that the launch is many short CTAs instead of a few that run as long as a full-width tile
-    const int th = x_hi - x_lo < 16 ? 32 : (x_hi - x_lo < 64 ? 128 : TH);
+    // slivers (leftover columns next to the fast spans) get somewhat shorter tiles; the launch runs on a side
+    // stream next to the fast kernel, so a few long CTAs are better than thousands of tiny ones
+    const int th = x_hi - x_lo < 64 ? 256 : TH;
     for (int64_t g = g_lo; g < g_hi; g += th) {
         const int nr = (int)std::min<int64_t>(th, g_hi - g);
         // column strips of equal width (no skinny last strip); even for the 32-bit paired stores of REMAP
@@ -675,17 +675,18 @@ static void emit_fast(std::vector<panfast::FastTile> &out, int kind, int i, int 
                       int64_t ga, int64_t gb, int64_t src_row_a, int fy, const oip_pan_desc *d, int th)
 {
     const int max_w = kind == panfast::FT_REMAP ? 2 * panfast::HALF_MAX : panfast::COPY_MAX;
-    const int width = cs.xb - cs.xa; // multiple of 8
+    const int width = cs.xb - cs.xa; // REMAP: multiple of 8; COPY: any (the last strip takes the odd columns)
     const int n_strips = (width + max_w - 1) / max_w;
-    const int base = width / n_strips / 8 * 8;
-    int extra = (width - base * n_strips) / 8; // this many strips are 8 columns wider
+    const int base = width / n_strips / 8 * 8;       // < max_w unless width == n_strips * max_w: the +8 / tail below fit
+    int extra = (width - base * n_strips) / 8;       // this many strips are 8 columns wider
+    const int tail = (width - base * n_strips) % 8;  // COPY only: odd columns, given to the last strip
     const int64_t len = gb - ga;
     const int n_t = (int)((len + th - 1) / th);
     const int64_t h = (len + n_t - 1) / n_t;
     for (int64_t g = ga; g < gb; g += h) {
         int x = cs.xa, ex = extra;
         for (int sidx = 0; sidx < n_strips; ++sidx) {
-            const int sw = base + (ex > 0 ? 8 : 0);
+            const int sw = base + (ex > 0 ? 8 : 0) + (sidx == n_strips - 1 ? tail : 0);
             if (ex > 0) --ex;
             panfast::FastTile t{};
             t.kind = kind;
@@ -730,7 +731,7 @@ static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows
             // COPY: TMA box origins need source columns that are multiples of 8 (16 bytes), the 128-bit stores need
             // the same of the output column
             const int xs = (lo + 7) & ~7;
-            const int usable = fast && xs < hi && (out_x + xs - lo) % 8 == 0 ? ((hi - xs) & ~7) : 0;
+            const int usable = fast && xs < hi && (out_x + xs - lo) % 8 == 0 ? hi - xs : 0;
             int64_t cur = r_lo;
             if (usable >= 8) {
                 const ColSpan cs{xs, xs + usable, 0};
@@ -818,26 +819,19 @@ static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows
         }
         out_x += hi - lo;
     }
-    // CTA = WARPS warp-tiles of one kind / CCD / row band, bands in raster order (neighbouring strips share halo
-    // columns through L2, COPY and REMAP CTAs interleave on every SM)
+    // CTA = WARPS consecutive warp-tiles (its warps are independent workers), row bands in raster order:
+    // neighbouring strips share halo columns through L2, COPY and REMAP tiles interleave on every SM
     std::stable_sort(fl.begin(), fl.end(), [&](const panfast::FastTile &a, const panfast::FastTile &b) {
         const int64_t ra = a.out_off / d->out_pitch_px / th, rb = b.out_off / d->out_pitch_px / th;
         if (ra != rb) return ra < rb;
+        if (a.kind != b.kind) return a.kind > b.kind; // REMAP tiles (long) first inside a band
         if (a.ccd != b.ccd) return a.ccd < b.ccd;
         return a.x_begin < b.x_begin;
     });
-    ftiles.clear();
+    ftiles = fl;
     panfast::FastTile none{};
     none.kind = panfast::FT_NONE;
-    for (size_t p = 0; p < fl.size();) {
-        size_t q = p;
-        const int64_t band = fl[p].out_off / d->out_pitch_px / th;
-        while (q < fl.size() && q - p < (size_t)panfast::WARPS && fl[q].ccd == fl[p].ccd && fl[q].kind == fl[p].kind &&
-               fl[q].out_off / d->out_pitch_px / th == band)
-            ftiles.push_back(fl[q++]);
-        for (size_t z = q - p; z < (size_t)panfast::WARPS; ++z) ftiles.push_back(none);
-        p = q;
-    }
+    while (ftiles.size() % panfast::WARPS) ftiles.push_back(none);
     return OIP_OK;
 }
 
