@@ -27,7 +27,7 @@ struct oip_ctx {
     int pan_fast = 1;            // 0: everything on the generic kernel
     int pan_fast_stages = 4;     // TMA stages per warp
     int pan_fast_rows = 128;     // output rows per warp-tile
-    int pan_fast_minb = 4;       // register-allocation variant of pan_fast_kernel (CTAs per SM: 2, 3, 4)
+    int pan_fast_minb = 3;       // register-allocation variant of pan_fast_kernel (CTAs per SM: 2, 3, 4)
     void *d_mss_plan = nullptr;
     size_t d_mss_plan_cap = 0;
     std::vector<uint8_t> mss_plan_key;

@@ -362,6 +362,75 @@ __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T
     }
 }
 
+// ------------------------------------------------------------------------------------------- EDGE warp-tile
+// Column slivers next to the REMAP spans: image-border columns (4x4 footprint partly outside the CCD) and the
+// few columns the 8-column span alignment leaves over, over the same regular interior ROW runs.  One output
+// column per lane, scalar FP32, both of OpenCV's accumulation orders (interior: per-row sums added row by row;
+// border: one flat left-to-right chain starting from 0) computed and selected per column.  Taps
+// outside the CCD are zero: TMA zero-fills them and their (k,b) are forced to 0.  < 0.1 % of the pixels.
+__device__ __forceinline__ void edge_tile(const FastParams &P, const FastTile &T, const WarpCtx &C)
+{
+    const int lane = C.lane, ns = C.ns;
+    const int n_chunks = (T.n_rows + 3 + RC - 1) / RC;
+    const int x0 = T.src_x0 & ~7;                  // floor to a multiple of 8 (also for negative columns)
+    const int col = T.src_x0 + lane;               // source column this lane converts = first tap of output column x_begin+lane
+    const uint32_t off = 2u * (uint32_t)(col - x0);
+    if (lane == 0) {
+        const int pre = min(ns, n_chunks);
+        for (int c = 0; c < pre; ++c) issue_stage(C, c, x0, T.src_y0 + c * RC);
+    }
+    const bool swap = P.ccd[T.ccd].swap != 0;
+    const double *kbp = P.ccd[T.ccd].kb;
+    const bool inside = col >= 0 && col < P.w;
+    double k = inside ? 1.0 : 0.0, b = 0.0;
+    if (kbp && inside) { k = kbp[2 * (int64_t)col]; b = kbp[2 * (int64_t)col + 1]; }
+    float W[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) W[r][c] = __fmul_rn(__ldg(P.tab + 4 * T.fy + r), __ldg(P.tab + 4 * T.fx + c));
+    const bool active = lane < T.half;
+    const bool border = !(col >= 0 && col < P.w - 3); // the footprint of my output column leaves the CCD: flat order
+    uint16_t *o = P.out + T.out_off + lane - 3 * P.out_pitch;
+    float A[4] = {0.f, 0.f, 0.f, 0.f}, F[4] = {0.f, 0.f, 0.f, 0.f}; // partial sums of the output rows in flight (index 0 unused)
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        mbar_wait_u32(C.bar0 + 8u * slot, phase);
+        const uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES + off;
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) {
+            uint32_t s;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(s) : "r"(sa + rr * ROW_BYTES));
+            if (swap) s = __byte_perm(s, 0u, 0x4401);
+            const float v = inside ? (float)(kbp ? rrc_px(s, k, b) : s) : 0.f;
+            float win[4];
+            win[0] = v;
+#pragma unroll
+            for (int j = 1; j < 4; ++j) win[j] = __shfl_down_sync(0xffffffffu, v, j);
+            // A[i] / F[i]: interior / flat partial sum of the output row that has received weight rows 0..i-1 so far
+            float d[4], f[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float p0 = __fmul_rn(win[0], W[r][0]), p1 = __fmul_rn(win[1], W[r][1]), p2 = __fmul_rn(win[2], W[r][2]),
+                            p3 = __fmul_rn(win[3], W[r][3]);
+                d[r] = __fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3);
+                f[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(r == 0 ? 0.f : F[r], p0), p1), p2), p3);
+            }
+            const float a_out = __fadd_rn(A[3], d[3]), f_out = f[3];
+            A[3] = __fadd_rn(A[2], d[2]); F[3] = f[2];
+            A[2] = __fadd_rn(A[1], d[1]); F[2] = f[1];
+            A[1] = d[0];                  F[1] = f[0];
+            const int m = c * RC + rr;
+            if (active && (unsigned)(m - 3) < (unsigned)T.n_rows) *o = (uint16_t)cast_u16(border ? f_out : a_out);
+            o += P.out_pitch;
+        }
+        __syncwarp();
+        if (lane == 0 && c + ns < n_chunks) issue_stage(C, slot, x0, T.src_y0 + (c + ns) * RC);
+        if (++slot == ns) { slot = 0; phase ^= 1u; }
+    }
+}
+
 template <int MODE, bool SWAP>
 __device__ __forceinline__ void remap_dispatch(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                                const double (&b)[8])
@@ -412,6 +481,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pan_fast_kernel(const __grid
         fence_mbar_init();
     }
     __syncwarp();
+    if (T.kind == FT_EDGE) {
+        edge_tile(P, T, C);
+        return;
+    }
 
     // (k,b) of the 8 detectors this lane converts, and the warp-wide RRC mode
     const double *kbp = P.ccd[T.ccd].kb;

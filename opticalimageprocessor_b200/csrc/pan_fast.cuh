@@ -14,7 +14,8 @@ constexpr int HALF_MAX = 124;   // REMAP: output columns per half (31 lanes x 4)
 constexpr int COPY_MAX = 256;   // COPY: output columns per warp-tile (32 lanes x 8)
 constexpr int MAX_MAPS = 8 * OIP_MAX_SEG;
 
-enum { FT_NONE = -1, FT_COPY = 0, FT_REMAP = 1 };
+enum { FT_NONE = -1, FT_COPY = 0, FT_REMAP = 1, FT_EDGE = 2 };
+constexpr int EDGE_MAX = 29;    // EDGE: output columns per warp-tile (one per lane; 3 more lanes supply window columns)
 
 // one warp's work: a column strip of one CCD over n_rows output rows whose source rows sit in ONE row
 // segment, whose 4x4 footprints are all inside the section's fresh rows / the CCD's columns, and whose
@@ -24,8 +25,8 @@ struct FastTile {
     int32_t ccd;
     int32_t tmap;     // tensor map index = ccd * OIP_MAX_SEG + segment
     int32_t x_begin;  // first CCD column produced
-    int32_t half;     // REMAP: columns per half (multiple of 4, <= HALF_MAX), n_cols = 2*half; COPY: n_cols (any, <= COPY_MAX)
-    int32_t src_x0;   // REMAP: source column of the first tap of x_begin;  COPY: x_begin
+    int32_t half;     // EDGE: columns of the sliver (<= EDGE_MAX), any alignment, image-border columns allowed;  REMAP: columns per half (multiple of 4, <= HALF_MAX), n_cols = 2*half; COPY: n_cols (any, <= COPY_MAX)
+    int32_t src_x0;   // REMAP / EDGE: source column of the first tap of x_begin (EDGE: may be < 0);  COPY: x_begin
     int32_t src_y0;   // row inside the segment of the first source row (first tap row of output row 0)
     int32_t n_rows;   // output rows
     int32_t fx, fy;   // sub-pixel phase (1/32) of the whole tile

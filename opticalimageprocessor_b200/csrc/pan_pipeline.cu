@@ -712,6 +712,46 @@ static void emit_fast(std::vector<panfast::FastTile> &out, int kind, int i, int 
     }
 }
 
+// column gap [xa,xb) of a shifted CCD over the fast row run [ga,gb): EDGE warp-tiles (one column per lane, both
+// accumulation orders, any alignment) where the fixed-point map is regular across the gap, generic tiles otherwise
+static void emit_gap(std::vector<Tile> &tiles, std::vector<panfast::FastTile> &fl, int i, int seg, const ShiftSegment &s, int xa, int xb,
+                     int lo, int out_x_ccd, int64_t ga, int64_t gb, int64_t src_row_a, int fy, const oip_pan_desc *d, int th)
+{
+    if (xb <= xa) return;
+    const double dX = d->ccd[i].dX;
+    int x = xa;
+    while (x < xb) {
+        const int sx0 = map_fixed(x, dX);
+        int xe = x + 1;
+        while (xe < xb && xe - x < panfast::EDGE_MAX && map_fixed(xe, dX) == sx0 + 32 * (xe - x)) ++xe;
+        const int ix0 = (sx0 >> 5) - 1;
+        if (ix0 < -30000 || ix0 > 30000) { // saturating coordinates: not a case for the fast path
+            emit_generic(tiles, i, true, s, x, xe, out_x_ccd + (x - lo), ga, gb);
+            x = xe;
+            continue;
+        }
+        const int64_t len = gb - ga;
+        const int n_t = (int)((len + th - 1) / th);
+        const int64_t h = (len + n_t - 1) / n_t;
+        for (int64_t g = ga; g < gb; g += h) {
+            panfast::FastTile t{};
+            t.kind = panfast::FT_EDGE;
+            t.ccd = i;
+            t.tmap = i * OIP_MAX_SEG + seg;
+            t.x_begin = x;
+            t.half = xe - x;
+            t.src_x0 = ix0;
+            t.src_y0 = (int)(src_row_a + (g - ga));
+            t.n_rows = (int)std::min<int64_t>(h, gb - g);
+            t.fx = sx0 & 31;
+            t.fy = fy;
+            t.out_off = (g - d->row0) * d->out_pitch_px + out_x_ccd + (x - lo);
+            fl.push_back(t);
+        }
+        x = xe;
+    }
+}
+
 static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows, std::vector<Tile> &tiles,
                       std::vector<panfast::FastTile> &ftiles)
 {
@@ -806,11 +846,11 @@ static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows
                     const int64_t src_row = s.sec_off + (sat_short(sy0 >> 5) - 1) - C.seg[k0].row0;
                     int xg = lo; // columns between the fast spans stay generic
                     for (const ColSpan &cs : spans) {
-                        emit_generic(tiles, i, true, s, xg, cs.xa, out_x + (xg - lo), g, ge);
+                        emit_gap(tiles, fl, i, k0, s, xg, cs.xa, lo, out_x, g, ge, src_row, sy0 & 31, d, th);
                         emit_fast(fl, panfast::FT_REMAP, i, k0, cs, lo, out_x, g, ge, src_row, sy0 & 31, d, th);
                         xg = cs.xb;
                     }
-                    emit_generic(tiles, i, true, s, xg, hi, out_x + (xg - lo), g, ge);
+                    emit_gap(tiles, fl, i, k0, s, xg, hi, lo, out_x, g, ge, src_row, sy0 & 31, d, th);
                     gen_from = ge;
                 }
                 g = ge;
@@ -950,7 +990,7 @@ extern "C" int oip_pan_plan_coverage(const oip_pan_desc *d, int enable_fast, int
     for (const panfast::FastTile &t : ftiles) {
         if (t.kind < 0) continue;
         ++n_fast;
-        const int nc = t.kind == panfast::FT_REMAP ? 2 * t.half : t.half;
+        const int nc = t.kind == panfast::FT_REMAP ? 2 * t.half : t.half; // COPY / EDGE: half = columns
         px_fast += (int64_t)nc * t.n_rows;
         if (cover)
             for (int64_t r = 0; r < t.n_rows; ++r)

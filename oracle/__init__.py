@@ -103,6 +103,37 @@ def ref_crc_lib():
     return _REF_CRC
 
 
+def ref_oip_lib():
+    """the reference's own headers compiled behind a C shim (oracle/_ref/libref_oip.so), or None."""
+    global _ref_oip
+    try:
+        return _ref_oip
+    except NameError:
+        pass
+    so = os.path.join(_HERE, "_ref", "libref_oip.so")
+    _ref_oip = None
+    if os.path.exists(so):
+        try:
+            L = C.CDLL(so)
+            L.ref_inplace_rrc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            L.ref_inplace_rrc.restype = None
+            _ref_oip = L
+        except OSError:
+            _ref_oip = None
+    return _ref_oip
+
+
+def ref_inplace_rrc(img: np.ndarray, kb: np.ndarray) -> np.ndarray:
+    """IMO::InplaceRRC as compiled from the reference's imageop.h (ref imageop.h:129-138); needs oracle/_ref"""
+    L = ref_oip_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libref_oip.so is not built")
+    out = np.ascontiguousarray(img, np.uint16).copy()
+    kb = np.ascontiguousarray(kb, np.float64)
+    L.ref_inplace_rrc(out.ctypes.data_as(C.c_void_p), out.shape[1], out.shape[0], kb.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def _ptr_array(arrs):
     a = (C.c_void_p * len(arrs))()
     for i, x in enumerate(arrs):
