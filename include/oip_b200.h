@@ -55,7 +55,8 @@ int oip_abi_version(void);
 int64_t oip_ctx_launch_count(oip_ctx *ctx);
 
 /* tunables / test switches.  "pan_fast" (0|1, default 1): 0 sends every PAN tile through the generic kernel;
- * "pan_fast_stages" (2..8): TMA stages per warp; "pan_fast_rows": output rows per warp-tile. */
+ * "pan_fast_stages" (2..8): TMA stages per warp; "pan_fast_rows": output rows per warp-tile;
+ * "mss_fast" (0|1), "mss_fast_rows": the same switches for oip_band_align_merge. */
 int oip_ctx_set_option(oip_ctx *ctx, const char *name, int64_t value);
 
 /* raw memory helpers for hosts without their own allocator (the CLI); torch callers pass data_ptr() */
@@ -244,6 +245,12 @@ typedef struct {
 } oip_mss_desc;
 int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_mss_desc *desc, uint16_t *d_out,
                          int64_t *rows_written);
+
+/* host-only planning diagnostic (no device work): how oip_band_align_merge splits its output between the
+ * regular-interior fast kernel and the exact generic kernel.  cover (rows_out x wb x 4 bytes, zeroed by the caller,
+ * may be NULL): += 1 per generic sample, += 2 per fast sample.  stats = {generic samples, fast samples, generic tiles,
+ * fast warp-tiles} (per band sample = one u16 of the interleaved raster). */
+int oip_mss_plan_coverage(const oip_mss_desc *desc, int enable_fast, int tile_rows, uint8_t *cover, int64_t stats[4]);
 
 /* replaces the geometry of IMO::StitchTiff / StitchTiffGDAL on CV_16UC4 data incl. the 1-based
  * band map -- ref imageop.h:416-421, :501-506, :529 */

@@ -81,6 +81,7 @@ SYMBOLS = {
     "oip_load_rrc_csv": (_I, [C.c_char_p, _I, _VP]),
     "oip_pan_pipeline": (_I, [_VP, C.POINTER(PanDesc)]),
     "oip_pan_plan_coverage": (_I, [C.POINTER(PanDesc), _I, _I, _VP, C.POINTER(_I64)]),
+    "oip_mss_plan_coverage": (_I, [C.POINTER(MssDesc), _I, _I, _VP, C.POINTER(_I64)]),
     "oip_pan_out_width": (_I, [_I, _I, _I]),
     "oip_pan_check_error": (_I, [_VP]),
     "oip_cubic_tab": (None, [_VP]),

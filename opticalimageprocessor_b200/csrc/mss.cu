@@ -5,7 +5,7 @@
 // into its channel of the interleaved CV_16UC4 raster (cv::merge layout, ref preproc.h:464).
 #include <algorithm>
 
-#include "oip_common.cuh"
+#include "mss_plan.cuh"
 
 namespace oip {
 namespace mss {
@@ -16,14 +16,6 @@ constexpr int RC = 32;    // output rows per chunk
 constexpr int RING = 48;  // float ring rows: RC + 3 taps + spread of the per-column row offsets
 constexpr int NT = 256;
 constexpr int TH = 256;   // output rows per tile
-
-struct Tile {
-    int32_t band, x_begin, x_end;
-    int32_t rows;      // section height = rows of the cv::Mat handed to cv::remap (ref preproc.h:453)
-    int32_t y0, n_rows; // section-local output rows [y0, y0+n_rows)
-    int64_t sec_off;   // first source line of the section (rowOffset)
-    int64_t dst_row0;  // output raster row of y0
-};
 
 struct Params {
     const uint8_t *base;
@@ -233,6 +225,55 @@ using namespace oip;
 
 extern "C" void oip_cubic_tab(float *tab128);
 
+// the reference's section loop (ref preproc.h:379-408); returns processedLines
+static int64_t build_sections(const oip_mss_desc *d, std::vector<mssfast::Section> &secs)
+{
+    const int lps = d->lines_per_section, overlap = d->overlap;
+    const int min_lines = d->min_process_lines > 0 ? d->min_process_lines : 1500;
+    uint64_t offset = (uint64_t)d->line_offset;
+    int64_t processed = 0;
+    for (int i = 0;; ++i) {
+        const uint64_t rem = (uint64_t)d->lines - offset;
+        const uint64_t n = std::min<uint64_t>(rem, (uint64_t)lps);                    // :380
+        if ((uint64_t)d->lines < offset || n < (uint64_t)min_lines) break;             // :381
+        const int y0 = (i == 0 && d->keep_leading) ? 0 : overlap;                      // :392-402
+        secs.push_back({(int64_t)offset, (int)n, y0, processed});
+        processed += (int64_t)n - y0;                                                   // :396,405
+        offset += (uint64_t)(lps - overlap);                                            // :407
+    }
+    return processed;
+}
+
+/* host-only diagnostic: how oip_band_align_merge splits its output between the fast and the generic kernel */
+extern "C" int oip_mss_plan_coverage(const oip_mss_desc *d, int enable_fast, int tile_rows, uint8_t *cover, int64_t stats[4])
+{
+    if (!d || d->wb < 4 || d->lines < 0 || d->lines_per_section < 8 || d->overlap < 0 || d->lines_per_section <= d->overlap)
+        return fail(OIP_E_INVALID, "oip_mss_plan_coverage: bad descriptor");
+    std::vector<mssfast::Section> secs;
+    build_sections(d, secs);
+    std::vector<mss::Tile> tiles;
+    std::vector<mssfast::FTile> ftiles;
+    mssfast::plan(d, secs, enable_fast != 0, tile_rows, tiles, ftiles);
+    int64_t g = 0, f = 0, nf = 0;
+    const int64_t wb = d->wb;
+    for (const mss::Tile &t : tiles) {
+        g += (int64_t)(t.x_end - t.x_begin) * t.n_rows;
+        if (cover)
+            for (int r = 0; r < t.n_rows; ++r)
+                for (int x = t.x_begin; x < t.x_end; ++x) cover[((t.dst_row0 + r) * wb + x) * 4 + t.band] += 1;
+    }
+    for (const mssfast::FTile &t : ftiles) {
+        if (t.band < 0) continue;
+        ++nf;
+        f += (int64_t)(t.nh + t.n_right) * t.n_rows;
+        if (cover)
+            for (int r = 0; r < t.n_rows; ++r)
+                for (int x = 0; x < t.nh + t.n_right; ++x) cover[t.out_off + (int64_t)r * wb * 4 + 4 * x] += 2;
+    }
+    if (stats) { stats[0] = g; stats[1] = f; stats[2] = (int64_t)tiles.size(); stats[3] = nf; }
+    return OIP_OK;
+}
+
 extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_mss_desc *d, uint16_t *d_out,
                                     int64_t *rows_written)
 {
@@ -251,50 +292,56 @@ extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_m
     if (d->lines - d->line_offset < min_lines) return fail(OIP_E_INVALID, "Too few image lines left to process");
     if (overlap < 0 || d->line_offset < 0) return fail(OIP_E_INVALID, "negative overlap / line offset");
 
-    // ---- section loop (ref preproc.h:379-408) -> tiles; cached on the geometry
-    struct Key { int wb, lps, overlap, keep, min_lines; int64_t lines, off; } key{d->wb, lps, overlap, d->keep_leading != 0, min_lines, d->lines, d->line_offset};
+    // ---- section loop (ref preproc.h:379-408) -> fast warp-tiles + generic tiles; cached on the geometry and the map
+    const bool fast_ok = ctx->mss_fast != 0 && (((uintptr_t)d_mss & 15) == 0) && ((d->pitch_px * 2) % 16 == 0) && d->wb >= 16;
+    struct Key { int wb, lps, overlap, keep, min_lines, fast, tile_rows; int64_t lines, off; double cX[8], cY[12]; } key{};
+    key.wb = d->wb; key.lps = lps; key.overlap = overlap; key.keep = d->keep_leading != 0; key.min_lines = min_lines;
+    key.fast = fast_ok; key.tile_rows = ctx->mss_fast_rows; key.lines = d->lines; key.off = d->line_offset;
+    memcpy(key.cX, d->cX, sizeof key.cX); memcpy(key.cY, d->cY, sizeof key.cY);
     const uint8_t *kbytes = reinterpret_cast<const uint8_t *>(&key);
     if (ctx->mss_plan_key.size() != sizeof key || memcmp(ctx->mss_plan_key.data(), kbytes, sizeof key) != 0) {
+        std::vector<mssfast::Section> secs;
+        const int64_t processed = build_sections(d, secs);
         std::vector<mss::Tile> tiles;
-        uint64_t offset = (uint64_t)d->line_offset;
-        int64_t processed = 0;
-        for (int i = 0;; ++i) {
-            const uint64_t rem = (uint64_t)d->lines - offset;
-            const uint64_t n = std::min<uint64_t>(rem, (uint64_t)lps);                    // :380
-            if ((uint64_t)d->lines < offset || n < (uint64_t)min_lines) break;             // :381
-            const int y0 = (i == 0 && d->keep_leading) ? 0 : overlap;                      // :392-402
-            for (int y = y0; y < (int)n; y += mss::TH)
-                for (int x = 0; x < d->wb; x += mss::TW)
-                    for (int b = 0; b < 4; ++b) { // the 4 bands of a block are adjacent launches: they fill the
-                        mss::Tile t{};            // same 8-byte pixels, so the sectors complete while in L2
-                        t.band = b; t.x_begin = x; t.x_end = std::min(d->wb, x + mss::TW);
-                        t.rows = (int)n; t.y0 = y; t.n_rows = std::min(mss::TH, (int)n - y);
-                        t.sec_off = (int64_t)offset; t.dst_row0 = processed + (y - y0);
-                        tiles.push_back(t);
-                    }
-            processed += (int64_t)n - y0;                                                   // :396,405
-            offset += (uint64_t)(lps - overlap);                                            // :407
-        }
+        std::vector<mssfast::FTile> ftiles;
+        mssfast::plan(d, secs, fast_ok, ctx->mss_fast_rows, tiles, ftiles);
         ctx->mss_plan_rows = processed;
-        float tab[128];
+        float tab[132] = {};
         oip_cubic_tab(tab);
-        const size_t bytes = 512 + tiles.size() * sizeof(mss::Tile);
+        tab[128] = tab[129] = -0.0f; // run-time (-0.0,-0.0) addend of the packed products (oip_common.cuh mul2)
+        const size_t fast_off = (1024 + tiles.size() * sizeof(mss::Tile) + 63) / 64 * 64;
+        const size_t bytes = fast_off + ftiles.size() * sizeof(mssfast::FTile) + 64;
         if (bytes > ctx->d_mss_plan_cap) {
             if (ctx->d_mss_plan) { OIP_CUDA(cudaStreamSynchronize(ctx->stream)); OIP_CUDA(cudaFree(ctx->d_mss_plan)); ctx->d_mss_plan = nullptr; }
             OIP_CUDA(cudaMalloc(&ctx->d_mss_plan, bytes * 2));
             ctx->d_mss_plan_cap = bytes * 2;
         }
-        int rc = ensure_pinned(ctx, bytes);
-        if (rc) return rc;
-        OIP_CUDA(cudaStreamSynchronize(ctx->stream));
-        memcpy(ctx->h_pinned, tab, 512);
-        if (!tiles.empty()) memcpy((uint8_t *)ctx->h_pinned + 512, tiles.data(), tiles.size() * sizeof(mss::Tile));
-        OIP_CUDA(cudaMemcpyAsync(ctx->d_mss_plan, ctx->h_pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        OIP_CUDA(cudaMemcpyAsync(ctx->d_mss_plan, tab, sizeof tab, cudaMemcpyHostToDevice, ctx->stream));
+        if (!tiles.empty())
+            OIP_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_mss_plan + 1024, tiles.data(), tiles.size() * sizeof(mss::Tile), cudaMemcpyHostToDevice, ctx->stream));
+        if (!ftiles.empty())
+            OIP_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_mss_plan + fast_off, ftiles.data(), ftiles.size() * sizeof(mssfast::FTile), cudaMemcpyHostToDevice, ctx->stream));
+        OIP_CUDA(cudaStreamSynchronize(ctx->stream)); // the host vectors go out of scope
         ctx->mss_plan_key.assign(kbytes, kbytes + sizeof key);
         ctx->mss_plan_tiles = (int64_t)tiles.size();
+        ctx->mss_fast_ctas = (int64_t)(ftiles.size() / mssfast::WARPS);
+        ctx->mss_fast_off = fast_off;
     }
     if (rows_written) *rows_written = ctx->mss_plan_rows;
-    if (ctx->mss_plan_tiles == 0) return OIP_OK;
+    if (ctx->mss_plan_tiles == 0 && ctx->mss_fast_ctas == 0) return OIP_OK;
+
+    // ---- fast kernel on the caller's stream; the generic tiles run next to it on a side stream
+    const bool fork = ctx->mss_fast_ctas > 0 && ctx->mss_plan_tiles > 0;
+    if (fork) {
+        if (!ctx->aux_stream) {
+            OIP_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+            OIP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            OIP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        OIP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        OIP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    }
+    cudaStream_t gstream = fork ? ctx->aux_stream : ctx->stream;
 
     mss::Params P{};
     P.base = (const uint8_t *)d_mss;
@@ -303,7 +350,7 @@ extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_m
     for (int i = 0; i < 8; ++i) P.cX[i] = d->cX[i];
     for (int i = 0; i < 12; ++i) P.cY[i] = d->cY[i];
     P.tab = (const float *)ctx->d_mss_plan;
-    P.tiles = (const mss::Tile *)((const uint8_t *)ctx->d_mss_plan + 512);
+    P.tiles = (const mss::Tile *)((const uint8_t *)ctx->d_mss_plan + 1024);
     P.out = d_out; P.err = ctx->d_err; P.fmt = d->fmt; P.wb = d->wb;
     P.vec_ok = (((uintptr_t)d_mss & 3) == 0 && (P.pitch_bytes & 3) == 0 && (d->wb % 2) == 0) ? 1 : 0;
     const size_t smem = (size_t)mss::RING * mss::SWC * 4;
@@ -311,9 +358,28 @@ extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_m
         OIP_CUDA(cudaFuncSetAttribute(mss::band_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->mss_attr_set = true;
     }
-    mss::band_align_kernel<<<(unsigned)ctx->mss_plan_tiles, mss::NT, smem, ctx->stream>>>(P);
-    OIP_CUDA(cudaGetLastError());
-    ctx->launches++;
+    if (ctx->mss_plan_tiles > 0) {
+        mss::band_align_kernel<<<(unsigned)ctx->mss_plan_tiles, mss::NT, smem, gstream>>>(P);
+        OIP_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (ctx->mss_fast_ctas > 0) {
+        mssfast::Params F;
+        memset(&F, 0, sizeof F);
+        int rc = mssfast::encode(&F.tmap, d_mss, 4 * d->wb, d->lines, d->pitch_px * 2);
+        if (rc) return rc;
+        for (int b = 0; b < 4; ++b) F.kb[b] = d->d_kb[b];
+        memcpy(F.cX, d->cX, sizeof F.cX); memcpy(F.cY, d->cY, sizeof F.cY);
+        F.tiles = (const mssfast::FTile *)((const uint8_t *)ctx->d_mss_plan + ctx->mss_fast_off);
+        F.out = d_out; F.tab = (const float *)ctx->d_mss_plan; F.wb = d->wb; F.swap = d->fmt == OIP_FMT_BE16;
+        F.n_stage = std::max(2, std::min(8, ctx->pan_fast_stages));
+        rc = mssfast::launch(ctx, F, ctx->mss_fast_ctas);
+        if (rc) return rc;
+    }
+    if (fork) {
+        OIP_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+        OIP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
     // the polynomial may exceed the staged window: report instead of returning wrong pixels
     int e = 0;
     OIP_CUDA(cudaMemcpyAsync(&e, ctx->d_err, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));

@@ -33,6 +33,10 @@ struct oip_ctx {
     std::vector<uint8_t> mss_plan_key;
     int64_t mss_plan_tiles = 0;
     int64_t mss_plan_rows = 0;
+    int64_t mss_fast_ctas = 0;   // mss_fast_kernel CTAs
+    size_t mss_fast_off = 0;     // byte offset of the FTile array inside d_mss_plan
+    int mss_fast = 1;            // 0: every MSS tile on the generic kernel
+    int mss_fast_rows = 128;     // output rows per MSS warp-tile
     // scratch for stage 1 (grown on demand)
     void *d_scratch = nullptr;
     size_t d_scratch_cap = 0;

@@ -19,6 +19,7 @@
 //   store     F2I.U16 (round-half-even, saturating) + 64-bit stores straight into the trimmed output raster
 // COPY warp-tiles (unshifted CCDs) use the same staging: swap + RRC + 128-bit stores.
 #include "pan_fast.cuh"
+#include "tma_warp.cuh"
 
 #ifndef OIP_DBG_VARIANT
 #define OIP_DBG_VARIANT 0 // 1..3: timing experiments that drop parts of the row loop (wrong output; tools/build_variant.py)
@@ -33,95 +34,7 @@ constexpr int MAX_STAGE = 8;
 static_assert(RC == 4, "the row loop is unrolled by the 4-deep accumulator rotation");
 static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int x, int y, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_init_u32(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a)
-{
-    uint32_t r;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
-    return r;
-}
-__device__ __forceinline__ uint2 lds64(uint32_t a)
-{
-    uint2 r;
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
-    return r;
-}
-__device__ __forceinline__ uint4 lds128(uint32_t a)
-{
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
-    return r;
-}
-__device__ __forceinline__ void stg_v2(void *p, uint32_t a, uint32_t b)
-{
-    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
-}
-// cvRound + saturate_cast<ushort>: PTX float->int conversions clamp to the destination range (SASS F2I.U16.NTZ)
-__device__ __forceinline__ uint32_t cast_u16(float s)
-{
-    unsigned short r;
-    asm("cvt.rni.u16.f32 %0, %1;" : "=h"(r) : "f"(s));
-    return r;
-}
-__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5410); }
-__device__ __forceinline__ f2 shfl_down1(f2 v)
-{
-    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-    lo = __shfl_down_sync(0xffffffffu, lo, 1);
-    hi = __shfl_down_sync(0xffffffffu, hi, 1);
-    return ((f2)hi << 32) | lo;
-}
-
-// On B200 the integer/logic instructions (PRMT, LOP3, MOV, IADD3 ...) take their cycles from the same datapath
-// as the FP32 instructions (tools/mix_rates.cu: FFMA2 + LOP3 times add up, FFMA2 + DADD overlap), and the FP32
-// datapath is what bounds this kernel.  So a 32-bit word of two samples is turned into two exact doubles on the
-// conversion and FP64 pipes alone: I2F.F64.U32, then hi = RZ(x*2^-16 + 2^52) - 2^52, lo = x - 65536*hi.
-struct D2 { double lo, hi; };
-__device__ __forceinline__ D2 split_word(uint32_t w)
-{
-    const double x = __uint2double_rn(w); // I2F.F64.U32: one issue slot (the magic-number form costs MOV + DADD)
-    D2 r;
-    r.hi = __dadd_rn(__fma_rz(x, 1.52587890625e-05, 4503599627370496.0), -4503599627370496.0);
-    r.lo = __fma_rn(r.hi, -65536.0, x);
-    return r;
-}
-// RRC of an exact sample value.  MODE 1: every (k,b) of the warp is >= 0 and k*65535+b < 2^31: truncation is the
-// low word of RZ(v + 2^52).  MODE 2: general (sign / range handling exactly like x86 cvttsd2si).  The low 16
-// bits of the result are taken by the consumer (I2F.U16 / PRMT).
-template <int MODE>
-__device__ __forceinline__ uint32_t rrc_d(double sd, double k, double b)
-{
-    const double v = __dadd_rn(__dmul_rn(k, sd), b);
-    if (MODE == 1) return (uint32_t)__double2loint(__dadd_rz(v, 4503599627370496.0));
-    const uint32_t hi = (uint32_t)__double2hiint(v);
-    if (hi < 0x41E00000u) return (uint32_t)__double2loint(__dadd_rz(v, 4503599627370496.0));
-    return (uint32_t)((v > -2147483649.0 && v < 2147483648.0) ? __double2int_rz(v) : (int)0x80000000);
-}
+using namespace tmaw;
 
 // 4 consecutive samples that start DM halfwords into the aligned 8-byte shared-memory word at `a`, as floats
 // (after byte swap and RRC).  The TMA unit only accepts box origins on 16-byte boundaries of a tensor row
@@ -511,6 +424,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pan_fast_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+} // namespace panfast
+
+namespace tmaw {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -528,19 +444,26 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-int fast_encode_tmap(CUtensorMap *tm, const void *base, int w, int64_t n_rows, int64_t pitch_bytes)
+int encode_tmap_u32(CUtensorMap *tm, const void *base, int w, int64_t n_rows, int64_t pitch_bytes, int box_w32, int box_rows)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(OIP_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)(w / 2), (cuuint64_t)n_rows}; // 32-bit elements = sample pairs
     const cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
-    const cuuint32_t box[2] = {BOX_W, RC};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w32, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(OIP_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return OIP_OK;
+}
+} // namespace tmaw
+
+namespace panfast {
+int fast_encode_tmap(CUtensorMap *tm, const void *base, int w, int64_t n_rows, int64_t pitch_bytes)
+{
+    return tmaw::encode_tmap_u32(tm, base, w, n_rows, pitch_bytes, BOX_W, RC);
 }
 
 int fast_launch(oip_ctx *ctx, const FastParams &P, int64_t n_ctas)

@@ -8,6 +8,14 @@ from opticalimageprocessor_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["fast", "generic"], autouse=True)
+def mss_mode(request, ctx):
+    """every test runs twice: planner splits work between mss_fast_kernel and band_align_kernel / generic kernel only"""
+    ctx.set_option("mss_fast", 1 if request.param == "fast" else 0)
+    yield request.param
+    ctx.set_option("mss_fast", 1)
+
+
 def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -78,3 +86,25 @@ def test_stitch_tiff_geometry(ctx, oracle_mod):
         want = oracle_mod.stitch_concat_c4(imgs, f, bm)
         got = ops.stitch_tiff_geometry(ctx, [_dev(i) for i in imgs], f, bm).cpu().numpy()
         assert np.array_equal(got, want)
+
+
+def test_band_align_long_section_reference_geometry(ctx, oracle_mod):
+    """reference geometry (3072 px bands, 20000-line sections, 520 overlap) across two sections and several
+    power-of-two row crossings of the map; small tiles so that every fast / generic seam is exercised"""
+    from opticalimageprocessor_b200 import ops
+    rng = np.random.default_rng(31)
+    lines, wb = 21600, 3072
+    mixed = rng.integers(0, 4096, (lines, 4 * wb), dtype=np.uint16)
+    kbs = [synth.rrc_coeffs(wb, 200 + b) for b in range(4)]
+    kbs[2][::9, 1] = -20.5          # general RRC mode on one band
+    cX, cY = _coeffs(1.0)
+    n_w, want = _oracle_full(oracle_mod, mixed, kbs, cX, cY)
+    ctx.set_option("mss_fast_rows", 61)
+    try:
+        n_g, got = ops.band_align(ctx, _dev(mixed), wb, [_dev(k) for k in kbs], cX, cY)
+    finally:
+        ctx.set_option("mss_fast_rows", 128)
+    assert n_g == n_w
+    got = got.cpu().numpy()
+    bad = np.argwhere(got[:n_g] != want[:n_w])
+    assert bad.size == 0, f"{len(bad)} samples differ, first {bad[:5].tolist()}"

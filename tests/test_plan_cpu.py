@@ -104,3 +104,42 @@ def test_odd_fold_keeps_store_alignment(lib):
     fast_cols = np.where((cover == 2).any(axis=0))[0]
     runs = np.split(fast_cols, np.where(np.diff(fast_cols) > 1)[0] + 1)
     assert all(r[0] % 4 == 0 for r in runs)
+
+
+# ------------------------------------------------------------------------------------------ MSS planner
+def _mss_desc(wb, lines, lps=20000, overlap=520, off=0, keep=False, min_lines=1500, scale=1.0):
+    from opticalimageprocessor_b200.capi import MssDesc
+    d = MssDesc()
+    d.fmt, d.wb, d.lines, d.pitch_px = capi.FMT_LE16, wb, lines, 4 * wb
+    for b in range(4):
+        d.d_kb[b] = 0x7D0000000000 + b * (1 << 24)
+        d.cX[2 * b], d.cX[2 * b + 1] = 0.8 + 0.1 * b, -1.5e-4 * (b + 1) * scale
+        d.cY[3 * b], d.cY[3 * b + 1], d.cY[3 * b + 2] = -3.2 + b, 2e-4 * (b + 1) * scale, -1e-8 * (b - 1.5) * scale
+    d.lines_per_section, d.line_offset, d.overlap, d.keep_leading, d.min_process_lines = lps, off, overlap, int(keep), min_lines
+    return d
+
+
+@pytest.mark.parametrize("wb,lines,lps,overlap,off,keep,scale", [(3072, 2400, 20000, 520, 0, False, 1.0), (96, 700, 300, 40, 0, True, 10.0),
+                                                                  (512, 650, 256, 32, 10, False, 1.0), (1000, 900, 333, 17, 5, False, 3.0)])
+def test_mss_every_sample_planned_once(lib, wb, lines, lps, overlap, off, keep, scale):
+    d = _mss_desc(wb, lines, lps, overlap, off, keep, 64, scale)
+    rows_out = lines - off - (0 if keep else overlap)
+    cover = np.zeros((rows_out, wb, 4), np.uint8)
+    st = (C.c_int64 * 4)()
+    capi.check(lib.oip_mss_plan_coverage(C.byref(d), 1, 128, cover.ctypes.data_as(C.c_void_p), st))
+    planned = cover[: (st[0] + st[1]) // (4 * wb)]
+    assert (st[0] + st[1]) % (4 * wb) == 0 and set(np.unique(planned)) <= {1, 2}, np.unique(planned, return_counts=True)
+    assert not cover[planned.shape[0]:].any()            # rows the reference never writes stay untouched
+    if wb >= 512:
+        assert st[1] > 0.5 * (st[0] + st[1]), list(st)
+    st0 = (C.c_int64 * 4)()
+    capi.check(lib.oip_mss_plan_coverage(C.byref(d), 0, 128, None, st0))
+    assert st0[1] == 0 and st0[0] == st[0] + st[1]
+
+
+def test_mss_reference_geometry_is_mostly_fast(lib):
+    """C3-like: 3072-px bands, 20000-line sections: only the power-of-two row zones and band edges stay generic"""
+    d = _mss_desc(3072, 40000)
+    st = (C.c_int64 * 4)()
+    capi.check(lib.oip_mss_plan_coverage(C.byref(d), 1, 128, None, st))
+    assert st[1] > 0.98 * (st[0] + st[1]), list(st)
