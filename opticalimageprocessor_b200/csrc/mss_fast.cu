@@ -94,7 +94,11 @@ __device__ __forceinline__ f2 shfl_down_f2(f2 v, int d)
     return ((f2)hi << 32) | lo;
 }
 
-template <int MODE, bool SWAP>
+// EDGE: the tile touches the band's left / right border: source columns outside [0, wb) are zero (cv::remap's
+// BORDER_CONSTANT on the band plane; in the mixed line they hold the neighbour band) and output columns whose 4x4
+// footprint leaves the band use OpenCV's border accumulation order (one flat chain from 0).  Both sums
+// are computed from the same products and selected per column.
+template <int MODE, bool SWAP, bool EDGE>
 __device__ __forceinline__ void mss_tile(const Params &P, const FTile &T, const WarpCtx &C)
 {
     const int lane = C.lane, ns = C.ns, b = T.band, wb = P.wb;
@@ -107,7 +111,10 @@ __device__ __forceinline__ void mss_tile(const Params &P, const FTile &T, const 
         for (int c = 0; c < pre; ++c) issue_stage(C, c, x0, T.src_row0 + c * RS);
     }
     // (k,b) of the two detectors this lane converts
-    const int colL = min(T.ix0 + lane, wb - 1), colR = min(T.ix0 + T.nh + lane, wb - 1);
+    const int rawL = T.ix0 + lane, rawR = T.ix0 + T.nh + lane;
+    const int colL = max(0, min(rawL, wb - 1)), colR = max(0, min(rawR, wb - 1));
+    const bool inL = !EDGE || (rawL >= 0 && rawL < wb), inR = !EDGE || (rawR >= 0 && rawR < wb);
+    const bool bordL = EDGE && !(rawL >= 0 && rawL <= wb - 4), bordR = EDGE && !(rawR >= 0 && rawR <= wb - 4);
     double kL = 1.0, bL = 0.0, kR = 1.0, bR = 0.0;
     if (MODE != 0) {
         const double *kbp = P.kb[b];
@@ -115,7 +122,7 @@ __device__ __forceinline__ void mss_tile(const Params &P, const FTile &T, const 
         kR = kbp[2 * colR]; bR = kbp[2 * colR + 1];
     }
     // per-lane weights: w[r][c] = fl32(wy[r] * wx[c]) of my left / right output column
-    const int xl = min(T.x_begin + lane, wb - 1), xr = min(T.x_begin + T.nh + lane, wb - 1);
+    const int xl = max(0, min(T.x_begin + lane, wb - 1)), xr = max(0, min(T.x_begin + T.nh + lane, wb - 1));
     const int fxl = dev_sx(P.cX, b, xl) & 31, fxr = dev_sx(P.cX, b, xr) & 31;
     const int fyl = dev_sy(P.cY, b, xl, T.ya) & 31, fyr = dev_sy(P.cY, b, xr, T.ya) & 31;
     const f2 nz = *reinterpret_cast<const f2 *>(P.tab + 128);
@@ -131,7 +138,7 @@ __device__ __forceinline__ void mss_tile(const Params &P, const FTile &T, const 
     uint16_t *oL = P.out + T.out_off + 4 * lane - 3 * pitch; // output row (m - 3) while source row m is consumed
     uint16_t *oR = oL + 4 * T.nh;
     const int n_rows = T.n_rows;
-    f2 A1 = 0ull, A2 = 0ull, A3 = 0ull;
+    f2 A1 = 0ull, A2 = 0ull, A3 = 0ull, F1 = 0ull, F2 = 0ull, F3 = 0ull;
 
     int slot = 0;
     uint32_t phase = 0;
@@ -152,18 +159,33 @@ __device__ __forceinline__ void mss_tile(const Params &P, const FTile &T, const 
                 fl = (float)(uint16_t)rrc_d<MODE>(__uint2double_rn(sL), kL, bL);
                 fr = (float)(uint16_t)rrc_d<MODE>(__uint2double_rn(sR), kR, bR);
             }
+            if (EDGE) {
+                fl = inL ? fl : 0.f;
+                fr = inR ? fr : 0.f;
+            }
             f2 win[4];
             win[0] = pk(fl, fr);
 #pragma unroll
             for (int j = 1; j < 4; ++j) win[j] = shfl_down_f2(win[0], j);
             // per row ((s0*w0 + s1*w1) + s2*w2) + s3*w3, rows accumulated in order 0,1,2,3 (OpenCV interior order)
-            auto dot = [&](const f2(&Wr)[4]) {
-                return add2(add2(add2(mul2(win[0], Wr[0], nz), mul2(win[1], Wr[1], nz)), mul2(win[2], Wr[2], nz)), mul2(win[3], Wr[3], nz));
-            };
-            const f2 out = add2(A3, dot(W[3]));
-            A3 = add2(A2, dot(W[2]));
-            A2 = add2(A1, dot(W[1]));
-            A1 = dot(W[0]);
+            f2 d[4], f[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const f2 p0 = mul2(win[0], W[r][0], nz), p1 = mul2(win[1], W[r][1], nz), p2 = mul2(win[2], W[r][2], nz), p3 = mul2(win[3], W[r][3], nz);
+                d[r] = add2(add2(add2(p0, p1), p2), p3);
+                if (EDGE) {
+                    const f2 prev = r == 0 ? 0ull : (r == 1 ? F1 : (r == 2 ? F2 : F3));
+                    f[r] = add2(add2(add2(add2(prev, p0), p1), p2), p3);
+                }
+            }
+            f2 out = add2(A3, d[3]);
+            A3 = add2(A2, d[2]);
+            A2 = add2(A1, d[1]);
+            A1 = d[0];
+            if (EDGE) {
+                out = pk(bordL ? lo_of(f[3]) : lo_of(out), bordR ? hi_of(f[3]) : hi_of(out));
+                F3 = f[2]; F2 = f[1]; F1 = f[0];
+            }
             const int m = c * RS + rr;
             const bool rows_ok = (unsigned)(m - 3) < (unsigned)n_rows;
             if (rows_ok && actL) *oL = (uint16_t)cast_u16(lo_of(out));
@@ -199,7 +221,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) mss_fast_kernel(const __grid_co
     int mode = 0;
     if (P.kb[T.band]) {
         const double *kbp = P.kb[T.band];
-        const int cl = min(T.ix0 + lane, P.wb - 1), cr = min(T.ix0 + T.nh + lane, P.wb - 1);
+        const int cl = max(0, min(T.ix0 + lane, P.wb - 1)), cr = max(0, min(T.ix0 + T.nh + lane, P.wb - 1));
         bool general = false;
         const int cols[2] = {cl, cr};
 #pragma unroll
@@ -210,10 +232,15 @@ __global__ void __launch_bounds__(WARPS * 32, 4) mss_fast_kernel(const __grid_co
         mode = __any_sync(0xffffffffu, general) ? 2 : 1;
     }
     const bool swap = P.swap != 0;
-#define OIP_MSS_GO(M)                                  \
-    do {                                               \
-        if (swap) mss_tile<M, true>(P, T, C);          \
-        else mss_tile<M, false>(P, T, C);              \
+#define OIP_MSS_GO(M)                                                   \
+    do {                                                                \
+        if (T.pad) {                                                    \
+            if (swap) mss_tile<M, true, true>(P, T, C);                 \
+            else mss_tile<M, false, true>(P, T, C);                     \
+        } else {                                                        \
+            if (swap) mss_tile<M, true, false>(P, T, C);                \
+            else mss_tile<M, false, false>(P, T, C);                    \
+        }                                                               \
     } while (0)
     if (mode == 1) OIP_MSS_GO(1);
     else if (mode == 0) OIP_MSS_GO(0);
@@ -263,6 +290,9 @@ void plan(const oip_mss_desc *d, const std::vector<Section> &secs, bool fast, in
                 const int p = k == 0 ? 0 : (1 << k);
                 zones.push_back({p - (int)std::ceil(cmax) - 2, p - (int)std::floor(cmin) + 3});
             }
+            // rows whose footprint can leave the section Mat at its top / bottom: border order, generic
+            zones.push_back({-(1 << 30), 3 - (int)std::floor(cmin)});
+            zones.push_back({S.rows - 6 - (int)std::ceil(cmax), 1 << 30});
             std::sort(zones.begin(), zones.end());
             int y = S.y0;
             size_t zi = 0;
@@ -286,7 +316,7 @@ void plan(const oip_mss_desc *d, const std::vector<Section> &secs, bool fast, in
                         const int sye = host_sy(Ay[x], ye - 1);
                         D[x] = sat_short(sya[x] >> 5) - 1 - ya;
                         const int ix = ixo[x] + x;
-                        ok[x] = sye == sya[x] + 32 * (ye - 1 - ya) && ix >= 0 && ix + 3 <= wb - 1 && ya + D[x] >= 0 &&
+                        ok[x] = sye == sya[x] + 32 * (ye - 1 - ya) && ix > -30000 && ix < 30000 && ya + D[x] >= 0 &&
                                 (ye - 1) + D[x] + 3 <= S.rows - 1;
                     }
                     int x = 0;
@@ -300,7 +330,6 @@ void plan(const oip_mss_desc *d, const std::vector<Section> &secs, bool fast, in
                         }
                         int xe = x + 1;
                         while (xe < wb && ok[xe] && ixo[xe] == ixo[x] && D[xe] == D[x]) ++xe;
-                        if (xe - x < 8) { emit_generic(tiles, S, b, x, xe, ya, ye); x = xe; continue; }
                         // strips of <= 2*NH columns, equal widths
                         const int width = xe - x, n_s = (width + 2 * NH - 1) / (2 * NH);
                         int xs = x;
@@ -309,6 +338,8 @@ void plan(const oip_mss_desc *d, const std::vector<Section> &secs, bool fast, in
                             FTile t{};
                             t.band = b; t.x_begin = xs; t.nh = (wS + 1) / 2; t.n_right = wS - t.nh;
                             t.ix0 = ixo[x] + xs; t.ya = ya; t.n_rows = ye - ya;
+                            // pad = 1: EDGE variant (some footprint of the strip, window lanes included, leaves the band)
+                            t.pad = (t.ix0 < 0 || t.ix0 + 2 * t.nh + 2 > wb - 1) ? 1 : 0;
                             t.src_row0 = S.sec_off + ya + D[x];
                             t.out_off = ((S.dst_row0 + (ya - S.y0)) * wb + xs) * 4 + b;
                             fl.push_back(t);

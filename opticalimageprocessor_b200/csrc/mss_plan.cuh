@@ -26,7 +26,7 @@ struct FTile {
     int32_t ix0;       // band-relative source column of x_begin's first tap
     int32_t ya;        // section-local row of output row 0 (the device derives every column's phase from it)
     int32_t n_rows;
-    int32_t pad;
+    int32_t pad;       // 1: the strip touches the band border (EDGE variant of the kernel)
     int64_t src_row0;  // line of the MSS buffer that holds the first tap row of output row 0
     int64_t out_off;   // element offset of (output row 0, x_begin, band) in the interleaved raster
 };
