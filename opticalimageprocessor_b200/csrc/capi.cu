@@ -106,7 +106,8 @@ void oip_ctx_destroy(oip_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     oip::host_pipe_destroy(ctx);
-    if (ctx->d_plan) cudaFree(ctx->d_plan);
+    for (oip_pan_plan &pl : ctx->pan_plans)
+        if (pl.d_plan) cudaFree(pl.d_plan);
     if (ctx->d_mss_plan) cudaFree(ctx->d_mss_plan);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -124,11 +125,12 @@ int oip_ctx_set_option(oip_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "pan_fast")) ctx->pan_fast = value != 0;
     else if (!strcmp(name, "pan_fast_stages") && value >= 2 && value <= 8) ctx->pan_fast_stages = (int)value;
     else if (!strcmp(name, "pan_fast_minb") && value >= 3 && value <= 4) ctx->pan_fast_minb = (int)value;
+    else if (!strcmp(name, "host_block_rows") && value >= 64 && value <= (1 << 20)) ctx->host_block_rows = (int)value;
     else if (!strcmp(name, "mss_fast")) ctx->mss_fast = value != 0;
     else if (!strcmp(name, "mss_fast_rows") && value >= 16 && value <= 32768) ctx->mss_fast_rows = (int)value;
     else if (!strcmp(name, "pan_fast_rows") && value >= 16 && value <= 32768) ctx->pan_fast_rows = (int)value;
     else return oip::fail(OIP_E_INVALID, "unknown option or value out of range: %s=%lld", name, (long long)value);
-    ctx->plan_key.clear();
+    for (oip_pan_plan &pl : ctx->pan_plans) pl.key.clear(); // buffers are reused
     ctx->mss_plan_key.clear();
     return OIP_OK;
 }

@@ -4,13 +4,14 @@
 // block b-1's output travels device->host on a third stream (pinned buffers make all three
 // overlap).  This is what the CLI uses for files and what bench.py reports as "e2e".
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 #include "oip_common.cuh"
 
 namespace oip {
 
 constexpr int HP_SLOTS = 3;
-constexpr int64_t HP_BLOCK_ROWS = 2048;
 
 struct HostPipe {
     cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -74,6 +75,15 @@ void host_pipe_destroy(oip_ctx *ctx)
     ctx->host_pipe = nullptr;
 }
 
+// rows x row_bytes between pitched buffers; one linear copy when both sides are dense (the 2-D DMA path is slower:
+// 34 GB/s against 47 GB/s per direction on this box, tools/pcie_probe.py)
+static cudaError_t copy_rows(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, size_t rows,
+                             cudaMemcpyKind kind, cudaStream_t st)
+{
+    if (dpitch == row_bytes && spitch == row_bytes) return cudaMemcpyAsync(dst, src, row_bytes * rows, kind, st);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, kind, st);
+}
+
 static int64_t row_bytes(int fmt, int w)
 {
     switch (fmt) {
@@ -114,9 +124,26 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
         d_kb[i] = (const double *)hp->d_kb[i];
     }
 
+    // block schedule: small blocks at both ends (the first H2D and the last D2H cannot overlap with anything), the
+    // configured size in between
+    const int64_t HP_BLOCK_ROWS = ctx->host_block_rows;
+    std::vector<int64_t> sizes;
+    {
+        int64_t left = h->n_rows;
+        std::vector<int64_t> head, tail;
+        for (int64_t b = std::min<int64_t>(256, HP_BLOCK_ROWS); b < HP_BLOCK_ROWS && left >= 4 * b; b *= 2) {
+            head.push_back(b);
+            tail.push_back(b);
+            left -= 2 * b;
+        }
+        sizes = head;
+        while (left > 0) { sizes.push_back(std::min(left, HP_BLOCK_ROWS)); left -= sizes.back(); }
+        sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
+    }
     int blk = 0;
-    for (int64_t r0 = h->row0; r0 < h->row0 + h->n_rows; r0 += HP_BLOCK_ROWS, ++blk) {
-        const int64_t nr = std::min<int64_t>(HP_BLOCK_ROWS, h->row0 + h->n_rows - r0);
+    int64_t r0 = h->row0;
+    for (size_t bi = 0; bi < sizes.size(); r0 += sizes[bi], ++bi, ++blk) {
+        const int64_t nr = sizes[bi];
         HostPipe::Slot &S = hp->slot[blk % HP_SLOTS];
         oip_pan_desc d = *h;
         d.row0 = r0;
@@ -147,14 +174,14 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
             o.d_kb = d_kb[i];
             o.n_seg = 0;
             if (n_main > 0) {
-                OIP_CUDA(cudaMemcpy2DAsync(dst, (size_t)pitch_d, (const uint8_t *)hs.base + (first - hs.row0) * hs.pitch_bytes,
-                                           (size_t)hs.pitch_bytes, (size_t)rb, (size_t)n_main, cudaMemcpyHostToDevice, hp->h2d));
+                OIP_CUDA(copy_rows(dst, (size_t)pitch_d, (const uint8_t *)hs.base + (first - hs.row0) * hs.pitch_bytes,
+                                   (size_t)hs.pitch_bytes, (size_t)rb, (size_t)n_main, cudaMemcpyHostToDevice, hp->h2d));
                 o.seg[o.n_seg++] = {dst, first, n_main, pitch_d};
             }
             if (n_stale > 0) {
                 uint8_t *dst2 = dst + n_main * pitch_d;
-                OIP_CUDA(cudaMemcpy2DAsync(dst2, (size_t)pitch_d, (const uint8_t *)hs.base + (sfirst - hs.row0) * hs.pitch_bytes,
-                                           (size_t)hs.pitch_bytes, (size_t)rb, (size_t)n_stale, cudaMemcpyHostToDevice, hp->h2d));
+                OIP_CUDA(copy_rows(dst2, (size_t)pitch_d, (const uint8_t *)hs.base + (sfirst - hs.row0) * hs.pitch_bytes,
+                                   (size_t)hs.pitch_bytes, (size_t)rb, (size_t)n_stale, cudaMemcpyHostToDevice, hp->h2d));
                 o.seg[o.n_seg++] = {dst2, sfirst, n_stale, pitch_d};
             }
             if (o.n_seg == 0) { // nothing to read (can only happen for degenerate geometry): keep a valid segment
@@ -170,13 +197,14 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
         OIP_CUDA(cudaStreamWaitEvent(ctx->stream, S.out_done, 0)); // previous D2H of this slot finished
         d.d_out = (uint16_t *)S.d_out;
         d.out_pitch_px = out_w;
-        rc = oip_pan_pipeline(ctx, &d);
+        static const bool skip_kernels = getenv("OIP_HP_SKIP_KERNELS") != nullptr; // timing experiment: copies only
+        rc = skip_kernels ? OIP_OK : oip_pan_pipeline(ctx, &d);
         if (rc) return rc;
         OIP_CUDA(cudaEventRecord(S.compute_done, ctx->stream));
         // ---- D2H
         OIP_CUDA(cudaStreamWaitEvent(hp->d2h, S.compute_done, 0));
-        OIP_CUDA(cudaMemcpy2DAsync((uint8_t *)h->d_out + (r0 - h->row0) * h->out_pitch_px * 2, (size_t)h->out_pitch_px * 2,
-                                   S.d_out, (size_t)out_w * 2, (size_t)out_w * 2, (size_t)nr, cudaMemcpyDeviceToHost, hp->d2h));
+        OIP_CUDA(copy_rows((uint8_t *)h->d_out + (r0 - h->row0) * h->out_pitch_px * 2, (size_t)h->out_pitch_px * 2, S.d_out,
+                           (size_t)out_w * 2, (size_t)out_w * 2, (size_t)nr, cudaMemcpyDeviceToHost, hp->d2h));
         OIP_CUDA(cudaEventRecord(S.out_done, hp->d2h));
     }
     OIP_CUDA(cudaStreamSynchronize(hp->d2h));

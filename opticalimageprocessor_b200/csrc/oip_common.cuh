@@ -10,6 +10,16 @@
 
 #include "../../include/oip_b200.h"
 
+// one cached oip_pan_pipeline plan (device-resident tile lists), keyed on everything the split depends on
+struct oip_pan_plan {
+    std::vector<uint8_t> key;
+    void *d_plan = nullptr;
+    size_t cap = 0;
+    int64_t tiles = 0, fast_ctas = 0;
+    size_t fast_off = 0;
+    uint64_t last_use = 0;
+};
+
 struct oip_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -17,13 +27,15 @@ struct oip_ctx {
     int sm_count = 148;
     int64_t launches = 0;
     // cached device-side plan buffers (re-uploaded only when the geometry changes)
-    void *d_plan = nullptr;
-    size_t d_plan_cap = 0;
-    std::vector<uint8_t> plan_key;
+    // (the host-buffer pipeline calls oip_pan_pipeline once per row block: every block keeps its own plan)
+    std::vector<oip_pan_plan> pan_plans;
+    uint64_t plan_clock = 0;
+    void *d_plan = nullptr;      // the plan of the current call (owned by pan_plans)
     int64_t plan_tiles = 0;      // generic tiles (pan_kernel CTAs)
     int64_t plan_fast_ctas = 0;  // pan_fast_kernel CTAs (4 warp-tiles each)
     size_t plan_fast_off = 0;    // byte offset of the FastTile array inside d_plan
     // tunables (oip_ctx_set_option)
+    int host_block_rows = 4096;  // oip_pan_pipeline_host: rows per H2D / compute / D2H block
     int pan_fast = 1;            // 0: everything on the generic kernel
     int pan_fast_stages = 4;     // TMA stages per warp
     int pan_fast_rows = 128;     // output rows per warp-tile
@@ -43,6 +55,8 @@ struct oip_ctx {
     void *h_pinned = nullptr; // small pinned staging for counters / plans
     size_t h_pinned_cap = 0;
     int *d_err = nullptr;     // device-side error flag
+    bool side_stream = true;  // generic tiles on aux_stream (off inside the host-buffer pipeline: its copy streams and the
+                              // side stream can share a hardware queue, which parks the kernel behind a 2 ms copy)
     cudaStream_t aux_stream = nullptr; // side stream of oip_pan_pipeline (generic tiles next to the fast kernel)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool pan_attr_set = false, mss_attr_set = false, fast_attr_set = false;

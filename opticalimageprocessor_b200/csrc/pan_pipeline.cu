@@ -1024,39 +1024,63 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         for (int s = 0; s < d->ccd[i].n_seg; ++s) { key.seg_row0[i][s] = d->ccd[i].seg[s].row0; key.seg_rows[i][s] = d->ccd[i].seg[s].n_rows; }
     }
     const uint8_t *kb = reinterpret_cast<const uint8_t *>(&key);
-    if (ctx->plan_key.size() != sizeof key || memcmp(ctx->plan_key.data(), kb, sizeof key) != 0) {
+    constexpr size_t MAX_PLANS = 96;
+    oip_pan_plan *pl = nullptr;
+    for (oip_pan_plan &c : ctx->pan_plans)
+        if (c.key.size() == sizeof key && memcmp(c.key.data(), kb, sizeof key) == 0) { pl = &c; break; }
+    if (!pl) {
         std::vector<pan::Tile> tiles;
         std::vector<panfast::FastTile> ftiles;
         rc = pan::build_plan(d, fast_ccd, ctx->pan_fast_rows, tiles, ftiles);
         if (rc) return rc;
         pan::upload_tab();
+        // a free slot, else the least recently used one (its buffer may still be read by kernels in flight)
+        for (oip_pan_plan &c : ctx->pan_plans)
+            if (c.key.empty()) { pl = &c; break; }
+        if (!pl && ctx->pan_plans.size() < MAX_PLANS) {
+            ctx->pan_plans.reserve(MAX_PLANS); // pointers into the vector stay valid
+            ctx->pan_plans.emplace_back();
+            pl = &ctx->pan_plans.back();
+        }
+        if (!pl) {
+            pl = &ctx->pan_plans[0];
+            for (oip_pan_plan &c : ctx->pan_plans)
+                if (c.last_use < pl->last_use) pl = &c;
+        }
         const size_t fast_off = (1024 + tiles.size() * sizeof(pan::Tile) + 63) / 64 * 64;
         const size_t bytes = fast_off + ftiles.size() * sizeof(panfast::FastTile) + 64;
-        if (bytes > ctx->d_plan_cap) {
-            if (ctx->d_plan) { OIP_CUDA(cudaStreamSynchronize(ctx->stream)); OIP_CUDA(cudaFree(ctx->d_plan)); ctx->d_plan = nullptr; }
-            OIP_CUDA(cudaMalloc(&ctx->d_plan, bytes * 2));
-            ctx->d_plan_cap = bytes * 2;
+        if (pl->d_plan) OIP_CUDA(cudaStreamSynchronize(ctx->stream)); // a kernel may still read the slot's old plan
+        if (ctx->aux_stream && pl->d_plan) OIP_CUDA(cudaStreamSynchronize(ctx->aux_stream));
+        if (bytes > pl->cap) {
+            if (pl->d_plan) { OIP_CUDA(cudaFree(pl->d_plan)); pl->d_plan = nullptr; pl->cap = 0; }
+            OIP_CUDA(cudaMalloc(&pl->d_plan, bytes + bytes / 4));
+            pl->cap = bytes + bytes / 4;
         }
-        // pageable sources: cudaMemcpyAsync stages them before returning, and the copies are ordered
-        // on the compute stream behind any kernel still reading the previous plan
+        // pageable sources: cudaMemcpyAsync stages them before returning
         float hdr[256] = {};
         memcpy(hdr, pan::g_tab_host, 512);
         hdr[128] = hdr[129] = -0.0f; // run-time (-0.0,-0.0) addend of the packed products, see mul2()
-        OIP_CUDA(cudaMemcpyAsync(ctx->d_plan, hdr, 1024, cudaMemcpyHostToDevice, ctx->stream));
+        OIP_CUDA(cudaMemcpyAsync(pl->d_plan, hdr, 1024, cudaMemcpyHostToDevice, ctx->stream));
         if (!tiles.empty())
-            OIP_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_plan + 1024, tiles.data(), tiles.size() * sizeof(pan::Tile),
+            OIP_CUDA(cudaMemcpyAsync((uint8_t *)pl->d_plan + 1024, tiles.data(), tiles.size() * sizeof(pan::Tile),
                                      cudaMemcpyHostToDevice, ctx->stream));
         if (!ftiles.empty())
-            OIP_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_plan + fast_off, ftiles.data(), ftiles.size() * sizeof(panfast::FastTile),
+            OIP_CUDA(cudaMemcpyAsync((uint8_t *)pl->d_plan + fast_off, ftiles.data(), ftiles.size() * sizeof(panfast::FastTile),
                                      cudaMemcpyHostToDevice, ctx->stream));
-        ctx->plan_key.assign(kb, kb + sizeof key);
-        ctx->plan_tiles = (int64_t)tiles.size();
-        ctx->plan_fast_ctas = (int64_t)(ftiles.size() / panfast::WARPS);
-        ctx->plan_fast_off = fast_off;
+        pl->key.assign(kb, kb + sizeof key);
+        pl->tiles = (int64_t)tiles.size();
+        pl->fast_ctas = (int64_t)(ftiles.size() / panfast::WARPS);
+        pl->fast_off = fast_off;
     }
+    pl->last_use = ++ctx->plan_clock;
+    ctx->d_plan = pl->d_plan;
+    ctx->plan_tiles = pl->tiles;
+    ctx->plan_fast_ctas = pl->fast_ctas;
+    ctx->plan_fast_off = pl->fast_off;
+    if (ctx->plan_tiles == 0 && ctx->plan_fast_ctas == 0) return OIP_OK;
 
     // the two kernels write disjoint pixels: the (small) generic launch runs on a side stream next to the fast one
-    const bool fork = ctx->plan_fast_ctas > 0 && ctx->plan_tiles > 0;
+    const bool fork = ctx->plan_fast_ctas > 0 && ctx->plan_tiles > 0 && ctx->side_stream;
     if (fork) {
         if (!ctx->aux_stream) {
             OIP_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
