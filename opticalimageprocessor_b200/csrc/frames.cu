@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) unpack_frames_kernel(const __grid_constan
     const int64_t *ent = P.tab + fr * 41;
     const int64_t frame_off = ent[0];
     if (item == 40) {
-        if (!P.aux) return;
+        if (!P.aux || blockIdx.z != 0) return;
         const int64_t nb = 192 * (int64_t)TL;
         uint8_t *dst = P.aux + fr * nb;
         if (frame_off < 0) {
@@ -547,16 +547,42 @@ __global__ void __launch_bounds__(256) unpack_frames_kernel(const __grid_constan
     const int64_t toff = ent[1 + item];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (frame_off < 0 || toff < 0) { // zero-filled gap frame (ref :302-311)
+        if (blockIdx.z != 0) return;
         for (int y = wid; y < TL; y += nw)
             for (int x = lane; x < TC; x += 32) dst[(int64_t)y * W + x] = 0;
         return;
     }
     const uint8_t *src = P.imdt + toff;
+    // blockIdx.z splits the tile's lines so that a handful of frames still fills the GPU
+    const int y_lo = (int)(((int64_t)TL * blockIdx.z) / gridDim.z), y_hi = (int)(((int64_t)TL * (blockIdx.z + 1)) / gridDim.z);
     const bool a4 = ((((uintptr_t)src) & 3) == 0) && (TC % 2 == 0) && ((((uintptr_t)dst) & 3) == 0);
-    for (int y = wid; y < TL; y += nw) {
+    // fast form: 16-byte output chunks (4 source words each; the stream is only 4-byte aligned), 4 chunks in flight per lane
+    const bool a16 = a4 && (TC % 8 == 0) && ((((uintptr_t)dst) & 15) == 0) && ((W * 2) % 16 == 0);
+    for (int y = y_lo + wid; y < y_hi; y += nw) {
         const uint8_t *sl = src + (int64_t)y * TC * 2;
         uint16_t *dl = dst + (int64_t)y * W;
-        if (a4) {
+        if (a16) {
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(sl);
+            uint4 *dq = reinterpret_cast<uint4 *>(dl);
+            const int nq = TC / 8;
+            for (int q0 = 0; q0 < nq; q0 += 128) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + lane + 32 * u;
+                    if (q < nq) {
+                        v[u].x = __ldg(sw + 4 * q);     v[u].y = __ldg(sw + 4 * q + 1);
+                        v[u].z = __ldg(sw + 4 * q + 2); v[u].w = __ldg(sw + 4 * q + 3);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + lane + 32 * u;
+                    if (q < nq)
+                        stg_na_v4(dq + q, make_uint4(bswap16x2(v[u].x), bswap16x2(v[u].y), bswap16x2(v[u].z), bswap16x2(v[u].w))); // :387-392
+                }
+            }
+        } else if (a4) {
             for (int x = lane; x < TC / 2; x += 32)
                 reinterpret_cast<uint32_t *>(dl)[x] = bswap16x2(reinterpret_cast<const uint32_t *>(sl)[x]); // :387-392
         } else {
@@ -906,7 +932,8 @@ extern "C" int oip_unpack_frames(oip_ctx *ctx, const uint8_t *d_imdt, size_t n_b
     UnpackParams P{};
     P.imdt = d_imdt; P.tab = (const int64_t *)ctx->d_scratch; P.aux = d_aux; P.pan = d_pan; P.mss = d_mss;
     P.tile_cols = geom->tile_cols; P.tile_lines = geom->tile_lines; P.n_frames = n_frames;
-    unpack_frames_kernel<<<dim3((unsigned)n_frames, 41), 256, 0, ctx->stream>>>(P);
+    const unsigned zsplit = (unsigned)std::max(1, std::min(geom->tile_lines / 8, (int)(4096 / std::max<int64_t>(1, n_frames * 41) + 1)));
+    unpack_frames_kernel<<<dim3((unsigned)n_frames, 41, zsplit), 256, 0, ctx->stream>>>(P);
     OIP_CUDA(cudaGetLastError());
     ctx->launches++;
     return OIP_OK;
