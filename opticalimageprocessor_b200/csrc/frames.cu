@@ -4,6 +4,7 @@
 // parallel candidate evaluation + a short dependent walk over the (tiny) candidate table.
 #include <algorithm>
 
+#include "crc_bitslice.cuh"
 #include "oip_common.cuh"
 
 namespace oip {
@@ -70,6 +71,35 @@ __device__ __forceinline__ uint32_t warp_crc16(const CrcPlan &P, GetByte get)
     const int b0 = lane * P.cs, b1 = min(P.len, b0 + P.cs);
     uint32_t r = 0;
     for (int i = b0; i < b1; ++i) r = crc16_byte(r, get(i));
+    uint32_t c = gfmul16(r, P.mul[lane]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
+    return c ^ P.init_term;
+}
+
+// Same split, message held in shared memory: lane l reads its 28-byte piece as 7 (+1) aligned words and runs the
+// byte recurrence out of registers (no byte loads, fully unrolled).  w32 = aligned word that holds message byte 0,
+// sh = byte offset (0..3) of message byte 0 inside it; up to 3 bytes past the piece are read (callers pad).
+// Needs P.cs == 28 (true for the two frame formats: 890 and 876 message bytes).
+__device__ __forceinline__ uint32_t warp_crc16_words(const CrcPlan &P, const uint32_t *w32, int sh)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t *w = w32 + 7 * lane;
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = w[j];
+    const int nb = max(0, min(28, P.len - 28 * lane));
+    const uint32_t s8 = 8u * (uint32_t)sh;
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const uint32_t m = __funnelshift_r(v[j], v[j + 1], s8);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t nr = crc16_byte(r, (m >> (8 * b)) & 0xFFu);
+            r = 4 * j + b < nb ? nr : r;
+        }
+    }
     uint32_t c = gfmul16(r, P.mul[lane]);
 #pragma unroll
     for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
@@ -172,11 +202,15 @@ static size_t scan_scratch_elems(int64_t n)
 }
 
 // =============================================================================================
-// AOS: sync search + frame validation, one CTA per 16 KiB chunk staged in shared memory
+// AOS: sync search + frame validation, one CTA per 32 KiB chunk staged in shared memory.
+// 32 KiB = 32 frames of a clean downlink = one bit-sliced CRC batch (crc_bitslice.cuh).
 // =============================================================================================
-constexpr int CH = 16384;           // file bytes owned by a CTA
+constexpr int CH = 32768;           // file bytes owned by a CTA
 constexpr int CH_HALO = 1024;       // a frame starting at the last owned byte ends here
-constexpr int AOS_T = 256;
+constexpr int CH_FRONT = 16;        // bytes in front of the chunk (the CRC span starts 2 bytes before a candidate)
+constexpr int AOS_T = 128;
+constexpr int AOS_WPT = CH / 32 / AOS_T; // bitmap words per thread (8)
+constexpr size_t AOS_SMEM = (size_t)CH_FRONT + CH + CH_HALO + 16 + (CH / 32) * 4 + (CH / 4) * 2;
 
 struct ChunkInfo {
     uint32_t slot0, count;
@@ -187,64 +221,89 @@ __global__ void __launch_bounds__(AOS_T) aos_scan_kernel(const uint8_t *__restri
                                                          uint32_t cap, ChunkInfo *info, uint64_t *cand_off,
                                                          int8_t *cand_st)
 {
-    __shared__ __align__(16) uint8_t s_buf[CH + CH_HALO + 16];
-    __shared__ uint32_t s_bits[CH / 32];
-    __shared__ uint16_t s_cand[CH / 4];
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    uint8_t *s_buf = s_dyn + CH_FRONT;                                                  // chunk byte 0 (16-byte aligned)
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_dyn + CH_FRONT + CH + CH_HALO + 16);
+    uint16_t *s_cand = reinterpret_cast<uint16_t *>(s_bits + CH / 32);
     __shared__ uint32_t s_slot0, s_total;
+    __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x;
     const int64_t c0 = (int64_t)blockIdx.x * CH;
     const int avail = (int)min((int64_t)(CH + CH_HALO), n - c0); // bytes of the file in s_buf
 
-    // ---- stage the chunk (+halo).  16-byte vector loads when the buffer allows it.
-    if ((((uintptr_t)buf) & 15) == 0) {
-        const int nv = avail >> 4;
-        const uint4 *src = reinterpret_cast<const uint4 *>(buf + c0);
-        for (int i = tid; i < nv; i += AOS_T) reinterpret_cast<uint4 *>(s_buf)[i] = ldg_nc_v4(src + i);
-        for (int i = (nv << 4) + tid; i < avail; i += AOS_T) s_buf[i] = buf[c0 + i];
+    // ---- stage the chunk (+halo): one bulk copy (TMA unit, no thread work, the whole chunk in flight at once) when
+    //      the buffer allows it, else a load loop
+    const bool bulk = (((uintptr_t)buf) & 15) == 0 && (avail & 15) == 0;
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            fence_mbar_init();
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)avail);
+            bulk_g2s(s_buf, buf + c0, (uint32_t)avail, &s_bar);
+        }
     } else {
         for (int i = tid; i < avail; i += AOS_T) s_buf[i] = buf[c0 + i];
     }
     for (int i = avail + tid; i < CH + CH_HALO + 16; i += AOS_T) s_buf[i] = 0;
+    if (tid < CH_FRONT) s_dyn[tid] = 0;
     for (int i = tid; i < CH / 32; i += AOS_T) s_bits[i] = 0;
-    __syncthreads();
+    __syncthreads(); // also publishes the barrier initialisation
+    if (bulk) {
+        while (!mbar_try_wait(&s_bar, 0)) {}
+    }
 
     // ---- sync search "1A CF FC 1D" (ref aux_separator.h:29, :622-625); a hit must leave room for a
     //      whole frame (p + 1024 <= n), anything later can never be accepted or counted
     const int own = (int)min((int64_t)CH, n - c0);
     const uint32_t *w32 = reinterpret_cast<const uint32_t *>(s_buf);
-    for (int wi = tid; wi < CH / 4; wi += AOS_T) {
-        const uint32_t w = w32[wi];
-        const uint32_t x = w ^ 0x1A1A1A1Au;
-        if ((x - 0x01010101u) & ~x & 0x80808080u) { // some byte equals 0x1A
-            const uint32_t nx = w32[wi + 1];
+    for (int qi = tid; qi < CH / 16; qi += AOS_T) {
+        // 16 bytes per step.  Filter: a 0x1A byte followed by a 0xCF byte (zero-byte trick on both, no false negatives),
+        // rare enough (2^-16 per position) that a warp almost never enters the exact comparison.
+        const uint4 q4 = reinterpret_cast<const uint4 *>(s_buf)[qi];
+        const uint32_t nx4 = w32[4 * qi + 4];
+        const uint32_t wv[5] = {q4.x, q4.y, q4.z, q4.w, nx4};
+        uint32_t z2[5], any = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t v = __funnelshift_r(w, nx, 8 * b);
-                const int p = wi * 4 + b;
-                if (v == 0x1DFCCF1Au && p < own && c0 + p + 1024 <= n) atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t x = wv[k] ^ 0xCFCFCFCFu;
+            z2[k] = (x - 0x01010101u) & ~x;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t x = wv[k] ^ 0x1A1A1A1Au;
+            any |= (x - 0x01010101u) & ~x & __funnelshift_r(z2[k], z2[k + 1], 8);
+        }
+        if (any & 0x80808080u) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t v = __funnelshift_r(wv[k], wv[k + 1], 8 * b);
+                    const int p = qi * 16 + k * 4 + b;
+                    if (v == 0x1DFCCF1Au && p < own && c0 + p + 1024 <= n) atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+                }
             }
         }
     }
     __syncthreads();
 
-    // ---- ordered list of hits (bitmap -> positions), two bitmap words per thread
+    // ---- ordered list of hits (bitmap -> positions), AOS_WPT consecutive bitmap words per thread
     {
-        const uint32_t m0 = s_bits[2 * tid], m1 = s_bits[2 * tid + 1];
-        const uint32_t cnt = __popc(m0) + __popc(m1);
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < AOS_WPT; ++k) cnt += __popc(s_bits[AOS_WPT * tid + k]);
         uint32_t tot;
         uint32_t at = block_exclusive_scan(cnt, &tot);
-        uint32_t m = m0;
-        while (m) {
-            int b = __ffs(m) - 1;
-            m &= m - 1;
-            s_cand[at++] = (uint16_t)(2 * tid * 32 + b);
-        }
-        m = m1;
-        while (m) {
-            int b = __ffs(m) - 1;
-            m &= m - 1;
-            s_cand[at++] = (uint16_t)((2 * tid + 1) * 32 + b);
+        if (cnt) {
+            for (int k = 0; k < AOS_WPT; ++k) {
+                uint32_t m = s_bits[AOS_WPT * tid + k];
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    s_cand[at++] = (uint16_t)((AOS_WPT * tid + k) * 32 + b);
+                }
+            }
         }
         if (tid == 0) {
             s_total = tot;
@@ -257,23 +316,47 @@ __global__ void __launch_bounds__(AOS_T) aos_scan_kernel(const uint8_t *__restri
     const uint32_t total = s_total, slot0 = s_slot0;
     if (slot0 + total > cap) return; // table too small: the host re-runs with the exact size
 
-    // ---- ValidateAosFrame (ref aux_separator.h:658-690), one warp per candidate
-    const int lane = tid & 31, wid = tid >> 5;
-    for (uint32_t j = wid; j < total; j += AOS_T / 32) {
-        const uint8_t *f = s_buf + s_cand[j];
+    // ---- ValidateAosFrame (ref aux_separator.h:658-690): a warp takes 32 candidates, one per lane
+    // (the warp that takes the first batch rotates with the CTA index: warp w of every CTA shares one of the SM's four
+    //  schedulers, and a clean chunk has exactly one batch)
+    const int lane = tid & 31, wid = ((tid >> 5) - (int)blockIdx.x) & (AOS_T / 32 - 1);
+    for (uint32_t g0 = 32u * wid; g0 < total; g0 += 32u * (AOS_T / 32)) {
+        const int cnt = (int)min(32u, total - g0);
+        const int mine = lane < cnt ? (int)s_cand[g0 + lane] : 0;
+        const uint8_t *f = s_buf + mine;
         const uint32_t vcid = f[5] & 0x3F;
-        const uint32_t inj = ((uint32_t)f[10] << 24) | ((uint32_t)f[11] << 16) | ((uint32_t)f[12] << 8) | f[13];
+        const uint32_t injw = ((uint32_t)f[10] << 24) | ((uint32_t)f[11] << 16) | ((uint32_t)f[12] << 8) | f[13];
+        const uint32_t want = ((uint32_t)f[894] << 8) | f[895];
         int st;
-        if (inj != 0xAAAAAAAAu && inj != 0u) st = -1;          // :675
-        else if (inj == 0xAAAAAAAAu && vcid == 0x3F) st = 0;   // :676
-        else {                                                 // :679-686, CRC over bytes 4..893
-            const uint32_t c = warp_crc16(crc, [&](int i) { return (uint32_t)f[4 + i]; });
-            const uint32_t want = ((uint32_t)f[894] << 8) | f[895];
-            st = c == want ? 1 : -1;
+        if (injw != 0xAAAAAAAAu && injw != 0u) st = -1;          // :675
+        else if (injw == 0xAAAAAAAAu && vcid == 0x3F) st = 0;   // :676
+        else st = 2;                                            // :679-686 CRC over bytes 4..893 decides
+        const int first = __shfl_sync(0xffffffffu, mine, 0);
+        const bool uniform = __all_sync(0xffffffffu, cnt == 32 && mine == first + 1024 * lane);
+        if (uniform) {
+            // the common case, 32 frames back to back: bit-sliced CRC, lane l = bytes [28l, 28l+28) of the 896-byte
+            // span that starts 2 bytes in front of each frame (4 sync bytes + 2 = the 6 bytes lane 0 drops)
+            const uint32_t B = smem_u32(s_buf) + (uint32_t)(first - 2 + 28 * lane);
+            uint32_t P[16];
+            bitslice::warp_crc32frames(
+                [&](int j, uint32_t(&T)[32]) {
+                    const uint32_t a = (B + 4u * (uint32_t)j) & ~3u, sh = B << 3;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) T[q] = __funnelshift_r(lds_u32(a + 1024u * q), lds_u32(a + 1024u * q + 4u), sh);
+                },
+                bitslice::SPAN - 890, P);
+            if (st == 2) st = (bitslice::unslice(P, lane) ^ bitslice::init_term(890)) == want ? 1 : -1;
+        } else {
+            for (int k = 0; k < cnt; ++k) { // irregular group (false sync, partial chunk): one candidate at a time
+                if (__shfl_sync(0xffffffffu, st, k) != 2) continue;
+                const int m0 = __shfl_sync(0xffffffffu, mine, k) + 4; // first message byte inside s_buf (16-byte aligned)
+                const uint32_t c = warp_crc16_words(crc, reinterpret_cast<const uint32_t *>(s_buf) + (m0 >> 2), m0 & 3);
+                if (lane == k) st = c == want ? 1 : -1;
+            }
         }
-        if (lane == 0) {
-            cand_off[slot0 + j] = (uint64_t)(c0 + s_cand[j]);
-            cand_st[slot0 + j] = (int8_t)st;
+        if (lane < cnt) {
+            cand_off[slot0 + g0 + lane] = (uint64_t)(c0 + mine);
+            cand_st[slot0 + g0 + lane] = (int8_t)st;
         }
     }
 }
@@ -314,31 +397,37 @@ __global__ void aos_walk_kernel(const uint64_t *off, const int8_t *st, const uin
                                 unsigned long long *counters)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    if (!(rs[i] || i == 0)) { return; }
-    unsigned long long n_inv = 0, n_emp = 0, n_val = 0;
-    int64_t j = i;
-    uint64_t next_free = 0; // first byte the scan may look at
-    if (rs[i]) {
-        acc[i] = 1;
-        n_val = 1;
-        next_free = off[i] + 1024;
-        j = i + 1;
-    }
-    for (; j < m && !rs[j]; ++j) {
-        if (off[j] < next_free) { acc[j] = 0; continue; } // inside an accepted frame: never seen
-        if (st[j] == 1) {
-            acc[j] = 1;
-            n_val++;
-            next_free = off[j] + 1024;
-        } else {
-            acc[j] = 0;
-            if (st[j] < 0) n_inv++; else n_emp++;
+    uint32_t n_inv = 0, n_emp = 0, n_val = 0;
+    if (i < m && (rs[i] || i == 0)) {
+        int64_t j = i;
+        uint64_t next_free = 0; // first byte the scan may look at
+        if (rs[i]) {
+            acc[i] = 1;
+            n_val = 1;
+            next_free = off[i] + 1024;
+            j = i + 1;
+        }
+        for (; j < m && !rs[j]; ++j) {
+            if (off[j] < next_free) { acc[j] = 0; continue; } // inside an accepted frame: never seen
+            if (st[j] == 1) {
+                acc[j] = 1;
+                n_val++;
+                next_free = off[j] + 1024;
+            } else {
+                acc[j] = 0;
+                if (st[j] < 0) n_inv++; else n_emp++;
+            }
         }
     }
-    if (n_val) atomicAdd(&counters[0], n_val);
-    if (n_inv) atomicAdd(&counters[1], n_inv);
-    if (n_emp) atomicAdd(&counters[2], n_emp);
+    // in a clean downlink every frame is its own run start: one atomic per warp, not three per thread
+    n_val = __reduce_add_sync(0xffffffffu, n_val);
+    n_inv = __reduce_add_sync(0xffffffffu, n_inv);
+    n_emp = __reduce_add_sync(0xffffffffu, n_emp);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_val) atomicAdd(&counters[0], (unsigned long long)n_val);
+        if (n_inv) atomicAdd(&counters[1], (unsigned long long)n_inv);
+        if (n_emp) atomicAdd(&counters[2], (unsigned long long)n_emp);
+    }
 }
 
 __global__ void aos_emit_kernel(const uint64_t *off, const uint32_t *acc, const uint32_t *rank, int64_t m,
@@ -352,54 +441,113 @@ __global__ void aos_emit_kernel(const uint64_t *off, const uint32_t *acc, const 
 // =============================================================================================
 // IMTR: fixed 882-byte cadence over the virtual concatenation of the 880-byte payloads
 // =============================================================================================
-__device__ __forceinline__ uint8_t stream_byte(const uint8_t *buf, const uint64_t *poff, int64_t s)
+// An 882-byte frame of the virtual stream spans 2 payloads (3 when only 1 byte of it lies in the first): three
+// contiguous source runs.  Frame position q lives at p0+q for q < l0, at p1+(q-l0) for q < l0+880, else at
+// p2+(q-l0-880).
+struct FrameSegs {
+    const uint8_t *p0, *p1, *p2;
+    int l0;
+};
+__device__ __forceinline__ FrameSegs frame_segs(const uint8_t *buf, const uint64_t *poff, int64_t n_payload, int64_t s0)
 {
-    const int64_t i = s / 880;
-    return buf[poff[i] + (uint64_t)(s - i * 880)];
+    const int64_t i = s0 / 880;
+    const int o = (int)(s0 - i * 880);
+    FrameSegs S;
+    S.l0 = 880 - o;
+    S.p0 = buf + poff[i] + o;
+    S.p1 = i + 1 < n_payload ? buf + poff[i + 1] : S.p0;
+    S.p2 = i + 2 < n_payload ? buf + poff[i + 2] : S.p1; // only touched when l0 < 2
+    return S;
+}
+__device__ __forceinline__ const uint8_t *seg_ptr(const FrameSegs &S, int q)
+{
+    return q < S.l0 ? S.p0 + q : (q < S.l0 + 880 ? S.p1 + (q - S.l0) : S.p2 + (q - S.l0 - 880));
+}
+// frame bytes q..q+3 as a little-endian word: two aligned 32-bit loads + funnel shift, taken from the run that holds
+// byte q.  Branch-free, so that all the loads of a lane are in flight together; a word that straddles a run boundary
+// (<= 2 per frame) comes out wrong in its trailing bytes and is redone by seg_word_bytes.  The aligned loads touch at
+// most 6 bytes past the run, which are bytes of the same 1024-byte AOS frame (CRC / LDPC field).
+__device__ __forceinline__ uint32_t seg_word(const FrameSegs &S, int q)
+{
+    const uint8_t *a = seg_ptr(S, q);
+    const uint32_t sh = (uint32_t)((uintptr_t)a & 3u);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a - sh);
+    const uint32_t lo = __ldg(w), hi = __ldg(w + (sh ? 1 : 0));
+    return __funnelshift_r(lo, hi, 8u * sh);
+}
+__device__ __forceinline__ uint32_t seg_word_bytes(const FrameSegs &S, int q, int n_bytes)
+{
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        if (b < n_bytes) v |= (uint32_t)__ldg(seg_ptr(S, q + b)) << (8 * b);
+    return v;
+}
+// does the word at frame position q (4 bytes) straddle one of the two run boundaries?
+__device__ __forceinline__ bool seg_straddles(const FrameSegs &S, int q)
+{
+    return (q < S.l0 && q + 3 >= S.l0) || (q < S.l0 + 880 && q + 3 >= S.l0 + 880);
 }
 
-constexpr int IMTR_WARPS = 8;
-__global__ void __launch_bounds__(IMTR_WARPS * 32) imtr_validate_kernel(const uint8_t *__restrict__ buf,
-                                                                         const uint64_t *__restrict__ poff,
-                                                                         int64_t n_frames,
-                                                                         const __grid_constant__ CrcPlan crc,
-                                                                         uint8_t *status, uint32_t *seq, uint8_t *chid,
-                                                                         uint32_t *valid)
+// A CTA validates 32 consecutive frames: its 4 warps gather 8 frames each into shared memory (896-byte slots), then
+// warp 0 runs ValidateImtrFrame for all of them, lane f = frame f, with the CRCs of the 32 frames bit-sliced.
+constexpr int IMTR_T = 128, IMTR_BATCH = 32, IMTR_SLOT = 896, IMTR_FRONT = 32;
+__global__ void __launch_bounds__(IMTR_T) imtr_validate_kernel(const uint8_t *__restrict__ buf, const uint64_t *__restrict__ poff,
+                                                               int64_t n_payload, int64_t n_frames, uint8_t *status,
+                                                               uint32_t *seq, uint8_t *chid, uint32_t *valid,
+                                                               unsigned long long *n_bad)
 {
-    __shared__ uint8_t s_f[IMTR_WARPS][896];
+    __shared__ __align__(16) uint32_t s_w[(IMTR_FRONT + IMTR_BATCH * IMTR_SLOT + 32) / 4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t f = (int64_t)blockIdx.x * IMTR_WARPS + wid;
-    if (f >= n_frames) return;
-    uint8_t *fr = s_f[wid];
-    const int64_t s0 = f * 882;
-    // gather the frame (it spans 2 or 3 payloads)
-    {
-        int64_t i = s0 / 880;
-        int o = (int)(s0 - i * 880);
-        // lane-strided byte copy; (i,o) advanced per byte position
-        for (int b = lane; b < 882; b += 32) {
-            int oo = o + b;
-            int64_t ii = i;
-            while (oo >= 880) { oo -= 880; ++ii; }
-            fr[b] = buf[poff[ii] + (uint64_t)oo];
+    const int64_t f0 = (int64_t)blockIdx.x * IMTR_BATCH;
+    for (int q = wid; q < IMTR_BATCH; q += IMTR_T / 32) {
+        if (f0 + q >= n_frames) break;
+        uint32_t *fw = s_w + (IMTR_FRONT + q * IMTR_SLOT) / 4;
+        const FrameSegs S = frame_segs(buf, poff, n_payload, (f0 + q) * 882);
+        uint32_t v[7]; // 220 whole words + 2 bytes; all of a lane's loads are issued before the first store
+#pragma unroll
+        for (int u = 0; u < 7; ++u) v[u] = seg_word(S, 4 * min(lane + 32 * u, 219));
+#pragma unroll
+        for (int u = 0; u < 7; ++u)
+            if (lane + 32 * u < 220) fw[lane + 32 * u] = v[u];
+        __syncwarp();
+        // the (at most two) words across a run boundary, and the last two bytes
+        if (lane < 2) {
+            const int b = lane == 0 ? S.l0 : S.l0 + 880;
+            if ((b & 3) && b < 880) fw[b >> 2] = seg_word_bytes(S, b & ~3, 4);
+        } else if (lane == 2) {
+            fw[220] = seg_word_bytes(S, 880, 2);
         }
     }
-    __syncwarp();
+    __syncthreads();
+    if (wid != (int)(blockIdx.x & 3)) return; // rotate the validating warp over the SM's four schedulers
     // ValidateImtrFrame, checks in the reference's order (ref aux_separator.h:558-590)
+    const uint32_t *fw = s_w + (IMTR_FRONT + lane * IMTR_SLOT) / 4;
+    const uint8_t *fr = reinterpret_cast<const uint8_t *>(fw);
     int st = 0;
-    if (!(fr[0] == 0x49 && fr[1] == 0x54 && fr[2] == 0xCE && fr[3] == 0x1F)) st = 1;                 // :559
+    if (fw[0] != 0x1FCE5449u) st = 1;                                                                // :559  49 54 CE 1F
     else if (!(fr[878] == 0x2E && fr[879] == 0xE9 && fr[880] == 0xC8 && fr[881] == 0xFD)) st = 2;     // :563
     else if (fr[9] != 0x22) st = 3;                                                                  // :572
-    else {
-        const uint32_t c = warp_crc16(crc, [&](int i) { return (uint32_t)fr[i]; });                  // :577-583
-        const uint32_t want = ((uint32_t)fr[876] << 8) | fr[877];
-        if (c != want) st = 4;
-    }
-    if (lane == 0) {
+    // :577-583 CRC over bytes 0..875: the 896-byte span ends with byte 875, i.e. starts 20 bytes before the frame
+    // (whatever the previous slot left there: lane 0 drops it).  Slots and pieces are word aligned.
+    const uint32_t B = smem_u32(s_w) + (uint32_t)(IMTR_FRONT - (bitslice::SPAN - 876) + 28 * lane);
+    uint32_t P[16];
+    bitslice::warp_crc32frames(
+        [&](int j, uint32_t(&T)[32]) {
+            const uint32_t a = B + 4u * (uint32_t)j;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) T[q] = lds_u32(a + (uint32_t)(IMTR_SLOT * q));
+        },
+        bitslice::SPAN - 876, P);
+    const uint32_t want = ((uint32_t)fr[876] << 8) | fr[877];
+    if (st == 0 && (bitslice::unslice(P, lane) ^ bitslice::init_term(876)) != want) st = 4;
+    const int64_t f = f0 + lane;
+    if (f < n_frames) {
         status[f] = (uint8_t)st;
-        seq[f] = ((uint32_t)fr[4] << 24) | ((uint32_t)fr[5] << 16) | ((uint32_t)fr[6] << 8) | fr[7];  // :568-569
+        seq[f] = __byte_perm(fw[1], 0u, 0x0123);                                                     // :568-569 BE u32 at 4
         chid[f] = fr[8];
         valid[f] = st == 0;
+        if (st) atomicAdd(&n_bad[st - 1], 1ull); // rejected frames are rare: counted here, not on the host
     }
 }
 
@@ -412,11 +560,11 @@ __global__ void imtr_compact_seq_kernel(const uint32_t *valid, const uint32_t *r
 }
 // restart rule: the IMDT file is (re)created when the previously accepted frame had seq 0
 // (lastImtrSeq == 0, ref :513-528); gap rule :530-533
-__global__ void imtr_rules_kernel(const uint32_t *seq_c, int64_t n_valid, unsigned long long *restart_last,
+__global__ void imtr_rules_kernel(const uint32_t *seq_c, const uint32_t *n_valid, unsigned long long *restart_last,
                                   unsigned long long *n_restarts, unsigned long long *n_gaps)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_valid) return;
+    if (k >= (int64_t)*n_valid) return;
     const uint32_t prev = k ? seq_c[k - 1] : 0u;
     if (prev == 0u) {
         atomicMax(restart_last, (unsigned long long)k);
@@ -425,9 +573,9 @@ __global__ void imtr_rules_kernel(const uint32_t *seq_c, int64_t n_valid, unsign
     if (prev + 1u != seq_c[k]) atomicAdd(n_gaps, 1ull);
 }
 __global__ void __launch_bounds__(256) imtr_copy_kernel(const uint8_t *__restrict__ buf, const uint64_t *__restrict__ poff,
-                                                        int64_t n_frames, const uint32_t *valid, const uint32_t *rank,
-                                                        const unsigned long long *restart_last, const uint8_t *chid,
-                                                        uint8_t *imdt, uint64_t cap, int *first_chid)
+                                                        int64_t n_payload, int64_t n_frames, const uint32_t *valid,
+                                                        const uint32_t *rank, const unsigned long long *restart_last,
+                                                        const uint8_t *chid, uint8_t *imdt, uint64_t cap, int *first_chid)
 {
     const int lane = threadIdx.x & 31;
     const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -437,15 +585,27 @@ __global__ void __launch_bounds__(256) imtr_copy_kernel(const uint8_t *__restric
     const uint64_t dst = (uint64_t)(rank[f] - r0) * 866;
     if (dst + 866 > cap) return;
     if (rank[f] == r0 && lane == 0) *first_chid = chid[f];
-    const int64_t s0 = f * 882 + 10; // IMTR_IMGDATA_OFF :72
-    int64_t i = s0 / 880;
-    const int o = (int)(s0 - i * 880);
-    for (int b = lane; b < 866; b += 32) {
-        int oo = o + b;
-        int64_t ii = i;
-        while (oo >= 880) { oo -= 880; ++ii; }
-        imdt[dst + b] = buf[poff[ii] + (uint64_t)oo];
+    const FrameSegs S = frame_segs(buf, poff, n_payload, f * 882);
+    // 866 payload bytes from frame position 10 (IMTR_IMGDATA_OFF :72): aligned destination words, source words
+    // re-aligned by funnel shift
+    uint8_t *d = imdt + dst;
+    const int head = (int)((4u - (uint32_t)((uintptr_t)d & 3u)) & 3u);
+    if (lane < head) d[lane] = __ldg(seg_ptr(S, 10 + lane));
+    const int nw = (866 - head) >> 2; // 215 or 216
+    uint32_t *dw = reinterpret_cast<uint32_t *>(d + head);
+    uint32_t v[7];
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+        const int k = lane + 32 * u, q = 10 + head + 4 * k;
+        v[u] = k < nw ? (seg_straddles(S, q) ? seg_word_bytes(S, q, 4) : seg_word(S, q)) : 0u;
     }
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+        const int k = lane + 32 * u;
+        if (k < nw) dw[k] = v[u];
+    }
+    const int t0 = head + 4 * nw;
+    if (lane < 866 - t0) d[t0 + lane] = __ldg(seg_ptr(S, 10 + t0 + lane));
 }
 
 // =============================================================================================
@@ -663,7 +823,8 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
         ChunkInfo *d_info = (ChunkInfo *)(S + o_info);
         OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 64, ctx->stream));
 
-        aos_scan_kernel<<<(unsigned)n_chunks, AOS_T, 0, ctx->stream>>>(d_buf, n, plan, d_cursor, cand_cap, d_info,
+        OIP_CUDA(cudaFuncSetAttribute(aos_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AOS_SMEM));
+        aos_scan_kernel<<<(unsigned)n_chunks, AOS_T, AOS_SMEM, ctx->stream>>>(d_buf, n, plan, d_cursor, cand_cap, d_info,
                                                                       (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst));
         OIP_CUDA(cudaGetLastError());
         ctx->launches++;
@@ -725,10 +886,9 @@ extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64
     if (nf == 0) return OIP_OK;
     if (!d_buf || !d_payload_off || !d_imdt) return fail(OIP_E_INVALID, "oip_imtr_deframe: null pointer");
     if (nf > 0x7fffffff) return fail(OIP_E_INVALID, "oip_imtr_deframe: too many frames for one call");
-    static const CrcPlan plan = make_crc_plan(876);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-    const size_t o_hdr = take(64); // restart_last | n_restarts | n_gaps (u64 each) | total(u32) | first_chid(i32)
+    const size_t o_hdr = take(64); // restart_last | n_restarts | n_gaps (u64 each) | total(u32) | first_chid(i32) | n_bad[4] (u64)
     const size_t o_status = take((size_t)nf);
     const size_t o_chid = take((size_t)nf);
     const size_t o_seq = take((size_t)nf * 4);
@@ -738,14 +898,18 @@ extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64
     const size_t o_scan = take(scan_scratch_elems(nf) * 4);
     int rc = ensure_scratch(ctx, o);
     if (rc) return rc;
+    rc = ensure_pinned(ctx, 64);
+    if (rc) return rc;
     uint8_t *S = (uint8_t *)ctx->d_scratch;
     unsigned long long *d_hdr = (unsigned long long *)(S + o_hdr);
     uint32_t *d_total = (uint32_t *)(S + o_hdr + 24);
     int *d_first_chid = (int *)(S + o_hdr + 28);
+    unsigned long long *d_bad = (unsigned long long *)(S + o_hdr + 32);
     OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 64, ctx->stream));
     OIP_CUDA(cudaMemsetAsync(d_first_chid, 0xFF, 4, ctx->stream));
-    imtr_validate_kernel<<<(unsigned)((nf + IMTR_WARPS - 1) / IMTR_WARPS), IMTR_WARPS * 32, 0, ctx->stream>>>(
-        d_buf, d_payload_off, nf, plan, S + o_status, (uint32_t *)(S + o_seq), S + o_chid, (uint32_t *)(S + o_valid));
+    // one stream-ordered chain, one host round trip at the end
+    imtr_validate_kernel<<<(unsigned)((nf + IMTR_BATCH - 1) / IMTR_BATCH), IMTR_T, 0, ctx->stream>>>(
+        d_buf, d_payload_off, n_payload, nf, S + o_status, (uint32_t *)(S + o_seq), S + o_chid, (uint32_t *)(S + o_valid), d_bad);
     OIP_CUDA(cudaGetLastError());
     ctx->launches++;
     rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank), nf, (uint32_t *)(S + o_scan), d_total);
@@ -754,29 +918,19 @@ extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64
     imtr_compact_seq_kernel<<<gb, 256, 0, ctx->stream>>>((uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank),
                                                          (uint32_t *)(S + o_seq), nf, (uint32_t *)(S + o_seqc));
     OIP_CUDA(cudaGetLastError());
-    ctx->launches++;
-    rc = ensure_pinned(ctx, 64 + (size_t)nf);
-    if (rc) return rc;
+    imtr_rules_kernel<<<gb, 256, 0, ctx->stream>>>((uint32_t *)(S + o_seqc), d_total, d_hdr, d_hdr + 1, d_hdr + 2);
+    OIP_CUDA(cudaGetLastError());
+    imtr_copy_kernel<<<(unsigned)((nf * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        d_buf, d_payload_off, n_payload, nf, (uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank), d_hdr, S + o_chid, d_imdt,
+        (uint64_t)cap, d_first_chid);
+    OIP_CUDA(cudaGetLastError());
+    ctx->launches += 3;
     uint8_t *hp = (uint8_t *)ctx->h_pinned;
-    OIP_CUDA(cudaMemcpyAsync(hp, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    OIP_CUDA(cudaStreamSynchronize(ctx->stream));
-    const uint32_t n_valid = *(uint32_t *)hp;
-    if (n_valid) {
-        imtr_rules_kernel<<<(n_valid + 255) / 256, 256, 0, ctx->stream>>>((uint32_t *)(S + o_seqc), n_valid, d_hdr, d_hdr + 1,
-                                                                         d_hdr + 2);
-        OIP_CUDA(cudaGetLastError());
-        imtr_copy_kernel<<<(unsigned)((nf * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            d_buf, d_payload_off, nf, (uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank), d_hdr, S + o_chid, d_imdt,
-            (uint64_t)cap, d_first_chid);
-        OIP_CUDA(cudaGetLastError());
-        ctx->launches += 2;
-    }
     OIP_CUDA(cudaMemcpyAsync(hp, S + o_hdr, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    OIP_CUDA(cudaMemcpyAsync(hp + 64, S + o_status, (size_t)nf, cudaMemcpyDeviceToHost, ctx->stream));
     OIP_CUDA(cudaStreamSynchronize(ctx->stream));
     const unsigned long long *hh = (const unsigned long long *)hp;
-    int64_t bad[5] = {0, 0, 0, 0, 0};
-    for (int64_t i = 0; i < nf; ++i) bad[hp[64 + i] < 5 ? hp[64 + i] : 0]++;
+    const uint32_t n_valid = *(const uint32_t *)(hp + 24);
+    const int64_t bad[5] = {0, (int64_t)hh[4], (int64_t)hh[5], (int64_t)hh[6], (int64_t)hh[7]};
     const int64_t out_frames = n_valid ? (int64_t)n_valid - (int64_t)hh[0] : 0;
     if ((uint64_t)out_frames * 866 > cap) return fail(OIP_E_INVALID, "oip_imtr_deframe: output capacity %zu too small", cap);
     if (stats) {

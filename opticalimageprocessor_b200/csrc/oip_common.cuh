@@ -135,6 +135,12 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t smem_addr)
+{
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(smem_addr));
+    return r;
+}
 __device__ __forceinline__ uint4 ldg_nc_v4(const void *p)
 {
     uint4 r;

@@ -16,7 +16,7 @@ buf = torch.from_numpy(file_np).cuda()
 print("file bytes", buf.numel())
 def ev():
     return torch.cuda.Event(enable_timing=True)
-for it in range(3):
+for it in range(5):
     t = [ev() for _ in range(5)]
     t[0].record()
     off, cnt = ops.aos_scan(ctx, buf); t[1].record()
@@ -25,6 +25,6 @@ for it in range(3):
     aux, pan, mss = ops.unpack_frames(ctx, imdt, 1536, 256, ents, int(fst[1])); t[4].record()
     torch.cuda.synchronize()
     ms = [t[i].elapsed_time(t[i + 1]) for i in range(4)]
-print("aos_scan %.3f ms (%.0f GB/s)  imtr_deframe %.3f ms (%.0f GB/s of payload)  index %.3f ms (%.0f GB/s)  unpack %.3f ms (%.0f GB/s r+w)" % (
-    ms[0], buf.numel() / ms[0] / 1e6, ms[1], off.numel() * 880 / ms[1] / 1e6, ms[2], imdt.numel() / ms[2] / 1e6, ms[3],
+    print("aos_scan %.3f ms (%.0f GB/s)  imtr_deframe %.3f ms (%.0f GB/s of payload)  index %.3f ms (%.0f GB/s)  unpack %.3f ms (%.0f GB/s r+w)" % (
+        ms[0], buf.numel() / ms[0] / 1e6, ms[1], off.numel() * 880 / ms[1] / 1e6, ms[2], imdt.numel() / ms[2] / 1e6, ms[3],
     (pan.numel() + mss.numel()) * 4 / ms[3] / 1e6), "frames", int(fst[1]), "counters", cnt.tolist())
