@@ -74,7 +74,7 @@ class ClockSampler:
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.02)
+                time.sleep(0.005)
         except Exception:
             pass
 
@@ -154,7 +154,7 @@ def run_reference(args):
                                    f"INTER_CUBIC ({cores} OpenCV threads, the reference's own library call) + concat, in memory"},
         "e2e": {"value": val, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -335,7 +335,7 @@ def run_gpu(args):
         else:
             line["e2e"] = {"value": None, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                            "note": "measured at N=1 only"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     for p in opened:
         ctx.lib.oip_ipc_close(ctx.h, C.c_void_p(p))
     if world > 1:
@@ -346,7 +346,25 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """the ONE JSON line, written to the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    # anything a library prints on fd 1 (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -261,6 +261,35 @@ int oip_stitch_concat_c4(oip_ctx *ctx, const uint16_t *const *d_img, int n_img, 
 int oip_unpack_lines(oip_ctx *ctx, const void *d_in, int fmt, int w, int64_t rows, int64_t pitch_bytes,
                      uint16_t *d_out);
 
+/* ---- inter-CMOS offset estimation (the caller that produces dX, dY) ---------- */
+/* replaces cv::phaseCorrelate(src1, src2, noArray(), &response) as called at ref stitcher.h:180 on two u16 slices
+ * (converted to float like the Mat1w -> Mat1f assignment at :175-176).  result = {dx, dy, response}.
+ * Floating point: agrees with OpenCV within ~1e-3 px (different DFT), not bit for bit.  DFT sizes must be even. */
+int oip_phase_correlate_u16(oip_ctx *ctx, const uint16_t *d_a, int64_t pitch_a_px, const uint16_t *d_b, int64_t pitch_b_px,
+                            int rows, int cols, double result[3]);
+
+typedef struct oip_stt_config { /* ref oipshared.h:49-54, Stitcher ctor stitcher.h:53-58 */
+    int32_t sections;          /* STT_DEF_SECTIONS 10 */
+    int32_t lines_per_section; /* STT_DEF_SECLINES 16000 */
+    int32_t overlap_cols;      /* STT_DEF_OVERLAPPX 200 */
+    int32_t edge_cols;         /* STT_DEF_EDGECOLS 0 */
+    double threshold;          /* STT_DEF_PHCTHRHLD 0.4 */
+    double max_delta_y;        /* STT_DEF_MAXDELTAY 0.0 = no filter */
+} oip_stt_config;
+typedef struct oip_stt_section {
+    int64_t line_offset;       /* first line of the section (global) */
+    double dx, dy, response;
+    int32_t valid;             /* 1 accepted, 0 rejected (threshold / max_delta_y), -1 rows not held by this shard */
+    int32_t pad;
+} oip_stt_section;
+/* replaces Stitcher::CalcSttParameters -- ref stitcher.h:148-201.  d_pan1 / d_pan2 hold rows [row0, row0+rows_here) of
+ * the two RRC-corrected strips (w px per line); sections wholly inside are correlated, the others are marked -1 (a
+ * scanline-block shard passes its own rows; ranks add their sums[] = {sum dx, sum dy, sum response, n valid} with one
+ * small all-reduce and divide, :197-199).  sections_out has cfg->sections entries. */
+int oip_stt_parameters(oip_ctx *ctx, const uint16_t *d_pan1, const uint16_t *d_pan2, int w, int64_t total_lines,
+                       int64_t row0, int64_t rows_here, int64_t pitch_px, const oip_stt_config *cfg,
+                       oip_stt_section *sections_out, double sums[4]);
+
 /* ---- whole-stage host-buffer entry points (what the CLI and bench.py "e2e" call) ------------ */
 /* host in / host out, copies on side streams overlapped with the kernels in row blocks */
 int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *desc_host_ptrs);

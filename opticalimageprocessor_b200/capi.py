@@ -51,6 +51,16 @@ class MssDesc(C.Structure):
                 ("keep_leading", C.c_int), ("min_process_lines", C.c_int)]
 
 
+class SttConfig(C.Structure):
+    _fields_ = [("sections", C.c_int32), ("lines_per_section", C.c_int32), ("overlap_cols", C.c_int32),
+                ("edge_cols", C.c_int32), ("threshold", C.c_double), ("max_delta_y", C.c_double)]
+
+
+class SttSection(C.Structure):
+    _fields_ = [("line_offset", C.c_int64), ("dx", C.c_double), ("dy", C.c_double), ("response", C.c_double),
+                ("valid", C.c_int32), ("pad", C.c_int32)]
+
+
 # every symbol include/oip_b200.h declares: name -> (restype, argtypes)
 _VP, _I, _I64, _SZ, _D = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 SYMBOLS = {
@@ -92,6 +102,9 @@ SYMBOLS = {
     "oip_stitch_concat_c4": (_I, [_VP, C.POINTER(_VP), _I, _I, _I64, _I, C.POINTER(_I), _VP]),
     "oip_unpack_lines": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP]),
     "oip_pan_pipeline_host": (_I, [_VP, C.POINTER(PanDesc)]),
+    "oip_phase_correlate_u16": (_I, [_VP, _VP, _I64, _VP, _I64, _I, _I, C.POINTER(_D)]),
+    "oip_stt_parameters": (_I, [_VP, _VP, _VP, _I, _I64, _I64, _I64, _I64, C.POINTER(SttConfig), C.POINTER(SttSection),
+                                C.POINTER(_D)]),
 }
 
 _lib = None

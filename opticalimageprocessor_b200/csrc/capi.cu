@@ -106,6 +106,7 @@ void oip_ctx_destroy(oip_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     oip::host_pipe_destroy(ctx);
+    oip::stt::destroy(ctx);
     for (oip_pan_plan &pl : ctx->pan_plans)
         if (pl.d_plan) cudaFree(pl.d_plan);
     if (ctx->d_mss_plan) cudaFree(ctx->d_mss_plan);

@@ -62,6 +62,7 @@ struct oip_ctx {
     bool pan_attr_set = false, mss_attr_set = false, fast_attr_set = false;
     // host-buffer pipeline (oip_pan_pipeline_host): staging slots + side streams
     void *host_pipe = nullptr;
+    void *stt_state = nullptr; // cuFFT plans of the offset estimation (stt.cu)
 };
 
 namespace oip {
@@ -86,6 +87,7 @@ int fail(int code, const char *fmt, ...);
 int ensure_scratch(oip_ctx *ctx, size_t bytes);
 int ensure_pinned(oip_ctx *ctx, size_t bytes);
 void host_pipe_destroy(oip_ctx *ctx);
+namespace stt { void destroy(oip_ctx *ctx); }
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

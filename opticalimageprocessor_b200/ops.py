@@ -279,3 +279,40 @@ def unpack_frames(ctx: Context, imdt: torch.Tensor, tile_cols: int, tile_lines: 
     check(ctx.lib.oip_unpack_frames(ctx.h, imdt.data_ptr(), imdt.numel(), C.byref(g), ents, n_frames, _ptr(aux),
                                     _ptr(pan), _ptr(mss)))
     return aux, pan, mss
+
+
+# ------------------------------------------------------------------------------------------------
+# inter-CMOS offset estimation (ref stitcher.h:148-201)
+# ------------------------------------------------------------------------------------------------
+def phase_correlate(ctx: Context, a: torch.Tensor, b: torch.Tensor):
+    """cv::phaseCorrelate(a, b) on two u16 device images (row views allowed) -> (dx, dy, response)"""
+    assert a.shape == b.shape and a.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    res = (C.c_double * 3)()
+    check(ctx.lib.oip_phase_correlate_u16(ctx.h, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), a.shape[0], a.shape[1], res))
+    return res[0], res[1], res[2]
+
+
+def calc_stt_parameters(ctx: Context, pan1: torch.Tensor, pan2: torch.Tensor, overlap_cols: int = 200, edge_cols: int = 0,
+                        sections: int = 10, lines_per_section: int = 16000, threshold: float = 0.4, max_delta_y: float = 0.0,
+                        total_lines: Optional[int] = None, row0: int = 0, group=None):
+    """Stitcher::CalcSttParameters: per-section rows (line_offset, dx, dy, response, valid) and the mean
+    (dx, dy, response) over the valid sections, or None when there is none (the reference throws there).
+    pan1 / pan2 may be one scanline-block shard (rows [row0, row0+len) of a total_lines strip): sections the shard
+    holds entirely are correlated here and the four sums are added over `group` with ONE small all-reduce."""
+    from .capi import SttConfig, SttSection
+    assert pan1.shape == pan2.shape and pan1.stride(1) == 1 and pan1.stride(0) == pan2.stride(0)
+    rows_here, w = pan1.shape
+    total = rows_here if total_lines is None else int(total_lines)
+    cfg = SttConfig(sections, lines_per_section, overlap_cols, edge_cols, threshold, max_delta_y)
+    secs = (SttSection * sections)()
+    sums = (C.c_double * 4)()
+    check(ctx.lib.oip_stt_parameters(ctx.h, pan1.data_ptr(), pan2.data_ptr(), w, total, row0, rows_here, pan1.stride(0),
+                                     C.byref(cfg), secs, sums))
+    rows = [(s.line_offset, s.dx, s.dy, s.response, s.valid) for s in secs]
+    tot = [sums[0], sums[1], sums[2], sums[3]]
+    if group is not None or (total_lines is not None and torch.distributed.is_available() and torch.distributed.is_initialized()):
+        t = torch.tensor(tot, dtype=torch.float64, device=pan1.device)
+        torch.distributed.all_reduce(t, group=group)
+        tot = t.tolist()
+    mean = None if tot[3] == 0 else (tot[0] / tot[3], tot[1] / tot[3], tot[2] / tot[3])
+    return rows, mean

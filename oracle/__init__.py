@@ -280,3 +280,72 @@ def mss_split(mixed: np.ndarray):
     planes = [np.zeros((lines, w // 4), np.uint16) for _ in range(4)]
     lib().oipo_mss_split(mixed, lines, w, _ptr_array(planes))
     return planes
+
+
+# ---------------------------------------------------------------------------------------------
+# N1: inter-CMOS offset estimation (ref stitcher.h:148-201).  The arithmetic is OpenCV's cv::phaseCorrelate
+# (imgproc/src/phasecorr.cpp, version left open by the reference's CMakeLists.txt:8): numpy restatement in fp64,
+# pinned against cv2.phaseCorrelate 4.13.0 in tests/test_phasecorr_cpu.py (floating point: tolerance, not bits).
+# ---------------------------------------------------------------------------------------------
+def optimal_dft_size(n: int) -> int:
+    """cv::getOptimalDFTSize: the smallest 2^a 3^b 5^c >= n"""
+    best = None
+    p2 = 1
+    while p2 < 2 * n:
+        p3 = p2
+        while p3 < 2 * n:
+            p5 = p3
+            while p5 < 2 * n:
+                if p5 >= n and (best is None or p5 < best):
+                    best = p5
+                p5 *= 5
+            p3 *= 3
+        p2 *= 2
+    return best
+
+
+def phase_correlate(a: np.ndarray, b: np.ndarray):
+    """(dx, dy, response) of cv::phaseCorrelate(a, b) without window: zero-pad to the optimal DFT size, normalised
+    cross-power spectrum F1 conj(F2) / |F1 conj(F2)|, unscaled inverse DFT, quadrant swap, first maximum,
+    5x5 weighted centroid clamped to the image, response = window sum / (M N), result = centre - centroid."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    M, N = optimal_dft_size(a.shape[0]), optimal_dft_size(a.shape[1])
+    if M % 2 or N % 2:
+        raise NotImplementedError("odd DFT sizes use OpenCV's asymmetric quadrant swap")
+    pa = np.zeros((M, N)); pa[: a.shape[0], : a.shape[1]] = a
+    pb = np.zeros((M, N)); pb[: b.shape[0], : b.shape[1]] = b
+    P = np.fft.rfft2(pa) * np.conj(np.fft.rfft2(pb))
+    mag = np.abs(P)
+    C = np.fft.irfft2(P * mag / (mag * mag + np.finfo(np.float32).eps), s=(M, N)) * (M * N)
+    C = np.roll(C, (M // 2, N // 2), axis=(0, 1)).astype(np.float32)
+    py, px = np.unravel_index(int(np.argmax(C)), C.shape)
+    y0, y1 = max(py - 2, 0), min(py + 2, M - 1)
+    x0, x1 = max(px - 2, 0), min(px + 2, N - 1)
+    win = C[y0:y1 + 1, x0:x1 + 1].astype(np.float64)
+    ys, xs = np.mgrid[y0:y1 + 1, x0:x1 + 1]
+    s = win.sum()
+    cx, cy = (xs * win).sum() / (s + np.finfo(np.float64).eps), (ys * win).sum() / (s + np.finfo(np.float64).eps)
+    return N / 2.0 - cx, M / 2.0 - cy, s / (M * N)
+
+
+def stt_parameters(pan1: np.ndarray, pan2: np.ndarray, overlap_cols=200, edge_cols=0, sections=10, lines_per_section=16000,
+                   threshold=0.4, max_delta_y=0.0, correlate=phase_correlate):
+    """Stitcher::CalcSttParameters (ref stitcher.h:148-201): per-section (line_offset, dx, dy, response, valid) and
+    the means over the valid sections (None when there is none: the reference throws)."""
+    lines, w = pan1.shape
+    gap = (lines - sections * lines_per_section) // (sections + 1)                         # :151
+    step = gap + lines_per_section                                                       # :152
+    rows = []
+    for i in range(sections):
+        off = gap + i * step                                                             # :167
+        s1 = pan1[off:off + lines_per_section, w - overlap_cols:w - edge_cols].astype(np.float32)   # :175
+        s2 = pan2[off:off + lines_per_section, edge_cols:overlap_cols].astype(np.float32)           # :176
+        dx, dy, r = correlate(s1, s2)
+        ok = r >= threshold and (max_delta_y <= 0.0 or abs(dy) <= max_delta_y)           # :181
+        rows.append((off, dx, dy, r, bool(ok)))
+    good = [q for q in rows if q[4]]
+    mean = None
+    if good:
+        mean = tuple(sum(q[k] for q in good) / len(good) for k in (1, 2, 3))             # :197-199
+    return rows, mean

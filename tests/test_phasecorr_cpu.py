@@ -1,0 +1,53 @@
+"""Oracle of SURVEY 8(f) N1 (Stitcher::CalcSttParameters, ref stitcher.h:148-201): the numpy restatement of
+cv::phaseCorrelate against the real cv2.phaseCorrelate (the reference's own library call, stitcher.h:180).
+Floating point: |d| <= 2e-3 px and |response| <= 1e-3 (cv2 runs its DFT in float32)."""
+import numpy as np
+import pytest
+
+import oracle
+
+cv2 = pytest.importorskip("cv2")
+
+
+def _pair(rows, cols, dx, dy, seed):
+    """two views of one smooth random scene, the second displaced by (dx, dy) (cubic resampling), as u16 DN"""
+    rng = np.random.default_rng(seed)
+    big = cv2.GaussianBlur(rng.random((rows + 64, cols + 64)).astype(np.float32), (0, 0), 1.2)
+    big = (big - big.min()) / (big.max() - big.min()) * 3000 + 200
+    xs, ys = np.meshgrid(np.arange(cols, dtype=np.float32) + 32, np.arange(rows, dtype=np.float32) + 32)
+    a = cv2.remap(big, xs, ys, cv2.INTER_CUBIC)
+    b = cv2.remap(big, xs - np.float32(dx), ys - np.float32(dy), cv2.INTER_CUBIC)
+    return np.round(a).astype(np.uint16), np.round(b).astype(np.uint16)
+
+
+@pytest.mark.parametrize("n", [1, 7, 100, 121, 200, 16000, 16001, 30000])
+def test_optimal_dft_size(n):
+    assert oracle.optimal_dft_size(n) == cv2.getOptimalDFTSize(n)
+
+
+@pytest.mark.parametrize("rows,cols,dx,dy", [(400, 200, 1.37, -2.61), (1000, 180, -0.83, 3.19), (500, 96, 0.0, 0.0), (750, 200, 4.5, 7.25)])
+def test_phase_correlate_matches_cv2(rows, cols, dx, dy):
+    a, b = _pair(rows, cols, dx, dy, seed=rows + cols)
+    (cx, cy), cr = cv2.phaseCorrelate(a.astype(np.float32), b.astype(np.float32))
+    ox, oy, orr = oracle.phase_correlate(a.astype(np.float32), b.astype(np.float32))
+    assert abs(ox - cx) <= 2e-3 and abs(oy - cy) <= 2e-3 and abs(orr - cr) <= 1e-3
+    assert abs(ox - dx) < 0.5 and abs(oy - dy) < 0.5  # and it does measure the displacement (5x5 centroid: biased towards the integer peak)
+
+
+def test_stt_parameters_follow_the_reference_loop():
+    lines, w, ov = 4096, 512, 200
+    scene_a, scene_b = _pair(lines, ov, 1.37, -2.61, seed=3)
+    pan1 = np.zeros((lines, w), np.uint16); pan2 = np.zeros((lines, w), np.uint16)
+    pan1[:, w - ov:] = scene_a
+    pan2[:, :ov] = scene_b
+    rows, mean = oracle.stt_parameters(pan1, pan2, overlap_cols=ov, sections=4, lines_per_section=600)
+    gap = (lines - 4 * 600) // 5
+    assert [r[0] for r in rows] == [gap + i * (gap + 600) for i in range(4)]
+    # the same loop on top of the real cv2.phaseCorrelate
+    def cvcorr(s1, s2):
+        (x, y), r = cv2.phaseCorrelate(s1, s2)
+        return x, y, r
+    rows_cv, mean_cv = oracle.stt_parameters(pan1, pan2, overlap_cols=ov, sections=4, lines_per_section=600, correlate=cvcorr)
+    assert [r[4] for r in rows] == [r[4] for r in rows_cv]
+    assert mean is not None and all(abs(p - q) <= 2e-3 for p, q in zip(mean, mean_cv))
+    assert abs(mean[0] - 1.37) < 0.5 and abs(mean[1] + 2.61) < 0.5

@@ -1,0 +1,95 @@
+"""SURVEY 8(f) N1 on the GPU: oip_phase_correlate_u16 / oip_stt_parameters against the reference's own library call
+(cv2.phaseCorrelate, ref stitcher.h:180) and the CalcSttParameters loop restated on top of it (oracle.stt_parameters).
+Floating point (different DFT implementation): |d| <= 2e-3 px, |response| <= 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from opticalimageprocessor_b200 import capi, ops
+from test_phasecorr_cpu import _pair
+
+cv2 = pytest.importorskip("cv2")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return ops.Context(0)
+
+
+@pytest.mark.parametrize("rows,cols,dx,dy", [(400, 200, 1.37, -2.61), (1000, 180, -0.83, 3.19), (500, 96, 0.0, 0.0),
+                                             (750, 200, 4.5, 7.25), (16000, 200, 1.37, -2.61)])
+def test_phase_correlate_matches_cv2(ctx, rows, cols, dx, dy):
+    a, b = _pair(rows, cols, dx, dy, seed=rows + cols)
+    (cx, cy), cr = cv2.phaseCorrelate(a.astype(np.float32), b.astype(np.float32))
+    gx, gy, gr = ops.phase_correlate(ctx, torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    assert abs(gx - cx) <= 2e-3 and abs(gy - cy) <= 2e-3 and abs(gr - cr) <= 1e-3, ((gx, gy, gr), (cx, cy, cr))
+
+
+def test_phase_correlate_on_column_views(ctx):
+    a, b = _pair(600, 200, -2.25, 1.5, seed=9)
+    wide1 = np.zeros((600, 512), np.uint16); wide1[:, 312:] = a
+    wide2 = np.zeros((600, 512), np.uint16); wide2[:, :200] = b
+    (cx, cy), cr = cv2.phaseCorrelate(a.astype(np.float32), b.astype(np.float32))
+    t1, t2 = torch.from_numpy(wide1).cuda(), torch.from_numpy(wide2).cuda()
+    gx, gy, gr = ops.phase_correlate(ctx, t1[:, 312:], t2[:, :200])
+    assert abs(gx - cx) <= 2e-3 and abs(gy - cy) <= 2e-3 and abs(gr - cr) <= 1e-3
+
+
+def test_odd_dft_size_is_refused(ctx):
+    a = torch.zeros((125, 64), dtype=torch.uint16, device="cuda")  # getOptimalDFTSize(125) = 125
+    with pytest.raises(capi.OipError):
+        ops.phase_correlate(ctx, a, a)
+
+
+def _strips(lines, w, ov, dx, dy, seed):
+    sa, sb = _pair(lines, ov, dx, dy, seed=seed)
+    rng = np.random.default_rng(seed)
+    pan1 = rng.integers(100, 4000, (lines, w)).astype(np.uint16)
+    pan2 = rng.integers(100, 4000, (lines, w)).astype(np.uint16)
+    pan1[:, w - ov:] = sa
+    pan2[:, :ov] = sb
+    return pan1, pan2
+
+
+def test_calc_stt_parameters_matches_reference_loop(ctx):
+    lines, w, ov = 8192, 1024, 200
+    pan1, pan2 = _strips(lines, w, ov, 1.37, -2.61, 5)
+    # make one section fail the response threshold: unrelated noise in its overlap
+    rows_cv, mean_cv = oracle.stt_parameters(pan1, pan2, overlap_cols=ov, edge_cols=4, sections=5, lines_per_section=1200)
+    off_bad = rows_cv[2][0]
+    pan2[off_bad:off_bad + 1200, :ov] = np.random.default_rng(1).integers(100, 4000, (1200, ov)).astype(np.uint16)
+
+    def cvcorr(s1, s2):
+        (x, y), r = cv2.phaseCorrelate(s1, s2)
+        return x, y, r
+    rows_cv, mean_cv = oracle.stt_parameters(pan1, pan2, overlap_cols=ov, edge_cols=4, sections=5, lines_per_section=1200, correlate=cvcorr)
+    rows, mean = ops.calc_stt_parameters(ctx, torch.from_numpy(pan1).cuda(), torch.from_numpy(pan2).cuda(), overlap_cols=ov,
+                                         edge_cols=4, sections=5, lines_per_section=1200)
+    assert [r[0] for r in rows] == [r[0] for r in rows_cv]
+    assert [r[4] for r in rows] == [int(r[4]) for r in rows_cv] and rows[2][4] == 0
+    for g, c in zip(rows, rows_cv):
+        if c[4]:
+            assert abs(g[1] - c[1]) <= 2e-3 and abs(g[2] - c[2]) <= 2e-3 and abs(g[3] - c[3]) <= 1e-3
+    assert all(abs(p - q) <= 2e-3 for p, q in zip(mean, mean_cv))
+
+
+def test_shards_add_up_to_the_whole(ctx):
+    """two scanline-block shards: every section lies in exactly one of them here, and the summed sums give the same mean"""
+    lines, w, ov = 8000, 512, 200
+    pan1, pan2 = _strips(lines, w, ov, -0.83, 3.19, 6)
+    t1, t2 = torch.from_numpy(pan1).cuda(), torch.from_numpy(pan2).cuda()
+    kw = dict(overlap_cols=ov, sections=4, lines_per_section=1000)
+    rows, mean = ops.calc_stt_parameters(ctx, t1, t2, **kw)
+    tot = np.zeros(4)
+    seen = []
+    for r0, r1 in [(0, 4000), (4000, 8000)]:
+        rs, _ = ops.calc_stt_parameters(ctx, t1[r0:r1], t2[r0:r1], total_lines=lines, row0=r0, **kw)
+        for s in rs:
+            if s[4] >= 0:
+                seen.append(s[0])
+                if s[4] == 1:
+                    tot += [s[1], s[2], s[3], 1]
+    assert sorted(seen) == [r[0] for r in rows]
+    assert all(abs(tot[k] / tot[3] - mean[k]) < 1e-9 for k in range(3))

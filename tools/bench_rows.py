@@ -239,3 +239,20 @@ psm = packed[:1024].cpu().numpy()
 tc = cpu_time(lambda: oracle.unpack_bits(psm, 12, W, 1024, psm.shape[1]))
 emit("ext", "oip_unpack_lines: MSB-first packed 12-bit -> u16 (not in the reference, SURVEY 0.1)", 4096 * W, "px", 4096 * W * 3.5, t,
      1024 * W, tc, "port", "C restatement, 1 thread, 1024 lines")
+
+# ------------------------------------------------------------------------------------------------ N1
+# Stitcher::CalcSttParameters at the reference defaults: 10 sections x 16000 lines x 200 overlap columns of two
+# 12288-px strips.  Algorithmic bytes: the two u16 slices, read once.  CPU: the same loop on cv2.phaseCorrelate.
+import cv2  # noqa: E402
+
+st_lines = 10 * 16000 + 11 * 400
+p1 = torch.from_numpy(rng.integers(64, 4032, (st_lines, W), dtype=np.uint16)).cuda()
+p2 = p1.view(torch.int16).roll(shifts=(3, 0), dims=(0, 1)).contiguous().view(torch.uint16)
+p2[:, :200] = p1[:, W - 200:].view(torch.int16).roll(shifts=(2, 1), dims=(0, 1)).view(torch.uint16)
+t = dev_time(lambda: ops.calc_stt_parameters(ctx, p1, p2), warm=2, it=5)
+s1 = p1[400:16400, W - 200:].cpu().numpy().astype(np.float32)
+s2 = p2[400:16400, :200].cpu().numpy().astype(np.float32)
+tc = cpu_time(lambda: cv2.phaseCorrelate(s1, s2), reps=3)
+emit("N1", "oip_stt_parameters: CalcSttParameters = 10 x phase correlation of 16000 x 200 overlap slices, cuFFT + own kernels (ref stitcher.h:148-201)",
+     10 * 16000 * 200 * 2, "px", 10 * 16000 * 200 * 2 * 2.0, t, 16000 * 200 * 2, tc, "reference",
+     f"cv2.phaseCorrelate ({cv2.getNumThreads()} OpenCV threads), one 16000 x 200 section")
