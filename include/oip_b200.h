@@ -290,6 +290,31 @@ int oip_stt_parameters(oip_ctx *ctx, const uint16_t *d_pan1, const uint16_t *d_p
                        int64_t row0, int64_t rows_here, int64_t pitch_px, const oip_stt_config *cfg,
                        oip_stt_section *sections_out, double sums[4]);
 
+/* ---- inter-band shift estimation + polynomial fit (produces cX, cY of oip_mss_desc) ---- */
+typedef struct oip_ibc_config {  /* ref oipshared.h:33-39 */
+    int32_t slices;              /* IBCV_DEF_SLICES 10 (>= min_slices) */
+    int32_t sections;            /* IBCV_DEF_SECTIONS 5 */
+    double threshold;            /* IBCV_DEF_THRESHOLD 0.4 */
+    int32_t correlation_lines;   /* CORRELATION_LINES 16000 (0 = default) */
+    int32_t min_slices;          /* IBCV_MIN_SLICES 8 (0 = default) */
+    int32_t min_count;           /* IBCV_MIN_COUNT 5 (0 = default) */
+    int32_t pad;
+} oip_ibc_config;
+typedef struct oip_ibc_shift {   /* InterBandShift, ref preproc.h:23-28 */
+    double dx, dy, rs;           /* dx, dy = NaN when rs < threshold (FilterInterBandShiftValues) */
+    int32_t cx;                  /* centre column of the slice, PAN pixels */
+    int32_t pad;
+} oip_ibc_shift;
+/* replaces PreProcessor::CalcInterBandCorrelation + FilterInterBandShiftValues + DoCorrelationPolynomialFitting --
+ * ref preproc.h:224-347, :492-550.  d_pan = the (RRC'd) PAN strip, w px per line; d_mss = the MSS strip, each line the
+ * 4 bands side by side (ref preproc.h:62-75).  Every PAN slice is correlated with the band slice upscaled x4 by
+ * cv::resize INTER_CUBIC semantics; shifts[band * slices*sections + sec*slices + i]; cX[band*2 + k], cY[band*3 + k]
+ * ascending coefficients as in mDeltaXcoeffs / mDeltaYcoeffs.  Fewer than min_count usable values in a band ->
+ * OIP_E_RANGE with the reference's message.  Floating point: tolerance, not bits. */
+int oip_inter_band_correlation(oip_ctx *ctx, const uint16_t *d_pan, int w, int64_t lines_pan, int64_t pan_pitch_px,
+                               const uint16_t *d_mss, int64_t lines_mss, int64_t mss_pitch_px, const oip_ibc_config *cfg,
+                               oip_ibc_shift *shifts, double cX[8], double cY[12]);
+
 /* ---- whole-stage host-buffer entry points (what the CLI and bench.py "e2e" call) ------------ */
 /* host in / host out, copies on side streams overlapped with the kernels in row blocks */
 int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *desc_host_ptrs);

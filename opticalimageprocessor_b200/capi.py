@@ -61,6 +61,15 @@ class SttSection(C.Structure):
                 ("valid", C.c_int32), ("pad", C.c_int32)]
 
 
+class IbcConfig(C.Structure):
+    _fields_ = [("slices", C.c_int32), ("sections", C.c_int32), ("threshold", C.c_double), ("correlation_lines", C.c_int32),
+                ("min_slices", C.c_int32), ("min_count", C.c_int32), ("pad", C.c_int32)]
+
+
+class IbcShift(C.Structure):
+    _fields_ = [("dx", C.c_double), ("dy", C.c_double), ("rs", C.c_double), ("cx", C.c_int32), ("pad", C.c_int32)]
+
+
 # every symbol include/oip_b200.h declares: name -> (restype, argtypes)
 _VP, _I, _I64, _SZ, _D = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 SYMBOLS = {
@@ -103,6 +112,8 @@ SYMBOLS = {
     "oip_unpack_lines": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP]),
     "oip_pan_pipeline_host": (_I, [_VP, C.POINTER(PanDesc)]),
     "oip_phase_correlate_u16": (_I, [_VP, _VP, _I64, _VP, _I64, _I, _I, C.POINTER(_D)]),
+    "oip_inter_band_correlation": (_I, [_VP, _VP, _I, _I64, _I64, _VP, _I64, _I64, C.POINTER(IbcConfig), C.POINTER(IbcShift),
+                                        C.POINTER(_D), C.POINTER(_D)]),
     "oip_stt_parameters": (_I, [_VP, _VP, _VP, _I, _I64, _I64, _I64, _I64, C.POINTER(SttConfig), C.POINTER(SttSection),
                                 C.POINTER(_D)]),
 }

@@ -4,7 +4,9 @@
 // normalised cross-power spectrum, inverse DFT, quadrant swap, first maximum, 5x5 weighted centroid.
 // The two DFTs are cuFFT (a plain library transform, like the reference's cv::dft); everything around them is here.
 // Floating point: parity with cv2.phaseCorrelate is a tolerance (tests: 2e-3 px), not bits.
+#include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cufft.h>
 
 #include "oip_common.cuh"
@@ -39,6 +41,54 @@ __global__ void pack_kernel(const uint16_t *__restrict__ a, int64_t pitch_a, con
         const int y = (int)(j / N), x = (int)(j - (int64_t)y * N);
         float v = 0.f;
         if (y < rows && x < cols) v = (float)(img ? b[(int64_t)y * pitch_b + x] : a[(int64_t)y * pitch_a + x]);
+        out[i] = v;
+    }
+}
+
+// N2 (ref preproc.h:256-304): plane 0 = the PAN slice as float, plane 1 = the MSS band slice upscaled to the same size by
+// cv::resize(..., INTER_CUBIC) on CV_32FC1: f = (float)((d + 0.5) * scale - 0.5), taps floor(f)-1..+2 clamped to the
+// image, weights interpolateCubic(A = -0.75) in float, horizontal pass then vertical pass (OpenCV's order)
+__device__ __forceinline__ void cubic_w(float x, float (&w)[4])
+{
+    const float A = -0.75f;
+    w[0] = ((A * (x + 1.f) - 5.f * A) * (x + 1.f) + 8.f * A) * (x + 1.f) - 4.f * A;
+    w[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    w[2] = ((A + 2.f) * (1.f - x) - (A + 3.f)) * (1.f - x) * (1.f - x) + 1.f;
+    w[3] = 1.f - w[0] - w[1] - w[2];
+}
+__global__ void pack_resize_kernel(const uint16_t *__restrict__ pan, int64_t pitch_pan, const uint16_t *__restrict__ band,
+                                   int64_t pitch_band, int rows, int cols, int brows, int bcols, double scale_y, double scale_x,
+                                   int M, int N, float *__restrict__ out)
+{
+    const int64_t n = (int64_t)M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int img = i >= n;
+        const int64_t j = i - (img ? n : 0);
+        const int y = (int)(j / N), x = (int)(j - (int64_t)y * N);
+        float v = 0.f;
+        if (y < rows && x < cols) {
+            if (!img) {
+                v = (float)pan[(int64_t)y * pitch_pan + x];
+            } else {
+                const float fy = (float)((y + 0.5) * scale_y - 0.5), fx = (float)((x + 0.5) * scale_x - 0.5);
+                const int sy = (int)floorf(fy), sx = (int)floorf(fx);
+                float wy[4], wx[4];
+                cubic_w(fy - (float)sy, wy);
+                cubic_w(fx - (float)sx, wx);
+                int xi[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xi[k] = min(max(sx - 1 + k, 0), bcols - 1);
+                float acc = 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint16_t *row = band + (int64_t)min(max(sy - 1 + r, 0), brows - 1) * pitch_band;
+                    const float h = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn((float)row[xi[0]], wx[0]), __fmul_rn((float)row[xi[1]], wx[1])),
+                                                        __fmul_rn((float)row[xi[2]], wx[2])), __fmul_rn((float)row[xi[3]], wx[3]));
+                    acc = r == 0 ? __fmul_rn(h, wy[0]) : __fadd_rn(acc, __fmul_rn(h, wy[r]));
+                }
+                v = acc;
+            }
+        }
         out[i] = v;
     }
 }
@@ -145,9 +195,10 @@ static int plans(oip_ctx *ctx, int M, int N, State **out)
     return OIP_OK;
 }
 
-// one phase correlation, result left in d_out[3]; launches only (no host synchronisation)
-static int correlate(oip_ctx *ctx, const uint16_t *d_a, int64_t pitch_a, const uint16_t *d_b, int64_t pitch_b, int rows, int cols,
-                     double *d_out)
+// one phase correlation, result left in d_out[3]; launches only (no host synchronisation).  pack(d_real, M, N, blocks)
+// launches the kernel that fills the two zero-padded float planes.
+template <typename Pack>
+static int correlate_with(oip_ctx *ctx, int rows, int cols, double *d_out, Pack pack)
 {
     const int M = optimal_dft_size(rows), N = optimal_dft_size(cols);
     if ((M | N) & 1)
@@ -165,7 +216,7 @@ static int correlate(oip_ctx *ctx, const uint16_t *d_a, int64_t pitch_a, const u
     float *d_real = (float *)S;
     cufftComplex *d_c = (cufftComplex *)(S + o_c);
     Peak *d_peaks = (Peak *)(S + o_p);
-    pack_kernel<<<blocks, 256, 0, ctx->stream>>>(d_a, pitch_a, d_b, pitch_b, rows, cols, M, N, d_real);
+    pack(d_real, M, N, blocks);
     OIP_CUDA(cudaGetLastError());
     OIP_CUFFT(cufftExecR2C(st->fwd, d_real, d_c));
     cross_power_kernel<<<blocks, 256, 0, ctx->stream>>>(d_c, d_c + (size_t)M * NC, (int64_t)M * NC);
@@ -177,6 +228,57 @@ static int correlate(oip_ctx *ctx, const uint16_t *d_a, int64_t pitch_a, const u
     OIP_CUDA(cudaGetLastError());
     ctx->launches += 4;
     return OIP_OK;
+}
+
+static int correlate(oip_ctx *ctx, const uint16_t *d_a, int64_t pitch_a, const uint16_t *d_b, int64_t pitch_b, int rows, int cols,
+                     double *d_out)
+{
+    return correlate_with(ctx, rows, cols, d_out, [&](float *d_real, int M, int N, int blocks) {
+        pack_kernel<<<blocks, 256, 0, ctx->stream>>>(d_a, pitch_a, d_b, pitch_b, rows, cols, M, N, d_real);
+    });
+}
+
+// least-squares polynomial of degree deg (ascending coefficients), like Poly1d::fit (ref preproc.h:533-534): normal
+// equations in long double on the centred / scaled abscissa, expanded back to powers of x
+static bool polyfit(const std::vector<double> &x, const std::vector<double> &y, int deg, double *coef)
+{
+    const int n = (int)x.size(), m = deg + 1;
+    if (n < m) return false;
+    long double mean = 0, sc = 0;
+    for (double v : x) mean += v;
+    mean /= n;
+    for (double v : x) sc = std::max(sc, fabsl((long double)v - mean));
+    if (sc == 0) sc = 1;
+    long double A[3][4] = {};
+    for (int i = 0; i < n; ++i) {
+        const long double t = ((long double)x[i] - mean) / sc;
+        long double p[5] = {1, t, t * t, t * t * t, t * t * t * t};
+        for (int r = 0; r < m; ++r) {
+            for (int c = 0; c < m; ++c) A[r][c] += p[r + c];
+            A[r][m] += p[r] * (long double)y[i];
+        }
+    }
+    for (int c = 0; c < m; ++c) { // Gauss-Jordan with partial pivoting
+        int piv = c;
+        for (int r = c + 1; r < m; ++r)
+            if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
+        if (fabsl(A[piv][c]) < 1e-300L) return false;
+        for (int k = 0; k <= m; ++k) std::swap(A[c][k], A[piv][k]);
+        for (int r = 0; r < m; ++r) {
+            if (r == c) continue;
+            const long double f = A[r][c] / A[c][c];
+            for (int k = c; k <= m; ++k) A[r][k] -= f * A[c][k];
+        }
+    }
+    long double q[3] = {0, 0, 0}; // coefficients in t
+    for (int r = 0; r < m; ++r) q[r] = A[r][m] / A[r][r];
+    // t = (x - mean) / sc  ->  powers of x
+    const long double a = 1 / sc, b = -mean / sc;
+    long double c0 = q[0] + q[1] * b + q[2] * b * b, c1 = q[1] * a + 2 * q[2] * a * b, c2 = q[2] * a * a;
+    coef[0] = (double)c0;
+    if (deg >= 1) coef[1] = (double)c1;
+    if (deg >= 2) coef[2] = (double)c2;
+    return true;
 }
 
 void destroy(oip_ctx *ctx)
@@ -256,6 +358,81 @@ extern "C" int oip_stt_parameters(oip_ctx *ctx, const uint16_t *d_pan1, const ui
             const bool ok = s.response >= cfg->threshold && (cfg->max_delta_y <= 0.0 || fabs(s.dy) <= cfg->max_delta_y); // :181
             s.valid = ok ? 1 : 0;
             if (ok && sums) { sums[0] += s.dx; sums[1] += s.dy; sums[2] += s.response; sums[3] += 1.0; } // :183-186
+        }
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int oip_inter_band_correlation(oip_ctx *ctx, const uint16_t *d_pan, int w, int64_t lines_pan, int64_t pan_pitch_px,
+                                          const uint16_t *d_mss, int64_t lines_mss, int64_t mss_pitch_px, const oip_ibc_config *cfg,
+                                          oip_ibc_shift *shifts, double cX[8], double cY[12])
+{
+    OIP_CHECK_CTX(ctx);
+    if (!d_pan || !d_mss || !cfg || !shifts) return fail(OIP_E_INVALID, "oip_inter_band_correlation: null pointer");
+    const int slices = cfg->slices, sections = cfg->sections, corr = cfg->correlation_lines > 0 ? cfg->correlation_lines : 16000;
+    const int min_slices = cfg->min_slices > 0 ? cfg->min_slices : 8, min_count = cfg->min_count > 0 ? cfg->min_count : 5;
+    if (slices < min_slices) return fail(OIP_E_INVALID, "CalcInterBandCorrelation: at lease %d slice needed", min_slices);           // ref preproc.h:228-230
+    if (sections <= 0) return fail(OIP_E_INVALID, "CalcInterBandCorrelation: section count should be a positive integer");          // :231-233
+    if (sections > 1 && (int64_t)sections * corr > lines_pan)                                                                       // :234-237
+        return fail(OIP_E_INVALID, "CalcInterBandCorrelation: too many sections (%d lines per section), not enough total PAN data lines", corr);
+    if (w < 4 * slices || (w & 3) || pan_pitch_px < w || mss_pitch_px < w || lines_pan < 4 || lines_mss < 1)
+        return fail(OIP_E_INVALID, "oip_inter_band_correlation: bad geometry");
+    const int base_rows = (int)std::min<int64_t>(lines_pan, corr);                     // :245
+    const int gap = (int)((lines_pan - (int64_t)base_rows * sections) / (sections + 1)); // :246
+    const int cols = w / slices;                                                        // :247
+    const int brows = base_rows / 4, bgap = gap / 4, bcols = cols / 4, wb = w / 4;      // :272-274, band width = W / MSS_BANDS
+    if (brows < 1 || bcols < 1) return fail(OIP_E_INVALID, "oip_inter_band_correlation: slices too small");
+    const int total = slices * sections;
+    int rc = ensure_pinned(ctx, 64 + (size_t)total * 4 * 3 * sizeof(double));
+    if (rc) return rc;
+    double *d_out;
+    OIP_CUDA(cudaMalloc(&d_out, (size_t)total * 4 * 3 * sizeof(double)));
+    for (int sec = 0; sec < sections && !rc; ++sec) {
+        const int64_t r0 = gap + (int64_t)sec * (base_rows + gap);                      // :256
+        const int64_t q0 = bgap + (int64_t)sec * (brows + bgap);                        // :283
+        if (r0 < 0 || r0 + base_rows > lines_pan || q0 < 0 || q0 + brows > lines_mss) {
+            rc = fail(OIP_E_RANGE, "oip_inter_band_correlation: section %d leaves the image (PAN %lld lines, MSS %lld lines)", sec,
+                      (long long)lines_pan, (long long)lines_mss);
+            break;
+        }
+        for (int i = 0; i < slices && !rc; ++i)
+            for (int b = 0; b < 4 && !rc; ++b) {
+                const uint16_t *pp = d_pan + r0 * pan_pitch_px + (int64_t)i * cols;
+                const uint16_t *bp = d_mss + q0 * mss_pitch_px + (int64_t)b * wb + (int64_t)i * bcols; // band b = columns [b*wb, (b+1)*wb) (ref preproc.h:62-75)
+                rc = stt::correlate_with(ctx, base_rows, cols, d_out + 3 * ((size_t)b * total + (size_t)sec * slices + i),
+                                         [&](float *d_real, int M, int N, int blocks) {
+                                             stt::pack_resize_kernel<<<blocks, 256, 0, ctx->stream>>>(
+                                                 pp, pan_pitch_px, bp, mss_pitch_px, base_rows, cols, brows, bcols, (double)brows / base_rows,
+                                                 (double)bcols / cols, M, N, d_real);
+                                         });
+            }
+    }
+    if (!rc) {
+        double *h = (double *)((uint8_t *)ctx->h_pinned + 64);
+        cudaError_t e = cudaMemcpyAsync(h, d_out, (size_t)total * 4 * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(OIP_E_CUDA, "oip_inter_band_correlation: %s", cudaGetErrorString(e));
+        for (int b = 0; b < 4 && !rc; ++b) {
+            std::vector<double> xs, dxs, dys;
+            for (int k = 0; k < total; ++k) {
+                oip_ibc_shift &s = shifts[(size_t)b * total + k];
+                const double *v = h + 3 * ((size_t)b * total + k);
+                s.dx = v[0]; s.dy = v[1]; s.rs = v[2];
+                s.cx = (k % slices) * cols + cols / 2;                                  // :326
+                s.pad = 0;
+                if (s.rs < cfg->threshold) { s.dx = s.dy = std::nan(""); continue; }     // FilterInterBandShiftValues :495-503
+                xs.push_back((double)s.cx); dxs.push_back(s.dx); dys.push_back(s.dy);
+            }
+            if ((int)xs.size() < min_count) {                                           // :505-510
+                rc = fail(OIP_E_RANGE, "Not enough valid correlation values for band#%d: %d valid values found, %d expected at least", b + 1,
+                          (int)xs.size(), min_count);
+                break;
+            }
+            if (cX && cY) {                                                             // DoCorrelationPolynomialFitting :513-547
+                if (!stt::polyfit(xs, dxs, 1, cX + 2 * b) || !stt::polyfit(xs, dys, 2, cY + 3 * b))
+                    rc = fail(OIP_E_RANGE, "polynomial fit of band#%d is singular", b + 1);
+            }
         }
     }
     cudaFree(d_out);

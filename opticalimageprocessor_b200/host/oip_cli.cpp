@@ -4,11 +4,11 @@
 // DOC/Usage.txt (task flow).  CLI11 is not available here: hand-written parser, same option names.
 //
 // Differences, all forced by what SURVEY 8f leaves for later rows:
-//   * prestitch: the inter-CMOS offset estimate (cv::phaseCorrelate, ref stitcher.h:148-201) is not
-//     implemented -> pass it with the extension options --dx/--dy.
-//   * default action: the inter-band correlation + polynomial fit (ref preproc.h:224-347,492-550) is
-//     not implemented -> pass the 4x5 coefficients with --poly FILE; the result is written as
-//     <stem>.ALIGNED.RAW (CV_16UC4 memory layout) because no TIFF writer exists yet.
+//   * prestitch: the inter-CMOS offset estimate (ref stitcher.h:148-201) runs on the GPU (oip_stt_parameters; agrees with
+//     cv::phaseCorrelate to ~1e-3 px); the extension options --dx/--dy skip it.
+//   * default action: the inter-band correlation + polynomial fit (ref preproc.h:224-347,492-550) runs on the GPU
+//     (oip_inter_band_correlation); the extension option --poly FILE (4 lines of cx0 cx1 cy0 cy1 cy2) skips it.  The
+//     result is written as <stem>.ALIGNED.RAW (CV_16UC4 memory layout) because no TIFF writer exists yet.
 //   * stitch: RAW in / RAW out only (TIFF codec: SURVEY 8f N3).
 // There is no CPU fallback: without a B200 every command fails with exit code 2.
 #include <strings.h>
@@ -316,11 +316,38 @@ static int cmd_prestitch(const std::vector<std::string> &av)
     OLOG("PAN: %lld lines total.", (long long)lines);
     if (lines < (int64_t)sections * sec_lines)
         throw std::invalid_argument("PAN line count less than sections times line-per-section, use smaller -s and/or -l value(s)");
-    if (!a.has("dx") || !a.has("dy"))
-        throw usage_error("inter-CMOS offset estimation (phase correlation, ref stitcher.h:148-201) is not part of this build: "
-                          "pass the offsets with --dx and --dy");
-    const double dx = a.getd("dx", 0), dy = a.getd("dy", 0);
-    OLOG("    dx: %.5f, dy: %.5f (given)", dx, dy);
+    double dx = 0.0, dy = 0.0;
+    if (a.has("dx") && a.has("dy")) { // extension: skip the estimate
+        dx = a.getd("dx", 0); dy = a.getd("dy", 0);
+        OLOG("    dx: %.5f, dy: %.5f (given)", dx, dy);
+    } else {
+        // Stitcher::CalcSttParameters, ref stitcher.h:148-201.  It runs on the files as given: PreStitch() calls it
+        // before DoRRC (ref main.cpp:280-284) and mRrcFilePAN1/2 still name the inputs (stitcher.h:79-80).
+        const size_t nb = s1;
+        Pinned hb(nb);
+        DevBuf d1(nb), d2(nb);
+        read_file(pan1, hb.p, 0, nb);
+        oip_check(oip_copy_h2d(ctx(), d1.p, hb.p, nb));
+        oip_check(oip_ctx_sync(ctx()));
+        read_file(pan2, hb.p, 0, nb);
+        oip_check(oip_copy_h2d(ctx(), d2.p, hb.p, nb));
+        oip_stt_config cfg{};
+        cfg.sections = sections; cfg.lines_per_section = sec_lines; cfg.overlap_cols = (int)overlap; cfg.edge_cols = (int)edge;
+        cfg.threshold = a.getd("stt-threshold", 0.4); cfg.max_delta_y = a.getd("stt-maxdeltay", 0.0);
+        std::vector<oip_stt_section> secs((size_t)sections);
+        double sums[4];
+        OLOG("Calculating stitching delta values ...");
+        oip_check(oip_stt_parameters(ctx(), (const uint16_t *)d1.p, (const uint16_t *)d2.p, PIXELS_PER_LINE, lines, 0, lines,
+                                     PIXELS_PER_LINE, &cfg, secs.data(), sums));
+        OLOG("| offset |  delta x |  delta y | response | r |");
+        OLOG("-----------------------------------------------");
+        for (const oip_stt_section &q : secs)
+            OLOG("|%7lld |%10.4f|%10.4f|%10.4f|%s|", (long long)q.line_offset, q.dx, q.dy, q.response, q.valid == 1 ? " + " : " x ");
+        if (sums[3] == 0.0) throw std::runtime_error("No valid delta value found for stitching parameter calculating");
+        dx = sums[0] / sums[3]; dy = sums[1] / sums[3];
+        OLOG("Total %d valid delta value pairs found, everage value:", (int)sums[3]);
+        OLOG("    dx: %.5f, dy: %.5f, r: %.5f", dx, dy, sums[2] / sums[3]);
+    }
     if (a.has("only-calculate")) return 0;
     if (do_rrc && (!a.has("rrc1") || !a.has("rrc2"))) throw std::runtime_error("open RRC Param file failed");
 
@@ -434,11 +461,8 @@ static int cmd_default(const std::vector<std::string> &av)
     const size_t sp = file_size(a.get("pan")), sm = file_size(a.get("mss"));
     if (sp != (size_t)MSS_BANDS * sm) throw std::runtime_error("PAN file size does not match MSS file size: PAN file should be 4x as large as MSS file");
     if (sp % (PIXELS_PER_LINE * BYTES_PER_PIXEL)) throw std::runtime_error("PAN file size invalid: should be multiplies of 24576");
-    if (!a.has("poly"))
-        throw usage_error("inter-band correlation + polynomial fitting (ref preproc.h:224-347) is not part of this build: pass the "
-                          "coefficients with --poly FILE (4 lines: cx0 cx1 cy0 cy1 cy2)");
     double cX[8], cY[12];
-    {
+    if (a.has("poly")) { // extension: skip the estimate, 4 lines "cx0 cx1 cy0 cy1 cy2"
         FILE *f = fopen(a.get("poly").c_str(), "r");
         if (!f) throw std::invalid_argument("cannot open --poly file");
         for (int b = 0; b < 4; ++b)
@@ -447,6 +471,46 @@ static int cmd_default(const std::vector<std::string> &av)
                 throw std::invalid_argument("--poly: need 4 lines of 5 numbers");
             }
         fclose(f);
+    } else {
+        // PreProcessor::CalcInterBandCorrelation on the (RRC'd) PAN and MSS data, ref main.cpp:306-316, preproc.h:224-347
+        const int64_t lp = (int64_t)(sp / (PIXELS_PER_LINE * BYTES_PER_PIXEL)), lm = (int64_t)(sm / (PIXELS_PER_LINE * BYTES_PER_PIXEL));
+        const int wb4 = PIXELS_PER_LINE / MSS_BANDS;
+        Pinned hp(sp);
+        DevBuf d_pan(sp), d_ms(sm);
+        read_file(a.get("pan"), hp.p, 0, sp);
+        oip_check(oip_copy_h2d(ctx(), d_pan.p, hp.p, sp));
+        oip_check(oip_ctx_sync(ctx()));
+        read_file(a.get("mss"), hp.p, 0, sm);
+        oip_check(oip_copy_h2d(ctx(), d_ms.p, hp.p, sm));
+        if (a.has("do-rrc4pan")) {                                                                     // DoRRC4PAN, ref preproc.h:188-200
+            std::vector<double> kb = load_rrc(a.get("rrc-pan"), PIXELS_PER_LINE);
+            DevBuf d_kb(kb.size() * 8);
+            oip_check(oip_copy_h2d(ctx(), d_kb.p, kb.data(), kb.size() * 8));
+            oip_check(oip_rrc_u16(ctx(), (uint16_t *)d_pan.p, PIXELS_PER_LINE, lp, PIXELS_PER_LINE, (const double *)d_kb.p));
+            oip_check(oip_ctx_sync(ctx()));
+        }
+        if (rrc_mss)                                                                                  // DoRRC4MSS, ref preproc.h:202-222
+            for (int b = 0; b < 4; ++b) {
+                char key[16]; snprintf(key, sizeof key, "rrc-msb%d", b + 1);
+                existing_file(a.get(key), key);
+                std::vector<double> kb = load_rrc(a.get(key), wb4);
+                DevBuf d_kb(kb.size() * 8);
+                oip_check(oip_copy_h2d(ctx(), d_kb.p, kb.data(), kb.size() * 8));
+                oip_check(oip_rrc_u16(ctx(), (uint16_t *)d_ms.p + (size_t)b * wb4, wb4, lm, PIXELS_PER_LINE, (const double *)d_kb.p));
+                oip_check(oip_ctx_sync(ctx()));
+            }
+        oip_ibc_config cfg{};
+        cfg.slices = (int)a.geti("slices", 10); cfg.sections = (int)a.geti("ibc-sections", 5); cfg.threshold = thr;
+        OLOG("Calculating inter-band correlation with %d slices in %d section(s) ...", cfg.slices, cfg.sections);
+        std::vector<oip_ibc_shift> sh((size_t)4 * std::max(1, cfg.slices) * std::max(1, cfg.sections));
+        oip_check(oip_inter_band_correlation(ctx(), (const uint16_t *)d_pan.p, PIXELS_PER_LINE, lp, PIXELS_PER_LINE, (const uint16_t *)d_ms.p,
+                                             lm, PIXELS_PER_LINE, &cfg, sh.data(), cX, cY));
+        for (int b = 0; b < 4; ++b) {
+            OLOG("Doing polynomial fitting for BAND %d ...", b);
+            OLOG("\tdeltaX coeff: [1] %.15f, [0] %.9f", cX[2 * b + 1], cX[2 * b]);
+            OLOG("\tdeltaY coeff: [2] %.15f, [1] %.15f, [0] %.9f", cY[3 * b + 2], cY[3 * b + 1], cY[3 * b]);
+        }
+        OLOG("CalcInterBandCorrelation(): done.");
     }
     const int wb = PIXELS_PER_LINE / MSS_BANDS;
     const int64_t lines = (int64_t)(sm / (PIXELS_PER_LINE * BYTES_PER_PIXEL));
@@ -495,7 +559,7 @@ static void usage()
          "         --lines-section --overlap-lines -k,--keep-leading --poly FILE\n"
          "Subcommands:\n"
          "  auxsep [-O,--offset N] file          Do aux & image data separation\n"
-         "  prestitch --pan1 F --pan2 F [--rrc1 F --rrc2 F] [-r|--no-rrc] [-c] --dx X --dy Y\n"
+         "  prestitch --pan1 F --pan2 F [--rrc1 F --rrc2 F] [-r|--no-rrc] [-c] [-s N -l N --stitch-overlap N -e N] [--dx X --dy Y]\n"
          "  stitch --image1 F --image2 F -c,--fold-cols N -o OUT.RAW");
 }
 

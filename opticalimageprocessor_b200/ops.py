@@ -316,3 +316,22 @@ def calc_stt_parameters(ctx: Context, pan1: torch.Tensor, pan2: torch.Tensor, ov
         tot = t.tolist()
     mean = None if tot[3] == 0 else (tot[0] / tot[3], tot[1] / tot[3], tot[2] / tot[3])
     return rows, mean
+
+
+# ------------------------------------------------------------------------------------------------
+# inter-band shift estimation + polynomial fit (ref preproc.h:224-347, :492-550)
+# ------------------------------------------------------------------------------------------------
+def calc_inter_band_correlation(ctx: Context, pan: torch.Tensor, mss: torch.Tensor, slices: int = 10, sections: int = 5,
+                                threshold: float = 0.4, correlation_lines: int = 16000, min_slices: int = 8, min_count: int = 5):
+    """PreProcessor::CalcInterBandCorrelation: pan (lines x W) and mss (lines/4 x W, 4 bands side by side) on the device
+    -> (shifts[band][sec*slices+i] = (dx, dy, rs, cx), cX[4][2], cY[4][3])"""
+    from .capi import IbcConfig, IbcShift
+    assert pan.stride(1) == 1 and mss.stride(1) == 1 and pan.shape[1] == mss.shape[1]
+    cfg = IbcConfig(slices, sections, threshold, correlation_lines, min_slices, min_count, 0)
+    n = slices * sections
+    sh = (IbcShift * (4 * n))()
+    cX, cY = (C.c_double * 8)(), (C.c_double * 12)()
+    check(ctx.lib.oip_inter_band_correlation(ctx.h, pan.data_ptr(), pan.shape[1], pan.shape[0], pan.stride(0), mss.data_ptr(),
+                                             mss.shape[0], mss.stride(0), C.byref(cfg), sh, cX, cY))
+    shifts = [[(sh[b * n + k].dx, sh[b * n + k].dy, sh[b * n + k].rs, sh[b * n + k].cx) for k in range(n)] for b in range(4)]
+    return shifts, [[cX[2 * b], cX[2 * b + 1]] for b in range(4)], [[cY[3 * b], cY[3 * b + 1], cY[3 * b + 2]] for b in range(4)]

@@ -349,3 +349,70 @@ def stt_parameters(pan1: np.ndarray, pan2: np.ndarray, overlap_cols=200, edge_co
     if good:
         mean = tuple(sum(q[k] for q in good) / len(good) for k in (1, 2, 3))             # :197-199
     return rows, mean
+
+
+# ---------------------------------------------------------------------------------------------
+# N2: inter-band shift estimation + polynomial fit (ref preproc.h:224-347, :492-550).  cv::resize INTER_CUBIC is
+# OpenCV's (restated in resize_cubic_x below, pinned against cv2.resize); the fit is a plain least-squares
+# polynomial (NumCpp Poly1d::fit in the reference, numpy.polyfit here), coefficients in ascending order.
+# ---------------------------------------------------------------------------------------------
+def resize_cubic(src: np.ndarray, rows: int, cols: int) -> np.ndarray:
+    """cv::resize(src, Size(cols, rows), 0, 0, INTER_CUBIC) for CV_32FC1: taps floor(f)-1..+2 clamped to the image,
+    weights interpolateCubic(A=-0.75) in float, horizontal pass then vertical pass."""
+    src = np.asarray(src, np.float32)
+
+    def axis_tab(n_src, n_dst):
+        scale = n_src / n_dst
+        f = ((np.arange(n_dst) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        x = (f - s).astype(np.float32)
+        A = np.float32(-0.75)
+        w0 = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A
+        w1 = ((A + 2) * x - (A + 3)) * x * x + 1
+        w2 = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1
+        w3 = np.float32(1) - w0 - w1 - w2
+        idx = np.clip(s[:, None] + np.arange(-1, 3)[None, :], 0, n_src - 1)
+        return idx, np.stack([w0, w1, w2, w3], 1).astype(np.float32)
+
+    ix, wx = axis_tab(src.shape[1], cols)
+    iy, wy = axis_tab(src.shape[0], rows)
+    h = np.zeros((src.shape[0], cols), np.float32)
+    for k in range(4):
+        h += src[:, ix[:, k]] * wx[None, :, k]
+    out = np.zeros((rows, cols), np.float32)
+    for k in range(4):
+        out += h[iy[:, k], :] * wy[:, None, k]
+    return out
+
+
+def inter_band_correlation(pan: np.ndarray, bands, slices=10, sections=5, threshold=0.4, corr_lines=16000, min_count=5,
+                           correlate=phase_correlate, resize=resize_cubic):
+    """PreProcessor::CalcInterBandCorrelation + FilterInterBandShiftValues + DoCorrelationPolynomialFitting.
+    Returns (shifts[band][sec*slices+i] = (dx, dy, rs, cx), cX[4][2], cY[4][3]); raises RuntimeError like the
+    reference when a band has fewer than min_count usable values (ref :505-510)."""
+    lines, w = pan.shape
+    base_rows = min(lines, corr_lines)                                                  # :245
+    gap = (lines - base_rows * sections) // (sections + 1)                              # :246
+    cols = w // slices                                                                  # :247
+    brow, bgap, bcols = base_rows // 4, gap // 4, cols // 4                              # :272-274
+    shifts = [[None] * (slices * sections) for _ in range(4)]
+    for sec in range(sections):
+        r0 = gap + sec * (base_rows + gap)                                              # :256
+        for i in range(slices):
+            base = pan[r0:r0 + base_rows, i * cols:(i + 1) * cols].astype(np.float32)
+            for b in range(4):
+                q0 = bgap + sec * (brow + bgap)                                         # :283
+                sl = bands[b][q0:q0 + brow, i * bcols:(i + 1) * bcols].astype(np.float32)
+                up = resize(sl, base_rows, cols)                                        # :299-304
+                dx, dy, rs = correlate(base, up)                                        # :314
+                shifts[b][sec * slices + i] = (dx, dy, rs, i * cols + cols // 2)        # :322-326
+    cX, cY = [], []
+    for b in range(4):
+        good = [s for s in shifts[b] if s[2] >= threshold]
+        if len(good) < min_count:
+            raise RuntimeError(f"Not enough valid correlation values for band#{b + 1}: {len(good)} valid values found, "
+                               f"{min_count} expected at least")
+        x = np.array([s[3] for s in good], np.float64)
+        cX.append(np.polyfit(x, np.array([s[0] for s in good]), 1)[::-1].tolist())      # :533 ascending coefficients
+        cY.append(np.polyfit(x, np.array([s[1] for s in good]), 2)[::-1].tolist())      # :534
+    return shifts, cX, cY

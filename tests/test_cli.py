@@ -95,8 +95,30 @@ def test_prestitch_and_stitch_task_flow(cli, tmp_path, oracle_mod):
     assert r.returncode == 0, r.stdout + r.stderr
     out = np.fromfile(os.path.join(d, "SYN_PAN-2.PRESTT.RAW"), np.uint16).reshape(rows, W)
     _check_prestitch(out, g, "neg")
-    # missing --dx/--dy: the estimate is not in this build -> usage error 254
-    assert run(cli, ["prestitch", "--pan1", p2, "--pan2", p2] + sec, d).returncode == 254
+    # without --dx/--dy the offsets are estimated (Stitcher::CalcSttParameters, ref stitcher.h:148-201); the overlap
+    # columns of this pair are unrelated noise -> no valid section -> std::runtime_error -> exit code 2 (ref :190-192)
+    r = run(cli, ["prestitch", "--pan1", p2, "--pan2", p2, "-c"] + sec, d)
+    assert r.returncode == 2 and "No valid delta value found" in (r.stdout + r.stderr)
+    # a pair that does overlap: -c prints the table and the means, which must match the reference loop on cv2.phaseCorrelate
+    import cv2
+    from test_phasecorr_cpu import _pair
+    sa, sb = _pair(rows, 200, 1.37, -2.61, seed=11)
+    o1, o2 = src.copy(), src[::-1].copy()
+    o1[:, W - 200:] = sa
+    o2[:, :200] = sb
+    q1, q2 = os.path.join(d, "OVL_PAN-1.RAW"), os.path.join(d, "OVL_PAN-2.RAW")
+    o1.tofile(q1); o2.tofile(q2)
+    r = run(cli, ["prestitch", "--pan1", q1, "--pan2", q2, "-c", "-e", "2"] + sec, d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    import re
+    m = re.search(r"dx: (-?[0-9.]+), dy: (-?[0-9.]+), r: (-?[0-9.]+)", r.stdout)
+    assert m and "Total 2 valid delta value pairs found" in r.stdout
+
+    def cvcorr(s1, s2):
+        (x, y), rr = cv2.phaseCorrelate(s1, s2)
+        return x, y, rr
+    _, mean = oracle_mod.stt_parameters(o1, o2, overlap_cols=200, edge_cols=2, sections=2, lines_per_section=16000, correlate=cvcorr)
+    assert all(abs(float(m.group(k + 1)) - mean[k]) <= 2e-3 for k in range(3))
     assert run(cli, ["prestitch", "--pan1", p2, "--pan2", p2, "--dx=1", "--dy=1"], d).returncode == 2   # too few lines for 10 x 16000
     # with RRC (default): <stem>.RRC.RAW for both and <stem>.RRC.PRESTT.RAW, first/last rows vs oracle
     kb1, kb2 = synth.rrc_coeffs(W, 1), synth.rrc_coeffs(W, 2)
@@ -139,7 +161,10 @@ def test_default_action_mss(cli, tmp_path, oracle_mod):
     with open(os.path.join(d, "poly.txt"), "w") as f:
         for b in range(4):
             f.write("%r %r %r %r %r\n" % (cX[b][0], cX[b][1], cY[b][0], cY[b][1], cY[b][2]))
-    assert run(cli, args, d).returncode == 254          # coefficients not given: estimation is not in this build
+    # without --poly the coefficients are estimated (CalcInterBandCorrelation); this PAN has 8400 lines, too few for the
+    # default 5 sections x 16000 lines -> std::invalid_argument -> exit code 2 (ref preproc.h:234-237, main.cpp:336-339)
+    r = run(cli, args, d)
+    assert r.returncode == 2 and "too many sections" in (r.stdout + r.stderr)
     r = run(cli, args + ["--poly", "poly.txt"], d)
     assert r.returncode == 0, r.stdout + r.stderr
     planes = [oracle_mod.rrc(p, k) for p, k in zip(oracle_mod.mss_split(mss), kbs)]

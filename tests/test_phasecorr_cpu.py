@@ -11,6 +11,9 @@ cv2 = pytest.importorskip("cv2")
 
 def _pair(rows, cols, dx, dy, seed):
     """two views of one smooth random scene, the second displaced by (dx, dy) (cubic resampling), as u16 DN"""
+    if rows > 16384:  # cv2.remap refuses images taller than 32767 rows: independent scenes stacked
+        parts = [_pair(min(16384, rows - r), cols, dx, dy, seed + 1 + r) for r in range(0, rows, 16384)]
+        return np.vstack([p[0] for p in parts]), np.vstack([p[1] for p in parts])
     rng = np.random.default_rng(seed)
     big = cv2.GaussianBlur(rng.random((rows + 64, cols + 64)).astype(np.float32), (0, 0), 1.2)
     big = (big - big.min()) / (big.max() - big.min()) * 3000 + 200
@@ -51,3 +54,42 @@ def test_stt_parameters_follow_the_reference_loop():
     assert [r[4] for r in rows] == [r[4] for r in rows_cv]
     assert mean is not None and all(abs(p - q) <= 2e-3 for p, q in zip(mean, mean_cv))
     assert abs(mean[0] - 1.37) < 0.5 and abs(mean[1] + 2.61) < 0.5
+
+
+@pytest.mark.parametrize("shape,dst", [((100, 77), (400, 308)), ((50, 64), (200, 256)), ((40, 31), (160, 125))])
+def test_resize_cubic_matches_cv2(shape, dst):
+    src = np.random.default_rng(4).random(shape).astype(np.float32) * 4000
+    want = cv2.resize(src, (dst[1], dst[0]), interpolation=cv2.INTER_CUBIC)
+    got = oracle.resize_cubic(src, dst[0], dst[1])
+    assert np.abs(got - want).max() <= 1e-2  # float32 rounding (different summation order) on values up to 4000: 2.5e-6 relative
+
+
+def _mss_scene(lines_pan, w, shifts, seed):
+    """a PAN strip and 4 quarter-resolution bands of the same scene, band b displaced by shifts[b] PAN pixels"""
+    rng = np.random.default_rng(seed)
+    big = cv2.GaussianBlur(rng.random((lines_pan + 64, w + 64)).astype(np.float32), (0, 0), 3.0)
+    big = (big - big.min()) / (big.max() - big.min()) * 3000 + 200
+    xs, ys = np.meshgrid(np.arange(w, dtype=np.float32) + 32, np.arange(lines_pan, dtype=np.float32) + 32)
+    pan = np.round(cv2.remap(big, xs, ys, cv2.INTER_CUBIC)).astype(np.uint16)
+    bands = []
+    for dx, dy in shifts:
+        full = cv2.remap(big, xs - np.float32(dx), ys - np.float32(dy), cv2.INTER_CUBIC)
+        bands.append(np.round(cv2.resize(full, (w // 4, lines_pan // 4), interpolation=cv2.INTER_AREA)).astype(np.uint16))
+    return pan, bands
+
+
+def test_inter_band_correlation_on_cv2_building_blocks():
+    """the restated resize + phase correlation give the same shifts and polynomials as the loop on cv2's own functions"""
+    pan, bands = _mss_scene(1600, 2048, [(2.0, -3.0), (1.0, 4.0), (-2.5, 1.5), (0.5, -0.5)], seed=8)
+    kw = dict(slices=8, sections=2, corr_lines=640)
+
+    def cvcorr(a, b):
+        (x, y), r = cv2.phaseCorrelate(a, b)
+        return x, y, r
+    ours = oracle.inter_band_correlation(pan, bands, **kw)
+    ref = oracle.inter_band_correlation(pan, bands, correlate=cvcorr,
+                                        resize=lambda s, r, c: cv2.resize(s, (c, r), interpolation=cv2.INTER_CUBIC), **kw)
+    for b in range(4):
+        for s, t in zip(ours[0][b], ref[0][b]):
+            assert s[3] == t[3] and abs(s[0] - t[0]) <= 2e-3 and abs(s[1] - t[1]) <= 2e-3 and abs(s[2] - t[2]) <= 1e-3
+        assert np.allclose(ours[1][b], ref[1][b], atol=2e-3) and np.allclose(ours[2][b], ref[2][b], atol=2e-3)

@@ -7,7 +7,7 @@ import torch
 
 import oracle
 from opticalimageprocessor_b200 import capi, ops
-from test_phasecorr_cpu import _pair
+from test_phasecorr_cpu import _mss_scene, _pair
 
 cv2 = pytest.importorskip("cv2")
 pytestmark = pytest.mark.gpu
@@ -93,3 +93,42 @@ def test_shards_add_up_to_the_whole(ctx):
                     tot += [s[1], s[2], s[3], 1]
     assert sorted(seen) == [r[0] for r in rows]
     assert all(abs(tot[k] / tot[3] - mean[k]) < 1e-9 for k in range(3))
+
+
+# ------------------------------------------------------------------------------------------------ N2
+def test_inter_band_correlation_matches_reference_loop(ctx):
+    """oip_inter_band_correlation against CalcInterBandCorrelation restated on cv2.resize + cv2.phaseCorrelate +
+    numpy.polyfit (ref preproc.h:224-347, :492-550): shifts within 3e-3 px, polynomial values within 3e-3 px over the line"""
+    true = [(2.0, -3.0), (1.0, 4.0), (-2.5, 1.5), (0.5, -0.5)]
+    pan, bands = _mss_scene(1600, 2048, true, seed=8)
+    mss = np.ascontiguousarray(np.hstack(bands))
+    kw = dict(slices=8, sections=2, threshold=0.3)
+
+    def cvcorr(a, b):
+        (x, y), r = cv2.phaseCorrelate(a, b)
+        return x, y, r
+    ref = oracle.inter_band_correlation(pan, bands, corr_lines=640, correlate=cvcorr,
+                                        resize=lambda s, r, c: cv2.resize(s, (c, r), interpolation=cv2.INTER_CUBIC), **kw)
+    got = ops.calc_inter_band_correlation(ctx, torch.from_numpy(pan).cuda(), torch.from_numpy(mss).cuda(), correlation_lines=640, **kw)
+    xs = np.array([0.0, 1024.0, 2047.0]) * 4
+    for b in range(4):
+        for g, r in zip(got[0][b], ref[0][b]):
+            assert g[3] == r[3] and abs(g[2] - r[2]) <= 1e-3
+            if r[2] >= 0.3:
+                assert abs(g[0] - r[0]) <= 3e-3 and abs(g[1] - r[1]) <= 3e-3, (b, g, r)
+            else:
+                assert np.isnan(g[0]) and np.isnan(g[1])
+        px = lambda c, x: sum(ck * x ** k for k, ck in enumerate(c))
+        assert all(abs(px(got[1][b], x) - px(ref[1][b], x)) <= 3e-3 for x in xs / 4)
+        assert all(abs(px(got[2][b], x) - px(ref[2][b], x)) <= 3e-3 for x in xs / 4)
+
+
+def test_inter_band_correlation_argument_errors(ctx):
+    pan = torch.zeros((1600, 2048), dtype=torch.uint16, device="cuda")
+    mss = torch.zeros((400, 2048), dtype=torch.uint16, device="cuda")
+    with pytest.raises(capi.OipError, match="at lease 8 slice needed"):
+        ops.calc_inter_band_correlation(ctx, pan, mss, slices=4)
+    with pytest.raises(capi.OipError, match="too many sections"):
+        ops.calc_inter_band_correlation(ctx, pan, mss, slices=8, sections=5)
+    with pytest.raises(capi.OipError, match="Not enough valid correlation values for band#1"):
+        ops.calc_inter_band_correlation(ctx, pan, mss, slices=8, sections=1)
