@@ -7,9 +7,10 @@
 //   * prestitch: the inter-CMOS offset estimate (ref stitcher.h:148-201) runs on the GPU (oip_stt_parameters; agrees with
 //     cv::phaseCorrelate to ~1e-3 px); the extension options --dx/--dy skip it.
 //   * default action: the inter-band correlation + polynomial fit (ref preproc.h:224-347,492-550) runs on the GPU
-//     (oip_inter_band_correlation); the extension option --poly FILE (4 lines of cx0 cx1 cy0 cy1 cy2) skips it.  The
-//     result is written as <stem>.ALIGNED.RAW (CV_16UC4 memory layout) because no TIFF writer exists yet.
-//   * stitch: RAW in / RAW out only (TIFF codec: SURVEY 8f N3).
+//     (oip_inter_band_correlation); the extension option --poly FILE (4 lines of cx0 cx1 cy0 cy1 cy2) skips it.
+//   * TIFF files (host/tiff_io.hpp): written uncompressed (the reference's libraries compress with LZW), so
+//     they match in geometry, sample order and pixel values, not byte for byte; TIFF INPUT must be uncompressed strips
+//     (our own products).  --aligned-raw additionally writes <stem>.ALIGNED.RAW (the CV_16UC4 memory image).
 // There is no CPU fallback: without a B200 every command fails with exit code 2.
 #include <strings.h>
 #include <sys/stat.h>
@@ -30,6 +31,7 @@
 #include <vector>
 
 #include "../../include/oip_b200.h"
+#include "tiff_io.hpp"
 
 namespace fs = std::filesystem;
 
@@ -409,9 +411,46 @@ static int cmd_stitch(const std::vector<std::string> &av)
     const std::string le = lower(fs::path(l).extension().string()), re = lower(fs::path(r).extension().string());
     if (le != re) throw std::invalid_argument("Stitch(): two images should be same type");                    // ref stitcher.h:31-33
     if (le != ".tiff" && le != ".raw") throw std::invalid_argument("Stitch(): only RAW and TIFF image supported");
-    if (le == ".tiff") throw std::runtime_error("TIFF input is not supported by this build (no TIFF codec, SURVEY 8f N3); use RAW files");
-    if (out.empty() || lower(fs::path(out).extension().string()) == ".tiff")
-        throw std::runtime_error("TIFF output is not supported by this build (no TIFF codec, SURVEY 8f N3); pass -o <file>.RAW");
+    if (le == ".tiff") { // IMO::StitchTiff / StitchTiffGDAL, ref imageop.h:365-567
+        std::string outp = out;
+        if (outp.empty()) outp = (fs::current_path() / "stitched.TIFF").string();                             // ref :373-375
+        else if (lower(fs::path(outp).extension().string()) != ".tiff") throw std::invalid_argument("Output file should be a tiff image"); // :376-380
+        OLOG("Reading tiff image from file `%s' ...", l.c_str());
+        const oiptiff::Info il = oiptiff::read_info(l), ir = oiptiff::read_info(r);
+        OLOG("Image size: %lld cols, %lld rows, channels: %d.", (long long)il.width, (long long)il.height, il.spp);
+        if (il.height != ir.height || il.width != ir.width) throw std::runtime_error("images have different sizes");   // :412-414
+        if (il.spp != 4 || ir.spp != 4) throw std::runtime_error("4-channel 16-bit TIFF images expected");
+        const int f = fold / 2, w = (int)il.width, ow = 2 * (w - f);
+        if (f >= w) throw std::invalid_argument("fold columns exceed the image width");
+        const size_t nb = (size_t)il.height * w * 8, ob = (size_t)il.height * ow * 8;
+        Pinned hl(nb), hr(nb), ho(ob);
+        oiptiff::read_u16(l, il, (uint16_t *)hl.p);
+        oiptiff::read_u16(r, ir, (uint16_t *)hr.p);
+        DevBuf dl(nb), dr(nb), dout(ob);
+        oip_check(oip_copy_h2d(ctx(), dl.p, hl.p, nb));
+        oip_check(oip_copy_h2d(ctx(), dr.p, hr.p, nb));
+        // Samples travel in FILE order.  cv::imwrite / cv::imread swap samples 0 and 2 of a 4-channel image (BGRA memory,
+        // RGBA file), so the cv path (ref :419-446) keeps the file order; the GDAL path (ref :522-537) writes band b from
+        // MEMORY channel map[b]-1, i.e. from file sample swap02(map[b]-1).
+        const bool gdal = a.has("GDAL") || file_size(l) >= 4000000000ull;                                      // ref :418
+        int map[4] = {1, 2, 3, 4};
+        if (a.has("band-map")) sscanf(a.get("band-map").c_str(), "%d,%d,%d,%d", map, map + 1, map + 2, map + 3);
+        int fmap[4];
+        for (int b = 0; b < 4; ++b) { const int m = map[b] - 1; fmap[b] = (m == 0 ? 2 : (m == 2 ? 0 : m)) + 1; }
+        const uint16_t *imgs[2] = {(const uint16_t *)dl.p, (const uint16_t *)dr.p};
+        OLOG("Begin stitching two images ...");
+        oip_check(oip_stitch_concat_c4(ctx(), imgs, 2, w, il.height, f, gdal ? fmap : nullptr, (uint16_t *)dout.p));
+        oip_check(oip_copy_d2h(ctx(), ho.p, dout.p, ob));
+        oip_check(oip_ctx_sync(ctx()));
+        OLOG("Write stitched image to file '%s' ...", outp.c_str());
+        oiptiff::write_u16(outp, (const uint16_t *)ho.p, ow, il.height, 4, 2);
+        OLOG("%zu bytes written.", ob);
+        return 0;
+    }
+    std::string raw_out = out;
+    bool out_tiff = true;                                                                                       // ref imageop.h:297-306
+    if (out.empty()) raw_out = (fs::current_path() / ("stitched_" + std::to_string(2 * (PIXELS_PER_LINE - fold / 2)) + "n16b.TIFF")).string();
+    else out_tiff = lower(fs::path(out).extension().string()) == ".tiff";
     const size_t szl = file_size(l), szr = file_size(r);
     if (szl != szr) throw std::invalid_argument("RAW image sizes not match");                                   // ref imageop.h:285-289
     const int f = fold / 2;                                                                                     // ref main.cpp:189
@@ -431,7 +470,9 @@ static int cmd_stitch(const std::vector<std::string> &av)
     d.d_out = (uint16_t *)ho.p; d.out_pitch_px = out_w;
     OLOG("Begin stitching two images ...");
     oip_check(oip_pan_pipeline_host(ctx(), &d));
-    write_file(out, ho.p, (size_t)lines * out_w * 2);
+    OLOG("Write stitched image to file '%s' ...", raw_out.c_str());
+    if (out_tiff) oiptiff::write_u16(raw_out, (const uint16_t *)ho.p, out_w, lines, 1, 1);   // single-band GTiff, ref imageop.h:316-328
+    else write_file(raw_out, ho.p, (size_t)lines * out_w * 2);
     OLOG("%zu bytes written.", (size_t)lines * out_w * 2);
     return 0;
 }
@@ -447,7 +488,7 @@ static int cmd_default(const std::vector<std::string> &av)
                         {"--rrc-msb3", nullptr, false}, {"--rrc-msb4", nullptr, false}, {"--slices", nullptr, false},
                         {"--ibc-sections", nullptr, false}, {"--ibc-threshold", nullptr, false}, {"--line-offset", nullptr, false},
                         {"--lines-section", nullptr, false}, {"--overlap-lines", nullptr, false}, {"--keep-leading", "-k", true},
-                        {"--poly", nullptr, false}}, 0);
+                        {"--poly", nullptr, false}, {"--aligned-raw", nullptr, true}}, 0);
     if (a.has("pan")) existing_file(a.get("pan"), "--pan");
     if (a.has("mss")) existing_file(a.get("mss"), "--mss");
     if (a.has("rrc-pan") && !a.has("do-rrc4pan")) throw parse_error(CLI_REQUIRES, "--rrc-pan requires --do-rrc4pan");
@@ -545,9 +586,18 @@ static int cmd_default(const std::vector<std::string> &av)
     Pinned ho((size_t)out_rows * wb * 8);
     oip_check(oip_copy_d2h(ctx(), ho.p, d_out.p, (size_t)out_rows * wb * 8));
     oip_check(oip_ctx_sync(ctx()));
-    const std::string out = build_output_path(a.get("mss"), ".ALIGNED", ".RAW");
-    write_file(out, ho.p, (size_t)out_rows * wb * 8);
-    OLOG("%lld lines aligned; written to file [%s] (CV_16UC4 layout, %d px x 4 bands per line).", (long long)rows, out.c_str(), wb);
+    if (a.has("aligned-raw")) { // extension: the CV_16UC4 memory image as it is
+        const std::string out = build_output_path(a.get("mss"), ".ALIGNED", ".RAW");
+        write_file(out, ho.p, (size_t)out_rows * wb * 8);
+        OLOG("%lld lines aligned; written to file [%s] (CV_16UC4 layout, %d px x 4 bands per line).", (long long)rows, out.c_str(), wb);
+    }
+    // WriteAlignedMSS_TIFF, ref preproc.h:167-185: cv::imwrite stores a 4-channel Mat as RGBA, i.e. samples 0 and 2 swapped
+    OLOG("Writing aligned MSS image as TIFF file ...");
+    uint16_t *px = (uint16_t *)ho.p;
+    for (size_t i = 0, n = (size_t)out_rows * wb; i < n; ++i) std::swap(px[4 * i], px[4 * i + 2]);
+    const std::string tif = build_output_path(a.get("mss"), ".ALIGNED", ".TIFF");
+    oiptiff::write_u16(tif, px, wb, out_rows, 4, 2);
+    OLOG("Written to file [%s].", tif.c_str());
     return 0;
 }
 

@@ -1,0 +1,212 @@
+// tiff_io.hpp -- SURVEY 8(f) N3: the TIFF files of the reference's task flow, without libtiff / GDAL.
+//
+// Writes what cv::imwrite (ref preproc.h:167-185, imageop.h:444) and the GTiff driver (ref imageop.h:316-328, :470-538)
+// are used for there: 16-bit unsigned rasters with 1 or 4 interleaved samples per pixel, as baseline TIFF strips
+// (classic TIFF below 4 GiB, BigTIFF above), UNCOMPRESSED -- the reference's own files are LZW-compressed by those
+// libraries, so files are equal in pixel content and geometry, not byte for byte.  Reads back the same subset
+// (uncompressed, chunky, 16-bit, either byte order, strips), which is what `stitch` needs for two of our own products.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace oiptiff {
+
+struct Info {
+    int64_t width = 0, height = 0, rows_per_strip = 0;
+    int spp = 1, bits = 16, compression = 1, planar = 1, photometric = 1;
+    bool big = false, little = true;
+    std::vector<uint64_t> strip_off, strip_cnt;
+};
+
+namespace detail {
+struct Out {
+    std::vector<uint8_t> b;
+    void u16(uint16_t v) { b.push_back((uint8_t)v); b.push_back((uint8_t)(v >> 8)); }
+    void u32(uint32_t v) { for (int i = 0; i < 4; ++i) b.push_back((uint8_t)(v >> (8 * i))); }
+    void u64(uint64_t v) { for (int i = 0; i < 8; ++i) b.push_back((uint8_t)(v >> (8 * i))); }
+};
+struct Entry {
+    uint16_t tag, type; // 3 SHORT, 4 LONG, 16 LONG8
+    std::vector<uint64_t> v;
+};
+inline size_t type_size(int t) { return t == 3 ? 2 : (t == 4 ? 4 : (t == 16 ? 8 : 1)); }
+} // namespace detail
+
+// pixels: height x width x spp, u16, row-major, samples interleaved in FILE order (the caller applies cv::imwrite's
+// channel swap).  photometric: 1 = BlackIsZero (1 sample), 2 = RGB (+ one unassociated-alpha extra sample when spp == 4)
+inline void write_u16(const std::string &path, const uint16_t *pixels, int64_t width, int64_t height, int spp, int photometric)
+{
+    using namespace detail;
+    if (width < 1 || height < 1 || (spp != 1 && spp != 4)) throw std::invalid_argument("tiff: unsupported geometry");
+    const uint64_t row_bytes = (uint64_t)width * spp * 2, data_bytes = row_bytes * (uint64_t)height;
+    int64_t rps = (int64_t)((8u << 20) / row_bytes);
+    if (rps < 1) rps = 1;
+    if (rps > height) rps = height;
+    const uint64_t n_strips = (uint64_t)((height + rps - 1) / rps);
+    const bool big = data_bytes + n_strips * 16 + 4096 >= 0xFFFF0000ull;
+    const int off_t = big ? 16 : 4;
+    std::vector<Entry> e;
+    e.push_back({256, 4, {(uint64_t)width}});
+    e.push_back({257, 4, {(uint64_t)height}});
+    e.push_back({258, 3, std::vector<uint64_t>((size_t)spp, 16)});
+    e.push_back({259, 3, {1}});
+    e.push_back({262, 3, {(uint64_t)photometric}});
+    e.push_back({273, (uint16_t)off_t, std::vector<uint64_t>(n_strips, 0)}); // filled below
+    e.push_back({277, 3, {(uint64_t)spp}});
+    e.push_back({278, 4, {(uint64_t)rps}});
+    e.push_back({279, (uint16_t)off_t, std::vector<uint64_t>(n_strips, 0)});
+    e.push_back({284, 3, {1}});
+    if (spp == 4) e.push_back({338, 3, {2}});
+    e.push_back({339, 3, std::vector<uint64_t>((size_t)spp, 1)});
+    // layout: header | IFD | out-of-line values | pad | pixel data
+    const size_t hdr = big ? 16 : 8, ent = big ? 20 : 12, inl = big ? 8 : 4;
+    const size_t ifd = hdr, ifd_bytes = (big ? 8 : 2) + e.size() * ent + (big ? 8 : 4);
+    size_t extra = ifd + ifd_bytes;
+    std::vector<size_t> where(e.size(), 0);
+    for (size_t i = 0; i < e.size(); ++i) {
+        const size_t nb = e[i].v.size() * type_size(e[i].type);
+        if (nb > inl) { where[i] = extra; extra += (nb + 7) & ~(size_t)7; }
+    }
+    const uint64_t data0 = (extra + 255) & ~(uint64_t)255;
+    for (uint64_t s = 0; s < n_strips; ++s) {
+        const uint64_t r0 = s * (uint64_t)rps, nr = std::min<uint64_t>((uint64_t)rps, (uint64_t)height - r0);
+        e[5].v[s] = data0 + r0 * row_bytes;
+        e[8].v[s] = nr * row_bytes;
+    }
+    Out o;
+    o.b.reserve(data0);
+    o.b.push_back('I'); o.b.push_back('I');
+    if (big) { o.u16(43); o.u16(8); o.u16(0); o.u64(ifd); } else { o.u16(42); o.u32((uint32_t)ifd); }
+    if (big) o.u64(e.size()); else o.u16((uint16_t)e.size());
+    auto put = [&](Out &dst, int type, uint64_t v) { if (type == 3) dst.u16((uint16_t)v); else if (type == 4) dst.u32((uint32_t)v); else dst.u64(v); };
+    for (size_t i = 0; i < e.size(); ++i) {
+        o.u16(e[i].tag); o.u16(e[i].type);
+        if (big) o.u64(e[i].v.size()); else o.u32((uint32_t)e[i].v.size());
+        const size_t at = o.b.size();
+        if (where[i]) { if (big) o.u64(where[i]); else o.u32((uint32_t)where[i]); }
+        else {
+            for (uint64_t v : e[i].v) put(o, e[i].type, v);
+            while (o.b.size() < at + inl) o.b.push_back(0);
+        }
+    }
+    if (big) o.u64(0); else o.u32(0); // no next IFD
+    for (size_t i = 0; i < e.size(); ++i) {
+        if (!where[i]) continue;
+        while (o.b.size() < where[i]) o.b.push_back(0);
+        for (uint64_t v : e[i].v) put(o, e[i].type, v);
+    }
+    while (o.b.size() < data0) o.b.push_back(0);
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("tiff: cannot create " + path);
+    bool ok = fwrite(o.b.data(), 1, o.b.size(), f) == o.b.size();
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(pixels);
+    for (uint64_t done = 0; ok && done < data_bytes;) {
+        const size_t n = (size_t)std::min<uint64_t>(data_bytes - done, 64u << 20);
+        ok = fwrite(p + done, 1, n, f) == n;
+        done += n;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw std::runtime_error("tiff: write failed: " + path);
+}
+
+namespace detail {
+struct In {
+    FILE *f;
+    bool little;
+    uint64_t rd(int n)
+    {
+        uint8_t b[8];
+        if (fread(b, 1, (size_t)n, f) != (size_t)n) throw std::runtime_error("tiff: truncated file");
+        uint64_t v = 0;
+        for (int i = 0; i < n; ++i) v |= (uint64_t)b[little ? i : n - 1 - i] << (8 * i);
+        return v;
+    }
+};
+} // namespace detail
+
+inline Info read_info(const std::string &path)
+{
+    using namespace detail;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("tiff: cannot open " + path);
+    Info I;
+    try {
+        char bo[2];
+        if (fread(bo, 1, 2, f) != 2 || (bo[0] != 'I' && bo[0] != 'M') || bo[0] != bo[1]) throw std::runtime_error("tiff: not a TIFF file: " + path);
+        In in{f, bo[0] == 'I'};
+        I.little = in.little;
+        const uint64_t magic = in.rd(2);
+        uint64_t ifd;
+        if (magic == 42) ifd = in.rd(4);
+        else if (magic == 43) { I.big = true; in.rd(2); in.rd(2); ifd = in.rd(8); }
+        else throw std::runtime_error("tiff: not a TIFF file: " + path);
+        fseeko(f, (off_t)ifd, SEEK_SET);
+        const uint64_t n = I.big ? in.rd(8) : in.rd(2);
+        for (uint64_t k = 0; k < n; ++k) {
+            fseeko(f, (off_t)(ifd + (I.big ? 8 : 2) + k * (I.big ? 20 : 12)), SEEK_SET);
+            const int tag = (int)in.rd(2), type = (int)in.rd(2);
+            const uint64_t cnt = I.big ? in.rd(8) : in.rd(4);
+            const size_t ts = type == 3 ? 2 : (type == 4 ? 4 : (type == 16 ? 8 : (type == 1 ? 1 : 0)));
+            auto values = [&]() {
+                std::vector<uint64_t> v;
+                if (!ts) return v;
+                if (cnt * ts > (I.big ? 8u : 4u)) fseeko(f, (off_t)(I.big ? in.rd(8) : in.rd(4)), SEEK_SET);
+                for (uint64_t i = 0; i < cnt; ++i) v.push_back(in.rd((int)ts));
+                return v;
+            };
+            switch (tag) {
+            case 256: I.width = (int64_t)values().at(0); break;
+            case 257: I.height = (int64_t)values().at(0); break;
+            case 258: I.bits = (int)values().at(0); break;
+            case 259: I.compression = (int)values().at(0); break;
+            case 262: I.photometric = (int)values().at(0); break;
+            case 273: I.strip_off = values(); break;
+            case 277: I.spp = (int)values().at(0); break;
+            case 278: I.rows_per_strip = (int64_t)values().at(0); break;
+            case 279: I.strip_cnt = values(); break;
+            case 284: I.planar = (int)values().at(0); break;
+            case 322: case 323: case 324: case 325: throw std::runtime_error("tiff: tiled TIFF is not supported: " + path);
+            default: break;
+            }
+        }
+    } catch (...) {
+        fclose(f);
+        throw;
+    }
+    fclose(f);
+    if (I.rows_per_strip <= 0 || I.rows_per_strip > I.height) I.rows_per_strip = I.height;
+    return I;
+}
+
+// the whole raster, u16 host order, samples interleaved in file order
+inline void read_u16(const std::string &path, const Info &I, uint16_t *dst)
+{
+    if (I.compression != 1)
+        throw std::runtime_error("tiff: compressed TIFF (compression " + std::to_string(I.compression) +
+                                 ") is not supported by this build -- re-save it uncompressed: " + path);
+    if (I.bits != 16 || I.planar != 1 || I.strip_off.empty() || I.strip_off.size() != I.strip_cnt.size())
+        throw std::runtime_error("tiff: only 16-bit chunky strip TIFF is supported: " + path);
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("tiff: cannot open " + path);
+    const uint64_t row_bytes = (uint64_t)I.width * I.spp * 2;
+    bool ok = true;
+    for (size_t s = 0; ok && s < I.strip_off.size(); ++s) {
+        const uint64_t r0 = (uint64_t)s * (uint64_t)I.rows_per_strip;
+        if (r0 >= (uint64_t)I.height) break;
+        const uint64_t want = std::min<uint64_t>((uint64_t)I.rows_per_strip, (uint64_t)I.height - r0) * row_bytes;
+        ok = I.strip_cnt[s] >= want && fseeko(f, (off_t)I.strip_off[s], SEEK_SET) == 0 &&
+             fread(reinterpret_cast<uint8_t *>(dst) + r0 * row_bytes, 1, (size_t)want, f) == (size_t)want;
+    }
+    fclose(f);
+    if (!ok) throw std::runtime_error("tiff: truncated or inconsistent strips: " + path);
+    if (!I.little) {
+        const uint64_t n = (uint64_t)I.width * I.height * I.spp;
+        for (uint64_t i = 0; i < n; ++i) dst[i] = (uint16_t)((dst[i] >> 8) | (dst[i] << 8));
+    }
+}
+
+} // namespace oiptiff

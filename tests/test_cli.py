@@ -141,6 +141,13 @@ def test_prestitch_and_stitch_task_flow(cli, tmp_path, oracle_mod):
     assert r.returncode == 0, r.stdout + r.stderr
     st = np.fromfile(os.path.join(d, "stitched-PAN.RAW"), np.uint16).reshape(rows, 2 * (W - 100))
     assert np.array_equal(st[:, :W - 100], rrc1[:, :W - 100]) and np.array_equal(st[:, W - 100:], pre[:, 100:])
+    # no -o: single-band TIFF under the reference's default name (ref imageop.h:299-303, GTiff :316-328)
+    r = run(cli, ["stitch", "--image1=SYN_PAN-1.RRC.RAW", "--image2=SYN_PAN-2.RRC.PRESTT.RAW", "--fold-cols=200"], d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    import cv2
+    os.environ.setdefault("OPENCV_IO_MAX_IMAGE_PIXELS", str(1 << 40))
+    tif = cv2.imread(os.path.join(d, f"stitched_{2 * (W - 100)}n16b.TIFF"), cv2.IMREAD_UNCHANGED)
+    assert tif is not None and np.array_equal(tif, st)
 
 
 @pytest.mark.gpu
@@ -165,9 +172,29 @@ def test_default_action_mss(cli, tmp_path, oracle_mod):
     # default 5 sections x 16000 lines -> std::invalid_argument -> exit code 2 (ref preproc.h:234-237, main.cpp:336-339)
     r = run(cli, args, d)
     assert r.returncode == 2 and "too many sections" in (r.stdout + r.stderr)
-    r = run(cli, args + ["--poly", "poly.txt"], d)
+    r = run(cli, args + ["--poly", "poly.txt", "--aligned-raw"], d)
     assert r.returncode == 0, r.stdout + r.stderr
     planes = [oracle_mod.rrc(p, k) for p, k in zip(oracle_mod.mss_split(mss), kbs)]
     n, want = oracle_mod.band_align(planes, cX, cY)
     got = np.fromfile(os.path.join(d, "SYN_MSS-1.ALIGNED.RAW"), np.uint16).reshape(lines - 520, wb, 4)
     assert n == lines - 520 and np.array_equal(got[:n], want[:n])
+    # the reference's product is <stem>.ALIGNED.TIFF written by cv::imwrite (ref preproc.h:167-185): read it the way the
+    # reference reads such files (cv::imread IMREAD_UNCHANGED, ref imageop.h:392) -> the CV_16UC4 memory image
+    import cv2
+    tif = cv2.imread(os.path.join(d, "SYN_MSS-1.ALIGNED.TIFF"), cv2.IMREAD_UNCHANGED)
+    assert tif is not None and tif.shape == (lines - 520, wb, 4) and np.array_equal(tif[:n], want[:n])
+    # stitch two 4-channel TIFFs (IMO::StitchTiff, ref imageop.h:365-457; GDAL variant with band map :460-567)
+    os.rename(os.path.join(d, "SYN_MSS-1.ALIGNED.TIFF"), os.path.join(d, "L.TIFF"))
+    cv2.imwrite(os.path.join(d, "R.TIFF"), tif[:, ::-1].copy(), [cv2.IMWRITE_TIFF_COMPRESSION, 1])   # a libtiff-written input
+    r = run(cli, ["stitch", "--image1=L.TIFF", "--image2=R.TIFF", "--fold-cols=50"], d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    st = cv2.imread(os.path.join(d, "stitched.TIFF"), cv2.IMREAD_UNCHANGED)                          # default name, ref :373-375
+    ref_st = oracle_mod.stitch_concat_c4([tif, tif[:, ::-1].copy()], 25)
+    assert np.array_equal(st, ref_st)
+    r = run(cli, ["stitch", "--image1=L.TIFF", "--image2=R.TIFF", "--fold-cols=50", "-g", "-m", "3,2,1,4", "-o", "g.TIFF"], d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    g = cv2.imread(os.path.join(d, "g.TIFF"), cv2.IMREAD_UNCHANGED)
+    # GDAL band b = memory channel map[b]-1 (ref :529); cv2.imread swaps samples 0/2 of what is in the file
+    file_order = oracle_mod.stitch_concat_c4([tif, tif[:, ::-1].copy()], 25, [3, 2, 1, 4])
+    assert np.array_equal(g, file_order[:, :, [2, 1, 0, 3]])
+    assert run(cli, ["stitch", "--image1=L.TIFF", "--image2=R.TIFF", "--fold-cols=50", "-o", "x.RAW"], d).returncode == 2   # ref :376-380

@@ -1,0 +1,48 @@
+"""host/tiff_io.hpp against libtiff as shipped in cv2 (the library the reference writes its TIFFs with,
+ref preproc.h:167-185, imageop.h:444): files we write are read back by cv2.imread with the same pixels, and uncompressed
+files cv2 writes are read by our reader; compressed input is refused with a clear message."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("tiff") / "tiff_io_host_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", out, os.path.join(HERE, "native", "tiff_io_host_test.cpp")])
+    return out
+
+
+@pytest.mark.parametrize("h,w,spp", [(37, 53, 1), (1200, 3072, 4), (5, 70000, 1), (3000, 1500, 4)])
+def test_written_files_are_read_by_libtiff(exe, tmp_path, h, w, spp):
+    px = np.random.default_rng(h + w).integers(0, 65536, (h, w, spp), dtype=np.uint16)
+    raw, tif = str(tmp_path / "in.raw"), str(tmp_path / "out.TIFF")
+    px.tofile(raw)
+    subprocess.check_call([exe, "write", tif, str(w), str(h), str(spp), raw])
+    img = cv2.imread(tif, cv2.IMREAD_UNCHANGED)
+    assert img is not None and img.dtype == np.uint16
+    if spp == 1:
+        assert np.array_equal(img, px[:, :, 0])
+    else:  # cv::imread hands a 4-sample RGBA file back as BGRA: samples 0 and 2 swapped
+        assert np.array_equal(img, px[:, :, [2, 1, 0, 3]])
+    # and our own reader
+    back = str(tmp_path / "back.raw")
+    dims = subprocess.check_output([exe, "read", tif, back], text=True).split()
+    assert [int(v) for v in dims] == [w, h, spp]
+    assert np.array_equal(np.fromfile(back, np.uint16).reshape(h, w, spp), px)
+
+
+def test_reads_uncompressed_libtiff_files_and_refuses_lzw(exe, tmp_path):
+    img = np.random.default_rng(2).integers(0, 65536, (300, 200, 4), dtype=np.uint16)
+    plain, lzw, back = str(tmp_path / "plain.TIFF"), str(tmp_path / "lzw.TIFF"), str(tmp_path / "back.raw")
+    assert cv2.imwrite(plain, img, [cv2.IMWRITE_TIFF_COMPRESSION, 1])
+    assert cv2.imwrite(lzw, img)  # cv::imwrite default: LZW, what the reference produces
+    subprocess.check_call([exe, "read", plain, back])
+    assert np.array_equal(np.fromfile(back, np.uint16).reshape(300, 200, 4), img[:, :, [2, 1, 0, 3]])  # file order = RGBA
+    r = subprocess.run([exe, "read", lzw, back], capture_output=True, text=True)
+    assert r.returncode == 1 and "compressed TIFF" in r.stderr
