@@ -79,3 +79,32 @@ def covers(desc: capi.PanDesc, ccd: int) -> bool:
             if not any(c.seg[s].row0 <= g < c.seg[s].row0 + c.seg[s].n_rows for s in range(c.n_seg)):
                 return False
     return True
+
+
+# ------------------------------------------------------------------------------------------------
+# N1 (ref stitcher.h:148-201): the sections of the inter-CMOS offset estimate on a sharded strip
+# ------------------------------------------------------------------------------------------------
+def stt_section_offsets(total_lines: int, sections: int, lines_per_section: int) -> List[int]:
+    """first line of every section (ref stitcher.h:151-152, :167)"""
+    gap = (total_lines - sections * lines_per_section) // (sections + 1)
+    return [gap + i * (gap + lines_per_section) for i in range(sections)]
+
+
+def stt_section_owner(total_lines: int, sections: int, lines_per_section: int, world: int) -> List[int]:
+    """rank whose scanline block holds a section entirely, or -1 when it straddles two blocks (then the caller must hand
+    those rows to one rank -- oip_stt_parameters marks such a section valid = -1 instead of guessing)"""
+    owners = []
+    for off in stt_section_offsets(total_lines, sections, lines_per_section):
+        own = -1
+        for r in range(world):
+            lo, hi = shard_range(total_lines, world, r)
+            if lo <= off and off + lines_per_section <= hi:
+                own = r
+        owners.append(own)
+    return owners
+
+
+def stt_combine(sums: Sequence[float]):
+    """(dx, dy, response) means from the all-reduced {sum dx, sum dy, sum response, n valid} (ref stitcher.h:197-199);
+    None when no section was valid (the reference throws)"""
+    return None if sums[3] == 0 else (sums[0] / sums[3], sums[1] / sums[3], sums[2] / sums[3])

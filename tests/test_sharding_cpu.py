@@ -98,3 +98,67 @@ def test_last_rank_stale_rows_owner():
     assert sl > sf, "dY > 0 with a partial last section must read stale rows"
     owner = [r for r in range(world) if sharding.shard_range(total, world, r)[0] <= sf < sharding.shard_range(total, world, r)[1]]
     assert owner[0] in req[2] or owner[0] == world - 1
+
+
+# ------------------------------------------------------------------------------------------------ N1 on shards
+def _stt_worker(rank, world, port, q):
+    """each rank correlates (CPU oracle standing in for oip_stt_parameters) the sections its block holds and the four
+    sums go through ONE small all-reduce -- the only collective of the path"""
+    import numpy as np
+    import oracle
+    from test_phasecorr_cpu import _pair
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lines, w, ov, ns, lps = 4800, 512, 200, 4, 500
+        sa, sb = _pair(lines, ov, 1.37, -2.61, seed=3)
+        pan1 = np.zeros((lines, w), np.uint16); pan2 = np.zeros((lines, w), np.uint16)
+        pan1[:, w - ov:] = sa
+        pan2[:, :ov] = sb
+        lo, hi = sharding.shard_range(lines, world, rank)
+        owners = sharding.stt_section_owner(lines, ns, lps, world)
+        sums = np.zeros(4)
+        for off, own in zip(sharding.stt_section_offsets(lines, ns, lps), owners):
+            if own != rank:
+                continue
+            assert lo <= off and off + lps <= hi
+            dx, dy, r = oracle.phase_correlate(pan1[off:off + lps, w - ov:].astype(np.float32), pan2[off:off + lps, :ov].astype(np.float32))
+            if r >= 0.4:
+                sums += [dx, dy, r, 1]
+        t = torch.from_numpy(sums)
+        dist.all_reduce(t)
+        whole_rows, whole_mean = oracle.stt_parameters(pan1, pan2, overlap_cols=ov, sections=ns, lines_per_section=lps)
+        q.put((rank, owners, sharding.stt_combine(t.tolist()), whole_mean))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stt_sections_on_two_shards_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stt_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, owners, mean, whole in res:
+        assert owners == [0, 0, 1, 1]
+        assert mean is not None and all(abs(a - b) < 1e-12 for a, b in zip(mean, whole))
+
+
+def test_stt_section_owner_reports_straddlers():
+    # reference defaults on a 4 x 65536-line strip: 16000-line sections, some cross a block boundary
+    total, world = 4 * 65536, 4
+    offs = sharding.stt_section_offsets(total, 10, 16000)
+    own = sharding.stt_section_owner(total, 10, 16000, world)
+    gap = (total - 160000) // 11
+    assert offs[0] == gap and offs[1] - offs[0] == gap + 16000
+    for off, o in zip(offs, own):
+        inside = [r for r in range(world) if sharding.shard_range(total, world, r)[0] <= off and off + 16000 <= sharding.shard_range(total, world, r)[1]]
+        assert (o == -1 and not inside) or inside == [o]
+    assert sharding.stt_combine([0, 0, 0, 0]) is None and sharding.stt_combine([2.0, 4.0, 1.0, 2.0]) == (1.0, 2.0, 0.5)
