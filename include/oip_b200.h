@@ -206,6 +206,9 @@ void oip_cubic_tab(float *tab128);
 /* source rows [*first,*last) of CCD `ccd` that producing [row0,row0+n_rows) reads (halo planning) */
 int oip_pan_rows_needed(const oip_pan_desc *desc, int ccd, int64_t *first, int64_t *last,
                         int64_t *stale_first, int64_t *stale_last);
+/* the same as up to max_ranges disjoint, sorted [first,last) pairs in ranges[2*max_ranges] (ranges closer than 64 rows
+ * are merged): what a host-buffer pipeline has to copy for one row block */
+int oip_pan_row_ranges(const oip_pan_desc *desc, int ccd, int64_t *ranges, int max_ranges, int *n_ranges);
 
 /* host-only planning diagnostic (no device work): how oip_pan_pipeline would split the output between its
  * regular-interior fast kernel and the exact generic kernel.  cover (n_rows x out_pitch_px bytes, zeroed by the

@@ -105,6 +105,7 @@ SYMBOLS = {
     "oip_pan_check_error": (_I, [_VP]),
     "oip_cubic_tab": (None, [_VP]),
     "oip_pan_rows_needed": (_I, [C.POINTER(PanDesc), _I, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
+    "oip_pan_row_ranges": (_I, [C.POINTER(PanDesc), _I, C.POINTER(_I64), _I, C.POINTER(_I)]),
     "oip_shift_cubic_u16": (_I, [_VP, _VP, _VP, _I, _I64, _D, _D, _I, _I]),
     "oip_stitch_concat_u16": (_I, [_VP, C.POINTER(_VP), _I, _I, _I64, _I, _VP]),
     "oip_band_align_merge": (_I, [_VP, _VP, C.POINTER(MssDesc), _VP, C.POINTER(_I64)]),

@@ -11,7 +11,8 @@
 
 namespace oip {
 
-constexpr int HP_SLOTS = 3;
+constexpr int HP_SLOTS_MAX = 6;
+static int hp_slots() { static const int n = [] { const char *e = getenv("OIP_HP_SLOTS"); int v = e ? atoi(e) : 3; return v < 2 ? 2 : (v > HP_SLOTS_MAX ? HP_SLOTS_MAX : v); }(); return n; }
 
 struct HostPipe {
     cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -21,7 +22,7 @@ struct HostPipe {
         void *d_out = nullptr;
         size_t out_cap = 0;
         cudaEvent_t in_ready = nullptr, compute_done = nullptr, out_done = nullptr;
-    } slot[HP_SLOTS];
+    } slot[HP_SLOTS_MAX];
     void *d_kb[8] = {};
     size_t kb_cap[8] = {};
 };
@@ -131,7 +132,8 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
     {
         int64_t left = h->n_rows;
         std::vector<int64_t> head, tail;
-        for (int64_t b = std::min<int64_t>(256, HP_BLOCK_ROWS); b < HP_BLOCK_ROWS && left >= 4 * b; b *= 2) {
+        static const bool no_ramp = getenv("OIP_HP_NORAMP") != nullptr; // timing experiment
+        for (int64_t b = std::min<int64_t>(256, HP_BLOCK_ROWS); !no_ramp && b < HP_BLOCK_ROWS && left >= 4 * b; b *= 2) {
             head.push_back(b);
             tail.push_back(b);
             left -= 2 * b;
@@ -144,48 +146,44 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
     int64_t r0 = h->row0;
     for (size_t bi = 0; bi < sizes.size(); r0 += sizes[bi], ++bi, ++blk) {
         const int64_t nr = sizes[bi];
-        HostPipe::Slot &S = hp->slot[blk % HP_SLOTS];
+        HostPipe::Slot &S = hp->slot[blk % hp_slots()];
         oip_pan_desc d = *h;
         d.row0 = r0;
         d.n_rows = nr;
         // ---- H2D of the rows this block reads (own rows + halo + stale-section rows)
-        OIP_CUDA(cudaStreamWaitEvent(hp->h2d, S.compute_done, 0)); // the slot's previous kernel is done with d_in
+        static const bool no_wait = getenv("OIP_HP_NOWAIT") != nullptr; // timing experiment (data hazards!)
+        if (!no_wait) OIP_CUDA(cudaStreamWaitEvent(hp->h2d, S.compute_done, 0)); // the slot's previous kernel is done with d_in
         for (int i = 0; i < h->n_ccd; ++i) {
             const oip_ccd_src &src = h->ccd[i];
-            int64_t first, last, sfirst, slast;
-            rc = oip_pan_rows_needed(&d, i, &first, &last, &sfirst, &slast);
+            int64_t rg[2 * OIP_MAX_SEG];
+            int n_rg = 0;
+            rc = oip_pan_row_ranges(&d, i, rg, OIP_MAX_SEG, &n_rg);
             if (rc) return rc;
             const oip_row_seg &hs = src.seg[0];
-            first = std::max(first, hs.row0);
-            last = std::min(last, hs.row0 + hs.n_rows);
-            sfirst = std::max(sfirst, hs.row0);
-            slast = std::min(slast, hs.row0 + hs.n_rows);
             const int64_t rb = row_bytes(src.fmt, h->w);
             const int64_t pitch_d = (rb + 15) / 16 * 16;
-            const int64_t n_main = std::max<int64_t>(0, last - first), n_stale = std::max<int64_t>(0, slast - sfirst);
-            rc = hp_reserve(&S.d_in[i], &S.in_cap[i], (size_t)((HP_BLOCK_ROWS + 64 + n_stale) * pitch_d));
-            if (rc) return rc;
-            if ((size_t)((n_main + n_stale) * pitch_d) > S.in_cap[i]) {
-                rc = hp_reserve(&S.d_in[i], &S.in_cap[i], (size_t)((n_main + n_stale) * pitch_d));
-                if (rc) return rc;
+            int64_t n_all = 0;
+            for (int k = 0; k < n_rg; ++k) {
+                rg[2 * k] = std::max(rg[2 * k], hs.row0);
+                rg[2 * k + 1] = std::min(rg[2 * k + 1], hs.row0 + hs.n_rows);
+                n_all += std::max<int64_t>(0, rg[2 * k + 1] - rg[2 * k]);
             }
+            rc = hp_reserve(&S.d_in[i], &S.in_cap[i], (size_t)(std::max<int64_t>(HP_BLOCK_ROWS + 256, n_all) * pitch_d));
+            if (rc) return rc;
             uint8_t *dst = (uint8_t *)S.d_in[i];
             oip_ccd_src &o = d.ccd[i];
             o.d_kb = d_kb[i];
             o.n_seg = 0;
-            if (n_main > 0) {
-                OIP_CUDA(copy_rows(dst, (size_t)pitch_d, (const uint8_t *)hs.base + (first - hs.row0) * hs.pitch_bytes,
-                                   (size_t)hs.pitch_bytes, (size_t)rb, (size_t)n_main, cudaMemcpyHostToDevice, hp->h2d));
-                o.seg[o.n_seg++] = {dst, first, n_main, pitch_d};
-            }
-            if (n_stale > 0) {
-                uint8_t *dst2 = dst + n_main * pitch_d;
-                OIP_CUDA(copy_rows(dst2, (size_t)pitch_d, (const uint8_t *)hs.base + (sfirst - hs.row0) * hs.pitch_bytes,
-                                   (size_t)hs.pitch_bytes, (size_t)rb, (size_t)n_stale, cudaMemcpyHostToDevice, hp->h2d));
-                o.seg[o.n_seg++] = {dst2, sfirst, n_stale, pitch_d};
+            for (int k = 0; k < n_rg; ++k) {
+                const int64_t a = rg[2 * k], n = rg[2 * k + 1] - a;
+                if (n <= 0) continue;
+                OIP_CUDA(copy_rows(dst, (size_t)pitch_d, (const uint8_t *)hs.base + (a - hs.row0) * hs.pitch_bytes, (size_t)hs.pitch_bytes,
+                                   (size_t)rb, (size_t)n, cudaMemcpyHostToDevice, hp->h2d));
+                o.seg[o.n_seg++] = {dst, a, n, pitch_d};
+                dst += n * pitch_d;
             }
             if (o.n_seg == 0) { // nothing to read (can only happen for degenerate geometry): keep a valid segment
-                o.seg[0] = {dst, 0, 0, pitch_d};
+                o.seg[0] = {S.d_in[i], 0, 0, pitch_d};
                 o.n_seg = 1;
             }
         }
@@ -194,7 +192,7 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
         rc = hp_reserve(&S.d_out, &S.out_cap, (size_t)(HP_BLOCK_ROWS * out_w * 2));
         if (rc) return rc;
         OIP_CUDA(cudaStreamWaitEvent(ctx->stream, S.in_ready, 0));
-        OIP_CUDA(cudaStreamWaitEvent(ctx->stream, S.out_done, 0)); // previous D2H of this slot finished
+        if (!no_wait) OIP_CUDA(cudaStreamWaitEvent(ctx->stream, S.out_done, 0)); // previous D2H of this slot finished
         d.d_out = (uint16_t *)S.d_out;
         d.out_pitch_px = out_w;
         static const bool skip_kernels = getenv("OIP_HP_SKIP_KERNELS") != nullptr; // timing experiment: copies only

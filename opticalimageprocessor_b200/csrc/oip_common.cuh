@@ -35,7 +35,7 @@ struct oip_ctx {
     int64_t plan_fast_ctas = 0;  // pan_fast_kernel CTAs (4 warp-tiles each)
     size_t plan_fast_off = 0;    // byte offset of the FastTile array inside d_plan
     // tunables (oip_ctx_set_option)
-    int host_block_rows = 4096;  // oip_pan_pipeline_host: rows per H2D / compute / D2H block
+    int host_block_rows = 2048;  // oip_pan_pipeline_host: rows per H2D / compute / D2H block
     int pan_fast = 1;            // 0: everything on the generic kernel
     int pan_fast_stages = 4;     // TMA stages per warp
     int pan_fast_rows = 128;     // output rows per warp-tile

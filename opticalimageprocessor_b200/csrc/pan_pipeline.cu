@@ -1203,6 +1203,53 @@ extern "C" int oip_pan_rows_needed(const oip_pan_desc *d, int ccd, int64_t *firs
     return OIP_OK;
 }
 
+// The same, as a list of disjoint row ranges: the stale rows of a partial last section come from two places of the
+// previous section (just below the fresh rows, and the last rows of the 30000-row buffer), ~27000 rows apart -- a
+// bounding range would make a host pipeline copy the whole section.  Ranges closer than 64 rows are merged.
+extern "C" int oip_pan_row_ranges(const oip_pan_desc *d, int ccd, int64_t *ranges, int max_ranges, int *n_ranges)
+{
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    if (ccd < 0 || ccd >= d->n_ccd || !ranges || !n_ranges || max_ranges < 1) return fail(OIP_E_INVALID, "oip_pan_row_ranges: bad argument");
+    std::vector<std::pair<int64_t, int64_t>> iv;
+    if (!d->ccd[ccd].shifted) {
+        iv.push_back({d->row0, d->row0 + d->n_rows});
+    } else {
+        std::vector<ShiftSegment> segs;
+        if (!plan_shift_segments(d->total_rows, d->section_rows, d->row_guard, d->ccd[ccd].dY, segs))
+            return fail(OIP_E_INVALID, "invalid section geometry");
+        for (const ShiftSegment &s : segs) {
+            int64_t g0 = std::max<int64_t>(s.g0, d->row0), g1 = std::min<int64_t>(s.g1, d->row0 + d->n_rows);
+            if (g1 <= g0) continue;
+            int64_t ta = tap_base(s.j0 + (g0 - s.g0), d->ccd[ccd].dY);
+            int64_t tb = (int64_t)tap_base(s.j0 + (g1 - 1 - s.g0), d->ccd[ccd].dY) + 3;
+            ta = std::max<int64_t>(ta, 0); tb = std::min<int64_t>(tb, s.hbuf - 1);
+            if (tb < ta) continue;
+            const int64_t fa = ta, fb = std::min<int64_t>(tb, s.rows_s - 1);
+            if (fb >= fa) iv.push_back({s.sec_off + fa, s.sec_off + fb + 1});
+            const int64_t sa = std::max<int64_t>(ta, s.rows_s), sb = tb;
+            if (sb >= sa && s.stale_off >= 0) iv.push_back({s.stale_off + sa, s.stale_off + sb + 1});
+        }
+    }
+    std::sort(iv.begin(), iv.end());
+    std::vector<std::pair<int64_t, int64_t>> m;
+    for (const auto &r : iv) {
+        if (r.second <= r.first) continue;
+        if (!m.empty() && r.first <= m.back().second + 64) m.back().second = std::max(m.back().second, r.second);
+        else m.push_back(r);
+    }
+    while ((int)m.size() > max_ranges) { // too many: merge the two closest
+        size_t best = 0;
+        for (size_t i = 1; i + 1 < m.size(); ++i)
+            if (m[i + 1].first - m[i].second < m[best + 1].first - m[best].second) best = i;
+        m[best].second = m[best + 1].second;
+        m.erase(m.begin() + best + 1);
+    }
+    *n_ranges = (int)m.size();
+    for (size_t i = 0; i < m.size(); ++i) { ranges[2 * i] = m[i].first; ranges[2 * i + 1] = m[i].second; }
+    return OIP_OK;
+}
+
 extern "C" int oip_shift_cubic_u16(oip_ctx *ctx, const uint16_t *d_src, uint16_t *d_dst, int w, int64_t rows,
                                    double dX, double dY, int section_rows, int row_guard)
 {

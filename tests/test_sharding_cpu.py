@@ -162,3 +162,29 @@ def test_stt_section_owner_reports_straddlers():
         inside = [r for r in range(world) if sharding.shard_range(total, world, r)[0] <= off and off + 16000 <= sharding.shard_range(total, world, r)[1]]
         assert (o == -1 and not inside) or inside == [o]
     assert sharding.stt_combine([0, 0, 0, 0]) is None and sharding.stt_combine([2.0, 4.0, 1.0, 2.0]) == (1.0, 2.0, 0.5)
+
+
+def test_row_ranges_are_tight_and_inside_the_bounding_ranges():
+    """oip_pan_row_ranges (what the host-buffer pipeline copies per row block): disjoint sorted ranges inside the bounding
+    ranges of oip_pan_rows_needed, covering their end points, and far smaller than the bounding stale range of the
+    partial last section (C2: one stale row ~27000 rows above the block instead of the whole previous section)"""
+    import ctypes as C
+    L = capi.load()
+    total = 32768
+    for r0, nr in [(0, 4096), (12288, 4096), (28672, 4096), (30000, 2768), (0, total)]:
+        d = _make_desc(total, 0, 1, [0.0, -2.61, 3.19])
+        d.row0, d.n_rows = r0, nr
+        for i in range(3):
+            (f, l), (sf, sl) = sharding.rows_needed(d, i)
+            rg = (C.c_int64 * 8)()
+            n = C.c_int()
+            capi.check(L.oip_pan_row_ranges(C.byref(d), i, rg, 4, C.byref(n)))
+            rs = [(rg[2 * k], rg[2 * k + 1]) for k in range(n.value)]
+            assert rs == sorted(rs) and all(a < b for a, b in rs)
+            assert all(b0 < a1 for (_, b0), (a1, _) in zip(rs, rs[1:]))
+            lo, hi = min(f if l > f else 1 << 60, sf if sl > sf else 1 << 60), max(l, sl)
+            assert rs[0][0] == lo and rs[-1][1] == hi
+            for a, b in rs:
+                assert (f <= a and b <= l) or (sf <= a and b <= sl) or (min(f, sf) <= a and b <= max(l, sl))
+            if (r0, nr, i) == (28672, 4096, 2):
+                assert sl - sf > 20000 and sum(b - a for a, b in rs) < nr + 16
