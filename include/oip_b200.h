@@ -245,6 +245,12 @@ typedef struct {
     int overlap;            /* IBPA_DEFAULT_LINEOVERLAP [520] */
     int keep_leading;       /* -k */
     int min_process_lines;  /* IBPA_MIN_PROCESSLINES [1500] */
+    /* section shard: the sections of the reference loop are independent, so a rank may produce a subset.
+     * sec_count == 0: all sections (then src_row0 must be 0).  Otherwise sections [sec_first, sec_first + sec_count) of
+     * the `lines`-line strip; d_mss points at strip line src_row0 (the rank holds at least the lines of its sections)
+     * and d_out row 0 is the first output row of section sec_first. */
+    int sec_first, sec_count;
+    int64_t src_row0;
 } oip_mss_desc;
 int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_mss_desc *desc, uint16_t *d_out,
                          int64_t *rows_written);

@@ -48,7 +48,8 @@ class MssDesc(C.Structure):
     _fields_ = [("fmt", C.c_int), ("wb", C.c_int), ("lines", C.c_int64), ("pitch_px", C.c_int64),
                 ("d_kb", C.c_void_p * 4), ("cX", C.c_double * 8), ("cY", C.c_double * 12),
                 ("lines_per_section", C.c_int), ("line_offset", C.c_int64), ("overlap", C.c_int),
-                ("keep_leading", C.c_int), ("min_process_lines", C.c_int)]
+                ("keep_leading", C.c_int), ("min_process_lines", C.c_int), ("sec_first", C.c_int), ("sec_count", C.c_int),
+                ("src_row0", C.c_int64)]
 
 
 class SttConfig(C.Structure):

@@ -241,6 +241,17 @@ static int64_t build_sections(const oip_mss_desc *d, std::vector<mssfast::Sectio
         processed += (int64_t)n - y0;                                                   // :396,405
         offset += (uint64_t)(lps - overlap);                                            // :407
     }
+    if (d->sec_count > 0) { // section shard: keep [sec_first, sec_first + sec_count), relative to the shard's buffers
+        std::vector<mssfast::Section> keep;
+        int64_t out0 = 0, rows = 0;
+        for (int i = d->sec_first; i < (int)secs.size() && i < d->sec_first + d->sec_count; ++i) {
+            if (keep.empty()) out0 = secs[i].dst_row0;
+            keep.push_back({secs[i].sec_off - d->src_row0, secs[i].rows, secs[i].y0, secs[i].dst_row0 - out0});
+            rows += secs[i].rows - secs[i].y0;
+        }
+        secs.swap(keep);
+        return rows;
+    }
     return processed;
 }
 
@@ -291,17 +302,25 @@ extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_m
     if (lps < overlap * 2) return fail(OIP_E_INVALID, "Lines per section too small or section overlapped lines too large");
     if (d->lines - d->line_offset < min_lines) return fail(OIP_E_INVALID, "Too few image lines left to process");
     if (overlap < 0 || d->line_offset < 0) return fail(OIP_E_INVALID, "negative overlap / line offset");
+    if (d->sec_count < 0 || d->sec_first < 0 || d->src_row0 < 0 || (d->sec_count == 0 && d->src_row0 != 0))
+        return fail(OIP_E_INVALID, "oip_band_align_merge: bad section shard (sec_first=%d sec_count=%d src_row0=%lld)", d->sec_first,
+                    d->sec_count, (long long)d->src_row0);
 
     // ---- section loop (ref preproc.h:379-408) -> fast warp-tiles + generic tiles; cached on the geometry and the map
     const bool fast_ok = ctx->mss_fast != 0 && (((uintptr_t)d_mss & 15) == 0) && ((d->pitch_px * 2) % 16 == 0) && d->wb >= 16;
-    struct Key { int wb, lps, overlap, keep, min_lines, fast, tile_rows; int64_t lines, off; double cX[8], cY[12]; } key{};
+    struct Key { int wb, lps, overlap, keep, min_lines, fast, tile_rows, sec_first, sec_count; int64_t lines, off, src_row0; double cX[8], cY[12]; } key{};
     key.wb = d->wb; key.lps = lps; key.overlap = overlap; key.keep = d->keep_leading != 0; key.min_lines = min_lines;
     key.fast = fast_ok; key.tile_rows = ctx->mss_fast_rows; key.lines = d->lines; key.off = d->line_offset;
+    key.sec_first = d->sec_first; key.sec_count = d->sec_count; key.src_row0 = d->src_row0;
     memcpy(key.cX, d->cX, sizeof key.cX); memcpy(key.cY, d->cY, sizeof key.cY);
     const uint8_t *kbytes = reinterpret_cast<const uint8_t *>(&key);
     if (ctx->mss_plan_key.size() != sizeof key || memcmp(ctx->mss_plan_key.data(), kbytes, sizeof key) != 0) {
         std::vector<mssfast::Section> secs;
         const int64_t processed = build_sections(d, secs);
+        for (const mssfast::Section &sc : secs)
+            if (sc.sec_off < 0)
+                return fail(OIP_E_RANGE, "oip_band_align_merge: section shard starts at strip line %lld, before src_row0 = %lld",
+                            (long long)(sc.sec_off + d->src_row0), (long long)d->src_row0);
         std::vector<mss::Tile> tiles;
         std::vector<mssfast::FTile> ftiles;
         mssfast::plan(d, secs, fast_ok, ctx->mss_fast_rows, tiles, ftiles);
@@ -366,7 +385,7 @@ extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_m
     if (ctx->mss_fast_ctas > 0) {
         mssfast::Params F;
         memset(&F, 0, sizeof F);
-        int rc = mssfast::encode(&F.tmap, d_mss, 4 * d->wb, d->lines, d->pitch_px * 2);
+        int rc = mssfast::encode(&F.tmap, d_mss, 4 * d->wb, d->lines - d->src_row0, d->pitch_px * 2);
         if (rc) return rc;
         for (int b = 0; b < 4; ++b) F.kb[b] = d->d_kb[b];
         memcpy(F.cX, d->cX, sizeof F.cX); memcpy(F.cY, d->cY, sizeof F.cY);

@@ -760,6 +760,7 @@ static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows
     std::vector<panfast::FastTile> fl;
     // keep the plan small on very long strips: taller warp-tiles
     int th = std::max(16, fast_rows);
+    if (fast_rows == 128 && d->n_rows >= 65536) th = 256; // long strips: the per-tile prologue amortises better (measured, tools/sweep_sizes.py)
     while ((double)d->n_rows / th * ((double)n * w / 248.0) > 400000.0) th *= 2;
     int out_x = 0;
     for (int i = 0; i < n; ++i) {
@@ -861,6 +862,7 @@ static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows
     }
     // CTA = WARPS consecutive warp-tiles (its warps are independent workers), row bands in raster order:
     // neighbouring strips share halo columns through L2, COPY and REMAP tiles interleave on every SM
+    // (putting all long REMAP tiles first and the short COPY tiles at the end of the launch was measured: no difference)
     std::stable_sort(fl.begin(), fl.end(), [&](const panfast::FastTile &a, const panfast::FastTile &b) {
         const int64_t ra = a.out_off / d->out_pitch_px / th, rb = b.out_off / d->out_pitch_px / th;
         if (ra != rb) return ra < rb;

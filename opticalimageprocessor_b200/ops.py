@@ -183,8 +183,11 @@ def cubic_tab() -> np.ndarray:
 # ------------------------------------------------------------------------------- stage 3 (MSS)
 def band_align(ctx: Context, mss: torch.Tensor, wb: int, kbs, cX, cY, lines_per_section: int = 20000,
                line_offset: int = 0, overlap: int = 520, keep_leading: bool = False, min_process_lines: int = 1500,
-               fmt: int = FMT_LE16, out: Optional[torch.Tensor] = None):
-    lines = mss.shape[0]
+               fmt: int = FMT_LE16, out: Optional[torch.Tensor] = None, total_lines: Optional[int] = None, src_row0: int = 0,
+               sec_first: int = 0, sec_count: int = 0):
+    """sec_count > 0: section shard -- mss holds strip lines [src_row0, src_row0 + len(mss)) of a total_lines strip and
+    `out` row 0 is the first output row of section sec_first (sharding.mss_sections / mss_rank_sections)"""
+    lines = mss.shape[0] if total_lines is None else int(total_lines)
     d = MssDesc()
     d.fmt = fmt
     d.wb = wb
@@ -203,12 +206,31 @@ def band_align(ctx: Context, mss: torch.Tensor, wb: int, kbs, cX, cY, lines_per_
     d.overlap = overlap
     d.keep_leading = int(keep_leading)
     d.min_process_lines = min_process_lines
+    d.sec_first, d.sec_count, d.src_row0 = sec_first, sec_count, src_row0
     rows = lines - line_offset - (0 if keep_leading else overlap)
     if out is None:
         out = torch.zeros((max(rows, 0), wb, 4), dtype=torch.uint16, device=mss.device)
     n = C.c_int64(0)
     check(ctx.lib.oip_band_align_merge(ctx.h, mss.data_ptr(), C.byref(d), out.data_ptr(), C.byref(n)))
     return int(n.value), out
+
+
+def band_align_sections(ctx: Context, mss: torch.Tensor, wb: int, kbs, cX, cY, sections, all_sections, out: torch.Tensor,
+                        total_lines: int, lines_per_section: int = 20000, overlap: int = 520, line_offset: int = 0,
+                        keep_leading: bool = False, min_process_lines: int = 1500, fmt: int = FMT_LE16, src_row0: int = 0) -> int:
+    """the band alignment of a contiguous run of sections (sharding.mss_rank_sections) in ONE call: a section depends only on
+    its own source lines, so a rank that holds lines [src_row0, src_row0 + len(mss)) produces the output rows of its
+    sections bit-identical to the whole-strip call.  `out` row 0 = first output row of the first section given."""
+    if not sections:
+        return 0
+    first = all_sections.index(sections[0])
+    assert list(all_sections[first:first + len(sections)]) == list(sections), "sections must be a contiguous run"
+    assert sections[0][0] >= src_row0 and sections[-1][0] + sections[-1][1] <= src_row0 + mss.shape[0], \
+        "the shard does not hold its sections' source lines"
+    n, _ = band_align(ctx, mss, wb, kbs, cX, cY, lines_per_section=lines_per_section, line_offset=line_offset, overlap=overlap,
+                      keep_leading=keep_leading, min_process_lines=min_process_lines, fmt=fmt, out=out, total_lines=total_lines,
+                      src_row0=src_row0, sec_first=first, sec_count=len(sections))
+    return n
 
 
 def stitch_tiff_geometry(ctx: Context, imgs: Sequence[torch.Tensor], fold_half: int, band_map=None) -> torch.Tensor:

@@ -108,3 +108,35 @@ def stt_combine(sums: Sequence[float]):
     """(dx, dy, response) means from the all-reduced {sum dx, sum dy, sum response, n valid} (ref stitcher.h:197-199);
     None when no section was valid (the reference throws)"""
     return None if sums[3] == 0 else (sums[0] / sums[3], sums[1] / sums[3], sums[2] / sums[3])
+
+
+# ------------------------------------------------------------------------------------------------
+# Band alignment (ref preproc.h:351-408): its sections are independent -- each one is remapped from its own source
+# lines with section-local map coordinates -- so the MSS path shards by SECTION: no halo rows, no exchange.
+# ------------------------------------------------------------------------------------------------
+def mss_sections(lines: int, lines_per_section: int = 20000, overlap: int = 520, line_offset: int = 0,
+                 keep_leading: bool = False, min_process_lines: int = 1500):
+    """the reference's section loop (ref preproc.h:379-408) as (src_row0, n_src_rows, rows_dropped, out_row0, n_out_rows)"""
+    secs, offset, processed, i = [], line_offset, 0, 0
+    while True:
+        n = min(lines - offset, lines_per_section)                                  # :380
+        if lines < offset or n < min_process_lines:                                  # :381
+            break
+        y0 = 0 if (i == 0 and keep_leading) else overlap                             # :392-402
+        secs.append((offset, n, y0, processed, n - y0))
+        processed += n - y0                                                          # :396, :405
+        offset += lines_per_section - overlap                                        # :407
+        i += 1
+    return secs
+
+
+def mss_rank_sections(secs, world: int, rank: int):
+    """contiguous runs of sections, balanced by output rows"""
+    total = sum(s[4] for s in secs)
+    out, acc = [], 0
+    for s in secs:
+        mid = acc + s[4] / 2.0
+        if int(mid * world / max(total, 1)) == rank:
+            out.append(s)
+        acc += s[4]
+    return out

@@ -108,3 +108,29 @@ def test_band_align_long_section_reference_geometry(ctx, oracle_mod):
     got = got.cpu().numpy()
     bad = np.argwhere(got[:n_g] != want[:n_w])
     assert bad.size == 0, f"{len(bad)} samples differ, first {bad[:5].tolist()}"
+
+
+def test_sections_computed_on_their_own_equal_the_whole_strip(ctx):
+    """C3 sharding: the band alignment shards by section -- every rank's run of sections, computed in one call
+    from only the source lines the rank holds, is bit-identical to the whole-strip call"""
+    from opticalimageprocessor_b200 import ops, sharding
+    lines, wb, lps, ov = 9000, 256, 2500, 300
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mss = torch.randint(0, 4096, (lines, 4 * wb), device="cuda", dtype=torch.int32, generator=g).to(torch.uint16)
+    kbs = [torch.from_numpy(synth.rrc_coeffs(wb, 60 + b)).cuda() for b in range(4)]
+    cX, cY = _coeffs(2.0)
+    for keep, off in [(False, 0), (True, 7)]:
+        n, whole = ops.band_align(ctx, mss, wb, kbs, cX, cY, lines_per_section=lps, overlap=ov, keep_leading=keep, line_offset=off)
+        secs = sharding.mss_sections(lines, lps, ov, off, keep, 1500)
+        assert sum(s[4] for s in secs) == n and len(secs) >= 3
+        for world in (2, 3):
+            got = torch.zeros_like(whole)
+            for rank in range(world):
+                mine = sharding.mss_rank_sections(secs, world, rank)
+                lo, hi = mine[0][0], mine[-1][0] + mine[-1][1]
+                shard = mss[lo:hi].clone()                       # the rank holds only these source lines
+                o0, no = mine[0][3], sum(s[4] for s in mine)
+                k = ops.band_align_sections(ctx, shard, wb, kbs, cX, cY, mine, secs, got[o0:o0 + no], total_lines=lines,
+                                            lines_per_section=lps, overlap=ov, line_offset=off, keep_leading=keep, src_row0=lo)
+                assert k == no
+            assert torch.equal(got[:n].view(torch.int16), whole[:n].view(torch.int16))

@@ -188,3 +188,34 @@ def test_row_ranges_are_tight_and_inside_the_bounding_ranges():
                 assert (f <= a and b <= l) or (sf <= a and b <= sl) or (min(f, sf) <= a and b <= max(l, sl))
             if (r0, nr, i) == (28672, 4096, 2):
                 assert sl - sf > 20000 and sum(b - a for a, b in rs) < nr + 16
+
+
+def test_mss_sections_follow_the_reference_loop_and_partition_over_ranks():
+    import numpy as np
+    import oracle
+    for lines, lps, ov, off, keep in [(65536, 20000, 520, 0, False), (65536, 20000, 520, 100, True), (5000, 1800, 200, 0, False),
+                                      (41000, 20000, 520, 0, False)]:
+        secs = sharding.mss_sections(lines, lps, ov, off, keep, 1500)
+        # output rows are contiguous and add up to the reference's processedLines
+        assert [s[3] for s in secs] == list(np.cumsum([0] + [s[4] for s in secs[:-1]]))
+        assert all(s[2] == ov for s in secs[1:]) and secs[0][2] == (0 if keep else ov)
+        assert all(b[0] - a[0] == lps - ov for a, b in zip(secs, secs[1:]))
+        for world in (1, 2, 3, 8):
+            parts = [sharding.mss_rank_sections(secs, world, r) for r in range(world)]
+            assert sorted(s for p in parts for s in p) == sorted(secs)
+            for p in parts:  # contiguous runs
+                idx = [secs.index(s) for s in p]
+                assert idx == list(range(idx[0], idx[0] + len(idx))) if idx else True
+    # against the oracle's own section loop on a small strip: per-section calls == whole call
+    rng = np.random.default_rng(0)
+    lines, wb = 700, 64
+    planes = [rng.integers(0, 4096, (lines, wb), dtype=np.uint16) for _ in range(4)]
+    cX = [[0.8 + 0.1 * b, -1.5e-4 * (b + 1)] for b in range(4)]
+    cY = [[-3.2 + b, 2e-4 * (b + 1), -1e-8] for b in range(4)]
+    n, whole = oracle.band_align(planes, cX, cY, lines_per_section=300, overlap=40, min_process_lines=100)
+    secs = sharding.mss_sections(lines, 300, 40, 0, False, 100)
+    assert sum(s[4] for s in secs) == n
+    for (o, m, y0, o0, no) in secs:
+        k, part = oracle.band_align([p[o:o + m] for p in planes], cX, cY, lines_per_section=300, overlap=40, keep_leading=(y0 == 0),
+                                    min_process_lines=41)
+        assert k == no and np.array_equal(part[:k], whole[o0:o0 + no])
