@@ -182,12 +182,13 @@ template <typename Load> OIP_BS_HD void piece32(Load load, int lane, int head, u
     }
 }
 
-// butterfly join, distance s: `mine` = own value, `theirs(v)` = the same register of lane ^ s.  The partner that
-// covers the EARLIER bytes (lane & s == 0) is advanced by the s*28 bytes of the later one.
-template <int S, typename Xchg> OIP_BS_HD void join_level(uint32_t (&P)[16], int lane, Xchg xchg)
+// butterfly join, distance s: xchg(v, s, i) = register i of lane ^ s.  The partner that covers the EARLIER bytes
+// (lane & s == 0) is advanced by the s * UNIT bits of the later one (UNIT = bits of the message between the ends of
+// two neighbouring lanes' data: 224 for contiguous 28-byte pieces, 32 for word-interleaved pieces).
+template <int S, int UNIT = 8 * PIECE, typename Xchg> OIP_BS_HD void join_level(uint32_t (&P)[16], int lane, Xchg xchg)
 {
     uint32_t M[16];
-    mul_xpow<8 * PIECE * S>(P, M);
+    mul_xpow<UNIT * S>(P, M);
     const bool early = (lane & S) == 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -195,6 +196,43 @@ template <int S, typename Xchg> OIP_BS_HD void join_level(uint32_t (&P)[16], int
     for (int i = 0; i < 16; ++i) {
         const uint32_t send = early ? M[i] : P[i];
         P[i] = send ^ xchg(send, S, i);
+    }
+}
+
+// Word-interleaved pieces (coalesced loads straight from global memory): the 896-byte span is seven 128-byte blocks and
+// lane l owns word l of every block, so a warp load instruction reads 128 contiguous bytes.  Between two of its words a
+// lane's remainder is advanced by the 124 bytes in between (one fixed XOR network per block).  load(j, T) fills T[f]
+// with word l of block j of frame f.  head = bytes in front of the message (even, < 128): words entirely inside it are
+// dropped, the word that straddles it is entered from its upper half.
+template <typename Load> OIP_BS_HD void piece32_interleaved(Load load, int lane, int head, uint32_t (&P)[16])
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 16; ++i) P[i] = 0u;
+    const int o = 4 * lane; // offset of this lane's word inside block 0
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j < 7; ++j) {
+        uint32_t T[32];
+        load(j, T);
+        transpose32(T);
+        if (j > 0) {
+            uint32_t Q[16];
+            mul_xpow<8 * 124>(P, Q);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int i = 0; i < 16; ++i) P[i] = Q[i];
+        }
+        lfsr_word(P, T, (j == 0 && o < head && head < o + 4) ? 8 * (head - o) : -1);
+        if (j == 0 && o + 4 <= head) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int i = 0; i < 16; ++i) P[i] = 0u;
+        }
     }
 }
 
@@ -210,6 +248,17 @@ template <typename Load> __device__ __forceinline__ void warp_crc32frames(Load l
     join_level<4>(P, lane, x);
     join_level<8>(P, lane, x);
     join_level<16>(P, lane, x);
+}
+template <typename Load> __device__ __forceinline__ void warp_crc32frames_interleaved(Load load, int head, uint32_t (&P)[16])
+{
+    const int lane = threadIdx.x & 31;
+    piece32_interleaved(load, lane, head, P);
+    auto x = [](uint32_t v, int s, int) { return __shfl_xor_sync(0xffffffffu, v, s); };
+    join_level<1, 32>(P, lane, x);
+    join_level<2, 32>(P, lane, x);
+    join_level<4, 32>(P, lane, x);
+    join_level<8, 32>(P, lane, x);
+    join_level<16, 32>(P, lane, x);
 }
 #endif
 

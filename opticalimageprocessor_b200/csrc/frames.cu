@@ -202,67 +202,69 @@ static size_t scan_scratch_elems(int64_t n)
 }
 
 // =============================================================================================
-// AOS: sync search + frame validation, one CTA per 32 KiB chunk staged in shared memory.
-// 32 KiB = 32 frames of a clean downlink = one bit-sliced CRC batch (crc_bitslice.cuh).
+// AOS: sync search + the validation rules that need no CRC.  One CTA streams a 32 KiB chunk of the file straight
+// from global memory (every thread has its eight 16-byte loads in flight at once), marks the sync hits in a
+// shared-memory bitmap and turns the bitmap into the chunk's ordered candidate list.
 // =============================================================================================
 constexpr int CH = 32768;           // file bytes owned by a CTA
-constexpr int CH_HALO = 1024;       // a frame starting at the last owned byte ends here
-constexpr int CH_FRONT = 16;        // bytes in front of the chunk (the CRC span starts 2 bytes before a candidate)
-constexpr int AOS_T = 128;
-constexpr int AOS_WPT = CH / 32 / AOS_T; // bitmap words per thread (8)
-constexpr size_t AOS_SMEM = (size_t)CH_FRONT + CH + CH_HALO + 16 + (CH / 32) * 4 + (CH / 4) * 2;
+constexpr int AOS_T = 256;
+constexpr int AOS_IT = CH / 16 / AOS_T;  // 16-byte steps per thread (8)
+constexpr int AOS_WPT = CH / 32 / AOS_T; // bitmap words per thread (4)
+constexpr int AOS_LIST = 1024;           // candidates per pass (a clean chunk has 32)
 
 struct ChunkInfo {
     uint32_t slot0, count;
 };
 
-__global__ void __launch_bounds__(AOS_T) aos_scan_kernel(const uint8_t *__restrict__ buf, int64_t n,
-                                                         const __grid_constant__ CrcPlan crc, uint32_t *cursor,
-                                                         uint32_t cap, ChunkInfo *info, uint64_t *cand_off,
-                                                         int8_t *cand_st)
+__global__ void __launch_bounds__(AOS_T) aos_scan_kernel(const uint8_t *__restrict__ buf, int64_t n, uint32_t *cursor,
+                                                         uint32_t cap, ChunkInfo *info, uint64_t *cand_off, int8_t *cand_st)
 {
-    extern __shared__ __align__(16) uint8_t s_dyn[];
-    uint8_t *s_buf = s_dyn + CH_FRONT;                                                  // chunk byte 0 (16-byte aligned)
-    uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_dyn + CH_FRONT + CH + CH_HALO + 16);
-    uint16_t *s_cand = reinterpret_cast<uint16_t *>(s_bits + CH / 32);
+    __shared__ uint32_t s_bits[CH / 32];
+    __shared__ uint16_t s_cand[AOS_LIST];
     __shared__ uint32_t s_slot0, s_total;
-    __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x;
     const int64_t c0 = (int64_t)blockIdx.x * CH;
-    const int avail = (int)min((int64_t)(CH + CH_HALO), n - c0); // bytes of the file in s_buf
-
-    // ---- stage the chunk (+halo): one bulk copy (TMA unit, no thread work, the whole chunk in flight at once) when
-    //      the buffer allows it, else a load loop
-    const bool bulk = (((uintptr_t)buf) & 15) == 0 && (avail & 15) == 0;
-    if (bulk) {
-        if (tid == 0) {
-            mbar_init(&s_bar, 1);
-            fence_mbar_init();
-            mbar_arrive_expect_tx(&s_bar, (uint32_t)avail);
-            bulk_g2s(s_buf, buf + c0, (uint32_t)avail, &s_bar);
-        }
-    } else {
-        for (int i = tid; i < avail; i += AOS_T) s_buf[i] = buf[c0 + i];
-    }
-    for (int i = avail + tid; i < CH + CH_HALO + 16; i += AOS_T) s_buf[i] = 0;
-    if (tid < CH_FRONT) s_dyn[tid] = 0;
-    for (int i = tid; i < CH / 32; i += AOS_T) s_bits[i] = 0;
-    __syncthreads(); // also publishes the barrier initialisation
-    if (bulk) {
-        while (!mbar_try_wait(&s_bar, 0)) {}
-    }
-
-    // ---- sync search "1A CF FC 1D" (ref aux_separator.h:29, :622-625); a hit must leave room for a
-    //      whole frame (p + 1024 <= n), anything later can never be accepted or counted
     const int own = (int)min((int64_t)CH, n - c0);
-    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(s_buf);
-    for (int qi = tid; qi < CH / 16; qi += AOS_T) {
-        // 16 bytes per step.  Filter: a 0x1A byte followed by a 0xCF byte (zero-byte trick on both, no false negatives),
-        // rare enough (2^-16 per position) that a warp almost never enters the exact comparison.
-        const uint4 q4 = reinterpret_cast<const uint4 *>(s_buf)[qi];
-        const uint32_t nx4 = w32[4 * qi + 4];
-        const uint32_t wv[5] = {q4.x, q4.y, q4.z, q4.w, nx4};
+    for (int i = tid; i < CH / 32; i += AOS_T) s_bits[i] = 0;
+    __syncthreads();
+
+    // ---- sync search "1A CF FC 1D" (ref aux_separator.h:29, :622-625); a hit must leave room for a whole frame
+    //      (p + 1024 <= n), anything later can never be accepted or counted.  Filter: a 0x1A byte followed by a 0xCF
+    //      byte (zero-byte trick on both, no false negatives), rare enough that a warp almost never enters the exact
+    //      comparison.
+    const bool vec = (((uintptr_t)buf) & 15) == 0 && c0 + CH + 4 <= n;
+    uint4 q4[AOS_IT];
+    uint32_t nx[AOS_IT];
+    if (vec) {
+#pragma unroll
+        for (int it = 0; it < AOS_IT; ++it) {
+            const uint8_t *p = buf + c0 + 16 * (int64_t)(it * AOS_T + tid);
+            q4[it] = ldg_nc_v4(p);
+            nx[it] = __ldg(reinterpret_cast<const uint32_t *>(p + 16));
+        }
+    } else { // last chunk of the file, or a buffer that is not 16-byte aligned: byte loads with bounds
+#pragma unroll
+        for (int it = 0; it < AOS_IT; ++it) {
+            const int64_t p0 = c0 + 16 * (int64_t)(it * AOS_T + tid);
+            uint32_t w[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+                    const int64_t q = p0 + 4 * k + bb;
+                    v |= (uint32_t)(q < n ? buf[q] : 0) << (8 * bb);
+                }
+                w[k] = v;
+            }
+            q4[it] = make_uint4(w[0], w[1], w[2], w[3]);
+            nx[it] = w[4];
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < AOS_IT; ++it) {
+        const uint32_t wv[5] = {q4[it].x, q4[it].y, q4[it].z, q4[it].w, nx[it]};
         uint32_t z2[5], any = 0;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(AOS_T) aos_scan_kernel(const uint8_t *__restri
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const uint32_t v = __funnelshift_r(wv[k], wv[k + 1], 8 * b);
-                    const int p = qi * 16 + k * 4 + b;
+                    const int p = (it * AOS_T + tid) * 16 + k * 4 + b;
                     if (v == 0x1DFCCF1Au && p < own && c0 + p + 1024 <= n) atomicOr(&s_bits[p >> 5], 1u << (p & 31));
                 }
             }
@@ -289,80 +291,107 @@ __global__ void __launch_bounds__(AOS_T) aos_scan_kernel(const uint8_t *__restri
     __syncthreads();
 
     // ---- ordered list of hits (bitmap -> positions), AOS_WPT consecutive bitmap words per thread
-    {
-        uint32_t cnt = 0;
+    uint32_t cnt = 0;
 #pragma unroll
-        for (int k = 0; k < AOS_WPT; ++k) cnt += __popc(s_bits[AOS_WPT * tid + k]);
-        uint32_t tot;
-        uint32_t at = block_exclusive_scan(cnt, &tot);
-        if (cnt) {
-            for (int k = 0; k < AOS_WPT; ++k) {
-                uint32_t m = s_bits[AOS_WPT * tid + k];
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    s_cand[at++] = (uint16_t)((AOS_WPT * tid + k) * 32 + b);
-                }
-            }
-        }
-        if (tid == 0) {
-            s_total = tot;
-            s_slot0 = tot ? atomicAdd(cursor, tot) : 0;
-            info[blockIdx.x].slot0 = s_slot0;
-            info[blockIdx.x].count = tot;
-        }
+    for (int k = 0; k < AOS_WPT; ++k) cnt += __popc(s_bits[AOS_WPT * tid + k]);
+    uint32_t tot;
+    const uint32_t at0 = block_exclusive_scan(cnt, &tot);
+    if (tid == 0) {
+        s_total = tot;
+        s_slot0 = tot ? atomicAdd(cursor, tot) : 0;
+        info[blockIdx.x].slot0 = s_slot0;
+        info[blockIdx.x].count = tot;
     }
     __syncthreads();
     const uint32_t total = s_total, slot0 = s_slot0;
     if (slot0 + total > cap) return; // table too small: the host re-runs with the exact size
 
-    // ---- ValidateAosFrame (ref aux_separator.h:658-690): a warp takes 32 candidates, one per lane
-    // (the warp that takes the first batch rotates with the CTA index: warp w of every CTA shares one of the SM's four
-    //  schedulers, and a clean chunk has exactly one batch)
-    const int lane = tid & 31, wid = ((tid >> 5) - (int)blockIdx.x) & (AOS_T / 32 - 1);
-    for (uint32_t g0 = 32u * wid; g0 < total; g0 += 32u * (AOS_T / 32)) {
-        const int cnt = (int)min(32u, total - g0);
-        const int mine = lane < cnt ? (int)s_cand[g0 + lane] : 0;
-        const uint8_t *f = s_buf + mine;
-        const uint32_t vcid = f[5] & 0x3F;
-        const uint32_t injw = ((uint32_t)f[10] << 24) | ((uint32_t)f[11] << 16) | ((uint32_t)f[12] << 8) | f[13];
-        const uint32_t want = ((uint32_t)f[894] << 8) | f[895];
-        int st;
-        if (injw != 0xAAAAAAAAu && injw != 0u) st = -1;          // :675
-        else if (injw == 0xAAAAAAAAu && vcid == 0x3F) st = 0;   // :676
-        else st = 2;                                            // :679-686 CRC over bytes 4..893 decides
-        const int first = __shfl_sync(0xffffffffu, mine, 0);
-        const bool uniform = __all_sync(0xffffffffu, cnt == 32 && mine == first + 1024 * lane);
-        if (uniform) {
-            // the common case, 32 frames back to back: bit-sliced CRC, lane l = bytes [28l, 28l+28) of the 896-byte
-            // span that starts 2 bytes in front of each frame (4 sync bytes + 2 = the 6 bytes lane 0 drops)
-            const uint32_t B = smem_u32(s_buf) + (uint32_t)(first - 2 + 28 * lane);
-            uint32_t P[16];
-            bitslice::warp_crc32frames(
-                [&](int j, uint32_t(&T)[32]) {
-                    const uint32_t a = (B + 4u * (uint32_t)j) & ~3u, sh = B << 3;
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) T[q] = __funnelshift_r(lds_u32(a + 1024u * q), lds_u32(a + 1024u * q + 4u), sh);
-                },
-                bitslice::SPAN - 890, P);
-            if (st == 2) st = (bitslice::unslice(P, lane) ^ bitslice::init_term(890)) == want ? 1 : -1;
-        } else {
-            for (int k = 0; k < cnt; ++k) { // irregular group (false sync, partial chunk): one candidate at a time
-                if (__shfl_sync(0xffffffffu, st, k) != 2) continue;
-                const int m0 = __shfl_sync(0xffffffffu, mine, k) + 4; // first message byte inside s_buf (16-byte aligned)
-                const uint32_t c = warp_crc16_words(crc, reinterpret_cast<const uint32_t *>(s_buf) + (m0 >> 2), m0 & 3);
-                if (lane == k) st = c == want ? 1 : -1;
+    for (uint32_t base = 0; base < total; base += AOS_LIST) { // one pass unless the chunk is full of sync patterns
+        if (cnt) {
+            uint32_t at = at0;
+            for (int k = 0; k < AOS_WPT; ++k) {
+                uint32_t m = s_bits[AOS_WPT * tid + k];
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (at >= base && at < base + AOS_LIST) s_cand[at - base] = (uint16_t)((AOS_WPT * tid + k) * 32 + b);
+                    ++at;
+                }
             }
         }
-        if (lane < cnt) {
-            cand_off[slot0 + g0 + lane] = (uint64_t)(c0 + mine);
-            cand_st[slot0 + g0 + lane] = (int8_t)st;
+        __syncthreads();
+        // ---- ValidateAosFrame, the rules that need no CRC (ref aux_separator.h:658-677); status 2 = "the CRC decides"
+        //      (aos_crc_kernel, on the candidates in file order)
+        const uint32_t here = min((uint32_t)AOS_LIST, total - base);
+        for (uint32_t j = tid; j < here; j += AOS_T) {
+            const int mine = (int)s_cand[j];
+            const uint8_t *f = buf + c0 + mine;
+            const uint32_t vcid = f[5] & 0x3F;
+            const uint32_t injw = ((uint32_t)f[10] << 24) | ((uint32_t)f[11] << 16) | ((uint32_t)f[12] << 8) | f[13];
+            int st;
+            if (injw != 0xAAAAAAAAu && injw != 0u) st = -1;          // :675
+            else if (injw == 0xAAAAAAAAu && vcid == 0x3F) st = 0;   // :676
+            else st = 2;                                            // :679-686
+            cand_off[slot0 + base + j] = (uint64_t)(c0 + mine);
+            cand_st[slot0 + base + j] = (int8_t)st;
         }
+        __syncthreads();
     }
 }
 
+// ---- CRC of the candidates that need one (ref aux_separator.h:679-686), on the file-ordered table: a warp takes 32
+// consecutive candidates.  32 frames back to back (the normal case) are bit-sliced straight from global memory with
+// word-interleaved pieces: lane l reads word l of each 128-byte block of the 896-byte span that ends with the last
+// message byte (starts 2 bytes before the frame), so every warp load is one contiguous 128-byte line and every byte is
+// read once.  Anything else (false sync, end of file) goes one candidate at a time.
+constexpr int AOS_CRC_WARPS = 4;
+__global__ void __launch_bounds__(AOS_CRC_WARPS * 32) aos_crc_kernel(const uint8_t *__restrict__ buf, const __grid_constant__ CrcPlan crc,
+                                                                      const uint64_t *__restrict__ off, int8_t *st_io,
+                                                                      const uint32_t *__restrict__ m_ptr)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t g0 = (((int64_t)blockIdx.x * AOS_CRC_WARPS) + (threadIdx.x >> 5)) * 32;
+    const int64_t m = (int64_t)*m_ptr;
+    if (g0 >= m) return;
+    const int cnt = (int)min((int64_t)32, m - g0);
+    const uint64_t mine = lane < cnt ? off[g0 + lane] : 0ull;
+    int st = lane < cnt ? (int)st_io[g0 + lane] : 0;
+    if (!__any_sync(0xffffffffu, st == 2)) return;
+    const uint8_t *f = buf + mine;
+    const uint32_t want = st == 2 ? (((uint32_t)f[894] << 8) | f[895]) : 0u;
+    const uint64_t first = __shfl_sync(0xffffffffu, mine, 0);
+    const bool uniform = __all_sync(0xffffffffu, cnt == 32 && mine == first + 1024ull * (uint64_t)lane) && first >= 4;
+    if (uniform) {
+        const uint8_t *A = buf + first - 2 + 4 * lane;          // span start of frame 0 + this lane's word
+        const uint32_t sh = (uint32_t)((uintptr_t)A & 3u);
+        const uint32_t *W = reinterpret_cast<const uint32_t *>(A - sh);
+        uint32_t P[16];
+        bitslice::warp_crc32frames_interleaved(
+            [&](int j, uint32_t(&T)[32]) {
+                const uint32_t *w = W + 32 * j;
+                if (sh) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) T[q] = __funnelshift_r(__ldg(w + 256 * q), __ldg(w + 256 * q + 1), 8u * sh);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) T[q] = __ldg(w + 256 * q);
+                }
+            },
+            bitslice::SPAN - 890, P);
+        if (st == 2) st = (bitslice::unslice(P, lane) ^ bitslice::init_term(890)) == want ? 1 : -1;
+    } else {
+        for (int k = 0; k < cnt; ++k) {
+            if (__shfl_sync(0xffffffffu, st, k) != 2) continue;
+            const uint8_t *p = buf + __shfl_sync(0xffffffffu, mine, k) + 4;
+            const uint32_t c = warp_crc16(crc, [&](int i) { return (uint32_t)p[i]; });
+            if (lane == k) st = c == want ? 1 : -1;
+        }
+    }
+    if (lane < cnt) st_io[g0 + lane] = (int8_t)st;
+}
+
 // candidates in file order: chunk c's run goes to [base[c], base[c]+count)
-__global__ void aos_order_kernel(const ChunkInfo *info, const uint32_t *base, int64_t n_chunks, const uint64_t *cand_off,
+__global__ void aos_order_kernel(const ChunkInfo *info, const uint32_t *base, int64_t n_chunks, uint32_t cap, const uint64_t *cand_off,
                                  const int8_t *cand_st, uint64_t *ord_off, int8_t *ord_st)
 {
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -370,17 +399,25 @@ __global__ void aos_order_kernel(const ChunkInfo *info, const uint32_t *base, in
     if (c >= n_chunks) return;
     const ChunkInfo ci = info[c];
     const uint32_t b = base[c];
+    if ((uint64_t)ci.slot0 + ci.count > cap || (uint64_t)b + ci.count > cap) return; // table overflow: the host re-runs with the exact size
     for (uint32_t j = lane; j < ci.count; j += 32) {
         ord_off[b + j] = cand_off[ci.slot0 + j];
         ord_st[b + j] = cand_st[ci.slot0 + j];
     }
 }
 
+// the candidate count the later kernels see never exceeds the table (an overflowing call is repeated by the host)
+__global__ void aos_clamp_kernel(uint32_t *total, uint32_t cap)
+{
+    if (*total > cap) *total = cap;
+}
+
 // A valid candidate with no valid candidate in the preceding 1023 bytes is always accepted by the
 // sequential scan (ref aux_separator.h:421-461): whatever was accepted before ends <= its offset.
-__global__ void aos_runstart_kernel(const uint64_t *off, const int8_t *st, int64_t m, uint8_t *rs)
+__global__ void aos_runstart_kernel(const uint64_t *off, const int8_t *st, const uint32_t *m_ptr, uint8_t *rs)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t m = (int64_t)*m_ptr;
     if (i >= m) return;
     uint8_t r = 0;
     if (st[i] == 1) {
@@ -393,10 +430,11 @@ __global__ void aos_runstart_kernel(const uint64_t *off, const int8_t *st, int64
 
 // each run start replays the reference's skip rules up to the next run start:
 // accepted frame -> next search position = off+1024; rejected candidate -> off+4 (:440-441,:456-457)
-__global__ void aos_walk_kernel(const uint64_t *off, const int8_t *st, const uint8_t *rs, int64_t m, uint32_t *acc,
+__global__ void aos_walk_kernel(const uint64_t *off, const int8_t *st, const uint8_t *rs, const uint32_t *m_ptr, uint32_t *acc,
                                 unsigned long long *counters)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t m = (int64_t)*m_ptr;
     uint32_t n_inv = 0, n_emp = 0, n_val = 0;
     if (i < m && (rs[i] || i == 0)) {
         int64_t j = i;
@@ -430,11 +468,11 @@ __global__ void aos_walk_kernel(const uint64_t *off, const int8_t *st, const uin
     }
 }
 
-__global__ void aos_emit_kernel(const uint64_t *off, const uint32_t *acc, const uint32_t *rank, int64_t m,
+__global__ void aos_emit_kernel(const uint64_t *off, const uint32_t *acc, const uint32_t *rank, const uint32_t *m_ptr,
                                 uint64_t *payload_off, uint64_t cap)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m || !acc[i]) return;
+    if (i >= (int64_t)*m_ptr || !acc[i]) return;
     if (rank[i] < cap) payload_off[rank[i]] = off[i] + 14; // AOS_DATA_OFF :44
 }
 
@@ -823,51 +861,56 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
         ChunkInfo *d_info = (ChunkInfo *)(S + o_info);
         OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 64, ctx->stream));
 
-        OIP_CUDA(cudaFuncSetAttribute(aos_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AOS_SMEM));
-        aos_scan_kernel<<<(unsigned)n_chunks, AOS_T, AOS_SMEM, ctx->stream>>>(d_buf, n, plan, d_cursor, cand_cap, d_info,
+        aos_scan_kernel<<<(unsigned)n_chunks, AOS_T, 0, ctx->stream>>>(d_buf, n, d_cursor, cand_cap, d_info,
                                                                       (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst));
         OIP_CUDA(cudaGetLastError());
         ctx->launches++;
         rc = ensure_pinned(ctx, 64);
         if (rc) return rc;
-        uint32_t *h = (uint32_t *)ctx->h_pinned;
-        OIP_CUDA(cudaMemcpyAsync(h, d_cursor, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        OIP_CUDA(cudaStreamSynchronize(ctx->stream));
-        const uint32_t m = h[0];
-        if (m > cand_cap) { // pathological input (sync pattern everywhere): retry with the exact size
-            cand_cap = m;
-            continue;
-        }
-        if (m == 0) return OIP_OK;
+        // everything below is sized by the table capacity and reads the candidate count on the device: one host round
+        // trip per call (the count only decides whether the pathological retry is needed)
         // file order: scan the per-chunk counts (ChunkInfo.count is strided -> copy out first)
         OIP_CUDA(cudaMemcpy2DAsync(S + o_cnt, 4, (uint8_t *)d_info + 4, sizeof(ChunkInfo), 4, (size_t)n_chunks,
                                    cudaMemcpyDeviceToDevice, ctx->stream));
         rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_cnt), (uint32_t *)(S + o_base), n_chunks, (uint32_t *)(S + o_scan),
                                 d_total);
         if (rc) return rc;
+        aos_clamp_kernel<<<1, 1, 0, ctx->stream>>>(d_total, cand_cap);
+        OIP_CUDA(cudaGetLastError());
         aos_order_kernel<<<(unsigned)((n_chunks * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            d_info, (uint32_t *)(S + o_base), n_chunks, (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst),
+            d_info, (uint32_t *)(S + o_base), n_chunks, cand_cap, (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst),
             (uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost));
         OIP_CUDA(cudaGetLastError());
-        const unsigned gb = (unsigned)((m + 255) / 256);
-        aos_runstart_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), m, S + o_rs);
+        aos_crc_kernel<<<(unsigned)(((size_t)cand_cap + 32 * AOS_CRC_WARPS - 1) / (32 * AOS_CRC_WARPS)), AOS_CRC_WARPS * 32, 0, ctx->stream>>>(
+            d_buf, plan, (uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), d_total);
         OIP_CUDA(cudaGetLastError());
-        aos_walk_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), S + o_rs, m,
+        const unsigned gb = (unsigned)(((size_t)cand_cap + 255) / 256);
+        OIP_CUDA(cudaMemsetAsync(S + o_acc, 0, (size_t)cand_cap * 4, ctx->stream)); // entries past the count stay 0 for the scan
+        aos_runstart_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), d_total, S + o_rs);
+        OIP_CUDA(cudaGetLastError());
+        aos_walk_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), S + o_rs, d_total,
                                                      (uint32_t *)(S + o_acc), d_counters);
         OIP_CUDA(cudaGetLastError());
-        ctx->launches += 3;
-        rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_acc), (uint32_t *)(S + o_rank), m, (uint32_t *)(S + o_scan),
+        ctx->launches += 5;
+        rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_acc), (uint32_t *)(S + o_rank), cand_cap, (uint32_t *)(S + o_scan),
                                 d_acc_total);
         if (rc) return rc;
         if (d_payload_off) {
             aos_emit_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (uint32_t *)(S + o_acc),
-                                                         (uint32_t *)(S + o_rank), m, d_payload_off, (uint64_t)cap);
+                                                         (uint32_t *)(S + o_rank), d_total, d_payload_off, (uint64_t)cap);
             OIP_CUDA(cudaGetLastError());
             ctx->launches++;
         }
-        unsigned long long *hc = (unsigned long long *)ctx->h_pinned;
-        OIP_CUDA(cudaMemcpyAsync(hc, d_counters, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        // header: cursor(u32) | total(u32) | counters(3 x u64)
+        uint8_t *hb = (uint8_t *)ctx->h_pinned;
+        OIP_CUDA(cudaMemcpyAsync(hb, S + o_hdr, 32, cudaMemcpyDeviceToHost, ctx->stream));
         OIP_CUDA(cudaStreamSynchronize(ctx->stream));
+        const uint32_t m = *(const uint32_t *)hb;
+        if (m > cand_cap) { // pathological input (sync pattern everywhere): retry with the exact size
+            cand_cap = m;
+            continue;
+        }
+        const unsigned long long *hc = (const unsigned long long *)(hb + 8);
         if (counters) { counters[0] = (int64_t)hc[0]; counters[1] = (int64_t)hc[1]; counters[2] = (int64_t)hc[2]; }
         if (d_payload_off && hc[0] > cap) return fail(OIP_E_INVALID, "oip_aos_scan: %llu valid frames exceed capacity %zu", hc[0], cap);
         return OIP_OK;

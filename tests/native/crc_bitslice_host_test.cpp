@@ -81,6 +81,52 @@ template <int LEN> static int run(int trials)
     return bad;
 }
 
+// word-interleaved pieces (the global-memory variant): lane l = word l of each of the seven 128-byte blocks
+template <int S> static void join_all32(uint32_t (&P)[32][16])
+{
+    uint32_t sent[32][16];
+    for (int lane = 0; lane < 32; ++lane) {
+        uint32_t M[16];
+        mul_xpow<32 * S>(P[lane], M);
+        for (int i = 0; i < 16; ++i) sent[lane][i] = (lane & S) == 0 ? M[i] : P[lane][i];
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+        auto x = [&](uint32_t, int s, int i) { return sent[lane ^ s][i]; };
+        join_level<S, 32>(P[lane], lane, x);
+    }
+}
+template <int LEN> static int run_interleaved(int trials)
+{
+    constexpr int HEAD = SPAN - LEN;
+    int bad = 0;
+    for (int tr = 0; tr < trials; ++tr) {
+        std::vector<uint8_t> buf(32 * 1100 + 64);
+        for (auto &b : buf) b = (uint8_t)rnd();
+        int start[32];
+        for (int f = 0; f < 32; ++f) start[f] = 32 + f * 1100 + (tr == 0 ? 0 : (int)(rnd() % 7));
+        uint32_t P[32][16];
+        for (int lane = 0; lane < 32; ++lane) {
+            auto load = [&](int j, uint32_t(&T)[32]) {
+                for (int f = 0; f < 32; ++f) {
+                    const uint8_t *q = &buf[start[f] - HEAD + 128 * j + 4 * lane];
+                    T[f] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+                }
+            };
+            piece32_interleaved(load, lane, HEAD, P[lane]);
+        }
+        join_all32<1>(P); join_all32<2>(P); join_all32<4>(P); join_all32<8>(P); join_all32<16>(P);
+        for (int f = 0; f < 32; ++f) {
+            const uint16_t want = crc_serial(&buf[start[f]], LEN);
+            const uint16_t got = (uint16_t)(unslice(P[5], f) ^ init_term(LEN));
+            if (got != want) {
+                if (bad < 5) printf("interleaved LEN %d trial %d frame %d: got %04X want %04X\n", LEN, tr, f, got, want);
+                ++bad;
+            }
+        }
+    }
+    return bad;
+}
+
 // join_level itself (the device code path) with an emulated exchange: two passes per level
 template <int S> static void join_all(uint32_t (&P)[32][16])
 {
@@ -106,7 +152,7 @@ int main()
     for (int k = 0; k < 32; ++k)
         for (int f = 0; f < 32; ++f)
             if (((a[k] >> f) & 1) != ((b[f] >> k) & 1)) { puts("transpose32 wrong"); return 3; }
-    int bad = run<890>(20) + run<876>(20);
+    int bad = run<890>(20) + run<876>(20) + run_interleaved<890>(20) + run_interleaved<876>(20);
     // join_level against the open-coded butterfly
     {
         uint32_t P[32][16], Q[32][16];
