@@ -216,7 +216,7 @@ struct ChunkInfo {
     uint32_t slot0, count;
 };
 
-__global__ void __launch_bounds__(AOS_T) aos_scan_kernel(const uint8_t *__restrict__ buf, int64_t n, uint32_t *cursor,
+__global__ void __launch_bounds__(AOS_T, 6) aos_scan_kernel(const uint8_t *__restrict__ buf, int64_t n, uint32_t *cursor,
                                                          uint32_t cap, ChunkInfo *info, uint64_t *cand_off, int8_t *cand_st)
 {
     __shared__ uint32_t s_bits[CH / 32];
@@ -234,56 +234,68 @@ __global__ void __launch_bounds__(AOS_T) aos_scan_kernel(const uint8_t *__restri
     //      byte (zero-byte trick on both, no false negatives), rare enough that a warp almost never enters the exact
     //      comparison.
     const bool vec = (((uintptr_t)buf) & 15) == 0 && c0 + CH + 4 <= n;
-    uint4 q4[AOS_IT];
-    uint32_t nx[AOS_IT];
-    if (vec) {
+    constexpr int HALF = AOS_IT / 2; // two rounds of four 16-byte loads in flight: 40 registers, 6 CTAs per SM
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        uint4 q4[HALF];
+        uint32_t nx[HALF];
+        if (vec) {
 #pragma unroll
-        for (int it = 0; it < AOS_IT; ++it) {
-            const uint8_t *p = buf + c0 + 16 * (int64_t)(it * AOS_T + tid);
-            q4[it] = ldg_nc_v4(p);
-            nx[it] = __ldg(reinterpret_cast<const uint32_t *>(p + 16));
+            for (int i = 0; i < HALF; ++i) {
+                const int it = round * HALF + i;
+                const uint8_t *p = buf + c0 + 16 * (int64_t)(it * AOS_T + tid);
+                q4[i] = ldg_nc_v4(p);
+                if ((tid & 31) == 31) nx[i] = __ldg(reinterpret_cast<const uint32_t *>(p + 16)); // the next warp's first word
+            }
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) { // the word after my 16 bytes is the neighbour lane's first word
+                const uint32_t v = __shfl_down_sync(0xffffffffu, q4[i].x, 1);
+                if ((tid & 31) != 31) nx[i] = v;
+            }
+        } else { // last chunk of the file, or a buffer that is not 16-byte aligned: byte loads with bounds
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) {
+                const int it = round * HALF + i;
+                const int64_t p0 = c0 + 16 * (int64_t)(it * AOS_T + tid);
+                uint32_t w[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) {
+                        const int64_t q = p0 + 4 * k + bb;
+                        v |= (uint32_t)(q < n ? buf[q] : 0) << (8 * bb);
+                    }
+                    w[k] = v;
+                }
+                q4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                nx[i] = w[4];
+            }
         }
-    } else { // last chunk of the file, or a buffer that is not 16-byte aligned: byte loads with bounds
 #pragma unroll
-        for (int it = 0; it < AOS_IT; ++it) {
-            const int64_t p0 = c0 + 16 * (int64_t)(it * AOS_T + tid);
-            uint32_t w[5];
+        for (int i = 0; i < HALF; ++i) {
+            const int it = round * HALF + i;
+            const uint32_t wv[5] = {q4[i].x, q4[i].y, q4[i].z, q4[i].w, nx[i]};
+            uint32_t z2[5], any = 0;
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int bb = 0; bb < 4; ++bb) {
-                    const int64_t q = p0 + 4 * k + bb;
-                    v |= (uint32_t)(q < n ? buf[q] : 0) << (8 * bb);
-                }
-                w[k] = v;
+                const uint32_t x = wv[k] ^ 0xCFCFCFCFu;
+                z2[k] = (x - 0x01010101u) & ~x;
             }
-            q4[it] = make_uint4(w[0], w[1], w[2], w[3]);
-            nx[it] = w[4];
-        }
-    }
-#pragma unroll
-    for (int it = 0; it < AOS_IT; ++it) {
-        const uint32_t wv[5] = {q4[it].x, q4[it].y, q4[it].z, q4[it].w, nx[it]};
-        uint32_t z2[5], any = 0;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const uint32_t x = wv[k] ^ 0xCFCFCFCFu;
-            z2[k] = (x - 0x01010101u) & ~x;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t x = wv[k] ^ 0x1A1A1A1Au;
-            any |= (x - 0x01010101u) & ~x & __funnelshift_r(z2[k], z2[k + 1], 8);
-        }
-        if (any & 0x80808080u) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+                const uint32_t x = wv[k] ^ 0x1A1A1A1Au;
+                any |= (x - 0x01010101u) & ~x & __funnelshift_r(z2[k], z2[k + 1], 8);
+            }
+            if (any & 0x80808080u) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t v = __funnelshift_r(wv[k], wv[k + 1], 8 * b);
-                    const int p = (it * AOS_T + tid) * 16 + k * 4 + b;
-                    if (v == 0x1DFCCF1Au && p < own && c0 + p + 1024 <= n) atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t v = __funnelshift_r(wv[k], wv[k + 1], 8 * b);
+                        const int p = (it * AOS_T + tid) * 16 + k * 4 + b;
+                        if (v == 0x1DFCCF1Au && p < own && c0 + p + 1024 <= n) atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+                    }
                 }
             }
         }
