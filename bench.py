@@ -265,12 +265,14 @@ def run_gpu(args):
         for _ in range(2):
             e2e_step()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n_e2e = max(2, min(args.steps, 5))
+        n_e2e = max(3, min(args.steps, 7))
+        ts = []
         for _ in range(n_e2e):
+            t0 = time.perf_counter()
             e2e_step()  # returns after the output block landed in host memory
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        e2e_ms = float(np.median(ts))  # the host link is shared with whatever else the box does: median, not mean
         # the device-resident path and the host path must agree
         if not torch.equal(host_out.view(torch.int16), d_out.cpu().view(torch.int16)):
             raise SystemExit("e2e output differs from the device-resident output")

@@ -545,7 +545,7 @@ constexpr int IMTR_T = 128, IMTR_BATCH = 32, IMTR_SLOT = 896, IMTR_FRONT = 32;
 __global__ void __launch_bounds__(IMTR_T) imtr_validate_kernel(const uint8_t *__restrict__ buf, const uint64_t *__restrict__ poff,
                                                                int64_t n_payload, int64_t n_frames, uint8_t *status,
                                                                uint32_t *seq, uint8_t *chid, uint32_t *valid,
-                                                               unsigned long long *n_bad)
+                                                               unsigned long long *n_bad, uint8_t *imdt_spec)
 {
     __shared__ __align__(16) uint32_t s_w[(IMTR_FRONT + IMTR_BATCH * IMTR_SLOT + 32) / 4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -567,6 +567,27 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_kernel(const uint8_t *__
             if ((b & 3) && b < 880) fw[b >> 2] = seg_word_bytes(S, b & ~3, 4);
         } else if (lane == 2) {
             fw[220] = seg_word_bytes(S, 880, 2);
+        }
+        if (imdt_spec) {
+            // speculative output: in a clean downlink every frame is valid and frame f's 866 payload bytes (frame bytes
+            // 10..875, IMTR_IMGDATA_OFF :72) land at f * 866 -- written here while the frame is in shared memory;
+            // imtr_copy_kernel then has nothing to do.  Anything else (a rejected frame, a sequence restart) is put
+            // right by imtr_copy_kernel, which rewrites the whole output from the source.
+            __syncwarp();
+            uint8_t *d = imdt_spec + (uint64_t)(f0 + q) * 866;
+            const uint8_t *fr = reinterpret_cast<const uint8_t *>(fw);
+            const int head = (int)((4u - (uint32_t)((uintptr_t)d & 3u)) & 3u);
+            if (lane < head) d[lane] = fr[10 + lane];
+            const int nw = (866 - head) >> 2, s0 = 10 + head;
+            const uint32_t sh = 8u * (uint32_t)(s0 & 3);
+            uint32_t *dw = reinterpret_cast<uint32_t *>(d + head);
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                const int k = lane + 32 * u;
+                if (k < nw) dw[k] = __funnelshift_r(fw[(s0 >> 2) + k], fw[(s0 >> 2) + k + 1], sh);
+            }
+            const int t0 = head + 4 * nw;
+            if (lane < 866 - t0) d[t0 + lane] = fr[10 + t0 + lane];
         }
     }
     __syncthreads();
@@ -625,12 +646,17 @@ __global__ void imtr_rules_kernel(const uint32_t *seq_c, const uint32_t *n_valid
 __global__ void __launch_bounds__(256) imtr_copy_kernel(const uint8_t *__restrict__ buf, const uint64_t *__restrict__ poff,
                                                         int64_t n_payload, int64_t n_frames, const uint32_t *valid,
                                                         const uint32_t *rank, const unsigned long long *restart_last,
-                                                        const uint8_t *chid, uint8_t *imdt, uint64_t cap, int *first_chid)
+                                                        const uint8_t *chid, uint8_t *imdt, uint64_t cap, int *first_chid,
+                                                        const uint32_t *n_valid, int speculative)
 {
     const int lane = threadIdx.x & 31;
     const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (f >= n_frames || !valid[f]) return;
     const uint64_t r0 = *restart_last;
+    if (speculative && r0 == 0 && (int64_t)*n_valid == n_frames) { // imtr_validate_kernel already wrote every frame in place
+        if (f == 0 && lane == 0) *first_chid = chid[0];
+        return;
+    }
     if (rank[f] < r0) return;
     const uint64_t dst = (uint64_t)(rank[f] - r0) * 866;
     if (dst + 866 > cap) return;
@@ -963,8 +989,10 @@ extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64
     OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 64, ctx->stream));
     OIP_CUDA(cudaMemsetAsync(d_first_chid, 0xFF, 4, ctx->stream));
     // one stream-ordered chain, one host round trip at the end
+    const bool speculative = (uint64_t)nf * 866 <= (uint64_t)cap; // room for every cut frame: validate writes them in place
     imtr_validate_kernel<<<(unsigned)((nf + IMTR_BATCH - 1) / IMTR_BATCH), IMTR_T, 0, ctx->stream>>>(
-        d_buf, d_payload_off, n_payload, nf, S + o_status, (uint32_t *)(S + o_seq), S + o_chid, (uint32_t *)(S + o_valid), d_bad);
+        d_buf, d_payload_off, n_payload, nf, S + o_status, (uint32_t *)(S + o_seq), S + o_chid, (uint32_t *)(S + o_valid), d_bad,
+        speculative ? d_imdt : nullptr);
     OIP_CUDA(cudaGetLastError());
     ctx->launches++;
     rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank), nf, (uint32_t *)(S + o_scan), d_total);
@@ -977,7 +1005,7 @@ extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64
     OIP_CUDA(cudaGetLastError());
     imtr_copy_kernel<<<(unsigned)((nf * 32 + 255) / 256), 256, 0, ctx->stream>>>(
         d_buf, d_payload_off, n_payload, nf, (uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank), d_hdr, S + o_chid, d_imdt,
-        (uint64_t)cap, d_first_chid);
+        (uint64_t)cap, d_first_chid, d_total, speculative ? 1 : 0);
     OIP_CUDA(cudaGetLastError());
     ctx->launches += 3;
     uint8_t *hp = (uint8_t *)ctx->h_pinned;
