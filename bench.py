@@ -56,32 +56,45 @@ def algorithmic_bytes_per_px():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled through NVML while the timed region runs (one sample is taken synchronously at
+    start and at stop, so a region shorter than the sampling period still has data)"""
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
     def __init__(self, dev):
-        self.dev, self.samples, self.reasons, self.max_mhz = dev, [], set(), None
+        self.dev, self.samples, self.reasons, self.max_mhz, self.h, self.nv = dev, [], set(), None, None, None
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.dev)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
-            while not self._stop.is_set():
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.005)
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    def _sample(self):
+        if self.h is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, nm in self.NAMES.items():
+                if r & bit:
+                    self.reasons.add(nm)
         except Exception:
             pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._sample()
+            time.sleep(0.005)
 
     def start(self):
         self._t.start()
 
     def stop(self):
+        self._sample()  # still under load: the caller stops the sampler before it synchronises
         self._stop.set()
         self._t.join(timeout=2)
         s = sorted(self.samples)
@@ -249,8 +262,8 @@ def run_gpu(args):
     for k in range(args.steps):
         step()
         ev[k + 1].record()
+    clk = clocks.stop()   # one more sample while the queued steps are still running
     sync_all()
-    clk = clocks.stop()
     launches = ctx.launches - l0
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = float(np.mean([ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]))

@@ -372,9 +372,12 @@ __global__ void __launch_bounds__(AOS_CRC_WARPS * 32) aos_crc_kernel(const uint8
     const uint8_t *f = buf + mine;
     const uint32_t want = st == 2 ? (((uint32_t)f[894] << 8) | f[895]) : 0u;
     const uint64_t first = __shfl_sync(0xffffffffu, mine, 0);
-    const bool uniform = __all_sync(0xffffffffu, cnt == 32 && mine == first + 1024ull * (uint64_t)lane) && first >= 4;
+    const bool uniform = __all_sync(0xffffffffu, cnt == 32 && mine == first + 1024ull * (uint64_t)lane);
     if (uniform) {
-        const uint8_t *A = buf + first - 2 + 4 * lane;          // span start of frame 0 + this lane's word
+        // The remainder is taken over message + stored CRC (892 bytes, frame bytes 4..895): it is zero exactly when the
+        // stored CRC matches (no reflection, no final xor).  That span of 896 bytes starts AT the frame, so the loads
+        // are word aligned whenever the frame is, and lane 0 drops the 4 sync bytes in front.
+        const uint8_t *A = buf + first + 4 * lane;              // span start of frame 0 + this lane's word
         const uint32_t sh = (uint32_t)((uintptr_t)A & 3u);
         const uint32_t *W = reinterpret_cast<const uint32_t *>(A - sh);
         uint32_t P[16];
@@ -389,8 +392,8 @@ __global__ void __launch_bounds__(AOS_CRC_WARPS * 32) aos_crc_kernel(const uint8
                     for (int q = 0; q < 32; ++q) T[q] = __ldg(w + 256 * q);
                 }
             },
-            bitslice::SPAN - 890, P);
-        if (st == 2) st = (bitslice::unslice(P, lane) ^ bitslice::init_term(890)) == want ? 1 : -1;
+            bitslice::SPAN - 892, P);
+        if (st == 2) st = (bitslice::unslice(P, lane) ^ bitslice::init_term(892)) == 0u ? 1 : -1;
     } else {
         for (int k = 0; k < cnt; ++k) {
             if (__shfl_sync(0xffffffffu, st, k) != 2) continue;

@@ -11,8 +11,7 @@
 
 namespace oip {
 
-constexpr int HP_SLOTS_MAX = 6;
-static int hp_slots() { static const int n = [] { const char *e = getenv("OIP_HP_SLOTS"); int v = e ? atoi(e) : 3; return v < 2 ? 2 : (v > HP_SLOTS_MAX ? HP_SLOTS_MAX : v); }(); return n; }
+constexpr int HP_SLOTS = 3; // 2, 4 and 6 slots were measured: no difference (the link is the limit)
 
 struct HostPipe {
     cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -22,7 +21,7 @@ struct HostPipe {
         void *d_out = nullptr;
         size_t out_cap = 0;
         cudaEvent_t in_ready = nullptr, compute_done = nullptr, out_done = nullptr;
-    } slot[HP_SLOTS_MAX];
+    } slot[HP_SLOTS];
     void *d_kb[8] = {};
     size_t kb_cap[8] = {};
 };
@@ -132,8 +131,7 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
     {
         int64_t left = h->n_rows;
         std::vector<int64_t> head, tail;
-        static const bool no_ramp = getenv("OIP_HP_NORAMP") != nullptr; // timing experiment
-        for (int64_t b = std::min<int64_t>(256, HP_BLOCK_ROWS); !no_ramp && b < HP_BLOCK_ROWS && left >= 4 * b; b *= 2) {
+        for (int64_t b = std::min<int64_t>(256, HP_BLOCK_ROWS); b < HP_BLOCK_ROWS && left >= 4 * b; b *= 2) {
             head.push_back(b);
             tail.push_back(b);
             left -= 2 * b;
@@ -146,13 +144,12 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
     int64_t r0 = h->row0;
     for (size_t bi = 0; bi < sizes.size(); r0 += sizes[bi], ++bi, ++blk) {
         const int64_t nr = sizes[bi];
-        HostPipe::Slot &S = hp->slot[blk % hp_slots()];
+        HostPipe::Slot &S = hp->slot[blk % HP_SLOTS];
         oip_pan_desc d = *h;
         d.row0 = r0;
         d.n_rows = nr;
         // ---- H2D of the rows this block reads (own rows + halo + stale-section rows)
-        static const bool no_wait = getenv("OIP_HP_NOWAIT") != nullptr; // timing experiment (data hazards!)
-        if (!no_wait) OIP_CUDA(cudaStreamWaitEvent(hp->h2d, S.compute_done, 0)); // the slot's previous kernel is done with d_in
+        OIP_CUDA(cudaStreamWaitEvent(hp->h2d, S.compute_done, 0)); // the slot's previous kernel is done with d_in
         for (int i = 0; i < h->n_ccd; ++i) {
             const oip_ccd_src &src = h->ccd[i];
             int64_t rg[2 * OIP_MAX_SEG];
@@ -192,7 +189,7 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
         rc = hp_reserve(&S.d_out, &S.out_cap, (size_t)(HP_BLOCK_ROWS * out_w * 2));
         if (rc) return rc;
         OIP_CUDA(cudaStreamWaitEvent(ctx->stream, S.in_ready, 0));
-        if (!no_wait) OIP_CUDA(cudaStreamWaitEvent(ctx->stream, S.out_done, 0)); // previous D2H of this slot finished
+        OIP_CUDA(cudaStreamWaitEvent(ctx->stream, S.out_done, 0)); // previous D2H of this slot finished
         d.d_out = (uint16_t *)S.d_out;
         d.out_pitch_px = out_w;
         static const bool skip_kernels = getenv("OIP_HP_SKIP_KERNELS") != nullptr; // timing experiment: copies only

@@ -96,6 +96,35 @@ __global__ void unpack_lines_kernel(const uint8_t *__restrict__ in, int fmt, int
     }
 }
 
+// word path for the packed formats: one thread = 16 output pixels = 6 (12-bit) or 5 (10-bit) aligned input words.
+// The MSB-first bit stream is rebuilt as big-endian words (one PRMT each); pixel k sits BITS*k bits from the top of the
+// group: one funnel shift + one right shift per pixel, two 16-byte stores per thread.
+template <int BITS>
+__global__ void __launch_bounds__(256) unpack_packed16_kernel(const uint8_t *__restrict__ in, int w, int64_t rows, int64_t pitch,
+                                                              uint16_t *__restrict__ out)
+{
+    constexpr int NW = BITS * 16 / 32;
+    const int64_t n16 = (int64_t)w / 16;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16 * rows; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n16;
+        const int g = (int)(i - r * n16);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(in + r * pitch) + (int64_t)g * NW;
+        uint32_t be[NW + 1];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) be[k] = __byte_perm(__ldg(src + k), 0u, 0x0123);
+        be[NW] = 0u;
+        uint32_t px[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int bit = BITS * k;
+            px[k] = __funnelshift_l(be[(bit >> 5) + 1], be[bit >> 5], bit & 31) >> (32 - BITS);
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(out + r * (int64_t)w + 16 * (int64_t)g);
+        stg_na_v4(o, make_uint4(px[0] | (px[1] << 16), px[2] | (px[3] << 16), px[4] | (px[5] << 16), px[6] | (px[7] << 16)));
+        stg_na_v4(o + 1, make_uint4(px[8] | (px[9] << 16), px[10] | (px[11] << 16), px[12] | (px[13] << 16), px[14] | (px[15] << 16)));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // StitchTiff geometry on CV_16UC4 pixels with band map (ref imageop.h:416-421, :501-506, :529)
 // one thread = one 4-channel pixel (8 B)
@@ -175,7 +204,14 @@ extern "C" int oip_unpack_lines(oip_ctx *ctx, const void *d_in, int fmt, int w, 
     if (rows == 0) return OIP_OK;
     const int64_t n = ((int64_t)w + 7) / 8 * rows;
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 32);
-    unpack_lines_kernel<<<blocks, 256, 0, ctx->stream>>>((const uint8_t *)d_in, fmt, w, rows, pitch_bytes, d_out);
+    const bool word_path = (fmt == OIP_FMT_PACK12 || fmt == OIP_FMT_PACK10) && w % 16 == 0 && pitch_bytes % 4 == 0 &&
+                           (((uintptr_t)d_in) & 3) == 0 && (((uintptr_t)d_out) & 15) == 0;
+    if (word_path) {
+        const int b2 = (int)std::min<int64_t>(((int64_t)w / 16 * rows + 255) / 256, (int64_t)ctx->sm_count * 32);
+        if (fmt == OIP_FMT_PACK12) unpack_packed16_kernel<12><<<b2, 256, 0, ctx->stream>>>((const uint8_t *)d_in, w, rows, pitch_bytes, d_out);
+        else unpack_packed16_kernel<10><<<b2, 256, 0, ctx->stream>>>((const uint8_t *)d_in, w, rows, pitch_bytes, d_out);
+    } else
+        unpack_lines_kernel<<<blocks, 256, 0, ctx->stream>>>((const uint8_t *)d_in, fmt, w, rows, pitch_bytes, d_out);
     OIP_CUDA(cudaGetLastError());
     ctx->launches++;
     return OIP_OK;

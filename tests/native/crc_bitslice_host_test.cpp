@@ -152,7 +152,16 @@ int main()
     for (int k = 0; k < 32; ++k)
         for (int f = 0; f < 32; ++f)
             if (((a[k] >> f) & 1) != ((b[f] >> k) & 1)) { puts("transpose32 wrong"); return 3; }
-    int bad = run<890>(20) + run<876>(20) + run_interleaved<890>(20) + run_interleaved<876>(20);
+    int bad = run<890>(20) + run<876>(20) + run_interleaved<890>(20) + run_interleaved<876>(20) + run_interleaved<892>(20);
+    { // message followed by its own CRC (big-endian) leaves a zero remainder: what aos_crc_kernel tests
+        uint8_t m[892];
+        for (int i = 0; i < 890; ++i) m[i] = (uint8_t)rnd();
+        const uint16_t c = crc_serial(m, 890);
+        m[890] = (uint8_t)(c >> 8); m[891] = (uint8_t)c;
+        if (crc_serial(m, 892) != 0) { puts("msg||crc remainder not zero"); ++bad; }
+        m[100] ^= 0x10;
+        if (crc_serial(m, 892) == 0) { puts("corrupted msg||crc remainder zero"); ++bad; }
+    }
     // join_level against the open-coded butterfly
     {
         uint32_t P[32][16], Q[32][16];

@@ -222,6 +222,10 @@ def test_packed_lines_extension(ctx, oracle_mod, bits):
     for im, raw in zip(imgs, raws):
         assert np.array_equal(oracle_mod.unpack_bits(raw, bits, w, rows, raw.shape[1]), im)
         assert np.array_equal(ops.unpack_lines(ctx, _dev(raw), fmt, w).cpu().numpy(), im)
+    for w2 in (496, 500, 16, 1040):  # multiples of 16 take the word path, anything else the byte path
+        im = rng.integers(0, 1 << bits, (37, w2), dtype=np.uint16)
+        raw = synth.pack_bits(im, bits)
+        assert np.array_equal(ops.unpack_lines(ctx, _dev(raw), fmt, w2).cpu().numpy(), im)
     kbs = [synth.rrc_coeffs(w, 5 + i) for i in range(2)]
     want = oracle_mod.pan_pipeline(imgs, kbs, [0, -0.83], [0, 3.19], f)
     got = ops.pan_pipeline(ctx, [_dev(r) for r in raws], [_dev(k) for k in kbs], [0, -0.83], [0, 3.19], f, fmt=fmt, w=w)
