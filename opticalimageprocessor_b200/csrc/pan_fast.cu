@@ -373,22 +373,11 @@ __device__ __forceinline__ void tile_dispatch(const FastParams &P, const FastTil
     }
 }
 
-// MINB = CTAs per SM the register allocation must allow (4: 128 registers, 3: 168)
-template <int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) pan_fast_kernel(const __grid_constant__ FastParams P)
+// one warp-tile, start to finish (the warp's stage ring and barriers are idle on entry and on return)
+__device__ __forceinline__ void run_tile(const FastParams &P, const FastTile &T, WarpCtx &C)
 {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[WARPS][MAX_STAGE];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const FastTile T = P.tiles[(int64_t)blockIdx.x * WARPS + warp];
-    if (T.kind < 0) return; // padding entry of a partial CTA; warps never synchronise with each other
-
-    WarpCtx C;
-    C.ns = P.n_stage;
-    C.lane = lane;
+    const int lane = C.lane;
     C.tm = &P.tmap[T.tmap];
-    C.stage0 = ((smem_u32(smem_raw) + 127u) & ~127u) + (uint32_t)(warp * C.ns) * STAGE_BYTES;
-    C.bar0 = smem_u32(&bars[warp][0]);
     if (lane == 0) {
         for (int s = 0; s < C.ns; ++s) mbar_init_u32(C.bar0 + 8u * s, 1);
         fence_mbar_init();
@@ -398,7 +387,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pan_fast_kernel(const __grid
         edge_tile(P, T, C);
         return;
     }
-
     // (k,b) of the 8 detectors this lane converts, and the warp-wide RRC mode
     const double *kbp = P.ccd[T.ccd].kb;
     double k[8], b[8];
@@ -421,6 +409,40 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pan_fast_kernel(const __grid
     if (mode == 1) tile_dispatch<1>(P, T, C, swap, k, b);
     else if (mode == 0) tile_dispatch<0>(P, T, C, swap, k, b);
     else tile_dispatch<2>(P, T, C, swap, k, b);
+}
+
+// MINB = CTAs per SM the register allocation must allow (4: 128 registers, 3: 168)
+template <int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) pan_fast_kernel(const __grid_constant__ FastParams P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[WARPS][MAX_STAGE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpCtx C;
+    C.ns = P.n_stage;
+    C.lane = lane;
+    C.tm = nullptr;
+    C.stage0 = ((smem_u32(smem_raw) + 127u) & ~127u) + (uint32_t)(warp * C.ns) * STAGE_BYTES;
+    C.bar0 = smem_u32(&bars[warp][0]);
+    if (!P.counter) {
+        const FastTile T = P.tiles[(int64_t)blockIdx.x * WARPS + warp];
+        if (T.kind < 0) return; // padding entry of a partial CTA; warps never synchronise with each other
+        run_tile(P, T, C);
+        return;
+    }
+    for (;;) { // persistent warp: next warp-tile from the queue
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(P.counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((int64_t)t >= P.n_tiles) break;
+        const FastTile T = P.tiles[t];
+        if (T.kind < 0) continue;
+        run_tile(P, T, C);
+        __syncwarp();
+        if (lane == 0) // every load of the tile was consumed: the barriers are idle and may be initialised again
+            for (int s = 0; s < C.ns; ++s) mbar_inval_u32(C.bar0 + 8u * s);
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -474,8 +496,13 @@ int fast_launch(oip_ctx *ctx, const FastParams &P, int64_t n_ctas)
         OIP_CUDA(cudaFuncSetAttribute(pan_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPS * MAX_STAGE * STAGE_BYTES + 128));
         ctx->fast_attr_set = true;
     }
-    if (ctx->pan_fast_minb == 3) pan_fast_kernel<3><<<(unsigned)n_ctas, WARPS * 32, smem, ctx->stream>>>(P);
-    else pan_fast_kernel<4><<<(unsigned)n_ctas, WARPS * 32, smem, ctx->stream>>>(P);
+    unsigned grid = (unsigned)n_ctas;
+    if (P.counter) { // persistent CTAs: as many as fit
+        OIP_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned int), ctx->stream));
+        grid = (unsigned)std::min<int64_t>(n_ctas, (int64_t)ctx->sm_count * ctx->pan_fast_minb);
+    }
+    if (ctx->pan_fast_minb == 3) pan_fast_kernel<3><<<grid, WARPS * 32, smem, ctx->stream>>>(P);
+    else pan_fast_kernel<4><<<grid, WARPS * 32, smem, ctx->stream>>>(P);
     OIP_CUDA(cudaGetLastError());
     ctx->launches++;
     return OIP_OK;
