@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(128) rrc_vec8_kernel(uint16_t *__restrict__ im
     const int64_t r1 = min(h, r0 + rows_per_block);
     uint16_t *p = img + r0 * pitch + (int64_t)cg * 8;
     int64_t r = r0;
+    // (four rows in flight per thread were measured: 1205 against 1252 Gpixel/s for two)
     for (; r + 1 < r1; r += 2, p += 2 * pitch) {
         uint4 a = ldg_nc_v4(p), c = ldg_nc_v4(p + pitch);
         uint32_t *aw = reinterpret_cast<uint32_t *>(&a), *cw = reinterpret_cast<uint32_t *>(&c);
@@ -135,30 +136,37 @@ struct ConcatC4 {
     int64_t rows;
     int map[4];
 };
-__global__ void concat_c4_kernel(const __grid_constant__ ConcatC4 P, uint16_t *__restrict__ out)
+__global__ void __launch_bounds__(256) concat_c4_kernel(const __grid_constant__ ConcatC4 P, uint16_t *__restrict__ out)
 {
+    // grid: x over the output pixels of a line, y (strided) over the lines; the channel map as two PRMT selectors
     const int wout = P.n * P.w - 2 * (P.n - 1) * P.f;
-    const int64_t total = (int64_t)wout * P.rows;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t y = i / wout;
-        int xo = (int)(i - y * wout);
-        // which image: widths are w-f, w-2f ..., w-f
-        int k = 0, x = xo;
-        int first = P.n == 1 ? P.w : P.w - P.f;
-        if (x >= first) {
-            x -= first;
-            int mid = P.w - 2 * P.f;
-            k = 1 + (mid > 0 ? x / mid : 0);
-            if (k > P.n - 1) k = P.n - 1;
-            x -= (k - 1) * mid;
-            x += P.f;
-        }
-        const uint2 s = *reinterpret_cast<const uint2 *>(P.img[k] + (y * P.w + x) * 4);
-        uint16_t c[4] = {(uint16_t)(s.x & 0xFFFF), (uint16_t)(s.x >> 16), (uint16_t)(s.y & 0xFFFF), (uint16_t)(s.y >> 16)};
+    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xo >= wout) return;
+    int k = 0, x = xo; // which image: widths are w-f, w-2f ..., w-f
+    const int first = P.n == 1 ? P.w : P.w - P.f;
+    if (x >= first) {
+        x -= first;
+        const int mid = P.w - 2 * P.f;
+        k = 1 + (mid > 0 ? x / mid : 0);
+        if (k > P.n - 1) k = P.n - 1;
+        x -= (k - 1) * mid;
+        x += P.f;
+    }
+    uint32_t sel[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int m0 = P.map[2 * h], m1 = P.map[2 * h + 1]; // output halfwords 2h, 2h+1 <- input halfwords m0, m1
+        sel[h] = (uint32_t)(2 * m0) | ((uint32_t)(2 * m0 + 1) << 4) | ((uint32_t)(2 * m1) << 8) | ((uint32_t)(2 * m1 + 1) << 12);
+    }
+    const uint16_t *src = P.img[k] + (int64_t)x * 4;
+    const int64_t in_pitch = (int64_t)P.w * 4, out_pitch = (int64_t)wout * 4;
+    for (int64_t y = blockIdx.y; y < P.rows; y += gridDim.y) {
+        uint2 s;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(s.x), "=r"(s.y) : "l"(src + y * in_pitch));
         uint2 o;
-        o.x = (uint32_t)c[P.map[0]] | ((uint32_t)c[P.map[1]] << 16);
-        o.y = (uint32_t)c[P.map[2]] | ((uint32_t)c[P.map[3]] << 16);
-        *reinterpret_cast<uint2 *>(out + i * 4) = o;
+        o.x = __byte_perm(s.x, s.y, sel[0]);
+        o.y = __byte_perm(s.x, s.y, sel[1]);
+        asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(out + y * out_pitch + (int64_t)xo * 4), "r"(o.x), "r"(o.y) : "memory");
     }
 }
 
@@ -236,9 +244,10 @@ extern "C" int oip_stitch_concat_c4(oip_ctx *ctx, const uint16_t *const *d_img, 
         P.map[b] = m - 1;
     }
     if (rows == 0) return OIP_OK;
-    const int64_t total = (int64_t)oip_pan_out_width(n_img, w, fold_half) * rows;
-    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 32);
-    concat_c4_kernel<<<blocks, 256, 0, ctx->stream>>>(P, d_dst);
+    const int wout = oip_pan_out_width(n_img, w, fold_half);
+    const int bx = (wout + 255) / 256;
+    const int by = (int)std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)ctx->sm_count * 32 / bx));
+    concat_c4_kernel<<<dim3(bx, by), 256, 0, ctx->stream>>>(P, d_dst);
     OIP_CUDA(cudaGetLastError());
     ctx->launches++;
     return OIP_OK;
