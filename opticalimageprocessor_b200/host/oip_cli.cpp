@@ -9,8 +9,9 @@
 //   * default action: the inter-band correlation + polynomial fit (ref preproc.h:224-347,492-550) runs on the GPU
 //     (oip_inter_band_correlation); the extension option --poly FILE (4 lines of cx0 cx1 cy0 cy1 cy2) skips it.
 //   * TIFF files (host/tiff_io.hpp): written uncompressed (the reference's libraries compress with LZW), so
-//     they match in geometry, sample order and pixel values, not byte for byte; TIFF INPUT must be uncompressed strips
-//     (our own products).  --aligned-raw additionally writes <stem>.ALIGNED.RAW (the CV_16UC4 memory image).
+//     they match in geometry, sample order and pixel values, not byte for byte; TIFF INPUT may be uncompressed or LZW
+//     (predictor 1 / 2) strips, i.e. our own products and the reference's.  --aligned-raw additionally writes
+//     <stem>.ALIGNED.RAW (the CV_16UC4 memory image).
 // There is no CPU fallback: without a B200 every command fails with exit code 2.
 #include <strings.h>
 #include <sys/stat.h>

@@ -3,8 +3,9 @@
 // Writes what cv::imwrite (ref preproc.h:167-185, imageop.h:444) and the GTiff driver (ref imageop.h:316-328, :470-538)
 // are used for there: 16-bit unsigned rasters with 1 or 4 interleaved samples per pixel, as baseline TIFF strips
 // (classic TIFF below 4 GiB, BigTIFF above), UNCOMPRESSED -- the reference's own files are LZW-compressed by those
-// libraries, so files are equal in pixel content and geometry, not byte for byte.  Reads back the same subset
-// (uncompressed, chunky, 16-bit, either byte order, strips), which is what `stitch` needs for two of our own products.
+// libraries, so files are equal in pixel content and geometry, not byte for byte.  Reads uncompressed and LZW-compressed
+// (predictor 1 or 2) chunky 16-bit strip TIFFs of either byte order: our own products and the reference's (cv::imwrite
+// defaults, GTiff COMPRESS=LZW PREDICTOR=2).
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -17,7 +18,7 @@ namespace oiptiff {
 
 struct Info {
     int64_t width = 0, height = 0, rows_per_strip = 0;
-    int spp = 1, bits = 16, compression = 1, planar = 1, photometric = 1;
+    int spp = 1, bits = 16, compression = 1, planar = 1, photometric = 1, predictor = 1;
     bool big = false, little = true;
     std::vector<uint64_t> strip_off, strip_cnt;
 };
@@ -169,6 +170,7 @@ inline Info read_info(const std::string &path)
             case 278: I.rows_per_strip = (int64_t)values().at(0); break;
             case 279: I.strip_cnt = values(); break;
             case 284: I.planar = (int)values().at(0); break;
+            case 317: I.predictor = (int)values().at(0); break;
             case 322: case 323: case 324: case 325: throw std::runtime_error("tiff: tiled TIFF is not supported: " + path);
             default: break;
             }
@@ -182,30 +184,101 @@ inline Info read_info(const std::string &path)
     return I;
 }
 
-// the whole raster, u16 host order, samples interleaved in file order
+namespace detail {
+// TIFF LZW (compression 5): MSB-first codes of 9..12 bits, 256 = clear, 257 = end of information, the code width grows
+// one entry early (libtiff's "early change"), every strip is its own stream.  Returns the bytes produced.
+inline size_t lzw_decode(const uint8_t *src, size_t n_src, uint8_t *dst, size_t n_dst)
+{
+    struct Entry { uint16_t prefix; uint8_t last, first; uint32_t len; };
+    std::vector<Entry> tab(4096);
+    for (int i = 0; i < 256; ++i) tab[i] = {0xFFFF, (uint8_t)i, (uint8_t)i, 1};
+    int next = 258, width = 9;
+    int prev = -1;
+    uint64_t acc = 0;
+    int nbits = 0;
+    size_t ip = 0, op = 0;
+    for (;;) {
+        while (nbits < width && ip < n_src) { acc = (acc << 8) | src[ip++]; nbits += 8; }
+        if (nbits < width) break;
+        const int code = (int)((acc >> (nbits - width)) & ((1u << width) - 1));
+        nbits -= width;
+        if (code == 257) break;
+        if (code == 256) { next = 258; width = 9; prev = -1; continue; }
+        int cur = code;
+        if (prev < 0) {
+            if (code >= 256) throw std::runtime_error("tiff: corrupt LZW stream");
+        } else {
+            if (code > next) throw std::runtime_error("tiff: corrupt LZW stream");
+            if (next < 4096) { // new entry = string(prev) + first byte of string(code) (or of string(prev) when code == next)
+                const uint8_t fb = code < next ? tab[code].first : tab[prev].first;
+                tab[next] = {(uint16_t)prev, fb, tab[prev].first, tab[prev].len + 1};
+                ++next;
+            }
+        }
+        const uint32_t len = tab[cur].len;
+        if (op + len > n_dst) { // the last strip may carry padding: stop at the raster's end
+            std::vector<uint8_t> tmp(len);
+            int c = cur;
+            for (uint32_t k = len; k-- > 0;) { tmp[k] = tab[c].last; c = tab[c].prefix; }
+            const size_t take = n_dst - op;
+            memcpy(dst + op, tmp.data(), take);
+            op += take;
+            break;
+        }
+        int c = cur;
+        for (uint32_t k = len; k-- > 0;) { dst[op + k] = tab[c].last; c = tab[c].prefix; }
+        op += len;
+        prev = cur;
+        if (next + 1 >= (1 << width) && width < 12) ++width; // early change
+    }
+    return op;
+}
+} // namespace detail
+
+// the whole raster, u16 host order, samples interleaved in file order.  Uncompressed or LZW (what cv::imwrite and the
+// reference's GTiff options produce, ref imageop.h:470-474), predictor 1 or 2, chunky, 16-bit, strips.
 inline void read_u16(const std::string &path, const Info &I, uint16_t *dst)
 {
-    if (I.compression != 1)
+    if (I.compression != 1 && I.compression != 5)
         throw std::runtime_error("tiff: compressed TIFF (compression " + std::to_string(I.compression) +
-                                 ") is not supported by this build -- re-save it uncompressed: " + path);
-    if (I.bits != 16 || I.planar != 1 || I.strip_off.empty() || I.strip_off.size() != I.strip_cnt.size())
-        throw std::runtime_error("tiff: only 16-bit chunky strip TIFF is supported: " + path);
+                                 ") is not supported by this build -- re-save it uncompressed or with LZW: " + path);
+    if (I.bits != 16 || I.planar != 1 || I.strip_off.empty() || I.strip_off.size() != I.strip_cnt.size() ||
+        (I.predictor != 1 && I.predictor != 2))
+        throw std::runtime_error("tiff: only 16-bit chunky strip TIFF (predictor 1 or 2) is supported: " + path);
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("tiff: cannot open " + path);
     const uint64_t row_bytes = (uint64_t)I.width * I.spp * 2;
     bool ok = true;
-    for (size_t s = 0; ok && s < I.strip_off.size(); ++s) {
-        const uint64_t r0 = (uint64_t)s * (uint64_t)I.rows_per_strip;
-        if (r0 >= (uint64_t)I.height) break;
-        const uint64_t want = std::min<uint64_t>((uint64_t)I.rows_per_strip, (uint64_t)I.height - r0) * row_bytes;
-        ok = I.strip_cnt[s] >= want && fseeko(f, (off_t)I.strip_off[s], SEEK_SET) == 0 &&
-             fread(reinterpret_cast<uint8_t *>(dst) + r0 * row_bytes, 1, (size_t)want, f) == (size_t)want;
+    std::vector<uint8_t> comp;
+    try {
+        for (size_t s = 0; ok && s < I.strip_off.size(); ++s) {
+            const uint64_t r0 = (uint64_t)s * (uint64_t)I.rows_per_strip;
+            if (r0 >= (uint64_t)I.height) break;
+            const uint64_t want = std::min<uint64_t>((uint64_t)I.rows_per_strip, (uint64_t)I.height - r0) * row_bytes;
+            uint8_t *out = reinterpret_cast<uint8_t *>(dst) + r0 * row_bytes;
+            if (I.compression == 1) {
+                ok = I.strip_cnt[s] >= want && fseeko(f, (off_t)I.strip_off[s], SEEK_SET) == 0 && fread(out, 1, (size_t)want, f) == (size_t)want;
+            } else {
+                comp.resize((size_t)I.strip_cnt[s]);
+                ok = fseeko(f, (off_t)I.strip_off[s], SEEK_SET) == 0 && fread(comp.data(), 1, comp.size(), f) == comp.size() &&
+                     detail::lzw_decode(comp.data(), comp.size(), out, (size_t)want) == (size_t)want;
+            }
+        }
+    } catch (...) {
+        fclose(f);
+        throw;
     }
     fclose(f);
     if (!ok) throw std::runtime_error("tiff: truncated or inconsistent strips: " + path);
-    if (!I.little) {
-        const uint64_t n = (uint64_t)I.width * I.height * I.spp;
+    const uint64_t n = (uint64_t)I.width * I.height * I.spp;
+    if (!I.little)
         for (uint64_t i = 0; i < n; ++i) dst[i] = (uint16_t)((dst[i] >> 8) | (dst[i] << 8));
+    if (I.predictor == 2) { // horizontal differencing per sample, row by row (on the 16-bit values)
+        const uint64_t rs = (uint64_t)I.width * I.spp;
+        for (int64_t y = 0; y < I.height; ++y) {
+            uint16_t *row = dst + (uint64_t)y * rs;
+            for (uint64_t i = (uint64_t)I.spp; i < rs; ++i) row[i] = (uint16_t)(row[i] + row[i - I.spp]);
+        }
     }
 }
 

@@ -185,7 +185,7 @@ def test_default_action_mss(cli, tmp_path, oracle_mod):
     assert tif is not None and tif.shape == (lines - 520, wb, 4) and np.array_equal(tif[:n], want[:n])
     # stitch two 4-channel TIFFs (IMO::StitchTiff, ref imageop.h:365-457; GDAL variant with band map :460-567)
     os.rename(os.path.join(d, "SYN_MSS-1.ALIGNED.TIFF"), os.path.join(d, "L.TIFF"))
-    cv2.imwrite(os.path.join(d, "R.TIFF"), tif[:, ::-1].copy(), [cv2.IMWRITE_TIFF_COMPRESSION, 1])   # a libtiff-written input
+    cv2.imwrite(os.path.join(d, "R.TIFF"), tif[:, ::-1].copy())   # a libtiff-written input with cv::imwrite's defaults (LZW, predictor 2)
     r = run(cli, ["stitch", "--image1=L.TIFF", "--image2=R.TIFF", "--fold-cols=50"], d)
     assert r.returncode == 0, r.stdout + r.stderr
     st = cv2.imread(os.path.join(d, "stitched.TIFF"), cv2.IMREAD_UNCHANGED)                          # default name, ref :373-375

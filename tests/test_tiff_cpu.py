@@ -37,12 +37,26 @@ def test_written_files_are_read_by_libtiff(exe, tmp_path, h, w, spp):
     assert np.array_equal(np.fromfile(back, np.uint16).reshape(h, w, spp), px)
 
 
-def test_reads_uncompressed_libtiff_files_and_refuses_lzw(exe, tmp_path):
-    img = np.random.default_rng(2).integers(0, 65536, (300, 200, 4), dtype=np.uint16)
-    plain, lzw, back = str(tmp_path / "plain.TIFF"), str(tmp_path / "lzw.TIFF"), str(tmp_path / "back.raw")
-    assert cv2.imwrite(plain, img, [cv2.IMWRITE_TIFF_COMPRESSION, 1])
-    assert cv2.imwrite(lzw, img)  # cv::imwrite default: LZW, what the reference produces
-    subprocess.check_call([exe, "read", plain, back])
-    assert np.array_equal(np.fromfile(back, np.uint16).reshape(300, 200, 4), img[:, :, [2, 1, 0, 3]])  # file order = RGBA
-    r = subprocess.run([exe, "read", lzw, back], capture_output=True, text=True)
+@pytest.mark.parametrize("shape", [(300, 200, 4), (257, 333, 1), (64, 5000, 4), (2000, 96, 1)])
+def test_reads_libtiff_files_uncompressed_and_lzw(exe, tmp_path, shape):
+    """cv::imwrite defaults (LZW + horizontal predictor, many strips) = what the reference's own TIFF products look like"""
+    rng = np.random.default_rng(shape[0])
+    smooth = (np.cumsum(rng.integers(-3, 4, shape), axis=1) + 2000).astype(np.uint16)   # compressible, exercises long LZW strings
+    noise = rng.integers(0, 65536, shape, dtype=np.uint16)
+    for img in (smooth, noise, np.zeros(shape, np.uint16)):
+        im = img[:, :, 0] if shape[2] == 1 else img
+        plain, lzw, back = str(tmp_path / "plain.TIFF"), str(tmp_path / "lzw.TIFF"), str(tmp_path / "back.raw")
+        assert cv2.imwrite(plain, im, [cv2.IMWRITE_TIFF_COMPRESSION, 1])
+        assert cv2.imwrite(lzw, im)  # cv::imwrite default: LZW, what the reference produces
+        want = img[:, :, [2, 1, 0, 3]] if shape[2] == 4 else img  # file order = RGBA
+        for path in (plain, lzw):
+            subprocess.check_call([exe, "read", path, back])
+            assert np.array_equal(np.fromfile(back, np.uint16).reshape(shape), want), path
+
+
+def test_refuses_other_compressions(exe, tmp_path):
+    img = np.random.default_rng(2).integers(0, 65536, (64, 64, 4), dtype=np.uint16)
+    z, back = str(tmp_path / "deflate.TIFF"), str(tmp_path / "back.raw")
+    assert cv2.imwrite(z, img, [cv2.IMWRITE_TIFF_COMPRESSION, 8])  # Adobe deflate
+    r = subprocess.run([exe, "read", z, back], capture_output=True, text=True)
     assert r.returncode == 1 and "compressed TIFF" in r.stderr
