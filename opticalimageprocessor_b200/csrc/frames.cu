@@ -77,35 +77,6 @@ __device__ __forceinline__ uint32_t warp_crc16(const CrcPlan &P, GetByte get)
     return c ^ P.init_term;
 }
 
-// Same split, message held in shared memory: lane l reads its 28-byte piece as 7 (+1) aligned words and runs the
-// byte recurrence out of registers (no byte loads, fully unrolled).  w32 = aligned word that holds message byte 0,
-// sh = byte offset (0..3) of message byte 0 inside it; up to 3 bytes past the piece are read (callers pad).
-// Needs P.cs == 28 (true for the two frame formats: 890 and 876 message bytes).
-__device__ __forceinline__ uint32_t warp_crc16_words(const CrcPlan &P, const uint32_t *w32, int sh)
-{
-    const int lane = threadIdx.x & 31;
-    const uint32_t *w = w32 + 7 * lane;
-    uint32_t v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = w[j];
-    const int nb = max(0, min(28, P.len - 28 * lane));
-    const uint32_t s8 = 8u * (uint32_t)sh;
-    uint32_t r = 0;
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-        const uint32_t m = __funnelshift_r(v[j], v[j + 1], s8);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const uint32_t nr = crc16_byte(r, (m >> (8 * b)) & 0xFFu);
-            r = 4 * j + b < nb ? nr : r;
-        }
-    }
-    uint32_t c = gfmul16(r, P.mul[lane]);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
-    return c ^ P.init_term;
-}
-
 // =============================================================================================
 // generic exclusive scan (u32), three small kernels; used on candidate tables only
 // =============================================================================================
@@ -557,6 +528,7 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_kernel(const uint8_t *__
         if (f0 + q >= n_frames) break;
         uint32_t *fw = s_w + (IMTR_FRONT + q * IMTR_SLOT) / 4;
         const FrameSegs S = frame_segs(buf, poff, n_payload, (f0 + q) * 882);
+        // (splitting this loop into a load pass over the warp's 8 frames and a fix-up / output pass was measured: slower)
         uint32_t v[7]; // 220 whole words + 2 bytes; all of a lane's loads are issued before the first store
 #pragma unroll
         for (int u = 0; u < 7; ++u) v[u] = seg_word(S, 4 * min(lane + 32 * u, 219));
