@@ -69,6 +69,32 @@ def main():
         ok = bad.size == 0
         if not ok:
             print(f"rank {rank}: {len(bad)} px differ, first {bad[:5].tolist()}", flush=True)
+    # ---- C3: the band alignment shards by section; every rank holds only the lines of its own sections and the strip's
+    #      output is the concatenation of the ranks' outputs; the offset-estimation sums go through one all-reduce
+    import oracle
+    lines, wb, lps, ov = 2300 * world, 96, 700, 60
+    mixed = np.random.default_rng(77).integers(0, 4096, (lines, 4 * wb)).astype(np.uint16)
+    mkb = [synth.rrc_coeffs(wb, 300 + b) for b in range(4)]
+    cX = [[0.8 + 0.1 * b, -1.5e-4 * (b + 1)] for b in range(4)]
+    cY = [[-3.2 + b, 2e-4 * (b + 1), -1e-8 * (b - 1.5)] for b in range(4)]
+    secs = sharding.mss_sections(lines, lps, ov, 0, False, 200)
+    mine = sharding.mss_rank_sections(secs, world, rank)
+    lo, hi = mine[0][0], mine[-1][0] + mine[-1][1]
+    shard = torch.from_numpy(np.ascontiguousarray(mixed[lo:hi])).cuda()
+    n_out = sum(sc[4] for sc in mine)
+    mout = torch.zeros((n_out, wb, 4), dtype=torch.uint16, device="cuda")
+    k = ops.band_align_sections(ctx, shard, wb, [torch.from_numpy(q).cuda() for q in mkb], cX, cY, mine, secs, mout, total_lines=lines,
+                                lines_per_section=lps, overlap=ov, min_process_lines=200, src_row0=lo)
+    planes = [oracle.rrc(pl, q) for pl, q in zip(oracle.mss_split(mixed), mkb)]
+    n_all, want_m = oracle.band_align(planes, cX, cY, lines_per_section=lps, overlap=ov, min_process_lines=200)
+    o0 = mine[0][3]
+    ok_m = k == n_out and np.array_equal(mout.cpu().numpy(), want_m[o0:o0 + n_out])
+    if not ok_m:
+        print(f"rank {rank}: MSS section shard differs from the whole-strip oracle", flush=True)
+    ok = ok and ok_m
+    sums = torch.tensor([1.37 * (rank + 1), -2.61, 0.9, 1.0], dtype=torch.float64, device="cuda")   # what oip_stt_parameters hands back
+    dist.all_reduce(sums)
+    ok = ok and sharding.stt_combine(sums.tolist())[1] == -2.61 and int(sums[3].item()) == world
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()

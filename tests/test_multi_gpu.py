@@ -1,4 +1,5 @@
-"""GPU parity at N=2: sharded fused PAN path with NVLink peer halo rows vs the whole-strip oracle."""
+"""GPU parity at N=2: sharded fused PAN path with NVLink peer halo rows, and the band alignment sharded by section, vs the
+whole-strip oracle; the offset-estimation sums through one all-reduce."""
 import os
 import subprocess
 import sys
