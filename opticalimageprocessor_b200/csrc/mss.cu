@@ -310,7 +310,9 @@ extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_m
     const bool fast_ok = ctx->mss_fast != 0 && (((uintptr_t)d_mss & 15) == 0) && ((d->pitch_px * 2) % 16 == 0) && d->wb >= 16;
     struct Key { int wb, lps, overlap, keep, min_lines, fast, tile_rows, sec_first, sec_count; int64_t lines, off, src_row0; double cX[8], cY[12]; } key{};
     key.wb = d->wb; key.lps = lps; key.overlap = overlap; key.keep = d->keep_leading != 0; key.min_lines = min_lines;
-    key.fast = fast_ok; key.tile_rows = ctx->mss_fast_rows; key.lines = d->lines; key.off = d->line_offset;
+    // long strips: taller warp-tiles amortise the per-tile prologue (C3: 501 -> 515 Gpixel/s, tools/bench_mss.py)
+    const int tile_rows = (ctx->mss_fast_rows == 128 && d->lines >= 32768) ? 256 : ctx->mss_fast_rows;
+    key.fast = fast_ok; key.tile_rows = tile_rows; key.lines = d->lines; key.off = d->line_offset;
     key.sec_first = d->sec_first; key.sec_count = d->sec_count; key.src_row0 = d->src_row0;
     memcpy(key.cX, d->cX, sizeof key.cX); memcpy(key.cY, d->cY, sizeof key.cY);
     const uint8_t *kbytes = reinterpret_cast<const uint8_t *>(&key);
@@ -323,7 +325,7 @@ extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_m
                             (long long)(sc.sec_off + d->src_row0), (long long)d->src_row0);
         std::vector<mss::Tile> tiles;
         std::vector<mssfast::FTile> ftiles;
-        mssfast::plan(d, secs, fast_ok, ctx->mss_fast_rows, tiles, ftiles);
+        mssfast::plan(d, secs, fast_ok, tile_rows, tiles, ftiles);
         ctx->mss_plan_rows = processed;
         float tab[132] = {};
         oip_cubic_tab(tab);

@@ -19,6 +19,8 @@ if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = ops.Context(local)
+if os.environ.get("MSS_FAST_ROWS"):  # development: warp-tile height of mss_fast_kernel
+    ctx.set_option("mss_fast_rows", int(os.environ["MSS_FAST_ROWS"]))
 LINES, WB, LPS, OV = 65536, 3072, 20000, 520
 total_lines = LINES * world                                   # weak scaling: one C3-sized strip per GPU
 secs = sharding.mss_sections(total_lines, LPS, OV, 0, False, 1500)
