@@ -126,7 +126,6 @@ int oip_ctx_set_option(oip_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "pan_fast")) ctx->pan_fast = value != 0;
     else if (!strcmp(name, "pan_fast_stages") && value >= 2 && value <= 8) ctx->pan_fast_stages = (int)value;
     else if (!strcmp(name, "pan_fast_minb") && value >= 3 && value <= 4) ctx->pan_fast_minb = (int)value;
-    else if (!strcmp(name, "pan_fast_dynamic")) ctx->pan_fast_dynamic = value != 0;
     else if (!strcmp(name, "host_block_rows") && value >= 64 && value <= (1 << 20)) ctx->host_block_rows = (int)value;
     else if (!strcmp(name, "mss_fast")) ctx->mss_fast = value != 0;
     else if (!strcmp(name, "mss_fast_rows") && value >= 16 && value <= 32768) ctx->mss_fast_rows = (int)value;

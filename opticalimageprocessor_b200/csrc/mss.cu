@@ -10,12 +10,11 @@
 namespace oip {
 namespace mss {
 
-constexpr int TW = 240;   // output columns per tile
+// tile limits (the planner in mss_fast.cu cuts generic tiles to them): 240 output columns x 256 output rows
 constexpr int SWC = 256;  // staged source columns
 constexpr int RC = 32;    // output rows per chunk
 constexpr int RING = 48;  // float ring rows: RC + 3 taps + spread of the per-column row offsets
 constexpr int NT = 256;
-constexpr int TH = 256;   // output rows per tile
 
 struct Params {
     const uint8_t *base;

@@ -40,8 +40,6 @@ struct oip_ctx {
     int pan_fast_stages = 4;     // TMA stages per warp
     int pan_fast_rows = 128;     // output rows per warp-tile
     int pan_fast_minb = 3;       // register-allocation variant of pan_fast_kernel (CTAs per SM: 2, 3, 4)
-    int pan_fast_dynamic = 0;    // 1: persistent warps pull warp-tiles from a queue.  Measured on C2: 1.25 ms against 1.03 ms for
-                                 // the static mapping (one CTA per 4 consecutive tiles) -- kept as an option, off by default
     void *d_mss_plan = nullptr;
     size_t d_mss_plan_cap = 0;
     std::vector<uint8_t> mss_plan_key;
@@ -169,14 +167,14 @@ __device__ __forceinline__ f2 pk(float lo, float hi)
 }
 __device__ __forceinline__ float lo_of(f2 v)
 {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    float a;
+    asm("{\n\t.reg .f32 t;\n\tmov.b64 {%0, t}, %1;\n\t}" : "=f"(a) : "l"(v));
     return a;
 }
 __device__ __forceinline__ float hi_of(f2 v)
 {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    float b;
+    asm("{\n\t.reg .f32 t;\n\tmov.b64 {t, %0}, %1;\n\t}" : "=f"(b) : "l"(v));
     return b;
 }
 // ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false (it honours the

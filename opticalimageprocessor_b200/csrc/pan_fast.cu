@@ -424,25 +424,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pan_fast_kernel(const __grid
     C.tm = nullptr;
     C.stage0 = ((smem_u32(smem_raw) + 127u) & ~127u) + (uint32_t)(warp * C.ns) * STAGE_BYTES;
     C.bar0 = smem_u32(&bars[warp][0]);
-    if (!P.counter) {
-        const FastTile T = P.tiles[(int64_t)blockIdx.x * WARPS + warp];
-        if (T.kind < 0) return; // padding entry of a partial CTA; warps never synchronise with each other
-        run_tile(P, T, C);
-        return;
-    }
-    for (;;) { // persistent warp: next warp-tile from the queue
-        unsigned int t = 0;
-        if (lane == 0) t = atomicAdd(P.counter, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if ((int64_t)t >= P.n_tiles) break;
-        const FastTile T = P.tiles[t];
-        if (T.kind < 0) continue;
-        run_tile(P, T, C);
-        __syncwarp();
-        if (lane == 0) // every load of the tile was consumed: the barriers are idle and may be initialised again
-            for (int s = 0; s < C.ns; ++s) mbar_inval_u32(C.bar0 + 8u * s);
-        __syncwarp();
-    }
+    const FastTile T = P.tiles[(int64_t)blockIdx.x * WARPS + warp];
+    if (T.kind < 0) return; // padding entry of a partial CTA; warps never synchronise with each other
+    run_tile(P, T, C);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -496,13 +480,8 @@ int fast_launch(oip_ctx *ctx, const FastParams &P, int64_t n_ctas)
         OIP_CUDA(cudaFuncSetAttribute(pan_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPS * MAX_STAGE * STAGE_BYTES + 128));
         ctx->fast_attr_set = true;
     }
-    unsigned grid = (unsigned)n_ctas;
-    if (P.counter) { // persistent CTAs: as many as fit
-        OIP_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned int), ctx->stream));
-        grid = (unsigned)std::min<int64_t>(n_ctas, (int64_t)ctx->sm_count * ctx->pan_fast_minb);
-    }
-    if (ctx->pan_fast_minb == 3) pan_fast_kernel<3><<<grid, WARPS * 32, smem, ctx->stream>>>(P);
-    else pan_fast_kernel<4><<<grid, WARPS * 32, smem, ctx->stream>>>(P);
+    if (ctx->pan_fast_minb == 3) pan_fast_kernel<3><<<(unsigned)n_ctas, WARPS * 32, smem, ctx->stream>>>(P);
+    else pan_fast_kernel<4><<<(unsigned)n_ctas, WARPS * 32, smem, ctx->stream>>>(P);
     OIP_CUDA(cudaGetLastError());
     ctx->launches++;
     return OIP_OK;

@@ -48,10 +48,6 @@ struct FastParams {
     const float *tab; // 32x4 cubic weights, then the run-time (-0.0,-0.0) pair
     int32_t w;
     int32_t n_stage; // TMA stages per warp (2..8)
-    // dynamic tile queue: persistent warps pull the next warp-tile with one atomic (no idle warps in a CTA whose other
-    // tiles are longer, no partial last wave); counter == nullptr: warp w of CTA c takes tile c * WARPS + w
-    unsigned int *counter;
-    int64_t n_tiles;
 };
 
 // host side (pan_fast.cu)

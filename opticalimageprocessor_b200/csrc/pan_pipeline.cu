@@ -1145,9 +1145,6 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         F.tab = reinterpret_cast<const float *>(ctx->d_plan);
         F.w = d->w;
         F.n_stage = std::max(2, std::min(8, ctx->pan_fast_stages));
-        // the tile queue's counter lives in the plan buffer's header (after the weight table)
-        F.counter = ctx->pan_fast_dynamic ? reinterpret_cast<unsigned int *>((uint8_t *)ctx->d_plan + 768) : nullptr;
-        F.n_tiles = ctx->plan_fast_ctas * panfast::WARPS;
         rc = panfast::fast_launch(ctx, F, ctx->plan_fast_ctas);
         if (rc) return rc;
     }

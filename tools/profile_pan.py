@@ -5,8 +5,6 @@ import numpy as np, torch
 import bench
 from opticalimageprocessor_b200 import ops, synth, capi
 ctx = ops.Context(0)
-if os.environ.get("PAN_DYNAMIC") is not None:
-    ctx.set_option("pan_fast_dynamic", int(os.environ["PAN_DYNAMIC"]))
 rows = int(os.environ.get("ROWS", bench.ROWS))
 ccds = [torch.from_numpy(synth.strip_dn(bench.W, rows, bench.SEED + i).byteswap()).cuda() for i in range(bench.N_CCD)]
 kbs = [torch.from_numpy(synth.rrc_coeffs(bench.W, bench.SEED + 100 + i)).cuda() for i in range(bench.N_CCD)]
