@@ -4,19 +4,26 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One step = one pass of the fused kernel over one strip shard: BASELINE.json configs[1]
-("3-CCD panchromatic strip, 3x8192 px with overlap, 32k lines") per GPU.  At N > 1 the strip is
-N x 32768 lines long, sharded by scanline blocks (weak scaling); section geometry is global and
-the few halo rows a shard needs from its neighbours are read by the kernel straight from the
-neighbour GPU's memory over NVLink (CUDA IPC peer mappings), no data-path collective.
+Workload = BASELINE.json configs[3], the configuration north_star quotes its target on: a 24576 px (3 CCD x 8192)
+x 1 048 576-line panchromatic strip, 16-bit big-endian raw samples (the byte order inside the downlink sub-images), fold 200,
+seam offsets (1.37, -2.61) / (-0.83, 3.19).  It fits one B200 (51.5 GB in + 50.7 GB out), so N = 1 runs the whole strip and
+N > 1 splits the SAME strip into N scanline blocks (strong scaling).  Section geometry is a function of the global line
+index; the few halo rows a block needs from its neighbours are read by the kernel straight from the neighbour GPU's
+memory over NVLink (CUDA IPC peer mappings), no data-path collective.  One step = one pass of the fused kernels over
+the rank's block.
 
-value    : Gpixel/s, device-timed (CUDA events on the launching stream), inputs resident in HBM,
-           whole job over all ranks, max over ranks.
-e2e      : same metric through the host-buffer C-ABI call (pinned host in/out, H2D/D2H inside).
+value    : Gpixel/s, device-timed (CUDA events on the launching stream), inputs resident in HBM, whole job over all
+           ranks, max over ranks.  Warm-up runs until the GPU has worked for >= 2 s (so the clocks are the sustained
+           ones), never fewer than --warmup / 3 steps.
+parity   : outside the timed region every rank compares a bounded set of its output rows (first / last 16 rows of its
+           block, +-8 rows around every global section edge of both shifted CCDs, the stale bottom rows) with the CPU
+           oracle (oracle.pan_rows) -> "parity_ok".
+e2e      : same metric through the host-buffer C-ABI call (oip_pan_pipeline_host: pinned host in/out, H2D + kernels +
+           D2H inside the timed call), every rank on its own block, max over ranks.
 roofline : algorithmic HBM bytes of the fused kernel / its mean launch time vs the measured copy peak.
-cpu_baseline / --impl reference : the reference's CPU path for the same work = fp64 RRC loop
-           (single thread, ref imageop.h:129-138) + cv2.remap in 30000-row sections with OpenCV's own
-           thread pool (the library call at imageop.h:258) + line concat, on a bounded slice.
+cpu_baseline / --impl reference : the reference's CPU path for the same work = fp64 RRC loop (single thread, ref
+           imageop.h:129-138) + cv2.remap in 30000-row sections with OpenCV's own thread pool (the library call at
+           imageop.h:258) + line concat, on a bounded slice of the same strip.
 """
 from __future__ import annotations
 
@@ -33,12 +40,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_CCD, W, ROWS, FOLD = 3, 8192, 32768, 200
+N_CCD, W, TOTAL_ROWS, FOLD = 3, 8192, 1 << 20, 200
 DX = [0.0, 1.37, -0.83]
 DY = [0.0, -2.61, 3.19]
-SEED = 0x0A11CE02
+SEED = 0x0A11CE04
 METRIC = "Gpixel/s (raw->stitched, device-timed)"
-WORKLOAD = "C2: 3 CCD x 8192 px x 32768 lines per GPU, 16-bit BE raw in, fold 200, RRC + cubic shift + stitch"
+WORKLOAD = ("C4: 24576 px (3 CCD x 8192) x 1048576 lines, 16-bit BE raw in, fold 200, RRC + cubic shift + stitch; "
+            "the strip is split into N scanline blocks (strong scaling)")
+WARM_SECONDS = 2.0
+REF_ROWS = 59996   # lines one step of the CPU reference arm processes: exactly two full 30000-row sections for both shifted CCDs (advance 29997 / 29996), like the 35 sections of the whole strip
 
 
 def hbm_peak():
@@ -103,30 +113,52 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference_pass(rows: int, threads=None):
-    """the reference's CPU path on `rows` lines of the C2 strip; returns seconds (in-memory, no disk)"""
+    """the reference's CPU path on the first `rows` lines of the strip (as a strip of its own); returns seconds (in memory,
+    no disk; the map fill of stitcher.h:93-99 is left out of the timed region -- generous to the reference)"""
     import cv2
     import oracle
     from opticalimageprocessor_b200 import synth
     oracle.build()
     if threads:
         cv2.setNumThreads(threads)
-    S = 30000
+    S, G = 30000, 32767                                                   # ref imageop.h:19-20
     ccds = [synth.strip_dn(W, rows, SEED + i) for i in range(N_CCD)]
     kbs = [synth.rrc_coeffs(W, SEED + 100 + i) for i in range(N_CCD)]
-    mx = [(np.arange(W)[None, :] + np.zeros((min(S, rows), 1)) + DX[i]).astype(np.float32) for i in range(N_CCD)]
-    my = [(np.arange(min(S, rows))[:, None] + np.zeros((1, W)) + DY[i]).astype(np.float32) for i in range(N_CCD)]
+    hb = rows if rows <= G else S
+    mx = [(np.arange(W)[None, :] + np.zeros((hb, 1)) + DX[i]).astype(np.float32) for i in range(N_CCD)]
+    my = [(np.arange(hb)[:, None] + np.zeros((1, W)) + DY[i]).astype(np.float32) for i in range(N_CCD)]
     f = FOLD // 2
     rrc = oracle.ref_inplace_rrc if oracle.ref_oip_lib() is not None else oracle.rrc   # the reference's own compiled loop if built
+    buff = np.zeros((S, W), np.uint16) if rows > G else None
     t0 = time.perf_counter()
     parts = []
     for i in range(N_CCD):
         r = rrc(ccds[i], kbs[i])                                          # ref imageop.h:129-138 (1 thread)
-        if i > 0:                                                         # ref stitcher.h:83-139 / imageop.h:258
-            r = cv2.remap(r, mx[i][:rows], my[i][:rows], cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT)
+        if i > 0 and rows <= G:                                           # one cv::remap (the reference throws here, imageop.h:242-244)
+            r = cv2.remap(r, mx[i], my[i], cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT)
+        elif i > 0:                                                       # ref stitcher.h:83-139 / imageop.h:246-272
+            ucut = 0 if DY[i] >= 0 else int(-DY[i]) + 1
+            bcut = int(DY[i]) + 1 if DY[i] >= 0 else 0
+            outp, off, sec, dst = [], 0, 0, None
+            while True:
+                n = min(S, rows - off)
+                if n <= ucut + bcut:
+                    break
+                buff[:n] = r[off:off + n]
+                dst = cv2.remap(buff, mx[i], my[i], cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT)   # imageop.h:258
+                if sec == 0 and ucut > 0:
+                    outp.append(dst[:ucut])
+                outp.append(dst[ucut:n - bcut])
+                off += n - ucut - bcut
+                sec += 1
+            if bcut > 0:
+                outp.append(dst[S - bcut:S])
+            r = np.concatenate(outp)
         lo, hi = (0 if i == 0 else f), (W if i == N_CCD - 1 else W - f)
         parts.append(r[:, lo:hi])
     out = np.concatenate(parts, axis=1)                                   # ref imageop.h:340-355
     dt = time.perf_counter() - t0
+    assert out.shape[0] == rows
     return dt, int(out[::97, ::89].astype(np.int64).sum())
 
 
@@ -141,13 +173,15 @@ def cpu_kind():
 
 
 def run_reference(args):
+    """the reference's own CPU implementation of the path on the box's host cores; one step = REF_ROWS lines of the C4
+    strip (a bounded sample: the whole strip would take ~1 minute per step)"""
     import cv2
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rows = 4096
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_reference_pass(256)
+    rows = REF_ROWS
+    for _ in range(max(0, args.warmup)):
+        cpu_reference_pass(2048)
     ts = []
     for _ in range(args.steps):
         dt, _ = cpu_reference_pass(rows)
@@ -158,24 +192,53 @@ def run_reference(args):
     cores = cv2.getNumThreads()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Gpixel/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64 RRC / f32 bicubic / u16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cpu_sample": f"{rows} lines of the same strip per step"},
+        "config": bench_config(int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": val, "unit": "Gpixel/s", "cores": cores, "kind": cpu_kind(),
-                         "sample": f"{N_CCD}x{W}x{rows} lines: IMO::InplaceRRC (the reference's imageop.h compiled under "
-                                   f"oracle/_ref when present, else its C restatement; 1 thread like the reference) + cv2.remap "
-                                   f"INTER_CUBIC ({cores} OpenCV threads, the reference's own library call) + concat, in memory"},
+                         "sample": f"{rows} lines (of the 1048576) of the same 3 x {W} px strip per step: IMO::InplaceRRC (the "
+                                   f"reference's imageop.h compiled under oracle/_ref when present, else its C restatement; 1 thread "
+                                   f"like the reference) + cv2.remap INTER_CUBIC in 30000-row sections ({cores} OpenCV threads, the "
+                                   f"reference's own library call) + concat, in memory"},
         "e2e": {"value": val, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
+def bench_config(world: int) -> dict:
+    return {"workload": WORKLOAD, "n_ccd": N_CCD, "w": W, "total_rows": TOTAL_ROWS, "rows_per_gpu": TOTAL_ROWS // world,
+            "fold_cols": FOLD, "dX": DX, "dY": DY,
+            "l2": "inputs (51.5 GB / N) and output (50.7 GB / N) per step >> 126 MB L2",
+            "multi_gpu": ("scanline-block shards of ONE strip, halo rows read from peer HBM over NVLink (CUDA IPC), "
+                          "no data-path collective") if world > 1 else "single GPU, whole strip"}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
+def parity_rows(first: int, last: int, total_rows: int):
+    """the bounded set of global output rows a rank checks against the oracle: first / last 16 rows of its block, +-8 rows
+    around every run of rows SectionaryRemap writes (section edges s*(30000-ucut-bcut), ref imageop.h:260-272) for both
+    shifted CCDs, and the last rows of the strip (stale rows of the partial last section)"""
+    import oracle
+    want = set(range(first, min(last, first + 16))) | set(range(max(first, last - 16), last))
+    for i in range(1, N_CCD):
+        pieces, _ = oracle.shift_pieces(total_rows, DY[i])
+        for o0, n, *_ in pieces:
+            for g in range(o0 - 8, o0 + 8):
+                if first <= g < last:
+                    want.add(g)
+    for g in range(total_rows - 16, total_rows):
+        if first <= g < last:
+            want.add(g)
+    return np.array(sorted(want), np.int64)
+
+
 def run_gpu(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
-    from opticalimageprocessor_b200 import build, capi, ops, synth
-    import ctypes as C
+
+    from opticalimageprocessor_b200 import build, capi, ops, sharding, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -188,41 +251,54 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     build.build()
     ctx = ops.Context(local)
+    lib = ctx.lib
     dev = torch.device("cuda", local)
-    total_rows = ROWS * world
-    row0 = ROWS * rank
+    total_rows = args.rows
+    first, last = sharding.shard_range(total_rows, world, rank)
+    rows = last - first
     out_w = ops.pan_out_width(N_CCD, W, FOLD // 2)
+    f = FOLD // 2
 
-    # ---- synthetic shard (host, pinned) -> device.  BE16 = byte order inside the downlink sub-images
-    host_in = []
+    def dev_alloc(nbytes):
+        p = C.c_void_p()
+        capi.check(lib.oip_dev_alloc(ctx.h, nbytes, C.byref(p)))
+        return p.value
+
+    # ---- the rank's block of the synthetic strip, generated on the device (BE16 = byte order inside the downlink
+    #      sub-images); raw cudaMalloc allocations because a CUDA-IPC handle maps a whole allocation
+    d_in = [dev_alloc(rows * W * 2) for _ in range(N_CCD)]
     for i in range(N_CCD):
-        a = synth.strip_dn(W, ROWS, SEED + i, row0=row0).byteswap()
-        t = torch.from_numpy(a).pin_memory()
-        host_in.append(t)
+        capi.check(lib.oip_synth_strip_dn(ctx.h, d_in[i], W, rows, first, W, SEED + i, 1))
+    d_out = torch.empty((rows, out_w), dtype=torch.uint16, device=dev)
+    d_out_ptr = d_out.data_ptr()
+    ctx.sync()
     kb_np = [synth.rrc_coeffs(W, SEED + 100 + i) for i in range(N_CCD)]
     kb_host = [torch.from_numpy(k) for k in kb_np]
-    # raw cudaMalloc allocations (not torch's caching allocator): an IPC handle maps a whole allocation
-    d_in = []
-    for t in host_in:
-        p = C.c_void_p()
-        capi.check(ctx.lib.oip_dev_alloc(ctx.h, t.numel() * 2, C.byref(p)))
-        capi.check(ctx.lib.oip_copy_h2d(ctx.h, p, C.c_void_p(t.data_ptr()), t.numel() * 2))
-        d_in.append(p.value)
-    ctx.sync()
     d_kb = [t.to(dev) for t in kb_host]
-    d_out = torch.empty((ROWS, out_w), dtype=torch.uint16, device=dev)
-    host_out = torch.empty((ROWS, out_w), dtype=torch.uint16).pin_memory()
 
-    # ---- halo rows from the neighbour shards: peer mappings over NVLink (no collective on the data path)
-    desc = ops.make_pan_desc(host_in, ops.FMT_BE16, d_kb, DX, DY, [i > 0 for i in range(N_CCD)], FOLD // 2, d_out,
-                             total_rows=total_rows, row0=row0, n_rows=ROWS,
-                             segs=[[(d_in[i], row0, ROWS, W * 2)] for i in range(N_CCD)])
+    class Shape:  # make_pan_desc only reads .shape of the CCD arguments when explicit segments are given
+        def __init__(self, r, c):
+            self.shape = (r, c)
+
+    class OutPtr:
+        def __init__(self, ptr, pitch):
+            self._p, self._s = ptr, pitch
+
+        def data_ptr(self):
+            return self._p
+
+        def stride(self, k):
+            return self._s
+
+    desc = ops.make_pan_desc([Shape(rows, W)] * N_CCD, ops.FMT_BE16, d_kb, DX, DY, [i > 0 for i in range(N_CCD)], f,
+                             d_out, total_rows=total_rows, row0=first, n_rows=rows,
+                             segs=[[(d_in[i], first, rows, W * 2)] for i in range(N_CCD)])
     opened = []
-    if world > 1:
+    if world > 1:  # halo rows from the neighbour blocks: peer mappings over NVLink (no collective on the data path)
         handles = []
         for i in range(N_CCD):
             hb = C.create_string_buffer(64)
-            capi.check(ctx.lib.oip_ipc_export(ctx.h, C.c_void_p(d_in[i]), hb))
+            capi.check(lib.oip_ipc_export(ctx.h, C.c_void_p(d_in[i]), hb))
             handles.append(hb.raw)
         allh = [None] * world
         dist.all_gather_object(allh, handles)
@@ -231,17 +307,16 @@ def run_gpu(args):
         def peer(r, i):
             if (r, i) not in peer_ptr:
                 p = C.c_void_p()
-                capi.check(ctx.lib.oip_ipc_open(ctx.h, allh[r][i], C.byref(p)))
+                capi.check(lib.oip_ipc_open(ctx.h, allh[r][i], C.byref(p)))
                 peer_ptr[(r, i)] = p.value
                 opened.append(p.value)
             return peer_ptr[(r, i)]
 
-        from opticalimageprocessor_b200 import sharding
         sharding.attach_segments(desc, N_CCD, total_rows, world, rank, d_in, W * 2, peer)
         dist.barrier()
 
     def step():
-        capi.check(ctx.lib.oip_pan_pipeline(ctx.h, C.byref(desc)))
+        capi.check(lib.oip_pan_pipeline(ctx.h, C.byref(desc)))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -249,9 +324,20 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    # ---- warm-up: >= W (>= 3) steps AND >= WARM_SECONDS of GPU work, so the timed steps run at the sustained clocks
+    n_warm = 0
+    t_w0 = time.perf_counter()
+    while True:
         step()
-    capi.check(ctx.lib.oip_pan_check_error(ctx.h))
+        n_warm += 1
+        if n_warm >= max(args.warmup, 3):
+            torch.cuda.synchronize()
+            busy = torch.tensor([time.perf_counter() - t_w0], device=dev)
+            if world > 1:
+                dist.all_reduce(busy, op=dist.ReduceOp.MIN)  # every rank leaves the loop at the same step
+            if busy.item() >= WARM_SECONDS or n_warm >= 4000:
+                break
+    capi.check(lib.oip_pan_check_error(ctx.h))
     sync_all()
     l0 = ctx.launches
     clocks = ClockSampler(local)
@@ -267,74 +353,162 @@ def run_gpu(args):
     launches = ctx.launches - l0
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = float(np.mean([ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]))
-    capi.check(ctx.lib.oip_pan_check_error(ctx.h))
+    capi.check(lib.oip_pan_check_error(ctx.h))
 
-    # ---- e2e: host buffers through oip_pan_pipeline_host (H2D + kernels + D2H), own shard only
-    def e2e_step():
-        ops.pan_pipeline_host(ctx, host_in, kb_host, DX, DY, FOLD // 2, host_out, fmt=ops.FMT_BE16)
+    # ---- parity (outside the timed region): a bounded set of this rank's output rows against the CPU oracle
+    parity_ok, parity_n, parity_bad = True, 0, 0
+    if not args.no_parity:
+        import oracle
+        oracle.build()
+        chk = parity_rows(first, last, total_rows)
+        got = np.empty((chk.size, out_w), np.uint16)
+        row_b = out_w * 2
+        for k, g in enumerate(chk):   # one small D2H per row (a few hundred rows)
+            capi.check(lib.oip_copy_d2h(ctx.h, C.c_void_p(got[k].ctypes.data), C.c_void_p(d_out_ptr + (int(g) - first) * row_b), row_b))
+        ctx.sync()
+        want = oracle.pan_rows(lambda i, a, b: synth.strip_dn(W, b - a, SEED + i, row0=a), N_CCD, W, kb_np, DX, DY, f, total_rows, chk)
+        parity_bad = int((got != want).sum())
+        parity_ok, parity_n = parity_bad == 0, int(chk.size)
+        if not parity_ok:
+            bad_rows = chk[np.flatnonzero((got != want).any(axis=1))]
+            sys.stderr.write(f"rank {rank}: PARITY FAILURE: {parity_bad} px differ in rows {bad_rows[:20].tolist()}\n")
 
-    e2e_ms = None
-    if world == 1:
-        for _ in range(2):
-            e2e_step()
-        torch.cuda.synchronize()
-        n_e2e = max(3, min(args.steps, 7))
+    # ---- e2e: host buffers through oip_pan_pipeline_host (H2D + kernels + D2H), every rank on its own block.  The host
+    #      segments hold the block plus the halo rows (read from the "file" = regenerated, as a host reader would) and,
+    #      where they lie outside, the stale rows of the partial last section
+    e2e_ms, e2e_rows, e2e_in_bytes, e2e_note = 0.0, 0, 0, None
+    if not args.no_e2e:
+        import psutil
+        need_full = N_CCD * W * 2 * rows + out_w * 2 * rows
+        avail = psutil.virtual_memory().available // world
+        e2e_rows = rows
+        while e2e_rows > 4096 and (N_CCD * W * 2 + out_w * 2) * e2e_rows * 1.25 + (8 << 30) > avail:
+            e2e_rows //= 2
+        if e2e_rows != rows:
+            e2e_note = f"host memory ({avail >> 30} GiB available per rank) holds {e2e_rows} of the block's {rows} lines"
+        hd = ops.make_pan_desc([Shape(e2e_rows, W)] * N_CCD, ops.FMT_BE16, kb_host, DX, DY, [i > 0 for i in range(N_CCD)], f,
+                               OutPtr(0, out_w), total_rows=total_rows, row0=first, n_rows=e2e_rows,
+                               segs=[[(0, first, e2e_rows, W * 2)] for _ in range(N_CCD)])  # host segments filled in below
+        pinned = []
+
+        def pin(nbytes):
+            p = C.c_void_p()
+            capi.check(lib.oip_host_alloc_pinned(nbytes, C.byref(p)))
+            pinned.append(p.value)
+            return p.value
+
+        chunk = 8192
+        d_tmp = dev_alloc(chunk * W * 2)
+        for i in range(N_CCD):
+            (nf, nl), (sf, sl) = sharding.rows_needed(hd, i)
+            segs = [(min(nf, first), max(nl, first + e2e_rows))]
+            if sl > sf and not (segs[0][0] <= sf and sl <= segs[0][1]):
+                segs.append((sf, sl))
+            c = hd.ccd[i]
+            c.n_seg = len(segs)
+            for q, (a, b) in enumerate(segs):
+                hp = pin((b - a) * W * 2)
+                e2e_in_bytes += (b - a) * W * 2
+                for r in range(a, b, chunk):   # the same synthetic rows, generated on the device and copied out
+                    n = min(chunk, b - r)
+                    capi.check(lib.oip_synth_strip_dn(ctx.h, d_tmp, W, n, r, W, SEED + i, 1))
+                    capi.check(lib.oip_copy_d2h(ctx.h, C.c_void_p(hp + (r - a) * W * 2), C.c_void_p(d_tmp), n * W * 2))
+                    ctx.sync()
+                c.seg[q] = capi.RowSeg(hp, a, b - a, W * 2)
+        capi.check(lib.oip_dev_free(ctx.h, C.c_void_p(d_tmp)))
+        h_out = pin(e2e_rows * out_w * 2)
+        hd.d_out = h_out
+
+        def e2e_step():
+            capi.check(lib.oip_pan_pipeline_host(ctx.h, C.byref(hd)))  # returns after the output landed in host memory
+
+        e2e_step()
+        sync_all()
         ts = []
-        for _ in range(n_e2e):
+        for _ in range(3):
+            if world > 1:
+                dist.barrier()
             t0 = time.perf_counter()
-            e2e_step()  # returns after the output block landed in host memory
+            e2e_step()
             torch.cuda.synchronize()
             ts.append((time.perf_counter() - t0) * 1e3)
         e2e_ms = float(np.median(ts))  # the host link is shared with whatever else the box does: median, not mean
-        # the device-resident path and the host path must agree
-        if not torch.equal(host_out.view(torch.int16), d_out.cpu().view(torch.int16)):
-            raise SystemExit("e2e output differs from the device-resident output")
+        # the host path and the device-resident path must agree: the host result goes back up in chunks and is compared there
+        cmp_rows = 4096
+        d_cmp = torch.empty((cmp_rows, out_w), dtype=torch.int16, device=dev)
+        same = True
+        for r in range(0, e2e_rows, cmp_rows):
+            n = min(cmp_rows, e2e_rows - r)
+            capi.check(lib.oip_copy_h2d(ctx.h, C.c_void_p(d_cmp.data_ptr()), C.c_void_p(h_out + r * out_w * 2), n * out_w * 2))
+            ctx.sync()
+            same = same and bool(torch.equal(d_cmp[:n], d_out[r:r + n].view(torch.int16)))
+        for p_ in pinned:
+            lib.oip_host_free_pinned(C.c_void_p(p_))
+        if not same:
+            parity_ok = False
+            sys.stderr.write(f"rank {rank}: e2e output differs from the device-resident output\n")
 
-    t = torch.tensor([total_ms, kernel_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, kernel_ms, e2e_ms, 0.0 if parity_ok else 1.0, float(clk["sm_mhz"] or 0)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([parity_n, parity_bad, e2e_rows, e2e_in_bytes], dtype=torch.int64, device=dev)
+    tmin = t.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kernel_ms, e2e_max = t.tolist()
-    px_rank = N_CCD * W * ROWS
-    px_all = px_rank * world
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(cnt)
+    total_ms, kernel_ms, e2e_max, parity_flag, _ = t.tolist()
+    parity_n_all, parity_bad_all, e2e_rows_all, e2e_in_all = cnt.tolist()
+    px_all = N_CCD * W * total_rows
     value = px_all * args.steps / (total_ms * 1e-3) / 1e9
     peak, peak_src = hbm_peak()
     bpp = algorithmic_bytes_per_px()
     # the dominant kernel (pan_fast_kernel) covers fast_frac of the output; the generic kernel runs next to it on
     # a side stream, so the step time measured on the launching stream bounds the fast kernel's duration from above
     st = (C.c_int64 * 4)()
-    capi.check(ctx.lib.oip_pan_plan_coverage(C.byref(desc), 1, 128, None, st))
+    capi.check(lib.oip_pan_plan_coverage(C.byref(desc), 1, 128, None, st))
     fast_frac = st[1] / max(1, st[0] + st[1])
+    px_rank = N_CCD * W * rows
     achieved = px_rank * fast_frac * bpp / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "pan_kernel_traffic.json")) as f:
-            tj = json.load(f)
-            if tj.get("workload") == WORKLOAD:
+        with open(os.path.join(ROOT, "profiles", "pan_kernel_traffic.json")) as fjs:
+            tj = json.load(fjs)
+            if world == 1 and tj.get("rows") == total_rows:
                 traffic = tj.get("dram_bytes_per_launch")
     except Exception:
         pass
 
     if rank == 0:
+        clk["sm_mhz_min_over_ranks"] = tmin.tolist()[4]
         line = {
             "metric": METRIC, "value": value, "unit": "Gpixel/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64 RRC / f32 bicubic / u16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_ccd": N_CCD, "w": W, "rows_per_gpu": ROWS, "total_rows": total_rows,
-                       "fold_cols": FOLD, "dX": DX, "dY": DY, "l2": "inputs (1.6 GB) and output (1.6 GB) per step >> 126 MB L2",
-                       "multi_gpu": "scanline-block shards, halo rows read from peer HBM over NVLink (CUDA IPC)" if world > 1 else "single GPU"},
+            "warmup": n_warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 RRC / f32 bicubic / u16", "data": "synthetic",
+            "config": bench_config(world),
             "gpu_launches": int(launches),
             "clocks": clk,
+            "warmup_policy": f">= {WARM_SECONDS} s of GPU work before the timed steps (sustained clocks), {n_warm} steps",
+            "parity_ok": bool(parity_flag == 0.0) if not args.no_parity or not args.no_e2e else None,
+            "parity": {"rows_checked": int(parity_n_all), "px_checked": int(parity_n_all) * out_w, "px_different": int(parity_bad_all),
+                       "against": "oracle.pan_rows (CPU restatement, pinned to the reference's compiled PreStitch); every rank: first/last "
+                                  "16 rows of its block, +-8 rows around every section edge of both shifted CCDs, the stale bottom rows; "
+                                  "plus e2e output == device-resident output"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "oip::panfast::pan_fast_kernel",
                          "algorithmic_bytes_per_px": bpp, "kernel_ms": kernel_ms, "px_share_of_step": fast_frac,
                          "note": "kernel_ms = CUDA-event time of one step on the launching stream (fast kernel + the "
-                                 "generic-tile kernel joined from a side stream): an upper bound of the fast kernel's duration"},
+                                 "generic-tile kernel joined from a side stream), max over ranks: an upper bound of the fast "
+                                 "kernel's duration"},
         }
+        if not args.no_e2e:
+            px_e2e = N_CCD * W * e2e_rows_all
+            line["e2e"] = {"value": px_e2e / (e2e_max * 1e-3) / 1e9, "unit": "Gpixel/s",
+                           "h2d_bytes_per_step": int(e2e_in_all + world * N_CCD * W * 16),
+                           "d2h_bytes_per_step": int(e2e_rows_all * out_w * 2), "ms_per_step": e2e_max,
+                           "rows": int(e2e_rows_all), "note": e2e_note,
+                           "api": "oip_pan_pipeline_host (C ABI, pinned host buffers), one call per rank on its own block"}
+        else:
+            line["e2e"] = {"value": None, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "--no-e2e"}
         if world == 1:
-            line["e2e"] = {"value": px_rank / (e2e_max * 1e-3) / 1e9, "unit": "Gpixel/s",
-                           "h2d_bytes_per_step": int(sum(t.numel() * 2 for t in host_in) + sum(k.numel() * 8 for k in kb_host)),
-                           "d2h_bytes_per_step": int(host_out.numel() * 2), "ms_per_step": e2e_max,
-                           "api": "oip_pan_pipeline_host (C ABI, pinned host buffers)"}
             # bounded CPU sample of the same workload (baseline, not the target)
             try:
                 import cv2
@@ -347,18 +521,17 @@ def run_gpu(args):
                                                   f"cv2.remap cubic ({cv2.getNumThreads()} threads) + concat, in memory"}
             except Exception as e:  # the CPU leg must never take the GPU number down
                 line["cpu_baseline"] = {"value": None, "unit": "Gpixel/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-        else:
-            line["e2e"] = {"value": None, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                           "note": "measured at N=1 only"}
         emit(line)
     for p in opened:
-        ctx.lib.oip_ipc_close(ctx.h, C.c_void_p(p))
+        lib.oip_ipc_close(ctx.h, C.c_void_p(p))
     if world > 1:
         dist.barrier()
     for p in d_in:
-        ctx.lib.oip_dev_free(ctx.h, C.c_void_p(p))
+        lib.oip_dev_free(ctx.h, C.c_void_p(p))
     if world > 1:
         dist.destroy_process_group()
+    if not parity_flag == 0.0:
+        raise SystemExit("parity check failed")
 
 
 _REAL_STDOUT = None
@@ -385,6 +558,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=TOTAL_ROWS, help="strip length in lines (default: the C4 strip; smaller = smoke runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -393,7 +569,8 @@ def main():
             # convenience: re-launch under torchrun
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__), "--gpus", str(args.gpus),
-                   "--steps", str(args.steps), "--warmup", str(args.warmup)]
+                   "--steps", str(args.steps), "--warmup", str(args.warmup), "--rows", str(args.rows)] + \
+                  (["--no-e2e"] if args.no_e2e else []) + (["--no-parity"] if args.no_parity else [])
             raise SystemExit(subprocess.call(cmd))
         run_gpu(args)
 

@@ -273,7 +273,7 @@ int oip_unpack_lines(oip_ctx *ctx, const void *d_in, int fmt, int w, int64_t row
 /* ---- inter-CMOS offset estimation (the caller that produces dX, dY) ---------- */
 /* replaces cv::phaseCorrelate(src1, src2, noArray(), &response) as called at ref stitcher.h:180 on two u16 slices
  * (converted to float like the Mat1w -> Mat1f assignment at :175-176).  result = {dx, dy, response}.
- * Floating point: agrees with OpenCV within ~1e-3 px (different DFT), not bit for bit.  DFT sizes must be even. */
+ * Floating point: agrees with OpenCV within ~1e-3 px (different DFT), not bit for bit.  Even and odd optimal DFT sizes. */
 int oip_phase_correlate_u16(oip_ctx *ctx, const uint16_t *d_a, int64_t pitch_a_px, const uint16_t *d_b, int64_t pitch_b_px,
                             int rows, int cols, double result[3]);
 
@@ -323,6 +323,14 @@ typedef struct oip_ibc_shift {   /* InterBandShift, ref preproc.h:23-28 */
 int oip_inter_band_correlation(oip_ctx *ctx, const uint16_t *d_pan, int w, int64_t lines_pan, int64_t pan_pitch_px,
                                const uint16_t *d_mss, int64_t lines_mss, int64_t mss_pitch_px, const oip_ibc_config *cfg,
                                oip_ibc_shift *shifts, double cX[8], double cY[12]);
+
+/* ---- bench / test input (NOT a replaced reference function) --------------------------------- */
+/* The reference ships no sample data; SURVEY 8(d) defines the synthetic strip DN(x,y) = 64 + ((37x mod 1500 + (y/8) mod 1200 +
+ * (splitmix64(seed ^ (y*w + x)) & 0xFF)) mod 3968).  This fills rows [row0, row0+rows) of that strip on the device
+ * (bit-identical to opticalimageprocessor_b200/synth.py:strip_dn), little- or big-endian samples: how bench.py makes its
+ * 51.5 GB C4 input without a host generator. */
+int oip_synth_strip_dn(oip_ctx *ctx, uint16_t *d_out, int w, int64_t rows, int64_t row0, int64_t pitch_px,
+                       uint64_t seed, int big_endian);
 
 /* ---- whole-stage host-buffer entry points (what the CLI and bench.py "e2e" call) ------------ */
 /* host in / host out, copies on side streams overlapped with the kernels in row blocks */

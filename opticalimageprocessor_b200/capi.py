@@ -113,6 +113,7 @@ SYMBOLS = {
     "oip_stitch_concat_c4": (_I, [_VP, C.POINTER(_VP), _I, _I, _I64, _I, C.POINTER(_I), _VP]),
     "oip_unpack_lines": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP]),
     "oip_pan_pipeline_host": (_I, [_VP, C.POINTER(PanDesc)]),
+    "oip_synth_strip_dn": (_I, [_VP, _VP, _I, _I64, _I64, _I64, C.c_uint64, _I]),
     "oip_phase_correlate_u16": (_I, [_VP, _VP, _I64, _VP, _I64, _I, _I, C.POINTER(_D)]),
     "oip_inter_band_correlation": (_I, [_VP, _VP, _I, _I64, _I64, _VP, _I64, _I64, C.POINTER(IbcConfig), C.POINTER(IbcShift),
                                         C.POINTER(_D), C.POINTER(_D)]),
@@ -131,7 +132,7 @@ def load() -> C.CDLL:
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -m opticalimageprocessor_b200.build` "
                 "(there is no CPU fallback)")
-        L = C.CDLL(os.environ.get("OIP_B200_LIB", LIB_PATH))  # override: kernel experiments (tools/build_variant.py)
+        L = C.CDLL(os.environ.get("OIP_B200_LIB", LIB_PATH))  # override: kernel experiments (tools/probes/build_variant.py)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError if the symbol is not exported
             fn.restype = res

@@ -107,8 +107,11 @@ void oip_ctx_destroy(oip_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     oip::host_pipe_destroy(ctx);
     oip::stt::destroy(ctx);
-    for (oip_pan_plan &pl : ctx->pan_plans)
+    for (oip_pan_plan &pl : ctx->pan_plans) {
         if (pl.d_plan) cudaFree(pl.d_plan);
+        if (pl.h_stage) cudaFreeHost(pl.h_stage);
+        if (pl.done) cudaEventDestroy(pl.done);
+    }
     if (ctx->d_mss_plan) cudaFree(ctx->d_mss_plan);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

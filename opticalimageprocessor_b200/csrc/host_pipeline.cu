@@ -105,7 +105,9 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
     if (!h->d_out && h->n_rows > 0) return fail(OIP_E_INVALID, "output buffer is null");
     for (int i = 0; i < h->n_ccd; ++i) {
         if (h->ccd[i].fmt == OIP_FMT_BE16_TILES) return fail(OIP_E_UNSUPPORTED, "host pipeline takes line formats only");
-        if (h->ccd[i].n_seg != 1 || !h->ccd[i].seg[0].base) return fail(OIP_E_INVALID, "host pipeline needs exactly one host segment per CCD");
+        if (h->ccd[i].n_seg < 1 || h->ccd[i].n_seg > OIP_MAX_SEG) return fail(OIP_E_INVALID, "ccd %d: n_seg=%d", i, h->ccd[i].n_seg);
+        for (int s = 0; s < h->ccd[i].n_seg; ++s)
+            if (!h->ccd[i].seg[s].base) return fail(OIP_E_INVALID, "ccd %d: host segment %d is null", i, s);
     }
     if (h->n_rows <= 0) return OIP_OK;
     HostPipe *hp = nullptr;
@@ -156,24 +158,35 @@ extern "C" int oip_pan_pipeline_host(oip_ctx *ctx, const oip_pan_desc *h)
             int n_rg = 0;
             rc = oip_pan_row_ranges(&d, i, rg, OIP_MAX_SEG, &n_rg);
             if (rc) return rc;
-            const oip_row_seg &hs = src.seg[0];
+            // a scanline-block shard hands in up to OIP_MAX_SEG HOST segments (its own block with the halo rows read from
+            // the file, the stale rows of a partial last section): every needed range is cut against each of them
             const int64_t rb = row_bytes(src.fmt, h->w);
             const int64_t pitch_d = (rb + 15) / 16 * 16;
+            struct Piece { int64_t a, n; int seg; };
+            Piece pieces[OIP_MAX_SEG * OIP_MAX_SEG];
+            int n_pc = 0;
             int64_t n_all = 0;
-            for (int k = 0; k < n_rg; ++k) {
-                rg[2 * k] = std::max(rg[2 * k], hs.row0);
-                rg[2 * k + 1] = std::min(rg[2 * k + 1], hs.row0 + hs.n_rows);
-                n_all += std::max<int64_t>(0, rg[2 * k + 1] - rg[2 * k]);
-            }
+            for (int k = 0; k < n_rg; ++k)
+                for (int q = 0; q < src.n_seg; ++q) {
+                    const oip_row_seg &hs = src.seg[q];
+                    const int64_t a = std::max(rg[2 * k], hs.row0), b = std::min(rg[2 * k + 1], hs.row0 + hs.n_rows);
+                    if (b <= a) continue;
+                    bool dup = false; // host segments may overlap (halo rows of a block are also inside the stale range)
+                    for (int e = 0; e < n_pc; ++e) dup = dup || (a >= pieces[e].a && b <= pieces[e].a + pieces[e].n);
+                    if (dup) continue;
+                    pieces[n_pc++] = {a, b - a, q};
+                    n_all += b - a;
+                }
+            if (n_pc > OIP_MAX_SEG) return fail(OIP_E_INVALID, "ccd %d: a row block needs %d host pieces (max %d)", i, n_pc, OIP_MAX_SEG);
             rc = hp_reserve(&S.d_in[i], &S.in_cap[i], (size_t)(std::max<int64_t>(HP_BLOCK_ROWS + 256, n_all) * pitch_d));
             if (rc) return rc;
             uint8_t *dst = (uint8_t *)S.d_in[i];
             oip_ccd_src &o = d.ccd[i];
             o.d_kb = d_kb[i];
             o.n_seg = 0;
-            for (int k = 0; k < n_rg; ++k) {
-                const int64_t a = rg[2 * k], n = rg[2 * k + 1] - a;
-                if (n <= 0) continue;
+            for (int e = 0; e < n_pc; ++e) {
+                const oip_row_seg &hs = src.seg[pieces[e].seg];
+                const int64_t a = pieces[e].a, n = pieces[e].n;
                 OIP_CUDA(copy_rows(dst, (size_t)pitch_d, (const uint8_t *)hs.base + (a - hs.row0) * hs.pitch_bytes, (size_t)hs.pitch_bytes,
                                    (size_t)rb, (size_t)n, cudaMemcpyHostToDevice, hp->h2d));
                 o.seg[o.n_seg++] = {dst, a, n, pitch_d};

@@ -18,6 +18,9 @@ struct oip_pan_plan {
     int64_t tiles = 0, fast_ctas = 0;
     size_t fast_off = 0;
     uint64_t last_use = 0;
+    void *h_stage = nullptr;    // pinned staging of the plan upload (a pageable source would tie the host to the stream)
+    size_t h_cap = 0;
+    cudaEvent_t done = nullptr; // recorded after the last launch that read d_plan: a slot is recycled behind it
 };
 
 struct oip_ctx {
@@ -207,7 +210,7 @@ __device__ __forceinline__ uint32_t crc16_byte(uint32_t crc, uint32_t byte)
 // (uint16_t)(k*s + b) exactly as the reference's x86 build evaluates it (ref imageop.h:134;
 // cvtsi2sd, mulsd, addsd, cvttsd2si(32-bit), low 16 bits).  No FMA contraction.
 // The conversion pipe (I2F/F2I .F64) issues at 16 lanes/clk/SM on B200 against 64 for DADD/DMUL
-// (tools/pipe_rates.cu), so both conversions are done with exact magic-number adds instead:
+// (tools/probes/pipe_rates.cu), so both conversions are done with exact magic-number adds instead:
 //   u16 -> f64 : (2^52 | s) - 2^52                      (exact, one DADD)
 //   trunc      : low word of RZ(v + 2^52) for 0 <= v < 2^31 (exact, one DADD.RZ); anything else
 //                takes the generic path (negative, >= 2^31, NaN: rare, input-contract territory)

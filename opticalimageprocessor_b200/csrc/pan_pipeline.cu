@@ -1051,24 +1051,29 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         }
         const size_t fast_off = (1024 + tiles.size() * sizeof(pan::Tile) + 63) / 64 * 64;
         const size_t bytes = fast_off + ftiles.size() * sizeof(panfast::FastTile) + 64;
-        if (pl->d_plan) OIP_CUDA(cudaStreamSynchronize(ctx->stream)); // a kernel may still read the slot's old plan
-        if (ctx->aux_stream && pl->d_plan) OIP_CUDA(cudaStreamSynchronize(ctx->aux_stream));
+        // a kernel may still read the slot's old plan: wait for the last launch that used it (the least recently used
+        // slot of a long host-buffer run finished long ago, so this does not drain the pipeline)
+        if (pl->done) OIP_CUDA(cudaEventSynchronize(pl->done));
+        else OIP_CUDA(cudaEventCreateWithFlags(&pl->done, cudaEventDisableTiming));
         if (bytes > pl->cap) {
             if (pl->d_plan) { OIP_CUDA(cudaFree(pl->d_plan)); pl->d_plan = nullptr; pl->cap = 0; }
             OIP_CUDA(cudaMalloc(&pl->d_plan, bytes + bytes / 4));
             pl->cap = bytes + bytes / 4;
         }
-        // pageable sources: cudaMemcpyAsync stages them before returning
-        float hdr[256] = {};
-        memcpy(hdr, pan::g_tab_host, 512);
-        hdr[128] = hdr[129] = -0.0f; // run-time (-0.0,-0.0) addend of the packed products, see mul2()
-        OIP_CUDA(cudaMemcpyAsync(pl->d_plan, hdr, 1024, cudaMemcpyHostToDevice, ctx->stream));
-        if (!tiles.empty())
-            OIP_CUDA(cudaMemcpyAsync((uint8_t *)pl->d_plan + 1024, tiles.data(), tiles.size() * sizeof(pan::Tile),
-                                     cudaMemcpyHostToDevice, ctx->stream));
-        if (!ftiles.empty())
-            OIP_CUDA(cudaMemcpyAsync((uint8_t *)pl->d_plan + fast_off, ftiles.data(), ftiles.size() * sizeof(panfast::FastTile),
-                                     cudaMemcpyHostToDevice, ctx->stream));
+        if (bytes > pl->h_cap) {
+            if (pl->h_stage) { OIP_CUDA(cudaFreeHost(pl->h_stage)); pl->h_stage = nullptr; pl->h_cap = 0; }
+            OIP_CUDA(cudaHostAlloc(&pl->h_stage, bytes + bytes / 4, cudaHostAllocDefault));
+            pl->h_cap = bytes + bytes / 4;
+        }
+        // header (weight table + the run-time (-0.0,-0.0) addend of the packed products, see mul2()), generic tiles,
+        // fast warp-tiles: ONE copy from pinned staging
+        uint8_t *hs = (uint8_t *)pl->h_stage;
+        memset(hs, 0, 1024);
+        memcpy(hs, pan::g_tab_host, 512);
+        reinterpret_cast<float *>(hs)[128] = reinterpret_cast<float *>(hs)[129] = -0.0f;
+        if (!tiles.empty()) memcpy(hs + 1024, tiles.data(), tiles.size() * sizeof(pan::Tile));
+        if (!ftiles.empty()) memcpy(hs + fast_off, ftiles.data(), ftiles.size() * sizeof(panfast::FastTile));
+        OIP_CUDA(cudaMemcpyAsync(pl->d_plan, hs, fast_off + ftiles.size() * sizeof(panfast::FastTile), cudaMemcpyHostToDevice, ctx->stream));
         pl->key.assign(kb, kb + sizeof key);
         pl->tiles = (int64_t)tiles.size();
         pl->fast_ctas = (int64_t)(ftiles.size() / panfast::WARPS);
@@ -1152,6 +1157,7 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         OIP_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
         OIP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
+    if (pl->done) OIP_CUDA(cudaEventRecord(pl->done, ctx->stream));
     return OIP_OK;
 }
 

@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(256) peak_kernel(const float *__restrict__ c, 
     const int64_t n = (int64_t)M * N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int y = (int)(i / N), x = (int)(i - (int64_t)y * N);
-        const int ys = y + M / 2 >= M ? y - M / 2 : y + M / 2, xs = x + N / 2 >= N ? x - N / 2 : x + N / 2;
+        // OpenCV's fftShift = circular shift by (M/2, N/2) for even AND odd sizes (phasecorr.cpp: q0 lands at (xMid, yMid))
+        const int ys = y + M / 2 >= M ? y + M / 2 - M : y + M / 2, xs = x + N / 2 >= N ? x + N / 2 - N : x + N / 2;
         const Peak p{c[i], (unsigned long long)ys * N + xs};
         if (better(p, best)) best = p;
     }
@@ -148,7 +149,7 @@ __global__ void centroid_kernel(const float *__restrict__ c, int M, int N, const
     double sx = 0.0, sy = 0.0, sum = 0.0;
     for (int ys = y0; ys <= y1; ++ys)
         for (int xs = x0; xs <= x1; ++xs) {
-            const int y = ys >= M / 2 ? ys - M / 2 : ys + M / 2, x = xs >= N / 2 ? xs - N / 2 : xs + N / 2; // undo the swap
+            const int y = ys >= M / 2 ? ys - M / 2 : ys + M - M / 2, x = xs >= N / 2 ? xs - N / 2 : xs + N - N / 2; // undo the shift
             const double v = (double)c[(int64_t)y * N + x];
             sx += xs * v;
             sy += ys * v;
@@ -201,8 +202,6 @@ template <typename Pack>
 static int correlate_with(oip_ctx *ctx, int rows, int cols, double *d_out, Pack pack)
 {
     const int M = optimal_dft_size(rows), N = optimal_dft_size(cols);
-    if ((M | N) & 1)
-        return fail(OIP_E_UNSUPPORTED, "phase correlation: odd DFT size %d x %d (OpenCV's asymmetric quadrant swap is not implemented)", M, N);
     State *st;
     int rc = plans(ctx, M, N, &st);
     if (rc) return rc;
@@ -324,7 +323,7 @@ extern "C" int oip_stt_parameters(oip_ctx *ctx, const uint16_t *d_pan1, const ui
     if (sums) sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
     if (!d_pan1 || !d_pan2 || !cfg || !sections_out) return fail(OIP_E_INVALID, "oip_stt_parameters: null pointer");
     const int ov = cfg->overlap_cols, ec = cfg->edge_cols, ns = cfg->sections, lps = cfg->lines_per_section;
-    if (w < 1 || pitch_px < w || ov < 1 || ov > w || ec < 0 || 2 * ec >= ov - 0 || ns < 1 || lps < 1 || total_lines < (int64_t)ns * lps)
+    if (w < 1 || pitch_px < w || ov < 1 || ov > w || ec < 0 || ec >= ov || ns < 1 || lps < 1 || total_lines < (int64_t)ns * lps)
         return fail(OIP_E_INVALID, "oip_stt_parameters: bad geometry (w=%d overlap=%d edge=%d sections=%d x %d lines of %lld)", w, ov, ec,
                     ns, lps, (long long)total_lines);
     const int64_t gap = (total_lines - (int64_t)ns * lps) / (ns + 1); // ref stitcher.h:151

@@ -73,7 +73,7 @@ __device__ __forceinline__ f2 shfl_down1(f2 v)
 }
 
 // On B200 the integer/logic instructions (PRMT, LOP3, MOV, IADD3 ...) take their cycles from the same datapath
-// as the FP32 instructions (tools/mix_rates.cu: FFMA2 + LOP3 times add up, FFMA2 + DADD overlap), and the FP32
+// as the FP32 instructions (tools/probes/mix_rates.cu: FFMA2 + LOP3 times add up, FFMA2 + DADD overlap), and the FP32
 // datapath is what bounds this kernel.  So a 32-bit word of two samples is turned into two exact doubles on the
 // conversion and FP64 pipes alone: I2F.F64.U32, then hi = RZ(x*2^-16 + 2^52) - 2^52, lo = x - 65536*hi.
 struct D2 { double lo, hi; };

@@ -333,8 +333,24 @@ def calc_stt_parameters(ctx: Context, pan1: torch.Tensor, pan2: torch.Tensor, ov
     rows = [(s.line_offset, s.dx, s.dy, s.response, s.valid) for s in secs]
     tot = [sums[0], sums[1], sums[2], sums[3]]
     if group is not None or (total_lines is not None and torch.distributed.is_available() and torch.distributed.is_initialized()):
+        from . import sharding
+        dist = torch.distributed
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        # sections that straddle two scanline blocks: their rows of the two overlap slices go to ONE rank (a few MB,
+        # point to point), which correlates them like any other section (ref stitcher.h:166-199 skips none)
+        mine = torch.tensor([row0, row0 + rows_here], dtype=torch.int64, device=pan1.device)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine, group=group)
+        plan = sharding.stt_section_plan(total, sections, lines_per_section, [tuple(t.tolist()) for t in allr])
+        for idx, a, b in sharding.stt_gather_straddling(pan1, pan2, row0, rank, plan, (w - overlap_cols, w - edge_cols),
+                                                        (edge_cols, overlap_cols), group):
+            dx, dy, rs = phase_correlate(ctx, a, b)
+            ok = rs >= threshold and (max_delta_y <= 0.0 or abs(dy) <= max_delta_y)          # ref stitcher.h:181
+            rows[idx] = (rows[idx][0], dx, dy, rs, int(ok))
+            if ok:
+                tot = [tot[0] + dx, tot[1] + dy, tot[2] + rs, tot[3] + 1.0]
         t = torch.tensor(tot, dtype=torch.float64, device=pan1.device)
-        torch.distributed.all_reduce(t, group=group)
+        dist.all_reduce(t, group=group)
         tot = t.tolist()
     mean = None if tot[3] == 0 else (tot[0] / tot[3], tot[1] / tot[3], tot[2] / tot[3])
     return rows, mean

@@ -91,8 +91,8 @@ def stt_section_offsets(total_lines: int, sections: int, lines_per_section: int)
 
 
 def stt_section_owner(total_lines: int, sections: int, lines_per_section: int, world: int) -> List[int]:
-    """rank whose scanline block holds a section entirely, or -1 when it straddles two blocks (then the caller must hand
-    those rows to one rank -- oip_stt_parameters marks such a section valid = -1 instead of guessing)"""
+    """rank whose scanline block holds a section entirely, or -1 when it straddles two blocks (oip_stt_parameters marks
+    such a section valid = -1; stt_gather_straddling hands its rows to one rank)"""
     owners = []
     for off in stt_section_offsets(total_lines, sections, lines_per_section):
         own = -1
@@ -102,6 +102,61 @@ def stt_section_owner(total_lines: int, sections: int, lines_per_section: int, w
                 own = r
         owners.append(own)
     return owners
+
+
+def stt_section_plan(total_lines: int, sections: int, lines_per_section: int, ranges: Sequence[Tuple[int, int]]):
+    """for every section of the offset estimate: (first line, owner rank, [(rank, first, last) pieces in row order]).
+    ranges[r] = [first, last) lines held by rank r.  A section inside one block has one piece; a section that straddles
+    blocks is owned by the rank that holds its first line and the other ranks send their rows of the two overlap
+    slices (lines x (overlap - edge) px x 2 strips: a few MB) -- ref stitcher.h:166-199 correlates every section."""
+    plan = []
+    for off in stt_section_offsets(total_lines, sections, lines_per_section):
+        pieces = []
+        for r, (lo, hi) in enumerate(ranges):
+            a, b = max(lo, off), min(hi, off + lines_per_section)
+            if b > a:
+                pieces.append((r, a, b))
+        pieces.sort(key=lambda p: p[1])
+        covered = sum(b - a for _, a, b in pieces)
+        if covered != lines_per_section or not pieces:
+            raise ValueError(f"section at line {off}: the shards hold {covered} of its {lines_per_section} lines")
+        plan.append((off, pieces[0][0], pieces))
+    return plan
+
+
+def stt_gather_straddling(pan1, pan2, row0: int, rank: int, plan, cols1: Tuple[int, int], cols2: Tuple[int, int], group=None):
+    """exchange step of the sharded offset estimate: for every section that straddles scanline blocks, the non-owner
+    ranks send their rows of pan1[:, cols1] / pan2[:, cols2] to the owner (point-to-point, torch.distributed: NCCL over
+    NVLink on a GPU box, gloo in the CPU tests).  Returns [(section index, a, b)] on the owner: the assembled
+    lines_per_section x cols slices, ready for the phase correlation."""
+    import torch
+    import torch.distributed as dist
+    out = []
+    n1, n2 = cols1[1] - cols1[0], cols2[1] - cols2[0]
+    assert n1 == n2
+    for idx, (off, owner, pieces) in enumerate(plan):
+        if len(pieces) == 1:
+            continue
+        mine = [p for p in pieces if p[0] == rank]
+        if rank == owner:
+            lps = pieces[-1][2] - off
+            buf = torch.empty((2, lps, n1), dtype=torch.int16, device=pan1.device)
+            for r, a, b in pieces:
+                dst = buf[:, a - off:b - off]
+                if r == rank:
+                    dst[0].copy_(pan1[a - row0:b - row0, cols1[0]:cols1[1]].view(torch.int16))
+                    dst[1].copy_(pan2[a - row0:b - row0, cols2[0]:cols2[1]].view(torch.int16))
+                else:
+                    tmp = torch.empty((2, b - a, n1), dtype=torch.int16, device=pan1.device)
+                    dist.recv(tmp, src=r if group is None else dist.get_global_rank(group, r), group=group)
+                    dst.copy_(tmp)
+            out.append((idx, buf[0].view(torch.uint16), buf[1].view(torch.uint16)))
+        elif mine:
+            _, a, b = mine[0]
+            tmp = torch.stack([pan1[a - row0:b - row0, cols1[0]:cols1[1]].view(torch.int16),
+                               pan2[a - row0:b - row0, cols2[0]:cols2[1]].view(torch.int16)]).contiguous()
+            dist.send(tmp, dst=owner if group is None else dist.get_global_rank(group, owner), group=group)
+    return out
 
 
 def stt_combine(sums: Sequence[float]):

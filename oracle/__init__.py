@@ -311,8 +311,7 @@ def phase_correlate(a: np.ndarray, b: np.ndarray):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     M, N = optimal_dft_size(a.shape[0]), optimal_dft_size(a.shape[1])
-    if M % 2 or N % 2:
-        raise NotImplementedError("odd DFT sizes use OpenCV's asymmetric quadrant swap")
+    # odd sizes: OpenCV's fftShift is the circular shift by (M // 2, N // 2) for every parity, which np.roll does below
     pa = np.zeros((M, N)); pa[: a.shape[0], : a.shape[1]] = a
     pb = np.zeros((M, N)); pb[: b.shape[0], : b.shape[1]] = b
     P = np.fft.rfft2(pa) * np.conj(np.fft.rfft2(pb))
@@ -416,3 +415,90 @@ def inter_band_correlation(pan: np.ndarray, bands, slices=10, sections=5, thresh
         cX.append(np.polyfit(x, np.array([s[0] for s in good]), 1)[::-1].tolist())      # :533 ascending coefficients
         cY.append(np.polyfit(x, np.array([s[1] for s in good]), 2)[::-1].tolist())      # :534
     return shifts, cX, cY
+
+
+# ---------------------------------------------------------------------------------------------
+# Row-window form of the fused PAN path: selected OUTPUT rows of a strip that is too long to run through
+# oipo_pan_pipeline as a whole (bench.py's in-run parity check on the 1 M-line strip, BASELINE configs[3]).
+# The sections of SectionaryRemap are written out once more here (ref imageop.h:246-272, stitcher.h:83-139, :122-123);
+# tests/test_oracle_cpu.py checks this form against the literal whole-strip restatement (oipo_pan_pipeline), which
+# is itself pinned against the reference's own compiled PreStitch (tests/golden/ref_prestitch.npz).
+# ---------------------------------------------------------------------------------------------
+def shift_pieces(total_rows: int, dY: float, section_rows: int = 30000, row_guard: int = 32767):
+    """the runs of output rows SectionaryRemap writes, in file order:
+    (out_row0, n_rows, dst_row0, sec_off, rows_s, stale_off): output rows [out_row0, +n) = rows [dst_row0, +n) of the
+    remapped section buffer; buffer rows [0, rows_s) hold source rows sec_off + t, buffer rows [rows_s, section_rows)
+    still hold the previous section's rows stale_off + t (or nothing: stale_off = -1)."""
+    if total_rows <= row_guard:                      # the reference throws (imageop.h:242-244); extension: one remap
+        return [(0, total_rows, 0, 0, total_rows, -1)], total_rows
+    ucut = 0 if dY >= 0.0 else int(-dY) + 1          # stitcher.h:122
+    bcut = int(dY) + 1 if dY >= 0.0 else 0           # :123
+    cut = ucut + bcut                                # imageop.h:246
+    pieces, off, written, prev_off, last = [], 0, 0, -1, None
+    s = 0
+    while True:
+        rows = min(section_rows, total_rows - off)   # :250
+        if rows <= cut:                              # :251
+            break
+        stale = prev_off if rows < section_rows else -1
+        if s == 0 and ucut > 0:                      # :260-263
+            pieces.append((written, ucut, 0, off, rows, stale))
+            written += ucut
+        pieces.append((written, rows - cut, ucut, off, rows, stale))     # :265
+        written += rows - cut
+        last = (off, rows, stale)
+        prev_off = off
+        off += rows - cut                            # :266
+        s += 1
+    if bcut > 0 and last is not None:                # :269-272
+        pieces.append((written, bcut, section_rows - bcut, last[0], last[1], last[2]))
+        written += bcut
+    return pieces, section_rows
+
+
+def pan_rows(gen, n_ccd: int, w: int, kbs, dX, dY, fold_half: int, total_rows: int, rows, section_rows: int = 30000,
+             row_guard: int = 32767) -> np.ndarray:
+    """output rows `rows` (sorted global line indices) of the fused PAN path of a total_rows-line strip.
+    gen(i, a, b) -> raw LE u16 lines [a, b) of CCD i (any lines can be asked for)."""
+    rows = np.asarray(rows, np.int64)
+    out_w = n_ccd * w - 2 * (n_ccd - 1) * fold_half
+    out = np.zeros((rows.size, out_w), np.uint16)
+    xo = 0
+    for i in range(n_ccd):
+        lo, hi = (0 if i == 0 else fold_half), (w if i == n_ccd - 1 else w - fold_half)
+        res = np.zeros((rows.size, w), np.uint16)
+        # consecutive runs of wanted rows
+        cuts = np.flatnonzero(np.diff(rows) != 1) + 1
+        runs = np.split(np.arange(rows.size), cuts) if rows.size else []
+        if i == 0:                                    # CMOS-1: radiometric correction only
+            for idx in runs:
+                a, b = int(rows[idx[0]]), int(rows[idx[-1]]) + 1
+                res[idx] = rrc(gen(i, a, b), kbs[i])
+        else:
+            pieces, hbuf = shift_pieces(total_rows, float(dY[i]), section_rows, row_guard)
+            m = int(np.ceil(abs(float(dY[i])))) + 4
+            for idx in runs:
+                g = int(rows[idx[0]])
+                g_end = int(rows[idx[-1]]) + 1
+                while g < g_end:
+                    pc = next(p for p in pieces if p[0] <= g < p[0] + p[1])
+                    o0, n, d0, sec_off, rows_s, stale = pc
+                    ge = min(g_end, o0 + n)
+                    ja, jb = d0 + (g - o0), d0 + (ge - o0)              # rows of the remapped section buffer
+                    ta, tb = max(0, ja - m), min(hbuf, jb + m)          # buffer rows the window holds
+                    win = np.zeros((tb - ta, w), np.uint16)
+                    fa, fb = ta, min(tb, rows_s)                         # fresh rows of this section
+                    if fb > fa:
+                        win[fa - ta:fb - ta] = rrc(gen(i, sec_off + fa, sec_off + fb), kbs[i])
+                    sa = max(ta, rows_s)                                 # rows left over from the previous section
+                    if tb > sa and stale >= 0:
+                        win[sa - ta:tb - ta] = rrc(gen(i, stale + sa, stale + tb), kbs[i])
+                    mx = (np.arange(w)[None, :] + np.zeros((jb - ja, 1)) + float(dX[i])).astype(np.float32)       # stitcher.h:96
+                    my = (np.arange(ja, jb)[:, None] + np.zeros((1, w)) + float(dY[i])).astype(np.float32)       # :97
+                    my = (my - np.float32(ta)).astype(np.float32)        # exact: an integer off a float with the same ulp
+                    sel = idx[(rows[idx] >= g) & (rows[idx] < ge)]
+                    res[sel] = remap_cubic(win, mx, my)
+                    g = ge
+        out[:, xo:xo + hi - lo] = res[:, lo:hi]
+        xo += hi - lo
+    return out

@@ -92,9 +92,29 @@ def main():
     if not ok_m:
         print(f"rank {rank}: MSS section shard differs from the whole-strip oracle", flush=True)
     ok = ok and ok_m
-    sums = torch.tensor([1.37 * (rank + 1), -2.61, 0.9, 1.0], dtype=torch.float64, device="cuda")   # what oip_stt_parameters hands back
-    dist.all_reduce(sums)
-    ok = ok and sharding.stt_combine(sums.tolist())[1] == -2.61 and int(sums[3].item()) == world
+    # ---- N1 on shards (ref stitcher.h:148-201): oip_stt_parameters on every rank's own rows, the section that straddles
+    #      the block boundary gathered onto one rank, ONE 4-double all-reduce; against the whole-strip CPU loop on cv2
+    import cv2
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_phasecorr_cpu import _pair
+    slines, sw, sov, sns, slps = 2400 * world, 512, 200, 2 * world - 1, 1000
+    sa, sb = _pair(slines, sov, 1.37, -2.61, seed=4)
+    pan1 = np.zeros((slines, sw), np.uint16); pan2 = np.zeros((slines, sw), np.uint16)
+    pan1[:, sw - sov:] = sa
+    pan2[:, :sov] = sb
+    s0, s1 = sharding.shard_range(slines, world, rank)
+    rows_g, mean_g = ops.calc_stt_parameters(ctx, torch.from_numpy(pan1[s0:s1].copy()).cuda(), torch.from_numpy(pan2[s0:s1].copy()).cuda(),
+                                             overlap_cols=sov, edge_cols=6, sections=sns, lines_per_section=slps, total_lines=slines, row0=s0)
+
+    def cvcorr(a, b):
+        (x, y), r = cv2.phaseCorrelate(a, b)
+        return x, y, r
+    rows_w, mean_w = oracle.stt_parameters(pan1, pan2, overlap_cols=sov, edge_cols=6, sections=sns, lines_per_section=slps, correlate=cvcorr)
+    owners = sharding.stt_section_owner(slines, sns, slps, world)
+    ok_s = -1 in owners and mean_g is not None and all(abs(a - b) <= 2e-3 for a, b in zip(mean_g, mean_w))
+    if not ok_s:
+        print(f"rank {rank}: sharded offset estimate {mean_g} vs whole strip {mean_w} (owners {owners})", flush=True)
+    ok = ok and ok_s
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()

@@ -380,3 +380,34 @@ def test_pan_rows_needed_planner():
     # dY=-2.61: taps start at floor(y-2.61)-1 = y-4 and end at y-3+2
     assert (f.value, l.value) == (35000 - 4, 35099 - 3 + 2 + 1)
     assert (sf.value, sl.value) == (0, 0)
+
+
+# ------------------------------------------------- row-window form used by bench.py's in-run parity check
+@pytest.mark.parametrize("total", [1500, 1337, 953, 449])
+@pytest.mark.parametrize("dX,dY", [([0, 1.37, -0.83], [0, -2.61, 3.19]), ([0, 2.5, -3.0], [0, 40.25, -17.5])])
+def test_pan_rows_window_form_equals_whole_strip(total, dX, dY):
+    """oracle.pan_rows (selected output rows from source-row windows: section edges, stale rows of a partial last section)
+    == the literal whole-strip restatement oipo_pan_pipeline (pinned against the reference's compiled PreStitch)"""
+    from opticalimageprocessor_b200 import synth
+    n, w, f, S, G = 3, 96, 10, 400, 450
+    ccds = [np.random.default_rng(5 + i).integers(0, 65536, (total, w), dtype=np.uint16) for i in range(n)]
+    kbs = [synth.rrc_coeffs(w, 70 + i) * np.array([1 / 16.0, 1.0]) for i in range(n)]
+    want = oracle.pan_pipeline(ccds, kbs, dX, dY, f, S, G)
+    gen = lambda i, a, b: ccds[i][a:b]
+    assert np.array_equal(oracle.pan_rows(gen, n, w, kbs, dX, dY, f, total, np.arange(total), S, G), want)
+    sub = np.unique(np.concatenate([np.arange(16), np.arange(total - 16, total), np.random.default_rng(1).integers(0, total, 60)]))
+    assert np.array_equal(oracle.pan_rows(gen, n, w, kbs, dX, dY, f, total, sub, S, G), want[sub])
+
+
+def test_pan_rows_reference_geometry_section_edges():
+    """30000-row sections / guard 32767 on a narrow 32768-line strip: the rows around the section edge and the stale
+    bottom rows, window form == whole strip"""
+    from opticalimageprocessor_b200 import synth
+    n, w, f, total = 2, 32, 4, 32768
+    ccds = [synth.strip_dn(w, total, 40 + i) for i in range(n)]
+    kbs = [synth.rrc_coeffs(w, 50 + i) for i in range(n)]
+    for dX, dY in [([0, 1.37], [0, -2.61]), ([0, -0.83], [0, 3.19])]:
+        want = oracle.pan_pipeline(ccds, kbs, dX, dY, f)
+        rows = np.unique(np.concatenate([np.arange(24), np.arange(29980, 30020), np.arange(total - 24, total)]))
+        got = oracle.pan_rows(lambda i, a, b: ccds[i][a:b], n, w, kbs, dX, dY, f, total, rows)
+        assert np.array_equal(got, want[rows])

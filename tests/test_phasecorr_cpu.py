@@ -37,6 +37,16 @@ def test_phase_correlate_matches_cv2(rows, cols, dx, dy):
     assert abs(ox - dx) < 0.5 and abs(oy - dy) < 0.5  # and it does measure the displacement (5x5 centroid: biased towards the integer peak)
 
 
+@pytest.mark.parametrize("rows,cols", [(125, 125), (243, 100), (250, 125), (600, 75), (135, 81)])
+def test_phase_correlate_odd_dft_sizes_match_cv2(rows, cols):
+    """odd optimal DFT sizes: fftShift is the circular shift by (M // 2, N // 2), the centre is (N / 2.0, M / 2.0)"""
+    assert oracle.optimal_dft_size(rows) % 2 or oracle.optimal_dft_size(cols) % 2
+    a, b = _pair(rows, cols, 1.37, -2.61, seed=rows * 7 + cols)
+    (cx, cy), cr = cv2.phaseCorrelate(a.astype(np.float32), b.astype(np.float32))
+    ox, oy, orr = oracle.phase_correlate(a.astype(np.float32), b.astype(np.float32))
+    assert abs(ox - cx) <= 2e-3 and abs(oy - cy) <= 2e-3 and abs(orr - cr) <= 1e-3
+
+
 def test_stt_parameters_follow_the_reference_loop():
     lines, w, ov = 4096, 512, 200
     scene_a, scene_b = _pair(lines, ov, 1.37, -2.61, seed=3)

@@ -151,6 +151,71 @@ def test_stt_sections_on_two_shards_gloo():
         assert mean is not None and all(abs(a - b) < 1e-12 for a, b in zip(mean, whole))
 
 
+def _stt_straddle_worker(rank, world, port, q):
+    """a section that straddles two scanline blocks must still be correlated -- its rows of the two overlap
+    slices are sent to the rank that holds its first line (sharding.stt_gather_straddling over gloo), so the sharded
+    mean equals the whole-strip mean (ref stitcher.h:166-199 correlates every section)"""
+    import numpy as np
+    import oracle
+    from test_phasecorr_cpu import _pair
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lines, w, ov, ec, ns, lps = 4800, 512, 200, 6, 3, 1000
+        sa, sb = _pair(lines, ov, 1.37, -2.61, seed=4)
+        pan1 = np.zeros((lines, w), np.uint16); pan2 = np.zeros((lines, w), np.uint16)
+        pan1[:, w - ov:] = sa
+        pan2[:, :ov] = sb
+        lo, hi = sharding.shard_range(lines, world, rank)
+        t1, t2 = torch.from_numpy(pan1[lo:hi].copy()), torch.from_numpy(pan2[lo:hi].copy())     # the shard only
+        ranges = [sharding.shard_range(lines, world, r) for r in range(world)]
+        plan = sharding.stt_section_plan(lines, ns, lps, ranges)
+        sums = np.zeros(4)
+        n_whole = 0
+        for off, owner, pieces in plan:
+            if len(pieces) == 1 and owner == rank:
+                n_whole += 1
+                dx, dy, r = oracle.phase_correlate(pan1[off:off + lps, w - ov:w - ec].astype(np.float32), pan2[off:off + lps, ec:ov].astype(np.float32))
+                if r >= 0.4:
+                    sums += [dx, dy, r, 1]
+        got = sharding.stt_gather_straddling(t1, t2, lo, rank, plan, (w - ov, w - ec), (ec, ov))
+        for idx, a, b in got:
+            dx, dy, r = oracle.phase_correlate(a.numpy().astype(np.float32), b.numpy().astype(np.float32))
+            if r >= 0.4:
+                sums += [dx, dy, r, 1]
+        t = torch.from_numpy(sums)
+        dist.all_reduce(t)
+        _, whole_mean = oracle.stt_parameters(pan1, pan2, overlap_cols=ov, edge_cols=ec, sections=ns, lines_per_section=lps)
+        q.put((rank, [(o, [p[0] for p in pc]) for _, o, pc in plan], n_whole, len(got), sharding.stt_combine(t.tolist()), whole_mean, t.tolist()[3]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stt_straddling_section_is_gathered_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stt_straddle_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, plan, n_whole, n_gathered, mean, whole, n_valid in res:
+        assert plan == [(0, [0]), (0, [0, 1]), (1, [1])]          # the middle section straddles: owned by rank 0
+        assert n_whole == 1 and n_gathered == (1 if rank == 0 else 0)
+        assert n_valid == 3.0
+        assert mean is not None and all(abs(a - b) < 1e-12 for a, b in zip(mean, whole))
+
+
+def test_stt_section_plan_rejects_missing_rows():
+    with pytest.raises(ValueError):
+        sharding.stt_section_plan(4800, 3, 1000, [(0, 2000), (2400, 4800)])
+
+
 def test_stt_section_owner_reports_straddlers():
     # reference defaults on a 4 x 65536-line strip: 16000-line sections, some cross a block boundary
     total, world = 4 * 65536, 4

@@ -37,10 +37,33 @@ def test_phase_correlate_on_column_views(ctx):
     assert abs(gx - cx) <= 2e-3 and abs(gy - cy) <= 2e-3 and abs(gr - cr) <= 1e-3
 
 
-def test_odd_dft_size_is_refused(ctx):
-    a = torch.zeros((125, 64), dtype=torch.uint16, device="cuda")  # getOptimalDFTSize(125) = 125
+@pytest.mark.parametrize("rows,cols", [(125, 125), (243, 100), (250, 125), (600, 75), (135, 81)])
+def test_odd_dft_sizes_match_cv2(ctx, rows, cols):
+    """getOptimalDFTSize gives an odd size (125, 243, 75, 135, 81 ...): OpenCV's fftShift is then the circular shift by
+    (M // 2, N // 2) and the centre is (N / 2.0, M / 2.0) (e.g. `prestitch --stitch-overlap 125`)"""
+    assert oracle.optimal_dft_size(rows) % 2 or oracle.optimal_dft_size(cols) % 2
+    a, b = _pair(rows, cols, 1.37, -2.61, seed=rows * 7 + cols)
+    (cx, cy), cr = cv2.phaseCorrelate(a.astype(np.float32), b.astype(np.float32))
+    gx, gy, gr = ops.phase_correlate(ctx, torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    assert abs(gx - cx) <= 2e-3 and abs(gy - cy) <= 2e-3 and abs(gr - cr) <= 1e-3, ((gx, gy, gr), (cx, cy, cr))
+
+
+def test_edge_cols_equal_to_half_the_overlap(ctx):
+    """`prestitch -e 100` with the default overlap 200 passes the reference CLI check (ref main.cpp:135-141) and
+    correlates colRange(W-200, W-100) with colRange(100, 200) (ref stitcher.h:175-176)"""
+    lines, w, ov = 4096, 512, 200
+    pan1, pan2 = _strips(lines, w, ov, 1.37, -2.61, 11)
+
+    def cvcorr(s1, s2):
+        (x, y), r = cv2.phaseCorrelate(s1, s2)
+        return x, y, r
+    kw = dict(overlap_cols=ov, edge_cols=100, sections=3, lines_per_section=1000, threshold=0.0)
+    rows_cv, mean_cv = oracle.stt_parameters(pan1, pan2, correlate=cvcorr, **kw)
+    rows, mean = ops.calc_stt_parameters(ctx, torch.from_numpy(pan1).cuda(), torch.from_numpy(pan2).cuda(), **kw)
+    for g, c in zip(rows, rows_cv):
+        assert g[0] == c[0] and abs(g[1] - c[1]) <= 2e-3 and abs(g[2] - c[2]) <= 2e-3 and abs(g[3] - c[3]) <= 1e-3
     with pytest.raises(capi.OipError):
-        ops.phase_correlate(ctx, a, a)
+        ops.calc_stt_parameters(ctx, torch.from_numpy(pan1).cuda(), torch.from_numpy(pan2).cuda(), overlap_cols=ov, edge_cols=ov)
 
 
 def _strips(lines, w, ov, dx, dy, seed):
