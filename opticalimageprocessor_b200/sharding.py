@@ -148,14 +148,15 @@ def stt_gather_straddling(pan1, pan2, row0: int, rank: int, plan, cols1: Tuple[i
                     dst[1].copy_(pan2[a - row0:b - row0, cols2[0]:cols2[1]].view(torch.int16))
                 else:
                     tmp = torch.empty((2, b - a, n1), dtype=torch.int16, device=pan1.device)
-                    dist.recv(tmp, src=r if group is None else dist.get_global_rank(group, r), group=group)
+                    # bytes on the wire: NCCL has no 16-bit integer type
+                    dist.recv(tmp.view(torch.uint8), src=r if group is None else dist.get_global_rank(group, r), group=group)
                     dst.copy_(tmp)
             out.append((idx, buf[0].view(torch.uint16), buf[1].view(torch.uint16)))
         elif mine:
             _, a, b = mine[0]
             tmp = torch.stack([pan1[a - row0:b - row0, cols1[0]:cols1[1]].view(torch.int16),
                                pan2[a - row0:b - row0, cols2[0]:cols2[1]].view(torch.int16)]).contiguous()
-            dist.send(tmp, dst=owner if group is None else dist.get_global_rank(group, owner), group=group)
+            dist.send(tmp.view(torch.uint8), dst=owner if group is None else dist.get_global_rank(group, owner), group=group)
     return out
 
 

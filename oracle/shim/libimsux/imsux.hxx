@@ -66,6 +66,7 @@ struct xs {
         va_list ap; va_start(ap, fmt); vsnprintf(s, sizeof s, fmt, ap); va_end(ap);
     }
     operator const char *() const { return s; }
+    operator std::string() const { return std::string(s); }
 };
 
 class comma_sep {

@@ -1,0 +1,2 @@
+#pragma once
+#include "../ref_cv_stub.hpp"

@@ -42,7 +42,9 @@ public:
     void create(int r, int c, int type) {
         if (r == rows && c == cols && type == type_ && data) return;
         rows = r; cols = c; type_ = type; step = (size_t)c * elemSize();
-        store_ = std::shared_ptr<uint8_t>(new uint8_t[(size_t)r * step + 64], std::default_delete<uint8_t[]>());
+        // zero-filled (the real cv::Mat::create leaves memory uninitialised): rows the reference never writes
+        // (SURVEY C-4) then read 0 in the golden files instead of garbage
+        store_ = std::shared_ptr<uint8_t>(new uint8_t[(size_t)r * step + 64](), std::default_delete<uint8_t[]>());
         data = store_.get();
     }
     void release() { store_.reset(); data = nullptr; rows = cols = 0; }
@@ -82,10 +84,32 @@ inline void remap(const Mat &src, Mat &dst, const Mat &mapx, const Mat &mapy, in
                          mapx.cols, mapx.rows, (const float *)mapx.data, (const float *)mapy.data);
 }
 inline Mat imread(const std::string &, int) { abort(); }
-inline bool imwrite(const std::string &, const Mat &) { abort(); }
+// imwrite stand-in: the matrix bytes as they lie in memory (rows x cols x channels u16), no container.  The real
+// cv::imwrite stores 4-channel data as a TIFF in RGBA order (host/tiff_io.hpp, tests/test_tiff_cpu.py)
+inline bool imwrite(const std::string &path, const Mat &m) {
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    bool ok = true;
+    for (int r = 0; r < m.rows && ok; ++r) ok = fwrite(m.ptr(r), m.elemSize(), (size_t)m.cols, f) == (size_t)m.cols;
+    fclose(f);
+    return ok;
+}
 inline Mat imdecode(const Mat &, int, Mat * = nullptr) { abort(); }
 inline void split(const Mat &, Mat *) { abort(); }
-inline void merge(const Mat *, size_t, Mat &) { abort(); }
+// cv::merge of n single-channel CV_16U planes -> interleaved rows x cols x n (verified against cv2.merge)
+inline void merge(const Mat *mv, size_t n, Mat &dst) {
+    if (n < 1 || n > 4) abort();
+    for (size_t c = 0; c < n; ++c)
+        if (mv[c].type() != CV_16UC1 || mv[c].rows != mv[0].rows || mv[c].cols != mv[0].cols) abort();
+    dst.create(mv[0].rows, mv[0].cols, CV_MAKETYPE(CV_16U, (int)n));
+    for (int r = 0; r < dst.rows; ++r) {
+        uint16_t *o = (uint16_t *)dst.ptr(r);
+        for (size_t c = 0; c < n; ++c) {
+            const uint16_t *s = (const uint16_t *)mv[c].ptr(r);
+            for (int x = 0; x < dst.cols; ++x) o[(size_t)x * n + c] = s[x];
+        }
+    }
+}
 inline void resize(const Mat &, Mat &, Size, double, double, int) { abort(); }
 template <typename A, typename B> inline Point2d phaseCorrelate(const A &, const B &, NoArray, double *) { abort(); }
 } // namespace cv

@@ -17,4 +17,4 @@ def test_two_gpu_shards_match_oracle(oracle_mod):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(here, "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "MULTI_GPU_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "MULTI_GPU_CHECK OK" in r.stdout, r.stdout[-3000:] + "\n".join(l for l in r.stderr.splitlines() if "site-packages/torch/distributed" not in l)[-6000:]

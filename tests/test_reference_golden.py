@@ -126,3 +126,90 @@ def test_reference_rrc_direct():
     want = img.copy()
     L.ref_inplace_rrc(want.ctypes.data_as(C.c_void_p), 12288, 64, kb.ctypes.data_as(C.c_void_p))
     assert np.array_equal(oracle.rrc(img, kb), want)
+
+
+# ------------------------------------------------------------------------------------------------
+# band alignment and the RRC CSV loader against the reference's own preproc.h / imageop.h (round 2):
+# tests/golden/ref_bandalign.npz and ref_rrc_csv.npz were written by PreProcessor::LoadMSS + DoRRC4MSS +
+# DoInterBandAlignment and IMO::LoadRRCParamFile compiled unmodified under oracle/_ref
+# ------------------------------------------------------------------------------------------------
+def _golden_consts():
+    src = open(os.path.join(GOLD, "make_golden_ref.py")).read()
+    ns = {}
+    a = src.index("BA_CX = ")
+    b = src.index("def make_bandalign")
+    c = src.index("RRC_CSV_TEXTS = ")
+    d = src.index("def make_rrccsv")
+    exec(compile("import numpy as np\n" + src[a:b] + src[c:d], "golden_consts", "exec"), ns)
+    return ns
+
+
+def _check_bandalign(out, g, tag):
+    rows = int(g[tag + "_rows"])
+    assert out.shape == (rows, 3072, 4)
+    blocks = [sha(out[i:i + 512]) for i in range(0, rows, 512)]
+    bad = [i for i, (a, b) in enumerate(zip(blocks, g[tag + "_block_sha"])) if a != str(b)]
+    assert not bad, f"{tag}: 512-row blocks {bad} differ from the reference's DoInterBandAlignment run"
+
+
+BA_TAGS = ["s3000", "s3000_keep_off_norrc", "default"]
+
+
+@pytest.mark.parametrize("tag", BA_TAGS)
+def test_oracle_reproduces_reference_band_alignment(tag):
+    """ref preproc.h:56-80 (band split), :202-222 (per-band RRC), :351-468 (sections, polynomial map, remap, merge)"""
+    g = np.load(os.path.join(GOLD, "ref_bandalign.npz"))
+    ns = _golden_consts()
+    lines, lps, off, ov, keep, do_rrc, seed = (int(v) for v in g[tag + "_params"])
+    mss = ns["bandalign_input"](lines, seed)
+    planes = oracle.mss_split(mss)
+    if do_rrc:
+        planes = [oracle.rrc(p, synth.rrc_coeffs(3072, 300 + b)) for b, p in enumerate(planes)]
+    n, out = oracle.band_align(planes, g["cX"], g["cY"], lines_per_section=lps, line_offset=off, overlap=ov, keep_leading=bool(keep))
+    _check_bandalign(out, g, tag)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", BA_TAGS)
+@pytest.mark.parametrize("fast", [1, 0])
+def test_gpu_reproduces_reference_band_alignment(ctx, tag, fast):
+    import torch
+    from opticalimageprocessor_b200 import ops
+    g = np.load(os.path.join(GOLD, "ref_bandalign.npz"))
+    ns = _golden_consts()
+    lines, lps, off, ov, keep, do_rrc, seed = (int(v) for v in g[tag + "_params"])
+    mss = torch.from_numpy(ns["bandalign_input"](lines, seed)).cuda()
+    kbs = [torch.from_numpy(synth.rrc_coeffs(3072, 300 + b)).cuda() for b in range(4)] if do_rrc else None
+    ctx.set_option("mss_fast", fast)
+    try:
+        n, out = ops.band_align(ctx, mss, 3072, kbs, g["cX"], g["cY"], lines_per_section=lps, line_offset=off, overlap=ov,
+                                keep_leading=bool(keep))
+        ctx.sync()
+    finally:
+        ctx.set_option("mss_fast", 1)
+    _check_bandalign(out.cpu().numpy(), g, tag)
+
+
+def test_rrc_csv_loaders_match_reference(tmp_path):
+    """IMO::LoadRRCParamFile (ref imageop.h:140-192) ran on these texts: the oracle's and the product's host parser
+    (oip_load_rrc_csv, no GPU involved) must accept / reject the same files and return the same doubles"""
+    import ctypes as C
+    from opticalimageprocessor_b200 import capi
+    g = np.load(os.path.join(GOLD, "ref_rrc_csv.npz"))
+    ns = _golden_consts()
+    L = capi.load()
+    for tag, text in ns["RRC_CSV_TEXTS"].items():
+        p = tmp_path / (tag + ".csv")
+        p.write_bytes(text.encode())
+        n = ns["RRC_CSV_EXPECT"][tag]
+        want_ok = bool(g[tag + "_ok"])
+        kb_o = np.zeros(2 * n)
+        rc_o = oracle.lib().oipo_load_rrc_csv(str(p).encode(), n, kb_o)
+        kb_p = np.zeros(2 * n)
+        rc_p = L.oip_load_rrc_csv(str(p).encode(), n, kb_p.ctypes.data)
+        assert (rc_o == 0) == want_ok, (tag, rc_o)
+        assert (rc_p == 0) == want_ok, (tag, rc_p, capi.last_error())
+        if want_ok:
+            assert np.array_equal(kb_o, g[tag + "_kb"]) and np.array_equal(kb_p, g[tag + "_kb"]), tag
+    assert not bool(g["missing_file_ok"])
+    assert L.oip_load_rrc_csv(str(tmp_path / "does_not_exist.csv").encode(), 2, np.zeros(4).ctypes.data) == capi.OIP_E_IO
