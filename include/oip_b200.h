@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OIP_ABI_VERSION 1
+#define OIP_ABI_VERSION 2
 
 typedef enum {
     OIP_OK = 0,
@@ -173,6 +173,10 @@ typedef struct {
      * of each sub-image, -1 for a zero-filled frame; lines_per_frame = 4*tile_lines */
     const int64_t *d_tile_off;
     int tile_cols, tile_lines;
+    /* OIP_FMT_BE16_TILES, optional: the same table in HOST memory (oip_image_frames_index returns its entries on the
+     * host).  With it the planner can prove the sub-images 4-byte aligned and sends the CCD through the fast kernel,
+     * which gathers its stage rows straight from the sub-images; without it the CCD runs on the generic kernel. */
+    const int64_t *h_tile_off;
 } oip_ccd_src;
 
 typedef struct {
@@ -323,6 +327,39 @@ typedef struct oip_ibc_shift {   /* InterBandShift, ref preproc.h:23-28 */
 int oip_inter_band_correlation(oip_ctx *ctx, const uint16_t *d_pan, int w, int64_t lines_pan, int64_t pan_pitch_px,
                                const uint16_t *d_mss, int64_t lines_mss, int64_t mss_pitch_px, const oip_ibc_config *cfg,
                                oip_ibc_shift *shifts, double cX[8], double cY[12]);
+
+/* ---- raw downlink files -> stitched PAN raster in one call ------------------- */
+/* one CCD's downlink: the AOS file image (ref aux_separator.h:224-245 mmaps it), device resident */
+typedef struct {
+    const uint8_t *d_file;
+    size_t n_bytes;
+    const double *d_kb;  /* 8*tile_cols {k,b} pairs or NULL */
+    int shifted;         /* as in oip_ccd_src */
+    double dX, dY;
+} oip_downlink_src;
+typedef struct {
+    int n_ccd;           /* 1..8 */
+    oip_frame_geom geom;
+    int fold_half, section_rows, row_guard;   /* as in oip_pan_desc */
+    oip_downlink_src ccd[8];
+    uint16_t *d_out;     /* out_rows_cap x out_w, out_w = oip_pan_out_width(n_ccd, 8*tile_cols, fold_half) */
+    int64_t out_pitch_px;
+    int64_t out_rows_cap;
+    uint8_t *d_aux[8];   /* optional per CCD: n_frames x 192*tile_lines bytes (.AUX, ref aux_separator.h:335-339) */
+    uint16_t *d_mss[8];  /* optional per CCD: n_frames*tile_lines lines of 8*tile_cols px (.MSS.RAW, ref :341-364) */
+} oip_downlink_desc;
+typedef struct {
+    int64_t aos[3];      /* valid, invalid, empty AOS frames (ref aux_separator.h:411-413) */
+    int64_t imtr[9];     /* as oip_imtr_deframe */
+    int64_t frames[4];   /* as oip_image_frames_index */
+    int64_t imdt_bytes;
+} oip_downlink_stats;
+/* replaces, for the PAN product, the whole chain `auxsep` -> `prestitch` -> `stitch`:
+ *   AuxSeparator::Separate (SeparateAosFile, DataTransFrameParser, SeparateImageData)  ref aux_separator.h:224-245, :256-590
+ *   IMO::InplaceRRC, Stitcher::PreStitch + IMO::SectionaryRemap, IMO::StitchBigRaw       ref imageop.h:129-138, :230-363
+ * The fused PAN kernel reads the sub-images where they lie in the IMDT stream; .PAN.RAW / .RRC.RAW / .PRESTT.RAW never
+ * exist.  *rows_out = lines produced (frames x 4*tile_lines, the shortest CCD decides); stats[n_ccd] may be NULL. */
+int oip_downlink_to_stitched(oip_ctx *ctx, const oip_downlink_desc *desc, int64_t *rows_out, oip_downlink_stats *stats);
 
 /* ---- bench / test input (NOT a replaced reference function) --------------------------------- */
 /* The reference ships no sample data; SURVEY 8(d) defines the synthetic strip DN(x,y) = 64 + ((37x mod 1500 + (y/8) mod 1200 +

@@ -27,7 +27,7 @@ class RowSeg(C.Structure):
 class CcdSrc(C.Structure):
     _fields_ = [("fmt", C.c_int), ("n_seg", C.c_int), ("seg", RowSeg * MAX_SEG), ("d_kb", C.c_void_p),
                 ("shifted", C.c_int), ("dX", C.c_double), ("dY", C.c_double), ("d_tile_off", C.c_void_p),
-                ("tile_cols", C.c_int), ("tile_lines", C.c_int)]
+                ("tile_cols", C.c_int), ("tile_lines", C.c_int), ("h_tile_off", C.c_void_p)]
 
 
 class PanDesc(C.Structure):
@@ -50,6 +50,21 @@ class MssDesc(C.Structure):
                 ("lines_per_section", C.c_int), ("line_offset", C.c_int64), ("overlap", C.c_int),
                 ("keep_leading", C.c_int), ("min_process_lines", C.c_int), ("sec_first", C.c_int), ("sec_count", C.c_int),
                 ("src_row0", C.c_int64)]
+
+
+class DownlinkSrc(C.Structure):
+    _fields_ = [("d_file", C.c_void_p), ("n_bytes", C.c_size_t), ("d_kb", C.c_void_p), ("shifted", C.c_int), ("dX", C.c_double),
+                ("dY", C.c_double)]
+
+
+class DownlinkDesc(C.Structure):
+    _fields_ = [("n_ccd", C.c_int), ("geom", FrameGeom), ("fold_half", C.c_int), ("section_rows", C.c_int), ("row_guard", C.c_int),
+                ("ccd", DownlinkSrc * 8), ("d_out", C.c_void_p), ("out_pitch_px", C.c_int64), ("out_rows_cap", C.c_int64),
+                ("d_aux", C.c_void_p * 8), ("d_mss", C.c_void_p * 8)]
+
+
+class DownlinkStats(C.Structure):
+    _fields_ = [("aos", C.c_int64 * 3), ("imtr", C.c_int64 * 9), ("frames", C.c_int64 * 4), ("imdt_bytes", C.c_int64)]
 
 
 class SttConfig(C.Structure):
@@ -113,6 +128,7 @@ SYMBOLS = {
     "oip_stitch_concat_c4": (_I, [_VP, C.POINTER(_VP), _I, _I, _I64, _I, C.POINTER(_I), _VP]),
     "oip_unpack_lines": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP]),
     "oip_pan_pipeline_host": (_I, [_VP, C.POINTER(PanDesc)]),
+    "oip_downlink_to_stitched": (_I, [_VP, C.POINTER(DownlinkDesc), C.POINTER(_I64), C.POINTER(DownlinkStats)]),
     "oip_synth_strip_dn": (_I, [_VP, _VP, _I, _I64, _I64, _I64, C.c_uint64, _I]),
     "oip_phase_correlate_u16": (_I, [_VP, _VP, _I64, _VP, _I64, _I, _I, C.POINTER(_D)]),
     "oip_inter_band_correlation": (_I, [_VP, _VP, _I, _I64, _I64, _VP, _I64, _I64, C.POINTER(IbcConfig), C.POINTER(IbcShift),

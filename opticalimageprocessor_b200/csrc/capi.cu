@@ -107,6 +107,7 @@ void oip_ctx_destroy(oip_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     oip::host_pipe_destroy(ctx);
     oip::stt::destroy(ctx);
+    oip::downlink_destroy(ctx);
     for (oip_pan_plan &pl : ctx->pan_plans) {
         if (pl.d_plan) cudaFree(pl.d_plan);
         if (pl.h_stage) cudaFreeHost(pl.h_stage);
@@ -128,7 +129,7 @@ int oip_ctx_set_option(oip_ctx *ctx, const char *name, int64_t value)
     if (!ctx || !name) return oip::fail(OIP_E_INVALID, "oip_ctx_set_option: null argument");
     if (!strcmp(name, "pan_fast")) ctx->pan_fast = value != 0;
     else if (!strcmp(name, "pan_fast_stages") && value >= 2 && value <= 8) ctx->pan_fast_stages = (int)value;
-    else if (!strcmp(name, "pan_fast_minb") && value >= 3 && value <= 4) ctx->pan_fast_minb = (int)value;
+    else if (!strcmp(name, "pan_fast_minb") && value >= 3 && value <= 4) ctx->pan_fast_minb = (int)value; // kept for old scripts: one variant is built
     else if (!strcmp(name, "host_block_rows") && value >= 64 && value <= (1 << 20)) ctx->host_block_rows = (int)value;
     else if (!strcmp(name, "mss_fast")) ctx->mss_fast = value != 0;
     else if (!strcmp(name, "mss_fast_rows") && value >= 16 && value <= 32768) ctx->mss_fast_rows = (int)value;

@@ -66,6 +66,7 @@ struct oip_ctx {
     // host-buffer pipeline (oip_pan_pipeline_host): staging slots + side streams
     void *host_pipe = nullptr;
     void *stt_state = nullptr; // cuFFT plans of the offset estimation (stt.cu)
+    void *downlink_state = nullptr; // per-CCD IMDT / table buffers of oip_downlink_to_stitched (downlink.cu)
 };
 
 namespace oip {
@@ -91,6 +92,7 @@ int ensure_scratch(oip_ctx *ctx, size_t bytes);
 int ensure_pinned(oip_ctx *ctx, size_t bytes);
 void host_pipe_destroy(oip_ctx *ctx);
 namespace stt { void destroy(oip_ctx *ctx); }
+void downlink_destroy(oip_ctx *ctx);
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

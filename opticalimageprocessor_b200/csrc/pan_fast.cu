@@ -82,12 +82,71 @@ struct WarpCtx {
     int ns, lane;
 };
 
-// x: first sample of the box (multiple of 8); the tensor map counts 32-bit elements
-__device__ __forceinline__ void issue_stage(const WarpCtx &C, int slot, int x, int y)
+__device__ __forceinline__ uint32_t fdiv(const FastDiv &d, uint32_t n)
 {
-    const uint32_t bar = C.bar0 + 8u * slot, dst = C.stage0 + (uint32_t)slot * STAGE_BYTES;
-    mbar_expect_tx_u32(bar, STAGE_BYTES);
-    tma_load_2d(dst, C.tm, x >> 1, y, bar);
+    const uint32_t t = __umulhi(d.m, n);
+    return (t + ((n - t) >> d.s1)) >> d.s2;
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// Stage loader for OIP_FMT_BE16_TILES sources: the same RC x BOX_W-word stage image the tensor copy produces, gathered
+// straight from the sub-images of the IMDT stream, so the frame tiles never become a raster in HBM (ref
+// aux_separator.h:341-372 MergeSubImage writes that raster).  Frames sit at arbitrary 4-byte offsets of
+// the stream (a frame is 12 mod 16 bytes long), which rules the TMA unit out (16-byte global alignment): every lane
+// copies 17 words of ONE row with 4-byte cp.async (LDGSTS, zero fill by src-size 0) and the stage's mbarrier counts the
+// 32 lanes' completions (cp.async.mbarrier.arrive.noinc).  No loader state lives across the row loop: the row's frame /
+// tile row / line come from its index by two multiply-high divisions.
+// x: first sample of the box (multiple of 8, may be < 0 for EDGE tiles), y: first row, c0 = floor(x / tile_cols)
+__device__ __forceinline__ void issue_stage_tiled(const FastCcd &S, const WarpCtx &C, int slot, int x, int y, int c0)
+{
+    const int rr = C.lane & 3, kq = C.lane >> 2;
+    const uint32_t bar = C.bar0 + 8u * slot;
+    const uint32_t dst = C.stage0 + (uint32_t)slot * STAGE_BYTES + (uint32_t)rr * ROW_BYTES + 4u * (uint32_t)kq;
+    const uint32_t yr = (uint32_t)(y + rr);
+    const uint32_t f = fdiv(S.div_lpf, yr), rl = yr - f * S.div_lpf.d;
+    const uint32_t r = fdiv(S.div_tl, rl), line = rl - r * S.div_tl.d;
+    const bool row_ok = f < (uint32_t)S.n_frames;          // rows past the last frame (chunk rounding): zero fill
+    const int xa = c0 * S.tile_cols, xb = xa + S.tile_cols;
+    const int xl = x + 2 * kq;                             // sample column of my first word
+    const int64_t *tab = S.tile_off + ((int64_t)f * 40 + r * 8);
+    int64_t oA = -1, oB = -1;
+    if (row_ok && (unsigned)c0 < 8u) oA = __ldg(tab + c0);
+    const uint8_t *pA = S.tile_base;
+    uint32_t szA = 0;
+    if (oA >= 0) { pA += oA + 2 * ((int64_t)line * S.tile_cols + (xl - xa)); szA = 4; }
+    if (x >= 0 && x + 2 * BOX_W <= xb) {                   // (warp-uniform) the whole window lies in one sub-image column
+#pragma unroll
+        for (int j = 0; j < BOX_W / 8; ++j) cp_async4(dst + 32u * j, pA + 32 * j, szA);
+    } else {
+        if (row_ok && (unsigned)(c0 + 1) < 8u) oB = __ldg(tab + c0 + 1);
+        const uint8_t *pB = S.tile_base;
+        uint32_t szB = 0;
+        if (oB >= 0) { pB += oB + 2 * ((int64_t)line * S.tile_cols + (xl - xb)); szB = 4; }
+        const int jb = xl >= xb ? 0 : (xb - xl + 15) >> 4; // first word of mine that lies in column c0 + 1
+#pragma unroll
+        for (int j = 0; j < BOX_W / 8; ++j) {
+            const bool b = j >= jb;
+            cp_async4(dst + 32u * j, (b ? pB : pA) + 32 * j, b ? szB : szA);
+        }
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// warp-collective.  Line formats: one lane issues the 2-D tensor copy (x: first sample of the box, a multiple of 8; the
+// tensor map counts 32-bit elements).  Tiled sources: see above.
+template <bool TILED>
+__device__ __forceinline__ void issue_stage(const FastParams &P, const FastTile &T, const WarpCtx &C, int slot, int x, int y)
+{
+    if (TILED) {
+        issue_stage_tiled(P.ccd[T.ccd], C, slot, x, y, T.tmap);
+    } else if (C.lane == 0) {
+        const uint32_t bar = C.bar0 + 8u * slot, dst = C.stage0 + (uint32_t)slot * STAGE_BYTES;
+        mbar_expect_tx_u32(bar, STAGE_BYTES);
+        tma_load_2d(dst, C.tm, x >> 1, y, bar);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ REMAP warp-tile
@@ -99,7 +158,7 @@ __device__ __forceinline__ void stg_v2_if(void *p, uint32_t a, uint32_t b, bool 
                  : "memory");
 }
 
-template <int MODE, int DM, bool SWAP>
+template <int MODE, int DM, bool SWAP, bool TILED>
 __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                            const double (&b)[8])
 {
@@ -108,9 +167,9 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
     const int x0 = T.src_x0 & ~7; // box origin; window column 0 sits (src_x0 & 7) samples in
     const uint32_t offL = 2u * (uint32_t)((T.src_x0 - x0) & ~3) + 8u * (uint32_t)lane;
     const uint32_t offR = 2u * (uint32_t)((T.src_x0 - x0 + T.half) & ~3) + 8u * (uint32_t)lane;
-    if (lane == 0) {
+    {
         const int pre = min(ns, n_chunks);
-        for (int c = 0; c < pre; ++c) issue_stage(C, c, x0, T.src_y0 + c * RC);
+        for (int c = 0; c < pre; ++c) issue_stage<TILED>(P, T, C, c, x0, T.src_y0 + c * RC);
     }
     // 2-D weights w[r][c] = fl32(wy[r] * wx[c]), identical for the whole tile
     const f2 nz = *reinterpret_cast<const f2 *>(P.tab + 128);
@@ -203,7 +262,7 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
         resample(wa, m + 2, B2, B3, B0, B1);
         // stage `slot` is consumed: refill it, move on to the next stage and convert its first row
         __syncwarp();
-        if (lane == 0 && c + ns < n_chunks) issue_stage(C, slot, x0, T.src_y0 + (c + ns) * RC);
+        if (c + ns < n_chunks) issue_stage<TILED>(P, T, C, slot, x0, T.src_y0 + (c + ns) * RC);
         if (++slot == ns) { slot = 0; phase ^= 1u; }
         mbar_wait_u32(C.bar0 + 8u * slot, phase);
         sa = C.stage0 + (uint32_t)slot * STAGE_BYTES;
@@ -223,16 +282,16 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
 }
 
 // ------------------------------------------------------------------------------------------- COPY warp-tile
-template <int MODE, bool SWAP, bool TAIL>
+template <int MODE, bool SWAP, bool TAIL, bool TILED>
 __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                           const double (&b)[8])
 {
     const int lane = C.lane, ns = C.ns;
     const int n_rows = T.n_rows;
     const int n_chunks = (n_rows + RC - 1) / RC;
-    if (lane == 0) {
+    {
         const int pre = min(ns, n_chunks);
-        for (int c = 0; c < pre; ++c) issue_stage(C, c, T.x_begin, T.src_y0 + c * RC);
+        for (int c = 0; c < pre; ++c) issue_stage<TILED>(P, T, C, c, T.x_begin, T.src_y0 + c * RC);
     }
     const bool full = 8 * lane + 8 <= T.half;       // T.half = columns of this strip: any number <= 256
     const int tail = full ? 0 : max(0, T.half - 8 * lane); // the lane that holds the strip's last odd columns
@@ -270,7 +329,7 @@ __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T
             o += pitch;
         }
         __syncwarp();
-        if (lane == 0 && c + ns < n_chunks) issue_stage(C, slot, T.x_begin, T.src_y0 + (c + ns) * RC);
+        if (c + ns < n_chunks) issue_stage<TILED>(P, T, C, slot, T.x_begin, T.src_y0 + (c + ns) * RC);
         if (++slot == ns) { slot = 0; phase ^= 1u; }
     }
 }
@@ -281,6 +340,7 @@ __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T
 // column per lane, scalar FP32, both of OpenCV's accumulation orders (interior: per-row sums added row by row;
 // border: one flat left-to-right chain starting from 0) computed and selected per column.  Taps
 // outside the CCD are zero: TMA zero-fills them and their (k,b) are forced to 0.  < 0.1 % of the pixels.
+template <bool TILED>
 __device__ __forceinline__ void edge_tile(const FastParams &P, const FastTile &T, const WarpCtx &C)
 {
     const int lane = C.lane, ns = C.ns;
@@ -288,9 +348,9 @@ __device__ __forceinline__ void edge_tile(const FastParams &P, const FastTile &T
     const int x0 = T.src_x0 & ~7;                  // floor to a multiple of 8 (also for negative columns)
     const int col = T.src_x0 + lane;               // source column this lane converts = first tap of output column x_begin+lane
     const uint32_t off = 2u * (uint32_t)(col - x0);
-    if (lane == 0) {
+    {
         const int pre = min(ns, n_chunks);
-        for (int c = 0; c < pre; ++c) issue_stage(C, c, x0, T.src_y0 + c * RC);
+        for (int c = 0; c < pre; ++c) issue_stage<TILED>(P, T, C, c, x0, T.src_y0 + c * RC);
     }
     const bool swap = P.ccd[T.ccd].swap != 0;
     const double *kbp = P.ccd[T.ccd].kb;
@@ -339,36 +399,40 @@ __device__ __forceinline__ void edge_tile(const FastParams &P, const FastTile &T
             o += P.out_pitch;
         }
         __syncwarp();
-        if (lane == 0 && c + ns < n_chunks) issue_stage(C, slot, x0, T.src_y0 + (c + ns) * RC);
+        if (c + ns < n_chunks) issue_stage<TILED>(P, T, C, slot, x0, T.src_y0 + (c + ns) * RC);
         if (++slot == ns) { slot = 0; phase ^= 1u; }
     }
 }
 
-template <int MODE, bool SWAP>
+template <int MODE, bool SWAP, bool TILED>
 __device__ __forceinline__ void remap_dispatch(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                                const double (&b)[8])
 {
     const int dm = T.src_x0 & 3;
-    if (dm == 0) remap_tile<MODE, 0, SWAP>(P, T, C, k, b);
-    else if (dm == 1) remap_tile<MODE, 1, SWAP>(P, T, C, k, b);
-    else if (dm == 2) remap_tile<MODE, 2, SWAP>(P, T, C, k, b);
-    else remap_tile<MODE, 3, SWAP>(P, T, C, k, b);
+    if (dm == 0) remap_tile<MODE, 0, SWAP, TILED>(P, T, C, k, b);
+    else if (dm == 1) remap_tile<MODE, 1, SWAP, TILED>(P, T, C, k, b);
+    else if (dm == 2) remap_tile<MODE, 2, SWAP, TILED>(P, T, C, k, b);
+    else remap_tile<MODE, 3, SWAP, TILED>(P, T, C, k, b);
 }
 
 template <int MODE>
-__device__ __forceinline__ void tile_dispatch(const FastParams &P, const FastTile &T, const WarpCtx &C, bool swap, const double (&k)[8],
-                                              const double (&b)[8])
+__device__ __forceinline__ void tile_dispatch(const FastParams &P, const FastTile &T, const WarpCtx &C, bool swap, bool tiled,
+                                              const double (&k)[8], const double (&b)[8])
 {
     if (T.kind == FT_REMAP) {
-        if (swap) remap_dispatch<MODE, true>(P, T, C, k, b);
-        else remap_dispatch<MODE, false>(P, T, C, k, b);
+        if (tiled) remap_dispatch<MODE, true, true>(P, T, C, k, b); // sub-images hold big-endian samples
+        else if (swap) remap_dispatch<MODE, true, false>(P, T, C, k, b);
+        else remap_dispatch<MODE, false, false>(P, T, C, k, b);
     } else {
-        if (T.half & 7) { // rare: keep the tail stores out of the common loop
-            if (swap) copy_tile<MODE, true, true>(P, T, C, k, b);
-            else copy_tile<MODE, false, true>(P, T, C, k, b);
+        if (tiled) {
+            if (T.half & 7) copy_tile<MODE, true, true, true>(P, T, C, k, b);
+            else copy_tile<MODE, true, false, true>(P, T, C, k, b);
+        } else if (T.half & 7) { // rare: keep the tail stores out of the common loop
+            if (swap) copy_tile<MODE, true, true, false>(P, T, C, k, b);
+            else copy_tile<MODE, false, true, false>(P, T, C, k, b);
         } else {
-            if (swap) copy_tile<MODE, true, false>(P, T, C, k, b);
-            else copy_tile<MODE, false, false>(P, T, C, k, b);
+            if (swap) copy_tile<MODE, true, false, false>(P, T, C, k, b);
+            else copy_tile<MODE, false, false, false>(P, T, C, k, b);
         }
     }
 }
@@ -377,14 +441,17 @@ __device__ __forceinline__ void tile_dispatch(const FastParams &P, const FastTil
 __device__ __forceinline__ void run_tile(const FastParams &P, const FastTile &T, WarpCtx &C)
 {
     const int lane = C.lane;
-    C.tm = &P.tmap[T.tmap];
+    const bool tiled = P.ccd[T.ccd].tiled != 0;
+    C.tm = tiled ? nullptr : &P.tmap[T.tmap];
     if (lane == 0) {
-        for (int s = 0; s < C.ns; ++s) mbar_init_u32(C.bar0 + 8u * s, 1);
+        // a stage completes on the tensor copy's byte count (one arrival), or on the 32 lanes' cp.async completions
+        for (int s = 0; s < C.ns; ++s) mbar_init_u32(C.bar0 + 8u * s, tiled ? 32u : 1u);
         fence_mbar_init();
     }
     __syncwarp();
     if (T.kind == FT_EDGE) {
-        edge_tile(P, T, C);
+        if (tiled) edge_tile<true>(P, T, C);
+        else edge_tile<false>(P, T, C);
         return;
     }
     // (k,b) of the 8 detectors this lane converts, and the warp-wide RRC mode
@@ -406,9 +473,9 @@ __device__ __forceinline__ void run_tile(const FastParams &P, const FastTile &T,
     }
     const bool swap = P.ccd[T.ccd].swap != 0;
     const int mode = kbp ? (__any_sync(0xffffffffu, general) ? 2 : 1) : 0;
-    if (mode == 1) tile_dispatch<1>(P, T, C, swap, k, b);
-    else if (mode == 0) tile_dispatch<0>(P, T, C, swap, k, b);
-    else tile_dispatch<2>(P, T, C, swap, k, b);
+    if (mode == 1) tile_dispatch<1>(P, T, C, swap, tiled, k, b);
+    else if (mode == 0) tile_dispatch<0>(P, T, C, swap, tiled, k, b);
+    else tile_dispatch<2>(P, T, C, swap, tiled, k, b);
 }
 
 // MINB = CTAs per SM the register allocation must allow (4: 128 registers, 3: 168)
@@ -477,11 +544,10 @@ int fast_launch(oip_ctx *ctx, const FastParams &P, int64_t n_ctas)
     const size_t smem = (size_t)WARPS * P.n_stage * STAGE_BYTES + 128;
     if (!ctx->fast_attr_set) {
         OIP_CUDA(cudaFuncSetAttribute(pan_fast_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPS * MAX_STAGE * STAGE_BYTES + 128));
-        OIP_CUDA(cudaFuncSetAttribute(pan_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPS * MAX_STAGE * STAGE_BYTES + 128));
         ctx->fast_attr_set = true;
     }
-    if (ctx->pan_fast_minb == 3) pan_fast_kernel<3><<<(unsigned)n_ctas, WARPS * 32, smem, ctx->stream>>>(P);
-    else pan_fast_kernel<4><<<(unsigned)n_ctas, WARPS * 32, smem, ctx->stream>>>(P);
+    // (a 4-CTAs/SM, 128-register instantiation was measured in round 1: no faster, heavy spills -- dropped)
+    pan_fast_kernel<3><<<(unsigned)n_ctas, WARPS * 32, smem, ctx->stream>>>(P);
     OIP_CUDA(cudaGetLastError());
     ctx->launches++;
     return OIP_OK;

@@ -23,7 +23,7 @@ constexpr int EDGE_MAX = 29;    // EDGE: output columns per warp-tile (one per l
 struct FastTile {
     int32_t kind;     // FT_*
     int32_t ccd;
-    int32_t tmap;     // tensor map index = ccd * OIP_MAX_SEG + segment
+    int32_t tmap;     // line formats: tensor map index = ccd * OIP_MAX_SEG + segment;  tiled CCDs: sub-image column floor(box origin / tile_cols)
     int32_t x_begin;  // first CCD column produced
     int32_t half;     // EDGE: columns of the sliver (<= EDGE_MAX), any alignment, image-border columns allowed;  REMAP: columns per half (multiple of 4, <= HALF_MAX), n_cols = 2*half; COPY: n_cols (any, <= COPY_MAX)
     int32_t src_x0;   // REMAP / EDGE: source column of the first tap of x_begin (EDGE: may be < 0);  COPY: x_begin
@@ -33,10 +33,29 @@ struct FastTile {
     int64_t out_off;  // element offset in the output raster of (output row 0, x_begin)
 };
 
+// exact n / d for n < 2^32 by one multiply-high (Granlund-Montgomery round-up form): q = (t + ((n - t) >> s1)) >> s2, t = mulhi(m, n)
+struct FastDiv { uint32_t m, s1, s2, d; };
+inline FastDiv fast_div_make(uint32_t d)
+{
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    FastDiv f;
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l < 1 ? 0 : l - 1;
+    f.d = d;
+    return f;
+}
+
 struct FastCcd {
     const double *kb; // {k,b} per detector or null
     int32_t swap;     // 1: samples are big-endian
-    int32_t pad;
+    int32_t tiled;    // 1: OIP_FMT_BE16_TILES -- rows are gathered from the sub-images of the IMDT stream (ref aux_separator.h:341-372)
+    // tiled sources only
+    const uint8_t *tile_base;  // IMDT stream (4-byte aligned)
+    const int64_t *tile_off;   // [frame * 40 + r * 8 + c] byte offset of each sub-image (multiple of 4), -1 = zero-filled frame
+    int32_t tile_cols, tile_lines, n_frames, pad;
+    FastDiv div_lpf, div_tl;   // / (4 * tile_lines), / tile_lines
 };
 
 struct FastParams {

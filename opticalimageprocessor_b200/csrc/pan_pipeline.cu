@@ -621,7 +621,7 @@ struct PlanKey {
     int64_t total_rows, row0, n_rows, out_pitch;
     double dX[8], dY[8];
     // what the fast-path split depends on: eligibility per CCD, row-segment layout, tunables
-    int fast[8], n_seg[8], fast_rows;
+    int fast[8], n_seg[8], fast_rows, fmt[8], tile_cols[8], tile_lines[8];
     int64_t seg_row0[8][OIP_MAX_SEG], seg_rows[8][OIP_MAX_SEG];
 };
 
@@ -870,6 +870,12 @@ static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows
         if (a.ccd != b.ccd) return a.ccd < b.ccd;
         return a.x_begin < b.x_begin;
     });
+    for (panfast::FastTile &t : fl) { // tiled sources: the sub-image column of the stage box origin instead of a tensor map
+        const oip_ccd_src &C = d->ccd[t.ccd];
+        if (C.fmt != OIP_FMT_BE16_TILES) continue;
+        const int x0 = t.kind == panfast::FT_COPY ? t.x_begin : (t.src_x0 & ~7);
+        t.tmap = x0 >= 0 ? x0 / C.tile_cols : -((-x0 + C.tile_cols - 1) / C.tile_cols);
+    }
     ftiles = fl;
     panfast::FastTile none{};
     none.kind = panfast::FT_NONE;
@@ -960,6 +966,22 @@ static void fast_eligibility(const oip_pan_desc *d, bool enable, bool *fast_ccd)
     const bool out_ok = (((uintptr_t)d->d_out & 15) == 0) && (d->out_pitch_px % 8 == 0);
     for (int i = 0; i < d->n_ccd; ++i) {
         const oip_ccd_src &c = d->ccd[i];
+        if (c.fmt == OIP_FMT_BE16_TILES) {
+            // frame tiles: gathered by 4-byte cp.async, so stream base and every sub-image offset must be 4-byte
+            // aligned (frames are multiples of 4 bytes long: true unless the stream starts with odd junk)
+            bool ok = enable && out_ok && c.h_tile_off && c.d_tile_off && (((uintptr_t)c.d_kb & 15) == 0) && d->w >= 64 && c.n_seg == 1 &&
+                      c.seg[0].base && (((uintptr_t)c.seg[0].base & 3) == 0) && c.seg[0].row0 == 0 && c.tile_lines >= 1 &&
+                      c.tile_cols >= 2 * panfast::BOX_W /* a stage window spans at most two sub-image columns */ && (c.tile_cols & 1) == 0 && c.seg[0].n_rows > 0 && c.seg[0].n_rows < (1ll << 31);
+            if (ok) {
+                const int64_t lpf = 4ll * c.tile_lines, n_fr = (c.seg[0].n_rows + lpf - 1) / lpf;
+                for (int64_t k = 0; k < n_fr * 40 && ok; ++k) {
+                    if (k % 40 >= 32) continue; // MSS sub-images are not read here
+                    ok = c.h_tile_off[k] < 0 || (c.h_tile_off[k] & 3) == 0;
+                }
+            }
+            fast_ccd[i] = ok;
+            continue;
+        }
         bool ok = enable && out_ok && (c.fmt == OIP_FMT_LE16 || c.fmt == OIP_FMT_BE16) && (((uintptr_t)c.d_kb & 15) == 0) &&
                   d->w >= 64;
         for (int s = 0; s < c.n_seg && ok; ++s)
@@ -1022,7 +1044,8 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
     key.n_rows = d->n_rows; key.out_pitch = d->out_pitch_px; key.fast_rows = ctx->pan_fast_rows;
     for (int i = 0; i < d->n_ccd; ++i) {
         key.dX[i] = d->ccd[i].dX; key.dY[i] = d->ccd[i].dY; key.shifted[i] = d->ccd[i].shifted != 0;
-        key.fast[i] = fast_ccd[i]; key.n_seg[i] = d->ccd[i].n_seg;
+        key.fast[i] = fast_ccd[i]; key.n_seg[i] = d->ccd[i].n_seg; key.fmt[i] = d->ccd[i].fmt;
+        if (d->ccd[i].fmt == OIP_FMT_BE16_TILES) { key.tile_cols[i] = d->ccd[i].tile_cols; key.tile_lines[i] = d->ccd[i].tile_lines; }
         for (int s = 0; s < d->ccd[i].n_seg; ++s) { key.seg_row0[i][s] = d->ccd[i].seg[s].row0; key.seg_rows[i][s] = d->ccd[i].seg[s].n_rows; }
     }
     const uint8_t *kb = reinterpret_cast<const uint8_t *>(&key);
@@ -1138,11 +1161,21 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         for (int i = 0; i < d->n_ccd; ++i) {
             if (!fast_ccd[i]) continue;
             const oip_ccd_src &c = d->ccd[i];
+            F.ccd[i].kb = c.d_kb;
+            if (c.fmt == OIP_FMT_BE16_TILES) {
+                panfast::FastCcd &o = F.ccd[i];
+                o.swap = 1; o.tiled = 1;
+                o.tile_base = (const uint8_t *)c.seg[0].base; o.tile_off = c.d_tile_off;
+                o.tile_cols = c.tile_cols; o.tile_lines = c.tile_lines;
+                o.n_frames = (int32_t)((c.seg[0].n_rows + 4ll * c.tile_lines - 1) / (4ll * c.tile_lines));
+                o.div_lpf = panfast::fast_div_make(4u * (uint32_t)c.tile_lines);
+                o.div_tl = panfast::fast_div_make((uint32_t)c.tile_lines);
+                continue;
+            }
             for (int s = 0; s < c.n_seg; ++s) {
                 rc = panfast::fast_encode_tmap(&F.tmap[i * OIP_MAX_SEG + s], c.seg[s].base, d->w, c.seg[s].n_rows, c.seg[s].pitch_bytes);
                 if (rc) return rc;
             }
-            F.ccd[i].kb = c.d_kb;
             F.ccd[i].swap = c.fmt == OIP_FMT_BE16;
         }
         F.tiles = reinterpret_cast<const panfast::FastTile *>((const uint8_t *)ctx->d_plan + ctx->plan_fast_off);

@@ -149,6 +149,87 @@ def pan_pipeline_host(ctx: Context, ccds_host, kbs_host, dX, dY, fold_half: int,
     return out_host
 
 
+def frame_tile_table(ents, n_frames: int) -> np.ndarray:
+    """(n_frames, 40) int64 sub-image byte offsets from oip_image_frames_index entries (-1 rows = zero-filled gap frames)"""
+    return np.array([[ents[k].tile_off[j] for j in range(40)] for k in range(n_frames)], np.int64).reshape(n_frames, 40)
+
+
+def pan_pipeline_from_frames(ctx: Context, imdts, tables, tile_cols: int, tile_lines: int, kbs, dX, dY, fold_half: int,
+                             shifted=None, section_rows: int = SECTION_ROWS, row_guard: int = ROW_GUARD,
+                             out: Optional[torch.Tensor] = None, check_error: bool = True, keep=None):
+    """K9: the fused PAN path straight from the image frames of the IMDT streams -- no PAN raster is
+    written in between (the reference writes .PAN.RAW, ref aux_separator.h:341-372, then .RRC.RAW and .PRESTT.RAW).
+    imdts[i]: device uint8 IMDT stream of CCD i; tables[i]: frame_tile_table() of its frames (host int64 [n_frames, 40])."""
+    n = len(imdts)
+    n_frames = min(t.shape[0] for t in tables)
+    rows = n_frames * 4 * tile_lines
+    w = 8 * tile_cols
+    if shifted is None:
+        shifted = [i > 0 for i in range(n)]
+    if out is None:
+        out = torch.empty((rows, pan_out_width(n, w, fold_half)), dtype=torch.uint16, device=imdts[0].device)
+    d = PanDesc()
+    d.n_ccd, d.w, d.total_rows, d.row0, d.n_rows = n, w, rows, 0, rows
+    d.fold_half, d.section_rows, d.row_guard = fold_half, section_rows, row_guard
+    hold = [] if keep is None else keep
+    for i in range(n):
+        c = d.ccd[i]
+        c.fmt, c.n_seg = FMT_BE16_TILES, 1
+        c.seg[0] = RowSeg(imdts[i].data_ptr(), 0, rows, 0)
+        c.d_kb = _ptr(kbs[i]) if kbs is not None and kbs[i] is not None else None
+        c.shifted, c.dX, c.dY = int(bool(shifted[i])), float(dX[i]), float(dY[i])
+        h_tab = np.ascontiguousarray(tables[i][:n_frames], np.int64)
+        d_tab = torch.from_numpy(h_tab).to(imdts[i].device)
+        hold += [h_tab, d_tab]
+        c.d_tile_off, c.h_tile_off, c.tile_cols, c.tile_lines = d_tab.data_ptr(), h_tab.ctypes.data, tile_cols, tile_lines
+    d.d_out, d.out_pitch_px = out.data_ptr(), out.stride(0)
+    check(ctx.lib.oip_pan_pipeline(ctx.h, C.byref(d)))
+    if check_error or keep is None:
+        check(ctx.lib.oip_pan_check_error(ctx.h))   # synchronises: the tables may be released afterwards
+    return out, d
+
+
+def downlink_to_stitched(ctx: Context, files, tile_cols: int, tile_lines: int, kbs, dX, dY, fold_half: int, shifted=None,
+                         section_rows: int = SECTION_ROWS, row_guard: int = ROW_GUARD, out: Optional[torch.Tensor] = None,
+                         want_aux: bool = False, want_mss: bool = False):
+    """raw downlink files (device uint8 tensors, one per CCD) -> stitched PAN raster in ONE call: AOS scan + CRC, IMTR
+    re-framing, image-frame index, then the fused RRC + shift + stitch reading the sub-images where they lie
+    (oip_downlink_to_stitched).  Returns (out[:rows], stats list, aux list, mss list)."""
+    from .capi import DownlinkDesc, DownlinkStats
+    n = len(files)
+    w = 8 * tile_cols
+    if shifted is None:
+        shifted = [i > 0 for i in range(n)]
+    # lines: bounded by the payload the smallest file can carry
+    frame_bytes = 192 * tile_lines + 40 * tile_lines * tile_cols * 2 + 172
+    cap_rows = (min(f.numel() for f in files) // frame_bytes + 1) * 4 * tile_lines
+    if out is None:
+        out = torch.empty((cap_rows, pan_out_width(n, w, fold_half)), dtype=torch.uint16, device=files[0].device)
+    d = DownlinkDesc()
+    d.n_ccd, d.geom = n, FrameGeom(tile_cols, tile_lines)
+    d.fold_half, d.section_rows, d.row_guard = fold_half, section_rows, row_guard
+    aux, mss = [None] * n, [None] * n
+    for i in range(n):
+        c = d.ccd[i]
+        c.d_file, c.n_bytes = files[i].data_ptr(), files[i].numel()
+        c.d_kb = _ptr(kbs[i]) if kbs is not None and kbs[i] is not None else None
+        c.shifted, c.dX, c.dY = int(bool(shifted[i])), float(dX[i]), float(dY[i])
+        if want_aux:
+            aux[i] = torch.zeros((cap_rows // (4 * tile_lines), 192 * tile_lines), dtype=torch.uint8, device=files[i].device)
+            d.d_aux[i] = aux[i].data_ptr()
+        if want_mss:
+            mss[i] = torch.zeros((cap_rows // 4, w), dtype=torch.uint16, device=files[i].device)
+            d.d_mss[i] = mss[i].data_ptr()
+    d.d_out, d.out_pitch_px, d.out_rows_cap = out.data_ptr(), out.stride(0), out.shape[0]
+    rows = C.c_int64(0)
+    st = (DownlinkStats * n)()
+    check(ctx.lib.oip_downlink_to_stitched(ctx.h, C.byref(d), C.byref(rows), st))
+    r = int(rows.value)
+    nf = r // (4 * tile_lines)
+    stats = [dict(aos=list(s.aos), imtr=list(s.imtr), frames=list(s.frames), imdt_bytes=int(s.imdt_bytes)) for s in st]
+    return out[:r], stats, [a[:nf] if a is not None else None for a in aux], [m[:nf * tile_lines] if m is not None else None for m in mss]
+
+
 def inplace_rrc(ctx: Context, img: torch.Tensor, kb: torch.Tensor) -> torch.Tensor:
     h, w = img.shape
     check(ctx.lib.oip_rrc_u16(ctx.h, img.data_ptr(), w, h, img.stride(0), kb.data_ptr()))
@@ -282,11 +363,17 @@ def imtr_deframe(ctx: Context, buf: torch.Tensor, payload_off: torch.Tensor):
 def image_frames_index(ctx: Context, imdt: torch.Tensor, tile_cols: int, tile_lines: int):
     g = FrameGeom(tile_cols, tile_lines)
     st = (C.c_int64 * 4)()
-    # first pass counts the emitted frames (gap frames included), second fills the table
-    check(ctx.lib.oip_image_frames_index(ctx.h, imdt.data_ptr(), imdt.numel(), C.byref(g), None, 0, st))
-    cap = max(1, int(st[1]))
+    # ONE pass: the table is sized for every complete frame the stream can hold (+ slack for zero-filled gap frames);
+    # only a stream with long sequence gaps needs the second call
+    frame_bytes = 192 * tile_lines + 40 * tile_lines * tile_cols * 2 + 172
+    cap = imdt.numel() // frame_bytes + 64
     ents = (FrameEntry * cap)()
-    check(ctx.lib.oip_image_frames_index(ctx.h, imdt.data_ptr(), imdt.numel(), C.byref(g), ents, cap, st))
+    rc = ctx.lib.oip_image_frames_index(ctx.h, imdt.data_ptr(), imdt.numel(), C.byref(g), ents, cap, st)
+    if rc == capi.OIP_E_INVALID and st[1] > cap:
+        cap = int(st[1])
+        ents = (FrameEntry * cap)()
+        rc = ctx.lib.oip_image_frames_index(ctx.h, imdt.data_ptr(), imdt.numel(), C.byref(g), ents, cap, st)
+    check(rc)
     return ents, np.array(list(st), np.int64)
 
 

@@ -211,6 +211,75 @@ def test_fused_pipeline_from_frame_tiles(ctx, oracle_mod):
     assert np.array_equal(out.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("tc,tl,n_fr,junk,skip,f", [(64, 8, 6, 4, (), 10), (288, 8, 5, 0, (3,), 20), (320, 64, 3, 8, (), 100),
+                                                  (272, 8, 6, 3, (), 10), (1024, 16, 2, 12, (), 100), (1536, 8, 3, 4, (2,), 100)])
+def test_fused_fast_path_from_frame_tiles(ctx, oracle_mod, tc, tl, n_fr, junk, skip, f):
+    """K9: the fast kernel gathers its stage rows straight from the sub-images (4-byte cp.async + mbarrier), windows
+    that straddle sub-image columns / rows / frames, a zero-filled gap frame, and a stream whose junk prefix leaves the
+    frames unaligned (-> generic kernel); always bit-identical to the oracle on the reassembled PAN strips"""
+    import ctypes as C
+    from opticalimageprocessor_b200 import capi, ops
+    W = 8 * tc
+    streams, pans, tabs = [], [], []
+    for i in range(3):
+        imdt, truth = synth.make_imdt(n_fr, tc, tl, seed=40 + i, junk_prefix=junk, skip_seqs=set(skip), max_dn=65536 if i == 1 else 4096)
+        d = _dev(imdt)
+        ents, st = ops.image_frames_index(ctx, d, tc, tl)
+        assert st[1] == n_fr
+        tabs.append(ops.frame_tile_table(ents, n_fr))
+        streams.append(d)
+        pans.append(np.concatenate([truth[s][1] if s in truth else np.zeros((4 * tl, W), np.uint16) for s in range(1, n_fr + 1)]))
+    kbs = [synth.rrc_coeffs(W, 77 + i) for i in range(3)]
+    dX, dY = [0, 1.37, -0.83], [0, -2.61, 3.19]
+    S, G = (30000, 32767) if n_fr * 4 * tl < 400 else (150, 160)
+    want = oracle_mod.pan_pipeline(pans, kbs, dX, dY, f, S, G)
+    keep = []
+    got, desc = ops.pan_pipeline_from_frames(ctx, streams, tabs, tc, tl, [_dev(k) for k in kbs], dX, dY, f, section_rows=S, row_guard=G,
+                                             keep=keep)
+    st = (C.c_int64 * 4)()
+    capi.check(ctx.lib.oip_pan_plan_coverage(C.byref(desc), 1, 128, None, st))
+    if junk % 4 == 0 and tc >= 272:   # 4-byte aligned frames, a stage window spans at most two sub-image columns
+        assert st[1] > 0.9 * (st[0] + st[1]), f"fast kernel share {st[1]} of {st[0] + st[1]} px"
+    else:
+        assert st[1] == 0
+    bad = np.argwhere(got.cpu().numpy() != want)
+    assert bad.size == 0, f"{len(bad)} px differ, first {bad[:5].tolist()}"
+
+
+@pytest.mark.parametrize("tc,tl,n_fr,skip", [(64, 8, 6, ()), (288, 16, 4, (2,))])
+def test_downlink_to_stitched_matches_oracle_chain(ctx, oracle_mod, tc, tl, n_fr, skip):
+    """oip_downlink_to_stitched: AOS files in, stitched PAN raster (+ aux, MSS) out, against the oracle's chain
+    aos_scan -> imtr_deframe -> image_frames -> pan_pipeline; empty frames, a corrupted duplicate and a bad inject word in
+    every downlink, a zero-filled gap frame in the second case"""
+    from opticalimageprocessor_b200 import ops
+    W, f = 8 * tc, 12
+    files, pans, auxs, msss = [], [], [], []
+    for i in range(3):
+        imdt, _ = synth.make_imdt(n_fr, tc, tl, seed=60 + i, skip_seqs=set(skip), max_dn=4096 if i else 65536)
+        aos = synth.build_aos_file(synth.aos_frames(synth.imtr_frames(imdt, chid=0x11 + 0x11 * (i & 1)).reshape(-1)), empty_every=7 + i,
+                                   bad_crc_at={3, 50 + i}, bad_inject_at={9}, prefix=b"\x00" * (5 * i))
+        off, cnt = oracle_mod.aos_scan(aos)
+        stream, st = oracle_mod.imtr_deframe(aos, off)
+        n, aux, pan, mss, fst = oracle_mod.image_frames(stream, tc, tl)
+        assert n == n_fr
+        files.append(_dev(aos)); pans.append(pan); auxs.append(aux); msss.append(mss)
+    kbs = [synth.rrc_coeffs(W, 90 + i) for i in range(3)]
+    dX, dY = [0, 1.37, -0.83], [0, -2.61, 3.19]
+    S, G = 150, 160
+    want = oracle_mod.pan_pipeline(pans, kbs, dX, dY, f, S, G)
+    l0 = ctx.launches
+    got, stats, aux_g, mss_g = ops.downlink_to_stitched(ctx, files, tc, tl, [_dev(k) for k in kbs], dX, dY, f, section_rows=S, row_guard=G,
+                                                        want_aux=True, want_mss=True)
+    ctx.sync()
+    assert ctx.launches > l0
+    assert got.shape == want.shape
+    bad = np.argwhere(got.cpu().numpy() != want)
+    assert bad.size == 0, f"{len(bad)} px differ, first {bad[:5].tolist()}"
+    for i in range(3):
+        assert stats[i]["frames"][1] == n_fr and stats[i]["aos"][1] >= 1 and stats[i]["aos"][2] >= 1
+        assert np.array_equal(aux_g[i].cpu().numpy(), auxs[i]) and np.array_equal(mss_g[i].cpu().numpy(), msss[i])
+
+
 @pytest.mark.parametrize("bits", [10, 12])
 def test_packed_lines_extension(ctx, oracle_mod, bits):
     from opticalimageprocessor_b200 import ops

@@ -350,7 +350,7 @@ def test_capi_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/oip_b200.h but not exported"
         assert name in capi.SYMBOLS, f"{name} has no ctypes prototype"
-    assert L.oip_abi_version() == 1
+    assert L.oip_abi_version() == 2
 
 
 def test_capi_fails_loudly_without_gpu():
