@@ -322,6 +322,232 @@ __global__ void __launch_bounds__(AOS_T, 6) aos_scan_kernel(const uint8_t *__res
     }
 }
 
+// =============================================================================================
+// AOS, fused single pass (round 2): sync check + header rules + CRC of 32 consecutive frames per warp, every file byte
+// read at most once.
+//
+// The reference scan (ref aux_separator.h:421-461) jumps from an accepted frame straight to its end, so the bytes INSIDE
+// an accepted frame are never searched.  A downlink is a run of back-to-back 1024-byte frames: with the phase of that
+// cadence known (first sync word of the file), a warp takes the 32 slots of a 32 KiB group and
+//   * checks the sync word at every slot start; if one is missing the cadence is broken here and the group is searched
+//     byte by byte like aos_scan_kernel does (slow path, exact for any input);
+//   * evaluates ValidateAosFrame for all 32 slots: header rules from the first words, the 32 CRCs bit-sliced with
+//     word-interleaved pieces straight from global memory (the 128-byte LDPC tail of a frame is not even read);
+//   * searches the interior of every slot that is NOT valid (empty, bad inject word, bad CRC): the reference advances by
+//     4 bytes there and goes on searching, so false sync words inside such a frame are candidates.
+// The candidates go to the same table the general kernels use (order / runstart / walk / emit below).  One case is left
+// to the general path: a VALID slot that the walk finds shadowed by an overlapping accepted frame -- its interior was
+// not searched although the reference's scan continues inside it.  aos_walk_kernel flags it and the host repeats the
+// call with the exhaustive search (two valid frames that overlap need a CRC collision: never seen, still exact).
+// =============================================================================================
+constexpr int GRP = 32 * 1024;      // bytes per group: 32 slots
+constexpr int AOS_F_WARPS = 4;
+
+__global__ void aos_phase_kernel(const uint8_t *__restrict__ buf, int64_t n, uint32_t *phase)
+{
+    // first sync word that leaves room for a frame, within the first 64 KiB (else: no cadence assumed, phase 0)
+    const int64_t lim = min((int64_t)65536, n - 1023);
+    uint32_t best = 0xFFFFFFFFu;
+    for (int64_t p = (int64_t)threadIdx.x * 256; p < lim && best == 0xFFFFFFFFu; p += (int64_t)blockDim.x * 256)
+        for (int64_t q = p; q < min(p + 256, lim); ++q)
+            if (buf[q] == 0x1A && buf[q + 1] == 0xCF && buf[q + 2] == 0xFC && buf[q + 3] == 0x1D) { best = (uint32_t)q; break; }
+    if (best != 0xFFFFFFFFu) atomicMin(phase, best);
+}
+
+// sync hits among the file positions [row + lo, row + hi) of one 1024-byte row, with p + 1024 <= n: lane l owns the
+// positions 32l .. 32l+31 and returns their hit mask
+__device__ __forceinline__ uint32_t aos_row_hits(const uint8_t *__restrict__ buf, int64_t n, int64_t row, int lo, int hi)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t p0 = row + 32 * lane;
+    uint32_t w[9];
+    if (((((uintptr_t)buf) + p0) & 3) == 0 && p0 + 36 <= n) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = __ldg(reinterpret_cast<const uint32_t *>(buf + p0) + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int64_t q = p0 + 4 * k + b;
+                v |= (uint32_t)(q >= 0 && q < n ? buf[q] : 0) << (8 * b);
+            }
+            w[k] = v;
+        }
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t x = w[k] ^ 0x1A1A1A1Au;
+        any |= (x - 0x01010101u) & ~x;
+    }
+    uint32_t mask = 0;
+    if (any & 0x80808080u) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int pos = 32 * lane + 4 * k + b;
+                if (__funnelshift_r(w[k], w[k + 1], 8 * b) == 0x1DFCCF1Au && pos >= lo && pos < hi && row + pos + 1024 <= n)
+                    mask |= 1u << (4 * k + b);
+            }
+    }
+    return mask;
+}
+// ValidateAosFrame without the CRC (ref aux_separator.h:658-677): -1 invalid, 0 empty, 2 = "the CRC decides"
+__device__ __forceinline__ int aos_rules(const uint8_t *f)
+{
+    const uint32_t vcid = f[5] & 0x3F;
+    const uint32_t injw = ((uint32_t)f[10] << 24) | ((uint32_t)f[11] << 16) | ((uint32_t)f[12] << 8) | f[13];
+    if (injw != 0xAAAAAAAAu && injw != 0u) return -1;
+    if (injw == 0xAAAAAAAAu && vcid == 0x3F) return 0;
+    return 2;
+}
+// emit this lane's hits of one row in file order at table position `at` (warp-wide exclusive prefix); returns the count
+__device__ __forceinline__ uint32_t aos_emit_row(const uint8_t *__restrict__ buf, int64_t row, uint32_t mask, uint32_t at, uint32_t cap,
+                                                 uint64_t *cand_off, int8_t *cand_st)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t c = __popc(mask);
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, x, 31);
+    uint32_t k = at + x - c;
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int64_t p = row + 32 * lane + b;
+        if (k < cap) {
+            cand_off[k] = (uint64_t)p;
+            cand_st[k] = (int8_t)aos_rules(buf + p);
+        }
+        ++k;
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(AOS_F_WARPS * 32) aos_fused_kernel(const uint8_t *__restrict__ buf, int64_t n, const uint32_t *__restrict__ phase_ptr,
+                                                                      int64_t n_groups, uint32_t *cursor, uint32_t cap, ChunkInfo *info,
+                                                                      uint64_t *cand_off, int8_t *cand_st)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * AOS_F_WARPS + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    const uint32_t ph = *phase_ptr;
+    const int64_t phase = ph == 0xFFFFFFFFu ? 0 : (int64_t)ph;
+    const int64_t g0 = phase + g * GRP;                       // first byte of the group = start of slot 0
+    if (g0 >= n && g > 0) {                                   // (the grid is sized for phase 0)
+        if (lane == 0) { info[g].slot0 = 0; info[g].count = 0; }
+        return;
+    }
+    bool fast = g0 + GRP + 4 <= n;                            // 32 whole slots (and the word after them is readable)
+    uint32_t nonvalid = 0;
+    int st = 0;
+    if (fast) {
+        // ---- 32 slots: sync word, header rules, bit-sliced CRC over message + stored CRC (frame bytes 4..895: the
+        //      remainder is zero exactly when the stored CRC matches; the 896-byte span starts AT the frame)
+        const uint8_t *A = buf + g0 + 4 * lane;
+        const uint32_t sh = (uint32_t)((uintptr_t)A & 3u);
+        const uint32_t *W = reinterpret_cast<const uint32_t *>(A - sh);
+        uint32_t m_sync = 0, m_a = 0, m_b = 0;                 // per-lane predicates over the 32 frames (bit q = frame q)
+        uint32_t P[16];
+        bitslice::warp_crc32frames_interleaved(
+            [&](int j, uint32_t(&T)[32]) {
+                const uint32_t *w = W + 32 * j;
+                if (sh) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) T[q] = __funnelshift_r(__ldg(w + 256 * q), __ldg(w + 256 * q + 1), 8u * sh);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) T[q] = __ldg(w + 256 * q);
+                }
+                if (j == 0) {
+                    // lane 0 holds word 0 (sync), lane 1 word 1 (byte 5 = VCID), lanes 2 / 3 words 2 / 3 (bytes 10..13 = inject word)
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const uint32_t t = T[q];
+                        const uint32_t hi16 = t >> 16, lo16 = t & 0xFFFFu;
+                        bool s, a, b;
+                        if (lane == 0) { s = t == 0x1DFCCF1Au; a = b = false; }
+                        else if (lane == 1) { s = ((t >> 8) & 0x3Fu) == 0x3Fu; a = b = false; }
+                        else if (lane == 2) { s = false; a = hi16 == 0u; b = hi16 == 0xAAAAu; }
+                        else { s = false; a = lo16 == 0u; b = lo16 == 0xAAAAu; }
+                        m_sync |= (uint32_t)s << q; m_a |= (uint32_t)a << q; m_b |= (uint32_t)b << q;
+                    }
+                }
+            },
+            bitslice::SPAN - 892, P);
+        const uint32_t sync_all = __shfl_sync(0xffffffffu, m_sync, 0);
+        if (sync_all != 0xFFFFFFFFu) {
+            fast = false;                                       // a slot start without sync word: cadence broken in this group
+        } else {
+            const uint32_t vc3f = __shfl_sync(0xffffffffu, m_sync, 1);
+            const uint32_t inj0 = __shfl_sync(0xffffffffu, m_a, 2) & __shfl_sync(0xffffffffu, m_a, 3);
+            const uint32_t injA = __shfl_sync(0xffffffffu, m_b, 2) & __shfl_sync(0xffffffffu, m_b, 3);
+            const bool invalid = !(((inj0 | injA) >> lane) & 1u);                      // :675
+            const bool empty = !invalid && ((injA >> lane) & 1u) && ((vc3f >> lane) & 1u); // :676
+            const bool crc_ok = (bitslice::unslice(P, lane) ^ bitslice::init_term(892)) == 0u;
+            st = invalid ? -1 : (empty ? 0 : (crc_ok ? 1 : -1));                        // :679-686
+            nonvalid = __ballot_sync(0xffffffffu, st != 1);
+        }
+    }
+    if (fast) {
+        // ---- interiors of the slots that are not valid (the scan goes on at slot + 4)
+        uint32_t extra = 0, has_hits = 0;
+        for (uint32_t m = nonvalid; m; m &= m - 1) {
+            const int q = __ffs(m) - 1;
+            const uint32_t hm = aos_row_hits(buf, n, g0 + 1024 * q, 4, 1024);
+            const uint32_t c = __reduce_add_sync(0xffffffffu, __popc(hm));
+            extra += c;
+            if (c) has_hits |= 1u << q;
+        }
+        const uint32_t total = 32u + extra;
+        uint32_t slot0 = 0;
+        if (lane == 0) {
+            slot0 = atomicAdd(cursor, total);
+            info[g].slot0 = slot0;
+            info[g].count = total;
+        }
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if ((uint64_t)slot0 + total > cap) return;             // table too small: the host re-runs with the exact size
+        if (!has_hits) {
+            cand_off[slot0 + lane] = (uint64_t)(g0 + 1024 * lane);
+            cand_st[slot0 + lane] = (int8_t)st;
+        } else {
+            uint32_t at = slot0;
+            for (int q = 0; q < 32; ++q) {
+                const int sq = __shfl_sync(0xffffffffu, st, q);
+                if (lane == 0) { cand_off[at] = (uint64_t)(g0 + 1024 * q); cand_st[at] = (int8_t)sq; }
+                ++at;
+                if ((has_hits >> q) & 1u) at += aos_emit_row(buf, g0 + 1024 * q, aos_row_hits(buf, n, g0 + 1024 * q, 4, 1024), at, cap, cand_off, cand_st);
+            }
+        }
+        return;
+    }
+    // ---- slow path: every position of the group (the last, partial group; a group where the cadence is broken; a file
+    //      without cadence).  Group 0 also owns the bytes in front of the phase (none of them starts a sync word).
+    const int64_t lo_byte = g == 0 ? 0 : g0, hi_byte = min(n, g0 + GRP);
+    uint32_t total = 0;
+    for (int64_t row = lo_byte; row < hi_byte; row += 1024)
+        total += __reduce_add_sync(0xffffffffu, __popc(aos_row_hits(buf, n, row, 0, (int)min((int64_t)1024, hi_byte - row))));
+    uint32_t slot0 = 0;
+    if (lane == 0) {
+        slot0 = total ? atomicAdd(cursor, total) : 0;
+        info[g].slot0 = slot0;
+        info[g].count = total;
+    }
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (!total || (uint64_t)slot0 + total > cap) return;
+    uint32_t at = slot0;
+    for (int64_t row = lo_byte; row < hi_byte; row += 1024)
+        at += aos_emit_row(buf, row, aos_row_hits(buf, n, row, 0, (int)min((int64_t)1024, hi_byte - row)), at, cap, cand_off, cand_st);
+}
+
 // ---- CRC of the candidates that need one (ref aux_separator.h:679-686), on the file-ordered table: a warp takes 32
 // consecutive candidates.  32 frames back to back (the normal case) are bit-sliced straight from global memory with
 // word-interleaved pieces: lane l reads word l of each 128-byte block of the 896-byte span that ends with the last
@@ -417,7 +643,7 @@ __global__ void aos_runstart_kernel(const uint64_t *off, const int8_t *st, const
 // each run start replays the reference's skip rules up to the next run start:
 // accepted frame -> next search position = off+1024; rejected candidate -> off+4 (:440-441,:456-457)
 __global__ void aos_walk_kernel(const uint64_t *off, const int8_t *st, const uint8_t *rs, const uint32_t *m_ptr, uint32_t *acc,
-                                unsigned long long *counters)
+                                unsigned long long *counters, uint32_t *shadowed_valid)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t m = (int64_t)*m_ptr;
@@ -432,7 +658,13 @@ __global__ void aos_walk_kernel(const uint64_t *off, const int8_t *st, const uin
             j = i + 1;
         }
         for (; j < m && !rs[j]; ++j) {
-            if (off[j] < next_free) { acc[j] = 0; continue; } // inside an accepted frame: never seen
+            if (off[j] < next_free) { // inside an accepted frame: never seen
+                acc[j] = 0;
+                // a VALID frame shadowed by an overlapping accepted one: the scan continues INSIDE it, where the fused
+                // kernel did not search (see aos_fused_kernel) -> the host repeats the call with the exhaustive search
+                if (st[j] == 1) *shadowed_valid = 1u;
+                continue;
+            }
             if (st[j] == 1) {
                 acc[j] = 1;
                 n_val++;
@@ -513,6 +745,9 @@ __device__ __forceinline__ bool seg_straddles(const FrameSegs &S, int q)
     return (q < S.l0 && q + 3 >= S.l0) || (q < S.l0 + 880 && q + 3 >= S.l0 + 880);
 }
 
+// (Round 2 measured a warp-private form -- every warp gathers and validates its own 32 frames, 28.8 KB of shared memory per warp,
+// 7 warps per SM, loads of 4 frames in flight: 0.9 ms per 810 MB file against 0.69 ms for this one; too few warps to
+// hide the latency of the gather, 500 instructions per frame.  Kept: this form.)
 // A CTA validates 32 consecutive frames: its 4 warps gather 8 frames each into shared memory (896-byte slots), then
 // warp 0 runs ValidateImtrFrame for all of them, lane f = frame f, with the CRCs of the 32 frames bit-sliced.
 constexpr int IMTR_T = 128, IMTR_BATCH = 32, IMTR_SLOT = 896, IMTR_FRONT = 32;
@@ -524,24 +759,60 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_kernel(const uint8_t *__
     __shared__ __align__(16) uint32_t s_w[(IMTR_FRONT + IMTR_BATCH * IMTR_SLOT + 32) / 4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t f0 = (int64_t)blockIdx.x * IMTR_BATCH;
+    // payload offsets of the whole batch in ONE round trip (every warp keeps its own copy in two registers per lane): the
+    // 32 frames span payloads i0 .. i0+33 (+2 for the run tails), handed out by shuffles -- no dependent load per frame
+    const int64_t s_first = f0 * 882;
+    const int64_t i0 = s_first / 880;
+    const int o0 = (int)(s_first - i0 * 880);
+    const unsigned long long pl0 = poff[min(i0 + lane, n_payload - 1)], pl1 = poff[min(i0 + 32 + lane, n_payload - 1)];
+    auto payload = [&](int k) -> const uint8_t * { // payload i0 + k (the index is clamped to the last one like frame_segs does)
+        const unsigned long long a = __shfl_sync(0xffffffffu, pl0, k & 31), b2 = __shfl_sync(0xffffffffu, pl1, k & 31);
+        return buf + (k < 32 ? a : b2);
+    };
     for (int q = wid; q < IMTR_BATCH; q += IMTR_T / 32) {
         if (f0 + q >= n_frames) break;
         uint32_t *fw = s_w + (IMTR_FRONT + q * IMTR_SLOT) / 4;
-        const FrameSegs S = frame_segs(buf, poff, n_payload, (f0 + q) * 882);
+        FrameSegs S;
+        {
+            const int t = o0 + 882 * q, k = t / 880, o = t - 880 * k;   // frame q starts o bytes into payload i0 + k
+            S.l0 = 880 - o;
+            S.p0 = payload(k) + o;
+            S.p1 = i0 + k + 1 < n_payload ? payload(k + 1) : S.p0;
+            S.p2 = i0 + k + 2 < n_payload ? payload(k + 2) : S.p1;
+        }
         // (splitting this loop into a load pass over the warp's 8 frames and a fix-up / output pass was measured: slower)
-        uint32_t v[7]; // 220 whole words + 2 bytes; all of a lane's loads are issued before the first store
+        // 220 whole words + 2 bytes.  ALL loads of the frame are issued before the first use of a loaded value (the raw
+        // word pairs and the fix-up bytes stay in registers; the funnel shifts come afterwards): one memory round trip per
+        // frame.  (Round 1 shifted each word right after its two loads and the compiler kept that order: seven dependent
+        // round trips per frame -- the critical path of the CTA, ncu: long-scoreboard stalls on every SHF.)
+        uint32_t lo[7], hi[7], shv[7], fxb[4];
 #pragma unroll
-        for (int u = 0; u < 7; ++u) v[u] = seg_word(S, 4 * min(lane + 32 * u, 219));
+        for (int u = 0; u < 7; ++u) {
+            const uint8_t *a = seg_ptr(S, 4 * min(lane + 32 * u, 219));
+            const uint32_t sh = (uint32_t)((uintptr_t)a & 3u);
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(a - sh);
+            lo[u] = __ldg(w);
+            hi[u] = __ldg(w + (sh ? 1 : 0));
+            shv[u] = 8u * sh;
+        }
+        {   // lanes 0 / 1: the word across the first / second run boundary; lane 2: the last two bytes (others: a harmless reload)
+            const int bnd = lane == 0 ? S.l0 : (lane == 1 ? S.l0 + 880 : 880);
+            const int qb = min(bnd & ~3, 880);
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) fxb[bb] = (uint32_t)__ldg(seg_ptr(S, min(qb + bb, 881)));
+        }
 #pragma unroll
         for (int u = 0; u < 7; ++u)
-            if (lane + 32 * u < 220) fw[lane + 32 * u] = v[u];
+            if (lane + 32 * u < 220) fw[lane + 32 * u] = __funnelshift_r(lo[u], hi[u], shv[u]);
         __syncwarp();
-        // the (at most two) words across a run boundary, and the last two bytes
-        if (lane < 2) {
-            const int b = lane == 0 ? S.l0 : S.l0 + 880;
-            if ((b & 3) && b < 880) fw[b >> 2] = seg_word_bytes(S, b & ~3, 4);
-        } else if (lane == 2) {
-            fw[220] = seg_word_bytes(S, 880, 2);
+        {
+            const uint32_t fx = fxb[0] | (fxb[1] << 8) | (fxb[2] << 16) | (fxb[3] << 24);
+            if (lane < 2) {
+                const int b = lane == 0 ? S.l0 : S.l0 + 880;
+                if ((b & 3) && b < 880) fw[b >> 2] = fx;
+            } else if (lane == 2) {
+                fw[220] = fx & 0xFFFFu;
+            }
         }
         if (imdt_spec) {
             // speculative output: in a clean downlink every frame is valid and frame f's 866 payload bytes (frame bytes
@@ -566,7 +837,57 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_kernel(const uint8_t *__
         }
     }
     __syncthreads();
+    // ---- CRCs of the 32 frames, bit-sliced (lane l = the 28-byte piece l of every frame, bit f of a register = frame f).
+    //      The seven words of a piece are split over the FOUR warps (0-1, 2-3, 4-5, 6): each warp runs its words from a
+    //      zero remainder and advances the result to the end of the piece (x^(32 * words after it), a fixed XOR
+    //      network); the partial remainders are added in shared memory.  (Round 1: one warp ran all seven words while
+    //      the other three had nothing left to do -- the validating warp was the critical path of the CTA.)
+    // :577-583 CRC over bytes 0..875: the 896-byte span ends with byte 875, i.e. starts 20 bytes before the frame
+    // (whatever the previous slot left there: lane 0 drops it).  Slots and pieces are word aligned.
+    __shared__ uint32_t s_part[4][16][32];
+    uint32_t P[16];
+    {
+        const uint32_t B = smem_u32(s_w) + (uint32_t)(IMTR_FRONT - (bitslice::SPAN - 876) + 28 * lane);
+        const int clear_bit = lane == 0 ? 8 * (bitslice::SPAN - 876) : -1; // lane 0: the 20 bytes in front of the frame
+        const int jlo = 2 * wid, jhi = min(2 * wid + 2, 7);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P[i] = 0u;
+#pragma unroll 1
+        for (int j = jlo; j < jhi; ++j) {
+            uint32_t T[32];
+            const uint32_t a = B + 4u * (uint32_t)j;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) T[q] = lds_u32(a + (uint32_t)(IMTR_SLOT * q));
+            bitslice::transpose32(T);
+            bitslice::lfsr_word(P, T, clear_bit - 32 * j);
+        }
+        if (lane == 0 && 32 * jhi <= 8 * (bitslice::SPAN - 876)) { // only bytes in front of the frame so far
+#pragma unroll
+            for (int i = 0; i < 16; ++i) P[i] = 0u;
+        }
+        uint32_t Q[16];
+        if (wid == 0) bitslice::mul_xpow<160>(P, Q);
+        else if (wid == 1) bitslice::mul_xpow<96>(P, Q);
+        else if (wid == 2) bitslice::mul_xpow<32>(P, Q);
+        else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) Q[i] = P[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s_part[wid][i][lane] = Q[i];
+    }
+    __syncthreads();
     if (wid != (int)(blockIdx.x & 3)) return; // rotate the validating warp over the SM's four schedulers
+#pragma unroll
+    for (int i = 0; i < 16; ++i) P[i] = s_part[0][i][lane] ^ s_part[1][i][lane] ^ s_part[2][i][lane] ^ s_part[3][i][lane];
+    {
+        auto x = [](uint32_t v, int sd, int) { return __shfl_xor_sync(0xffffffffu, v, sd); };
+        bitslice::join_level<1>(P, lane, x);
+        bitslice::join_level<2>(P, lane, x);
+        bitslice::join_level<4>(P, lane, x);
+        bitslice::join_level<8>(P, lane, x);
+        bitslice::join_level<16>(P, lane, x);
+    }
     // ValidateImtrFrame, checks in the reference's order (ref aux_separator.h:558-590)
     const uint32_t *fw = s_w + (IMTR_FRONT + lane * IMTR_SLOT) / 4;
     const uint8_t *fr = reinterpret_cast<const uint8_t *>(fw);
@@ -574,17 +895,6 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_kernel(const uint8_t *__
     if (fw[0] != 0x1FCE5449u) st = 1;                                                                // :559  49 54 CE 1F
     else if (!(fr[878] == 0x2E && fr[879] == 0xE9 && fr[880] == 0xC8 && fr[881] == 0xFD)) st = 2;     // :563
     else if (fr[9] != 0x22) st = 3;                                                                  // :572
-    // :577-583 CRC over bytes 0..875: the 896-byte span ends with byte 875, i.e. starts 20 bytes before the frame
-    // (whatever the previous slot left there: lane 0 drops it).  Slots and pieces are word aligned.
-    const uint32_t B = smem_u32(s_w) + (uint32_t)(IMTR_FRONT - (bitslice::SPAN - 876) + 28 * lane);
-    uint32_t P[16];
-    bitslice::warp_crc32frames(
-        [&](int j, uint32_t(&T)[32]) {
-            const uint32_t a = B + 4u * (uint32_t)j;
-#pragma unroll
-            for (int q = 0; q < 32; ++q) T[q] = lds_u32(a + (uint32_t)(IMTR_SLOT * q));
-        },
-        bitslice::SPAN - 876, P);
     const uint32_t want = ((uint32_t)fr[876] << 8) | fr[877];
     if (st == 0 && (bitslice::unslice(P, lane) ^ bitslice::init_term(876)) != want) st = 4;
     const int64_t f = f0 + lane;
@@ -848,11 +1158,12 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
     static const CrcPlan plan = make_crc_plan(890);
 
     uint32_t cand_cap = (uint32_t)std::min<int64_t>(n / 4 + 1, n / 512 + 4096);
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    bool fused = ctx->aos_fused != 0;
+    for (int attempt = 0; attempt < 3; ++attempt) {
         // scratch layout
         size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-        const size_t o_hdr = take(64);                       // cursor(u32) | total(u32) | counters(3 x u64) | acc_total
+        const size_t o_hdr = take(64);                       // cursor(u32) | total(u32) | counters(3 x u64) | .. | acc_total @40 | phase @44 | shadowed @48
         const size_t o_info = take((size_t)n_chunks * sizeof(ChunkInfo));
         const size_t o_cnt = take((size_t)n_chunks * 4);
         const size_t o_base = take((size_t)n_chunks * 4);
@@ -871,13 +1182,26 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
         uint32_t *d_total = d_cursor + 1;
         unsigned long long *d_counters = (unsigned long long *)(S + o_hdr + 8);
         uint32_t *d_acc_total = (uint32_t *)(S + o_hdr + 40);
+        uint32_t *d_phase = (uint32_t *)(S + o_hdr + 44);
+        uint32_t *d_shadowed = (uint32_t *)(S + o_hdr + 48);
         ChunkInfo *d_info = (ChunkInfo *)(S + o_info);
         OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 64, ctx->stream));
 
-        aos_scan_kernel<<<(unsigned)n_chunks, AOS_T, 0, ctx->stream>>>(d_buf, n, d_cursor, cand_cap, d_info,
-                                                                      (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst));
-        OIP_CUDA(cudaGetLastError());
-        ctx->launches++;
+        if (fused) {
+            // one pass: cadence phase, then sync + rules + CRC of 32 slots per warp (CH == GRP: the same group table)
+            OIP_CUDA(cudaMemsetAsync(d_phase, 0xFF, 4, ctx->stream));
+            aos_phase_kernel<<<1, 256, 0, ctx->stream>>>(d_buf, n, d_phase);
+            OIP_CUDA(cudaGetLastError());
+            aos_fused_kernel<<<(unsigned)((n_chunks + AOS_F_WARPS - 1) / AOS_F_WARPS), AOS_F_WARPS * 32, 0, ctx->stream>>>(
+                d_buf, n, d_phase, n_chunks, d_cursor, cand_cap, d_info, (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst));
+            OIP_CUDA(cudaGetLastError());
+            ctx->launches += 2;
+        } else {
+            aos_scan_kernel<<<(unsigned)n_chunks, AOS_T, 0, ctx->stream>>>(d_buf, n, d_cursor, cand_cap, d_info,
+                                                                          (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst));
+            OIP_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
         rc = ensure_pinned(ctx, 64);
         if (rc) return rc;
         // everything below is sized by the table capacity and reads the candidate count on the device: one host round
@@ -894,6 +1218,8 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
             d_info, (uint32_t *)(S + o_base), n_chunks, cand_cap, (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst),
             (uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost));
         OIP_CUDA(cudaGetLastError());
+        // (after the fused kernel only the irregular candidates still wait for their CRC: false sync words inside rejected
+        // frames, groups without cadence)
         aos_crc_kernel<<<(unsigned)(((size_t)cand_cap + 32 * AOS_CRC_WARPS - 1) / (32 * AOS_CRC_WARPS)), AOS_CRC_WARPS * 32, 0, ctx->stream>>>(
             d_buf, plan, (uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), d_total);
         OIP_CUDA(cudaGetLastError());
@@ -902,7 +1228,7 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
         aos_runstart_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), d_total, S + o_rs);
         OIP_CUDA(cudaGetLastError());
         aos_walk_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), S + o_rs, d_total,
-                                                     (uint32_t *)(S + o_acc), d_counters);
+                                                     (uint32_t *)(S + o_acc), d_counters, d_shadowed);
         OIP_CUDA(cudaGetLastError());
         ctx->launches += 5;
         rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_acc), (uint32_t *)(S + o_rank), cand_cap, (uint32_t *)(S + o_scan),
@@ -914,13 +1240,17 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
             OIP_CUDA(cudaGetLastError());
             ctx->launches++;
         }
-        // header: cursor(u32) | total(u32) | counters(3 x u64)
+        // header: cursor(u32) | total(u32) | counters(3 x u64) | .. | shadowed-valid flag @48
         uint8_t *hb = (uint8_t *)ctx->h_pinned;
-        OIP_CUDA(cudaMemcpyAsync(hb, S + o_hdr, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        OIP_CUDA(cudaMemcpyAsync(hb, S + o_hdr, 64, cudaMemcpyDeviceToHost, ctx->stream));
         OIP_CUDA(cudaStreamSynchronize(ctx->stream));
         const uint32_t m = *(const uint32_t *)hb;
         if (m > cand_cap) { // pathological input (sync pattern everywhere): retry with the exact size
             cand_cap = m;
+            continue;
+        }
+        if (fused && *(const uint32_t *)(hb + 48)) { // a valid frame shadowed by an overlapping one: exhaustive search
+            fused = false;
             continue;
         }
         const unsigned long long *hc = (const unsigned long long *)(hb + 8);

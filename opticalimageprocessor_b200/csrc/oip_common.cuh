@@ -50,6 +50,7 @@ struct oip_ctx {
     int64_t mss_plan_rows = 0;
     int64_t mss_fast_ctas = 0;   // mss_fast_kernel CTAs
     size_t mss_fast_off = 0;     // byte offset of the FTile array inside d_mss_plan
+    int aos_fused = 1;           // 0: oip_aos_scan uses the exhaustive search kernels of round 1 (aos_scan_kernel + aos_crc_kernel)
     int mss_fast = 1;            // 0: every MSS tile on the generic kernel
     int mss_fast_rows = 128;     // output rows per MSS warp-tile
     // scratch for stage 1 (grown on demand)
@@ -62,7 +63,7 @@ struct oip_ctx {
                               // side stream can share a hardware queue, which parks the kernel behind a 2 ms copy)
     cudaStream_t aux_stream = nullptr; // side stream of oip_pan_pipeline (generic tiles next to the fast kernel)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool pan_attr_set = false, mss_attr_set = false, fast_attr_set = false;
+    bool pan_attr_set = false, mss_attr_set = false, fast_attr_set = false, imtr_attr_set = false;
     // host-buffer pipeline (oip_pan_pipeline_host): staging slots + side streams
     void *host_pipe = nullptr;
     void *stt_state = nullptr; // cuFFT plans of the offset estimation (stt.cu)

@@ -33,9 +33,14 @@ def test_crc16_batch(ctx, oracle_mod, length):
 def _check_aos(ctx, oracle_mod, buf):
     from opticalimageprocessor_b200 import ops
     off_w, cnt_w = oracle_mod.aos_scan(buf)
-    off_g, cnt_g = ops.aos_scan(ctx, _dev(buf))
-    assert cnt_g.tolist() == cnt_w.tolist()
-    assert np.array_equal(off_g.cpu().numpy().astype(np.uint64), off_w)
+    for fused in (1, 0):   # the single-pass cadence kernel (default) and the exhaustive search kernels it falls back to
+        ctx.set_option("aos_fused", fused)
+        try:
+            off_g, cnt_g = ops.aos_scan(ctx, _dev(buf))
+        finally:
+            ctx.set_option("aos_fused", 1)
+        assert cnt_g.tolist() == cnt_w.tolist(), (fused, cnt_g.tolist(), cnt_w.tolist())
+        assert np.array_equal(off_g.cpu().numpy().astype(np.uint64), off_w), fused
     return off_w
 
 
@@ -70,7 +75,39 @@ def test_aos_scan_false_syncs(ctx, oracle_mod):
     _check_aos(ctx, oracle_mod, np.concatenate([storm, aos[:8].reshape(-1), storm]))
 
 
-@pytest.mark.parametrize("n", [0, 1023, 1024, 1025, 16384, 16384 + 1024, 3 * 16384 - 5])
+def test_aos_scan_cadence_breaks(ctx, oracle_mod):
+    """the single-pass kernel assumes back-to-back frames at the phase of the first sync word: byte slips (inserted /
+    dropped bytes), a file that starts with a long junk prefix, a corrupted sync word, garbage runs containing sync
+    words, a false sync inside an EMPTY frame and inside a bad-CRC frame -- all bit-identical to the sequential scan"""
+    imdt, truth, imtr, aos = _downlink(n_frames=12, tc=32, tl=8)
+    assert aos.shape[0] > 300
+    flat = aos.reshape(-1).copy()
+    rng = np.random.default_rng(11)
+    sync = np.frombuffer(synth.AOS_SYNC, np.uint8)
+    # byte slips: 5 bytes inserted after frame 40, 3 bytes dropped inside frame 90, 1 inserted after frame 200
+    a = np.concatenate([flat[:40 * 1024], rng.integers(0, 256, 5, dtype=np.uint8), flat[40 * 1024:90 * 1024 + 500],
+                        flat[90 * 1024 + 503:200 * 1024], np.zeros(1, np.uint8), flat[200 * 1024:]])
+    _check_aos(ctx, oracle_mod, a)
+    # long junk prefix with sync words in it (some followed by a whole frame's worth of bytes, none valid), then the frames
+    junk = rng.integers(0, 256, 70000, dtype=np.uint8)
+    for p in (100, 5000, 5002, 33000, 69990):
+        junk[p:p + 4] = sync
+    _check_aos(ctx, oracle_mod, np.concatenate([junk, flat]))
+    # a corrupted sync word, a false sync inside an empty frame and inside a bad-CRC frame
+    b = synth.build_aos_file(aos, empty_every=9, bad_crc_at={17, 60})
+    fr = b.reshape(-1, 1024) if b.size % 1024 == 0 else None
+    assert fr is not None
+    fr = fr.copy()
+    fr[30, 1] ^= 0x40                                         # frame 30 loses its sync word
+    empties = [i for i in range(fr.shape[0]) if fr[i, 5] == 0x3F and fr[i, 10] == 0xAA]
+    fr[empties[2], 500:504] = sync                            # visited: the scan continues inside an empty frame
+    fr[empties[3], 1021:1024] = sync[:3]                      # ... and a sync word that straddles into the next frame? (next starts 1A: not CF)
+    _check_aos(ctx, oracle_mod, fr.reshape(-1))
+    # tail: the file ends in the middle of a frame, and with a lone sync word
+    _check_aos(ctx, oracle_mod, np.concatenate([flat[:77 * 1024 + 333], sync]))
+
+
+@pytest.mark.parametrize("n", [0, 1023, 1024, 1025, 16384, 16384 + 1024, 3 * 16384 - 5, 32768 + 7, 32768 * 3 + 1024 + 9])
 def test_aos_scan_sizes_and_chunk_boundaries(ctx, oracle_mod, n):
     imdt, truth, imtr, aos = _downlink(n_frames=2)
     buf = np.concatenate([np.zeros(7, np.uint8), aos.reshape(-1)])[:n]  # frames straddle the 16 KiB chunks
