@@ -521,6 +521,17 @@ def run_gpu(args):
                                                   f"cv2.remap cubic ({cv2.getNumThreads()} threads) + concat, in memory"}
             except Exception as e:  # the CPU leg must never take the GPU number down
                 line["cpu_baseline"] = {"value": None, "unit": "Gpixel/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+            # second workload, same run: the C2 strip as raw DOWNLINK FILES (AOS frames -> IMTR frames -> image frames), every
+            # stage-1 kernel inside the timed region (oip_downlink_to_stitched); its own roofline, parity against the oracle chain
+            if not args.no_framed:
+                try:
+                    sys.path.insert(0, os.path.join(ROOT, "tools"))
+                    import bench_framed
+                    line["framed"] = bench_framed.run(ctx, 32768, max(3, min(args.steps, 10)), check=not args.no_parity, peak_gbs=peak)
+                    if line["framed"].get("parity_ok") is False:
+                        line["parity_ok"] = False
+                except Exception as e:
+                    line["framed"] = {"value": None, "note": f"failed: {e}"}
         emit(line)
     for p in opened:
         lib.oip_ipc_close(ctx.h, C.c_void_p(p))
@@ -561,6 +572,7 @@ def main():
     ap.add_argument("--rows", type=int, default=TOTAL_ROWS, help="strip length in lines (default: the C4 strip; smaller = smoke runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check")
+    ap.add_argument("--no-framed", action="store_true", help="skip the second workload (C2 as framed downlink files)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -570,7 +582,7 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__), "--gpus", str(args.gpus),
                    "--steps", str(args.steps), "--warmup", str(args.warmup), "--rows", str(args.rows)] + \
-                  (["--no-e2e"] if args.no_e2e else []) + (["--no-parity"] if args.no_parity else [])
+                  (["--no-e2e"] if args.no_e2e else []) + (["--no-parity"] if args.no_parity else []) + (["--no-framed"] if args.no_framed else [])
             raise SystemExit(subprocess.call(cmd))
         run_gpu(args)
 

@@ -345,13 +345,21 @@ constexpr int AOS_F_WARPS = 4;
 
 __global__ void aos_phase_kernel(const uint8_t *__restrict__ buf, int64_t n, uint32_t *phase)
 {
-    // first sync word that leaves room for a frame, within the first 64 KiB (else: no cadence assumed, phase 0)
+    // first sync word that leaves room for a frame, within the first 64 KiB (else: no cadence assumed, phase 0);
+    // 64 CTAs x 256 threads x 4 positions
     const int64_t lim = min((int64_t)65536, n - 1023);
+    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     uint32_t best = 0xFFFFFFFFu;
-    for (int64_t p = (int64_t)threadIdx.x * 256; p < lim && best == 0xFFFFFFFFu; p += (int64_t)blockDim.x * 256)
-        for (int64_t q = p; q < min(p + 256, lim); ++q)
-            if (buf[q] == 0x1A && buf[q + 1] == 0xCF && buf[q + 2] == 0xFC && buf[q + 3] == 0x1D) { best = (uint32_t)q; break; }
-    if (best != 0xFFFFFFFFu) atomicMin(phase, best);
+    if (p0 < lim) {
+        uint32_t b[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) b[i] = p0 + i < n ? buf[p0 + i] : 0u;
+#pragma unroll
+        for (int i = 3; i >= 0; --i)
+            if (p0 + i < lim && b[i] == 0x1A && b[i + 1] == 0xCF && b[i + 2] == 0xFC && b[i + 3] == 0x1D) best = (uint32_t)(p0 + i);
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if ((threadIdx.x & 31) == 0 && best != 0xFFFFFFFFu) atomicMin(phase, best);
 }
 
 // sync hits among the file positions [row + lo, row + hi) of one 1024-byte row, with p + 1024 <= n: lane l owns the
@@ -433,7 +441,7 @@ __device__ __forceinline__ uint32_t aos_emit_row(const uint8_t *__restrict__ buf
 
 __global__ void __launch_bounds__(AOS_F_WARPS * 32) aos_fused_kernel(const uint8_t *__restrict__ buf, int64_t n, const uint32_t *__restrict__ phase_ptr,
                                                                       int64_t n_groups, uint32_t *cursor, uint32_t cap, ChunkInfo *info,
-                                                                      uint64_t *cand_off, int8_t *cand_st)
+                                                                      uint64_t *cand_off, int8_t *cand_st, uint32_t *n_irregular)
 {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * AOS_F_WARPS + (threadIdx.x >> 5);
@@ -519,6 +527,7 @@ __global__ void __launch_bounds__(AOS_F_WARPS * 32) aos_fused_kernel(const uint8
             cand_off[slot0 + lane] = (uint64_t)(g0 + 1024 * lane);
             cand_st[slot0 + lane] = (int8_t)st;
         } else {
+            if (lane == 0) atomicAdd(n_irregular, 1u);         // candidates that still wait for their CRC (aos_crc_kernel)
             uint32_t at = slot0;
             for (int q = 0; q < 32; ++q) {
                 const int sq = __shfl_sync(0xffffffffu, st, q);
@@ -543,6 +552,7 @@ __global__ void __launch_bounds__(AOS_F_WARPS * 32) aos_fused_kernel(const uint8
     }
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
     if (!total || (uint64_t)slot0 + total > cap) return;
+    if (lane == 0) atomicAdd(n_irregular, 1u);
     uint32_t at = slot0;
     for (int64_t row = lo_byte; row < hi_byte; row += 1024)
         at += aos_emit_row(buf, row, aos_row_hits(buf, n, row, 0, (int)min((int64_t)1024, hi_byte - row)), at, cap, cand_off, cand_st);
@@ -556,8 +566,9 @@ __global__ void __launch_bounds__(AOS_F_WARPS * 32) aos_fused_kernel(const uint8
 constexpr int AOS_CRC_WARPS = 4;
 __global__ void __launch_bounds__(AOS_CRC_WARPS * 32) aos_crc_kernel(const uint8_t *__restrict__ buf, const __grid_constant__ CrcPlan crc,
                                                                       const uint64_t *__restrict__ off, int8_t *st_io,
-                                                                      const uint32_t *__restrict__ m_ptr)
+                                                                      const uint32_t *__restrict__ m_ptr, const uint32_t *__restrict__ skip_unless)
 {
+    if (skip_unless && *skip_unless == 0u) return; // after the fused kernel: no candidate is waiting for a CRC
     const int lane = threadIdx.x & 31;
     const int64_t g0 = (((int64_t)blockIdx.x * AOS_CRC_WARPS) + (threadIdx.x >> 5)) * 32;
     const int64_t m = (int64_t)*m_ptr;
@@ -935,16 +946,17 @@ __global__ void __launch_bounds__(256) imtr_copy_kernel(const uint8_t *__restric
                                                         const uint32_t *n_valid, int speculative)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (f >= n_frames || !valid[f]) return;
     const uint64_t r0 = *restart_last;
     if (speculative && r0 == 0 && (int64_t)*n_valid == n_frames) { // imtr_validate_kernel already wrote every frame in place
-        if (f == 0 && lane == 0) *first_chid = chid[0];
+        if (blockIdx.x == 0 && threadIdx.x == 0) *first_chid = chid[0];
         return;
     }
-    if (rank[f] < r0) return;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < n_frames; f += n_warps) {
+    if (!valid[f]) continue;
+    if (rank[f] < r0) continue;
     const uint64_t dst = (uint64_t)(rank[f] - r0) * 866;
-    if (dst + 866 > cap) return;
+    if (dst + 866 > cap) continue;
     if (rank[f] == r0 && lane == 0) *first_chid = chid[f];
     const FrameSegs S = frame_segs(buf, poff, n_payload, f * 882);
     // 866 payload bytes from frame position 10 (IMTR_IMGDATA_OFF :72): aligned destination words, source words
@@ -967,6 +979,7 @@ __global__ void __launch_bounds__(256) imtr_copy_kernel(const uint8_t *__restric
     }
     const int t0 = head + 4 * nw;
     if (lane < 866 - t0) d[t0 + lane] = __ldg(seg_ptr(S, 10 + t0 + lane));
+    }
 }
 
 // =============================================================================================
@@ -1184,16 +1197,17 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
         uint32_t *d_acc_total = (uint32_t *)(S + o_hdr + 40);
         uint32_t *d_phase = (uint32_t *)(S + o_hdr + 44);
         uint32_t *d_shadowed = (uint32_t *)(S + o_hdr + 48);
+        uint32_t *d_irregular = (uint32_t *)(S + o_hdr + 52);
         ChunkInfo *d_info = (ChunkInfo *)(S + o_info);
         OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 64, ctx->stream));
 
         if (fused) {
             // one pass: cadence phase, then sync + rules + CRC of 32 slots per warp (CH == GRP: the same group table)
             OIP_CUDA(cudaMemsetAsync(d_phase, 0xFF, 4, ctx->stream));
-            aos_phase_kernel<<<1, 256, 0, ctx->stream>>>(d_buf, n, d_phase);
+            aos_phase_kernel<<<64, 256, 0, ctx->stream>>>(d_buf, n, d_phase);
             OIP_CUDA(cudaGetLastError());
             aos_fused_kernel<<<(unsigned)((n_chunks + AOS_F_WARPS - 1) / AOS_F_WARPS), AOS_F_WARPS * 32, 0, ctx->stream>>>(
-                d_buf, n, d_phase, n_chunks, d_cursor, cand_cap, d_info, (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst));
+                d_buf, n, d_phase, n_chunks, d_cursor, cand_cap, d_info, (uint64_t *)(S + o_coff), (int8_t *)(S + o_cst), d_irregular);
             OIP_CUDA(cudaGetLastError());
             ctx->launches += 2;
         } else {
@@ -1221,7 +1235,7 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
         // (after the fused kernel only the irregular candidates still wait for their CRC: false sync words inside rejected
         // frames, groups without cadence)
         aos_crc_kernel<<<(unsigned)(((size_t)cand_cap + 32 * AOS_CRC_WARPS - 1) / (32 * AOS_CRC_WARPS)), AOS_CRC_WARPS * 32, 0, ctx->stream>>>(
-            d_buf, plan, (uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), d_total);
+            d_buf, plan, (uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), d_total, fused ? d_irregular : nullptr);
         OIP_CUDA(cudaGetLastError());
         const unsigned gb = (unsigned)(((size_t)cand_cap + 255) / 256);
         OIP_CUDA(cudaMemsetAsync(S + o_acc, 0, (size_t)cand_cap * 4, ctx->stream)); // entries past the count stay 0 for the scan
@@ -1308,7 +1322,7 @@ extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64
     OIP_CUDA(cudaGetLastError());
     imtr_rules_kernel<<<gb, 256, 0, ctx->stream>>>((uint32_t *)(S + o_seqc), d_total, d_hdr, d_hdr + 1, d_hdr + 2);
     OIP_CUDA(cudaGetLastError());
-    imtr_copy_kernel<<<(unsigned)((nf * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+    imtr_copy_kernel<<<(unsigned)std::min<int64_t>((nf * 32 + 255) / 256, (int64_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(
         d_buf, d_payload_off, n_payload, nf, (uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank), d_hdr, S + o_chid, d_imdt,
         (uint64_t)cap, d_first_chid, d_total, speculative ? 1 : 0);
     OIP_CUDA(cudaGetLastError());
