@@ -2,16 +2,20 @@
 //
 // Writes what cv::imwrite (ref preproc.h:167-185, imageop.h:444) and the GTiff driver (ref imageop.h:316-328, :470-538)
 // are used for there: 16-bit unsigned rasters with 1 or 4 interleaved samples per pixel, as baseline TIFF strips
-// (classic TIFF below 4 GiB, BigTIFF above), UNCOMPRESSED -- the reference's own files are LZW-compressed by those
-// libraries, so files are equal in pixel content and geometry, not byte for byte.  Reads uncompressed and LZW-compressed
-// (predictor 1 or 2) chunky 16-bit strip TIFFs of either byte order: our own products and the reference's (cv::imwrite
-// defaults, GTiff COMPRESS=LZW PREDICTOR=2).
+// (classic TIFF below 4 GiB, BigTIFF above), uncompressed (the single-band GTiff of ref imageop.h:316-328) or with the
+// options the reference's libraries apply to the other products: COMPRESS=LZW + PREDICTOR=2 (ref imageop.h:470-474;
+// cv::imwrite's TIFF default).  The LZW coder follows libtiff's (MSB-first 9..12-bit codes, early change, one stream per
+// strip); strips are compressed on all host cores.  Files carry the same pixels, geometry, compression and predictor as
+// the reference's; the strip layout (and therefore the bytes) is the writer's own.  Reads uncompressed and
+// LZW-compressed (predictor 1 or 2) chunky 16-bit strip TIFFs of either byte order: our own products and the
+// reference's.
 #pragma once
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace oiptiff {
@@ -39,10 +43,23 @@ inline size_t type_size(int t) { return t == 3 ? 2 : (t == 4 ? 4 : (t == 16 ? 8 
 
 // pixels: height x width x spp, u16, row-major, samples interleaved in FILE order (the caller applies cv::imwrite's
 // channel swap).  photometric: 1 = BlackIsZero (1 sample), 2 = RGB (+ one unassociated-alpha extra sample when spp == 4)
-inline void write_u16(const std::string &path, const uint16_t *pixels, int64_t width, int64_t height, int spp, int photometric)
+enum { COMPRESS_NONE = 1, COMPRESS_LZW = 5 };
+inline void write_u16_lzw(const std::string &path, const uint16_t *pixels, int64_t width, int64_t height, int spp, int photometric);
+
+// Returns the file offset of the first pixel of an uncompressed file (0 for LZW).  pixels == nullptr (uncompressed
+// only): header and IFD only -- the caller writes the height x width x spp samples itself from that offset on (row blocks
+// written in parallel by a streaming pipeline).
+inline uint64_t write_u16(const std::string &path, const uint16_t *pixels, int64_t width, int64_t height, int spp, int photometric,
+                          int compression = COMPRESS_NONE)
 {
     using namespace detail;
     if (width < 1 || height < 1 || (spp != 1 && spp != 4)) throw std::invalid_argument("tiff: unsupported geometry");
+    if (compression == COMPRESS_LZW) {
+        if (!pixels) throw std::invalid_argument("tiff: header-only mode needs an uncompressed file");
+        write_u16_lzw(path, pixels, width, height, spp, photometric);
+        return 0;
+    }
+    if (compression != COMPRESS_NONE) throw std::invalid_argument("tiff: unsupported compression");
     const uint64_t row_bytes = (uint64_t)width * spp * 2, data_bytes = row_bytes * (uint64_t)height;
     int64_t rps = (int64_t)((8u << 20) / row_bytes);
     if (rps < 1) rps = 1;
@@ -105,11 +122,171 @@ inline void write_u16(const std::string &path, const uint16_t *pixels, int64_t w
     if (!f) throw std::runtime_error("tiff: cannot create " + path);
     bool ok = fwrite(o.b.data(), 1, o.b.size(), f) == o.b.size();
     const uint8_t *p = reinterpret_cast<const uint8_t *>(pixels);
-    for (uint64_t done = 0; ok && done < data_bytes;) {
+    for (uint64_t done = 0; ok && p && done < data_bytes;) {
         const size_t n = (size_t)std::min<uint64_t>(data_bytes - done, 64u << 20);
         ok = fwrite(p + done, 1, n, f) == n;
         done += n;
     }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw std::runtime_error("tiff: write failed: " + path);
+    return data0;
+}
+
+namespace detail {
+// TIFF LZW encoder, the counterpart of lzw_decode below and of libtiff's LZWEncode / LZWPostEncode: ClearCode first,
+// codes MSB-first, the width grows when the next free code exceeds 2^width - 1 (which a decoder, one entry behind,
+// sees "one early"), the table is cleared at 4094 entries, EndOfInformation last.
+inline void lzw_encode(const uint8_t *src, size_t n, std::vector<uint8_t> &out)
+{
+    constexpr int HSIZE = 9001, HSHIFT = 13 - 8;
+    struct Slot { int32_t key; uint16_t code; };
+    std::vector<Slot> tab(HSIZE);
+    auto reset = [&]() { for (auto &t : tab) t.key = -1; };
+    uint64_t acc = 0;
+    int nacc = 0, width = 9, next = 258;
+    auto put = [&](int code) {
+        acc = (acc << width) | (uint32_t)code;
+        nacc += width;
+        while (nacc >= 8) { out.push_back((uint8_t)(acc >> (nacc - 8))); nacc -= 8; }
+    };
+    reset();
+    put(256);
+    if (n == 0) { put(257); if (nacc) out.push_back((uint8_t)(acc << (8 - nacc))); return; }
+    int w = src[0];
+    for (size_t i = 1; i < n; ++i) {
+        const int c = src[i];
+        const int32_t key = (c << 12) + w;
+        int h = (c << HSHIFT) ^ w;
+        bool found = false;
+        if (tab[h].key == key) { w = tab[h].code; continue; }
+        if (tab[h].key >= 0) { // secondary probe, like libtiff
+            int disp = h == 0 ? 1 : HSIZE - h;
+            do {
+                if ((h -= disp) < 0) h += HSIZE;
+                if (tab[h].key == key) { w = tab[h].code; found = true; break; }
+            } while (tab[h].key >= 0);
+        }
+        if (found) continue;
+        put(w);
+        tab[h].key = key;
+        tab[h].code = (uint16_t)next++;
+        if (next == 4094) { put(256); reset(); next = 258; width = 9; }
+        else if (next > (1 << width) - 1) ++width;
+        w = c;
+    }
+    put(w);
+    ++next;
+    if (next == 4094) { put(256); width = 9; }
+    else if (next > (1 << width) - 1) ++width;
+    put(257);
+    if (nacc) out.push_back((uint8_t)(acc << (8 - nacc)));
+}
+} // namespace detail
+
+// COMPRESS=LZW, PREDICTOR=2 (horizontal differencing of the 16-bit samples, per channel), strips of ~1 MiB compressed on
+// all host cores and written in order; the IFD follows the data (its position is patched into the header)
+inline void write_u16_lzw(const std::string &path, const uint16_t *pixels, int64_t width, int64_t height, int spp, int photometric)
+{
+    using namespace detail;
+    const uint64_t row_bytes = (uint64_t)width * spp * 2, data_bytes = row_bytes * (uint64_t)height;
+    int64_t rps = (int64_t)((1u << 20) / row_bytes);
+    if (rps < 1) rps = 1;
+    if (rps > height) rps = height;
+    const uint64_t n_strips = (uint64_t)((height + rps - 1) / rps);
+    const bool big = data_bytes + data_bytes / 2 + n_strips * 16 + 4096 >= 0xFFFF0000ull; // LZW can expand noise by ~40 %
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("tiff: cannot create " + path);
+    bool ok = true;
+    {
+        Out h;
+        h.b.push_back('I'); h.b.push_back('I');
+        if (big) { h.u16(43); h.u16(8); h.u16(0); h.u64(0); } else { h.u16(42); h.u32(0); }
+        ok = fwrite(h.b.data(), 1, h.b.size(), f) == h.b.size();
+    }
+    uint64_t pos = big ? 16 : 8;
+    std::vector<uint64_t> offs(n_strips), cnts(n_strips);
+    unsigned n_thr = std::thread::hardware_concurrency();
+    if (n_thr < 1) n_thr = 1;
+    if (n_thr > 32) n_thr = 32;
+    const uint64_t batch = (uint64_t)n_thr * 2;
+    std::vector<std::vector<uint8_t>> bufs(batch);
+    for (uint64_t s0 = 0; ok && s0 < n_strips; s0 += batch) {
+        const uint64_t nb = std::min<uint64_t>(batch, n_strips - s0);
+        auto work = [&](uint64_t k) {
+            const uint64_t s = s0 + k, r0 = s * (uint64_t)rps, nr = std::min<uint64_t>((uint64_t)rps, (uint64_t)height - r0);
+            std::vector<uint16_t> diff((size_t)(nr * row_bytes / 2));
+            const uint64_t rs = (uint64_t)width * spp;
+            for (uint64_t y = 0; y < nr; ++y) {
+                const uint16_t *row = pixels + (r0 + y) * rs;
+                uint16_t *d = diff.data() + y * rs;
+                for (uint64_t i = 0; i < rs; ++i) d[i] = i < (uint64_t)spp ? row[i] : (uint16_t)(row[i] - row[i - spp]);
+            }
+            bufs[k].clear();
+            bufs[k].reserve((size_t)(nr * row_bytes / 2));
+            lzw_encode(reinterpret_cast<const uint8_t *>(diff.data()), (size_t)(nr * row_bytes), bufs[k]);
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < n_thr; ++t)
+            pool.emplace_back([&, t]() { for (uint64_t k = t; k < nb; k += n_thr) work(k); });
+        for (auto &th : pool) th.join();
+        for (uint64_t k = 0; ok && k < nb; ++k) {
+            offs[s0 + k] = pos;
+            cnts[s0 + k] = bufs[k].size();
+            ok = fwrite(bufs[k].data(), 1, bufs[k].size(), f) == bufs[k].size();
+            pos += bufs[k].size();
+            if (ok && (pos & 1)) { ok = fputc(0, f) != EOF; ++pos; } // strips start on even offsets
+        }
+    }
+    // ---- IFD after the data
+    const int off_t = big ? 16 : 4;
+    std::vector<Entry> e;
+    e.push_back({256, 4, {(uint64_t)width}});
+    e.push_back({257, 4, {(uint64_t)height}});
+    e.push_back({258, 3, std::vector<uint64_t>((size_t)spp, 16)});
+    e.push_back({259, 3, {(uint64_t)COMPRESS_LZW}});
+    e.push_back({262, 3, {(uint64_t)photometric}});
+    e.push_back({273, (uint16_t)off_t, offs});
+    e.push_back({277, 3, {(uint64_t)spp}});
+    e.push_back({278, 4, {(uint64_t)rps}});
+    e.push_back({279, (uint16_t)off_t, cnts});
+    e.push_back({284, 3, {1}});
+    e.push_back({317, 3, {2}});
+    if (spp == 4) e.push_back({338, 3, {2}});
+    e.push_back({339, 3, std::vector<uint64_t>((size_t)spp, 1)});
+    const size_t ent = big ? 20 : 12, inl = big ? 8 : 4;
+    const uint64_t ifd = (pos + 7) & ~(uint64_t)7;
+    const size_t ifd_bytes = (big ? 8 : 2) + e.size() * ent + (big ? 8 : 4);
+    uint64_t extra = ifd + ifd_bytes;
+    std::vector<uint64_t> where(e.size(), 0);
+    for (size_t i = 0; i < e.size(); ++i) {
+        const size_t nb = e[i].v.size() * type_size(e[i].type);
+        if (nb > inl) { where[i] = extra; extra += (nb + 7) & ~(size_t)7; }
+    }
+    if (!big && extra >= 0xFFFFFFF0ull) { fclose(f); throw std::runtime_error("tiff: classic TIFF overflow: " + path); }
+    Out o;
+    for (uint64_t q = pos; q < ifd; ++q) o.b.push_back(0);
+    if (big) o.u64(e.size()); else o.u16((uint16_t)e.size());
+    auto put = [&](Out &dst, int type, uint64_t v) { if (type == 3) dst.u16((uint16_t)v); else if (type == 4) dst.u32((uint32_t)v); else dst.u64(v); };
+    for (size_t i = 0; i < e.size(); ++i) {
+        o.u16(e[i].tag); o.u16(e[i].type);
+        if (big) o.u64(e[i].v.size()); else o.u32((uint32_t)e[i].v.size());
+        const size_t at = o.b.size();
+        if (where[i]) { if (big) o.u64(where[i]); else o.u32((uint32_t)where[i]); }
+        else {
+            for (uint64_t v : e[i].v) put(o, e[i].type, v);
+            while (o.b.size() < at + inl) o.b.push_back(0);
+        }
+    }
+    if (big) o.u64(0); else o.u32(0);
+    for (size_t i = 0; i < e.size(); ++i) {
+        if (!where[i]) continue;
+        while (pos + o.b.size() < where[i]) o.b.push_back(0);
+        for (uint64_t v : e[i].v) put(o, e[i].type, v);
+    }
+    ok = ok && fwrite(o.b.data(), 1, o.b.size(), f) == o.b.size();
+    Out hp;
+    if (big) hp.u64(ifd); else hp.u32((uint32_t)ifd);
+    ok = ok && fseeko(f, big ? 8 : 4, SEEK_SET) == 0 && fwrite(hp.b.data(), 1, hp.b.size(), f) == hp.b.size();
     ok = (fclose(f) == 0) && ok;
     if (!ok) throw std::runtime_error("tiff: write failed: " + path);
 }

@@ -1,5 +1,5 @@
 // Host driver for host/tiff_io.hpp, used by tests/test_tiff_cpu.py:
-//   tiff_io_host_test write <out.tiff> <width> <height> <spp> <raw u16 file>
+//   tiff_io_host_test write <out.tiff> <width> <height> <spp> <raw u16 file> [lzw]
 //   tiff_io_host_test read  <in.tiff> <raw u16 out>      (prints "width height spp")
 #include <cstdio>
 #include <cstdlib>
@@ -12,14 +12,14 @@ int main(int argc, char **argv)
 {
     try {
         const std::string mode = argc > 1 ? argv[1] : "";
-        if (mode == "write" && argc == 7) {
+        if (mode == "write" && (argc == 7 || argc == 8)) {
             const long w = atol(argv[3]), h = atol(argv[4]);
             const int spp = atoi(argv[5]);
             std::vector<uint16_t> px((size_t)w * h * spp);
             FILE *f = fopen(argv[6], "rb");
             if (!f || fread(px.data(), 2, px.size(), f) != px.size()) return 3;
             fclose(f);
-            oiptiff::write_u16(argv[2], px.data(), w, h, spp, spp == 1 ? 1 : 2);
+            oiptiff::write_u16(argv[2], px.data(), w, h, spp, spp == 1 ? 1 : 2, argc == 8 ? oiptiff::COMPRESS_LZW : oiptiff::COMPRESS_NONE);
             return 0;
         }
         if (mode == "read" && argc == 4) {

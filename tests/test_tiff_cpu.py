@@ -54,6 +54,45 @@ def test_reads_libtiff_files_uncompressed_and_lzw(exe, tmp_path, shape):
             assert np.array_equal(np.fromfile(back, np.uint16).reshape(shape), want), path
 
 
+@pytest.mark.parametrize("h,w,spp,kind", [(37, 53, 1, "noise"), (1200, 3072, 4, "smooth"), (5, 70000, 1, "smooth"), (3000, 1500, 4, "noise"),
+                                          (700, 3072, 4, "zeros"), (4096, 1024, 1, "dn12")])
+def test_lzw_predictor2_files_are_read_by_libtiff(exe, tmp_path, h, w, spp, kind):
+    """the reference's product options COMPRESS=LZW + PREDICTOR=2 (ref imageop.h:470-474, cv::imwrite's TIFF default): what
+    we write, libtiff (cv2.imread) decodes to the same pixels, the tags say LZW / predictor 2, and compressible data shrinks"""
+    rng = np.random.default_rng(h * 3 + w)
+    if kind == "noise":
+        px = rng.integers(0, 65536, (h, w, spp), dtype=np.uint16)
+    elif kind == "smooth":
+        px = (np.cumsum(rng.integers(-3, 4, (h, w, spp)), axis=1) + 2000).astype(np.uint16)
+    elif kind == "zeros":
+        px = np.zeros((h, w, spp), np.uint16)
+    else:
+        px = rng.integers(64, 4032, (h, w, spp), dtype=np.uint16)
+    raw, tif = str(tmp_path / "in.raw"), str(tmp_path / "out.TIFF")
+    px.tofile(raw)
+    subprocess.check_call([exe, "write", tif, str(w), str(h), str(spp), raw, "lzw"])
+    img = cv2.imread(tif, cv2.IMREAD_UNCHANGED)
+    assert img is not None and img.dtype == np.uint16
+    assert np.array_equal(img, px[:, :, 0] if spp == 1 else px[:, :, [2, 1, 0, 3]])
+    back = str(tmp_path / "back.raw")
+    dims = subprocess.check_output([exe, "read", tif, back], text=True).split()
+    assert [int(v) for v in dims] == [w, h, spp]
+    assert np.array_equal(np.fromfile(back, np.uint16).reshape(h, w, spp), px)
+    data = open(tif, "rb").read()
+    assert data[:2] == b"II"
+    if kind in ("smooth", "zeros"):
+        assert len(data) < px.nbytes * 0.6
+    # tags 259 (Compression) = 5 and 317 (Predictor) = 2, via our own parser's view
+    import struct
+    ifd = struct.unpack("<I", data[4:8])[0]
+    n = struct.unpack("<H", data[ifd:ifd + 2])[0]
+    tags = {}
+    for k in range(n):
+        t, ty, cnt, val = struct.unpack("<HHII", data[ifd + 2 + 12 * k: ifd + 14 + 12 * k])
+        tags[t] = val & 0xFFFF if ty == 3 else val
+    assert tags[259] == 5 and tags[317] == 2
+
+
 def test_refuses_other_compressions(exe, tmp_path):
     img = np.random.default_rng(2).integers(0, 65536, (64, 64, 4), dtype=np.uint16)
     z, back = str(tmp_path / "deflate.TIFF"), str(tmp_path / "back.raw")
