@@ -91,6 +91,17 @@ int oip_crc16_batch(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_off, i
 int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, uint64_t *d_payload_off,
                  size_t cap, int64_t counters[3]);
 
+/* Byte-range shard of the same scan (the downlink of one strip spread over the GPUs of a box).  d_buf holds
+ * file bytes [B, B + n_bytes): the shard owns the candidates that start in its first own_bytes, the rest (up to 1023
+ * bytes, read from the file by the same rank) is the halo that lets the frames starting near the end be validated.
+ * carry_in = buffer offset where this shard's scan starts (0, or the bytes of the previous shard's last accepted frame that
+ * reach in here); *carry_out = the same quantity for the next shard.  Shards are independent given carry_in; ranks
+ * exchange (carry_out, n_valid) with ONE all-gather, re-run the rare shard whose assumed carry_in was wrong, and add the
+ * three counters with one all-reduce (opticalimageprocessor_b200/sharding.py: aos_shard_ranges / aos_resolve_carries).
+ * Payload offsets are relative to d_buf.  Concatenating the shards' results gives oip_aos_scan of the whole file. */
+int oip_aos_scan_shard(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, size_t own_bytes, size_t carry_in,
+                       uint64_t *d_payload_off, size_t cap, int64_t counters[3], int64_t *carry_out);
+
 /* IMTR re-framing at the fixed 882-byte cadence over the concatenated payloads, validation and
  * extraction of the 866-byte bodies.
  * replaces AuxSeparator::DataTransFrameParser + ValidateImtrFrame -- ref aux_separator.h:469-590.
@@ -99,6 +110,19 @@ int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, uint64_t *d
 int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_payload_off,
                      int64_t n_payload, uint8_t *d_imdt, size_t cap, int64_t stats[9],
                      int64_t *imdt_bytes);
+
+/* The same on a shard of the payload stream.  The cadence is cut from GLOBAL stream byte 0, so a rank whose
+ * payloads are stream bytes [880 P, 880 (P + n_own)) owns the frames that START in that range: the first one begins
+ * skip_bytes into its first payload, n_frames of them follow (sharding.imtr_shard_frames computes both from the all-gathered
+ * payload counts); d_payload_off lists the rank's own payloads plus the 1-2 payloads of the next rank its last frame
+ * reaches into.  prev_seq = sequence number accepted before this shard (0 at the start of the stream, < 0: not known yet
+ * -- the restart / gap rule of the first valid frame is then left to the caller, who applies it after the all-gather of
+ * seq_info).  seq_info = {first valid seq, last valid seq, index of the last restart among the valid frames or -1}.
+ * stats and d_imdt are local to the shard; the IMDT stream is the concatenation of the ranks' pieces from the last
+ * restart on (sharding.imtr_combine). */
+int oip_imtr_deframe_shard(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_payload_off, int64_t n_payload,
+                           int skip_bytes, int64_t n_frames, int64_t prev_seq, uint8_t *d_imdt, size_t cap, int64_t stats[9],
+                           int64_t *imdt_bytes, int64_t seq_info[3]);
 
 /* image-frame geometry, reference values in brackets (ref aux_separator.h:84-93) */
 typedef struct {

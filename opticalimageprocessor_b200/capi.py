@@ -109,7 +109,9 @@ SYMBOLS = {
     "oip_ipc_close": (_I, [_VP, _VP]),
     "oip_crc16_batch": (_I, [_VP, _VP, _VP, _I64, _I, _VP]),
     "oip_aos_scan": (_I, [_VP, _VP, _SZ, _VP, _SZ, C.POINTER(_I64)]),
+    "oip_aos_scan_shard": (_I, [_VP, _VP, _SZ, _SZ, _SZ, _VP, _SZ, C.POINTER(_I64), C.POINTER(_I64)]),
     "oip_imtr_deframe": (_I, [_VP, _VP, _VP, _I64, _VP, _SZ, C.POINTER(_I64), C.POINTER(_I64)]),
+    "oip_imtr_deframe_shard": (_I, [_VP, _VP, _VP, _I64, _I, _I64, _I64, _VP, _SZ, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "oip_image_frames_index": (_I, [_VP, _VP, _SZ, C.POINTER(FrameGeom), C.POINTER(FrameEntry), _I64, C.POINTER(_I64)]),
     "oip_unpack_frames": (_I, [_VP, _VP, _SZ, C.POINTER(FrameGeom), C.POINTER(FrameEntry), _I64, _VP, _VP, _VP]),
     "oip_rrc_u16": (_I, [_VP, _VP, _I, _I64, _I64, _VP]),

@@ -635,6 +635,18 @@ __global__ void aos_clamp_kernel(uint32_t *total, uint32_t cap)
     if (*total > cap) *total = cap;
 }
 
+// Byte-range shard of a file: the scan of this shard starts at buffer offset carry_in (the previous shard's
+// last accepted frame ends there) and owns the candidates that START before `own`; the bytes after `own` are the halo that
+// lets the frames starting near the end be validated.  Candidates in front of carry_in get status -2 ("not there"),
+// the table is cut at the first candidate >= own.
+__global__ void aos_shard_trim_kernel(const uint64_t *off, int8_t *st, uint32_t *m_ptr, uint64_t own, uint64_t carry_in, uint32_t *m_own)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)*m_ptr) return;
+    if (off[i] < carry_in) st[i] = -2;
+    if (off[i] < own) atomicMax(m_own, (uint32_t)(i + 1));
+}
+
 // A valid candidate with no valid candidate in the preceding 1023 bytes is always accepted by the
 // sequential scan (ref aux_separator.h:421-461): whatever was accepted before ends <= its offset.
 __global__ void aos_runstart_kernel(const uint64_t *off, const int8_t *st, const uint32_t *m_ptr, uint8_t *rs)
@@ -682,7 +694,7 @@ __global__ void aos_walk_kernel(const uint64_t *off, const int8_t *st, const uin
                 next_free = off[j] + 1024;
             } else {
                 acc[j] = 0;
-                if (st[j] < 0) n_inv++; else n_emp++;
+                if (st[j] == -1) n_inv++; else if (st[j] == 0) n_emp++; // (-2: in front of a shard's scan start, not there)
             }
         }
     }
@@ -698,11 +710,12 @@ __global__ void aos_walk_kernel(const uint64_t *off, const int8_t *st, const uin
 }
 
 __global__ void aos_emit_kernel(const uint64_t *off, const uint32_t *acc, const uint32_t *rank, const uint32_t *m_ptr,
-                                uint64_t *payload_off, uint64_t cap)
+                                uint64_t *payload_off, uint64_t cap, unsigned long long *last_end)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)*m_ptr || !acc[i]) return;
-    if (rank[i] < cap) payload_off[rank[i]] = off[i] + 14; // AOS_DATA_OFF :44
+    if (payload_off && rank[i] < cap) payload_off[rank[i]] = off[i] + 14; // AOS_DATA_OFF :44
+    if (i + 1 == (int64_t)*m_ptr || !acc[i + 1]) atomicMax(last_end, (unsigned long long)(off[i] + 1024)); // where the scan goes on (a shard's carry-out)
 }
 
 // =============================================================================================
@@ -765,14 +778,14 @@ constexpr int IMTR_T = 128, IMTR_BATCH = 32, IMTR_SLOT = 896, IMTR_FRONT = 32;
 __global__ void __launch_bounds__(IMTR_T) imtr_validate_kernel(const uint8_t *__restrict__ buf, const uint64_t *__restrict__ poff,
                                                                int64_t n_payload, int64_t n_frames, uint8_t *status,
                                                                uint32_t *seq, uint8_t *chid, uint32_t *valid,
-                                                               unsigned long long *n_bad, uint8_t *imdt_spec)
+                                                               unsigned long long *n_bad, uint8_t *imdt_spec, int skip)
 {
     __shared__ __align__(16) uint32_t s_w[(IMTR_FRONT + IMTR_BATCH * IMTR_SLOT + 32) / 4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t f0 = (int64_t)blockIdx.x * IMTR_BATCH;
     // payload offsets of the whole batch in ONE round trip (every warp keeps its own copy in two registers per lane): the
     // 32 frames span payloads i0 .. i0+33 (+2 for the run tails), handed out by shuffles -- no dependent load per frame
-    const int64_t s_first = f0 * 882;
+    const int64_t s_first = (int64_t)skip + f0 * 882; // (a shard's first frame starts `skip` bytes into its first payload)
     const int64_t i0 = s_first / 880;
     const int o0 = (int)(s_first - i0 * 880);
     const unsigned long long pl0 = poff[min(i0 + lane, n_payload - 1)], pl1 = poff[min(i0 + 32 + lane, n_payload - 1)];
@@ -927,12 +940,17 @@ __global__ void imtr_compact_seq_kernel(const uint32_t *valid, const uint32_t *r
 }
 // restart rule: the IMDT file is (re)created when the previously accepted frame had seq 0
 // (lastImtrSeq == 0, ref :513-528); gap rule :530-533
+// prev_in: sequence number accepted before the first frame of this call (0 at the start of a stream); < 0 = unknown (a
+// shard whose predecessor is not known yet): the rules of the first valid frame are left to the caller
 __global__ void imtr_rules_kernel(const uint32_t *seq_c, const uint32_t *n_valid, unsigned long long *restart_last,
-                                  unsigned long long *n_restarts, unsigned long long *n_gaps)
+                                  unsigned long long *n_restarts, unsigned long long *n_gaps, long long prev_in, unsigned long long *seq_first_last)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= (int64_t)*n_valid) return;
-    const uint32_t prev = k ? seq_c[k - 1] : 0u;
+    if (k == 0) seq_first_last[0] = seq_c[0];
+    if (k + 1 == (int64_t)*n_valid) seq_first_last[1] = seq_c[k];
+    if (k == 0 && prev_in < 0) return;
+    const uint32_t prev = k ? seq_c[k - 1] : (uint32_t)prev_in;
     if (prev == 0u) {
         atomicMax(restart_last, (unsigned long long)k);
         atomicAdd(n_restarts, 1ull);
@@ -943,7 +961,7 @@ __global__ void __launch_bounds__(256) imtr_copy_kernel(const uint8_t *__restric
                                                         int64_t n_payload, int64_t n_frames, const uint32_t *valid,
                                                         const uint32_t *rank, const unsigned long long *restart_last,
                                                         const uint8_t *chid, uint8_t *imdt, uint64_t cap, int *first_chid,
-                                                        const uint32_t *n_valid, int speculative)
+                                                        const uint32_t *n_valid, int speculative, int skip)
 {
     const int lane = threadIdx.x & 31;
     const uint64_t r0 = *restart_last;
@@ -958,7 +976,7 @@ __global__ void __launch_bounds__(256) imtr_copy_kernel(const uint8_t *__restric
     const uint64_t dst = (uint64_t)(rank[f] - r0) * 866;
     if (dst + 866 > cap) continue;
     if (rank[f] == r0 && lane == 0) *first_chid = chid[f];
-    const FrameSegs S = frame_segs(buf, poff, n_payload, f * 882);
+    const FrameSegs S = frame_segs(buf, poff, n_payload, (int64_t)skip + f * 882);
     // 866 payload bytes from frame position 10 (IMTR_IMGDATA_OFF :72): aligned destination words, source words
     // re-aligned by funnel shift
     uint8_t *d = imdt + dst;
@@ -1158,13 +1176,31 @@ extern "C" int oip_crc16_batch(oip_ctx *ctx, const uint8_t *d_buf, const uint64_
     return OIP_OK;
 }
 
+static int aos_scan_impl(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, size_t own_bytes, size_t carry_in, uint64_t *d_payload_off,
+                         size_t cap, int64_t counters[3], int64_t *carry_out);
+
 extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, uint64_t *d_payload_off, size_t cap,
                             int64_t counters[3])
 {
+    return aos_scan_impl(ctx, d_buf, n_bytes, n_bytes, 0, d_payload_off, cap, counters, nullptr);
+}
+
+extern "C" int oip_aos_scan_shard(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, size_t own_bytes, size_t carry_in,
+                                  uint64_t *d_payload_off, size_t cap, int64_t counters[3], int64_t *carry_out)
+{
+    if (own_bytes > n_bytes || carry_in > 1023 + 1) return fail(OIP_E_INVALID, "oip_aos_scan_shard: own_bytes=%zu of %zu, carry_in=%zu", own_bytes, n_bytes, carry_in);
+    return aos_scan_impl(ctx, d_buf, n_bytes, own_bytes, carry_in, d_payload_off, cap, counters, carry_out);
+}
+
+static int aos_scan_impl(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, size_t own_bytes, size_t carry_in, uint64_t *d_payload_off,
+                         size_t cap, int64_t counters[3], int64_t *carry_out)
+{
     OIP_CHECK_CTX(ctx);
     if (counters) counters[0] = counters[1] = counters[2] = 0;
+    if (carry_out) *carry_out = (int64_t)std::max<size_t>(carry_in, own_bytes) - (int64_t)own_bytes;
     if (!d_buf && n_bytes) return fail(OIP_E_INVALID, "oip_aos_scan: null buffer");
     if (n_bytes < 1024) return OIP_OK; // ref :623
+    const bool shard = own_bytes != n_bytes || carry_in != 0;
     if (n_bytes / 4 > 0x7fffffffull) return fail(OIP_E_INVALID, "oip_aos_scan: buffer too large for one call");
     const int64_t n = (int64_t)n_bytes;
     const int64_t n_chunks = (n + CH - 1) / CH;
@@ -1198,6 +1234,8 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
         uint32_t *d_phase = (uint32_t *)(S + o_hdr + 44);
         uint32_t *d_shadowed = (uint32_t *)(S + o_hdr + 48);
         uint32_t *d_irregular = (uint32_t *)(S + o_hdr + 52);
+        uint32_t *d_m_own = (uint32_t *)(S + o_hdr + 56);
+        unsigned long long *d_last_end = (unsigned long long *)(S + o_hdr + 32);
         ChunkInfo *d_info = (ChunkInfo *)(S + o_info);
         OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 64, ctx->stream));
 
@@ -1239,6 +1277,13 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
         OIP_CUDA(cudaGetLastError());
         const unsigned gb = (unsigned)(((size_t)cand_cap + 255) / 256);
         OIP_CUDA(cudaMemsetAsync(S + o_acc, 0, (size_t)cand_cap * 4, ctx->stream)); // entries past the count stay 0 for the scan
+        if (shard) { // from here on the table holds the shard's own candidates only (the total stays in d_cursor for the overflow test)
+            aos_shard_trim_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), d_total, (uint64_t)own_bytes,
+                                                               (uint64_t)carry_in, d_m_own);
+            OIP_CUDA(cudaGetLastError());
+            OIP_CUDA(cudaMemcpyAsync(d_total, d_m_own, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            ctx->launches++;
+        }
         aos_runstart_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), d_total, S + o_rs);
         OIP_CUDA(cudaGetLastError());
         aos_walk_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (int8_t *)(S + o_ost), S + o_rs, d_total,
@@ -1248,9 +1293,9 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
         rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_acc), (uint32_t *)(S + o_rank), cand_cap, (uint32_t *)(S + o_scan),
                                 d_acc_total);
         if (rc) return rc;
-        if (d_payload_off) {
+        if (d_payload_off || carry_out) {
             aos_emit_kernel<<<gb, 256, 0, ctx->stream>>>((uint64_t *)(S + o_ooff), (uint32_t *)(S + o_acc),
-                                                         (uint32_t *)(S + o_rank), d_total, d_payload_off, (uint64_t)cap);
+                                                         (uint32_t *)(S + o_rank), d_total, d_payload_off, (uint64_t)cap, d_last_end);
             OIP_CUDA(cudaGetLastError());
             ctx->launches++;
         }
@@ -1269,26 +1314,52 @@ extern "C" int oip_aos_scan(oip_ctx *ctx, const uint8_t *d_buf, size_t n_bytes, 
         }
         const unsigned long long *hc = (const unsigned long long *)(hb + 8);
         if (counters) { counters[0] = (int64_t)hc[0]; counters[1] = (int64_t)hc[1]; counters[2] = (int64_t)hc[2]; }
+        if (carry_out) { // where the next shard's scan starts, relative to its first byte
+            const unsigned long long le = *(const unsigned long long *)(hb + 32);
+            *carry_out = (int64_t)std::max<unsigned long long>(std::max<size_t>(carry_in, own_bytes), le) - (int64_t)own_bytes;
+        }
         if (d_payload_off && hc[0] > cap) return fail(OIP_E_INVALID, "oip_aos_scan: %llu valid frames exceed capacity %zu", hc[0], cap);
         return OIP_OK;
     }
     return fail(OIP_E_NOMEM, "oip_aos_scan: candidate table overflow");
 }
 
+static int imtr_deframe_impl(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_payload_off, int64_t n_payload, int skip,
+                             int64_t nf, long long prev_seq, uint8_t *d_imdt, size_t cap, int64_t stats[9], int64_t *imdt_bytes,
+                             int64_t seq_info[3]);
+
 extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_payload_off, int64_t n_payload,
                                 uint8_t *d_imdt, size_t cap, int64_t stats[9], int64_t *imdt_bytes)
+{
+    if (n_payload < 0) return fail(OIP_E_INVALID, "oip_imtr_deframe: n_payload < 0");
+    return imtr_deframe_impl(ctx, d_buf, d_payload_off, n_payload, 0, n_payload * 880 / 882 /* frames cut by the cadence, ref :487-510 */, 0,
+                             d_imdt, cap, stats, imdt_bytes, nullptr);
+}
+
+extern "C" int oip_imtr_deframe_shard(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_payload_off, int64_t n_payload,
+                                      int skip_bytes, int64_t n_frames, int64_t prev_seq, uint8_t *d_imdt, size_t cap, int64_t stats[9],
+                                      int64_t *imdt_bytes, int64_t seq_info[3])
+{
+    if (n_payload < 0 || n_frames < 0 || skip_bytes < 0 || skip_bytes > 881 || (int64_t)skip_bytes + n_frames * 882 > n_payload * 880)
+        return fail(OIP_E_INVALID, "oip_imtr_deframe_shard: %lld frames from byte %d do not fit %lld payloads", (long long)n_frames, skip_bytes,
+                    (long long)n_payload);
+    return imtr_deframe_impl(ctx, d_buf, d_payload_off, n_payload, skip_bytes, n_frames, prev_seq, d_imdt, cap, stats, imdt_bytes, seq_info);
+}
+
+static int imtr_deframe_impl(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_payload_off, int64_t n_payload, int skip,
+                             int64_t nf, long long prev_seq, uint8_t *d_imdt, size_t cap, int64_t stats[9], int64_t *imdt_bytes,
+                             int64_t seq_info[3])
 {
     OIP_CHECK_CTX(ctx);
     if (stats) { for (int i = 0; i < 9; ++i) stats[i] = 0; stats[7] = -1; }
     if (imdt_bytes) *imdt_bytes = 0;
-    if (n_payload < 0) return fail(OIP_E_INVALID, "oip_imtr_deframe: n_payload < 0");
-    const int64_t nf = n_payload * 880 / 882; // frames cut by the cadence (ref :487-510)
+    if (seq_info) { seq_info[0] = seq_info[1] = -1; seq_info[2] = -1; }
     if (nf == 0) return OIP_OK;
     if (!d_buf || !d_payload_off || !d_imdt) return fail(OIP_E_INVALID, "oip_imtr_deframe: null pointer");
     if (nf > 0x7fffffff) return fail(OIP_E_INVALID, "oip_imtr_deframe: too many frames for one call");
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-    const size_t o_hdr = take(64); // restart_last | n_restarts | n_gaps (u64 each) | total(u32) | first_chid(i32) | n_bad[4] (u64)
+    const size_t o_hdr = take(96); // restart_last | n_restarts | n_gaps (u64 each) | total(u32) | first_chid(i32) | n_bad[4] (u64) | seq first, last (u64)
     const size_t o_status = take((size_t)nf);
     const size_t o_chid = take((size_t)nf);
     const size_t o_seq = take((size_t)nf * 4);
@@ -1298,20 +1369,20 @@ extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64
     const size_t o_scan = take(scan_scratch_elems(nf) * 4);
     int rc = ensure_scratch(ctx, o);
     if (rc) return rc;
-    rc = ensure_pinned(ctx, 64);
+    rc = ensure_pinned(ctx, 96);
     if (rc) return rc;
     uint8_t *S = (uint8_t *)ctx->d_scratch;
     unsigned long long *d_hdr = (unsigned long long *)(S + o_hdr);
     uint32_t *d_total = (uint32_t *)(S + o_hdr + 24);
     int *d_first_chid = (int *)(S + o_hdr + 28);
     unsigned long long *d_bad = (unsigned long long *)(S + o_hdr + 32);
-    OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 64, ctx->stream));
+    OIP_CUDA(cudaMemsetAsync(S + o_hdr, 0, 96, ctx->stream));
     OIP_CUDA(cudaMemsetAsync(d_first_chid, 0xFF, 4, ctx->stream));
     // one stream-ordered chain, one host round trip at the end
     const bool speculative = (uint64_t)nf * 866 <= (uint64_t)cap; // room for every cut frame: validate writes them in place
     imtr_validate_kernel<<<(unsigned)((nf + IMTR_BATCH - 1) / IMTR_BATCH), IMTR_T, 0, ctx->stream>>>(
         d_buf, d_payload_off, n_payload, nf, S + o_status, (uint32_t *)(S + o_seq), S + o_chid, (uint32_t *)(S + o_valid), d_bad,
-        speculative ? d_imdt : nullptr);
+        speculative ? d_imdt : nullptr, skip);
     OIP_CUDA(cudaGetLastError());
     ctx->launches++;
     rc = exclusive_scan_u32(ctx, (uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank), nf, (uint32_t *)(S + o_scan), d_total);
@@ -1320,15 +1391,15 @@ extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64
     imtr_compact_seq_kernel<<<gb, 256, 0, ctx->stream>>>((uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank),
                                                          (uint32_t *)(S + o_seq), nf, (uint32_t *)(S + o_seqc));
     OIP_CUDA(cudaGetLastError());
-    imtr_rules_kernel<<<gb, 256, 0, ctx->stream>>>((uint32_t *)(S + o_seqc), d_total, d_hdr, d_hdr + 1, d_hdr + 2);
+    imtr_rules_kernel<<<gb, 256, 0, ctx->stream>>>((uint32_t *)(S + o_seqc), d_total, d_hdr, d_hdr + 1, d_hdr + 2, prev_seq, d_hdr + 8);
     OIP_CUDA(cudaGetLastError());
     imtr_copy_kernel<<<(unsigned)std::min<int64_t>((nf * 32 + 255) / 256, (int64_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(
         d_buf, d_payload_off, n_payload, nf, (uint32_t *)(S + o_valid), (uint32_t *)(S + o_rank), d_hdr, S + o_chid, d_imdt,
-        (uint64_t)cap, d_first_chid, d_total, speculative ? 1 : 0);
+        (uint64_t)cap, d_first_chid, d_total, speculative ? 1 : 0, skip);
     OIP_CUDA(cudaGetLastError());
     ctx->launches += 3;
     uint8_t *hp = (uint8_t *)ctx->h_pinned;
-    OIP_CUDA(cudaMemcpyAsync(hp, S + o_hdr, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    OIP_CUDA(cudaMemcpyAsync(hp, S + o_hdr, 96, cudaMemcpyDeviceToHost, ctx->stream));
     OIP_CUDA(cudaStreamSynchronize(ctx->stream));
     const unsigned long long *hh = (const unsigned long long *)hp;
     const uint32_t n_valid = *(const uint32_t *)(hp + 24);
@@ -1338,6 +1409,10 @@ extern "C" int oip_imtr_deframe(oip_ctx *ctx, const uint8_t *d_buf, const uint64
     if (stats) {
         stats[0] = nf; stats[1] = n_valid; stats[2] = bad[1]; stats[3] = bad[2]; stats[4] = bad[3]; stats[5] = bad[4];
         stats[6] = (int64_t)hh[2]; stats[7] = n_valid ? *(int *)(hp + 28) : -1; stats[8] = (int64_t)hh[1];
+    }
+    if (seq_info && n_valid) {
+        seq_info[0] = (int64_t)hh[8]; seq_info[1] = (int64_t)hh[9];
+        seq_info[2] = hh[1] ? (int64_t)hh[0] : -1; // index (among this call's valid frames) of the last restart, -1: none
     }
     if (imdt_bytes) *imdt_bytes = out_frames * 866;
     return OIP_OK;

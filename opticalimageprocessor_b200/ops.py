@@ -349,6 +349,34 @@ def aos_scan(ctx: Context, buf: torch.Tensor):
     return off[: cnt[0]], np.array(list(cnt), np.int64)
 
 
+def aos_scan_shard(ctx: Context, buf: torch.Tensor, own_bytes: int, carry_in: int = 0):
+    """byte-range shard of the AOS scan (oip_aos_scan_shard): buf = the shard's own bytes + up to 1023 halo bytes.
+    Returns (payload_off relative to buf [n_valid], counters np.int64[3], carry_out)."""
+    n = buf.numel()
+    cap = n // 1024 + 1
+    off = torch.empty(cap, dtype=torch.int64, device=buf.device)
+    cnt = (C.c_int64 * 3)()
+    co = C.c_int64(0)
+    check(ctx.lib.oip_aos_scan_shard(ctx.h, buf.data_ptr(), n, own_bytes, carry_in, off.data_ptr(), cap, cnt, C.byref(co)))
+    return off[: cnt[0]], np.array(list(cnt), np.int64), int(co.value)
+
+
+def imtr_deframe_shard(ctx: Context, buf: torch.Tensor, payload_off: torch.Tensor, skip: int, n_frames: int, prev_seq: int = -1):
+    """shard of the IMTR re-framing (oip_imtr_deframe_shard).  Returns (imdt piece, info dict for sharding.imtr_combine)."""
+    n = payload_off.numel()
+    cap = (n_frames + 1) * 866
+    imdt = torch.empty(cap, dtype=torch.uint8, device=buf.device)
+    st = (C.c_int64 * 9)()
+    nb = C.c_int64(0)
+    si = (C.c_int64 * 3)()
+    check(ctx.lib.oip_imtr_deframe_shard(ctx.h, buf.data_ptr(), payload_off.data_ptr(), n, skip, n_frames, prev_seq, imdt.data_ptr(), cap,
+                                         st, C.byref(nb), si))
+    info = dict(n_frames=int(st[0]), n_valid=int(st[1]), bad=[int(st[2]), int(st[3]), int(st[4]), int(st[5])], first_seq=int(si[0]),
+                last_seq=int(si[1]), gaps=int(st[6]), restarts=int(st[8]), local_restart=int(si[2]), first_chid=int(st[7]),
+                imdt_bytes=int(nb.value))
+    return imdt[: nb.value], info
+
+
 def imtr_deframe(ctx: Context, buf: torch.Tensor, payload_off: torch.Tensor):
     n = payload_off.numel()
     cap = (n * 880 // 882 + 1) * 866

@@ -196,3 +196,105 @@ def mss_rank_sections(secs, world: int, rank: int):
             out.append(s)
         acc += s[4]
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Stage 1 on byte-range shards of one downlink file (SURVEY 8e; ref aux_separator.h:395-467 is one sequential scan)
+# ------------------------------------------------------------------------------------------------
+AOS_FRAME = 1024
+
+
+def aos_shard_ranges(n_bytes: int, world: int, phase: int = 0):
+    """[first, last) file bytes whose sync candidates rank r owns: equal runs of whole 1024-byte slots at the cadence phase
+    of the file (the offset of its first sync word), so that in a clean downlink no frame straddles a boundary and every
+    shard's scan starts at its first byte; rank 0 also owns the bytes in front of the phase, the last rank the tail.
+    A rank READS [first, min(n_bytes, last + 1023)): the halo lets it validate the frames that start near its end."""
+    phase = phase % AOS_FRAME if n_bytes > phase else 0
+    slots = max(0, (n_bytes - phase) // AOS_FRAME)
+    out = []
+    for r in range(world):
+        a = 0 if r == 0 else phase + (slots * r // world) * AOS_FRAME
+        b = n_bytes if r == world - 1 else phase + (slots * (r + 1) // world) * AOS_FRAME
+        out.append((a, max(a, b)))
+    return out
+
+
+def aos_resolve_carries(scan_shard, world: int, rank: int, group=None, max_rounds: int = None):
+    """Runs the shard scans with ONE all-gather per round.  scan_shard(carry_in) -> (result, carry_out, n_valid)
+    scans this rank's shard from buffer offset carry_in.  Round 0 assumes carry_in = 0 everywhere (true whenever the
+    boundaries sit on the frame cadence); the all-gather of (carry_in used, carry_out, n_valid) shows every rank the carry
+    its left neighbour produced; a rank whose assumption was wrong scans again.  A scan re-synchronises at the first frame
+    that no earlier frame overlaps, so carry_out practically never depends on carry_in and the second round is final;
+    the loop is bounded by `world` rounds for the pathological chain.
+    Returns (result, carry_in, [n_valid of every rank])."""
+    import torch
+    import torch.distributed as dist
+    carry_in = 0
+    res, carry_out, n_valid = scan_shard(carry_in)
+    rounds = world if max_rounds is None else max_rounds
+    for _ in range(rounds):
+        mine = torch.tensor([carry_in, carry_out, n_valid], dtype=torch.int64)
+        allv = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
+        if world > 1:
+            dev = None
+            if dist.get_backend(group) == "nccl":
+                dev = torch.device("cuda", torch.cuda.current_device())
+                mine = mine.to(dev)
+                allv = [t.to(dev) for t in allv]
+            dist.all_gather(allv, mine, group=group)
+            allv = [t.cpu() for t in allv]
+        else:
+            allv = [mine]
+        want = 0 if rank == 0 else int(allv[rank - 1][1])
+        consistent = all((0 if r == 0 else int(allv[r - 1][1])) == int(allv[r][0]) for r in range(world))
+        if consistent:
+            return res, carry_in, [int(t[2]) for t in allv]
+        if want != carry_in:
+            carry_in = want
+            res, carry_out, n_valid = scan_shard(carry_in)
+    raise RuntimeError("AOS shard carries did not settle")
+
+
+def imtr_shard_frames(n_valid_all, rank: int):
+    """The fixed 882-byte cadence over the concatenated 880-byte payloads (ref aux_separator.h:487-510) on shards: rank r's
+    payloads are stream bytes [880 * P_r, 880 * P_{r+1}) with P_r = payloads of the ranks before it (prefix of the
+    all-gathered n_valid).  It owns the frames that START in its range: returns (first_frame, n_frames, skip, halo_payloads):
+    skip = bytes of its first payload that still belong to the previous rank's last frame, halo_payloads = payloads of the
+    following ranks its last frame reaches into (0..2)."""
+    total = sum(n_valid_all)
+    p0 = sum(n_valid_all[:rank])
+    p1 = p0 + n_valid_all[rank]
+    n_frames_global = total * 880 // 882
+    f0 = (880 * p0 + 881) // 882
+    f1 = min((880 * p1 + 881) // 882, n_frames_global)
+    n = max(0, f1 - f0)
+    skip = 882 * f0 - 880 * p0 if n else 0
+    halo = 0
+    if n:
+        end = 882 * f1                       # one past the last stream byte of my last frame
+        halo = max(0, (end - 880 * p1 + 879) // 880)
+    return f0, n, skip, halo
+
+
+def imtr_combine(infos):
+    """Puts the shards of the IMTR re-framing together (ref aux_separator.h:513-533: the sequence rules look at the
+    previously ACCEPTED frame, which for a shard's first valid frame lives on another rank).
+    infos[r] = dict(n_frames, n_valid, bad=[sig, endsig, type, crc], first_seq, last_seq, gaps, restarts (both WITHOUT the
+    rule of the shard's first valid frame), local_restart (index of the last restart among its valid frames, -1 none),
+    first_chid, imdt_bytes) -- what every rank all-gathers (a dozen integers).
+    Returns (keep[r]: does rank r's IMDT piece belong to the product, stats[9] of the whole stream)."""
+    prev, gaps, restarts, last_restart_rank = 0, 0, 0, -1
+    for r, q in enumerate(infos):
+        if q["n_valid"] == 0:
+            continue
+        boundary_restart = prev == 0                                   # :513-528, lastImtrSeq == 0
+        restarts += int(boundary_restart) + q["restarts"]
+        gaps += int(prev + 1 != q["first_seq"]) + q["gaps"]            # :530-533
+        if boundary_restart or q["local_restart"] >= 0:
+            last_restart_rank = r
+        prev = q["last_seq"]
+    keep = [q["n_valid"] > 0 and r >= last_restart_rank for r, q in enumerate(infos)]
+    n_valid = sum(q["n_valid"] for q in infos)
+    stats = [sum(q["n_frames"] for q in infos), n_valid] + [sum(q["bad"][k] for q in infos) for k in range(4)] + \
+            [gaps, infos[last_restart_rank]["first_chid"] if last_restart_rank >= 0 else -1, restarts]
+    return keep, stats

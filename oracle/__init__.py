@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
         L.oipo_aos_validate.argtypes = [u8p] + [C.POINTER(C.c_uint32)] * 4
         L.oipo_aos_scan.restype = C.c_int64
         L.oipo_aos_scan.argtypes = [u8p, C.c_size_t, u64p, C.c_size_t, i64p]
+        L.oipo_aos_scan_range.restype = C.c_int64
+        L.oipo_aos_scan_range.argtypes = [u8p, C.c_size_t, C.c_size_t, C.c_size_t, u64p, C.c_size_t, i64p, C.POINTER(C.c_uint64)]
         L.oipo_imtr_deframe.restype = C.c_int64
         L.oipo_imtr_deframe.argtypes = [u8p, u64p, C.c_int64, u8p, C.c_size_t, i64p]
         L.oipo_image_frames.restype = C.c_int64
@@ -154,6 +156,18 @@ def aos_scan(buf: np.ndarray):
     cnt = np.zeros(3, np.int64)
     n = lib().oipo_aos_scan(buf, buf.size, off, cap, cnt)
     return off[:n].copy(), cnt
+
+
+def aos_scan_range(buf: np.ndarray, start: int, own_end: int):
+    """byte-range shard of the scan: candidates that start in [start, own_end) of buf (which carries the halo after own_end);
+    returns (payload offsets, counters, next search position)"""
+    buf = np.ascontiguousarray(buf, np.uint8)
+    cap = buf.size // 1024 + 1
+    off = np.zeros(cap, np.uint64)
+    cnt = np.zeros(3, np.int64)
+    nxt = C.c_uint64(0)
+    n = lib().oipo_aos_scan_range(buf, buf.size, start, own_end, off, cap, cnt, C.byref(nxt))
+    return off[:n].copy(), cnt, int(nxt.value)
 
 
 def imtr_deframe(buf: np.ndarray, payload_off: np.ndarray):

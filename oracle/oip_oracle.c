@@ -83,6 +83,39 @@ int64_t oipo_aos_scan(const uint8_t *buf, size_t n, uint64_t *payload_off, size_
     return valid;
 }
 
+/* The same scan restricted to the candidates that start in [start, own_end) of a buffer of n bytes (a byte-range shard,
+ * SURVEY 8e): the sequential loop of aux_separator.h:421-461 entered at search position `start` and left when the next
+ * sync word starts at or after own_end.  *next_pos = where the scan would go on (>= own_end when a frame accepted here
+ * reaches past the shard).  Running the shards one after the other, each from the previous one's next_pos, IS the
+ * whole-file scan. */
+int64_t oipo_aos_scan_range(const uint8_t *buf, size_t n, size_t start, size_t own_end, uint64_t *payload_off, size_t cap,
+                            int64_t counters[3], uint64_t *next_pos)
+{
+    static const uint8_t sync[4] = {0x1A, 0xCF, 0xFC, 0x1D};
+    int64_t valid = 0, invalid = 0, empty = 0;
+    size_t p = start;
+    for (;;) {
+        if (p >= n || n - p < 1024) break;                             /* :623 */
+        const uint8_t *hit = (const uint8_t *)memmem(buf + p, n - p, sync, 4);
+        if (!hit) break;
+        size_t h = (size_t)(hit - buf);
+        if (h >= own_end) break;                                       /* the next shard's candidate */
+        if (h + 1024 > n) break;
+        int r = oipo_aos_validate(hit, NULL, NULL, NULL, NULL);
+        if (r != 1) {
+            if (r < 0) invalid++; else empty++;
+            p = h + 4;
+            continue;
+        }
+        if ((size_t)valid < cap && payload_off) payload_off[valid] = h + 14;
+        valid++;
+        p = h + 1024;
+    }
+    if (counters) { counters[0] = valid; counters[1] = invalid; counters[2] = empty; }
+    if (next_pos) *next_pos = p;
+    return valid;
+}
+
 /* ref aux_separator.h:469-556 (cadence :499-510), ValidateImtrFrame :558-590 */
 int64_t oipo_imtr_deframe(const uint8_t *buf, const uint64_t *payload_off, int64_t n_payload,
                           uint8_t *imdt, size_t cap, int64_t stats[9])

@@ -42,6 +42,10 @@ int oipo_aos_validate(const uint8_t *frame, uint32_t *vcid, uint32_t *seq, uint3
 int64_t oipo_aos_scan(const uint8_t *buf, size_t n, uint64_t *payload_off, size_t cap,
                       int64_t counters[3]);
 
+/* byte-range shard of the scan: candidates starting in [start, own_end); see oip_oracle.c */
+int64_t oipo_aos_scan_range(const uint8_t *buf, size_t n, size_t start, size_t own_end, uint64_t *payload_off, size_t cap,
+                            int64_t counters[3], uint64_t *next_pos);
+
 /* DataTransFrameParser + ValidateImtrFrame. ref aux_separator.h:469-590.
  * Cuts the concatenated 880-byte payloads at a fixed 882-byte cadence from stream byte 0,
  * validates, appends the 866-byte body of each valid frame to imdt.

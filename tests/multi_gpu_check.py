@@ -115,6 +115,45 @@ def main():
     if not ok_s:
         print(f"rank {rank}: sharded offset estimate {mean_g} vs whole strip {mean_w} (owners {owners})", flush=True)
     ok = ok and ok_s
+    # ---- stage 1 on byte-range shards: every rank scans its part of ONE downlink file (boundaries that cut
+    #      through frames), the carries settle with one all-gather per round, the 3 counters go through an all-reduce,
+    #      the IMTR cadence starts at the prefix of the all-gathered payload counts, the seq rules are combined on the host
+    from test_sharding_cpu import _stage1_file
+    fbuf = _stage1_file(prefix=b"\x00" * 13, restart_at=77)
+    off_w, cnt_w = oracle.aos_scan(fbuf)
+    imdt_w, st_w = oracle.imtr_deframe(fbuf, off_w)
+    fa, fb = fbuf.size * rank // world + (3 if rank else 0), fbuf.size * (rank + 1) // world + (3 if rank + 1 < world else 0)
+    fsub = torch.from_numpy(np.concatenate([fbuf[fa:min(fbuf.size, fb + 1023)], np.zeros(2 * 880, np.uint8)])).cuda()   # + room for 2 halo payloads
+    n_sub = min(fbuf.size, fb + 1023) - fa
+
+    def scan(carry):
+        o, c, co = ops.aos_scan_shard(ctx, fsub[:n_sub], fb - fa, carry)
+        return (o, c), co, int(c[0])
+    (poff, pcnt), carry_in, n_valid_all = sharding.aos_resolve_carries(scan, world, rank)
+    tc = torch.from_numpy(pcnt.copy()).cuda()
+    dist.all_reduce(tc)
+    heads = [None] * world
+    mine_heads = [fsub[int(o):int(o) + 880].cpu().numpy() for o in poff[:2].tolist()]
+    dist.all_gather_object(heads, mine_heads)
+    f0, nf, skip, halo = sharding.imtr_shard_frames(n_valid_all, rank)
+    following = [h for q in range(rank + 1, world) for h in heads[q]][:halo]
+    offs = poff.tolist()
+    for k, h in enumerate(following):
+        fsub[n_sub + 880 * k:n_sub + 880 * (k + 1)] = torch.from_numpy(h).cuda()
+        offs.append(n_sub + 880 * k)
+    piece, info = ops.imtr_deframe_shard(ctx, fsub, torch.tensor(offs, dtype=torch.int64, device="cuda"), skip, nf)
+    infos = [None] * world
+    dist.all_gather_object(infos, info)
+    keep, st_all = sharding.imtr_combine(infos)
+    pieces = [None] * world
+    dist.all_gather_object(pieces, piece.cpu().numpy() if keep[rank] else np.zeros(0, np.uint8))
+    ok_f = tc.cpu().tolist() == cnt_w.tolist() and st_all == st_w.tolist() and np.array_equal(np.concatenate(pieces), imdt_w)
+    gathered_off = [None] * world
+    dist.all_gather_object(gathered_off, (poff.cpu().numpy().astype(np.uint64) + np.uint64(fa)).tolist())
+    ok_f = ok_f and sum(gathered_off, []) == off_w.tolist() and (rank == 0 or carry_in > 0)
+    if not ok_f:
+        print(f"rank {rank}: sharded stage 1 differs from the whole-file oracle (counters {tc.cpu().tolist()} vs {cnt_w.tolist()}, stats {st_all} vs {st_w.tolist()})", flush=True)
+    ok = ok and ok_f
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()

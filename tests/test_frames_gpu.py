@@ -336,3 +336,30 @@ def test_packed_lines_extension(ctx, oracle_mod, bits):
     want = oracle_mod.pan_pipeline(imgs, kbs, [0, -0.83], [0, 3.19], f)
     got = ops.pan_pipeline(ctx, [_dev(r) for r in raws], [_dev(k) for k in kbs], [0, -0.83], [0, 3.19], f, fmt=fmt, w=w)
     assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("prefix,restart_at", [(b"", None), (b"\x00" * 13, 77)])
+@pytest.mark.parametrize("world", [2, 5])
+def test_stage1_byte_range_shards_on_the_gpu(ctx, oracle_mod, world, prefix, restart_at):
+    """oip_aos_scan_shard + oip_imtr_deframe_shard driven by the same two exchanges as the CPU test
+    (tests/test_sharding_cpu.py, where gloo carries them): shards on and off the frame cadence, a sequence restart and a bad
+    IMTR frame -- payload list, counters, IMDT bytes and IMTR stats equal the sequential whole-file oracle"""
+    from opticalimageprocessor_b200 import ops, sharding
+    from test_sharding_cpu import _run_stage1_sharded, _stage1_file
+    buf = _stage1_file(prefix=prefix, restart_at=restart_at)
+    off_w, cnt_w = oracle_mod.aos_scan(buf)
+    imdt_w, st_w = oracle_mod.imtr_deframe(buf, off_w)
+
+    def aos_shard(sub, own, carry):
+        o, c, co = ops.aos_scan_shard(ctx, _dev(sub), own, carry)
+        return o.cpu().numpy().astype(np.uint64), c, co
+
+    def imtr_shard(ext, offs, skip, nf):
+        piece, info = ops.imtr_deframe_shard(ctx, _dev(ext), _dev(offs.astype(np.int64)), skip, nf)
+        return piece.cpu().numpy(), info
+    for ranges in (sharding.aos_shard_ranges(buf.size, world, len(prefix)),
+                   [(buf.size * r // world + (3 if r else 0), buf.size * (r + 1) // world + (3 if r + 1 < world else 0)) for r in range(world)]):
+        off, cnt, imdt, stats, carries = _run_stage1_sharded(buf, world, ranges, aos_shard, imtr_shard)
+        assert np.array_equal(off, off_w) and cnt.tolist() == cnt_w.tolist()
+        assert stats == st_w.tolist(), (stats, st_w.tolist())
+        assert np.array_equal(imdt, imdt_w)

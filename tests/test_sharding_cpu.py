@@ -284,3 +284,154 @@ def test_mss_sections_follow_the_reference_loop_and_partition_over_ranks():
         k, part = oracle.band_align([p[o:o + m] for p in planes], cX, cY, lines_per_section=300, overlap=40, keep_leading=(y0 == 0),
                                     min_process_lines=41)
         assert k == no and np.array_equal(part[:k], whole[o0:o0 + no])
+
+
+# ------------------------------------------------------------------------------------------------ stage 1 on byte-range shards
+def _stage1_file(seed=3, prefix=b"", restart_at=None):
+    import numpy as np
+    from opticalimageprocessor_b200 import synth
+    imdt, _ = synth.make_imdt(6, 32, 8, seed=seed)
+    imtr = synth.imtr_frames(imdt, chid=0x22)
+    if restart_at is not None:                      # a frame with sequence number 0: the frame after it re-creates the IMDT file
+        imtr[restart_at, 4:8] = 0
+        synth.refresh_imtr_crc(imtr)
+    imtr[40, 300] ^= 0x10                            # one IMTR frame with a bad CRC (its AOS frames are fine)
+    aos = synth.aos_frames(imtr.reshape(-1))
+    return synth.build_aos_file(aos, empty_every=7, bad_crc_at={3, 50}, bad_inject_at={9}, prefix=prefix)
+
+
+def _oracle_imtr_shard(buf, payload_off, skip, n_frames):
+    """CPU stand-in for oip_imtr_deframe_shard(prev_seq unknown): the oracle's re-framing on the shard's own stream"""
+    import numpy as np
+    import oracle
+    stream = np.concatenate([buf[int(o):int(o) + 880] for o in payload_off]) if len(payload_off) else np.zeros(0, np.uint8)
+    stream = stream[skip:skip + 882 * n_frames]
+    pad = (-stream.size) % 880
+    stream = np.concatenate([stream, np.zeros(pad, np.uint8)])
+    offs = np.arange(0, stream.size, 880, dtype=np.uint64)
+    imdt, st = oracle.imtr_deframe(stream, offs)
+    assert st[0] == n_frames
+    # the oracle applied "previous seq = 0" to the first valid frame: take that rule out again, keep the sequence numbers
+    seqs = []
+    for q in range(n_frames):
+        fr = stream[882 * q:882 * q + 882]
+        ok = fr[:4].tobytes() == b"\x49\x54\xCE\x1F" and fr[878:882].tobytes() == b"\x2E\xE9\xC8\xFD" and fr[9] == 0x22 and \
+            oracle.crc16(fr[:876]) == (int(fr[876]) << 8 | int(fr[877]))
+        if ok:
+            seqs.append(int.from_bytes(fr[4:8].tobytes(), "big"))
+    local_restart = max([k for k in range(1, len(seqs)) if seqs[k - 1] == 0], default=-1)
+    info = dict(n_frames=n_frames, n_valid=len(seqs), bad=[int(st[2]), int(st[3]), int(st[4]), int(st[5])],
+                first_seq=seqs[0] if seqs else -1, last_seq=seqs[-1] if seqs else -1,
+                gaps=sum(1 for k in range(1, len(seqs)) if seqs[k - 1] + 1 != seqs[k]),
+                restarts=sum(1 for k in range(1, len(seqs)) if seqs[k - 1] == 0), local_restart=local_restart,
+                first_chid=int(st[7]), imdt_bytes=int(imdt.size))
+    return imdt, info
+
+
+def _run_stage1_sharded(buf, world, ranges, aos_shard, imtr_shard):
+    """sequential simulation of `world` ranks with the two exchanges of SURVEY 8e spelled out"""
+    import numpy as np
+    n = buf.size
+    subs = [buf[a:min(n, b + 1023)] for a, b in ranges]
+    # round 0: every shard from its first byte; "all-gather" of (carry_in, carry_out, n_valid); re-run where the assumption was wrong
+    res = [aos_shard(subs[r], ranges[r][1] - ranges[r][0], 0) for r in range(world)]
+    carry_in = [0] * world
+    for _ in range(world):
+        want = [0] + [res[r][2] for r in range(world - 1)]
+        if want == carry_in:
+            break
+        for r in range(world):
+            if want[r] != carry_in[r]:
+                carry_in[r] = want[r]
+                res[r] = aos_shard(subs[r], ranges[r][1] - ranges[r][0], carry_in[r])
+    else:
+        raise AssertionError("carries did not settle")
+    counters = sum(r_[1] for r_ in res)
+    n_valid = [int(r_[1][0]) for r_ in res]
+    # halo payloads: the first two payloads of every rank travel ("all-gather" of 1760 bytes + n_valid)
+    heads = [[subs[r][int(o):int(o) + 880] for o in res[r][0][:2]] for r in range(world)]
+    pieces, infos = [], []
+    for r in range(world):
+        f0, nf, skip, halo = sharding.imtr_shard_frames(n_valid, r)
+        following = [h for q in range(r + 1, world) for h in heads[q]][:halo]
+        assert len(following) == halo
+        ext = np.concatenate([subs[r]] + following) if following else subs[r]
+        offs = list(res[r][0]) + [subs[r].size + 880 * k for k in range(halo)]
+        piece, info = imtr_shard(ext, np.array(offs, np.uint64), skip, nf)
+        pieces.append(piece)
+        infos.append(info)
+    keep, stats = sharding.imtr_combine(infos)
+    all_off = np.concatenate([res[r][0].astype(np.uint64) + np.uint64(ranges[r][0]) for r in range(world)])
+    imdt = np.concatenate([pieces[r] for r in range(world) if keep[r]] or [np.zeros(0, np.uint8)])
+    return all_off, counters, imdt, stats, carry_in
+
+
+@pytest.mark.parametrize("prefix,restart_at", [(b"", None), (b"\x00" * 13, None), (b"", 77), (b"\x07" * 5, 150)])
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_stage1_byte_range_shards_equal_the_whole_file(world, prefix, restart_at):
+    """AOS scan + IMTR re-framing on byte-range shards (carry resolution, payload-count prefix, seq rules across ranks)
+    == the sequential whole-file oracle: payload list, the 3 counters, IMDT bytes and the 9 IMTR stats"""
+    import numpy as np
+    import oracle
+    buf = _stage1_file(prefix=prefix, restart_at=restart_at)
+    off_w, cnt_w = oracle.aos_scan(buf)
+    imdt_w, st_w = oracle.imtr_deframe(buf, off_w)
+
+    def aos_shard(sub, own, carry):
+        o, c, nxt = oracle.aos_scan_range(sub, carry, own)
+        return o, c, max(0, nxt - own)
+    for ranges in (sharding.aos_shard_ranges(buf.size, world, len(prefix)),                       # on the frame cadence: no carries
+                   [(buf.size * r // world + (3 if r else 0), buf.size * (r + 1) // world + (3 if r + 1 < world else 0)) for r in range(world)]):
+        off, cnt, imdt, stats, carries = _run_stage1_sharded(buf, world, ranges, aos_shard, _oracle_imtr_shard)
+        assert np.array_equal(off, off_w) and cnt.tolist() == cnt_w.tolist()
+        assert stats == st_w.tolist(), (stats, st_w.tolist())
+        assert np.array_equal(imdt, imdt_w)
+    assert any(c for c in carries)    # the second partition cuts through frames
+
+
+def _carry_worker(rank, world, port, q):
+    """aos_resolve_carries over gloo: ONE all-gather per round, the rank with a wrong assumption scans again"""
+    import numpy as np
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        buf = _stage1_file()
+        a, b = [(0, 70001), (70001, buf.size)][rank]
+        sub = buf[a:min(buf.size, b + 1023)]
+        calls = []
+
+        def scan(carry):
+            calls.append(carry)
+            o, c, nxt = oracle.aos_scan_range(sub, carry, b - a)
+            return (o + np.uint64(a), c), max(0, nxt - (b - a)), int(c[0])
+        (off, cnt), carry_in, n_valid_all = sharding.aos_resolve_carries(scan, world, rank)
+        t = torch.from_numpy(cnt.copy())
+        dist.all_reduce(t)                                  # the 3-counter all-reduce
+        gathered = [None] * world
+        dist.all_gather_object(gathered, off.tolist())
+        q.put((rank, calls, carry_in, n_valid_all, t.tolist(), sum(gathered, [])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_aos_carry_resolution_gloo():
+    import numpy as np
+    import oracle
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_carry_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    buf = _stage1_file()
+    off_w, cnt_w = oracle.aos_scan(buf)
+    for rank, calls, carry_in, n_valid_all, cnt, offs in res:
+        assert cnt == cnt_w.tolist() and offs == off_w.tolist() and sum(n_valid_all) == cnt_w[0]
+        assert calls == ([0] if rank == 0 else [0, carry_in]) and (rank == 0 or carry_in > 0)
