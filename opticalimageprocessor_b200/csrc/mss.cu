@@ -106,7 +106,49 @@ __global__ void __launch_bounds__(NT, 2) band_align_kernel(const __grid_constant
     d_max += 1;
     const int c_lo = (ix_min >= 0 ? ix_min : ix_min - 7) / 8 * 8;
     if (ix_max + 3 >= c_lo + SWC || RC + 3 + (d_max - d_min) > RING) {
-        if (tid == 0) atomicExch(P.err, 2); // polynomial too steep for the staged window
+        // The polynomial is too steep for the staged window (the tap rows of the tile's columns spread over more than
+        // RING rows, or its source columns over more than SWC): every thread resamples its column straight from global
+        // memory, tap by tap -- slow, exact, and what the reference computes (round 1 returned OIP_E_UNSUPPORTED here).
+        if (active) {
+            const bool be_d = P.fmt == OIP_FMT_BE16;
+            const uint8_t *bb = P.base + ((int64_t)b * wb) * 2;
+            const double *kbd = P.kb[b];
+            auto tap = [&](int t, int c) -> float {
+                if (t < 0 || t >= T.rows || c < 0 || c >= wb) return 0.f; // constant border of the section Mat (SURVEY C-1)
+                uint32_t a = *reinterpret_cast<const uint16_t *>(bb + (T.sec_off + t) * P.pitch_bytes + 2 * (int64_t)c);
+                if (be_d) a = ((a & 0xFF) << 8) | (a >> 8);
+                if (kbd) a = rrc_px(a, kbd[2 * c], kbd[2 * c + 1]);
+                return u16_to_f32(a);
+            };
+            const bool col_int_d = (unsigned)ix < (unsigned)max(wb - 3, 0);
+            uint16_t *o = P.out + ((T.dst_row0 * wb + x) * 4 + b);
+            for (int i = 0; i < T.n_rows; ++i, o += (int64_t)wb * 4) {
+                const int sy = sy_of(T.y0 + i);
+                const int iy = sat_short(sy >> 5) - 1, fy = sy & 31;
+                float wgt[4][4], v[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        wgt[r][c] = __fmul_rn(s_tab[4 * fy + r], s_tab[4 * fx + c]);
+                        v[r][c] = tap(iy + r, ix + c);
+                    }
+                float sum;
+                if ((unsigned)iy < (unsigned)max(T.rows - 3, 0) && col_int_d) {
+                    sum = dot4(v[0], wgt[0]);
+                    sum = __fadd_rn(sum, dot4(v[1], wgt[1]));
+                    sum = __fadd_rn(sum, dot4(v[2], wgt[2]));
+                    sum = __fadd_rn(sum, dot4(v[3], wgt[3]));
+                } else {
+                    sum = 0.f;
+                    sum = acc4(sum, v[0], wgt[0]);
+                    sum = acc4(sum, v[1], wgt[1]);
+                    sum = acc4(sum, v[2], wgt[2]);
+                    sum = acc4(sum, v[3], wgt[3]);
+                }
+                *o = (uint16_t)max(0, min(65535, __float2int_rn(sum)));
+            }
+        }
         return;
     }
     const bool col_int = (unsigned)ix < (unsigned)max(wb - 3, 0);
@@ -400,13 +442,7 @@ extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_m
         OIP_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
         OIP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
-    // the polynomial may exceed the staged window: report instead of returning wrong pixels
-    int e = 0;
-    OIP_CUDA(cudaMemcpyAsync(&e, ctx->d_err, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
-    OIP_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (e) {
-        OIP_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
-        return fail(OIP_E_UNSUPPORTED, "band alignment polynomial moves taps by more than the staged window allows");
-    }
+    // (no device-side error channel any more: a polynomial that exceeds the staged window is resampled tap by tap inside
+    // band_align_kernel, so the call returns without a device-to-host copy or a stream synchronisation)
     return OIP_OK;
 }

@@ -134,3 +134,23 @@ def test_sections_computed_on_their_own_equal_the_whole_strip(ctx):
                                             lines_per_section=lps, overlap=ov, line_offset=off, keep_leading=keep, src_row0=lo)
                 assert k == no
             assert torch.equal(got[:n].view(torch.int16), whole[:n].view(torch.int16))
+
+
+@pytest.mark.parametrize("cy1,cx1", [(0.5, -1.5e-4), (-0.9, 0.0), (2e-4, 0.6), (0.3, -0.4)])
+def test_steep_polynomials_are_computed(ctx, oracle_mod, cy1, cx1):
+    """a polynomial whose tap rows / columns spread beyond the staged window of a tile (round 1: OIP_E_UNSUPPORTED) is
+    resampled tap by tap inside the generic kernel: still bit-identical to the oracle, and no error is reported"""
+    from opticalimageprocessor_b200 import ops
+    rng = np.random.default_rng(31)
+    lines, wb = 420, 384
+    mixed = rng.integers(0, 65536, (lines, 4 * wb), dtype=np.uint16)
+    kbs = [synth.rrc_coeffs(wb, 120 + b) for b in range(4)]
+    cX = [[0.8 + 0.1 * b, cx1] for b in range(4)]
+    cY = [[-3.2 + b, cy1, -1e-8] for b in range(4)]
+    kw = dict(lines_per_section=200, line_offset=0, overlap=24, keep_leading=True, min_process_lines=64)
+    n_w, want = _oracle_full(oracle_mod, mixed, kbs, cX, cY, **kw)
+    n_g, got = ops.band_align(ctx, _dev(mixed), wb, [_dev(k) for k in kbs], cX, cY, **kw)
+    ctx.sync()
+    assert n_g == n_w
+    bad = np.argwhere(got.cpu().numpy()[:n_g] != want[:n_w])
+    assert bad.size == 0, f"{len(bad)} samples differ, first {bad[:5].tolist()}"
