@@ -647,19 +647,19 @@ __global__ void aos_shard_trim_kernel(const uint64_t *off, int8_t *st, uint32_t 
     if (off[i] < own) atomicMax(m_own, (uint32_t)(i + 1));
 }
 
-// A valid candidate with no valid candidate in the preceding 1023 bytes is always accepted by the
-// sequential scan (ref aux_separator.h:421-461): whatever was accepted before ends <= its offset.
+// A candidate with no VALID candidate in the preceding 1023 bytes cannot lie inside an accepted frame, so the sequential
+// scan (ref aux_separator.h:421-461) always visits it: it starts a run that is resolved on its own.  A valid one is
+// accepted there; a rejected one (empty / bad inject word / bad CRC) is counted and changes nothing for what follows.
+// (Round 1 started runs at valid candidates only: a long stretch of fill frames or of corrupted frames -- or a file without
+// a single valid frame -- was then walked by ONE thread.  ADVICE r1.)
 __global__ void aos_runstart_kernel(const uint64_t *off, const int8_t *st, const uint32_t *m_ptr, uint8_t *rs)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t m = (int64_t)*m_ptr;
     if (i >= m) return;
-    uint8_t r = 0;
-    if (st[i] == 1) {
-        r = 1;
-        for (int64_t j = i - 1; j >= 0 && off[i] - off[j] < 1024; --j)
-            if (st[j] == 1) { r = 0; break; }
-    }
+    uint8_t r = 1;
+    for (int64_t j = i - 1; j >= 0 && off[i] - off[j] < 1024; --j)
+        if (st[j] == 1) { r = 0; break; }
     rs[i] = r;
 }
 
@@ -671,16 +671,9 @@ __global__ void aos_walk_kernel(const uint64_t *off, const int8_t *st, const uin
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t m = (int64_t)*m_ptr;
     uint32_t n_inv = 0, n_emp = 0, n_val = 0;
-    if (i < m && (rs[i] || i == 0)) {
-        int64_t j = i;
+    if (i < m && rs[i]) {
         uint64_t next_free = 0; // first byte the scan may look at
-        if (rs[i]) {
-            acc[i] = 1;
-            n_val = 1;
-            next_free = off[i] + 1024;
-            j = i + 1;
-        }
-        for (; j < m && !rs[j]; ++j) {
+        for (int64_t j = i; j < m && (j == i || !rs[j]); ++j) {
             if (off[j] < next_free) { // inside an accepted frame: never seen
                 acc[j] = 0;
                 // a VALID frame shadowed by an overlapping accepted one: the scan continues INSIDE it, where the fused

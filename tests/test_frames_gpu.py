@@ -363,3 +363,16 @@ def test_stage1_byte_range_shards_on_the_gpu(ctx, oracle_mod, world, prefix, res
         assert np.array_equal(off, off_w) and cnt.tolist() == cnt_w.tolist()
         assert stats == st_w.tolist(), (stats, st_w.tolist())
         assert np.array_equal(imdt, imdt_w)
+
+
+def test_aos_scan_without_a_single_valid_frame(ctx, oracle_mod):
+    """a stretch (here: a whole file) of fill frames and corrupted frames used to be walked by one thread; now
+    every candidate that no valid frame can shadow is resolved on its own.  40000 candidates, counters equal the oracle"""
+    imdt, truth, imtr, aos = _downlink(n_frames=2)
+    bad = np.tile(aos, (400 // aos.shape[0] + 1, 1))[:400].copy()
+    bad[:, 600] ^= 0x21                                          # every frame fails its CRC
+    emp = np.tile(synth.aos_empty_frame(), (100, 1))
+    buf = np.concatenate([np.concatenate([bad, emp]).reshape(-1)] * 80)
+    off_w, cnt_w = oracle_mod.aos_scan(buf)
+    assert cnt_w.tolist() == [0, 32000, 8000]
+    _check_aos(ctx, oracle_mod, buf)
