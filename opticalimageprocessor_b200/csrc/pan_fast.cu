@@ -79,6 +79,7 @@ __device__ __forceinline__ void convert4(uint32_t a, const double *k, const doub
 struct WarpCtx {
     const CUtensorMap *tm;
     uint32_t stage0, bar0; // shared-memory addresses of this warp's stage ring and barriers
+    uint32_t le0;          // packed sources: the warp's unpacked (u16 LE) image of the stage being consumed
     int ns, lane;
 };
 
@@ -137,16 +138,62 @@ __device__ __forceinline__ void issue_stage_tiled(const FastCcd &S, const WarpCt
 
 // warp-collective.  Line formats: one lane issues the 2-D tensor copy (x: first sample of the box, a multiple of 8; the
 // tensor map counts 32-bit elements).  Tiled sources: see above.
-template <bool TILED>
+// Packed sources (PB = 12 / 10, MSB-first bit stream per line): the box origin must sit on a 16-byte boundary of the
+// packed line, i.e. on a multiple of 32 (12-bit: 48 bytes) / 64 (10-bit: 80 bytes) samples; the box covers the 16-sample
+// groups that hold the 272-sample window.
+template <int PB> __device__ __forceinline__ int packed_origin(int x) { return PB == 12 ? (x & ~31) : (x & ~63); }
+template <bool TILED, int PB = 0>
 __device__ __forceinline__ void issue_stage(const FastParams &P, const FastTile &T, const WarpCtx &C, int slot, int x, int y)
 {
     if (TILED) {
         issue_stage_tiled(P.ccd[T.ccd], C, slot, x, y, T.tmap);
     } else if (C.lane == 0) {
         const uint32_t bar = C.bar0 + 8u * slot, dst = C.stage0 + (uint32_t)slot * STAGE_BYTES;
-        mbar_expect_tx_u32(bar, STAGE_BYTES);
-        tma_load_2d(dst, C.tm, x >> 1, y, bar);
+        if (PB == 0) {
+            mbar_expect_tx_u32(bar, STAGE_BYTES);
+            tma_load_2d(dst, C.tm, x >> 1, y, bar);
+        } else {
+            constexpr int BOXW = PB == 12 ? PBOX12 : PBOX10;
+            mbar_expect_tx_u32(bar, (uint32_t)(BOXW * 4 * RC));
+            tma_load_2d(dst, C.tm, (packed_origin<PB>(x) * PB) >> 5, y, bar);
+        }
     }
+}
+// Packed sources: the stage that just arrived (RC rows of packed bytes) -> the warp's u16 little-endian stage image, the
+// same layout a tensor copy of 16-bit lines produces (ROW_BYTES per row, sample x at 2 * (x - x_le)).  16 samples = 6 / 5
+// aligned words rebuilt big-endian (one PRMT each), one funnel shift + one shift per sample, two 16-byte stores; 18 groups
+// per row cover the window, 72 per stage = 2.25 per lane.  (oip_unpack_lines does the same between two HBM buffers.)
+template <int PB>
+__device__ __forceinline__ void unpack_stage(const WarpCtx &C, uint32_t stage, int x_le)
+{
+    constexpr int NW = PB * 16 / 32, BOXB = (PB == 12 ? PBOX12 : PBOX10) * 4;
+    const int xg = x_le & ~15, xp = packed_origin<PB>(x_le);
+    const uint32_t g_byte0 = (uint32_t)(((xg - xp) * PB) >> 3);     // first group's offset inside a packed box row
+    const int lead = x_le - xg;                                      // 0 or 8: samples of group 0 in front of the image
+#pragma unroll 1
+    for (int it = C.lane; it < 18 * RC; it += 32) {
+        const int rr = it / 18, g = it - rr * 18;
+        const uint32_t src = stage + (uint32_t)rr * BOXB + g_byte0 + (uint32_t)(g * NW * 4);
+        uint32_t be[NW + 1];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) be[k] = __byte_perm(lds32(src + 4u * k), 0u, 0x0123);
+        be[NW] = 0u;
+        uint32_t px[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int bit = PB * k;
+            px[k] = __funnelshift_l(be[(bit >> 5) + 1], be[bit >> 5], bit & 31) >> (32 - PB);
+        }
+        const int s0 = 16 * g - lead;                                // image sample index of the group's first sample
+        const uint32_t dst = C.le0 + (uint32_t)rr * ROW_BYTES + (uint32_t)(2 * s0);
+        if (s0 >= 0 && s0 + 8 <= 2 * BOX_W)
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(px[0] | (px[1] << 16)), "r"(px[2] | (px[3] << 16)),
+                         "r"(px[4] | (px[5] << 16)), "r"(px[6] | (px[7] << 16)) : "memory");
+        if (s0 + 8 >= 0 && s0 + 16 <= 2 * BOX_W)
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u), "r"(px[8] | (px[9] << 16)), "r"(px[10] | (px[11] << 16)),
+                         "r"(px[12] | (px[13] << 16)), "r"(px[14] | (px[15] << 16)) : "memory");
+    }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------ REMAP warp-tile
@@ -158,7 +205,7 @@ __device__ __forceinline__ void stg_v2_if(void *p, uint32_t a, uint32_t b, bool 
                  : "memory");
 }
 
-template <int MODE, int DM, bool SWAP, bool TILED>
+template <int MODE, int DM, bool SWAP, bool TILED, int PB = 0>
 __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                            const double (&b)[8])
 {
@@ -169,7 +216,7 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
     const uint32_t offR = 2u * (uint32_t)((T.src_x0 - x0 + T.half) & ~3) + 8u * (uint32_t)lane;
     {
         const int pre = min(ns, n_chunks);
-        for (int c = 0; c < pre; ++c) issue_stage<TILED>(P, T, C, c, x0, T.src_y0 + c * RC);
+        for (int c = 0; c < pre; ++c) issue_stage<TILED, PB>(P, T, C, c, x0, T.src_y0 + c * RC);
     }
     // 2-D weights w[r][c] = fl32(wy[r] * wx[c]), identical for the whole tile
     const f2 nz = *reinterpret_cast<const f2 *>(P.tab + 128);
@@ -250,6 +297,7 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
     uint32_t phase = 0;
     mbar_wait_u32(C.bar0, 0);
     uint32_t sa = C.stage0;
+    if (PB) { unpack_stage<PB>(C, sa, x0); sa = C.le0; } // packed: rows are converted from the unpacked image of the stage
     f2 wa[7], wb[7];
     convert(sa, 0, wa);
     for (int c = 0; c + 1 < n_chunks; ++c) {
@@ -262,10 +310,14 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
         resample(wa, m + 2, B2, B3, B0, B1);
         // stage `slot` is consumed: refill it, move on to the next stage and convert its first row
         __syncwarp();
-        if (c + ns < n_chunks) issue_stage<TILED>(P, T, C, slot, x0, T.src_y0 + (c + ns) * RC);
+        if (c + ns < n_chunks) issue_stage<TILED, PB>(P, T, C, slot, x0, T.src_y0 + (c + ns) * RC);
         if (++slot == ns) { slot = 0; phase ^= 1u; }
         mbar_wait_u32(C.bar0 + 8u * slot, phase);
         sa = C.stage0 + (uint32_t)slot * STAGE_BYTES;
+        if (PB) { // the unpacked image of the previous stage has been consumed (the __syncwarp above ordered its last reads)
+            unpack_stage<PB>(C, sa, x0);
+            sa = C.le0;
+        }
         convert(sa, 0, wa);
         resample(wb, m + 3, B1, B2, B3, B0);
     }
@@ -282,7 +334,7 @@ __device__ __forceinline__ void remap_tile(const FastParams &P, const FastTile &
 }
 
 // ------------------------------------------------------------------------------------------- COPY warp-tile
-template <int MODE, bool SWAP, bool TAIL, bool TILED>
+template <int MODE, bool SWAP, bool TAIL, bool TILED, int PB = 0>
 __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                           const double (&b)[8])
 {
@@ -291,7 +343,7 @@ __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T
     const int n_chunks = (n_rows + RC - 1) / RC;
     {
         const int pre = min(ns, n_chunks);
-        for (int c = 0; c < pre; ++c) issue_stage<TILED>(P, T, C, c, T.x_begin, T.src_y0 + c * RC);
+        for (int c = 0; c < pre; ++c) issue_stage<TILED, PB>(P, T, C, c, T.x_begin, T.src_y0 + c * RC);
     }
     const bool full = 8 * lane + 8 <= T.half;       // T.half = columns of this strip: any number <= 256
     const int tail = full ? 0 : max(0, T.half - 8 * lane); // the lane that holds the strip's last odd columns
@@ -301,7 +353,8 @@ __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T
     uint32_t phase = 0;
     for (int c = 0; c < n_chunks; ++c) {
         mbar_wait_u32(C.bar0 + 8u * slot, phase);
-        const uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES + 16u * (uint32_t)lane;
+        uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES + 16u * (uint32_t)lane;
+        if (PB) { unpack_stage<PB>(C, C.stage0 + (uint32_t)slot * STAGE_BYTES, T.x_begin); sa = C.le0 + 16u * (uint32_t)lane; }
 #pragma unroll
         for (int rr = 0; rr < RC; ++rr) {
             const uint4 v = lds128(sa + rr * ROW_BYTES);
@@ -329,7 +382,7 @@ __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T
             o += pitch;
         }
         __syncwarp();
-        if (c + ns < n_chunks) issue_stage<TILED>(P, T, C, slot, T.x_begin, T.src_y0 + (c + ns) * RC);
+        if (c + ns < n_chunks) issue_stage<TILED, PB>(P, T, C, slot, T.x_begin, T.src_y0 + (c + ns) * RC);
         if (++slot == ns) { slot = 0; phase ^= 1u; }
     }
 }
@@ -340,7 +393,7 @@ __device__ __forceinline__ void copy_tile(const FastParams &P, const FastTile &T
 // column per lane, scalar FP32, both of OpenCV's accumulation orders (interior: per-row sums added row by row;
 // border: one flat left-to-right chain starting from 0) computed and selected per column.  Taps
 // outside the CCD are zero: TMA zero-fills them and their (k,b) are forced to 0.  < 0.1 % of the pixels.
-template <bool TILED>
+template <bool TILED, int PB = 0>
 __device__ __forceinline__ void edge_tile(const FastParams &P, const FastTile &T, const WarpCtx &C)
 {
     const int lane = C.lane, ns = C.ns;
@@ -350,7 +403,7 @@ __device__ __forceinline__ void edge_tile(const FastParams &P, const FastTile &T
     const uint32_t off = 2u * (uint32_t)(col - x0);
     {
         const int pre = min(ns, n_chunks);
-        for (int c = 0; c < pre; ++c) issue_stage<TILED>(P, T, C, c, x0, T.src_y0 + c * RC);
+        for (int c = 0; c < pre; ++c) issue_stage<TILED, PB>(P, T, C, c, x0, T.src_y0 + c * RC);
     }
     const bool swap = P.ccd[T.ccd].swap != 0;
     const double *kbp = P.ccd[T.ccd].kb;
@@ -370,7 +423,8 @@ __device__ __forceinline__ void edge_tile(const FastParams &P, const FastTile &T
     uint32_t phase = 0;
     for (int c = 0; c < n_chunks; ++c) {
         mbar_wait_u32(C.bar0 + 8u * slot, phase);
-        const uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES + off;
+        uint32_t sa = C.stage0 + (uint32_t)slot * STAGE_BYTES + off;
+        if (PB) { unpack_stage<PB>(C, C.stage0 + (uint32_t)slot * STAGE_BYTES, x0); sa = C.le0 + off; }
 #pragma unroll
         for (int rr = 0; rr < RC; ++rr) {
             uint32_t s;
@@ -399,26 +453,38 @@ __device__ __forceinline__ void edge_tile(const FastParams &P, const FastTile &T
             o += P.out_pitch;
         }
         __syncwarp();
-        if (c + ns < n_chunks) issue_stage<TILED>(P, T, C, slot, x0, T.src_y0 + (c + ns) * RC);
+        if (c + ns < n_chunks) issue_stage<TILED, PB>(P, T, C, slot, x0, T.src_y0 + (c + ns) * RC);
         if (++slot == ns) { slot = 0; phase ^= 1u; }
     }
 }
 
-template <int MODE, bool SWAP, bool TILED>
+template <int MODE, bool SWAP, bool TILED, int PB = 0>
 __device__ __forceinline__ void remap_dispatch(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
                                                const double (&b)[8])
 {
     const int dm = T.src_x0 & 3;
-    if (dm == 0) remap_tile<MODE, 0, SWAP, TILED>(P, T, C, k, b);
-    else if (dm == 1) remap_tile<MODE, 1, SWAP, TILED>(P, T, C, k, b);
-    else if (dm == 2) remap_tile<MODE, 2, SWAP, TILED>(P, T, C, k, b);
-    else remap_tile<MODE, 3, SWAP, TILED>(P, T, C, k, b);
+    if (dm == 0) remap_tile<MODE, 0, SWAP, TILED, PB>(P, T, C, k, b);
+    else if (dm == 1) remap_tile<MODE, 1, SWAP, TILED, PB>(P, T, C, k, b);
+    else if (dm == 2) remap_tile<MODE, 2, SWAP, TILED, PB>(P, T, C, k, b);
+    else remap_tile<MODE, 3, SWAP, TILED, PB>(P, T, C, k, b);
+}
+
+template <int MODE, int PB>
+__device__ __forceinline__ void packed_dispatch(const FastParams &P, const FastTile &T, const WarpCtx &C, const double (&k)[8],
+                                                const double (&b)[8])
+{
+    if (T.kind == FT_REMAP) remap_dispatch<MODE, false, false, PB>(P, T, C, k, b); // the unpacked image holds native u16
+    else if (T.half & 7) copy_tile<MODE, false, true, false, PB>(P, T, C, k, b);
+    else copy_tile<MODE, false, false, false, PB>(P, T, C, k, b);
 }
 
 template <int MODE>
 __device__ __forceinline__ void tile_dispatch(const FastParams &P, const FastTile &T, const WarpCtx &C, bool swap, bool tiled,
                                               const double (&k)[8], const double (&b)[8])
 {
+    const int pb = P.ccd[T.ccd].pbits;
+    if (pb == 12) { packed_dispatch<MODE, 12>(P, T, C, k, b); return; }
+    if (pb == 10) { packed_dispatch<MODE, 10>(P, T, C, k, b); return; }
     if (T.kind == FT_REMAP) {
         if (tiled) remap_dispatch<MODE, true, true>(P, T, C, k, b); // sub-images hold big-endian samples
         else if (swap) remap_dispatch<MODE, true, false>(P, T, C, k, b);
@@ -450,7 +516,10 @@ __device__ __forceinline__ void run_tile(const FastParams &P, const FastTile &T,
     }
     __syncwarp();
     if (T.kind == FT_EDGE) {
+        const int pb = P.ccd[T.ccd].pbits;
         if (tiled) edge_tile<true>(P, T, C);
+        else if (pb == 12) edge_tile<false, 12>(P, T, C);
+        else if (pb == 10) edge_tile<false, 10>(P, T, C);
         else edge_tile<false>(P, T, C);
         return;
     }
@@ -490,6 +559,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pan_fast_kernel(const __grid
     C.lane = lane;
     C.tm = nullptr;
     C.stage0 = ((smem_u32(smem_raw) + 127u) & ~127u) + (uint32_t)(warp * C.ns) * STAGE_BYTES;
+    C.le0 = ((smem_u32(smem_raw) + 127u) & ~127u) + (uint32_t)(WARPS * C.ns + warp) * STAGE_BYTES; // (allocated when a CCD is packed)
     C.bar0 = smem_u32(&bars[warp][0]);
     const FastTile T = P.tiles[(int64_t)blockIdx.x * WARPS + warp];
     if (T.kind < 0) return; // padding entry of a partial CTA; warps never synchronise with each other
@@ -539,11 +609,19 @@ int fast_encode_tmap(CUtensorMap *tm, const void *base, int w, int64_t n_rows, i
     return tmaw::encode_tmap_u32(tm, base, w, n_rows, pitch_bytes, BOX_W, RC);
 }
 
+int fast_encode_tmap_packed(CUtensorMap *tm, const void *base, int w, int bits, int64_t n_rows, int64_t pitch_bytes)
+{
+    // the packed line as 32-bit elements (w * bits / 32 of them): encode_tmap_u32 counts w / 2 elements for w samples
+    return tmaw::encode_tmap_u32(tm, base, 2 * (w * bits / 32), n_rows, pitch_bytes, bits == 12 ? PBOX12 : PBOX10, RC);
+}
+
 int fast_launch(oip_ctx *ctx, const FastParams &P, int64_t n_ctas)
 {
-    const size_t smem = (size_t)WARPS * P.n_stage * STAGE_BYTES + 128;
+    bool packed = false;
+    for (int i = 0; i < 8; ++i) packed = packed || P.ccd[i].pbits != 0;
+    const size_t smem = (size_t)WARPS * (P.n_stage + (packed ? 1 : 0)) * STAGE_BYTES + 128;
     if (!ctx->fast_attr_set) {
-        OIP_CUDA(cudaFuncSetAttribute(pan_fast_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPS * MAX_STAGE * STAGE_BYTES + 128));
+        OIP_CUDA(cudaFuncSetAttribute(pan_fast_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPS * (MAX_STAGE + 1) * STAGE_BYTES + 128));
         ctx->fast_attr_set = true;
     }
     // (a 4-CTAs/SM, 128-register instantiation was measured in round 1: no faster, heavy spills -- dropped)

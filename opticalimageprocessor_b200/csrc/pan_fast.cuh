@@ -51,6 +51,8 @@ struct FastCcd {
     const double *kb; // {k,b} per detector or null
     int32_t swap;     // 1: samples are big-endian
     int32_t tiled;    // 1: OIP_FMT_BE16_TILES -- rows are gathered from the sub-images of the IMDT stream (ref aux_separator.h:341-372)
+    int32_t pbits;    // 0, or 12 / 10: MSB-first packed samples (OIP_FMT_PACK12 / PACK10): the stage is unpacked in shared memory
+    int32_t pad2;
     // tiled sources only
     const uint8_t *tile_base;  // IMDT stream (4-byte aligned)
     const int64_t *tile_off;   // [frame * 40 + r * 8 + c] byte offset of each sub-image (multiple of 4), -1 = zero-filled frame
@@ -71,6 +73,8 @@ struct FastParams {
 
 // host side (pan_fast.cu)
 int fast_encode_tmap(CUtensorMap *tm, const void *base, int w, int64_t n_rows, int64_t pitch_bytes);
+int fast_encode_tmap_packed(CUtensorMap *tm, const void *base, int w, int bits, int64_t n_rows, int64_t pitch_bytes);
+constexpr int PBOX12 = 116, PBOX10 = 108; // 32-bit elements per box row of a packed stage: 16 + 288 samples of 12 bits, 48 + 288 of 10 bits
 int fast_launch(oip_ctx *ctx, const FastParams &P, int64_t n_ctas);
 
 } // namespace panfast

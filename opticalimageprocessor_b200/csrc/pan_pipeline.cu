@@ -982,11 +982,14 @@ static void fast_eligibility(const oip_pan_desc *d, bool enable, bool *fast_ccd)
             fast_ccd[i] = ok;
             continue;
         }
-        bool ok = enable && out_ok && (c.fmt == OIP_FMT_LE16 || c.fmt == OIP_FMT_BE16) && (((uintptr_t)c.d_kb & 15) == 0) &&
-                  d->w >= 64;
+        const bool packed = c.fmt == OIP_FMT_PACK12 || c.fmt == OIP_FMT_PACK10;
+        // packed lines: the line is addressed as 32-bit elements and unpacked in 16-sample groups
+        bool ok = enable && out_ok && (c.fmt == OIP_FMT_LE16 || c.fmt == OIP_FMT_BE16 || (packed && d->w % 16 == 0)) &&
+                  (((uintptr_t)c.d_kb & 15) == 0) && d->w >= 64;
+        const int64_t min_pitch = packed ? (int64_t)d->w * (c.fmt == OIP_FMT_PACK12 ? 12 : 10) / 8 : 2 * (int64_t)d->w;
         for (int s = 0; s < c.n_seg && ok; ++s)
             ok = c.seg[s].base && (((uintptr_t)c.seg[s].base & 15) == 0) && (c.seg[s].pitch_bytes % 16 == 0) &&
-                 c.seg[s].pitch_bytes >= 2 * (int64_t)d->w && c.seg[s].n_rows > 0;
+                 c.seg[s].pitch_bytes >= min_pitch && c.seg[s].n_rows > 0;
         fast_ccd[i] = ok;
     }
 }
@@ -1172,11 +1175,14 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
                 o.div_tl = panfast::fast_div_make((uint32_t)c.tile_lines);
                 continue;
             }
+            const int pbits = c.fmt == OIP_FMT_PACK12 ? 12 : (c.fmt == OIP_FMT_PACK10 ? 10 : 0);
             for (int s = 0; s < c.n_seg; ++s) {
-                rc = panfast::fast_encode_tmap(&F.tmap[i * OIP_MAX_SEG + s], c.seg[s].base, d->w, c.seg[s].n_rows, c.seg[s].pitch_bytes);
+                rc = pbits ? panfast::fast_encode_tmap_packed(&F.tmap[i * OIP_MAX_SEG + s], c.seg[s].base, d->w, pbits, c.seg[s].n_rows, c.seg[s].pitch_bytes)
+                           : panfast::fast_encode_tmap(&F.tmap[i * OIP_MAX_SEG + s], c.seg[s].base, d->w, c.seg[s].n_rows, c.seg[s].pitch_bytes);
                 if (rc) return rc;
             }
             F.ccd[i].swap = c.fmt == OIP_FMT_BE16;
+            F.ccd[i].pbits = pbits;
         }
         F.tiles = reinterpret_cast<const panfast::FastTile *>((const uint8_t *)ctx->d_plan + ctx->plan_fast_off);
         F.out = d->d_out; F.out_pitch = d->out_pitch_px;

@@ -376,3 +376,34 @@ def test_aos_scan_without_a_single_valid_frame(ctx, oracle_mod):
     off_w, cnt_w = oracle_mod.aos_scan(buf)
     assert cnt_w.tolist() == [0, 32000, 8000]
     _check_aos(ctx, oracle_mod, buf)
+
+
+@pytest.mark.parametrize("bits,w,rows", [(12, 2048, 700), (10, 2048, 700), (12, 8192, 260), (10, 4096, 300), (12, 1000, 300)])
+def test_packed_samples_on_the_fast_kernel(ctx, oracle_mod, bits, w, rows):
+    """MSB-first packed 12 / 10-bit lines (north_star (1); not in the reference) through the fused path: the fast kernel
+    takes them -- the packed stage is unpacked in shared memory -- whenever the line is a whole number of 16-sample groups;
+    3 CCDs, both signs of dY, short sections (edges, stale rows), bit-identical to the oracle on the unpacked samples"""
+    import ctypes as C
+    from opticalimageprocessor_b200 import capi, ops
+    rng = np.random.default_rng(bits * 1000 + w)
+    f = 50
+    imgs = [rng.integers(0, 1 << bits, (rows, w), dtype=np.uint16) for _ in range(3)]
+    raws = [synth.pack_bits(im, bits) for im in imgs]
+    fmt = ops.FMT_PACK12 if bits == 12 else ops.FMT_PACK10
+    kbs = [synth.rrc_coeffs(w, 5 + i) for i in range(3)]
+    dX, dY = [0, 1.37, -0.83], [0, -2.61, 3.19]
+    S, G = 250, 260
+    want = oracle_mod.pan_pipeline(imgs, kbs, dX, dY, f, S, G)
+    dev = [_dev(r) for r in raws]
+    dkb = [_dev(k) for k in kbs]
+    got = ops.pan_pipeline(ctx, dev, dkb, dX, dY, f, fmt=fmt, w=w, section_rows=S, row_guard=G)
+    out = torch.empty_like(got)
+    d = ops.make_pan_desc(dev, fmt, dkb, dX, dY, [False, True, True], f, out, section_rows=S, row_guard=G, w=w)
+    st = (C.c_int64 * 4)()
+    capi.check(ctx.lib.oip_pan_plan_coverage(C.byref(d), 1, 128, None, st))
+    if w % 16 == 0:
+        assert st[1] > 0.9 * (st[0] + st[1]), f"fast kernel share {st[1]} of {st[0] + st[1]} px"
+    else:
+        assert st[1] == 0
+    bad = np.argwhere(got.cpu().numpy() != want)
+    assert bad.size == 0, f"{len(bad)} px differ, first {bad[:5].tolist()}"
