@@ -256,3 +256,25 @@ tc = cpu_time(lambda: cv2.phaseCorrelate(s1, s2), reps=3)
 emit("N1", "oip_stt_parameters: CalcSttParameters = 10 x phase correlation of 16000 x 200 overlap slices, cuFFT + own kernels (ref stitcher.h:148-201)",
      10 * 16000 * 200 * 2, "px", 10 * 16000 * 200 * 2 * 2.0, t, 16000 * 200 * 2, tc, "reference",
      f"cv2.phaseCorrelate ({cv2.getNumThreads()} OpenCV threads), one 16000 x 200 section")
+
+# ------------------------------------------------------------------------------------------------ fused C2, three raw sample formats
+# north_star: unpack -> correct -> stitch in one pass.  3 CCD x 8192 px x 32768 lines; algorithmic bytes per input px =
+# b_in + 2 * W_out / W_in with b_in = 2 (BE16), 1.5 (12-bit packed), 1.25 (10-bit packed)  
+del p1, p2
+torch.cuda.empty_cache()
+Wc, Rc, fc = 8192, (8192 if QUICK else 32768), 100
+dXc, dYc = [0.0, 1.37, -0.83], [0.0, -2.61, 3.19]
+kbc = [torch.from_numpy(synth.rrc_coeffs(Wc, 300 + i)).cuda() for i in range(3)]
+outc = torch.empty((Rc, ops.pan_out_width(3, Wc, fc)), dtype=torch.uint16, device="cuda")
+px_c = 3 * Wc * Rc
+for name, fmt, b_in, bits in [("BE16", ops.FMT_BE16, 2.0, 16), ("12-bit packed", ops.FMT_PACK12, 1.5, 12), ("10-bit packed", ops.FMT_PACK10, 1.25, 10)]:
+    ccds = []
+    for i in range(3):
+        dn = synth.strip_dn(Wc, Rc, 400 + i)
+        if bits == 10:
+            dn = dn >> 2
+        ccds.append(torch.from_numpy(dn.byteswap() if bits == 16 else synth.pack_bits(dn, bits)).cuda())
+    t = dev_time(lambda: ops.pan_pipeline(ctx, ccds, kbc, dXc, dYc, fc, fmt=fmt, out=outc, check_error=False, w=Wc))
+    emit(f"fused C2 {name}", f"oip_pan_pipeline: 3 CCD x {Wc} px x {Rc} lines, {name} samples in, RRC + cubic shift of 2 CCDs + stitch, one pass",
+         px_c, "px", px_c * b_in + outc.numel() * 2.0, t, 1, 1.0, "n/a", "see the BE16 row of bench.py for the CPU reference")
+    del ccds
