@@ -205,8 +205,9 @@ def run_reference(args):
     emit(line)
 
 
-def bench_config(world: int) -> dict:
-    return {"workload": WORKLOAD, "n_ccd": N_CCD, "w": W, "total_rows": TOTAL_ROWS, "rows_per_gpu": TOTAL_ROWS // world,
+def bench_config(world: int, total_rows: int = TOTAL_ROWS) -> dict:
+    return {"workload": WORKLOAD if total_rows == TOTAL_ROWS else WORKLOAD.replace("1048576 lines", f"{total_rows} lines (--rows)"),
+            "n_ccd": N_CCD, "w": W, "total_rows": total_rows, "rows_per_gpu": total_rows // world,
             "fold_cols": FOLD, "dX": DX, "dY": DY,
             "l2": "inputs (51.5 GB / N) and output (50.7 GB / N) per step >> 126 MB L2",
             "multi_gpu": ("scanline-block shards of ONE strip, halo rows read from peer HBM over NVLink (CUDA IPC), "
@@ -483,7 +484,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": "Gpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64 RRC / f32 bicubic / u16", "data": "synthetic",
-            "config": bench_config(world),
+            "config": bench_config(world, total_rows),
             "gpu_launches": int(launches),
             "clocks": clk,
             "warmup_policy": f">= {WARM_SECONDS} s of GPU work before the timed steps (sustained clocks), {n_warm} steps",
