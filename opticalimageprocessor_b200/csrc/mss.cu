@@ -433,7 +433,7 @@ extern "C" int oip_band_align_merge(oip_ctx *ctx, const void *d_mss, const oip_m
         for (int b = 0; b < 4; ++b) F.kb[b] = d->d_kb[b];
         memcpy(F.cX, d->cX, sizeof F.cX); memcpy(F.cY, d->cY, sizeof F.cY);
         F.tiles = (const mssfast::FTile *)((const uint8_t *)ctx->d_mss_plan + ctx->mss_fast_off);
-        F.out = d_out; F.tab = (const float *)ctx->d_mss_plan; F.wb = d->wb; F.swap = d->fmt == OIP_FMT_BE16;
+        F.out = d_out; F.tab = (const float *)ctx->d_mss_plan; F.nz = 0x8000000080000000ull; F.wb = d->wb; F.swap = d->fmt == OIP_FMT_BE16;
         F.n_stage = std::max(2, std::min(8, ctx->pan_fast_stages));
         rc = mssfast::launch(ctx, F, ctx->mss_fast_ctas);
         if (rc) return rc;

@@ -36,7 +36,8 @@ struct Params {
     double cX[8], cY[12];
     const FTile *tiles;
     uint16_t *out;
-    const float *tab; // 32x4 cubic weights, then the run-time (-0.0,-0.0) pair
+    const float *tab; // 32x4 cubic weights
+    uint64_t nz;      // run-time (-0.0,-0.0) addend of the packed products: a uniform-register operand (see pan_fast.cuh)
     int32_t wb, swap, n_stage, pad;
 };
 // one section of the reference's loop (ref preproc.h:379-408)

@@ -66,7 +66,7 @@ struct FastParams {
     const FastTile *tiles;
     uint16_t *out;
     int64_t out_pitch;
-    const float *tab; // 32x4 cubic weights, then the run-time (-0.0,-0.0) pair
+    const float *tab; // 32x4 cubic weights, then the run-time -0.0 addend of the packed products (mul2())
     int32_t w;
     int32_t n_stage; // TMA stages per warp (2..8)
 };

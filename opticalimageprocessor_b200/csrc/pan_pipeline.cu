@@ -762,6 +762,7 @@ static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows
     int th = std::max(16, fast_rows);
     if (fast_rows == 128 && d->n_rows >= 65536) th = 256; // long strips: the per-tile prologue amortises better (measured, tools/sweep_sizes.py)
     while ((double)d->n_rows / th * ((double)n * w / 248.0) > 400000.0) th *= 2;
+    while (th > 16 && (int64_t)(th + 8) * d->out_pitch_px * 2 >= (1ll << 32)) th /= 2; // REMAP tiles step a 32-bit row offset (pan_fast.cu)
     int out_x = 0;
     for (int i = 0; i < n; ++i) {
         const oip_ccd_src &C = d->ccd[i];
