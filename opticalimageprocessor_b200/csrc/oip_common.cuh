@@ -16,6 +16,7 @@ struct oip_pan_plan {
     void *d_plan = nullptr;
     size_t cap = 0;
     int64_t tiles = 0, fast_ctas = 0;
+    int64_t fast_cls[3] = {0, 0, 0}; // pan_fast_kernel CTAs per source-format class (line rasters / sub-image tiles / packed lines)
     size_t fast_off = 0;
     uint64_t last_use = 0;
     void *h_stage = nullptr;    // pinned staging of the plan upload (a pageable source would tie the host to the stream)
@@ -35,7 +36,8 @@ struct oip_ctx {
     uint64_t plan_clock = 0;
     void *d_plan = nullptr;      // the plan of the current call (owned by pan_plans)
     int64_t plan_tiles = 0;      // generic tiles (pan_kernel CTAs)
-    int64_t plan_fast_ctas = 0;  // pan_fast_kernel CTAs (4 warp-tiles each)
+    int64_t plan_fast_ctas = 0;  // pan_fast_kernel CTAs (4 warp-tiles each), all classes
+    int64_t plan_fast_cls[3] = {0, 0, 0};
     size_t plan_fast_off = 0;    // byte offset of the FastTile array inside d_plan
     // tunables (oip_ctx_set_option)
     int host_block_rows = 2048;  // oip_pan_pipeline_host: rows per H2D / compute / D2H block
@@ -63,7 +65,7 @@ struct oip_ctx {
                               // side stream can share a hardware queue, which parks the kernel behind a 2 ms copy)
     cudaStream_t aux_stream = nullptr; // side stream of oip_pan_pipeline (generic tiles next to the fast kernel)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool pan_attr_set = false, mss_attr_set = false, fast_attr_set = false, imtr_attr_set = false;
+    bool pan_attr_set = false, mss_attr_set = false, fast_attr_set[3] = {false, false, false}, imtr_attr_set = false;
     // host-buffer pipeline (oip_pan_pipeline_host): staging slots + side streams
     void *host_pipe = nullptr;
     void *stt_state = nullptr; // cuFFT plans of the offset estimation (stt.cu)

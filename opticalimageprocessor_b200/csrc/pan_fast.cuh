@@ -75,7 +75,13 @@ struct FastParams {
 int fast_encode_tmap(CUtensorMap *tm, const void *base, int w, int64_t n_rows, int64_t pitch_bytes);
 int fast_encode_tmap_packed(CUtensorMap *tm, const void *base, int w, int bits, int64_t n_rows, int64_t pitch_bytes);
 constexpr int PBOX12 = 116, PBOX10 = 108; // 32-bit elements per box row of a packed stage: 16 + 288 samples of 12 bits, 48 + 288 of 10 bits
-int fast_launch(oip_ctx *ctx, const FastParams &P, int64_t n_ctas);
+// source-format class of a CCD: one pan_fast_kernel instantiation (and translation unit, pan_fast_c<N>.cu) each
+inline int fast_class(int fmt) { return fmt == OIP_FMT_BE16_TILES ? 1 : (fmt == OIP_FMT_PACK12 || fmt == OIP_FMT_PACK10) ? 2 : 0; }
+template <int CLS> int fast_launch_cls(oip_ctx *ctx, const FastParams &P, int64_t tile0, int64_t n_ctas);
+template <> int fast_launch_cls<0>(oip_ctx *ctx, const FastParams &P, int64_t tile0, int64_t n_ctas);
+template <> int fast_launch_cls<1>(oip_ctx *ctx, const FastParams &P, int64_t tile0, int64_t n_ctas);
+template <> int fast_launch_cls<2>(oip_ctx *ctx, const FastParams &P, int64_t tile0, int64_t n_ctas);
+int fast_launch(oip_ctx *ctx, const FastParams &P, const int64_t *cls_ctas); // the classes follow each other in P.tiles
 
 } // namespace panfast
 } // namespace oip

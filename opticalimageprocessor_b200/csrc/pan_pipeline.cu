@@ -753,7 +753,7 @@ static void emit_gap(std::vector<Tile> &tiles, std::vector<panfast::FastTile> &f
 }
 
 static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows, std::vector<Tile> &tiles,
-                      std::vector<panfast::FastTile> &ftiles)
+                      std::vector<panfast::FastTile> &ftiles, int64_t (&cls_ctas)[3])
 {
     const int n = d->n_ccd, w = d->w, f = d->fold_half;
     const int64_t r_lo = d->row0, r_hi = d->row0 + d->n_rows;
@@ -865,6 +865,8 @@ static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows
     // neighbouring strips share halo columns through L2, COPY and REMAP tiles interleave on every SM
     // (putting all long REMAP tiles first and the short COPY tiles at the end of the launch was measured: no difference)
     std::stable_sort(fl.begin(), fl.end(), [&](const panfast::FastTile &a, const panfast::FastTile &b) {
+        const int ca = panfast::fast_class(d->ccd[a.ccd].fmt), cb = panfast::fast_class(d->ccd[b.ccd].fmt);
+        if (ca != cb) return ca < cb; // one launch per source-format class (a strip is almost always of one class)
         const int64_t ra = a.out_off / d->out_pitch_px / th, rb = b.out_off / d->out_pitch_px / th;
         if (ra != rb) return ra < rb;
         if (a.kind != b.kind) return a.kind > b.kind; // REMAP tiles (long) first inside a band
@@ -877,10 +879,16 @@ static int build_plan(const oip_pan_desc *d, const bool *fast_ccd, int fast_rows
         const int x0 = t.kind == panfast::FT_COPY ? t.x_begin : (t.src_x0 & ~7);
         t.tmap = x0 >= 0 ? x0 / C.tile_cols : -((-x0 + C.tile_cols - 1) / C.tile_cols);
     }
-    ftiles = fl;
     panfast::FastTile none{};
     none.kind = panfast::FT_NONE;
-    while (ftiles.size() % panfast::WARPS) ftiles.push_back(none);
+    ftiles.clear();
+    for (int c = 0; c < 3; ++c) { // every class padded to whole CTAs
+        const size_t before = ftiles.size();
+        for (const panfast::FastTile &t : fl)
+            if (panfast::fast_class(d->ccd[t.ccd].fmt) == c) ftiles.push_back(t);
+        while (ftiles.size() % panfast::WARPS) ftiles.push_back(none);
+        cls_ctas[c] = (int64_t)((ftiles.size() - before) / panfast::WARPS);
+    }
     return OIP_OK;
 }
 
@@ -1005,7 +1013,8 @@ extern "C" int oip_pan_plan_coverage(const oip_pan_desc *d, int enable_fast, int
     fast_eligibility(d, enable_fast != 0, fast_ccd);
     std::vector<pan::Tile> tiles;
     std::vector<panfast::FastTile> ftiles;
-    rc = pan::build_plan(d, fast_ccd, fast_rows, tiles, ftiles);
+    int64_t cls_ctas[3] = {0, 0, 0};
+    rc = pan::build_plan(d, fast_ccd, fast_rows, tiles, ftiles, cls_ctas);
     if (rc) return rc;
     int64_t px_gen = 0, px_fast = 0, n_fast = 0;
     const int64_t pitch = d->out_pitch_px;
@@ -1060,7 +1069,8 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
     if (!pl) {
         std::vector<pan::Tile> tiles;
         std::vector<panfast::FastTile> ftiles;
-        rc = pan::build_plan(d, fast_ccd, ctx->pan_fast_rows, tiles, ftiles);
+        int64_t cls_ctas[3] = {0, 0, 0};
+        rc = pan::build_plan(d, fast_ccd, ctx->pan_fast_rows, tiles, ftiles, cls_ctas);
         if (rc) return rc;
         pan::upload_tab();
         // a free slot, else the least recently used one (its buffer may still be read by kernels in flight)
@@ -1104,12 +1114,14 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         pl->key.assign(kb, kb + sizeof key);
         pl->tiles = (int64_t)tiles.size();
         pl->fast_ctas = (int64_t)(ftiles.size() / panfast::WARPS);
+        for (int c = 0; c < 3; ++c) pl->fast_cls[c] = cls_ctas[c];
         pl->fast_off = fast_off;
     }
     pl->last_use = ++ctx->plan_clock;
     ctx->d_plan = pl->d_plan;
     ctx->plan_tiles = pl->tiles;
     ctx->plan_fast_ctas = pl->fast_ctas;
+    for (int c = 0; c < 3; ++c) ctx->plan_fast_cls[c] = pl->fast_cls[c];
     ctx->plan_fast_off = pl->fast_off;
     if (ctx->plan_tiles == 0 && ctx->plan_fast_ctas == 0) return OIP_OK;
 
@@ -1190,7 +1202,7 @@ extern "C" int oip_pan_pipeline(oip_ctx *ctx, const oip_pan_desc *d)
         F.tab = reinterpret_cast<const float *>(ctx->d_plan);
         F.w = d->w;
         F.n_stage = std::max(2, std::min(8, ctx->pan_fast_stages));
-        rc = panfast::fast_launch(ctx, F, ctx->plan_fast_ctas);
+        rc = panfast::fast_launch(ctx, F, ctx->plan_fast_cls);
         if (rc) return rc;
     }
     if (fork) {

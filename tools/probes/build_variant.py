@@ -10,7 +10,7 @@ if not os.environ.get('NO_BASE_BUILD'):
     B.build()
 for src in B.sources():
     base = os.path.basename(src)[:-3]
-    if base in os.environ.get("VARIANT_FILES", "pan_fast").split(","):
+    if base in os.environ.get("VARIANT_FILES", "pan_fast_c0").split(","):
         obj = os.path.join(out_dir, f"{name}_{base}.o")
         subprocess.check_call([B.NVCC] + [f for f in B.FLAGS if f not in ("-Xptxas", "-v")] + defs + ["-c", src, "-o", obj])
     else:
