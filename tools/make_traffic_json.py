@@ -8,7 +8,7 @@ for line in open(path):
     m = re.match(r"(dram__bytes_(?:read|write)\.sum)\s+([0-9.,]+)\s+(\w+)", line)
     if m:
         vals[m.group(1)] = float(m.group(2).replace(",", "")) * unit[m.group(3)]
-out = {"workload_rows": rows, "rows": rows, "kernel": "oip::panfast::pan_fast_kernel<3>",
+out = {"workload_rows": rows, "rows": rows, "kernel": "oip::panfast::pan_fast_kernel<0>",
        "dram_bytes_read": vals["dram__bytes_read.sum"], "dram_bytes_write": vals["dram__bytes_write.sum"],
        "dram_bytes_per_launch": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"],
        "source": os.path.relpath(path, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))) + " (one `ncu --set full` capture, tools/collect_profiles.sh)"}
