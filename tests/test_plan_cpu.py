@@ -143,3 +143,18 @@ def test_mss_reference_geometry_is_mostly_fast(lib):
     st = (C.c_int64 * 4)()
     capi.check(lib.oip_mss_plan_coverage(C.byref(d), 1, 128, None, st))
     assert st[1] > 0.98 * (st[0] + st[1]), list(st)
+
+
+def test_mixed_source_formats_are_planned_once_per_pixel(lib):
+    """CCDs of different source-format classes in one strip (big-endian raster, packed 12-bit lines, native raster): the
+    warp-tile list is laid out class by class (one pan_fast_kernel launch each); every output pixel is still covered
+    exactly once and the packed CCD stays on the fast path"""
+    n, w, total, f = 3, 2048, 700, 50
+    d, out_w = _desc(n, w, total, f, [0.0, 1.37, -0.83], [0.0, -2.61, 3.19], 250, 260)
+    d.ccd[1].fmt = capi.FMT_PACK12
+    d.ccd[1].seg[0] = RowSeg(0x7F0000000000 + (1 << 36), 0, total, w * 12 // 8)
+    d.ccd[2].fmt = capi.FMT_LE16
+    cover, st = _coverage(lib, d, out_w)
+    assert set(np.unique(cover[:, :out_w])) <= {1, 2}
+    assert st[0] + st[1] == total * out_w
+    assert st[1] > 0.8 * total * out_w, st
