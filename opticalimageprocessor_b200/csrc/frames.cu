@@ -924,6 +924,144 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_kernel(const uint8_t *__
     }
 }
 
+// ---- run-based form of the same kernel (the default; option imtr_runs = 0 selects the per-frame gather above) ----------
+// The 32 frames of a CTA are 28224 consecutive bytes of the payload stream, i.e. pieces of at most 34 consecutive payload
+// RUNS of 880 bytes.  880 and 32 * 882 are multiples of four, so when the runs are laid down back to back in shared
+// memory -- run i0 + k at word 220 k -- every run is a whole number of destination words and its source is re-aligned by ONE
+// funnel shift per word with a shift that is constant over the run: no per-word run selection, no boundary fix-ups.  The
+// frames then start at byte o0 + 882 q of that image (any alignment when a shard starts `skip` bytes into its first payload):
+// the CRC pieces and the payload words are read with two aligned LDS + a funnel shift whose amount depends on the parity of
+// q only.  Per frame ~45 instructions of gather instead of ~300.
+constexpr int IMTR_RUNS = 34, IMTR_RUN_WORDS = 220;
+__global__ void __launch_bounds__(IMTR_T) imtr_validate_runs_kernel(const uint8_t *__restrict__ buf, const uint64_t *__restrict__ poff,
+                                                                    int64_t n_payload, int64_t n_frames, uint8_t *status,
+                                                                    uint32_t *seq, uint8_t *chid, uint32_t *valid,
+                                                                    unsigned long long *n_bad, uint8_t *imdt_spec, int skip)
+{
+    __shared__ __align__(16) uint32_t s_w[(IMTR_FRONT + IMTR_RUNS * IMTR_RUN_WORDS * 4 + 32) / 4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t f0 = (int64_t)blockIdx.x * IMTR_BATCH;
+    const int n_here = (int)min((int64_t)IMTR_BATCH, n_frames - f0);
+    const int64_t s_first = (int64_t)skip + f0 * 882;
+    const int64_t i0 = s_first / 880;
+    const int o0 = (int)(s_first - i0 * 880);              // frame 0 of the batch starts o0 bytes into run i0
+    const int n_runs = (o0 + 882 * n_here + 879) / 880;      // runs that hold bytes of this batch (<= 34, all < n_payload)
+    const unsigned long long pl0 = poff[min(i0 + lane, n_payload - 1)], pl1 = poff[min(i0 + 32 + lane, n_payload - 1)];
+    uint32_t *runs = s_w + IMTR_FRONT / 4;
+    for (int k = wid; k < n_runs; k += IMTR_T / 32) {
+        const unsigned long long a0 = __shfl_sync(0xffffffffu, pl0, k & 31), a1 = __shfl_sync(0xffffffffu, pl1, k & 31);
+        const uint8_t *a = buf + (k < 32 ? a0 : a1);
+        const uint32_t sh = (uint32_t)((uintptr_t)a & 3u);
+        // aligned words around the run: the last one reaches at most 3 bytes past it, which are bytes of the same 1024-byte
+        // AOS frame (CRC / LDPC field); an aligned run reads nothing past its end
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(a - sh);
+        const int up = sh ? 1 : 0;
+        uint32_t lo[7], hi[7];
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+            const int idx = min(lane + 32 * u, IMTR_RUN_WORDS - 1);
+            lo[u] = __ldg(w + idx);
+            hi[u] = __ldg(w + idx + up);
+        }
+        uint32_t *dst = runs + IMTR_RUN_WORDS * k;
+#pragma unroll
+        for (int u = 0; u < 7; ++u)
+            if (lane + 32 * u < IMTR_RUN_WORDS) dst[lane + 32 * u] = __funnelshift_r(lo[u], hi[u], 8u * sh);
+    }
+    __syncthreads();
+    const uint32_t fbase = (uint32_t)(IMTR_FRONT + o0);    // byte offset of frame 0 inside s_w
+    if (imdt_spec) {
+        // speculative output (see imtr_validate_kernel): frame f's 866 payload bytes land at f * 866
+        for (int q = wid; q < n_here; q += IMTR_T / 32) {
+            uint8_t *d = imdt_spec + (uint64_t)(f0 + q) * 866;
+            const uint32_t pb = fbase + 882u * (uint32_t)q + 10u;        // payload start inside s_w (bytes)
+            const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_w);
+            const int head = (int)((4u - (uint32_t)((uintptr_t)d & 3u)) & 3u);
+            if (lane < head) d[lane] = sb[pb + lane];
+            const int nw = (866 - head) >> 2;
+            const uint32_t s0 = pb + (uint32_t)head;
+            const uint32_t sh = 8u * (s0 & 3u);
+            const uint32_t *sw = s_w + (s0 >> 2);
+            uint32_t *dw = reinterpret_cast<uint32_t *>(d + head);
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                const int k = lane + 32 * u;
+                if (k < nw) dw[k] = __funnelshift_r(sw[k], sw[k + 1], sh);
+            }
+            const int t0 = head + 4 * nw;
+            if (lane < 866 - t0) d[t0 + lane] = sb[pb + t0 + lane];
+        }
+    }
+    // ---- CRCs of the 32 frames, bit-sliced exactly as in imtr_validate_kernel; only the loads differ: the span of frame q
+    //      starts at byte fbase - 20 + 882 q, so odd and even frames have their own alignment (two aligned words + shift)
+    __shared__ uint32_t s_part[4][16][32];
+    uint32_t P[16];
+    {
+        const uint32_t c = fbase - (uint32_t)(bitslice::SPAN - 876) + 28u * (uint32_t)lane; // this lane's piece of frame 0 (IMTR_FRONT >= 20)
+        const uint32_t r = c & 3u, t = r + 2u;
+        const uint32_t base_e = smem_u32(s_w) + (c - r), sh_e = 8u * r;
+        const uint32_t base_o = smem_u32(s_w) + (c - r) + (t >= 4u ? 4u : 0u), sh_o = 8u * (t & 3u);
+        const int clear_bit = lane == 0 ? 8 * (bitslice::SPAN - 876) : -1;
+        const int jlo = 2 * wid, jhi = min(2 * wid + 2, 7);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P[i] = 0u;
+#pragma unroll 1
+        for (int j = jlo; j < jhi; ++j) {
+            uint32_t T[32];
+            const uint32_t ae = base_e + 4u * (uint32_t)j, ao = base_o + 4u * (uint32_t)j;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const uint32_t a = ((q & 1) ? ao : ae) + (uint32_t)((882 * q) & ~3);
+                T[q] = __funnelshift_r(lds_u32(a), lds_u32(a + 4u), (q & 1) ? sh_o : sh_e);
+            }
+            bitslice::transpose32(T);
+            bitslice::lfsr_word(P, T, clear_bit - 32 * j);
+        }
+        if (lane == 0 && 32 * jhi <= 8 * (bitslice::SPAN - 876)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) P[i] = 0u;
+        }
+        uint32_t Q[16];
+        if (wid == 0) bitslice::mul_xpow<160>(P, Q);
+        else if (wid == 1) bitslice::mul_xpow<96>(P, Q);
+        else if (wid == 2) bitslice::mul_xpow<32>(P, Q);
+        else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) Q[i] = P[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s_part[wid][i][lane] = Q[i];
+    }
+    __syncthreads();
+    if (wid != (int)(blockIdx.x & 3)) return;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) P[i] = s_part[0][i][lane] ^ s_part[1][i][lane] ^ s_part[2][i][lane] ^ s_part[3][i][lane];
+    {
+        auto x = [](uint32_t v, int sd, int) { return __shfl_xor_sync(0xffffffffu, v, sd); };
+        bitslice::join_level<1>(P, lane, x);
+        bitslice::join_level<2>(P, lane, x);
+        bitslice::join_level<4>(P, lane, x);
+        bitslice::join_level<8>(P, lane, x);
+        bitslice::join_level<16>(P, lane, x);
+    }
+    // ValidateImtrFrame, checks in the reference's order (ref aux_separator.h:558-590); lane = frame
+    const uint8_t *fr = reinterpret_cast<const uint8_t *>(s_w) + fbase + 882u * (uint32_t)lane;
+    int st = 0;
+    if (!(fr[0] == 0x49 && fr[1] == 0x54 && fr[2] == 0xCE && fr[3] == 0x1F)) st = 1;                  // :559
+    else if (!(fr[878] == 0x2E && fr[879] == 0xE9 && fr[880] == 0xC8 && fr[881] == 0xFD)) st = 2;     // :563
+    else if (fr[9] != 0x22) st = 3;                                                                  // :572
+    const uint32_t want = ((uint32_t)fr[876] << 8) | fr[877];
+    if (st == 0 && (bitslice::unslice(P, lane) ^ bitslice::init_term(876)) != want) st = 4;
+    const int64_t f = f0 + lane;
+    if (f < n_frames) {
+        status[f] = (uint8_t)st;
+        seq[f] = ((uint32_t)fr[4] << 24) | ((uint32_t)fr[5] << 16) | ((uint32_t)fr[6] << 8) | fr[7];  // :568-569 BE u32 at 4
+        chid[f] = fr[8];
+        valid[f] = st == 0;
+        if (st) atomicAdd(&n_bad[st - 1], 1ull);
+    }
+}
+
 // seq of the valid frames in order (to evaluate the "previous accepted seq" rules)
 __global__ void imtr_compact_seq_kernel(const uint32_t *valid, const uint32_t *rank, const uint32_t *seq, int64_t n,
                                         uint32_t *seq_c)
@@ -996,41 +1134,69 @@ __global__ void __launch_bounds__(256) imtr_copy_kernel(const uint8_t *__restric
 // =============================================================================================
 // image frames: trailer-signature search, trailer gather, sub-image unpack
 // =============================================================================================
-__global__ void find_sig4_kernel(const uint8_t *__restrict__ buf, int64_t n, uint32_t sig_le, uint8_t first,
-                                 unsigned long long *hits, uint32_t cap, uint32_t *n_hits)
+// All occurrences of a 4-byte signature.  A thread takes one ALIGNED 16-byte chunk (one 128-bit load; the chunk grid starts
+// at the buffer address rounded down to 16, positions in front of the buffer are never reported) plus the first word of
+// the next chunk (from lane + 1 by shuffle; lane 31 loads it).  Filter: a position can only match where byte p is the
+// first AND byte p + 1 the second signature byte -- (w ^ first) | ((w >> 8 | next << 24) ^ second) has a zero byte exactly
+// there, found with the zero-byte trick (no false negatives), five instructions per word and one branch per chunk that is
+// taken for ~1 chunk in 4000 on arbitrary data (the one-byte filter of round 1 sent almost every warp into the slow path:
+// 85 instructions per 16 positions, issue-bound at 63 % of the slots; `first` is kept for the signature of the call).
+__global__ void __launch_bounds__(256) find_sig4_kernel(const uint8_t *__restrict__ buf, int64_t n, uint32_t sig_le, uint8_t first,
+                                                        unsigned long long *hits, uint32_t cap, uint32_t *n_hits)
 {
-    // each thread scans 16 consecutive positions; word-wise reject on the first signature byte
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
-    const uint32_t pat = 0x01010101u * first;
-    for (int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; p0 < n; p0 += stride) {
+    (void)first;
+    const int lane = threadIdx.x & 31;
+    const uint32_t mis = (uint32_t)((uintptr_t)buf & 15u);
+    const uint8_t *A = buf - mis;                               // aligned origin; stream position p sits at A + mis + p
+    const int64_t end = (int64_t)mis + n;                       // bytes [mis, end) of the aligned image are the stream
+    const int64_t n_chunks = (end + 15) >> 4;
+    const uint32_t p0pat = 0x01010101u * (sig_le & 0xFFu), p1pat = 0x01010101u * ((sig_le >> 8) & 0xFFu);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // (the loop bound is warp-uniform: every lane of a warp takes part in the shuffle)
+    for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); c0 < n_chunks; c0 += stride) {
+        const int64_t c = c0 + lane, q0 = c << 4;
         uint32_t w[5];
-        if (p0 + 20 <= n && ((((uintptr_t)buf) + p0) & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) w[i] = reinterpret_cast<const uint32_t *>(buf + p0)[i];
+        if (q0 + 16 <= end) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(A + q0));
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
         } else {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 uint32_t v = 0;
                 for (int b = 0; b < 4; ++b) {
-                    int64_t q = p0 + 4 * i + b;
-                    v |= (uint32_t)(q < n ? buf[q] : 0) << (8 * b);
+                    const int64_t q = q0 + 4 * i + b;
+                    v |= (uint32_t)(q < end ? A[q] : 0) << (8 * b);
                 }
                 w[i] = v;
             }
         }
+        w[4] = __shfl_down_sync(0xffffffffu, w[0], 1);
+        if (lane == 31) {
+            w[4] = 0u;
+            if (q0 + 20 <= end) w[4] = __ldg(reinterpret_cast<const uint32_t *>(A + q0 + 16));
+            else
+                for (int b = 0; b < 4; ++b) {
+                    const int64_t q = q0 + 16 + b;
+                    w[4] |= (uint32_t)(q < end ? A[q] : 0) << (8 * b);
+                }
+        }
+        uint32_t acc = 0u;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint32_t x = w[i] ^ pat;
-            if ((x - 0x01010101u) & ~x & 0x80808080u) {
+            const uint32_t t = (w[i] ^ p0pat) | (__funnelshift_r(w[i], w[i + 1], 8) ^ p1pat);
+            acc |= (t - 0x01010101u) & ~t;
+        }
+        if (acc & 0x80808080u) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const int64_t p = p0 + 4 * i + b;
-                    if (__funnelshift_r(w[i], w[i + 1], 8 * b) == sig_le && p + 4 <= n) {
+                    const int64_t p = q0 + 4 * i + b - (int64_t)mis;
+                    if (__funnelshift_r(w[i], w[i + 1], 8 * b) == sig_le && p >= 0 && p + 4 <= n) {
                         uint32_t k = atomicAdd(n_hits, 1u);
                         if (k < cap) hits[k] = (unsigned long long)p;
                     }
                 }
-            }
         }
     }
 }
@@ -1373,7 +1539,7 @@ static int imtr_deframe_impl(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t 
     OIP_CUDA(cudaMemsetAsync(d_first_chid, 0xFF, 4, ctx->stream));
     // one stream-ordered chain, one host round trip at the end
     const bool speculative = (uint64_t)nf * 866 <= (uint64_t)cap; // room for every cut frame: validate writes them in place
-    imtr_validate_kernel<<<(unsigned)((nf + IMTR_BATCH - 1) / IMTR_BATCH), IMTR_T, 0, ctx->stream>>>(
+    (ctx->imtr_runs ? imtr_validate_runs_kernel : imtr_validate_kernel)<<<(unsigned)((nf + IMTR_BATCH - 1) / IMTR_BATCH), IMTR_T, 0, ctx->stream>>>(
         d_buf, d_payload_off, n_payload, nf, S + o_status, (uint32_t *)(S + o_seq), S + o_chid, (uint32_t *)(S + o_valid), d_bad,
         speculative ? d_imdt : nullptr, skip);
     OIP_CUDA(cudaGetLastError());
@@ -1434,7 +1600,7 @@ extern "C" int oip_image_frames_index(oip_ctx *ctx, const uint8_t *d_imdt, size_
         if (rc) return rc;
         uint8_t *S = (uint8_t *)ctx->d_scratch;
         OIP_CUDA(cudaMemsetAsync(S + o_n, 0, 16, ctx->stream));
-        const int blocks = (int)std::min<int64_t>((n / 16 + 255) / 256 + 1, (int64_t)ctx->sm_count * 16);
+        const int blocks = (int)std::min<int64_t>((n / 16 + 1 + 255) / 256 + 1, (int64_t)ctx->sm_count * 32);
         find_sig4_kernel<<<blocks, 256, 0, ctx->stream>>>(d_imdt, n, 0x4DE190EBu, 0xEB, (unsigned long long *)(S + o_hits),
                                                          hit_cap, (uint32_t *)(S + o_n));
         OIP_CUDA(cudaGetLastError());

@@ -128,9 +128,14 @@ def test_imtr_deframe(ctx, oracle_mod):
     buf = synth.build_aos_file(synth.aos_frames(imtr.reshape(-1)), empty_every=9)
     off = _check_aos(ctx, oracle_mod, buf)
     want, st_w = oracle_mod.imtr_deframe(buf, off)
-    got, st_g = ops.imtr_deframe(ctx, _dev(buf), _dev(off.astype(np.int64)))
-    assert st_g.tolist() == st_w.tolist()
-    assert np.array_equal(got.cpu().numpy(), want)
+    for runs in (1, 0):   # run-based gather (default) and the per-frame gather
+        ctx.set_option("imtr_runs", runs)
+        try:
+            got, st_g = ops.imtr_deframe(ctx, _dev(buf), _dev(off.astype(np.int64)))
+        finally:
+            ctx.set_option("imtr_runs", 1)
+        assert st_g.tolist() == st_w.tolist(), runs
+        assert np.array_equal(got.cpu().numpy(), want), runs
 
 
 def test_imtr_deframe_clean_stream(ctx, oracle_mod):
@@ -139,10 +144,41 @@ def test_imtr_deframe_clean_stream(ctx, oracle_mod):
     buf = aos.reshape(-1)
     off, _ = oracle_mod.aos_scan(buf)
     want, st_w = oracle_mod.imtr_deframe(buf, off)
-    got, st_g = ops.imtr_deframe(ctx, _dev(buf), _dev(off.astype(np.int64)))
-    assert st_g.tolist() == st_w.tolist() and st_w[1] == st_w[0]
-    assert np.array_equal(got.cpu().numpy(), want)
+    for runs in (1, 0):
+        ctx.set_option("imtr_runs", runs)
+        try:
+            got, st_g = ops.imtr_deframe(ctx, _dev(buf), _dev(off.astype(np.int64)))
+        finally:
+            ctx.set_option("imtr_runs", 1)
+        assert st_g.tolist() == st_w.tolist() and st_w[1] == st_w[0], runs
+        assert np.array_equal(got.cpu().numpy(), want), runs
     assert np.array_equal(want[:imdt.size], imdt)
+
+
+@pytest.mark.parametrize("prefix", [0, 1, 2, 3, 5])
+@pytest.mark.parametrize("n_aos", [1, 2, 3, 33, 34, 65, 300])
+def test_imtr_deframe_alignments_and_tails(ctx, oracle_mod, prefix, n_aos):
+    """every byte alignment of the payload runs (file prefix of 0..5 bytes), payload counts around the 32-frame batches of a CTA,
+    a cut that ends inside the last payload; a few frames damaged so that the compaction path runs as well"""
+    from opticalimageprocessor_b200 import ops
+    imdt, truth, imtr, aos = _downlink(n_frames=12, tc=32, tl=8, seed=21 + prefix)
+    imtr = imtr[:max(1, (n_aos * 880) // 882 + 1)].copy()
+    if imtr.shape[0] > 40:
+        imtr[7, 333] ^= 0x10
+        imtr[39, 2] ^= 0x01
+    a = synth.aos_frames(imtr.reshape(-1))[:n_aos]
+    buf = np.concatenate([np.full(prefix, 0x5A, np.uint8), a.reshape(-1)])
+    off, _ = oracle_mod.aos_scan(buf)
+    assert off.size == a.shape[0]
+    want, st_w = oracle_mod.imtr_deframe(buf, off)
+    for runs in (1, 0):
+        ctx.set_option("imtr_runs", runs)
+        try:
+            got, st_g = ops.imtr_deframe(ctx, _dev(buf), _dev(off.astype(np.int64)))
+        finally:
+            ctx.set_option("imtr_runs", 1)
+        assert st_g.tolist() == st_w.tolist(), runs
+        assert np.array_equal(got.cpu().numpy(), want), runs
 
 
 @pytest.mark.parametrize("tc,tl,skip,junk", [(16, 4, (), 0), (16, 4, {3}, 0), (24, 2, {2, 3}, 333), (1536, 1, (), 0)])
@@ -182,6 +218,34 @@ def test_image_frames_incomplete_and_false_signature(ctx, oracle_mod):
         ctx.sync()
         assert np.array_equal(pan.cpu().numpy(), pan_w) and np.array_equal(aux.cpu().numpy(), aux_w)
         assert np.array_equal(mss.cpu().numpy(), mss_w)
+
+
+@pytest.mark.parametrize("shift", [0, 1, 3, 4, 7, 13, 15, 16, 21])
+def test_image_frames_index_pointer_alignment_and_partial_signatures(ctx, oracle_mod, shift):
+    """the trailer search works on aligned 16-byte chunks: every alignment of the buffer pointer (a view `shift` bytes into
+    an allocation), signatures straddling chunk / warp boundaries (frame lengths are 12 mod 16, so the trailers walk
+    through all phases), first-two- and first-three-byte matches that are no signature"""
+    from opticalimageprocessor_b200 import ops
+    tc, tl = 24, 2
+    imdt, truth = synth.make_imdt(9, tc, tl, seed=31 + shift)
+    buf = imdt.copy()
+    rng = np.random.default_rng(shift)
+    sig = np.frombuffer(synth.IMG_SIG, np.uint8)
+    frame_bytes = 192 * tl + 40 * tc * tl * 2 + 172
+    spots = [int(p) for p in rng.integers(0, buf.size - 8, 300) if p % frame_bytes < frame_bytes - 180]
+    for p in spots[:200]:                             # decoys inside aux / pixel data (not in the trailers): EB 90, EB 90 E1
+        buf[p:p + 2] = sig[:2]
+    for p in spots[200:]:
+        buf[p:p + 3] = sig[:3]
+    n_w, aux_w, pan_w, mss_w, st_w = oracle_mod.image_frames(buf, tc, tl)
+    d = _dev(np.concatenate([np.full(shift, 0xEB, np.uint8), buf]))[shift:]
+    assert d.data_ptr() % 16 == shift % 16
+    ents, st_g = ops.image_frames_index(ctx, d, tc, tl)
+    assert st_g.tolist() == st_w.tolist()
+    aux, pan, mss = ops.unpack_frames(ctx, d, tc, tl, ents, int(st_g[1]))
+    ctx.sync()
+    assert np.array_equal(pan.cpu().numpy(), pan_w) and np.array_equal(aux.cpu().numpy(), aux_w)
+    assert np.array_equal(mss.cpu().numpy(), mss_w)
 
 
 def test_full_downlink_to_raw(ctx, oracle_mod):

@@ -16,7 +16,11 @@ buf = torch.from_numpy(file_np).cuda()
 print("file bytes", buf.numel())
 def ev():
     return torch.cuda.Event(enable_timing=True)
-for it in range(5):
+variants = [int(v) for v in os.environ.get("IMTR_RUNS", "1").split(",")]   # 1: run-based gather (default), 0: per-frame gather; "0,1" = A/B
+for runs, it in [(r, i) for r in variants for i in range(5)]:
+    if it == 0:
+        ctx.set_option("imtr_runs", runs)
+        print("imtr_runs =", runs)
     t = [ev() for _ in range(5)]
     t[0].record()
     off, cnt = ops.aos_scan(ctx, buf); t[1].record()
