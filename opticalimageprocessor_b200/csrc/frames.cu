@@ -932,11 +932,11 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_kernel(const uint8_t *__
 // frames then start at byte o0 + 882 q of that image (any alignment when a shard starts `skip` bytes into its first payload):
 // the CRC pieces and the payload words are read with two aligned LDS + a funnel shift whose amount depends on the parity of
 // q only.  Per frame ~45 instructions of gather instead of ~300.
-constexpr int IMTR_RUNS = 34, IMTR_RUN_WORDS = 220;
-__global__ void __launch_bounds__(IMTR_T) imtr_validate_runs_kernel(const uint8_t *__restrict__ buf, const uint64_t *__restrict__ poff,
-                                                                    int64_t n_payload, int64_t n_frames, uint8_t *status,
-                                                                    uint32_t *seq, uint8_t *chid, uint32_t *valid,
-                                                                    unsigned long long *n_bad, uint8_t *imdt_spec, int skip)
+constexpr int IMTR_RUNS = 34, IMTR_RUN_WORDS = 220, IMTR_DEPTH = 3;
+__global__ void __launch_bounds__(IMTR_T, 6) imtr_validate_runs_kernel(const uint8_t *__restrict__ buf, const uint64_t *__restrict__ poff,
+                                                                       int64_t n_payload, int64_t n_frames, uint8_t *status,
+                                                                       uint32_t *seq, uint8_t *chid, uint32_t *valid,
+                                                                       unsigned long long *n_bad, uint8_t *imdt_spec, int skip)
 {
     __shared__ __align__(16) uint32_t s_w[(IMTR_FRONT + IMTR_RUNS * IMTR_RUN_WORDS * 4 + 32) / 4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -948,25 +948,40 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_runs_kernel(const uint8_
     const int n_runs = (o0 + 882 * n_here + 879) / 880;      // runs that hold bytes of this batch (<= 34, all < n_payload)
     const unsigned long long pl0 = poff[min(i0 + lane, n_payload - 1)], pl1 = poff[min(i0 + 32 + lane, n_payload - 1)];
     uint32_t *runs = s_w + IMTR_FRONT / 4;
-    for (int k = wid; k < n_runs; k += IMTR_T / 32) {
+    // A warp copies runs wid, wid + 4, ...: lane l loads the ALIGNED source words l, l + 32, ... (221 words cover the run at any
+    // alignment: the last one reaches at most 4 bytes past the payload, still inside its 1024-byte AOS frame); the upper
+    // neighbour of a word comes from lane + 1 by shuffle, so a run costs 7 loads and 7 registers per lane and the loads of
+    // IMTR_DEPTH runs are in flight while the oldest is shifted and stored (the first version loaded both words of every
+    // pair and waited for one run at a time: 9 dependent memory round trips per warp, long-scoreboard stall 4.3 per issue).
+    uint32_t R[IMTR_DEPTH][7], shv[IMTR_DEPTH];
+    auto load_run = [&](int k, uint32_t (&dstw)[7], uint32_t &sh) {
         const unsigned long long a0 = __shfl_sync(0xffffffffu, pl0, k & 31), a1 = __shfl_sync(0xffffffffu, pl1, k & 31);
         const uint8_t *a = buf + (k < 32 ? a0 : a1);
-        const uint32_t sh = (uint32_t)((uintptr_t)a & 3u);
-        // aligned words around the run: the last one reaches at most 3 bytes past it, which are bytes of the same 1024-byte
-        // AOS frame (CRC / LDPC field); an aligned run reads nothing past its end
+        sh = (uint32_t)((uintptr_t)a & 3u);
         const uint32_t *w = reinterpret_cast<const uint32_t *>(a - sh);
-        const int up = sh ? 1 : 0;
-        uint32_t lo[7], hi[7];
 #pragma unroll
-        for (int u = 0; u < 7; ++u) {
-            const int idx = min(lane + 32 * u, IMTR_RUN_WORDS - 1);
-            lo[u] = __ldg(w + idx);
-            hi[u] = __ldg(w + idx + up);
-        }
+        for (int u = 0; u < 7; ++u) dstw[u] = __ldg(w + min(lane + 32 * u, IMTR_RUN_WORDS));
+    };
+#pragma unroll
+    for (int d = 0; d < IMTR_DEPTH - 1; ++d)
+        if (wid + 4 * d < n_runs) load_run(wid + 4 * d, R[d], shv[d]);
+#pragma unroll
+    for (int it = 0; it < (IMTR_RUNS + 3) / 4; ++it) {
+        const int k = wid + 4 * it;
+        if (k >= n_runs) break;
+        if (k + 4 * (IMTR_DEPTH - 1) < n_runs) load_run(k + 4 * (IMTR_DEPTH - 1), R[(it + IMTR_DEPTH - 1) % IMTR_DEPTH], shv[(it + IMTR_DEPTH - 1) % IMTR_DEPTH]);
+        uint32_t (&lo)[7] = R[it % IMTR_DEPTH];
+        const uint32_t sh8 = 8u * shv[it % IMTR_DEPTH];
         uint32_t *dst = runs + IMTR_RUN_WORDS * k;
 #pragma unroll
-        for (int u = 0; u < 7; ++u)
-            if (lane + 32 * u < IMTR_RUN_WORDS) dst[lane + 32 * u] = __funnelshift_r(lo[u], hi[u], 8u * sh);
+        for (int u = 0; u < 7; ++u) {
+            uint32_t hi = __shfl_down_sync(0xffffffffu, lo[u], 1);
+            if (u < 6) {
+                const uint32_t first = __shfl_sync(0xffffffffu, lo[u + 1], 0);
+                hi = lane == 31 ? first : hi;
+            }
+            if (lane + 32 * u < IMTR_RUN_WORDS) dst[lane + 32 * u] = __funnelshift_r(lo[u], hi, sh8);
+        }
     }
     __syncthreads();
     const uint32_t fbase = (uint32_t)(IMTR_FRONT + o0);    // byte offset of frame 0 inside s_w
@@ -994,8 +1009,9 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_runs_kernel(const uint8_
     }
     // ---- CRCs of the 32 frames, bit-sliced exactly as in imtr_validate_kernel; only the loads differ: the span of frame q
     //      starts at byte fbase - 20 + 882 q, so odd and even frames have their own alignment (two aligned words + shift)
-    __shared__ uint32_t s_part[4][16][32];
-    uint32_t P[16];
+    __shared__ uint32_t s_part[3][16][32];              // the validating warp keeps its own part in registers
+    const int vwarp = (int)(blockIdx.x & 3);            // rotate the validating warp over the SM's four schedulers
+    uint32_t P[16], Q[16];
     {
         const uint32_t c = fbase - (uint32_t)(bitslice::SPAN - 876) + 28u * (uint32_t)lane; // this lane's piece of frame 0 (IMTR_FRONT >= 20)
         const uint32_t r = c & 3u, t = r + 2u;
@@ -1021,7 +1037,6 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_runs_kernel(const uint8_
 #pragma unroll
             for (int i = 0; i < 16; ++i) P[i] = 0u;
         }
-        uint32_t Q[16];
         if (wid == 0) bitslice::mul_xpow<160>(P, Q);
         else if (wid == 1) bitslice::mul_xpow<96>(P, Q);
         else if (wid == 2) bitslice::mul_xpow<32>(P, Q);
@@ -1029,13 +1044,15 @@ __global__ void __launch_bounds__(IMTR_T) imtr_validate_runs_kernel(const uint8_
 #pragma unroll
             for (int i = 0; i < 16; ++i) Q[i] = P[i];
         }
+        if (wid != vwarp) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s_part[wid][i][lane] = Q[i];
+            for (int i = 0; i < 16; ++i) s_part[(wid - vwarp - 1) & 3][i][lane] = Q[i];
+        }
     }
     __syncthreads();
-    if (wid != (int)(blockIdx.x & 3)) return;
+    if (wid != vwarp) return;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) P[i] = s_part[0][i][lane] ^ s_part[1][i][lane] ^ s_part[2][i][lane] ^ s_part[3][i][lane];
+    for (int i = 0; i < 16; ++i) P[i] = Q[i] ^ s_part[0][i][lane] ^ s_part[1][i][lane] ^ s_part[2][i][lane];
     {
         auto x = [](uint32_t v, int sd, int) { return __shfl_xor_sync(0xffffffffu, v, sd); };
         bitslice::join_level<1>(P, lane, x);
@@ -1151,35 +1168,7 @@ __global__ void __launch_bounds__(256) find_sig4_kernel(const uint8_t *__restric
     const int64_t end = (int64_t)mis + n;                       // bytes [mis, end) of the aligned image are the stream
     const int64_t n_chunks = (end + 15) >> 4;
     const uint32_t p0pat = 0x01010101u * (sig_le & 0xFFu), p1pat = 0x01010101u * ((sig_le >> 8) & 0xFFu);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // (the loop bound is warp-uniform: every lane of a warp takes part in the shuffle)
-    for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); c0 < n_chunks; c0 += stride) {
-        const int64_t c = c0 + lane, q0 = c << 4;
-        uint32_t w[5];
-        if (q0 + 16 <= end) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(A + q0));
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint32_t v = 0;
-                for (int b = 0; b < 4; ++b) {
-                    const int64_t q = q0 + 4 * i + b;
-                    v |= (uint32_t)(q < end ? A[q] : 0) << (8 * b);
-                }
-                w[i] = v;
-            }
-        }
-        w[4] = __shfl_down_sync(0xffffffffu, w[0], 1);
-        if (lane == 31) {
-            w[4] = 0u;
-            if (q0 + 20 <= end) w[4] = __ldg(reinterpret_cast<const uint32_t *>(A + q0 + 16));
-            else
-                for (int b = 0; b < 4; ++b) {
-                    const int64_t q = q0 + 16 + b;
-                    w[4] |= (uint32_t)(q < end ? A[q] : 0) << (8 * b);
-                }
-        }
+    auto scan16 = [&](const uint32_t (&w)[5], int64_t q0) {   // the 16 positions of one chunk (w[4] = first word of the next chunk)
         uint32_t acc = 0u;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1197,6 +1186,42 @@ __global__ void __launch_bounds__(256) find_sig4_kernel(const uint8_t *__restric
                         if (k < cap) hits[k] = (unsigned long long)p;
                     }
                 }
+        }
+    };
+    // a warp takes FIND_M x 32 consecutive chunks per iteration (all loads issued before the first use: one 16-byte load per
+    // thread in flight left the kernel latency-bound at 46 % of the DRAM rate); the loop bounds are warp-uniform
+    constexpr int FIND_M = 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * FIND_M;
+    for (int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * FIND_M; c0 < n_chunks; c0 += stride) {
+        if (((c0 + 32 * FIND_M) << 4) + 4 <= end) {          // everything this warp touches lies inside the stream image
+            uint4 v[FIND_M];
+#pragma unroll
+            for (int m = 0; m < FIND_M; ++m) v[m] = __ldg(reinterpret_cast<const uint4 *>(A + ((c0 + 32 * m + lane) << 4)));
+            uint32_t tail = 0u;
+            if (lane == 31) tail = __ldg(reinterpret_cast<const uint32_t *>(A + ((c0 + 32 * FIND_M) << 4)));
+#pragma unroll
+            for (int m = 0; m < FIND_M; ++m) {
+                uint32_t w[5] = {v[m].x, v[m].y, v[m].z, v[m].w, 0u};
+                w[4] = __shfl_down_sync(0xffffffffu, v[m].x, 1);
+                const uint32_t nxt = m + 1 < FIND_M ? __shfl_sync(0xffffffffu, v[m + 1 < FIND_M ? m + 1 : m].x, 0) : tail;
+                if (lane == 31) w[4] = nxt;
+                scan16(w, (c0 + 32 * m + lane) << 4);
+            }
+            continue;
+        }
+        for (int m = 0; m < FIND_M; ++m) {                    // the last chunks of the stream: guarded byte loads
+            const int64_t q0 = (c0 + 32 * m + lane) << 4;
+            uint32_t w[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                uint32_t x = 0;
+                for (int b = 0; b < 4; ++b) {
+                    const int64_t q = q0 + 4 * i + b;
+                    x |= (uint32_t)(q < end ? A[q] : 0) << (8 * b);
+                }
+                w[i] = x;
+            }
+            scan16(w, q0);
         }
     }
 }
@@ -1539,6 +1564,10 @@ static int imtr_deframe_impl(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t 
     OIP_CUDA(cudaMemsetAsync(d_first_chid, 0xFF, 4, ctx->stream));
     // one stream-ordered chain, one host round trip at the end
     const bool speculative = (uint64_t)nf * 866 <= (uint64_t)cap; // room for every cut frame: validate writes them in place
+    if (!ctx->imtr_attr_set) { // six 36 KB CTAs per SM need the large shared-memory carve-out
+        OIP_CUDA(cudaFuncSetAttribute(imtr_validate_runs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        ctx->imtr_attr_set = true;
+    }
     (ctx->imtr_runs ? imtr_validate_runs_kernel : imtr_validate_kernel)<<<(unsigned)((nf + IMTR_BATCH - 1) / IMTR_BATCH), IMTR_T, 0, ctx->stream>>>(
         d_buf, d_payload_off, n_payload, nf, S + o_status, (uint32_t *)(S + o_seq), S + o_chid, (uint32_t *)(S + o_valid), d_bad,
         speculative ? d_imdt : nullptr, skip);
@@ -1600,7 +1629,7 @@ extern "C" int oip_image_frames_index(oip_ctx *ctx, const uint8_t *d_imdt, size_
         if (rc) return rc;
         uint8_t *S = (uint8_t *)ctx->d_scratch;
         OIP_CUDA(cudaMemsetAsync(S + o_n, 0, 16, ctx->stream));
-        const int blocks = (int)std::min<int64_t>((n / 16 + 1 + 255) / 256 + 1, (int64_t)ctx->sm_count * 32);
+        const int blocks = (int)std::min<int64_t>((n / 64 + 1 + 255) / 256 + 1, (int64_t)ctx->sm_count * 16);
         find_sig4_kernel<<<blocks, 256, 0, ctx->stream>>>(d_imdt, n, 0x4DE190EBu, 0xEB, (unsigned long long *)(S + o_hits),
                                                          hit_cap, (uint32_t *)(S + o_n));
         OIP_CUDA(cudaGetLastError());
