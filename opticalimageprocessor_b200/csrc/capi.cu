@@ -134,6 +134,7 @@ int oip_ctx_set_option(oip_ctx *ctx, const char *name, int64_t value)
     else if (!strcmp(name, "mss_fast")) ctx->mss_fast = value != 0;
     else if (!strcmp(name, "aos_fused")) ctx->aos_fused = value != 0;
     else if (!strcmp(name, "imtr_runs")) ctx->imtr_runs = value != 0;
+    else if (!strcmp(name, "downlink_threads")) ctx->downlink_threads = value != 0;
     else if (!strcmp(name, "mss_fast_rows") && value >= 16 && value <= 32768) ctx->mss_fast_rows = (int)value;
     else if (!strcmp(name, "pan_fast_rows") && value >= 16 && value <= 32768) ctx->pan_fast_rows = (int)value;
     else return oip::fail(OIP_E_INVALID, "unknown option or value out of range: %s=%lld", name, (long long)value);

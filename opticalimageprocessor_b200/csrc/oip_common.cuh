@@ -53,6 +53,7 @@ struct oip_ctx {
     int64_t mss_fast_ctas = 0;   // mss_fast_kernel CTAs
     size_t mss_fast_off = 0;     // byte offset of the FTile array inside d_mss_plan
     int aos_fused = 1;           // 0: oip_aos_scan uses the exhaustive search kernels of round 1 (aos_scan_kernel + aos_crc_kernel)
+    int downlink_threads = 1;    // 0: oip_downlink_to_stitched runs stage 1 of its CCDs one after the other on the caller's stream
     int imtr_runs = 1;           // 0: oip_imtr_deframe gathers frame by frame (imtr_validate_kernel) instead of run by run
     int mss_fast = 1;            // 0: every MSS tile on the generic kernel
     int mss_fast_rows = 128;     // output rows per MSS warp-tile

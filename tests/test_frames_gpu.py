@@ -368,17 +368,45 @@ def test_downlink_to_stitched_matches_oracle_chain(ctx, oracle_mod, tc, tl, n_fr
     dX, dY = [0, 1.37, -0.83], [0, -2.61, 3.19]
     S, G = 150, 160
     want = oracle_mod.pan_pipeline(pans, kbs, dX, dY, f, S, G)
-    l0 = ctx.launches
-    got, stats, aux_g, mss_g = ops.downlink_to_stitched(ctx, files, tc, tl, [_dev(k) for k in kbs], dX, dY, f, section_rows=S, row_guard=G,
-                                                        want_aux=True, want_mss=True)
-    ctx.sync()
-    assert ctx.launches > l0
-    assert got.shape == want.shape
-    bad = np.argwhere(got.cpu().numpy() != want)
-    assert bad.size == 0, f"{len(bad)} px differ, first {bad[:5].tolist()}"
-    for i in range(3):
-        assert stats[i]["frames"][1] == n_fr and stats[i]["aos"][1] >= 1 and stats[i]["aos"][2] >= 1
-        assert np.array_equal(aux_g[i].cpu().numpy(), auxs[i]) and np.array_equal(mss_g[i].cpu().numpy(), msss[i])
+    for threads in (1, 0, 1):   # stage 1 of the three CCDs side by side (child contexts + host threads, the default; twice: the
+        ctx.set_option("downlink_threads", threads)   # second call reuses the child contexts) and one after the other
+        try:
+            l0 = ctx.launches
+            got, stats, aux_g, mss_g = ops.downlink_to_stitched(ctx, files, tc, tl, [_dev(k) for k in kbs], dX, dY, f, section_rows=S,
+                                                                row_guard=G, want_aux=True, want_mss=True)
+            ctx.sync()
+        finally:
+            ctx.set_option("downlink_threads", 1)
+        assert ctx.launches > l0 + 20, threads
+        assert got.shape == want.shape
+        bad = np.argwhere(got.cpu().numpy() != want)
+        assert bad.size == 0, f"{len(bad)} px differ, first {bad[:5].tolist()} (threads={threads})"
+        for i in range(3):
+            assert stats[i]["frames"][1] == n_fr and stats[i]["aos"][1] >= 1 and stats[i]["aos"][2] >= 1
+            assert np.array_equal(aux_g[i].cpu().numpy(), auxs[i]) and np.array_equal(mss_g[i].cpu().numpy(), msss[i])
+
+
+def test_downlink_to_stitched_reports_the_failing_ccd(ctx):
+    """an error inside a worker thread (here: a JPEG-2000 compressed frame in the second downlink, which is refused) reaches
+    the caller with its text and the CCD it belongs to"""
+    from opticalimageprocessor_b200 import ops
+    tc, tl = 16, 4
+    imdt, _ = synth.make_imdt(2, tc, tl, seed=3)
+    frame_bytes = 192 * tl + 40 * tc * tl * 2 + 172
+    z = imdt.copy()
+    z[frame_bytes - 172 + 4] |= 0x05          # z_ratio of frame 1 (ref aux_separator.h:639)
+    wrap = lambda b: _dev(synth.aos_frames(synth.imtr_frames(b, chid=0x11).reshape(-1)).reshape(-1))
+    good, bad = wrap(imdt), wrap(z)
+    kbs = [_dev(synth.rrc_coeffs(8 * tc, 5 + i)) for i in range(3)]
+    for threads in (1, 0):
+        ctx.set_option("downlink_threads", threads)
+        try:
+            with pytest.raises(RuntimeError, match="JPEG-2000") as ei:
+                ops.downlink_to_stitched(ctx, [good, bad, good], tc, tl, kbs, [0, 1.0, -1.0], [0, 1.0, -1.0], 4)
+        finally:
+            ctx.set_option("downlink_threads", 1)
+        if threads:
+            assert "ccd 1" in str(ei.value)
 
 
 @pytest.mark.parametrize("bits", [10, 12])
