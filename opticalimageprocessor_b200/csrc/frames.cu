@@ -992,28 +992,6 @@ __global__ void __launch_bounds__(IMTR_T, 6) imtr_validate_runs_kernel(const uin
     }
     __syncthreads();
     const uint32_t fbase = (uint32_t)(IMTR_FRONT + o0);    // byte offset of frame 0 inside s_w
-    if (imdt_spec) {
-        // speculative output (see imtr_validate_kernel): frame f's 866 payload bytes land at f * 866
-        for (int q = wid; q < n_here; q += IMTR_T / 32) {
-            uint8_t *d = imdt_spec + (uint64_t)(f0 + q) * 866;
-            const uint32_t pb = fbase + 882u * (uint32_t)q + 10u;        // payload start inside s_w (bytes)
-            const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_w);
-            const int head = (int)((4u - (uint32_t)((uintptr_t)d & 3u)) & 3u);
-            if (lane < head) d[lane] = sb[pb + lane];
-            const int nw = (866 - head) >> 2;
-            const uint32_t s0 = pb + (uint32_t)head;
-            const uint32_t sh = 8u * (s0 & 3u);
-            const uint32_t *sw = s_w + (s0 >> 2);
-            uint32_t *dw = reinterpret_cast<uint32_t *>(d + head);
-#pragma unroll
-            for (int u = 0; u < 7; ++u) {
-                const int k = lane + 32 * u;
-                if (k < nw) dw[k] = __funnelshift_r(sw[k], sw[k + 1], sh);
-            }
-            const int t0 = head + 4 * nw;
-            if (lane < 866 - t0) d[t0 + lane] = sb[pb + t0 + lane];
-        }
-    }
     // ---- CRCs of the 32 frames, bit-sliced exactly as in imtr_validate_kernel; only the loads differ: the span of frame q
     //      starts at byte fbase - 20 + 882 q, so odd and even frames have their own alignment (two aligned words + shift)
     __shared__ uint32_t s_part[3][16][32];              // the validating warp keeps its own part in registers
@@ -1057,6 +1035,30 @@ __global__ void __launch_bounds__(IMTR_T, 6) imtr_validate_runs_kernel(const uin
         }
     }
     __syncthreads();
+    if (wid != vwarp && imdt_spec) {
+        // speculative output (see imtr_validate_kernel): frame f's 866 payload bytes land at f * 866.  Done by the three warps
+        // that have no part in the last phase, WHILE the fourth joins the CRCs and validates (stores next to ALU work; with
+        // the stores in front of the CRC phase the CTA kept its shared memory for ~1.5 us with one warp running)
+        for (int q = (wid - vwarp - 1) & 3; q < n_here; q += IMTR_T / 32 - 1) {
+            uint8_t *d = imdt_spec + (uint64_t)(f0 + q) * 866;
+            const uint32_t pb = fbase + 882u * (uint32_t)q + 10u;        // payload start inside s_w (bytes)
+            const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_w);
+            const int head = (int)((4u - (uint32_t)((uintptr_t)d & 3u)) & 3u);
+            if (lane < head) d[lane] = sb[pb + lane];
+            const int nw = (866 - head) >> 2;
+            const uint32_t s0 = pb + (uint32_t)head;
+            const uint32_t sh = 8u * (s0 & 3u);
+            const uint32_t *sw = s_w + (s0 >> 2);
+            uint32_t *dw = reinterpret_cast<uint32_t *>(d + head);
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                const int k = lane + 32 * u;
+                if (k < nw) dw[k] = __funnelshift_r(sw[k], sw[k + 1], sh);
+            }
+            const int t0 = head + 4 * nw;
+            if (lane < 866 - t0) d[t0 + lane] = sb[pb + t0 + lane];
+        }
+    }
     if (wid != vwarp) return;
 #pragma unroll
     for (int i = 0; i < 16; ++i) P[i] = Q[i] ^ s_part[0][i][lane] ^ s_part[1][i][lane] ^ s_part[2][i][lane];
