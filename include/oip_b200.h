@@ -56,7 +56,12 @@ int64_t oip_ctx_launch_count(oip_ctx *ctx);
 
 /* tunables / test switches.  "pan_fast" (0|1, default 1): 0 sends every PAN tile through the generic kernel;
  * "pan_fast_stages" (2..8): TMA stages per warp; "pan_fast_rows": output rows per warp-tile;
- * "mss_fast" (0|1), "mss_fast_rows": the same switches for oip_band_align_merge. */
+ * "mss_fast" (0|1), "mss_fast_rows": the same switches for oip_band_align_merge;
+ * "aos_fused" (0|1, default 1): 0 = oip_aos_scan searches every byte (aos_scan_kernel + aos_crc_kernel) instead of
+ * the single cadence pass; "imtr_runs" (0|1, default 1): 0 = oip_imtr_deframe gathers frame by frame instead of run by
+ * run; "downlink_threads" (0|1, default 1): 0 = oip_downlink_to_stitched runs stage 1 of its CCDs one after the other
+ * on the caller's stream instead of side by side; "host_block_rows": rows per block of oip_pan_pipeline_host.
+ * Every switch selects between two implementations with identical results (the tests run both). */
 int oip_ctx_set_option(oip_ctx *ctx, const char *name, int64_t value);
 
 /* raw memory helpers for hosts without their own allocator (the CLI); torch callers pass data_ptr() */
@@ -382,7 +387,10 @@ typedef struct {
  *   AuxSeparator::Separate (SeparateAosFile, DataTransFrameParser, SeparateImageData)  ref aux_separator.h:224-245, :256-590
  *   IMO::InplaceRRC, Stitcher::PreStitch + IMO::SectionaryRemap, IMO::StitchBigRaw       ref imageop.h:129-138, :230-363
  * The fused PAN kernel reads the sub-images where they lie in the IMDT stream; .PAN.RAW / .RRC.RAW / .PRESTT.RAW never
- * exist.  *rows_out = lines produced (frames x 4*tile_lines, the shortest CCD decides); stats[n_ccd] may be NULL. */
+ * exist.  *rows_out = lines produced (frames x 4*tile_lines, the shortest CCD decides); stats[n_ccd] may be NULL.
+ * Stage 1 of the CCDs runs side by side (one child context with its own stream and one host thread per CCD, joined
+ * before the PAN launch on ctx's stream; the files are read after whatever ctx's stream held when the call was made).
+ * A failure in one CCD is returned with "ccd <i>: " in front of its text. */
 int oip_downlink_to_stitched(oip_ctx *ctx, const oip_downlink_desc *desc, int64_t *rows_out, oip_downlink_stats *stats);
 
 /* ---- bench / test input (NOT a replaced reference function) --------------------------------- */

@@ -972,22 +972,27 @@ __global__ void __launch_bounds__(IMTR_T, 6) imtr_validate_runs_kernel(const uin
 #pragma unroll
     for (int d = 0; d < IMTR_DEPTH - 1; ++d)
         if (wid + 4 * d < n_runs) load_run(wid + 4 * d, R[d], shv[d]);
+    // (the ring index is a compile-time constant inside the IMTR_DEPTH-times unrolled body; the outer loop stays rolled: with
+    // all nine iterations unrolled the kernel grew to 4096 instructions and stalled on instruction fetch, 1.8 per issue)
+#pragma unroll 1
+    for (int it0 = 0; wid + 4 * it0 < n_runs; it0 += IMTR_DEPTH) {
 #pragma unroll
-    for (int it = 0; it < (IMTR_RUNS + 3) / 4; ++it) {
-        const int k = wid + 4 * it;
-        if (k >= n_runs) break;
-        if (k + 4 * (IMTR_DEPTH - 1) < n_runs) load_run(k + 4 * (IMTR_DEPTH - 1), R[(it + IMTR_DEPTH - 1) % IMTR_DEPTH], shv[(it + IMTR_DEPTH - 1) % IMTR_DEPTH]);
-        uint32_t (&lo)[7] = R[it % IMTR_DEPTH];
-        const uint32_t sh8 = 8u * shv[it % IMTR_DEPTH];
-        uint32_t *dst = runs + IMTR_RUN_WORDS * k;
+        for (int d = 0; d < IMTR_DEPTH; ++d) {
+            const int k = wid + 4 * (it0 + d);
+            if (k >= n_runs) break;
+            if (k + 4 * (IMTR_DEPTH - 1) < n_runs) load_run(k + 4 * (IMTR_DEPTH - 1), R[(d + IMTR_DEPTH - 1) % IMTR_DEPTH], shv[(d + IMTR_DEPTH - 1) % IMTR_DEPTH]);
+            uint32_t (&lo)[7] = R[d];
+            const uint32_t sh8 = 8u * shv[d];
+            uint32_t *dst = runs + IMTR_RUN_WORDS * k;
 #pragma unroll
-        for (int u = 0; u < 7; ++u) {
-            uint32_t hi = __shfl_down_sync(0xffffffffu, lo[u], 1);
-            if (u < 6) {
-                const uint32_t first = __shfl_sync(0xffffffffu, lo[u + 1], 0);
-                hi = lane == 31 ? first : hi;
+            for (int u = 0; u < 7; ++u) {
+                uint32_t hi = __shfl_down_sync(0xffffffffu, lo[u], 1);
+                if (u < 6) {
+                    const uint32_t first = __shfl_sync(0xffffffffu, lo[u + 1], 0);
+                    hi = lane == 31 ? first : hi;
+                }
+                if (lane + 32 * u < IMTR_RUN_WORDS) dst[lane + 32 * u] = __funnelshift_r(lo[u], hi, sh8);
             }
-            if (lane + 32 * u < IMTR_RUN_WORDS) dst[lane + 32 * u] = __funnelshift_r(lo[u], hi, sh8);
         }
     }
     __syncthreads();
