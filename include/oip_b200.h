@@ -152,6 +152,20 @@ int oip_image_frames_index(oip_ctx *ctx, const uint8_t *d_imdt, size_t n_bytes,
                            const oip_frame_geom *geom, oip_frame_entry *entries, int64_t cap,
                            int64_t stats[4]);
 
+/* The two halves of oip_image_frames_index, for an IMDT stream that lives in pieces on several GPUs: every
+ * rank searches its own piece (plus the first 174 bytes of what follows, so that a signature or trailer cut by the piece
+ * boundary is seen whole), the ranks all-gather the few hundred (offset, trailer) pairs, and each runs the chain over the
+ * whole table (opticalimageprocessor_b200/sharding.py frames_index_shards).
+ * oip_image_frames_hits: every occurrence of the trailer signature EB 90 E1 4D (ref aux_separator.h:82, :632 memmem) in
+ * d_imdt[0, n_bytes), ascending, with the 172 bytes that start there (zero padded past the end); hits / trailers are HOST
+ * arrays of capacity cap / cap * 172; *n_hits is set even when the capacity was too small (OIP_E_INVALID).
+ * oip_image_frames_chain: host only, no context -- NextImageDataFrame + the gap rules of SeparateImageData over a
+ * signature table whose offsets are relative to the whole stream of n_bytes (ref aux_separator.h:627-656, :287-320). */
+int oip_image_frames_hits(oip_ctx *ctx, const uint8_t *d_imdt, size_t n_bytes, uint64_t *hits, uint8_t *trailers, int64_t cap,
+                          int64_t *n_hits);
+int oip_image_frames_chain(const uint64_t *hits, const uint8_t *trailers, int64_t n_hits, size_t n_bytes, const oip_frame_geom *geom,
+                           oip_frame_entry *entries, int64_t cap, int64_t stats[4]);
+
 /* aux copy + tile de-interleave + BE->LE swap for n_frames entries (zero fill for gap entries).
  * replaces WriteAuxData / WriteImageData / MergeSubImage / InflateSubImage(z_ratio==0) --
  * ref aux_separator.h:335-393.  Any of d_aux/d_pan/d_mss may be NULL to skip that product.

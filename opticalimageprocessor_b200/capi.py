@@ -113,6 +113,8 @@ SYMBOLS = {
     "oip_imtr_deframe": (_I, [_VP, _VP, _VP, _I64, _VP, _SZ, C.POINTER(_I64), C.POINTER(_I64)]),
     "oip_imtr_deframe_shard": (_I, [_VP, _VP, _VP, _I64, _I, _I64, _I64, _VP, _SZ, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "oip_image_frames_index": (_I, [_VP, _VP, _SZ, C.POINTER(FrameGeom), C.POINTER(FrameEntry), _I64, C.POINTER(_I64)]),
+    "oip_image_frames_hits": (_I, [_VP, _VP, _SZ, _VP, _VP, _I64, C.POINTER(_I64)]),
+    "oip_image_frames_chain": (_I, [_VP, _VP, _I64, _SZ, C.POINTER(FrameGeom), C.POINTER(FrameEntry), _I64, C.POINTER(_I64)]),
     "oip_unpack_frames": (_I, [_VP, _VP, _SZ, C.POINTER(FrameGeom), C.POINTER(FrameEntry), _I64, _VP, _VP, _VP]),
     "oip_rrc_u16": (_I, [_VP, _VP, _I, _I64, _I64, _VP]),
     "oip_load_rrc_csv": (_I, [C.c_char_p, _I, _VP]),

@@ -1623,18 +1623,9 @@ static int imtr_deframe_impl(oip_ctx *ctx, const uint8_t *d_buf, const uint64_t 
     return OIP_OK;
 }
 
-extern "C" int oip_image_frames_index(oip_ctx *ctx, const uint8_t *d_imdt, size_t n_bytes, const oip_frame_geom *geom,
-                                      oip_frame_entry *entries, int64_t cap, int64_t stats[4])
+// device part of the frame index: every occurrence of EB 90 E1 4D, in ascending order, with the 172 bytes that start there
+static int frames_hits(oip_ctx *ctx, const uint8_t *d_imdt, int64_t n, std::vector<unsigned long long> &hits_sorted, std::vector<uint8_t> &trailers_sorted)
 {
-    OIP_CHECK_CTX(ctx);
-    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
-    if (!geom || geom->tile_cols < 1 || geom->tile_lines < 1) return fail(OIP_E_INVALID, "oip_image_frames_index: bad geometry");
-    if (!d_imdt && n_bytes) return fail(OIP_E_INVALID, "oip_image_frames_index: null buffer");
-    const int64_t n = (int64_t)n_bytes;
-    const int64_t aux_all = 192 * (int64_t)geom->tile_lines;            // IMGSIG_AUX_ALLBYTES
-    const int64_t tile_bytes = (int64_t)geom->tile_lines * geom->tile_cols * 2;
-    if (n <= aux_all + 172) return OIP_OK;                               // ref :630
-    // ---- device: all occurrences of EB 90 E1 4D
     uint32_t hit_cap = (uint32_t)std::min<int64_t>(n / 4 + 1, std::max<int64_t>(4096, n / 65536));
     std::vector<unsigned long long> hits;
     std::vector<uint8_t> trailers;
@@ -1671,7 +1662,46 @@ extern "C" int oip_image_frames_index(oip_ctx *ctx, const uint8_t *d_imdt, size_
     std::vector<uint32_t> order(hits.size());
     for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hits[a] < hits[b]; });
+    hits_sorted.resize(hits.size());
+    trailers_sorted.resize(trailers.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+        hits_sorted[i] = hits[order[i]];
+        memcpy(trailers_sorted.data() + i * 172, trailers.data() + (size_t)order[i] * 172, 172);
+    }
+    return OIP_OK;
+}
 
+extern "C" int oip_image_frames_hits(oip_ctx *ctx, const uint8_t *d_imdt, size_t n_bytes, uint64_t *hits, uint8_t *trailers, int64_t cap,
+                                     int64_t *n_hits)
+{
+    OIP_CHECK_CTX(ctx);
+    if (!n_hits) return fail(OIP_E_INVALID, "oip_image_frames_hits: n_hits is null");
+    *n_hits = 0;
+    if (!d_imdt && n_bytes) return fail(OIP_E_INVALID, "oip_image_frames_hits: null buffer");
+    if (n_bytes < 4) return OIP_OK;
+    std::vector<unsigned long long> h;
+    std::vector<uint8_t> t;
+    int rc = frames_hits(ctx, d_imdt, (int64_t)n_bytes, h, t);
+    if (rc) return rc;
+    *n_hits = (int64_t)h.size();
+    if ((int64_t)h.size() > cap) return fail(OIP_E_INVALID, "oip_image_frames_hits: %zu signatures exceed capacity %lld", h.size(), (long long)cap);
+    if (h.size() && (!hits || !trailers)) return fail(OIP_E_INVALID, "oip_image_frames_hits: null output");
+    for (size_t i = 0; i < h.size(); ++i) hits[i] = (uint64_t)h[i];
+    if (t.size()) memcpy(trailers, t.data(), t.size());
+    return OIP_OK;
+}
+
+// host part of the frame index (no device, no context): NextImageDataFrame chain + gap rules over the signature table
+extern "C" int oip_image_frames_chain(const uint64_t *hits, const uint8_t *trailer_bytes, int64_t n_hits, size_t n_bytes, const oip_frame_geom *geom,
+                                      oip_frame_entry *entries, int64_t cap, int64_t stats[4])
+{
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (!geom || geom->tile_cols < 1 || geom->tile_lines < 1) return fail(OIP_E_INVALID, "oip_image_frames_chain: bad geometry");
+    if (n_hits < 0 || (n_hits && (!hits || !trailer_bytes))) return fail(OIP_E_INVALID, "oip_image_frames_chain: bad signature table");
+    const int64_t n = (int64_t)n_bytes;
+    const int64_t aux_all = 192 * (int64_t)geom->tile_lines;            // IMGSIG_AUX_ALLBYTES
+    const int64_t tile_bytes = (int64_t)geom->tile_lines * geom->tile_cols * 2;
+    if (n <= aux_all + 172) return OIP_OK;                               // ref :630
     // ---- host: NextImageDataFrame chain + gap rules (ref :627-656, :287-320); only trailers are needed
     auto be32 = [](const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; };
     int64_t p = 0, remain = n, emitted = 0, found = 0, incomplete = 0;
@@ -1679,11 +1709,11 @@ extern "C" int oip_image_frames_index(oip_ctx *ctx, const uint8_t *d_imdt, size_
     size_t hi = 0;
     for (;;) {
         if (remain <= aux_all + 172) break;                              // :630
-        while (hi < order.size() && (int64_t)hits[order[hi]] < p) ++hi;   // memmem from p
-        if (hi >= order.size()) break;
-        const int64_t sp = (int64_t)hits[order[hi]];
+        while (hi < (size_t)n_hits && (int64_t)hits[hi] < p) ++hi;        // memmem from p
+        if (hi >= (size_t)n_hits) break;
+        const int64_t sp = (int64_t)hits[hi];
         if (sp + 172 > n) break; // the reference would parse past the mapping
-        const uint8_t *t = trailers.data() + (size_t)order[hi] * 172;
+        const uint8_t *t = trailer_bytes + hi * 172;
         const int64_t frame_end = sp + 172;                              // :634
         const int z_ratio = t[4] & 0x3F;                                 // :639
         const int seq = (int)(((uint32_t)t[6] << 8) | t[7]);            // :642-643
@@ -1732,6 +1762,22 @@ extern "C" int oip_image_frames_index(oip_ctx *ctx, const uint8_t *d_imdt, size_
     if (stats) { stats[0] = found; stats[1] = emitted; stats[2] = incomplete; stats[3] = last_seq; }
     if (entries && emitted > cap) return fail(OIP_E_INVALID, "oip_image_frames_index: %lld frames exceed capacity %lld", (long long)emitted, (long long)cap);
     return OIP_OK;
+}
+
+extern "C" int oip_image_frames_index(oip_ctx *ctx, const uint8_t *d_imdt, size_t n_bytes, const oip_frame_geom *geom,
+                                      oip_frame_entry *entries, int64_t cap, int64_t stats[4])
+{
+    OIP_CHECK_CTX(ctx);
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (!geom || geom->tile_cols < 1 || geom->tile_lines < 1) return fail(OIP_E_INVALID, "oip_image_frames_index: bad geometry");
+    if (!d_imdt && n_bytes) return fail(OIP_E_INVALID, "oip_image_frames_index: null buffer");
+    if ((int64_t)n_bytes <= 192 * (int64_t)geom->tile_lines + 172) return OIP_OK;                    // ref :630
+    std::vector<unsigned long long> h;
+    std::vector<uint8_t> t;
+    int rc = frames_hits(ctx, d_imdt, (int64_t)n_bytes, h, t);
+    if (rc) return rc;
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "hit table layout");
+    return oip_image_frames_chain(reinterpret_cast<const uint64_t *>(h.data()), t.data(), (int64_t)h.size(), n_bytes, geom, entries, cap, stats);
 }
 
 extern "C" int oip_unpack_frames(oip_ctx *ctx, const uint8_t *d_imdt, size_t n_bytes, const oip_frame_geom *geom,

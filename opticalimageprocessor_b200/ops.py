@@ -405,6 +405,46 @@ def image_frames_index(ctx: Context, imdt: torch.Tensor, tile_cols: int, tile_li
     return ents, np.array(list(st), np.int64)
 
 
+def image_frames_hits(ctx: Context, imdt: torch.Tensor):
+    """device half of the frame index (oip_image_frames_hits): ascending offsets of the trailer signature in `imdt` and the
+    172 bytes that start at each (zero padded past the end) -> (uint64[n], uint8[n, 172]) on the host"""
+    cap = max(64, imdt.numel() // 4096 + 64)
+    for _ in range(2):
+        hits = np.zeros(cap, np.uint64)
+        tr = np.zeros((cap, 172), np.uint8)
+        n = C.c_int64(0)
+        rc = ctx.lib.oip_image_frames_hits(ctx.h, imdt.data_ptr(), imdt.numel(), hits.ctypes.data, tr.ctypes.data, cap, C.byref(n))
+        if rc == capi.OIP_E_INVALID and n.value > cap:
+            cap = int(n.value)
+            continue
+        check(rc)
+        return hits[: n.value].copy(), tr[: n.value].copy()
+    raise RuntimeError("oip_image_frames_hits: capacity did not settle")
+
+
+def image_frames_chain(hits: np.ndarray, trailers: np.ndarray, n_bytes: int, tile_cols: int, tile_lines: int):
+    """host half of the frame index (oip_image_frames_chain; no GPU, no context): the reference's frame chain and gap rules
+    over a signature table with offsets relative to the whole IMDT stream of n_bytes -> (entries, stats[4])"""
+    lib = capi.load()
+    hits = np.ascontiguousarray(hits, np.uint64)
+    trailers = np.ascontiguousarray(trailers, np.uint8).reshape(-1, 172) if len(hits) else np.zeros((0, 172), np.uint8)
+    assert trailers.shape[0] == hits.shape[0]
+    g = FrameGeom(tile_cols, tile_lines)
+    st = (C.c_int64 * 4)()
+    frame_bytes = 192 * tile_lines + 40 * tile_lines * tile_cols * 2 + 172
+    cap = int(n_bytes) // frame_bytes + 64
+    for _ in range(2):
+        ents = (FrameEntry * cap)()
+        rc = lib.oip_image_frames_chain(hits.ctypes.data if len(hits) else None, trailers.ctypes.data if len(hits) else None, len(hits),
+                                        int(n_bytes), C.byref(g), ents, cap, st)
+        if rc == capi.OIP_E_INVALID and st[1] > cap:
+            cap = int(st[1])
+            continue
+        check(rc)
+        return ents, np.array(list(st), np.int64)
+    raise RuntimeError("oip_image_frames_chain: capacity did not settle")
+
+
 def unpack_frames(ctx: Context, imdt: torch.Tensor, tile_cols: int, tile_lines: int, ents, n_frames: int,
                   want_aux=True, want_pan=True, want_mss=True):
     g = FrameGeom(tile_cols, tile_lines)

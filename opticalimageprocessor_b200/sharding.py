@@ -298,3 +298,65 @@ def imtr_combine(infos):
     stats = [sum(q["n_frames"] for q in infos), n_valid] + [sum(q["bad"][k] for q in infos) for k in range(4)] + \
             [gaps, infos[last_restart_rank]["first_chid"] if last_restart_rank >= 0 else -1, restarts]
     return keep, stats
+
+
+# ------------------------------------------------------------------------------------------------
+# Frame index over the pieces of an IMDT stream (the output of the sharded IMTR re-framing stays where it was produced)
+# ------------------------------------------------------------------------------------------------
+FRAME_TRAILER = 172
+FRAME_HALO = FRAME_TRAILER + 2    # bytes of the following pieces a rank reads: a signature that starts in its last 3 bytes
+                                  # still ends, with its trailer, inside piece + halo
+
+
+def frames_piece_halo(heads: Sequence, rank: int):
+    """the first FRAME_HALO bytes of the stream that follows rank's piece, cut from the all-gathered heads of the pieces
+    (heads[r] = the first FRAME_HALO bytes of piece r, shorter for a short piece; a piece shorter than the halo lets the
+    next one contribute)"""
+    import numpy as np
+    out = []
+    need = FRAME_HALO
+    for q in range(rank + 1, len(heads)):
+        if need <= 0:
+            break
+        h = np.asarray(heads[q], np.uint8)[:need]
+        out.append(h)
+        need -= h.size
+    return np.concatenate(out) if out else np.zeros(0, np.uint8)
+
+
+def frames_local_hits(find_hits, piece_bytes: Sequence[int], rank: int):
+    """what a rank contributes to the exchange: the signatures that START inside its piece, as (global offsets, trailer bytes).
+    find_hits() -> (offsets, trailers) of the signatures in this rank's piece + halo, offsets relative to the piece."""
+    import numpy as np
+    off, tr = find_hits()
+    off = np.asarray(off, np.uint64)
+    tr = np.asarray(tr, np.uint8).reshape(-1, FRAME_TRAILER)
+    mine = off < np.uint64(piece_bytes[rank])
+    base = sum(int(b) for b in piece_bytes[:rank])
+    return (off[mine] + np.uint64(base)).tolist(), tr[mine].tobytes()
+
+
+def frames_chain_all(payloads, piece_bytes: Sequence[int], tile_cols: int, tile_lines: int):
+    """the host chain over the all-gathered contributions (rank order = stream order) -> (entries, stats[4])"""
+    import numpy as np
+    from . import ops
+    hits = np.array(sum((list(p[0]) for p in payloads), []), np.uint64)
+    trailers = np.frombuffer(b"".join(p[1] for p in payloads), np.uint8).reshape(-1, FRAME_TRAILER)
+    return ops.image_frames_chain(hits, trailers, sum(int(b) for b in piece_bytes), tile_cols, tile_lines)
+
+
+def frames_index_shards(find_hits, piece_bytes: Sequence[int], rank: int, tile_cols: int, tile_lines: int, group=None):
+    """oip_image_frames_index for an IMDT stream that lives in pieces (ref aux_separator.h:627-656 is one sequential memmem
+    loop): a rank keeps the signatures that start inside its piece (found in piece + halo), all ranks exchange (global offset,
+    trailer) -- a few hundred entries of 180 bytes, one all_gather_object -- and each runs the host chain over the whole
+    table, so every rank ends up with the same frame table, offsets relative to the whole stream.
+    Returns (entries, stats[4])."""
+    world = len(piece_bytes)
+    payload = frames_local_hits(find_hits, piece_bytes, rank)
+    if world > 1:
+        import torch.distributed as dist
+        allp = [None] * world
+        dist.all_gather_object(allp, payload, group=group)
+    else:
+        allp = [payload]
+    return frames_chain_all(allp, piece_bytes, tile_cols, tile_lines)

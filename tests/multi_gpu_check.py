@@ -154,6 +154,22 @@ def main():
     if not ok_f:
         print(f"rank {rank}: sharded stage 1 differs from the whole-file oracle (counters {tc.cpu().tolist()} vs {cnt_w.tolist()}, stats {st_all} vs {st_w.tolist()})", flush=True)
     ok = ok and ok_f
+    # ---- frame index over the IMDT pieces, which stay on the GPUs that produced them: every rank searches its piece + the
+    #      174-byte head of what follows, one all_gather_object of the (offset, trailer) pairs, the host chain on every rank
+    my_piece = piece if keep[rank] else piece[:0]
+    sizes = [int(q["imdt_bytes"]) if keep[r] else 0 for r, q in enumerate(infos)]
+    hd = [None] * world
+    dist.all_gather_object(hd, my_piece[:sharding.FRAME_HALO].cpu().numpy().tobytes())
+    halo_b = sharding.frames_piece_halo([np.frombuffer(h, np.uint8) for h in hd], rank)
+    ext = torch.cat([my_piece, torch.from_numpy(halo_b.copy()).cuda()]) if halo_b.size else my_piece
+    ents_g, fst_g = sharding.frames_index_shards(lambda: ops.image_frames_hits(ctx, ext), sizes, rank, 32, 8)
+    ents_1, fst_1 = ops.image_frames_index(ctx, torch.from_numpy(imdt_w).cuda(), 32, 8)
+    fst_w = oracle.image_frames(imdt_w, 32, 8)[4]
+    ok_i = sum(sizes) == imdt_w.size and fst_g.tolist() == fst_w.tolist() == fst_1.tolist() and int(fst_g[1]) > 0 and all(
+        ents_g[f].frame_off == ents_1[f].frame_off and list(ents_g[f].tile_off) == list(ents_1[f].tile_off) for f in range(int(fst_g[1])))
+    if not ok_i:
+        print(f"rank {rank}: frame index over pieces {fst_g.tolist()} vs whole stream {fst_w.tolist()} (sizes {sizes})", flush=True)
+    ok = ok and ok_i
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()

@@ -248,6 +248,35 @@ def test_image_frames_index_pointer_alignment_and_partial_signatures(ctx, oracle
     assert np.array_equal(mss.cpu().numpy(), mss_w)
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_frame_index_on_pieces_of_the_stream(ctx, oracle_mod, world):
+    """oip_image_frames_hits on every piece (+ the 174-byte head of what follows; the pieces are views into one allocation,
+    i.e. arbitrarily aligned pointers) and oip_image_frames_chain over the joined table == oip_image_frames_index on the
+    whole stream == the oracle (the IMDT pieces stay where the sharded re-framing produced them)"""
+    from opticalimageprocessor_b200 import ops, sharding
+    from test_sharding_cpu import _imdt_cases, _piece_cuts
+    tc, tl, frame_bytes, cases = _imdt_cases()
+    for i, buf in enumerate(cases):
+        st_w = oracle_mod.image_frames(buf, tc, tl)[4]
+        d = _dev(buf)
+        ents_1, st_1 = ops.image_frames_index(ctx, d, tc, tl)
+        assert st_1.tolist() == st_w.tolist(), i
+        h1, t1 = ops.image_frames_hits(ctx, d)
+        assert np.all(h1[1:] > h1[:-1]) and all(bytes(t1[k, :4]) == synth.IMG_SIG for k in range(len(h1)))
+        for variant in range(3):
+            cuts = _piece_cuts(buf.size, frame_bytes, world, variant)
+            sizes = [cuts[r + 1] - cuts[r] for r in range(world)]
+            payloads = []
+            for r in range(world):
+                ext = d[cuts[r]:min(buf.size, cuts[r + 1] + sharding.FRAME_HALO)]      # piece + halo, a view
+                payloads.append(sharding.frames_local_hits(lambda: ops.image_frames_hits(ctx, ext), sizes, r))
+            ents, st = sharding.frames_chain_all(payloads, sizes, tc, tl)
+            assert st.tolist() == st_w.tolist(), (i, variant)
+            assert sum(len(p[0]) for p in payloads) == len(h1)
+            for f in range(int(st[1])):
+                assert ents[f].frame_off == ents_1[f].frame_off and list(ents[f].tile_off) == list(ents_1[f].tile_off), (i, variant, f)
+
+
 def test_full_downlink_to_raw(ctx, oracle_mod):
     """AOS file -> payloads -> IMDT -> frames -> PAN/MSS/AUX, reference geometry tile width, vs ground truth"""
     from opticalimageprocessor_b200 import ops

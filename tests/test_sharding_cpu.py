@@ -435,3 +435,161 @@ def test_aos_carry_resolution_gloo():
     for rank, calls, carry_in, n_valid_all, cnt, offs in res:
         assert cnt == cnt_w.tolist() and offs == off_w.tolist() and sum(n_valid_all) == cnt_w[0]
         assert calls == ([0] if rank == 0 else [0, carry_in]) and (rank == 0 or carry_in > 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# frame index: host-only chain (oip_image_frames_chain) and the index over pieces of an IMDT stream
+# ------------------------------------------------------------------------------------------------
+def _np_find_hits(buf):
+    """numpy stand-in for the device search (oip_image_frames_hits): ascending signature offsets + the 172 bytes there"""
+    import numpy as np
+    from opticalimageprocessor_b200 import synth
+    sig = np.frombuffer(synth.IMG_SIG, np.uint8)
+    if buf.size < 4:
+        return np.zeros(0, np.uint64), np.zeros((0, 172), np.uint8)
+    m = (buf[:-3] == sig[0]) & (buf[1:-2] == sig[1]) & (buf[2:-1] == sig[2]) & (buf[3:] == sig[3])
+    off = np.flatnonzero(m).astype(np.uint64)
+    pad = np.concatenate([buf, np.zeros(172, np.uint8)])
+    tr = np.stack([pad[int(o):int(o) + 172] for o in off]) if off.size else np.zeros((0, 172), np.uint8)
+    return off, tr
+
+
+def _np_unpack(imdt, ents, n, tc, tl):
+    """aux / PAN / MSS rasters from a frame table (what oip_unpack_frames does), to compare a table with the oracle's output"""
+    import numpy as np
+    W = 8 * tc
+    aux = np.zeros((n, 192 * tl), np.uint8)
+    pan = np.zeros((n * 4 * tl, W), np.uint16)
+    mss = np.zeros((n * tl, W), np.uint16)
+    for f in range(n):
+        e = ents[f]
+        if e.frame_off < 0:
+            continue
+        aux[f] = imdt[e.frame_off:e.frame_off + 192 * tl]
+        for k in range(40):
+            o = e.tile_off[k]
+            t = imdt[o:o + tc * tl * 2].view(">u2").reshape(tl, tc)
+            r, c = divmod(k, 8)
+            if r < 4:
+                pan[f * 4 * tl + r * tl:f * 4 * tl + (r + 1) * tl, c * tc:(c + 1) * tc] = t
+            else:
+                mss[f * tl:(f + 1) * tl, c * tc:(c + 1) * tc] = t
+    return aux, pan, mss
+
+
+def _imdt_cases():
+    import numpy as np
+    from opticalimageprocessor_b200 import synth
+    tc, tl = 16, 4
+    frame_bytes = 192 * tl + 40 * tc * tl * 2 + 172
+    a, _ = synth.make_imdt(5, tc, tl, seed=10)
+    b, _ = synth.make_imdt(6, tc, tl, seed=11, skip_seqs={3}, junk_prefix=333)
+    c, _ = synth.make_imdt(4, tc, tl, seed=9)
+    c1 = c[100:].copy()                                   # first frame incomplete
+    c2 = c.copy()
+    pos = frame_bytes + 192 * tl + 64                     # a false signature inside frame 2
+    c2[pos:pos + 4] = np.frombuffer(synth.IMG_SIG, np.uint8)
+    c3 = c[:-50].copy()                                   # last trailer cut
+    return tc, tl, frame_bytes, [a, b, c1, c2, c3]
+
+
+def test_frames_chain_on_the_host_equals_the_oracle():
+    """oip_image_frames_chain needs no GPU: fed with the signature table of a numpy search it reproduces the oracle's frame
+    walk (stats, and the rasters its table unpacks to) -- junk prefix, sequence gap, incomplete first frame, false
+    signature, cut last trailer"""
+    import numpy as np
+    import oracle
+    from opticalimageprocessor_b200 import ops
+    tc, tl, _, cases = _imdt_cases()
+    for i, buf in enumerate(cases):
+        n_w, aux_w, pan_w, mss_w, st_w = oracle.image_frames(buf, tc, tl)
+        off, tr = _np_find_hits(buf)
+        ents, st = ops.image_frames_chain(off, tr, buf.size, tc, tl)
+        assert st.tolist() == st_w.tolist(), i
+        aux, pan, mss = _np_unpack(buf, ents, int(st[1]), tc, tl)
+        assert np.array_equal(aux, aux_w) and np.array_equal(pan, pan_w) and np.array_equal(mss, mss_w), i
+    # degenerate tables
+    ents, st = ops.image_frames_chain(np.zeros(0, np.uint64), np.zeros((0, 172), np.uint8), 10 ** 6, tc, tl)
+    assert st.tolist() == [0, 0, 0, 0]
+    ents, st = ops.image_frames_chain(np.zeros(0, np.uint64), np.zeros((0, 172), np.uint8), 100, tc, tl)
+    assert st.tolist() == [0, 0, 0, 0]
+
+
+def _piece_cuts(n, frame_bytes, world, variant):
+    if variant == 0:                                       # equal pieces
+        return [n * r // world for r in range(world + 1)]
+    if variant == 1:                                       # cuts inside signatures / trailers: 1, 2, 3 bytes and 100 bytes into a trailer
+        c = [0] + [min(n, (r * (n // frame_bytes) // world) * frame_bytes + frame_bytes - 172 + (1, 2, 3, 100)[r % 4]) for r in range(1, world)] + [n]
+        return sorted(c)
+    c = [0] + [min(n, 7 * r) for r in range(1, world)] + [n]   # tiny leading pieces (shorter than the halo)
+    return c
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_frames_index_on_pieces_equals_the_whole_stream(world):
+    """the IMDT stream cut into `world` pieces at arbitrary bytes (through signatures, through trailers, pieces shorter than
+    the halo): piece + halo search, contributions in rank order, host chain == the chain over the whole stream"""
+    import numpy as np
+    from opticalimageprocessor_b200 import ops
+    tc, tl, frame_bytes, cases = _imdt_cases()
+    for i, buf in enumerate(cases):
+        ents_w, st_w = ops.image_frames_chain(*_np_find_hits(buf), buf.size, tc, tl)
+        for variant in range(3):
+            cuts = _piece_cuts(buf.size, frame_bytes, world, variant)
+            pieces = [buf[cuts[r]:cuts[r + 1]] for r in range(world)]
+            sizes = [p.size for p in pieces]
+            heads = [p[:sharding.FRAME_HALO] for p in pieces]       # "all-gather" of the piece heads
+            payloads = []
+            for r in range(world):
+                ext = np.concatenate([pieces[r], sharding.frames_piece_halo(heads, r)])
+                assert ext.size <= pieces[r].size + sharding.FRAME_HALO
+                payloads.append(sharding.frames_local_hits(lambda: _np_find_hits(ext), sizes, r))
+            ents, st = sharding.frames_chain_all(payloads, sizes, tc, tl)
+            assert st.tolist() == st_w.tolist(), (i, variant)
+            for f in range(int(st[1])):
+                assert ents[f].frame_off == ents_w[f].frame_off and list(ents[f].tile_off) == list(ents_w[f].tile_off) and ents[f].seq == ents_w[f].seq
+
+
+def _frames_worker(rank, world, port, q):
+    import numpy as np
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tc, tl, frame_bytes, cases = _imdt_cases()
+        buf = cases[1]
+        cut = 2 * frame_bytes + 333 + frame_bytes - 172 + 2            # two bytes into the third trailer's signature
+        piece = buf[:cut] if rank == 0 else buf[cut:]
+        sizes = [cut, buf.size - cut]
+        heads = [None] * world
+        dist.all_gather_object(heads, piece[:sharding.FRAME_HALO].tobytes())
+        ext = np.concatenate([piece, sharding.frames_piece_halo([np.frombuffer(h, np.uint8) for h in heads], rank)])
+        ents, st = sharding.frames_index_shards(lambda: _np_find_hits(ext), sizes, rank, tc, tl)
+        q.put((rank, st.tolist(), [(ents[f].frame_off, ents[f].seq, ents[f].tile_off[39]) for f in range(int(st[1]))]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frames_index_shards_gloo():
+    """two processes, one all_gather_object of the piece heads and one of the (offset, trailer) contributions: both ranks
+    end up with the whole-stream frame table"""
+    import oracle
+    from opticalimageprocessor_b200 import ops
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_frames_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    tc, tl, _, cases = _imdt_cases()
+    buf = cases[1]
+    ents_w, st_w = ops.image_frames_chain(*_np_find_hits(buf), buf.size, tc, tl)
+    assert st_w.tolist() == oracle.image_frames(buf, tc, tl)[4].tolist()
+    want = [(ents_w[f].frame_off, ents_w[f].seq, ents_w[f].tile_off[39]) for f in range(int(st_w[1]))]
+    for rank, st, table in res:
+        assert st == st_w.tolist() and table == want
