@@ -956,7 +956,7 @@ __global__ void __launch_bounds__(IMTR_T, 6) imtr_validate_runs_kernel(const uin
     const unsigned long long pl0 = poff[min(i0 + lane, n_payload - 1)], pl1 = poff[min(i0 + 32 + lane, n_payload - 1)];
     uint32_t *runs = s_w + IMTR_FRONT / 4;
     // A warp copies runs wid, wid + 4, ...: lane l loads the ALIGNED source words l, l + 32, ... (221 words cover the run at any
-    // alignment: the last one reaches at most 4 bytes past the payload, still inside its 1024-byte AOS frame); the upper
+    // alignment; no word lies entirely outside the payload, so nothing past the caller's buffer is ever touched); the upper
     // neighbour of a word comes from lane + 1 by shuffle, so a run costs 7 loads and 7 registers per lane and the loads of
     // IMTR_DEPTH runs are in flight while the oldest is shifted and stored (the first version loaded both words of every
     // pair and waited for one run at a time: 9 dependent memory round trips per warp, long-scoreboard stall 4.3 per issue).
@@ -966,8 +966,10 @@ __global__ void __launch_bounds__(IMTR_T, 6) imtr_validate_runs_kernel(const uin
         const uint8_t *a = buf + (k < 32 ? a0 : a1);
         sh = (uint32_t)((uintptr_t)a & 3u);
         const uint32_t *w = reinterpret_cast<const uint32_t *>(a - sh);
+        // an aligned run needs no word past its end: every word that is loaded holds at least one byte of the payload
+        const int last = IMTR_RUN_WORDS - 1 + (sh ? 1 : 0);
 #pragma unroll
-        for (int u = 0; u < 7; ++u) dstw[u] = __ldg(w + min(lane + 32 * u, IMTR_RUN_WORDS));
+        for (int u = 0; u < 7; ++u) dstw[u] = __ldg(w + min(lane + 32 * u, last));
     };
 #pragma unroll
     for (int d = 0; d < IMTR_DEPTH - 1; ++d)
