@@ -593,3 +593,35 @@ def test_frames_index_shards_gloo():
     want = [(ents_w[f].frame_off, ents_w[f].seq, ents_w[f].tile_off[39]) for f in range(int(st_w[1]))]
     for rank, st, table in res:
         assert st == st_w.tolist() and table == want
+
+
+def test_frames_chain_error_behaviour():
+    """the host chain refuses what the index refuses: a JPEG-2000 compressed frame (z_ratio != 0, ref aux_separator.h:639 --
+    OIP_E_UNSUPPORTED), a table that does not fit the caller's capacity (OIP_E_INVALID with the needed count
+    in stats[1]), a bad geometry; a sub-image that would leave the buffer is OIP_E_RANGE"""
+    import ctypes as C
+    import numpy as np
+    from opticalimageprocessor_b200 import ops
+    from opticalimageprocessor_b200.capi import FrameEntry, FrameGeom, OipError
+    tc, tl, frame_bytes, cases = _imdt_cases()
+    buf = cases[0]
+    off, tr = _np_find_hits(buf)
+    z = tr.copy()
+    z[1, 4] |= 0x05
+    with pytest.raises(OipError, match="JPEG-2000") as ei:
+        ops.image_frames_chain(off, z, buf.size, tc, tl)
+    assert ei.value.code == capi.OIP_E_UNSUPPORTED
+    lib = capi.load()
+    st = (C.c_int64 * 4)()
+    ents = (FrameEntry * 2)()
+    g = FrameGeom(tc, tl)
+    rc = lib.oip_image_frames_chain(off.ctypes.data, tr.ctypes.data, len(off), buf.size, C.byref(g), ents, 2, st)
+    assert rc == capi.OIP_E_INVALID and st[1] == 5 and ents[1].frame_off == frame_bytes       # the first two entries are filled
+    rc = lib.oip_image_frames_chain(off.ctypes.data, tr.ctypes.data, len(off), buf.size, C.byref(g), None, 0, st)
+    assert rc == capi.OIP_OK and st[1] == 5                                                   # count-only call
+    bad = FrameGeom(0, tl)
+    assert lib.oip_image_frames_chain(off.ctypes.data, tr.ctypes.data, len(off), buf.size, C.byref(bad), None, 0, st) == capi.OIP_E_INVALID
+    # the same table read with four times the tile width: the last sub-image of the last frame would leave the buffer
+    with pytest.raises(OipError, match="leaves the buffer") as ei:
+        ops.image_frames_chain(off, tr, buf.size, 4 * tc, tl)
+    assert ei.value.code == capi.OIP_E_RANGE
