@@ -521,7 +521,12 @@ def _piece_cuts(n, frame_bytes, world, variant):
     if variant == 1:                                       # cuts inside signatures / trailers: 1, 2, 3 bytes and 100 bytes into a trailer
         c = [0] + [min(n, (r * (n // frame_bytes) // world) * frame_bytes + frame_bytes - 172 + (1, 2, 3, 100)[r % 4]) for r in range(1, world)] + [n]
         return sorted(c)
-    c = [0] + [min(n, 7 * r) for r in range(1, world)] + [n]   # tiny leading pieces (shorter than the halo)
+    if variant == 2:
+        return [0] + [min(n, 7 * r) for r in range(1, world)] + [n]   # tiny leading pieces (shorter than the halo)
+    # empty pieces (ranks whose IMDT piece was dropped by a sequence restart): first and, for world > 2, one in the middle
+    c = [0, 0] + [n * r // world for r in range(2, world)] + [n]
+    if world > 2:
+        c[2] = c[3]
     return c
 
 
@@ -534,8 +539,9 @@ def test_frames_index_on_pieces_equals_the_whole_stream(world):
     tc, tl, frame_bytes, cases = _imdt_cases()
     for i, buf in enumerate(cases):
         ents_w, st_w = ops.image_frames_chain(*_np_find_hits(buf), buf.size, tc, tl)
-        for variant in range(3):
+        for variant in range(4):
             cuts = _piece_cuts(buf.size, frame_bytes, world, variant)
+            assert len(cuts) == world + 1 and cuts == sorted(cuts)
             pieces = [buf[cuts[r]:cuts[r + 1]] for r in range(world)]
             sizes = [p.size for p in pieces]
             heads = [p[:sharding.FRAME_HALO] for p in pieces]       # "all-gather" of the piece heads
