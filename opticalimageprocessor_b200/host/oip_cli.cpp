@@ -609,6 +609,92 @@ static int cmd_stitch(const std::vector<std::string> &av)
 }
 
 // =============================================================================================
+// downlink  (EXTENSION -- no counterpart in the reference's grammar, ref main.cpp:92-191 has auxsep / prestitch / stitch as
+// three programs that talk through files, DOC/Usage.txt).  The same chain for the PAN product in one call: both CMOS
+// downlinks in, stitched raster out (oip_downlink_to_stitched: AOS scan + CRC, IMTR re-framing, frame index, then the fused
+// RRC + shift + stitch kernel reading the sub-images where they lie).  .IMDT / .PAN.RAW / .RRC.RAW / .PRESTT.RAW are never
+// written.  The shift of CMOS-2 must be given (--dx / --dy): the estimate of `prestitch` needs the PAN rasters this command
+// does not materialise.
+// =============================================================================================
+static int cmd_downlink(const std::vector<std::string> &av)
+{
+    Args a = parse(av, {{"--aos1", nullptr, false}, {"--aos2", nullptr, false}, {"--rrc1", nullptr, false}, {"--rrc2", nullptr, false},
+                        {"--no-rrc", nullptr, true}, {"--dx", nullptr, false}, {"--dy", nullptr, false}, {"--fold-cols", "-c", false},
+                        {"--out", "-o", false}}, 0);
+    require(a, "aos1"); require(a, "aos2"); require(a, "dx"); require(a, "dy"); require(a, "fold-cols");
+    const std::string f1 = a.get("aos1"), f2 = a.get("aos2");
+    existing_file(f1, "--aos1"); existing_file(f2, "--aos2");
+    if (a.has("rrc1")) existing_file(a.get("rrc1"), "--rrc1");
+    if (a.has("rrc2")) existing_file(a.get("rrc2"), "--rrc2");
+    const int fold = (int)a.geti("fold-cols", 0);
+    if (fold < 2) throw parse_error(CLI_VALIDATION, "--fold-cols: fold column value too small");              // as `stitch`, ref main.cpp:166-170
+    const bool do_rrc = !a.has("no-rrc");
+    if (do_rrc && (!a.has("rrc1") || !a.has("rrc2"))) throw std::runtime_error("open RRC Param file failed");   // as `prestitch`
+    const double dx = a.getd("dx", 0), dy = a.getd("dy", 0);
+    const size_t n1 = file_size(f1), n2 = file_size(f2);
+    if (n1 < 1024 || n2 < 1024) throw std::invalid_argument("AOS file too small");
+    OLOG("Launching fused downlink processing (AOS separation, RRC, pre-stitch, stitch) ...");
+    OLOG("    dx: %.5f, dy: %.5f (given)", dx, dy);
+    DevBuf d1(n1), d2(n2);
+    upload_file(f1, 0, n1, d1.p);
+    upload_file(f2, 0, n2, d2.p);
+    std::unique_ptr<DevBuf> kb[2];
+    if (do_rrc)
+        for (int i = 0; i < 2; ++i) {
+            std::vector<double> v = load_rrc(a.get(i ? "rrc2" : "rrc1"), PIXELS_PER_LINE);
+            kb[i].reset(new DevBuf(v.size() * 8));
+            oip_check(oip_copy_h2d(ctx(), kb[i]->p, v.data(), v.size() * 8));
+            oip_check(oip_ctx_sync(ctx()));                                      // v leaves scope
+        }
+    const oip_frame_geom g{1536, 256};                                            // ref aux_separator.h:92-93
+    const int64_t frame_bytes = 49152 + 40ll * 1536 * 256 * 2 + 172, lpf = 4 * 256;
+    const int out_w = oip_pan_out_width(2, PIXELS_PER_LINE, fold / 2);
+    // room for every complete frame the shorter downlink can carry plus zero-filled gap frames; grown once if a stream with
+    // long sequence gaps needs more (the call says how many lines it has)
+    int64_t cap_rows = ((int64_t)(std::min(n1, n2) / (size_t)frame_bytes) + 8) * lpf;
+    oip_downlink_stats st[2] = {};
+    int64_t rows = 0;
+    std::unique_ptr<DevBuf> d_out;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        d_out.reset();
+        d_out.reset(new DevBuf((size_t)cap_rows * out_w * 2));
+        oip_downlink_desc d{};
+        d.n_ccd = 2; d.geom = g; d.fold_half = fold / 2; d.section_rows = REMAP_SECTION_ROWS; d.row_guard = REMAP_ROW_GUARD;
+        d.ccd[0] = {(const uint8_t *)d1.p, n1, do_rrc ? (const double *)kb[0]->p : nullptr, 0, 0.0, 0.0};
+        d.ccd[1] = {(const uint8_t *)d2.p, n2, do_rrc ? (const double *)kb[1]->p : nullptr, 1, dx, dy};
+        d.d_out = (uint16_t *)d_out->p; d.out_pitch_px = out_w; d.out_rows_cap = cap_rows;
+        const int rc = oip_downlink_to_stitched(ctx(), &d, &rows, st);
+        if (rc == OIP_E_INVALID && attempt == 0) {
+            const int64_t need = std::min(st[0].frames[1], st[1].frames[1]) * lpf;   // filled in before the capacity check
+            if (need > cap_rows) { cap_rows = need; continue; }
+        }
+        oip_check(rc);
+        break;
+    }
+    oip_check(oip_pan_check_error(ctx()));
+    for (int i = 0; i < 2; ++i) {
+        OLOG("CMOS-%d: %lld valid, %lld invalid, %lld empty AOS frames; %lld image transfer frames cut, %lld accepted; %lld image frames.",
+             i + 1, (long long)st[i].aos[0], (long long)st[i].aos[1], (long long)st[i].aos[2], (long long)st[i].imtr[0],
+             (long long)st[i].imtr[1], (long long)st[i].frames[1]);
+    }
+    if (rows == 0) { OLOG("No image frame data, end of job."); return 0; }
+    if (rows <= REMAP_ROW_GUARD)
+        OLOG("%lld lines: fewer than the %d the reference's prestitch accepts (ref imageop.h:242-244); shifted as one section.", (long long)rows,
+             REMAP_ROW_GUARD + 1);
+    std::string out = a.get("out");
+    bool out_tiff = true;                                                                                       // as `stitch`, ref imageop.h:297-306
+    if (out.empty()) out = (fs::current_path() / ("stitched_" + std::to_string(out_w) + "n16b.TIFF")).string();
+    else out_tiff = lower(fs::path(out).extension().string()) == ".tiff";
+    const size_t out_bytes = (size_t)rows * out_w * 2;
+    size_t data0 = 0;
+    if (out_tiff) data0 = (size_t)oiptiff::write_u16(out, nullptr, out_w, rows, 1, 1);   // single-band GTiff header first, ref imageop.h:316-328
+    OLOG("Write stitched image to file '%s' ...", out.c_str());
+    download_to_file(out, d_out->p, out_bytes, data0);
+    OLOG("%zu bytes written.", out_bytes);
+    return 0;
+}
+
+// =============================================================================================
 // default action  (ref main.cpp:193-258, :288-317; preproc.h)
 // =============================================================================================
 static int cmd_default(const std::vector<std::string> &av)
@@ -735,7 +821,9 @@ static void usage()
          "Subcommands:\n"
          "  auxsep [-O,--offset N] file          Do aux & image data separation\n"
          "  prestitch --pan1 F --pan2 F [--rrc1 F --rrc2 F] [-r|--no-rrc] [-c] [-s N -l N --stitch-overlap N -e N] [--dx X --dy Y]\n"
-         "  stitch --image1 F --image2 F -c,--fold-cols N -o OUT.RAW");
+         "  stitch --image1 F --image2 F -c,--fold-cols N -o OUT.RAW\n"
+         "  downlink --aos1 F --aos2 F --rrc1 F --rrc2 F|--no-rrc --dx X --dy Y -c,--fold-cols N [-o OUT]   (extension: the three\n"
+         "           steps above for the PAN product in one fused pass, no intermediate files)");
 }
 
 int main(int argc, const char *argv[])
@@ -753,6 +841,7 @@ int main(int argc, const char *argv[])
             if (!av.empty() && av[0] == "auxsep") rc = cmd_auxsep({av.begin() + 1, av.end()});
             else if (!av.empty() && av[0] == "prestitch") rc = cmd_prestitch({av.begin() + 1, av.end()});
             else if (!av.empty() && av[0] == "stitch") rc = cmd_stitch({av.begin() + 1, av.end()});
+            else if (!av.empty() && av[0] == "downlink") rc = cmd_downlink({av.begin() + 1, av.end()});   // extension
             else rc = cmd_default(av);
             // every product is closed / stored by now: leave without the CUDA context teardown (0.5 - 0.9 s for nothing)
             if (g_log) fflush(g_log);

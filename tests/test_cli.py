@@ -198,3 +198,44 @@ def test_default_action_mss(cli, tmp_path, oracle_mod):
     file_order = oracle_mod.stitch_concat_c4([tif, tif[:, ::-1].copy()], 25, [3, 2, 1, 4])
     assert np.array_equal(g, file_order[:, :, [2, 1, 0, 3]])
     assert run(cli, ["stitch", "--image1=L.TIFF", "--image2=R.TIFF", "--fold-cols=50", "-o", "x.RAW"], d).returncode == 2   # ref :376-380
+
+
+def test_downlink_extension_grammar(cli, tmp_path):
+    """`downlink` (extension: auxsep -> prestitch -> stitch for the PAN product in one fused pass) follows the conventions of
+    the reference's sub-commands: required options, file validators, fold-cols check, RRC files unless --no-rrc"""
+    d = str(tmp_path)
+    open(os.path.join(d, "a.DAT"), "wb").write(b"\0" * 4096)
+    assert run(cli, ["downlink", "--aos1", "a.DAT"], d).returncode == 106                                   # CLI::RequiredError
+    assert run(cli, ["downlink", "--aos1", "a.DAT", "--aos2", "nope.DAT", "--dx", "1", "--dy", "1", "-c", "200"], d).returncode == 105
+    assert run(cli, ["downlink", "--aos1", "a.DAT", "--aos2", "a.DAT", "--dx", "1", "--dy", "1", "-c", "1"], d).returncode == 105
+    assert run(cli, ["downlink", "--aos1", "a.DAT", "--aos2", "a.DAT", "--dx", "x", "--dy", "1", "-c", "200", "--no-rrc"], d).returncode == 104  # CLI::ConversionError
+    r = run(cli, ["downlink", "--aos1", "a.DAT", "--aos2", "a.DAT", "--dx", "1", "--dy", "1", "-c", "200"], d)
+    assert r.returncode == 2 and "open RRC Param file failed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_downlink_extension_equals_the_three_step_chain(cli, tmp_path, oracle_mod):
+    """both CMOS downlinks in, stitched raster out: byte-identical to the oracle's chain aos_scan -> imtr_deframe ->
+    image_frames -> RRC + shift + stitch on the downlink the reference's own auxsep golden was made from (reference geometry,
+    a complete frame, two incomplete ones and zero-filled gap frames); the same file serves as CMOS-1 and CMOS-2
+    (measured once by hand: profiles/r02k_cli_downlink.log)"""
+    from test_reference_golden import _inputs
+    W = 12288
+    d = str(tmp_path)
+    buf = _inputs()["auxsep_input"]()
+    p = os.path.join(d, "KEL_MN200_20220316_120309_1.DAT")
+    buf.tofile(p)
+    kb1, kb2 = synth.rrc_coeffs(W, 1), synth.rrc_coeffs(W, 2)
+    synth.write_rrc_csv(os.path.join(d, "PAN-1.csv"), kb1)
+    synth.write_rrc_csv(os.path.join(d, "PAN-2.csv"), kb2)
+    off, _ = oracle_mod.aos_scan(buf)
+    imdt, _ = oracle_mod.imtr_deframe(buf, off)
+    n, _, pan, _, _ = oracle_mod.image_frames(imdt, 1536, 256)
+    dx, dy, fold = 1.37, -2.61, 200
+    want = oracle_mod.pan_pipeline([pan, pan], [kb1, kb2], [0, dx], [0, dy], fold // 2, 30000, 32767)
+    r = run(cli, ["downlink", "--aos1", p, "--aos2", p, "--rrc1", "PAN-1.csv", "--rrc2", "PAN-2.csv", "--dx", str(dx), "--dy", str(dy),
+                  "-c", str(fold), "-o", "out.RAW"], d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(os.path.join(d, "out.RAW"), np.uint16).reshape(-1, want.shape[1])
+    assert got.shape == want.shape == (n * 1024, 2 * W - fold) and np.array_equal(got, want)
+    assert not [f for f in os.listdir(d) if f.upper().endswith((".IMDT", ".AUX", ".PAN.RAW", ".MSS.RAW", ".RRC.RAW", ".PRESTT.RAW"))]  # no intermediate files
