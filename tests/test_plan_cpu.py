@@ -158,3 +158,56 @@ def test_mixed_source_formats_are_planned_once_per_pixel(lib):
     assert set(np.unique(cover[:, :out_w])) <= {1, 2}
     assert st[0] + st[1] == total * out_w
     assert st[1] > 0.8 * total * out_w, st
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_geometries_are_planned_exactly_once(lib, seed):
+    """300 random strips per seed -- 1..4 CCDs, widths off every alignment, folds, section / guard sizes, shifts with 0..3
+    decimals (integer shifts included), both 16-bit byte orders, warp-tile heights, whole strips and row shards: every
+    output pixel of the shard is planned exactly once (fast or generic), whatever the split between the two kernels"""
+    rng = np.random.default_rng(seed)
+    for it in range(300):
+        n = int(rng.integers(1, 5))
+        w = int(rng.choice([264, 520, 1000, 1024, 1536, 2048, 3000]))
+        f = int(rng.integers(0, min(120, w // 4)))
+        G = int(rng.integers(60, 600))
+        S = int(rng.integers(8, G + 1))
+        total = int(rng.integers(40, 1500))
+        dX = [0.0] + [float(np.round(rng.uniform(-6, 6), int(rng.integers(0, 4)))) for _ in range(n - 1)]
+        dY = [0.0] + [float(np.round(rng.uniform(-6, 6), int(rng.integers(0, 4)))) for _ in range(n - 1)]
+        fmt = int(rng.choice([capi.FMT_BE16, capi.FMT_LE16]))
+        rows = int(rng.choice([16, 61, 128, 256]))
+        row0, n_rows = 0, None
+        if rng.random() < 0.3 and total > 200:
+            row0 = int(rng.integers(0, total // 2))
+            n_rows = int(rng.integers(20, total - row0))
+        d, out_w = _desc(n, w, total, f, dX, dY, S, G, row0=row0, n_rows=n_rows, fmt=fmt)
+        cover, st = _coverage(lib, d, out_w, rows=rows)
+        what = (seed, it, n, w, total, f, S, G, dX, dY, row0, n_rows, rows)
+        assert set(np.unique(cover[:, :out_w])) <= {1, 2}, what
+        assert st[0] + st[1] == d.n_rows * out_w, what
+
+
+def test_mss_random_geometries_are_planned_exactly_once(lib):
+    """150 random band-alignment jobs -- band widths, section lengths, overlaps, line offsets, keep-leading on and off,
+    polynomials from flat to steep (x 40), warp-tile heights: every sample the reference writes is planned exactly once and
+    the rows it never writes stay untouched"""
+    rng = np.random.default_rng(7)
+    for it in range(150):
+        wb = int(rng.choice([96, 200, 512, 1000, 1536, 3072]))
+        lps = int(rng.integers(100, 900))
+        overlap = int(rng.integers(0, min(lps // 2, 120)))
+        off = int(rng.integers(0, 30))
+        keep = bool(rng.random() < 0.4)
+        lines = int(rng.integers(lps + overlap + off + 10, 2500))
+        scale = float(rng.choice([0.0, 0.3, 1.0, 3.0, 10.0, 40.0]))
+        rows = int(rng.choice([16, 61, 128]))
+        d = _mss_desc(wb, lines, lps, overlap, off, keep, int(rng.integers(1, 200)), scale)
+        rows_out = lines - off - (0 if keep else overlap)
+        cover = np.zeros((rows_out, wb, 4), np.uint8)
+        st = (C.c_int64 * 4)()
+        capi.check(lib.oip_mss_plan_coverage(C.byref(d), 1, rows, cover.ctypes.data_as(C.c_void_p), st))
+        what = (it, wb, lines, lps, overlap, off, keep, scale, rows, d.min_process_lines)
+        planned = cover[: (st[0] + st[1]) // (4 * wb)]
+        assert (st[0] + st[1]) % (4 * wb) == 0 and set(np.unique(planned)) <= {1, 2}, what
+        assert not cover[planned.shape[0]:].any(), what
