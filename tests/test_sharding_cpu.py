@@ -631,3 +631,54 @@ def test_frames_chain_error_behaviour():
     with pytest.raises(OipError, match="leaves the buffer") as ei:
         ops.image_frames_chain(off, tr, buf.size, 4 * tc, tl)
     assert ei.value.code == capi.OIP_E_RANGE
+
+
+def test_frames_chain_fuzz_against_the_oracle():
+    """1000 damaged IMDT streams (ranges dropped, false signatures, cut tails, junk inserted, sequence gaps, junk prefixes):
+    the host chain fed by a numpy signature search gives the oracle's frame walk -- same counters, same rasters, and an error
+    exactly where the oracle refuses the stream (a sub-image that would leave the buffer)"""
+    import numpy as np
+    import oracle
+    from opticalimageprocessor_b200 import ops, synth
+    from opticalimageprocessor_b200.capi import OipError
+    rng = np.random.default_rng(20221019)
+    sig = np.frombuffer(synth.IMG_SIG, np.uint8)
+    n_err = 0
+    for it in range(1000):
+        tc, tl = int(rng.choice([8, 16, 24])), int(rng.choice([1, 2, 4]))
+        nfr = int(rng.integers(1, 7))
+        skip = set(int(x) for x in rng.choice(np.arange(1, nfr + 2), size=int(rng.integers(0, 2)), replace=False)) if nfr > 1 else set()
+        imdt, _ = synth.make_imdt(nfr, tc, tl, seed=int(rng.integers(1 << 30)), skip_seqs=skip, junk_prefix=int(rng.choice([0, 0, 5, 333])))
+        buf = imdt.copy()
+        for _ in range(int(rng.integers(0, 4))):
+            kind = int(rng.integers(0, 4))
+            if kind == 0 and buf.size > 600:
+                a = int(rng.integers(0, buf.size - 500))
+                buf = np.concatenate([buf[:a], buf[a + int(rng.integers(1, 500)):]])
+            elif kind == 1:
+                p = int(rng.integers(0, buf.size - 4))
+                buf[p:p + 4] = sig
+            elif kind == 2:
+                buf = buf[:max(10, buf.size - int(rng.integers(1, 400)))]
+            else:
+                p = int(rng.integers(0, buf.size))
+                buf = np.concatenate([buf[:p], rng.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8), buf[p:]])
+        buf = np.ascontiguousarray(buf)
+        try:
+            n_w, aux_w, pan_w, mss_w, st_w = oracle.image_frames(buf, tc, tl)
+        except AssertionError:        # the oracle's fill pass refused what its counting pass had accepted
+            n_w = -1
+        off, tr = _np_find_hits(buf)
+        try:
+            ents, st = ops.image_frames_chain(off, tr, buf.size, tc, tl)
+            failed = False
+        except OipError:
+            failed = True
+        if n_w < 0 or failed:
+            assert n_w < 0 and failed, it
+            n_err += 1
+            continue
+        assert st.tolist() == st_w.tolist(), it
+        aux, pan, mss = _np_unpack(buf, ents, int(st[1]), tc, tl)
+        assert np.array_equal(aux, aux_w) and np.array_equal(pan, pan_w) and np.array_equal(mss, mss_w), it
+    assert 20 < n_err < 500
