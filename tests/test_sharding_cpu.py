@@ -682,3 +682,51 @@ def test_frames_chain_fuzz_against_the_oracle():
         aux, pan, mss = _np_unpack(buf, ents, int(st[1]), tc, tl)
         assert np.array_equal(aux, aux_w) and np.array_equal(pan, pan_w) and np.array_equal(mss, mss_w), it
     assert 20 < n_err < 500
+
+
+def test_stage1_shards_fuzz_against_the_whole_file():
+    """300 random downlinks (damaged IMTR frames, sequence restarts, empty / bad-CRC / bad-inject AOS frames, byte slips,
+    prefixes) cut into 2..6 shards at random bytes (shards shorter than a frame included): carry resolution, the payload-count
+    prefix of the IMTR cadence and the sequence rules across ranks reproduce the sequential whole-file result -- payload
+    list, the 3 counters, IMDT bytes, the 9 IMTR stats"""
+    import numpy as np
+    import oracle
+    from opticalimageprocessor_b200 import synth
+    rng = np.random.default_rng(4711)
+
+    def aos_shard(sub, own, carry):
+        o, c, nxt = oracle.aos_scan_range(sub, carry, own)
+        return o, c, max(0, nxt - own)
+    done = 0
+    for it in range(300):
+        imdt, _ = synth.make_imdt(int(rng.integers(1, 4)), 16, 4, seed=int(rng.integers(1 << 30)))
+        imtr = synth.imtr_frames(imdt, chid=0x22)
+        nfr = imtr.shape[0]
+        for _ in range(int(rng.integers(0, 3))):
+            imtr[int(rng.integers(0, nfr)), int(rng.integers(0, 882))] ^= 0x20
+        if rng.random() < 0.3 and nfr > 5:
+            imtr[int(rng.integers(1, nfr - 1)), 4:8] = 0
+            synth.refresh_imtr_crc(imtr)
+        aos = synth.aos_frames(imtr.reshape(-1))
+        na = aos.shape[0]
+        buf = synth.build_aos_file(aos, empty_every=int(rng.integers(3, 12)), bad_crc_at=set(int(x) for x in rng.integers(0, na, 2)),
+                                   bad_inject_at=set(int(x) for x in rng.integers(0, na, 1)), prefix=bytes(int(rng.integers(0, 20)))).copy()
+        for _ in range(int(rng.integers(0, 3))):
+            p = int(rng.integers(0, buf.size))
+            if rng.random() < 0.5:
+                buf = np.concatenate([buf[:p], rng.integers(0, 256, int(rng.integers(1, 9)), dtype=np.uint8), buf[p:]])
+            else:
+                buf = np.concatenate([buf[:p], buf[p + int(rng.integers(1, 9)):]])
+        buf = np.ascontiguousarray(buf)
+        off_w, cnt_w = oracle.aos_scan(buf)
+        imdt_w, st_w = oracle.imtr_deframe(buf, off_w)
+        world = int(rng.integers(2, 7))
+        cuts = sorted(int(x) for x in rng.integers(1, buf.size - 1, world - 1))
+        if len(set(cuts)) < world - 1:
+            continue
+        ranges = list(zip([0] + cuts, cuts + [buf.size]))
+        off, cnt, imdt_s, stats, _ = _run_stage1_sharded(buf, world, ranges, aos_shard, _oracle_imtr_shard)
+        assert np.array_equal(off, off_w) and cnt.tolist() == cnt_w.tolist(), (it, ranges)
+        assert stats == st_w.tolist() and np.array_equal(imdt_s, imdt_w), (it, ranges, stats, st_w.tolist())
+        done += 1
+    assert done > 250
