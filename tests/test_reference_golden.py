@@ -128,6 +128,30 @@ def test_reference_rrc_direct():
     assert np.array_equal(oracle.rrc(img, kb), want)
 
 
+def test_reference_rrc_direct_extreme_coefficients():
+    """the same comparison over coefficient extremes: zero / negative / denormal / huge gains, biases at and beyond the
+    uint16 and int32 ranges, NaN and infinities -- the oracle restates what the reference's compiled (double)->(uint16)
+    conversion does in every one of these cases (ref imageop.h:134-136)"""
+    so = os.path.join(os.path.dirname(oracle.__file__), "_ref", "libref_oip.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libref_oip.so not built (no /root/reference here)")
+    import ctypes as C
+    L = C.CDLL(so)
+    rng = np.random.default_rng(1)
+    W = 12288
+    for it in range(10):
+        img = rng.integers(0, 65536, (8, W), dtype=np.uint16)
+        k, b = rng.normal(1.0, 0.2, W), rng.normal(0, 50, W)
+        idx = rng.choice(W, 600, replace=False)
+        k[idx] = rng.choice([0.0, -1.0, -0.0, 1e-300, 1e5, -1e5, 32768.5, 65536.0, 1e10, -1e10, np.nan, np.inf, -np.inf, 4.9e-324], 600)
+        b[idx[::2]] = rng.choice([0.0, -0.5, 0.5, 65535.0, 65536.0, -65536.0, 2147483647.0, 2147483648.0, -2147483649.0, 1e19, -1e19,
+                                  np.nan, np.inf, -np.inf], 300)
+        kb = np.ascontiguousarray(np.stack([k, b], 1))
+        want = img.copy()
+        L.ref_inplace_rrc(want.ctypes.data_as(C.c_void_p), W, 8, kb.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(oracle.rrc(img, kb), want), it
+
+
 # ------------------------------------------------------------------------------------------------
 # band alignment and the RRC CSV loader against the reference's own preproc.h / imageop.h (round 2):
 # tests/golden/ref_bandalign.npz and ref_rrc_csv.npz were written by PreProcessor::LoadMSS + DoRRC4MSS +
