@@ -237,3 +237,60 @@ def test_rrc_csv_loaders_match_reference(tmp_path):
             assert np.array_equal(kb_o, g[tag + "_kb"]) and np.array_equal(kb_p, g[tag + "_kb"]), tag
     assert not bool(g["missing_file_ok"])
     assert L.oip_load_rrc_csv(str(tmp_path / "does_not_exist.csv").encode(), 2, np.zeros(4).ctypes.data) == capi.OIP_E_IO
+
+
+def test_rrc_csv_loader_fuzz_against_the_reference_parser(tmp_path):
+    """1500 random CSV texts -- CRLF / blank lines, odd separators, leading and trailing blanks, numbers in every spelling
+    strtod knows and a few it does not, wrong headers, too few rows -- go through IMO::LoadRRCParamFile (compiled unmodified,
+    oracle/_ref) and through oip_load_rrc_csv: both accept the same texts and return the same doubles.  Texts with MORE rows
+    than columns are left out: the reference writes them past the end of its array (glibc aborts with heap corruption);
+    oip_load_rrc_csv refuses them with the reference's own message and touches nothing beyond the caller's buffer."""
+    so = os.path.join(os.path.dirname(oracle.__file__), "_ref", "libref_oip.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libref_oip.so not built (no /root/reference here)")
+    import ctypes as C
+    from opticalimageprocessor_b200 import capi
+    REF = C.CDLL(so)
+    REF.ref_load_rrc_csv.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double)]
+    lib = capi.load()
+    rng = np.random.default_rng(0)
+    nums = ["1", "0", "-1", "1.5", "0.987654321012", "1e0", "1E1", "-3e-3", ".5", "5.", "+2", "1e400", "-1e-400", "nan", "inf", "0x10", "1,5",
+            "", " ", "abc", "1.2.3", "1e", "--1"]
+    seps = [" , ", ",", " ,", ", ", "\t,\t", " ", ";", " , , ", ",,"]
+    eols = ["\n", "\r\n", "\n\n", "\r"]
+    p = str(tmp_path / "t.csv")
+    accepted = 0
+    for it in range(1500):
+        n = int(rng.integers(1, 6))
+        eol = eols[int(rng.choice(len(eols), p=[0.6, 0.25, 0.1, 0.05]))]
+        head = [str(rng.choice(["1", "2", "x", ""], p=[0.85, 0.05, 0.05, 0.05])),
+                str(rng.choice([str(n), str(n + 1), "0", "n", ""], p=[0.8, 0.05, 0.05, 0.05, 0.05])),
+                str(rng.choice(["0", "1", "", "zero"], p=[0.85, 0.05, 0.05, 0.05]))]
+        if rng.random() < 0.05:
+            head = head[:int(rng.integers(0, 3))]
+        rows = []
+        for r in range(int(rng.choice([n, n - 1, 0], p=[0.9, 0.07, 0.03]))):
+            good = rng.random() < 0.93
+            a = str(rng.choice(nums[:11])) if good else str(rng.choice(nums))
+            b = str(rng.choice(nums[:11])) if good else str(rng.choice(nums))
+            sep = seps[0] if good and rng.random() < 0.7 else str(rng.choice(seps))
+            tail = "" if rng.random() < 0.9 else str(rng.choice([" extra", " ,3", "   ", "\t"]))
+            lead = "" if rng.random() < 0.9 else str(rng.choice(["  ", "\t"]))
+            rows.append(lead + a + sep + b + tail)
+        text = eol.join(head + rows) + (eol if rng.random() < 0.8 else "")
+        with open(p, "wb") as f:
+            f.write(text.encode())
+        kr, kg = (C.c_double * (2 * n))(), (C.c_double * (2 * n))()
+        rc_r = REF.ref_load_rrc_csv(p.encode(), n, kr)
+        rc_g = lib.oip_load_rrc_csv(p.encode(), n, kg)
+        assert (rc_r == 0) == (rc_g == 0), (it, rc_r, rc_g, text)
+        if rc_r == 0:
+            accepted += 1
+            assert np.array_equal(np.array(list(kr)), np.array(list(kg)), equal_nan=True), (it, text, list(kr), list(kg))
+    assert 300 < accepted < 1300, accepted
+    # more rows than columns: refused, nothing written past the two expected pairs
+    with open(p, "w") as f:
+        f.write("1\n2\n0\n1 , 0\n2 , 1\n3 , 2\n4 , 3\n")
+    kg = (C.c_double * 6)(*([-7.0] * 6))
+    assert lib.oip_load_rrc_csv(p.encode(), 2, kg) == capi.OIP_E_INVALID and list(kg)[4:] == [-7.0, -7.0]
+    assert b"2 lines of param expected, 4 lines parsed" in lib.oip_last_error()
