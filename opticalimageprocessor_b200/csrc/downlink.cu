@@ -7,6 +7,7 @@
 // (OIP_FMT_BE16_TILES): no PAN raster, no corrected raster, no shifted raster is ever written.  What still passes
 // through HBM between the kernels is the IMDT stream itself (the CRC-checked 866-byte bodies) and the small tables.
 #include <algorithm>
+#include <exception>
 #include <string>
 #include <thread>
 #include <vector>
@@ -132,8 +133,13 @@ extern "C" int oip_downlink_to_stitched(oip_ctx *ctx, const oip_downlink_desc *d
             if (rcs[i]) msgs[i] = oip_last_error();           // the error text is per thread
         };
         std::vector<std::thread> th;
-        for (int i = 1; i < d->n_ccd; ++i) th.emplace_back(work, i);
+        int started = 1;                                      // CCD 0 runs on the calling thread
+        try {
+            for (int i = 1; i < d->n_ccd; ++i) { th.emplace_back(work, i); started = i + 1; }
+        } catch (const std::exception &) {                    // no more threads to be had: the rest runs here, one after the other
+        }
         work(0);
+        for (int i = started; i < d->n_ccd; ++i) work(i);
         for (std::thread &t : th) t.join();
         for (int i = 0; i < d->n_ccd; ++i) {
             ctx->launches += st->sub[i]->launches;
