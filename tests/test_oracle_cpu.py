@@ -353,6 +353,42 @@ def test_capi_library_exports_every_declared_symbol():
     assert L.oip_abi_version() == 2
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/oip_b200.h compiles as pedantic C99 (no C++ or torch types in a signature) and
+    a C program links against the in-tree library -- the host-only entry points run without a GPU, oip_ctx_create says why
+    it cannot"""
+    import subprocess
+    import torch
+    from opticalimageprocessor_b200 import build
+    build.build()
+    root = os.path.join(os.path.dirname(__file__), "..")
+    src = tmp_path / "abi.c"
+    src.write_text("""
+#include <stdio.h>
+#include <string.h>
+#include "oip_b200.h"
+int main(void) {
+    oip_ctx *ctx = NULL;
+    oip_frame_geom g = {16, 4};
+    int64_t st[4] = {-1, -1, -1, -1};
+    if (oip_abi_version() != 2) return 10;
+    if (oip_pan_out_width(3, 8192, 100) != 3 * 8192 - 4 * 100) return 11;
+    if (oip_image_frames_chain(NULL, NULL, 0, 1000000, &g, NULL, 0, st) != OIP_OK || st[1] != 0) return 12;
+    if (oip_ctx_create(0, NULL, 1, &ctx) == OIP_OK) { oip_ctx_destroy(ctx); puts("gpu"); return 0; }
+    if (!strstr(oip_last_error(), "no CPU fallback")) return 13;
+    puts("no gpu");
+    return 0;
+}
+""")
+    exe = str(tmp_path / "abi")
+    lib_dir = os.path.dirname(build.LIB)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", exe,
+                           "-L" + lib_dir, "-loip_b200", "-Wl,-rpath," + lib_dir])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.strip() == ("gpu" if torch.cuda.is_available() else "no gpu")
+
+
 def test_capi_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
