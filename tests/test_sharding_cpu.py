@@ -730,3 +730,61 @@ def test_stage1_shards_fuzz_against_the_whole_file():
         assert stats == st_w.tolist() and np.array_equal(imdt_s, imdt_w), (it, ranges, stats, st_w.tolist())
         done += 1
     assert done > 250
+
+
+def test_row_ranges_are_sufficient_and_tight_fuzz():
+    """oip_pan_row_ranges against the oracle on 600 random strips / row shards (2-3 CCDs, random folds, section and guard
+    sizes incl. single-section strips, shifts of both signs): the oracle computes the shard's output once from the whole
+    strip and once from a strip in which every row OUTSIDE the declared ranges is random garbage -- identical, so the ranges
+    hold every row the arithmetic reads (halo rows, the stale rows of a partial last section); with one row taken off
+    either end of every range the two differ, so the ranges are tight"""
+    import ctypes as C
+    import numpy as np
+    import oracle
+    from opticalimageprocessor_b200 import synth
+    L = capi.load()
+    rng = np.random.default_rng(99)
+    w = 64
+    teeth = 0
+    for it in range(600):
+        n = int(rng.integers(2, 4))
+        f = int(rng.integers(0, 9))
+        G = int(rng.integers(40, 300))
+        S = int(rng.integers(8, G + 1))
+        total = int(rng.integers(G + 1, 1200)) if rng.random() < 0.85 else int(rng.integers(20, G + 1))
+        dX = [0.0] + [float(np.round(rng.uniform(-5, 5), 2)) for _ in range(n - 1)]
+        dY = [0.0] + [float(np.round(rng.uniform(-5, 5), int(rng.integers(0, 3)))) for _ in range(n - 1)]
+        row0 = int(rng.integers(0, total))
+        n_rows = int(rng.integers(1, total - row0 + 1))
+        d = capi.PanDesc()
+        d.n_ccd, d.w, d.total_rows, d.row0, d.n_rows = n, w, total, row0, n_rows
+        d.fold_half, d.section_rows, d.row_guard = f, S, G
+        for i in range(n):
+            d.ccd[i].fmt, d.ccd[i].n_seg, d.ccd[i].shifted = capi.FMT_LE16, 1, int(i > 0)
+            d.ccd[i].dX, d.ccd[i].dY = dX[i], dY[i]
+        data = [rng.integers(0, 65536, (total, w), dtype=np.uint16) for _ in range(n)]
+        kbs = [synth.rrc_coeffs(w, 3 + i) for i in range(n)]
+        ranges = []
+        for i in range(n):
+            rg = (C.c_int64 * 16)()
+            cnt = C.c_int()
+            capi.check(L.oip_pan_row_ranges(C.byref(d), i, rg, 8, C.byref(cnt)))
+            ranges.append([(rg[2 * k], rg[2 * k + 1]) for k in range(cnt.value)])
+
+        def poisoned(rgs):
+            def gen(i, a, b):
+                out = rng.integers(0, 65536, (b - a, w), dtype=np.uint16)
+                for ra, rb in rgs[i]:
+                    lo, hi = max(a, ra), min(b, rb)
+                    if hi > lo:
+                        out[lo - a:hi - a] = data[i][lo:hi]
+                return out
+            return gen
+        rows = np.arange(row0, row0 + n_rows)
+        what = dict(it=it, n=n, f=f, S=S, G=G, total=total, dX=dX, dY=dY, row0=row0, n_rows=n_rows, ranges=ranges)
+        want = oracle.pan_rows(lambda i, a, b: data[i][a:b], n, w, kbs, dX, dY, f, total, rows, S, G)
+        assert np.array_equal(oracle.pan_rows(poisoned(ranges), n, w, kbs, dX, dY, f, total, rows, S, G), want), what
+        if it % 10 == 0:      # the test has teeth: a row short at either end changes the output
+            for cut in ([[(a, b - 1) for a, b in r] for r in ranges], [[(a + 1, b) for a, b in r] for r in ranges]):
+                teeth += not np.array_equal(oracle.pan_rows(poisoned(cut), n, w, kbs, dX, dY, f, total, rows, S, G), want)
+    assert teeth >= 110
