@@ -294,3 +294,46 @@ def test_rrc_csv_loader_fuzz_against_the_reference_parser(tmp_path):
     kg = (C.c_double * 6)(*([-7.0] * 6))
     assert lib.oip_load_rrc_csv(p.encode(), 2, kg) == capi.OIP_E_INVALID and list(kg)[4:] == [-7.0, -7.0]
     assert b"2 lines of param expected, 4 lines parsed" in lib.oip_last_error()
+
+
+def test_reference_imdt_after_a_mid_stream_restart(tmp_path):
+    """A frame with sequence number 0 makes the reference re-create the IMDT file (ref aux_separator.h:513-528:
+    `imdt.attach(fopen(name, "wb"))`).  The new stream truncates the file, but the OLD stream is only flushed afterwards, at its
+    old offset: when more data preceded the restart than follows it, the reference's file is [data after the restart] + a
+    hole of zeros + the last buffered bytes of the data before it.  The oracle (and liboip) write the data after the last
+    restart and nothing else -- the documented deviation; the two agree byte for byte whenever the data
+    after the restart is the longer part, and the reference's file always STARTS with the oracle's."""
+    so = os.path.join(os.path.dirname(oracle.__file__), "_ref", "libref_oip.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libref_oip.so not built (no /root/reference here)")
+    import ctypes as C
+    REF = C.CDLL(so)
+    REF.ref_auxsep.argtypes = [C.c_char_p, C.c_char_p]
+    rng = np.random.default_rng(3)
+    n_imtr = 3000
+    payload = rng.integers(0, 256, n_imtr * 866, dtype=np.uint8)
+    payload[payload == 0xEB] = 0                      # no image-frame signatures: stage 1g finds nothing to write
+    for k_restart in (700, 2200):
+        imtr = synth.imtr_frames(payload, chid=0x22)
+        imtr[k_restart, 4:8] = 0
+        synth.refresh_imtr_crc(imtr[k_restart:k_restart + 1])
+        buf = synth.aos_frames(imtr.reshape(-1)).reshape(-1)
+        off, _ = oracle.aos_scan(buf)
+        imdt_o, st = oracle.imtr_deframe(buf, off)
+        work = tmp_path / f"out{k_restart}"
+        work.mkdir()
+        src = tmp_path / "KEL_MN200_20220316_120309_1.DAT"
+        buf.tofile(str(src))
+        assert REF.ref_auxsep(str(src).encode(), str(work).encode()) == 0
+        name = [n for n in os.listdir(work) if n.endswith(".IMDT")][0]
+        ref = np.fromfile(str(work / name), np.uint8)
+        pre, post = (k_restart + 1) * 866, (n_imtr - k_restart - 1) * 866
+        assert st[8] == 2 and imdt_o.size == post and np.array_equal(imdt_o, payload[pre:])
+        assert np.array_equal(ref[:post], imdt_o)                       # the reference's file starts with the oracle's stream
+        if post >= pre:
+            assert ref.size == post                                     # ... and is nothing else when the new data is the longer part
+        else:
+            tail = ref[post:]
+            nz = np.flatnonzero(tail)
+            assert ref.size == pre and nz.size and nz[0] > tail.size - 8192
+            assert np.array_equal(tail[nz[0]:], payload[post + nz[0]:pre])   # the old stream's last buffer, flushed after the truncation
