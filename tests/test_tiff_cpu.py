@@ -99,3 +99,34 @@ def test_refuses_other_compressions(exe, tmp_path):
     assert cv2.imwrite(z, img, [cv2.IMWRITE_TIFF_COMPRESSION, 8])  # Adobe deflate
     r = subprocess.run([exe, "read", z, back], capture_output=True, text=True)
     assert r.returncode == 1 and "compressed TIFF" in r.stderr
+
+
+def test_lzw_round_trips_with_libtiff_fuzz(exe, tmp_path):
+    """200 random rasters (1..400 x 1..900, 1 or 4 samples; noise, constants, random walks, 16-pixel runs, four-level data --
+    short strips, strings that fill and reset the LZW table): what we write libtiff reads, what libtiff writes we read"""
+    rng = np.random.default_rng(11)
+    raw, tif, back = str(tmp_path / "in.raw"), str(tmp_path / "o.TIFF"), str(tmp_path / "b.raw")
+    for it in range(200):
+        h, w, spp = int(rng.integers(1, 400)), int(rng.integers(1, 900)), int(rng.choice([1, 4]))
+        kind = int(rng.integers(0, 5))
+        if kind == 0:
+            px = rng.integers(0, 65536, (h, w, spp), dtype=np.uint16)
+        elif kind == 1:
+            px = np.full((h, w, spp), int(rng.integers(0, 65536)), np.uint16)
+        elif kind == 2:
+            px = (np.cumsum(rng.integers(-2, 3, (h, w, spp)), axis=1) + 3000).astype(np.uint16)
+        elif kind == 3:
+            px = np.repeat(rng.integers(0, 65536, (h, (w + 15) // 16, spp), dtype=np.uint16), 16, axis=1)[:, :w]
+        else:
+            px = (rng.integers(0, 4, (h, w, spp)) * 257).astype(np.uint16)
+        px = np.ascontiguousarray(px)
+        px.tofile(raw)
+        subprocess.check_call([exe, "write", tif, str(w), str(h), str(spp), raw, "lzw"])
+        want = px[:, :, 0] if spp == 1 else px[:, :, [2, 1, 0, 3]]
+        img = cv2.imread(tif, cv2.IMREAD_UNCHANGED)
+        assert img is not None and img.shape == want.shape and np.array_equal(img, want), (it, h, w, spp, kind)
+        subprocess.check_output([exe, "read", tif, back])
+        assert np.array_equal(np.fromfile(back, np.uint16).reshape(h, w, spp), px), (it, h, w, spp, kind)
+        assert cv2.imwrite(tif, want)                     # libtiff's own LZW + predictor file of the same pixels
+        subprocess.check_output([exe, "read", tif, back])
+        assert np.array_equal(np.fromfile(back, np.uint16).reshape(h, w, spp), px), (it, h, w, spp, kind)
